@@ -1,0 +1,85 @@
+// cb_mul.cuh -- exact L x L -> 2L limb product held entirely in registers (sm_100a).
+//
+// Replaces the mpn_mul_n calls that Arb's arf_mul / arf_complex_mul make underneath
+// acb_mul at reference src/fuchs_solver.c:118 and src/frobenius_solver.c:59,107.
+//
+// Schoolbook rows.  Row i multiplies all limbs of `a` by b[i]; products that land on
+// an even column pair go to the `ev` accumulator, those on an odd column pair go to
+// `od` (od[k] is column k+1).  Each (row, parity) is one carry chain of L/2
+// mad.lo.cc/madc.hi.cc pairs; ptxas fuses every pair into a single
+// IMAD.WIDE.U32.X Rd, Pout, Ra, Rb, Rc, Pin, so a product is L*L IMAD.WIDE plus
+// 2L-1 IADD3.X for the final ev + (od << 32).  Accumulators start as compile-time
+// zeros, which ptxas turns into RZ operands (no MOVs).
+#pragma once
+#include <stdint.h>
+
+namespace cb {
+
+#if defined(__CUDA_ARCH__)
+
+template <int L, int K0, int J0, bool CARRY, int N>
+__device__ __forceinline__ void mul_chain(uint32_t (&acc)[N], const uint32_t (&a)[L], uint32_t b) {
+    asm volatile("mad.lo.cc.u32 %0, %2, %3, %4; madc.hi.cc.u32 %1, %2, %3, %5;"
+                 : "=r"(acc[K0]), "=r"(acc[K0 + 1])
+                 : "r"(a[J0]), "r"(b), "r"(acc[K0]), "r"(acc[K0 + 1]));
+#pragma unroll
+    for (int j = 2; j < L; j += 2)
+        asm volatile("madc.lo.cc.u32 %0, %2, %3, %4; madc.hi.cc.u32 %1, %2, %3, %5;"
+                     : "=r"(acc[K0 + j]), "=r"(acc[K0 + j + 1])
+                     : "r"(a[J0 + j]), "r"(b), "r"(acc[K0 + j]), "r"(acc[K0 + j + 1]));
+    if (CARRY) asm volatile("addc.u32 %0, %1, 0;" : "=r"(acc[K0 + L]) : "r"(acc[K0 + L]));
+}
+
+template <int L, int I>
+struct MulRows {
+    template <int N>
+    static __device__ __forceinline__ void run(uint32_t (&ev)[N], uint32_t (&od)[N],
+                                               const uint32_t (&a)[L], const uint32_t (&b)[L]) {
+        if constexpr (I < L) {
+            if constexpr ((I & 1) == 0) {
+                mul_chain<L, I, 0, true>(ev, a, b[I]);
+                mul_chain<L, I, 1, true>(od, a, b[I]);
+            } else {
+                mul_chain<L, I - 1, 0, true>(od, a, b[I]);
+                mul_chain<L, I + 1, 1, (I + 1 + L < 2 * L)>(ev, a, b[I]);
+            }
+            MulRows<L, I + 1>::run(ev, od, a, b);
+        }
+    }
+};
+
+// r[0..2L) = a[0..L) * b[0..L), little-endian limbs, exact.
+template <int L>
+__device__ __forceinline__ void mul_full(uint32_t (&r)[2 * L], const uint32_t (&a)[L],
+                                         const uint32_t (&b)[L]) {
+    static_assert(L % 2 == 0, "even limb count");
+    uint32_t ev[2 * L], od[2 * L];
+#pragma unroll
+    for (int k = 0; k < 2 * L; k++) { ev[k] = 0; od[k] = 0; }
+    MulRows<L, 0>::run(ev, od, a, b);
+    r[0] = ev[0];
+    asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r[1]) : "r"(ev[1]), "r"(od[0]));
+#pragma unroll
+    for (int k = 2; k < 2 * L; k++)
+        asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r[k]) : "r"(ev[k]), "r"(od[k - 1]));
+}
+
+#else  // host build of the same interface (tests/host_sim only; never shipped in the library)
+
+template <int L>
+inline void mul_full(uint32_t (&r)[2 * L], const uint32_t (&a)[L], const uint32_t (&b)[L]) {
+    for (int k = 0; k < 2 * L; k++) r[k] = 0;
+    for (int i = 0; i < L; i++) {
+        uint64_t c = 0;
+        for (int j = 0; j < L; j++) {
+            uint64_t t = (uint64_t)a[j] * b[i] + r[i + j] + c;
+            r[i + j] = (uint32_t)t;
+            c = t >> 32;
+        }
+        r[i + L] = (uint32_t)c;
+    }
+}
+
+#endif
+
+}  // namespace cb
