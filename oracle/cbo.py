@@ -1,0 +1,135 @@
+"""ctypes binding of the CPU oracle (oracle/_build/libcbo*.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product package (cascade_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from cascade_b200.format import Balls
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS: dict = {}
+
+OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_INV = 0, 1, 2, 3, 4
+OP_MUL_SI, OP_ADD_SI = 16, 17
+
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+
+
+def build() -> None:
+    subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+
+
+def lib(plain: bool = False) -> C.CDLL:
+    name = "libcbo_plain.so" if plain else "libcbo.so"
+    if name in _LIBS:
+        return _LIBS[name]
+    path = os.path.join(_HERE, "_build", name)
+    if not os.path.exists(path):
+        build()
+    L = C.CDLL(path)
+    L.cbo_backend.restype = C.c_char_p
+    L.cbo_ew_binary.argtypes = [C.c_int, C.c_int, C.c_int64, _u32p, _i32p, _u32p, _i32p, _u32p, _i32p]
+    L.cbo_ew_scalar_si.argtypes = [C.c_int, C.c_int, C.c_int64, _u32p, _i32p, _u32p, _i32p, _i64p]
+    L.cbo_fuchs_batch.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int,
+                                  _u32p, _i32p, _u32p, _i32p, C.c_int]
+    L.cbo_frobenius1_batch.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int,
+                                       _u32p, _i32p, _u32p, _i32p, _u32p, _i32p, C.c_int]
+    L.cbo_horner_batch.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int, _u32p, _i32p, _u32p,
+                                   _i32p, _u32p, _i32p, C.c_int]
+    L.cbo_ode_shift_flat.argtypes = [C.c_int, C.c_int, C.c_int, _u32p, _i32p, _u32p, _i32p, _u32p, _i32p]
+    L.cbo_ode_solves_flat.argtypes = [C.c_int, C.c_int, C.c_int, _u32p, _i32p, _u32p, _i32p,
+                                      C.c_int64, C.c_int64]
+    L.cbo_example_flat.argtypes = [C.c_int, C.c_int, C.c_uint64, _u32p, _i32p, _u32p, _i32p]
+    _LIBS[name] = L
+    return L
+
+
+def backend(plain: bool = False) -> str:
+    return lib(plain).cbo_backend().decode()
+
+
+def ew_binary(op: int, x: Balls, y: Balls | None = None, plain: bool = False) -> Balls:
+    y = x if y is None else y
+    z = Balls.zeros(x.n_slots, x.L)
+    rc = lib(plain).cbo_ew_binary(op, x.L, x.n_slots // 2, z.mant, z.meta, x.mant, x.meta, y.mant, y.meta)
+    assert rc == 0
+    return z
+
+
+def ew_scalar_si(op: int, x: Balls, k, plain: bool = False) -> Balls:
+    z = Balls.zeros(x.n_slots, x.L)
+    k = np.ascontiguousarray(np.broadcast_to(np.asarray(k, np.int64), (x.n_slots // 2,)))
+    rc = lib(plain).cbo_ew_scalar_si(op, x.L, x.n_slots // 2, z.mant, z.meta, x.mant, x.meta, k)
+    assert rc == 0
+    return z
+
+
+def _series_with_init(init: Balls, batch: int, n: int, ninit: int) -> Balls:
+    """[batch][n+1] complex balls with the first ninit of each row taken from init[batch][ninit]."""
+    L = init.L
+    res = Balls.zeros(batch * (n + 1) * 2, L)
+    rm = res.mant.reshape(batch, n + 1, 2, L)
+    rt = res.meta.reshape(batch, n + 1, 2, 4)
+    rm[:, :ninit] = init.mant.reshape(batch, ninit, 2, L)
+    rt[:, :ninit] = init.meta.reshape(batch, ninit, 2, 4)
+    return res
+
+
+def fuchs_batch(order: int, degree: int, n: int, ode: Balls, init: Balls, batch: int,
+                shared_ode: bool, nthreads: int = 1, plain: bool = False):
+    """init: [batch][ninit] complex balls (ninit = -valuation).  Returns (rc, res[batch][n+1])."""
+    ninit = init.n_slots // (2 * batch)
+    res = _series_with_init(init, batch, n, ninit)
+    rc = lib(plain).cbo_fuchs_batch(ode.L, order, degree, n, batch, int(shared_ode), ode.mant,
+                                    ode.meta, res.mant, res.meta, nthreads)
+    return rc, res
+
+
+def frobenius1_batch(order: int, degree: int, n: int, ode: Balls, rho: Balls, batch: int,
+                     shared_ode: bool, nthreads: int = 1, plain: bool = False) -> Balls:
+    res = Balls.zeros(batch * (n + 1) * 2, ode.L)
+    rc = lib(plain).cbo_frobenius1_batch(ode.L, order, degree, n, batch, int(shared_ode), ode.mant,
+                                         ode.meta, rho.mant, rho.meta, res.mant, res.meta, nthreads)
+    assert rc == 0
+    return res
+
+
+def horner_batch(f: Balls, pts: Balls, nder: int = 1, nthreads: int = 1, plain: bool = False) -> Balls:
+    npts = pts.n_slots // 2
+    out = Balls.zeros(npts * nder * 2, f.L)
+    rc = lib(plain).cbo_horner_batch(f.L, f.n_slots // 2, npts, nder, f.mant, f.meta, pts.mant,
+                                     pts.meta, out.mant, out.meta, nthreads)
+    assert rc == 0
+    return out
+
+
+def ode_shift(order: int, degree: int, ode: Balls, a: Balls, plain: bool = False) -> Balls:
+    out = Balls.zeros(ode.n_slots, ode.L)
+    rc = lib(plain).cbo_ode_shift_flat(ode.L, order, degree, ode.mant, ode.meta, a.mant, a.meta,
+                                       out.mant, out.meta)
+    assert rc == 0
+    return out
+
+
+def ode_solves(order: int, degree: int, ode: Balls, res: Balls, deg: int, plain: bool = False) -> bool:
+    return bool(lib(plain).cbo_ode_solves_flat(ode.L, order, degree, ode.mant, ode.meta, res.mant,
+                                               res.meta, res.n_slots // 2, deg))
+
+
+def example(which: str, L: int, n: int = 0, params: Balls | None = None, plain: bool = False) -> Balls:
+    """legendre(n) | bessel(nu) | hypgeom(a, b, c): the 3x3 operator as 9 complex balls."""
+    code = {"legendre": 0, "bessel": 1, "hypgeom": 2}[which]
+    params = Balls.zeros(6, L) if params is None else params.copy()
+    out = Balls.zeros(18, L)
+    rc = lib(plain).cbo_example_flat(code, L, n, params.mant, params.meta, out.mant, out.meta)
+    assert rc == 0
+    return out

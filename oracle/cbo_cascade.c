@@ -1,0 +1,429 @@
+/* cbo_cascade.c -- ORACLE restatement of Cascade's hot-path loops on cbo ball arithmetic.
+ * TEST INFRASTRUCTURE ONLY (see cbo.h): the product never links or calls this file.
+ *
+ * Each function follows the operation ORDER of the reference function it names, so that the
+ * rounding sequence (and therefore every ball) is the one the reference would produce on an
+ * Arb with the semantics stated in cbo_arith.c.
+ */
+#include "cbo.h"
+#include <stdlib.h>
+#include <string.h>
+
+static int64_t clampi(int64_t x, int64_t lo, int64_t hi) { /* reference src/cascade.h:30-38 */
+    return x < lo ? lo : (x > hi ? hi : x);
+}
+
+/* ---------------------------------------------------------------- operator (src/acb_ode.c) */
+cbo_ode *cbo_ode_new(int degree, int order) { /* acb_ode_init_blank, src/acb_ode.c:28-41 */
+    cbo_ode *o = (cbo_ode *)calloc(1, sizeof(cbo_ode));
+    o->order = order;
+    o->degree = degree;
+    o->valuation = CBO_UNDEFINED;
+    int cnt = (order + 1) * (degree + 1);
+    o->polys = (cbo_acb *)malloc(sizeof(cbo_acb) * cnt);
+    for (int i = 0; i < cnt; i++) cbo_acb_zero(o->polys + i);
+    return o;
+}
+void cbo_ode_free(cbo_ode *o) {
+    if (!o) return;
+    free(o->polys);
+    free(o);
+}
+#define COEFF(o, i, j) ((o)->polys + (i) * ((o)->degree + 1) + (j))
+
+int cbo_ode_valuation(cbo_ode *o) { /* acb_ode_valuation, src/acb_ode.c:159-181 */
+    if (o->valuation != CBO_UNDEFINED) return o->valuation;
+    int val = o->degree;
+    for (int i = 0; i <= o->order; i++) {
+        int z = 0;
+        while (z <= o->degree && cbo_acb_is_zero(COEFF(o, i, z))) z++;
+        if (z - i < val) val = z - i;
+    }
+    o->valuation = val;
+    return val;
+}
+
+/* examples, src/examples.c:3-44 */
+void cbo_ode_legendre(cbo_ode *o, uint64_t n, int L) {
+    cbo_acb_set_si(COEFF(o, 0, 0), (int64_t)(n * (n + 1)), L);
+    cbo_acb_set_si(COEFF(o, 1, 1), -2, L);
+    cbo_acb_set_si(COEFF(o, 2, 0), 1, L);
+    cbo_acb_set_si(COEFF(o, 2, 2), -1, L);
+}
+void cbo_ode_bessel(cbo_ode *o, cbo_acb *nu, int L) {
+    cbo_acb_set_si(COEFF(o, 2, 2), 1, L);
+    cbo_acb_set_si(COEFF(o, 1, 1), 1, L);
+    cbo_acb_set_si(COEFF(o, 0, 2), 1, L);
+    cbo_acb_mul(nu, nu, nu, L); /* the reference squares its argument in place, :20 */
+    cbo_acb_neg(COEFF(o, 0, 0), nu);
+}
+void cbo_ode_hypgeom(cbo_ode *o, const cbo_acb *a, const cbo_acb *b, const cbo_acb *c, int L) {
+    cbo_acb t;
+    cbo_acb_set_si(COEFF(o, 2, 1), 1, L);
+    cbo_acb_set_si(COEFF(o, 2, 2), -1, L);
+    *COEFF(o, 1, 0) = *c;
+    cbo_acb_one(&t, L);
+    cbo_acb_add(&t, &t, a, L);
+    cbo_acb_add(&t, &t, b, L);
+    cbo_acb_neg(COEFF(o, 1, 1), &t);
+    cbo_acb_mul(&t, a, b, L);
+    cbo_acb_neg(COEFF(o, 0, 0), &t);
+}
+
+/* acb_ode_shift, src/acb_ode.c:124-135.  Each row is Taylor-shifted with the Horner scheme
+ * (Arb's _acb_poly_taylor_shift_horner, the algorithm Arb selects for these 3-term rows):
+ *   for i = n-2 .. 0: for j = i .. n-2: p[j] += p[j+1] * a        (acb_addmul) */
+void cbo_ode_shift(cbo_ode *out, cbo_ode *in, const cbo_acb *a, int L) {
+    int cnt = (in->order + 1) * (in->degree + 1);
+    if (out != in) {
+        out->order = in->order;
+        out->degree = in->degree;
+        memcpy(out->polys, in->polys, sizeof(cbo_acb) * cnt);
+        out->valuation = cbo_ode_valuation(in);
+    }
+    if (cbo_acb_is_zero(a) || in->degree == 0) return;
+    int n = out->degree + 1;
+    for (int row = 0; row <= out->order; row++) {
+        cbo_acb *p = COEFF(out, row, 0);
+        for (int i = n - 2; i >= 0; i--)
+            for (int j = i; j <= n - 2; j++) cbo_acb_addmul(p + j, p + j + 1, a, L);
+    }
+    out->valuation = CBO_UNDEFINED;
+}
+
+/* ---------------------------------------------------------------- Fuchs (src/fuchs_solver.c:96-145) */
+int cbo_solve_fuchs(cbo_acb *res, cbo_ode *o, int64_t n, int L) {
+    int v = cbo_ode_valuation(o);
+    if (v >= 0) return -1;
+    cbo_acb t1, t2, acc;
+    for (int64_t bmax = -v; bmax <= n; bmax++) {
+        cbo_acb_zero(&acc);
+        int64_t e = bmax + v;
+        int64_t bmin = clampi(e - o->degree, 0, bmax);
+        t2 = *COEFF(o, 0, e - bmin);
+        int64_t b = bmin;
+        do {
+            t1 = res[b];
+            cbo_acb_mul(&t2, &t1, &t2, L);   /* :118 */
+            cbo_acb_sub(&acc, &acc, &t2, L); /* :119 */
+            cbo_acb_zero(&t2);
+            int64_t fac = 1;
+            b++;
+            int64_t imin = clampi(b - e, 0, -v);
+            int64_t imax = clampi(b - bmin, 0, o->order);
+            for (int64_t i = imin; i <= imax; i++) { /* :127-133 */
+                t1 = *COEFF(o, i, i + e - b);
+                cbo_acb_mul_si(&t1, &t1, fac, L);
+                cbo_acb_add(&t2, &t2, &t1, L);
+                fac *= (b - i);
+            }
+            /* rising factorial (b-imin+1)...(b), imin factors, :134 */
+            fac = 1;
+            for (int64_t k = 0; k < imin; k++) fac *= (b - imin + 1 + k);
+            cbo_acb_mul_si(&t2, &t2, fac, L); /* :135 */
+        } while (b != bmax);
+        cbo_acb_div(&acc, &acc, &t2, L); /* :137 */
+        res[bmax] = acc;
+    }
+    return 0;
+}
+
+/* ---------------------------------------------------------------- Frobenius (src/frobenius_solver.c) */
+void cbo_indicial_polynomial_evaluate(cbo_acb *result, cbo_ode *o, int64_t nu, const cbo_acb *rho,
+                                      int64_t shift, int L) { /* :41-70 */
+    nu += cbo_ode_valuation(o);
+    if (nu > o->degree) {
+        cbo_acb_zero(result);
+        return;
+    }
+    cbo_acb t, out;
+    cbo_acb_zero(&out);
+    for (int64_t lam = clampi(o->degree - nu, 0, o->order); lam >= 0; lam--) {
+        cbo_acb_add_si(&t, rho, shift - lam, L);
+        cbo_acb_mul(&out, &out, &t, L);
+        if (lam + nu < 0) continue;
+        cbo_acb_add(&out, &out, COEFF(o, lam, lam + nu), L);
+    }
+    *result = out;
+}
+
+/* _acb_ode_solve_frobenius, :72-121.  rhs == NULL or all-zero rhs polynomial: g_0 = 1. */
+void cbo_solve_frobenius1(cbo_acb *res, cbo_ode *o, const cbo_acb *rho_in, const cbo_acb *rhs,
+                          int64_t rhs_len, int64_t n, int L) {
+    cbo_acb g_new, ind, g_i, rho = *rho_in, zero;
+    cbo_acb_zero(&zero);
+    int rhs_zero = 1;
+    for (int64_t i = 0; i < rhs_len; i++)
+        if (!cbo_acb_is_zero(rhs + i)) rhs_zero = 0;
+    if (rhs_zero) {
+        cbo_acb_one(res, L);
+        for (int64_t i = 1; i <= n; i++) cbo_acb_zero(res + i);
+    } else {
+        int v = cbo_ode_valuation(o);
+        cbo_acb_add_si(&rho, &rho, -(int64_t)v, L); /* acb_sub_si(rho, rho, v), :89 */
+        g_new = rhs[0];
+        cbo_indicial_polynomial_evaluate(&ind, o, 0, &rho, 0, L);
+        cbo_acb_div(&g_new, &g_new, &ind, L);
+        res[0] = g_new;
+    }
+    for (int64_t nu = 1; nu <= n; nu++) {
+        g_new = (!rhs_zero && nu < rhs_len) ? rhs[nu] : zero;
+        int64_t i = clampi(nu, 1, o->degree);
+        cbo_indicial_polynomial_evaluate(&ind, o, i, &rho, nu - i, L);
+        do {
+            g_i = res[nu - i];
+            cbo_acb_mul(&ind, &ind, &g_i, L);
+            cbo_acb_sub(&g_new, &g_new, &ind, L);
+            i--;
+            cbo_indicial_polynomial_evaluate(&ind, o, i, &rho, nu - i, L);
+        } while (i > 0);
+        cbo_acb_div(&g_new, &g_new, &ind, L);
+        res[nu] = g_new;
+    }
+}
+
+/* ---------------------------------------------------------------- Horner
+ * acb_poly_evaluate as used at src/acb_ode_solution.c:40,45,72,103 (Arb's
+ * _acb_poly_evaluate_horner: t = f[len-1]; t = t*a + f[i]), extended with the first nder-1
+ * normalised derivatives  out[k] = f^(k)(a)/k!  (the only part of acb_poly_taylor_shift at
+ * src/fuchs_solver.c:159 that the next solve reads):
+ *   for j = len-2 .. 0:  for k = nder-1 .. 1: out[k] = out[k]*a + out[k-1];  out[0] = out[0]*a + f[j] */
+void cbo_poly_evaluate_horner(cbo_acb *out, const cbo_acb *f, int64_t len, const cbo_acb *a,
+                              int nder, int L) {
+    for (int k = 0; k < nder; k++) cbo_acb_zero(out + k);
+    if (len <= 0) return;
+    out[0] = f[len - 1];
+    for (int64_t j = len - 2; j >= 0; j--) {
+        for (int k = nder - 1; k >= 1; k--) {
+            cbo_acb_mul(out + k, out + k, a, L);
+            cbo_acb_add(out + k, out + k, out + k - 1, L);
+        }
+        cbo_acb_mul(out, out, a, L);
+        cbo_acb_add(out, out, f + j, L);
+    }
+}
+
+/* ---------------------------------------------------------------- residual check
+ * acb_ode_apply / acb_ode_solves, src/acb_ode.c:185-240: out = sum_i p_i * in^(i) with classical
+ * polynomial products; the reference's own acceptance criterion for both solvers. */
+void cbo_ode_apply(cbo_acb *out, int64_t out_len, cbo_ode *o, const cbo_acb *in, int64_t len_in,
+                   int L) {
+    cbo_acb *der = (cbo_acb *)malloc(sizeof(cbo_acb) * (len_in + 1));
+    cbo_acb t;
+    memcpy(der, in, sizeof(cbo_acb) * len_in);
+    int64_t dl = len_in;
+    for (int64_t k = 0; k < out_len; k++) cbo_acb_zero(out + k);
+    for (int i = 0; i <= o->order; i++) {
+        for (int j = 0; j <= o->degree; j++) {
+            const cbo_acb *p = COEFF(o, i, j);
+            if (cbo_acb_is_zero(p)) continue;
+            for (int64_t k = 0; k < dl && j + k < out_len; k++) {
+                cbo_acb_mul(&t, p, der + k, L);
+                cbo_acb_add(out + j + k, out + j + k, &t, L);
+            }
+        }
+        /* derivative */
+        for (int64_t k = 1; k < dl; k++) cbo_acb_mul_si(der + k - 1, der + k, k, L);
+        if (dl > 0) dl--;
+    }
+    free(der);
+}
+int cbo_ode_solves(cbo_ode *o, const cbo_acb *res, int64_t len, int64_t deg, int L) {
+    int64_t out_len = len + o->degree;
+    cbo_acb *out = (cbo_acb *)malloc(sizeof(cbo_acb) * (out_len > 0 ? out_len : 1));
+    cbo_ode_apply(out, out_len, o, res, len, L);
+    int ok = 1;
+    for (int64_t i = 0; i < deg && i < out_len; i++) {
+        if (!cbo_acb_is_finite(out + i) || !cbo_acb_contains_zero(out + i)) {
+            ok = 0;
+            break;
+        }
+    }
+    free(out);
+    return ok;
+}
+
+
+/* ---------------------------------------------------------------- tiny pthread parallel-for */
+#include <pthread.h>
+typedef void (*pf_body)(int64_t idx, void *ctx);
+typedef struct {
+    pf_body body;
+    void *ctx;
+    int64_t n;
+    int64_t next;
+    pthread_mutex_t mu;
+} pf_state;
+static void *pf_worker(void *arg) {
+    pf_state *st = (pf_state *)arg;
+    for (;;) {
+        pthread_mutex_lock(&st->mu);
+        int64_t i = st->next++;
+        pthread_mutex_unlock(&st->mu);
+        if (i >= st->n) break;
+        st->body(i, st->ctx);
+    }
+    return NULL;
+}
+static void parallel_for(int64_t n, int nthreads, pf_body body, void *ctx) {
+    pf_state st;
+    st.body = body;
+    st.ctx = ctx;
+    st.n = n;
+    st.next = 0;
+    pthread_mutex_init(&st.mu, NULL);
+    if (nthreads <= 1 || n <= 1) {
+        pf_worker(&st);
+    } else {
+        if (nthreads > 256) nthreads = 256;
+        pthread_t th[256];
+        for (int t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, pf_worker, &st);
+        for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    }
+    pthread_mutex_destroy(&st.mu);
+}
+
+/* ---------------------------------------------------------------- flat (ctypes) entry points */
+static void load_acb(cbo_acb *z, const uint32_t *m, const int32_t *t, int64_t i, int L) {
+    cbo_load(&z->re, m + (2 * i) * L, t + (2 * i) * 4, L);
+    cbo_load(&z->im, m + (2 * i + 1) * L, t + (2 * i + 1) * 4, L);
+}
+static void store_acb(uint32_t *m, int32_t *t, int64_t i, const cbo_acb *z, int L) {
+    cbo_store(m + (2 * i) * L, t + (2 * i) * 4, &z->re, L);
+    cbo_store(m + (2 * i + 1) * L, t + (2 * i + 1) * 4, &z->im, L);
+}
+static cbo_ode *load_ode(int L, int order, int degree, const uint32_t *m, const int32_t *t,
+                         int64_t inst) {
+    cbo_ode *o = cbo_ode_new(degree, order);
+    int cnt = (order + 1) * (degree + 1);
+    for (int k = 0; k < cnt; k++) load_acb(o->polys + k, m, t, inst * cnt + k, L);
+    return o;
+}
+
+/* res arrays: [batch][n+1] complex balls; on entry the first -v of each row are the initial values.
+ * ode arrays: [batch or 1][(order+1)(degree+1)] complex balls. */
+typedef struct {
+    int L, order, degree, shared_ode, rc;
+    int64_t n;
+    const uint32_t *ode_m, *rho_m;
+    const int32_t *ode_t, *rho_t;
+    uint32_t *res_m;
+    int32_t *res_t;
+} solve_ctx;
+
+static void fuchs_body(int64_t s, void *vc) {
+    solve_ctx *c = (solve_ctx *)vc;
+    int L = c->L;
+    int64_t n = c->n;
+    cbo_ode *o = load_ode(L, c->order, c->degree, c->ode_m, c->ode_t, c->shared_ode ? 0 : s);
+    cbo_acb *res = (cbo_acb *)malloc(sizeof(cbo_acb) * (n + 1));
+    for (int64_t k = 0; k <= n; k++) load_acb(res + k, c->res_m, c->res_t, s * (n + 1) + k, L);
+    if (cbo_solve_fuchs(res, o, n, L) != 0) c->rc = -1;
+    for (int64_t k = 0; k <= n; k++) store_acb(c->res_m, c->res_t, s * (n + 1) + k, res + k, L);
+    free(res);
+    cbo_ode_free(o);
+}
+int cbo_fuchs_batch(int L, int order, int degree, int64_t n, int64_t batch, int shared_ode,
+                    const uint32_t *ode_m, const int32_t *ode_t, uint32_t *res_m, int32_t *res_t,
+                    int nthreads) {
+    solve_ctx c = {L, order, degree, shared_ode, 0, n, ode_m, NULL, ode_t, NULL, res_m, res_t};
+    parallel_for(batch, nthreads, fuchs_body, &c);
+    return c.rc;
+}
+
+static void frob_body(int64_t s, void *vc) {
+    solve_ctx *c = (solve_ctx *)vc;
+    int L = c->L;
+    int64_t n = c->n;
+    cbo_ode *o = load_ode(L, c->order, c->degree, c->ode_m, c->ode_t, c->shared_ode ? 0 : s);
+    cbo_acb *res = (cbo_acb *)malloc(sizeof(cbo_acb) * (n + 1));
+    cbo_acb rho;
+    load_acb(&rho, c->rho_m, c->rho_t, s, L);
+    cbo_solve_frobenius1(res, o, &rho, NULL, 0, n, L);
+    for (int64_t k = 0; k <= n; k++) store_acb(c->res_m, c->res_t, s * (n + 1) + k, res + k, L);
+    free(res);
+    cbo_ode_free(o);
+}
+int cbo_frobenius1_batch(int L, int order, int degree, int64_t n, int64_t batch, int shared_ode,
+                         const uint32_t *ode_m, const int32_t *ode_t, const uint32_t *rho_m,
+                         const int32_t *rho_t, uint32_t *res_m, int32_t *res_t, int nthreads) {
+    solve_ctx c = {L, order, degree, shared_ode, 0, n, ode_m, rho_m, ode_t, rho_t, res_m, res_t};
+    parallel_for(batch, nthreads, frob_body, &c);
+    return 0;
+}
+
+/* f: one series of len complex balls shared by all points; out: [npts][nder] */
+typedef struct {
+    int L, nder;
+    int64_t len;
+    const cbo_acb *f;
+    const uint32_t *a_m;
+    const int32_t *a_t;
+    uint32_t *out_m;
+    int32_t *out_t;
+} horner_ctx;
+static void horner_body(int64_t p, void *vc) {
+    horner_ctx *c = (horner_ctx *)vc;
+    cbo_acb a, out[8];
+    load_acb(&a, c->a_m, c->a_t, p, c->L);
+    cbo_poly_evaluate_horner(out, c->f, c->len, &a, c->nder, c->L);
+    for (int k = 0; k < c->nder; k++) store_acb(c->out_m, c->out_t, p * c->nder + k, out + k, c->L);
+}
+int cbo_horner_batch(int L, int64_t len, int64_t npts, int nder, const uint32_t *f_m,
+                     const int32_t *f_t, const uint32_t *a_m, const int32_t *a_t, uint32_t *out_m,
+                     int32_t *out_t, int nthreads) {
+    if (nder < 1 || nder > 8) return -1;
+    cbo_acb *f = (cbo_acb *)malloc(sizeof(cbo_acb) * (len > 0 ? len : 1));
+    for (int64_t k = 0; k < len; k++) load_acb(f + k, f_m, f_t, k, L);
+    horner_ctx c = {L, nder, len, f, a_m, a_t, out_m, out_t};
+    parallel_for(npts, nthreads, horner_body, &c);
+    free(f);
+    return 0;
+}
+
+int cbo_ode_shift_flat(int L, int order, int degree, const uint32_t *in_m, const int32_t *in_t,
+                       const uint32_t *a_m, const int32_t *a_t, uint32_t *out_m, int32_t *out_t) {
+    cbo_ode *in = load_ode(L, order, degree, in_m, in_t, 0);
+    cbo_ode *out = cbo_ode_new(degree, order);
+    cbo_acb a;
+    load_acb(&a, a_m, a_t, 0, L);
+    cbo_ode_shift(out, in, &a, L);
+    int cnt = (order + 1) * (degree + 1);
+    for (int k = 0; k < cnt; k++) store_acb(out_m, out_t, k, out->polys + k, L);
+    cbo_ode_free(in);
+    cbo_ode_free(out);
+    return 0;
+}
+
+int cbo_ode_solves_flat(int L, int order, int degree, const uint32_t *ode_m, const int32_t *ode_t,
+                        const uint32_t *res_m, const int32_t *res_t, int64_t len, int64_t deg) {
+    cbo_ode *o = load_ode(L, order, degree, ode_m, ode_t, 0);
+    cbo_acb *res = (cbo_acb *)malloc(sizeof(cbo_acb) * (len > 0 ? len : 1));
+    for (int64_t k = 0; k < len; k++) load_acb(res + k, res_m, res_t, k, L);
+    int ok = cbo_ode_solves(o, res, len, deg, L);
+    free(res);
+    cbo_ode_free(o);
+    return ok;
+}
+
+/* which: 0 legendre(n), 1 bessel(par[0]) (par[0] is overwritten with nu^2), 2 hypgeom(par[0..2]) */
+int cbo_example_flat(int which, int L, uint64_t n, const uint32_t *par_m, const int32_t *par_t,
+                     uint32_t *out_m, int32_t *out_t) {
+    cbo_ode *o = cbo_ode_new(2, 2);
+    cbo_acb p[3];
+    if (which == 0) {
+        cbo_ode_legendre(o, n, L);
+    } else if (which == 1) {
+        load_acb(&p[0], par_m, par_t, 0, L);
+        cbo_ode_bessel(o, &p[0], L);
+    } else if (which == 2) {
+        for (int k = 0; k < 3; k++) load_acb(&p[k], par_m, par_t, k, L);
+        cbo_ode_hypgeom(o, &p[0], &p[1], &p[2], L);
+    } else {
+        cbo_ode_free(o);
+        return -1;
+    }
+    for (int k = 0; k < 9; k++) store_acb(out_m, out_t, k, o->polys + k, L);
+    cbo_ode_free(o);
+    return 0;
+}
