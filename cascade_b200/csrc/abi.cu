@@ -1,0 +1,295 @@
+// abi.cu -- the C ABI (include/cascade_b200.h) of libcascade_b200.so.
+// sm_100a only; there is no CPU path in this library.
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/cascade_b200.h"
+#include "cb_kernels.cuh"
+
+using namespace cb;
+
+static_assert(sizeof(cb_meta) == sizeof(Meta), "meta layout");
+
+namespace {
+
+std::atomic<uint64_t> g_launches{0};
+
+const LaunchTable* table_for(int L) {
+    switch (L) {
+        case 4: return &launch_table_L4;
+        case 32: return &launch_table_L32;
+        case 64: return &launch_table_L64;
+        case 128: return &launch_table_L128;
+        default: return nullptr;
+    }
+}
+
+bool supported_L(int L) { return L == 4 || L == 32 || L == 64 || L == 128; }
+
+size_t arr_mant_bytes(int L, int64_t entries, int64_t S) { return (size_t)entries * L * S * 4; }
+size_t arr_meta_bytes(int64_t entries, int64_t S) { return (size_t)entries * S * 16; }
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// carve a ball array out of a workspace
+CArr carve(char*& w, int L, int64_t entries, int64_t S) {
+    CArr a;
+    a.m = (uint32_t*)w;
+    w += align256(arr_mant_bytes(L, entries, S));
+    a.t = (Meta*)w;
+    w += align256(arr_meta_bytes(entries, S));
+    a.S = (size_t)S;
+    return a;
+}
+size_t carve_bytes(int L, int64_t entries, int64_t S) {
+    return align256(arr_mant_bytes(L, entries, S)) + align256(arr_meta_bytes(entries, S));
+}
+
+// does n^(order+1) fit comfortably in int64?  (the integer factors of src/fuchs_solver.c:132,134)
+bool factor_fits(int64_t n, int order) {
+    long double v = 1;
+    for (int i = 0; i <= order; i++) v *= (long double)(n + 1);
+    return v < 4.0e18L;
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* cb200_version(void) { return "cascade_b200 0.1 (sm_100a)"; }
+
+int cb200_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return -(int)e;
+    return n;
+}
+
+uint64_t cb200_kernel_launches(void) { return g_launches.load(); }
+
+size_t cb200_fuchs_workspace_bytes(int L, int64_t batch, int64_t, int) {
+    return carve_bytes(L, FUCHS_NTMP, 2 * batch);
+}
+size_t cb200_frobenius_workspace_bytes(int L, int64_t batch) { return carve_bytes(L, FROB_NTMP, 2 * batch); }
+size_t cb200_horner_workspace_bytes(int L, int64_t npts) { return carve_bytes(L, 1, 2 * npts); }
+size_t cb200_ew_workspace_bytes(int L, int64_t n) { return carve_bytes(L, 2, 2 * n); }
+
+int cb200_fuchs_batch_dev(int L_, int order, int degree, int valuation, int64_t n, int64_t batch,
+                          const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
+                          uint32_t* res_mant, cb_meta* res_meta, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+    if (!supported_L(L_) || order < 1 || degree < 0 || batch < 0 || n < 0) return CB200_EINVAL;
+    if (valuation >= 0) return CB200_EVALUATION;
+    if (!factor_fits(n, order)) return CB200_ERANGE;
+    if (workspace_bytes < cb200_fuchs_workspace_bytes(L_, batch, n, shared_ode)) return CB200_ENOMEM;
+    FuchsParams p;
+    p.order = order;
+    p.degree = degree;
+    p.valuation = valuation;
+    p.n = n;
+    p.batch = batch;
+    p.ode = CArr{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta),
+                 shared_ode ? (size_t)2 : (size_t)(2 * batch)};
+    p.res = CArr{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
+    char* w = (char*)workspace;
+    p.tmp = carve(w, L_, FUCHS_NTMP, 2 * batch);
+    g_launches.fetch_add(batch > 0);
+    return table_for(L_)->fuchs(p, (cudaStream_t)stream);
+}
+
+int cb200_frobenius1_batch_dev(int L_, int order, int degree, int valuation, int64_t n, int64_t batch,
+                               const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
+                               const uint32_t* rho_mant, const cb_meta* rho_meta, int shared_rho,
+                               uint32_t* res_mant, cb_meta* res_meta, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    if (!supported_L(L_) || order < 1 || degree < 1 || batch < 0 || n < 0) return CB200_EINVAL;
+    if (workspace_bytes < cb200_frobenius_workspace_bytes(L_, batch)) return CB200_ENOMEM;
+    FrobParams p;
+    p.order = order;
+    p.degree = degree;
+    p.valuation = valuation;
+    p.n = n;
+    p.batch = batch;
+    p.ode = CArr{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta),
+                 shared_ode ? (size_t)2 : (size_t)(2 * batch)};
+    p.rho = CArr{const_cast<uint32_t*>(rho_mant), (Meta*)const_cast<cb_meta*>(rho_meta),
+                 shared_rho ? (size_t)2 : (size_t)(2 * batch)};
+    p.res = CArr{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
+    char* w = (char*)workspace;
+    p.tmp = carve(w, L_, FROB_NTMP, 2 * batch);
+    g_launches.fetch_add(batch > 0);
+    return table_for(L_)->frobenius1(p, (cudaStream_t)stream);
+}
+
+int cb200_horner_batch_dev(int L_, int64_t len, int64_t npts, int nder, const uint32_t* f_mant,
+                           const cb_meta* f_meta, int shared_f, const uint32_t* pts_mant,
+                           const cb_meta* pts_meta, uint32_t* out_mant, cb_meta* out_meta,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+    if (!supported_L(L_) || len < 0 || npts < 0 || nder < 1 || nder > HORNER_MAXDER) return CB200_EINVAL;
+    if (workspace_bytes < cb200_horner_workspace_bytes(L_, npts)) return CB200_ENOMEM;
+    HornerParams p;
+    p.nder = nder;
+    p.len = len;
+    p.npts = npts;
+    p.f = CArr{const_cast<uint32_t*>(f_mant), (Meta*)const_cast<cb_meta*>(f_meta),
+               shared_f ? (size_t)2 : (size_t)(2 * npts)};
+    p.pts = CArr{const_cast<uint32_t*>(pts_mant), (Meta*)const_cast<cb_meta*>(pts_meta), (size_t)(2 * npts)};
+    p.out = CArr{out_mant, (Meta*)out_meta, (size_t)(2 * npts)};
+    char* w = (char*)workspace;
+    p.tmp = carve(w, L_, 1, 2 * npts);
+    g_launches.fetch_add(npts > 0);
+    return table_for(L_)->horner(p, (cudaStream_t)stream);
+}
+
+int cb200_ew_dev(int op, int L_, int64_t n, uint32_t* z_mant, cb_meta* z_meta, const uint32_t* x_mant,
+                 const cb_meta* x_meta, const uint32_t* y_mant, const cb_meta* y_meta, const int64_t* k,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+    if (!supported_L(L_) || n < 0) return CB200_EINVAL;
+    bool binary = op == CB200_OP_ADD || op == CB200_OP_SUB || op == CB200_OP_MUL || op == CB200_OP_DIV;
+    bool unary = op == CB200_OP_INV, si = op == CB200_OP_MUL_SI || op == CB200_OP_ADD_SI;
+    if (!(binary || unary || si)) return CB200_EINVAL;
+    if (si && !k) return CB200_EINVAL;
+    if (workspace_bytes < cb200_ew_workspace_bytes(L_, n)) return CB200_ENOMEM;
+    EwParams p;
+    p.op = op;
+    p.n = n;
+    p.z = CArr{z_mant, (Meta*)z_meta, (size_t)(2 * n)};
+    p.x = CArr{const_cast<uint32_t*>(x_mant), (Meta*)const_cast<cb_meta*>(x_meta), (size_t)(2 * n)};
+    p.y = binary ? CArr{const_cast<uint32_t*>(y_mant), (Meta*)const_cast<cb_meta*>(y_meta), (size_t)(2 * n)} : p.x;
+    p.k = k;
+    char* w = (char*)workspace;
+    p.tmp = carve(w, L_, 2, 2 * n);
+    g_launches.fetch_add(n > 0);
+    return table_for(L_)->ew(p, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ host-buffer (end-to-end) entry points
+#define CK(x)                                \
+    do {                                     \
+        cudaError_t e_ = (x);                \
+        if (e_ != cudaSuccess) return (int)e_; \
+    } while (0)
+
+int cb200_fuchs_batch_host(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
+                           const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
+                           uint32_t* res_mant, cb_meta* res_meta, int device) {
+    if (!supported_L(L) || order < 1 || degree < 0 || batch < 0 || n < 0) return CB200_EINVAL;
+    if (valuation >= 0) return CB200_EVALUATION;
+    CK(cudaSetDevice(device));
+    int64_t So = shared_ode ? 2 : 2 * batch, S = 2 * batch, ne = (int64_t)(order + 1) * (degree + 1);
+    DevBuf om, ot, rm, rt, ws;
+    size_t wsb = cb200_fuchs_workspace_bytes(L, batch, n, shared_ode);
+    CK(om.alloc(arr_mant_bytes(L, ne, So)));
+    CK(ot.alloc(arr_meta_bytes(ne, So)));
+    CK(rm.alloc(arr_mant_bytes(L, n + 1, S)));
+    CK(rt.alloc(arr_meta_bytes(n + 1, S)));
+    CK(ws.alloc(wsb));
+    CK(cudaMemcpy(om.p, ode_mant, arr_mant_bytes(L, ne, So), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ot.p, ode_meta, arr_meta_bytes(ne, So), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(rm.p, res_mant, arr_mant_bytes(L, n + 1, S), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(rt.p, res_meta, arr_meta_bytes(n + 1, S), cudaMemcpyHostToDevice));
+    int rc = cb200_fuchs_batch_dev(L, order, degree, valuation, n, batch, (uint32_t*)om.p, (cb_meta*)ot.p,
+                                   shared_ode, (uint32_t*)rm.p, (cb_meta*)rt.p, ws.p, wsb, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(res_mant, rm.p, arr_mant_bytes(L, n + 1, S), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(res_meta, rt.p, arr_meta_bytes(n + 1, S), cudaMemcpyDeviceToHost));
+    return (int)cudaDeviceSynchronize();
+}
+
+int cb200_frobenius1_batch_host(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
+                                const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
+                                const uint32_t* rho_mant, const cb_meta* rho_meta, int shared_rho,
+                                uint32_t* res_mant, cb_meta* res_meta, int device) {
+    if (!supported_L(L) || order < 1 || degree < 1 || batch < 0 || n < 0) return CB200_EINVAL;
+    CK(cudaSetDevice(device));
+    int64_t So = shared_ode ? 2 : 2 * batch, Sr = shared_rho ? 2 : 2 * batch, S = 2 * batch;
+    int64_t ne = (int64_t)(order + 1) * (degree + 1);
+    DevBuf om, ot, pm, pt, rm, rt, ws;
+    size_t wsb = cb200_frobenius_workspace_bytes(L, batch);
+    CK(om.alloc(arr_mant_bytes(L, ne, So)));
+    CK(ot.alloc(arr_meta_bytes(ne, So)));
+    CK(pm.alloc(arr_mant_bytes(L, 1, Sr)));
+    CK(pt.alloc(arr_meta_bytes(1, Sr)));
+    CK(rm.alloc(arr_mant_bytes(L, n + 1, S)));
+    CK(rt.alloc(arr_meta_bytes(n + 1, S)));
+    CK(ws.alloc(wsb));
+    CK(cudaMemcpy(om.p, ode_mant, arr_mant_bytes(L, ne, So), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ot.p, ode_meta, arr_meta_bytes(ne, So), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pm.p, rho_mant, arr_mant_bytes(L, 1, Sr), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pt.p, rho_meta, arr_meta_bytes(1, Sr), cudaMemcpyHostToDevice));
+    int rc = cb200_frobenius1_batch_dev(L, order, degree, valuation, n, batch, (uint32_t*)om.p, (cb_meta*)ot.p,
+                                        shared_ode, (uint32_t*)pm.p, (cb_meta*)pt.p, shared_rho,
+                                        (uint32_t*)rm.p, (cb_meta*)rt.p, ws.p, wsb, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(res_mant, rm.p, arr_mant_bytes(L, n + 1, S), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(res_meta, rt.p, arr_meta_bytes(n + 1, S), cudaMemcpyDeviceToHost));
+    return (int)cudaDeviceSynchronize();
+}
+
+int cb200_horner_batch_host(int L, int64_t len, int64_t npts, int nder, const uint32_t* f_mant,
+                            const cb_meta* f_meta, int shared_f, const uint32_t* pts_mant,
+                            const cb_meta* pts_meta, uint32_t* out_mant, cb_meta* out_meta, int device) {
+    if (!supported_L(L) || len < 0 || npts < 0 || nder < 1 || nder > HORNER_MAXDER) return CB200_EINVAL;
+    CK(cudaSetDevice(device));
+    int64_t Sf = shared_f ? 2 : 2 * npts, S = 2 * npts;
+    DevBuf fm, ft, pm, pt, om, ot, ws;
+    size_t wsb = cb200_horner_workspace_bytes(L, npts);
+    CK(fm.alloc(arr_mant_bytes(L, len, Sf)));
+    CK(ft.alloc(arr_meta_bytes(len, Sf)));
+    CK(pm.alloc(arr_mant_bytes(L, 1, S)));
+    CK(pt.alloc(arr_meta_bytes(1, S)));
+    CK(om.alloc(arr_mant_bytes(L, nder, S)));
+    CK(ot.alloc(arr_meta_bytes(nder, S)));
+    CK(ws.alloc(wsb));
+    CK(cudaMemcpy(fm.p, f_mant, arr_mant_bytes(L, len, Sf), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ft.p, f_meta, arr_meta_bytes(len, Sf), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pm.p, pts_mant, arr_mant_bytes(L, 1, S), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pt.p, pts_meta, arr_meta_bytes(1, S), cudaMemcpyHostToDevice));
+    int rc = cb200_horner_batch_dev(L, len, npts, nder, (uint32_t*)fm.p, (cb_meta*)ft.p, shared_f,
+                                    (uint32_t*)pm.p, (cb_meta*)pt.p, (uint32_t*)om.p, (cb_meta*)ot.p, ws.p,
+                                    wsb, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(out_mant, om.p, arr_mant_bytes(L, nder, S), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out_meta, ot.p, arr_meta_bytes(nder, S), cudaMemcpyDeviceToHost));
+    return (int)cudaDeviceSynchronize();
+}
+
+int cb200_ew_host(int op, int L, int64_t n, uint32_t* z_mant, cb_meta* z_meta, const uint32_t* x_mant,
+                  const cb_meta* x_meta, const uint32_t* y_mant, const cb_meta* y_meta, const int64_t* k,
+                  int device) {
+    if (!supported_L(L) || n < 0) return CB200_EINVAL;
+    CK(cudaSetDevice(device));
+    int64_t S = 2 * n;
+    DevBuf zm, zt, xm, xt, ym, yt, kk, ws;
+    size_t wsb = cb200_ew_workspace_bytes(L, n);
+    CK(zm.alloc(arr_mant_bytes(L, 1, S)));
+    CK(zt.alloc(arr_meta_bytes(1, S)));
+    CK(xm.alloc(arr_mant_bytes(L, 1, S)));
+    CK(xt.alloc(arr_meta_bytes(1, S)));
+    CK(ym.alloc(arr_mant_bytes(L, 1, S)));
+    CK(yt.alloc(arr_meta_bytes(1, S)));
+    CK(kk.alloc(sizeof(int64_t) * n));
+    CK(ws.alloc(wsb));
+    CK(cudaMemcpy(xm.p, x_mant, arr_mant_bytes(L, 1, S), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(xt.p, x_meta, arr_meta_bytes(1, S), cudaMemcpyHostToDevice));
+    if (y_mant && y_meta) {
+        CK(cudaMemcpy(ym.p, y_mant, arr_mant_bytes(L, 1, S), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(yt.p, y_meta, arr_meta_bytes(1, S), cudaMemcpyHostToDevice));
+    }
+    if (k) CK(cudaMemcpy(kk.p, k, sizeof(int64_t) * n, cudaMemcpyHostToDevice));
+    int rc = cb200_ew_dev(op, L, n, (uint32_t*)zm.p, (cb_meta*)zt.p, (uint32_t*)xm.p, (cb_meta*)xt.p,
+                          (uint32_t*)ym.p, (cb_meta*)yt.p, k ? (int64_t*)kk.p : nullptr, ws.p, wsb, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(z_mant, zm.p, arr_mant_bytes(L, 1, S), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(z_meta, zt.p, arr_meta_bytes(1, S), cudaMemcpyDeviceToHost));
+    return (int)cudaDeviceSynchronize();
+}
+
+}  // extern "C"

@@ -1,0 +1,614 @@
+// cb_arith.cuh -- device ball arithmetic for sm_100a: one CUDA thread owns one complex ODE
+// instance and runs plain multi-limb code on 32-bit limbs (IMAD.WIDE carry chains, see
+// cb_mul.cuh); per-thread scratch lives in shared memory in a [word][thread] layout so that
+// data-dependent limb offsets (alignment, renormalisation) stay bank-conflict free.
+//
+// This is the device replacement for the Arb calls Cascade's hot path makes:
+//   acb_mul / acb_sub / acb_add / acb_div / acb_mul_fmpz   reference src/fuchs_solver.c:118-137
+//   acb_add_si / acb_mul / acb_add / acb_div               reference src/frobenius_solver.c:58-113
+//   acb_mul / acb_add (Horner inside acb_poly_evaluate)    reference src/acb_ode_solution.c:40-49
+//
+// Semantics (DESIGN.md "Ball arithmetic"): midpoints are the EXACT result rounded toward zero
+// to 32 L bits from the leading bit, with an exact "inexact" flag; radii are 30-bit magnitudes
+// rounded up, formulas as written at each function.  The same header compiles for the host
+// (tests/host_sim) so the logic can be checked against the oracle without a GPU; the product
+// library only ever contains the device build.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include "cb_mul.cuh"
+
+#if defined(__CUDACC__)
+#define CB_HD __host__ __device__ __forceinline__
+#define CB_NOINLINE __host__ __device__ __noinline__
+#else
+#define CB_HD inline
+#define CB_NOINLINE __attribute__((noinline))
+#endif
+
+namespace cb {
+
+constexpr uint32_t F_SIGN = 1u, F_ZERO = 2u, F_NAN = 4u;
+constexpr int32_t EXP_LIMIT = 1 << 28;
+
+struct Meta {
+    int32_t exp;
+    uint32_t flags;
+    uint32_t rman;
+    int32_t rexp;
+};
+
+// ---------------------------------------------------------------- small helpers
+CB_HD int clz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __clz((int)x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
+CB_HD int clz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)x);
+#else
+    return x ? __builtin_clzll(x) : 64;
+#endif
+}
+// (hi:lo) >> r, low word; r in [0,31]
+CB_HD uint32_t shr_pair(uint32_t lo, uint32_t hi, int r) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, (uint32_t)r);
+#else
+    return r ? (lo >> r) | (hi << (32 - r)) : lo;
+#endif
+}
+CB_HD bool warp_all(bool p) {
+#if defined(__CUDA_ARCH__)
+    return __all_sync(__activemask(), p);
+#else
+    return p;
+#endif
+}
+CB_HD bool warp_any(bool p) {
+#if defined(__CUDA_ARCH__)
+    return __any_sync(__activemask(), p);
+#else
+    return p;
+#endif
+}
+
+// Per-thread scratch column.  Device: word k of this thread is at p[k * STRIDE] (shared memory,
+// STRIDE = threads per block, so lane t always hits bank t).  Host: STRIDE = 1.
+// On the device the column is addressed through ld.shared/st.shared on a 32-bit shared-window
+// address, so the address space survives the (non-inlined) call boundaries below.
+template <int STRIDE>
+struct Scratch {
+#if defined(__CUDA_ARCH__)
+    uint32_t a;  // shared-space byte address of word 0 of this thread's column
+    __device__ __forceinline__ uint32_t ld(int k) const {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a + (uint32_t)(k * (STRIDE * 4))));
+        return v;
+    }
+    __device__ __forceinline__ void st(int k, uint32_t v) const {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(a + (uint32_t)(k * (STRIDE * 4))), "r"(v));
+    }
+#else
+    uint32_t* p;
+    uint32_t ld(int k) const { return p[(ptrdiff_t)k * STRIDE]; }
+    void st(int k, uint32_t v) const { p[(ptrdiff_t)k * STRIDE] = v; }
+#endif
+};
+
+// ---------------------------------------------------------------- magnitudes (radii)
+// value = man * 2^(exp-30), man in [2^29, 2^30) or 0.  Every function mirrors oracle/cbo_arith.c.
+struct Mag {
+    uint32_t man;
+    int32_t exp;
+};
+CB_HD Mag mag_zero() { return Mag{0u, 0}; }
+CB_HD Mag mag_of(const Meta& t) { return Mag{t.rman, t.rexp}; }
+CB_HD Mag mag_mul(Mag x, Mag y) {  // upper bound
+    if (x.man == 0 || y.man == 0) return mag_zero();
+    uint32_t m = (uint32_t)(((uint64_t)x.man * y.man) >> 30) + 1;
+    int32_t e = x.exp + y.exp;
+    if (!(m >> 29)) {
+        m <<= 1;
+        e -= 1;
+    }
+    return Mag{m, e};
+}
+CB_HD Mag mag_mul_lower(Mag x, Mag y) {
+    if (x.man == 0 || y.man == 0) return mag_zero();
+    uint32_t m = (uint32_t)(((uint64_t)x.man * y.man) >> 30);
+    int32_t e = x.exp + y.exp;
+    if (!(m >> 29)) {
+        m <<= 1;
+        e -= 1;
+    }
+    return Mag{m, e};
+}
+CB_HD Mag mag_add(Mag x, Mag y) {  // upper bound
+    if (x.man == 0) return y;
+    if (y.man == 0) return x;
+    if (x.exp < y.exp) {
+        Mag t = x;
+        x = y;
+        y = t;
+    }
+    int32_t sh = x.exp - y.exp;
+    uint32_t m;
+    if (sh == 0)
+        m = x.man + y.man;
+    else if (sh >= 30)
+        m = x.man + 1;
+    else
+        m = x.man + (y.man >> sh) + 1;
+    int32_t e = x.exp;
+    if (m >> 30) {
+        m = (m >> 1) + (m & 1);
+        e += 1;
+    }
+    return Mag{m, e};
+}
+CB_HD Mag mag_sub_lower(Mag x, Mag y) {  // lower bound of x - y, 0 if not provably positive
+    if (y.man == 0) return x;
+    if (x.man == 0) return mag_zero();
+    int32_t sh = x.exp - y.exp;
+    if (sh < 0) return mag_zero();
+    int32_t m;
+    if (sh >= 30)
+        m = (int32_t)x.man - 1;
+    else
+        m = (int32_t)x.man - (int32_t)(y.man >> sh) - 1;
+    if (m <= 0) return mag_zero();
+    int s = clz32((uint32_t)m) - 2;
+    return Mag{(uint32_t)m << s, x.exp - s};
+}
+CB_HD Mag mag_div(Mag x, Mag y) {  // upper bound of x / y, y > 0
+    if (x.man == 0) return mag_zero();
+    uint32_t q = (uint32_t)((((uint64_t)x.man) << 30) / y.man) + 1;
+    int32_t e = x.exp - y.exp;
+    while (q >> 30) {
+        q = (q >> 1) + (q & 1);
+        e += 1;
+    }
+    return Mag{q, e};
+}
+CB_HD Mag mag_mid_upper(const Meta& t, uint32_t top_limb) {
+    if (t.flags & F_ZERO) return mag_zero();
+    uint32_t m = (top_limb >> 2) + 1;
+    int32_t e = t.exp;
+    if (m >> 30) {
+        m = 1u << 29;
+        e += 1;
+    }
+    return Mag{m, e};
+}
+CB_HD Mag mag_mid_lower(const Meta& t, uint32_t top_limb) {
+    if (t.flags & F_ZERO) return mag_zero();
+    return Mag{top_limb >> 2, t.exp};
+}
+template <int L>
+CB_HD Mag mag_ulp(int32_t exp) {
+    return Mag{1u << 29, exp - 32 * L + 1};
+}
+// |x|^ yr + |y|^ xr + xr yr added onto acc, in this order
+CB_HD Mag mul_rad(Mag acc, const Meta& x, uint32_t xtop, const Meta& y, uint32_t ytop) {
+    acc = mag_add(acc, mag_mul(mag_mid_upper(x, xtop), mag_of(y)));
+    acc = mag_add(acc, mag_mul(mag_mid_upper(y, ytop), mag_of(x)));
+    acc = mag_add(acc, mag_mul(mag_of(x), mag_of(y)));
+    return acc;
+}
+
+CB_HD Meta meta_nan() { return Meta{0, F_NAN, 0xFFFFFFFFu, 0}; }
+CB_HD Meta meta_zero() { return Meta{0, F_ZERO, 0u, 0}; }
+CB_HD bool is_nan(const Meta& t) { return (t.flags & F_NAN) != 0; }
+CB_HD bool is_zero_mid(const Meta& t) { return (t.flags & F_ZERO) != 0; }
+CB_HD bool is_exact_zero(const Meta& t) { return (t.flags & F_ZERO) && t.rman == 0; }
+
+// a real ball in memory: limb k at m[k*stride]; meta by value
+struct RRef {
+    const uint32_t* m;
+    size_t stride;
+};
+struct WRef {
+    uint32_t* m;
+    size_t stride;
+};
+
+// Rounded midpoint result description produced by extract()
+struct Rounded {
+    int32_t exp;
+    bool zero;
+    bool inexact;
+    bool overflow;
+};
+
+// ---------------------------------------------------------------- extract
+// R[0..hi] (scratch words, R[hi] != 0 unless the value is zero) is an unsigned integer V whose
+// bit 0 has weight 2^frame.  Writes the top 32 L bits of V to dst (truncation), returns exponent
+// and the exact inexact flag.  lo = index of the lowest nonzero word (or a value > hi if V == 0).
+template <int L, class SCR>
+CB_HD Rounded extract(WRef dst, SCR R, int hi, int lo, bool sticky, int64_t frame) {
+    Rounded out;
+    uint32_t top = (hi >= 0) ? R.ld(hi) : 0u;
+    if (hi < 0 || top == 0) {
+#pragma unroll
+        for (int j = 0; j < L; j++) dst.m[j * dst.stride] = 0u;
+        out.exp = 0;
+        out.zero = true;
+        out.inexact = sticky;  // cannot happen with sticky (see align_add), kept for safety
+        out.overflow = false;
+        return out;
+    }
+    int bl = 32 * hi + 32 - clz32(top);
+    int off = bl - 32 * L;
+    int q = off >> 5;  // arithmetic shift: floor
+    int r = off & 31;
+    uint32_t cur = (q >= 0 && q <= hi) ? R.ld(q) : 0u;
+    bool inex = sticky || (lo < q) || (lo == q && r != 0 && (cur & ((1u << r) - 1u)) != 0u);
+#pragma unroll
+    for (int j = 0; j < L; j++) {
+        int idx = q + j + 1;
+        uint32_t nxt = (idx >= 0 && idx <= hi) ? R.ld(idx) : 0u;
+        dst.m[j * dst.stride] = shr_pair(cur, nxt, r);
+        cur = nxt;
+    }
+    int64_t e = frame + bl;
+    out.overflow = (e > EXP_LIMIT || e < -EXP_LIMIT);
+    out.exp = (int32_t)e;
+    out.zero = false;
+    out.inexact = inex;
+    return out;
+}
+
+// ---------------------------------------------------------------- align_add
+// A and B hold N-limb magnitudes (words 0..N-1), top aligned: |a| = A * 2^(ea - 32 N).
+// Computes |R| = | sa*a + sb*b | exactly as far as truncation to 32 L bits can tell, into the
+// scratch column of the larger operand (words 0..N+1), and rounds it into dst.
+// Returns the rounded description and the result sign through *neg.
+template <int L, int N, class SCR>
+CB_HD Rounded align_add(WRef dst, SCR A, SCR B, int64_t ea, int64_t eb, bool nega, bool negb,
+                        bool za, bool zb, bool* neg) {
+    // pick "big": the nonzero one, else the larger exponent (ties: A)
+    bool swap = za ? true : (zb ? false : (eb > ea));
+    SCR big = swap ? B : A, small = swap ? A : B;
+    int64_t ebig = swap ? eb : ea, esm = swap ? ea : eb;
+    bool nbig = swap ? negb : nega, nsm = swap ? nega : negb;
+    bool zbig = swap ? zb : za, zsm = swap ? za : zb;
+    if (zbig) {  // both zero
+        *neg = false;
+        return extract<L>(dst, big, -1, 0, false, 0);
+    }
+    int64_t d64 = zsm ? 0 : (ebig - esm);
+    bool far = d64 > 32 * (N + 2);  // small lies entirely below the window
+    int d = far ? 32 * (N + 2) : (int)d64;
+    int q = d >> 5, r = d & 31;
+    bool sub = (nbig != nsm) && !zsm;
+    // sticky: nonzero bits of T = small * 2^32 (N+1 words, T[0] = 0) below bit d
+    bool sticky = false;
+    if (warp_any(q >= 2 || far)) {
+        uint32_t acc = 0;
+#pragma unroll 8
+        for (int j = 0; j < N; j++) {  // T[j+1] = small[j]; fully below iff j+1 < q
+            uint32_t v = small.ld(j);
+            acc |= (j + 1 < q) ? v : 0u;
+        }
+        sticky = acc != 0u;
+    }
+    if (q >= 1 && q <= N && r != 0) sticky = sticky || ((small.ld(q - 1) & ((1u << r) - 1u)) != 0u);
+    if (zsm) sticky = false;
+    // aligned top words decide the operand order of a subtraction (ties resolved by a fix-up)
+    auto Tw = [&](int idx) -> uint32_t { return (idx >= 1 && idx <= N && !zsm) ? small.ld(idx - 1) : 0u; };
+    bool swapped = false;
+    if (sub) {
+        uint32_t s_hi = shr_pair(Tw(N + q), Tw(N + q + 1), r);
+        uint32_t s_lo = shr_pair(Tw(N - 1 + q), Tw(N + q), r);
+        uint32_t w_hi = big.ld(N - 1), w_lo = (N >= 2) ? big.ld(N - 2) : 0u;
+        uint64_t s64 = ((uint64_t)s_hi << 32) | s_lo, w64 = ((uint64_t)w_hi << 32) | w_lo;
+        swapped = s64 > w64;
+    }
+    uint32_t mw = (sub && swapped) ? 0xFFFFFFFFu : 0u;
+    uint32_t ms = (sub && !swapped) ? 0xFFFFFFFFu : 0u;
+    uint32_t carry = (sub && !sticky) ? 1u : 0u;
+    int hi = -1, lo = 0x7FFFFFFF;
+    uint32_t wprev = 0u;           // W[k] = big[k-1]
+    uint32_t tcur = Tw(q);         // T[k+q]
+#pragma unroll
+    for (int k = 0; k <= N; k++) {
+        uint32_t wnext = (k < N) ? big.ld(k) : 0u;  // read before the slot is overwritten
+        uint32_t tnxt = Tw(k + q + 1);
+        uint32_t s = shr_pair(tcur, tnxt, r);
+        uint64_t t = (uint64_t)(wprev ^ mw) + (uint64_t)(s ^ ms) + carry;
+        uint32_t v = (uint32_t)t;
+        carry = (uint32_t)(t >> 32);
+        big.st(k, v);
+        if (v != 0u) {
+            hi = k;
+            lo = lo < k ? lo : k;
+        }
+        wprev = wnext;
+        tcur = tnxt;
+    }
+    bool rneg = nbig;
+    if (!sub) {
+        big.st(N + 1, carry);
+        if (carry) hi = N + 1, lo = lo < N + 1 ? lo : N + 1;
+    } else {
+        big.st(N + 1, 0u);
+        if (swapped) rneg = nsm;
+        if (carry == 0u) {
+            // the order guess was wrong (top 64 aligned bits tied): negate in place
+            rneg = !rneg;
+            uint32_t c = 1u;
+            hi = -1;
+            lo = 0x7FFFFFFF;
+#pragma unroll 1
+            for (int k = 0; k <= N; k++) {
+                uint64_t t = (uint64_t)(~big.ld(k)) + c;
+                uint32_t v = (uint32_t)t;
+                c = (uint32_t)(t >> 32);
+                big.st(k, v);
+                if (v != 0u) {
+                    hi = k;
+                    lo = lo < k ? lo : k;
+                }
+            }
+        }
+    }
+    *neg = rneg;
+    return extract<L>(dst, big, hi, lo, sticky, ebig - 32 * (int64_t)N - 32);
+}
+
+// ---------------------------------------------------------------- products into scratch
+// P[0..2L) = x * y (exact), limbs read from memory
+template <int L, class SCR>
+CB_HD void product(SCR P, RRef x, RRef y) {
+    if constexpr (L <= 32) {
+        uint32_t a[L], b[L], r[2 * L];
+#pragma unroll
+        for (int j = 0; j < L; j++) a[j] = x.m[j * x.stride];
+#pragma unroll
+        for (int j = 0; j < L; j++) b[j] = y.m[j * y.stride];
+        mul_full<L>(r, a, b);
+#pragma unroll
+        for (int k = 0; k < 2 * L; k++) P.st(k, r[k]);
+    } else {
+        constexpr int NB = L / 32;
+#pragma unroll 1
+        for (int k = 0; k < 2 * L; k++) P.st(k, 0u);
+#pragma unroll 1
+        for (int bi = 0; bi < NB; bi++) {
+            uint32_t a[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) a[j] = x.m[(32 * bi + j) * x.stride];
+#pragma unroll 1
+            for (int bj = 0; bj < NB; bj++) {
+                uint32_t b[32], r[64];
+#pragma unroll
+                for (int j = 0; j < 32; j++) b[j] = y.m[(32 * bj + j) * y.stride];
+                mul_full<32>(r, a, b);
+                int off = 32 * (bi + bj);
+                uint32_t c = 0u;
+#pragma unroll
+                for (int k = 0; k < 64; k++) {
+                    uint64_t t = (uint64_t)P.ld(off + k) + r[k] + c;
+                    P.st(off + k, (uint32_t)t);
+                    c = (uint32_t)(t >> 32);
+                }
+#pragma unroll 1
+                for (int k = off + 64; c != 0u && k < 2 * L; k++) {
+                    uint64_t t = (uint64_t)P.ld(k) + c;
+                    P.st(k, (uint32_t)t);
+                    c = (uint32_t)(t >> 32);
+                }
+            }
+        }
+    }
+}
+
+// one real operand: where its limbs are and its meta record
+struct Opd {
+    RRef r;
+    Meta t;
+};
+template <int L>
+CB_HD uint32_t top_limb(const Opd& o) {
+    return o.r.m[(L - 1) * o.r.stride];
+}
+
+template <int L>
+CB_HD Meta finish(const Rounded& rr, bool neg, Mag rad) {
+    if (rr.overflow) return meta_nan();
+    Meta t;
+    if (rr.zero) {
+        t.exp = 0;
+        t.flags = F_ZERO;
+    } else {
+        t.exp = rr.exp;
+        t.flags = neg ? F_SIGN : 0u;
+        if (rr.inexact) rad = mag_add(rad, mag_ulp<L>(rr.exp));
+    }
+    t.rman = rad.man;
+    t.rexp = rad.man ? rad.exp : 0;
+    return t;
+}
+template <int L>
+CB_HD void store_nan(WRef dst) {
+#pragma unroll
+    for (int j = 0; j < L; j++) dst.m[j * dst.stride] = 0u;
+}
+
+// ---------------------------------------------------------------- arb level
+// dst = x1*y1 + (neg2 ? -1 : 1) * x2*y2, one rounding.  S0/S1: two scratch columns of 2L+2 words.
+template <int L, class SCR>
+CB_NOINLINE Meta arb_fdot2(WRef dst, Opd x1, Opd y1, Opd x2, Opd y2, bool neg2, SCR S0, SCR S1) {
+    bool nan = is_nan(x1.t) || is_nan(y1.t) || is_nan(x2.t) || is_nan(y2.t);
+    bool z1 = is_zero_mid(x1.t) || is_zero_mid(y1.t);
+    bool z2 = is_zero_mid(x2.t) || is_zero_mid(y2.t);
+    Mag rad = mul_rad(mag_zero(), x1.t, top_limb<L>(x1), y1.t, top_limb<L>(y1));
+    rad = mul_rad(rad, x2.t, top_limb<L>(x2), y2.t, top_limb<L>(y2));
+    bool skip1 = warp_all(z1 || nan), skip2 = warp_all(z2 || nan);
+#pragma unroll 1
+    for (int term = 0; term < 2; term++) {  // a loop, so that the product code exists once
+        if (term ? skip2 : skip1) continue;
+        product<L>(term ? S1 : S0, term ? x2.r : x1.r, term ? y2.r : y1.r);
+    }
+    bool n1 = ((x1.t.flags ^ y1.t.flags) & F_SIGN) != 0;
+    bool n2 = (((x2.t.flags ^ y2.t.flags) & F_SIGN) != 0) != neg2;
+    bool neg;
+    Rounded rr = align_add<L, 2 * L>(dst, S0, S1, (int64_t)x1.t.exp + y1.t.exp,
+                                     (int64_t)x2.t.exp + y2.t.exp, n1, n2, z1 || nan, z2 || nan, &neg);
+    if (nan) return meta_nan();
+    return finish<L>(rr, neg, rad);
+}
+
+// dst = x + (negy ? -y : y)
+template <int L, class SCR>
+CB_NOINLINE Meta arb_addsub(WRef dst, Opd x, Opd y, bool negy, SCR S0, SCR S1) {
+    bool nan = is_nan(x.t) || is_nan(y.t);
+    bool zx = is_zero_mid(x.t) || nan, zy = is_zero_mid(y.t) || nan;
+#pragma unroll
+    for (int j = 0; j < L; j++) S0.st(j, x.r.m[j * x.r.stride]);
+#pragma unroll
+    for (int j = 0; j < L; j++) S1.st(j, y.r.m[j * y.r.stride]);
+    bool neg;
+    Rounded rr = align_add<L, L>(dst, S0, S1, x.t.exp, y.t.exp, (x.t.flags & F_SIGN) != 0,
+                                 ((y.t.flags & F_SIGN) != 0) != negy, zx, zy, &neg);
+    if (nan) return meta_nan();
+    return finish<L>(rr, neg, mag_add(mag_of(x.t), mag_of(y.t)));
+}
+
+// dst = x * k, k a signed 64-bit integer (acb_mul_fmpz / acb_mul_si with a small integer)
+template <int L, class SCR>
+CB_NOINLINE Meta arb_mul_si(WRef dst, Opd x, int64_t k, SCR S0) {
+    bool nan = is_nan(x.t);
+    uint64_t ka = k < 0 ? (uint64_t)0 - (uint64_t)k : (uint64_t)k;
+    uint32_t k0 = (uint32_t)ka, k1 = (uint32_t)(ka >> 32);
+    // radius: |k|^ * xr  (|x|^ * 0 and xr * 0 drop out)
+    Mag km = mag_zero();
+    if (ka) {
+        int sh = clz64(ka);
+        uint64_t kn = ka << sh;  // top bit at 63
+        Meta kt{64 - sh, 0u, 0u, 0};
+        km = mag_mid_upper(kt, (uint32_t)(kn >> 32));
+    }
+    Mag rad = mag_mul(km, mag_of(x.t));
+    bool z = is_zero_mid(x.t) || ka == 0 || nan;
+    // P[0..L+2) = x * ka, column by column:
+    //   col j = lo(x_j k0) + hi(x_{j-1} k0) + lo(x_{j-1} k1) + hi(x_{j-2} k1) + carry
+    uint32_t hi0_prev = 0u, lo1_prev = 0u, hi1_prev = 0u, hi1_prev2 = 0u, carry = 0u;
+    int hi = -1, lo = 0x7FFFFFFF;
+#pragma unroll
+    for (int j = 0; j < L + 2; j++) {
+        uint32_t xj = (j < L) ? x.r.m[j * x.r.stride] : 0u;
+        uint64_t p0 = (uint64_t)xj * k0, p1 = (uint64_t)xj * k1;
+        uint64_t t = (uint64_t)carry + (uint32_t)p0 + hi0_prev + lo1_prev + hi1_prev2;
+        uint32_t v = z ? 0u : (uint32_t)t;
+        carry = (uint32_t)(t >> 32);
+        S0.st(j, v);
+        if (v != 0u) {
+            hi = j;
+            lo = lo < j ? lo : j;
+        }
+        hi0_prev = (uint32_t)(p0 >> 32);
+        hi1_prev2 = hi1_prev;
+        hi1_prev = (uint32_t)(p1 >> 32);
+        lo1_prev = (uint32_t)p1;
+    }
+    Rounded rr = extract<L>(dst, S0, hi, lo, false, (int64_t)x.t.exp - 32 * L);
+    if (nan) return meta_nan();
+    bool neg = ((x.t.flags & F_SIGN) != 0) != (k < 0);
+    return finish<L>(rr, neg, rad);
+}
+
+// dst = x / y  (Knuth D on 32-bit limbs; numerator x * 2^(32L) in S0, divisor in S1)
+template <int L, class SCR>
+CB_NOINLINE Meta arb_div(WRef dst, Opd x, Opd y, SCR S0, SCR S1) {
+    bool nan = is_nan(x.t) || is_nan(y.t) || is_zero_mid(y.t);
+    uint32_t ytop = top_limb<L>(y), xtop = top_limb<L>(x);
+    Mag yl = mag_mid_lower(y.t, ytop);
+    Mag gap = mag_sub_lower(yl, mag_of(y.t));
+    if (gap.man == 0) nan = true;
+    Mag rad = mag_zero();
+    if (!nan && (x.t.rman != 0 || y.t.rman != 0)) {
+        Mag num = mag_add(mag_mul(mag_mid_upper(x.t, xtop), mag_of(y.t)),
+                          mag_mul(mag_mid_upper(y.t, ytop), mag_of(x.t)));
+        rad = mag_div(num, mag_mul_lower(yl, gap));
+    }
+    bool zx = is_zero_mid(x.t);
+    // U[0..2L] = x << 32L (U[2L] = 0), D[0..L) = y (made a harmless normalised dummy when nan)
+#pragma unroll
+    for (int j = 0; j < L; j++) S0.st(j, 0u);
+#pragma unroll
+    for (int j = 0; j < L; j++) S0.st(L + j, (zx || nan) ? 0u : x.r.m[j * x.r.stride]);
+    S0.st(2 * L, 0u);
+#pragma unroll
+    for (int j = 0; j < L; j++) S1.st(j, nan ? (j == L - 1 ? 0x80000000u : 0u) : y.r.m[j * y.r.stride]);
+    uint32_t d1 = S1.ld(L - 1), d0 = S1.ld(L - 2);
+    // quotient words q_j are kept in the upper half of S1 (words L..2L)
+    int hi = -1, lo = 0x7FFFFFFF;
+#pragma unroll 1
+    for (int j = L; j >= 0; j--) {
+        uint32_t u2 = S0.ld(j + L), u1 = S0.ld(j + L - 1), u0 = S0.ld(j + L - 2);
+        uint64_t num = ((uint64_t)u2 << 32) | u1;
+        uint64_t qh, rh;
+        if (u2 >= d1) {
+            qh = 0xFFFFFFFFull;
+            rh = num - qh * d1;
+        } else {
+            qh = num / d1;
+            rh = num - qh * d1;
+        }
+        while (rh <= 0xFFFFFFFFull && qh * d0 > ((rh << 32) | u0)) {
+            qh--;
+            rh += d1;
+        }
+        // U[j .. j+L] -= qh * D
+        uint32_t qd = (uint32_t)qh, borrow = 0u, mc = 0u;
+#pragma unroll 8
+        for (int i = 0; i < L; i++) {
+            uint64_t p = (uint64_t)qd * S1.ld(i) + mc;
+            mc = (uint32_t)(p >> 32);
+            uint64_t t = (uint64_t)S0.ld(i + j) - (uint32_t)p - borrow;
+            S0.st(i + j, (uint32_t)t);
+            borrow = (uint32_t)(t >> 32) & 1u;
+        }
+        uint64_t t = (uint64_t)S0.ld(j + L) - mc - borrow;
+        S0.st(j + L, (uint32_t)t);
+        if ((uint32_t)(t >> 32) & 1u) {  // one too large: add the divisor back
+            qd--;
+            uint32_t c = 0u;
+#pragma unroll 8
+            for (int i = 0; i < L; i++) {
+                uint64_t s = (uint64_t)S0.ld(i + j) + S1.ld(i) + c;
+                S0.st(i + j, (uint32_t)s);
+                c = (uint32_t)(s >> 32);
+            }
+            S0.st(j + L, S0.ld(j + L) + c);
+        }
+        S1.st(L + j, qd);
+        if (qd != 0u) {
+            hi = hi < 0 ? j : hi;
+            lo = j;
+        }
+    }
+    // remainder in U[0..L)
+    uint32_t rem = 0u;
+#pragma unroll 8
+    for (int i = 0; i < L; i++) rem |= S0.ld(i);
+    // Q = S1[L .. 2L] (L+1 words), presented to extract() as a column starting at word L
+    struct View {
+        SCR s;
+        CB_HD uint32_t ld(int k) const { return s.ld(L + k); }
+    } V{S1};
+    Rounded rr = extract<L>(dst, V, hi, lo, rem != 0u, (int64_t)x.t.exp - y.t.exp - 32 * L);
+    if (nan) {
+        store_nan<L>(dst);
+        return meta_nan();
+    }
+    bool neg = ((x.t.flags ^ y.t.flags) & F_SIGN) != 0;
+    return finish<L>(rr, neg, rad);
+}
+
+}  // namespace cb

@@ -1,0 +1,82 @@
+// cb_kernels.cuh -- __global__ wrappers around the per-thread solver bodies, and their launchers.
+// Included by one translation unit per precision (kern_L*.cu) so the precisions compile in parallel.
+#pragma once
+#include <cuda_runtime.h>
+#include "cb_solvers.cuh"
+
+namespace cb {
+
+// threads per block for each precision: bounded by the shared-memory scratch
+// (2 columns of 2L+3 words per thread) and by 255 registers per thread.
+template <int L> struct Cfg;
+template <> struct Cfg<4> { static constexpr int TPB = 128; };
+template <> struct Cfg<32> { static constexpr int TPB = 224; };
+template <> struct Cfg<64> { static constexpr int TPB = 128; };
+template <> struct Cfg<128> { static constexpr int TPB = 64; };
+
+template <int L> struct Sizes {
+    static constexpr int WORDS = 2 * L + 3;  // words per scratch column
+    static constexpr size_t SMEM = (size_t)2 * WORDS * Cfg<L>::TPB * sizeof(uint32_t);
+};
+
+#define CB_KERNEL_PROLOGUE(COUNT)                                                              \
+    extern __shared__ uint32_t cb_smem[];                                                      \
+    constexpr int TPB = Cfg<L>::TPB;                                                           \
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cb_smem) + 4u * threadIdx.x;     \
+    Scratch<TPB> S0{sbase};                                                                    \
+    Scratch<TPB> S1{sbase + 4u * (uint32_t)(Sizes<L>::WORDS * TPB)};                           \
+    const int64_t idx = (int64_t)blockIdx.x * TPB + threadIdx.x;                               \
+    if (idx >= (COUNT)) return;
+
+template <int L>
+__global__ void __launch_bounds__(Cfg<L>::TPB, 1) fuchs_kernel(FuchsParams p) {
+    CB_KERNEL_PROLOGUE(p.batch)
+    fuchs_thread<L>(p, idx, S0, S1);
+}
+template <int L>
+__global__ void __launch_bounds__(Cfg<L>::TPB, 1) frobenius1_kernel(FrobParams p) {
+    CB_KERNEL_PROLOGUE(p.batch)
+    frobenius1_thread<L>(p, idx, S0, S1);
+}
+template <int L>
+__global__ void __launch_bounds__(Cfg<L>::TPB, 1) horner_kernel(HornerParams p) {
+    CB_KERNEL_PROLOGUE(p.npts)
+    horner_thread<L>(p, idx, S0, S1);
+}
+template <int L>
+__global__ void __launch_bounds__(Cfg<L>::TPB, 1) ew_kernel(EwParams p) {
+    CB_KERNEL_PROLOGUE(p.n)
+    ew_thread<L>(p, idx, S0, S1);
+}
+
+template <int L, class P>
+int launch(void (*kern)(P), const P& p, int64_t count, cudaStream_t st) {
+    if (count <= 0) return 0;
+    constexpr int TPB = Cfg<L>::TPB;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sizes<L>::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    unsigned grid = (unsigned)((count + TPB - 1) / TPB);
+    kern<<<grid, TPB, Sizes<L>::SMEM, st>>>(p);
+    return (int)cudaGetLastError();
+}
+
+// per-precision launch table, filled by kern_L*.cu
+struct LaunchTable {
+    int (*fuchs)(const FuchsParams&, cudaStream_t);
+    int (*frobenius1)(const FrobParams&, cudaStream_t);
+    int (*horner)(const HornerParams&, cudaStream_t);
+    int (*ew)(const EwParams&, cudaStream_t);
+};
+
+#define CB_DEFINE_LAUNCH_TABLE(LL)                                                                         \
+    namespace cb {                                                                                         \
+    static int fuchs_##LL(const FuchsParams& p, cudaStream_t s) { return launch<LL>(fuchs_kernel<LL>, p, p.batch, s); }   \
+    static int frob_##LL(const FrobParams& p, cudaStream_t s) { return launch<LL>(frobenius1_kernel<LL>, p, p.batch, s); } \
+    static int horner_##LL(const HornerParams& p, cudaStream_t s) { return launch<LL>(horner_kernel<LL>, p, p.npts, s); } \
+    static int ew_##LL(const EwParams& p, cudaStream_t s) { return launch<LL>(ew_kernel<LL>, p, p.n, s); }                \
+    extern const LaunchTable launch_table_L##LL = {fuchs_##LL, frob_##LL, horner_##LL, ew_##LL};           \
+    }
+
+extern const LaunchTable launch_table_L4, launch_table_L32, launch_table_L64, launch_table_L128;
+
+}  // namespace cb

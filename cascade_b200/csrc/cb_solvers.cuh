@@ -1,0 +1,328 @@
+// cb_solvers.cuh -- per-thread bodies of the batched solvers: complex ball ops on top of
+// cb_arith.cuh and the restated Cascade loops, one CUDA thread per ODE instance.
+//
+//   fuchs_thread       <- acb_ode_solve_fuchs            reference src/fuchs_solver.c:96-145
+//   frobenius1_thread  <- _acb_ode_solve_frobenius       reference src/frobenius_solver.c:72-121
+//                         indicial_polynomial_evaluate   reference src/frobenius_solver.c:41-70
+//   horner_thread      <- acb_poly_evaluate (Horner) and the first `order` Taylor coefficients
+//                         of acb_poly_taylor_shift       reference src/acb_ode_solution.c:40,
+//                                                                  src/fuchs_solver.c:159
+//   ew_thread          <- the scalar Arb calls themselves (unit-test surface)
+//
+// Memory layout: every ball array is [entry][limb][S] mantissa words + [entry][S] meta records,
+// S = 2 * batch (slot = 2*instance + part) for per-instance data and S = 2 for data shared by
+// the whole batch.  A thread reads/writes only its own slots (and shared data), so no
+// synchronisation between threads is needed anywhere.
+#pragma once
+#include "cb_arith.cuh"
+
+namespace cb {
+
+// a complex ball in memory
+struct CRef {
+    uint32_t* m;  // re limb k at m[k*stride], im limb k at m[k*stride + 1]
+    size_t stride;
+    Meta* t;  // t[0] re, t[1] im
+};
+// an array of complex balls
+struct CArr {
+    uint32_t* m;
+    Meta* t;
+    size_t S;  // slots per entry
+};
+template <int L>
+CB_HD CRef at(const CArr& a, int64_t entry, size_t slot) {
+    return CRef{a.m + (size_t)entry * L * a.S + slot, a.S, a.t + (size_t)entry * a.S + slot};
+}
+
+CB_HD Meta ld_meta(const Meta* p) {
+#if defined(__CUDA_ARCH__)
+    int4 v = *reinterpret_cast<const int4*>(p);
+    return Meta{v.x, (uint32_t)v.y, (uint32_t)v.z, v.w};
+#else
+    return *p;
+#endif
+}
+CB_HD void st_meta(Meta* p, const Meta& t) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<int4*>(p) = make_int4(t.exp, (int)t.flags, (int)t.rman, t.rexp);
+#else
+    *p = t;
+#endif
+}
+CB_HD Opd re_of(const CRef& x) { return Opd{RRef{x.m, x.stride}, ld_meta(x.t)}; }
+CB_HD Opd im_of(const CRef& x) { return Opd{RRef{x.m + 1, x.stride}, ld_meta(x.t + 1)}; }
+CB_HD WRef wre(const CRef& x) { return WRef{x.m, x.stride}; }
+CB_HD WRef wim(const CRef& x) { return WRef{x.m + 1, x.stride}; }
+
+template <int L>
+CB_HD void acb_set(const CRef& z, const CRef& x) {
+#pragma unroll
+    for (int k = 0; k < L; k++) {
+        z.m[k * z.stride] = x.m[k * x.stride];
+        z.m[k * z.stride + 1] = x.m[k * x.stride + 1];
+    }
+    st_meta(z.t, ld_meta(x.t));
+    st_meta(z.t + 1, ld_meta(x.t + 1));
+}
+template <int L>
+CB_HD void acb_zero(const CRef& z) {
+#pragma unroll
+    for (int k = 0; k < L; k++) {
+        z.m[k * z.stride] = 0u;
+        z.m[k * z.stride + 1] = 0u;
+    }
+    st_meta(z.t, meta_zero());
+    st_meta(z.t + 1, meta_zero());
+}
+template <int L>
+CB_HD void acb_one(const CRef& z) {
+    acb_zero<L>(z);
+    z.m[(L - 1) * z.stride] = 0x80000000u;
+    st_meta(z.t, Meta{1, 0u, 0u, 0});
+}
+
+// z = x * y.  z must not alias x or y.  (acb_mul: one rounding per component)
+template <int L, class SCR>
+CB_HD void acb_mul(const CRef& z, const CRef& x, const CRef& y, SCR S0, SCR S1) {
+    Opd a = re_of(x), b = im_of(x), c = re_of(y), d = im_of(y);
+    Meta tr = arb_fdot2<L>(wre(z), a, c, b, d, true, S0, S1);
+    Meta ti = arb_fdot2<L>(wim(z), a, d, b, c, false, S0, S1);
+    st_meta(z.t, tr);
+    st_meta(z.t + 1, ti);
+}
+// z = x +- y (componentwise; z may alias x or y)
+template <int L, class SCR>
+CB_HD void acb_addsub(const CRef& z, const CRef& x, const CRef& y, bool sub, SCR S0, SCR S1) {
+    Meta tr = arb_addsub<L>(wre(z), re_of(x), re_of(y), sub, S0, S1);
+    Meta ti = arb_addsub<L>(wim(z), im_of(x), im_of(y), sub, S0, S1);
+    st_meta(z.t, tr);
+    st_meta(z.t + 1, ti);
+}
+template <int L, class SCR>
+CB_HD void acb_mul_si(const CRef& z, const CRef& x, int64_t k, SCR S0) {
+    Meta tr = arb_mul_si<L>(wre(z), re_of(x), k, S0);
+    Meta ti = arb_mul_si<L>(wim(z), im_of(x), k, S0);
+    st_meta(z.t, tr);
+    st_meta(z.t + 1, ti);
+}
+// z = x + k: real part gets the integer, imaginary part is copied (acb_add_si)
+template <int L, class SCR>
+CB_HD void acb_add_si(const CRef& z, const CRef& x, int64_t k, const CRef& kball, SCR S0, SCR S1) {
+    // materialise k as an exact ball in kball.re (scratch ball owned by the caller)
+    uint64_t ka = k < 0 ? (uint64_t)0 - (uint64_t)k : (uint64_t)k;
+    int sh = clz64(ka);
+    uint64_t kn = ka ? ka << sh : 0;
+#pragma unroll
+    for (int j = 0; j < L; j++) kball.m[j * kball.stride] = 0u;
+    kball.m[(L - 1) * kball.stride] = (uint32_t)(kn >> 32);
+    kball.m[(L - 2) * kball.stride] = (uint32_t)kn;
+    Meta kt = ka ? Meta{64 - sh, k < 0 ? F_SIGN : 0u, 0u, 0} : meta_zero();
+    Opd ko{RRef{kball.m, kball.stride}, kt};
+    Meta tr = arb_addsub<L>(wre(z), re_of(x), ko, false, S0, S1);
+    st_meta(z.t, tr);
+    if (z.m != x.m) {
+#pragma unroll
+        for (int j = 0; j < L; j++) z.m[j * z.stride + 1] = x.m[j * x.stride + 1];
+        st_meta(z.t + 1, ld_meta(x.t + 1));
+    }
+}
+// z = 1 / y; z must not alias y; uses tmp.re as a real temporary
+template <int L, class SCR>
+CB_HD void acb_inv(const CRef& z, const CRef& y, const CRef& tmp, SCR S0, SCR S1) {
+    Opd c = re_of(y), d = im_of(y);
+    Meta tt = arb_fdot2<L>(wre(tmp), c, c, d, d, false, S0, S1);
+    Opd t{RRef{tmp.m, tmp.stride}, tt};
+    Meta tr = arb_div<L>(wre(z), c, t, S0, S1);
+    Meta ti = arb_div<L>(wim(z), d, t, S0, S1);
+    if (!is_nan(ti) && !is_zero_mid(ti)) ti.flags ^= F_SIGN;
+    st_meta(z.t, tr);
+    st_meta(z.t + 1, ti);
+}
+// z = x / y; z must not alias x or y; inv: a complex temporary
+template <int L, class SCR>
+CB_HD void acb_div(const CRef& z, const CRef& x, const CRef& y, const CRef& inv, SCR S0, SCR S1) {
+    Meta yim = ld_meta(y.t + 1);
+    if (is_exact_zero(yim)) {
+        Opd c = re_of(y);
+        Meta tr = arb_div<L>(wre(z), re_of(x), c, S0, S1);
+        Meta ti = arb_div<L>(wim(z), im_of(x), c, S0, S1);
+        st_meta(z.t, tr);
+        st_meta(z.t + 1, ti);
+    } else {
+        acb_inv<L>(inv, y, z, S0, S1);
+        acb_mul<L>(z, x, inv, S0, S1);
+    }
+}
+
+CB_HD int64_t clampi(int64_t x, int64_t lo, int64_t hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+// ================================================================ Fuchs
+struct FuchsParams {
+    int order, degree, valuation;
+    int64_t n;      // highest coefficient index written (res has n+1 entries)
+    int64_t batch;  // instances
+    CArr ode;       // (order+1)(degree+1) entries, S = 2*batch or 2 (shared)
+    CArr res;       // n+1 entries, S = 2*batch
+    CArr tmp;       // FUCHS_NTMP entries, S = 2*batch
+};
+constexpr int FUCHS_NTMP = 5;
+
+template <int L, class SCR>
+CB_HD void fuchs_thread(const FuchsParams& p, int64_t inst, SCR S0, SCR S1) {
+    const size_t slot = 2 * (size_t)inst;
+    const size_t oslot = (p.ode.S == 2) ? 0 : slot;
+    const int v = p.valuation, D1 = p.degree + 1;
+    CRef acc = at<L>(p.tmp, 0, slot), prod = at<L>(p.tmp, 1, slot), t1 = at<L>(p.tmp, 2, slot),
+         t2 = at<L>(p.tmp, 3, slot), inv = at<L>(p.tmp, 4, slot);
+#pragma unroll 1
+    for (int64_t bmax = -v; bmax <= p.n; bmax++) {
+        acb_zero<L>(acc);
+        int64_t e = bmax + v;
+        int64_t bmin = clampi(e - p.degree, 0, bmax);
+        CRef cur = at<L>(p.ode, 0 * D1 + (e - bmin), oslot);
+        int64_t b = bmin;
+#pragma unroll 1
+        do {
+            acb_mul<L>(prod, at<L>(p.res, b, slot), cur, S0, S1);
+            acb_addsub<L>(acc, acc, prod, true, S0, S1);
+            acb_zero<L>(t2);
+            int64_t fac = 1;
+            b++;
+            int64_t imin = clampi(b - e, 0, -v);
+            int64_t imax = clampi(b - bmin, 0, p.order);
+#pragma unroll 1
+            for (int64_t i = imin; i <= imax; i++) {
+                acb_mul_si<L>(t1, at<L>(p.ode, i * D1 + (i + e - b), oslot), fac, S0);
+                acb_addsub<L>(t2, t2, t1, false, S0, S1);
+                fac *= (b - i);
+            }
+            fac = 1;
+            for (int64_t k = 0; k < imin; k++) fac *= (b - imin + 1 + k);
+            acb_mul_si<L>(t2, t2, fac, S0);
+            cur = t2;
+        } while (b != bmax);
+        acb_div<L>(at<L>(p.res, bmax, slot), acc, t2, inv, S0, S1);
+    }
+}
+
+// ================================================================ Frobenius (M = 1)
+struct FrobParams {
+    int order, degree, valuation;
+    int64_t n, batch;
+    CArr ode;  // S = 2*batch or 2
+    CArr rho;  // 1 entry, S = 2*batch or 2
+    CArr res;  // n+1 entries
+    CArr tmp;  // FROB_NTMP entries
+};
+constexpr int FROB_NTMP = 6;
+
+// result may be one of (o1, o2): returns which holds f_nu(rho + shift)
+template <int L, class SCR>
+CB_HD CRef indicial_eval(const FrobParams& p, size_t oslot, int64_t nu, const CRef& rho, int64_t shift,
+                         CRef o1, CRef o2, const CRef& t, const CRef& kb, SCR S0, SCR S1) {
+    const int D1 = p.degree + 1;
+    nu += p.valuation;
+    acb_zero<L>(o1);
+    if (nu > p.degree) return o1;
+#pragma unroll 1
+    for (int64_t lam = clampi(p.degree - nu, 0, p.order); lam >= 0; lam--) {
+        acb_add_si<L>(t, rho, shift - lam, kb, S0, S1);
+        acb_mul<L>(o2, o1, t, S0, S1);
+        CRef sw = o1;
+        o1 = o2;
+        o2 = sw;
+        if (lam + nu < 0) continue;
+        acb_addsub<L>(o1, o1, at<L>(p.ode, lam * D1 + (lam + nu), oslot), false, S0, S1);
+    }
+    return o1;
+}
+
+template <int L, class SCR>
+CB_HD void frobenius1_thread(const FrobParams& p, int64_t inst, SCR S0, SCR S1) {
+    const size_t slot = 2 * (size_t)inst;
+    const size_t oslot = (p.ode.S == 2) ? 0 : slot;
+    const size_t rslot = (p.rho.S == 2) ? 0 : slot;
+    CRef gnew = at<L>(p.tmp, 0, slot), o1 = at<L>(p.tmp, 1, slot), o2 = at<L>(p.tmp, 2, slot),
+         t = at<L>(p.tmp, 3, slot), kb = at<L>(p.tmp, 4, slot), prod = at<L>(p.tmp, 5, slot);
+    CRef rho = at<L>(p.rho, 0, rslot);
+    acb_one<L>(at<L>(p.res, 0, slot));  // homogeneous case: g_0 = 1 (src/frobenius_solver.c:84-85)
+#pragma unroll 1
+    for (int64_t nu = 1; nu <= p.n; nu++) {
+        acb_zero<L>(gnew);
+        int64_t i = clampi(nu, 1, p.degree);
+        CRef ind = indicial_eval<L>(p, oslot, i, rho, nu - i, o1, o2, t, kb, S0, S1);
+#pragma unroll 1
+        do {
+            acb_mul<L>(prod, ind, at<L>(p.res, nu - i, slot), S0, S1);
+            acb_addsub<L>(gnew, gnew, prod, true, S0, S1);
+            i--;
+            ind = indicial_eval<L>(p, oslot, i, rho, nu - i, o1, o2, t, kb, S0, S1);
+        } while (i > 0);
+        // g_nu = g_new / f_0(rho + nu); `prod` and the unused one of (o1,o2) are free temporaries
+        CRef spare = (ind.m == o1.m) ? o2 : o1;
+        acb_div<L>(at<L>(p.res, nu, slot), gnew, ind, spare, S0, S1);
+    }
+}
+
+// ================================================================ Horner
+struct HornerParams {
+    int nder;       // number of Taylor coefficients wanted (1 = plain evaluation)
+    int64_t len;    // series length
+    int64_t npts;   // evaluation points == threads
+    CArr f;         // len entries; S = 2 (one series for all points) or 2*npts
+    CArr pts;       // 1 entry, S = 2*npts
+    CArr out;       // nder entries, S = 2*npts
+    CArr tmp;       // 1 entry, S = 2*npts
+};
+constexpr int HORNER_MAXDER = 4;
+
+template <int L, class SCR>
+CB_HD void horner_thread(const HornerParams& p, int64_t pt, SCR S0, SCR S1) {
+    const size_t slot = 2 * (size_t)pt;
+    const size_t fslot = (p.f.S == 2) ? 0 : slot;
+    CRef a = at<L>(p.pts, 0, slot), tmp = at<L>(p.tmp, 0, slot);
+    for (int k = 0; k < p.nder; k++) acb_zero<L>(at<L>(p.out, k, slot));
+    if (p.len <= 0) return;
+    acb_set<L>(at<L>(p.out, 0, slot), at<L>(p.f, p.len - 1, fslot));
+#pragma unroll 1
+    for (int64_t j = p.len - 2; j >= 0; j--) {
+#pragma unroll 1
+        for (int k = p.nder - 1; k >= 0; k--) {
+            CRef o = at<L>(p.out, k, slot);
+            acb_mul<L>(tmp, o, a, S0, S1);
+            if (k > 0)
+                acb_addsub<L>(o, tmp, at<L>(p.out, k - 1, slot), false, S0, S1);
+            else
+                acb_addsub<L>(o, tmp, at<L>(p.f, j, fslot), false, S0, S1);
+        }
+    }
+}
+
+// ================================================================ elementwise (unit-test surface)
+enum { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_DIV = 3, OP_INV = 4, OP_MUL_SI = 16, OP_ADD_SI = 17 };
+struct EwParams {
+    int op;
+    int64_t n;
+    CArr z, x, y;  // 1 entry each, S = 2*n
+    CArr tmp;      // 2 entries
+    const int64_t* k;
+};
+template <int L, class SCR>
+CB_HD void ew_thread(const EwParams& p, int64_t i, SCR S0, SCR S1) {
+    const size_t slot = 2 * (size_t)i;
+    CRef z = at<L>(p.z, 0, slot), x = at<L>(p.x, 0, slot), y = at<L>(p.y, 0, slot);
+    CRef t0 = at<L>(p.tmp, 0, slot), t1 = at<L>(p.tmp, 1, slot);
+    switch (p.op) {
+        case OP_ADD: acb_addsub<L>(z, x, y, false, S0, S1); break;
+        case OP_SUB: acb_addsub<L>(z, x, y, true, S0, S1); break;
+        case OP_MUL: acb_mul<L>(z, x, y, S0, S1); break;
+        case OP_DIV: acb_div<L>(z, x, y, t0, S0, S1); break;
+        case OP_INV: acb_inv<L>(z, x, t0, S0, S1); break;
+        case OP_MUL_SI: acb_mul_si<L>(z, x, p.k[i], S0); break;
+        case OP_ADD_SI: acb_add_si<L>(z, x, p.k[i], t1, S0, S1); break;
+        default: break;
+    }
+}
+
+}  // namespace cb

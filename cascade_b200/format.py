@@ -208,3 +208,33 @@ def random_balls(rng: np.random.Generator, n_slots: int, L: int, exp_lo: int = -
     elif rad != "zero":
         raise ValueError(rad)
     return Balls(L, mant, meta)
+
+
+# ---------------------------------------------------------------- device array layout
+def pack_entries(b: Balls, entries: int, S: int) -> tuple[np.ndarray, np.ndarray]:
+    """Balls with slot index ``e*S + s``  ->  (mant[E, L, S] uint32, meta[E, S, 4] int32)."""
+    assert b.n_slots == entries * S
+    mant = np.ascontiguousarray(b.mant.reshape(entries, S, b.L).transpose(0, 2, 1))
+    meta = np.ascontiguousarray(b.meta.reshape(entries, S, 4))
+    return mant, meta
+
+
+def unpack_entries(L: int, mant: np.ndarray, meta: np.ndarray) -> Balls:
+    """Inverse of :func:`pack_entries`."""
+    E, L_, S = mant.shape
+    assert L_ == L
+    return Balls(L, np.ascontiguousarray(mant.transpose(0, 2, 1)).reshape(E * S, L),
+                 np.ascontiguousarray(meta).reshape(E * S, 4))
+
+
+def instance_major_to_entry_major(b: Balls, batch: int, per_inst: int) -> Balls:
+    """[batch][per_inst] complex balls -> [per_inst][batch] complex balls."""
+    m = b.mant.reshape(batch, per_inst, 2, b.L).transpose(1, 0, 2, 3).reshape(-1, b.L)
+    t = b.meta.reshape(batch, per_inst, 2, 4).transpose(1, 0, 2, 3).reshape(-1, 4)
+    return Balls(b.L, np.ascontiguousarray(m), np.ascontiguousarray(t))
+
+
+def entry_major_to_instance_major(b: Balls, batch: int, per_inst: int) -> Balls:
+    m = b.mant.reshape(per_inst, batch, 2, b.L).transpose(1, 0, 2, 3).reshape(-1, b.L)
+    t = b.meta.reshape(per_inst, batch, 2, 4).transpose(1, 0, 2, 3).reshape(-1, 4)
+    return Balls(b.L, np.ascontiguousarray(m), np.ascontiguousarray(t))

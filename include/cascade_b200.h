@@ -1,0 +1,117 @@
+/* cascade_b200.h -- C ABI of libcascade_b200.so: batched, device-resident replacements for the
+ * hot path of Cascade (MGessinger/Cascade).  Plain pointers and sizes only.
+ *
+ * Cascade has no plugin/FFI layer; its boundary is the public C API of libcascade.so
+ * (reference src/acb_ode.h:25-67, src/cascade.h:8-26).  Each entry point below names the
+ * reference function whose loop it runs for a whole batch; the scalar drop-in wrappers with the
+ * reference's own names and signatures live in include/cascade_compat.h and call these with
+ * batch = 1.  INTEGRATION.md shows the binding a Cascade maintainer would add.
+ *
+ * DATA LAYOUT (see include/cb_format.h).  prec = 32*L bits, L in {4, 32, 64, 128}.
+ * A real ball is a "slot": L little-endian 32-bit mantissa limbs + one cb_meta record.
+ * A complex ball is two adjacent slots (re, im).  A ball ARRAY of E entries with S slots per
+ * entry is
+ *      mant : uint32_t[E][L][S]     (limb-major inside an entry)
+ *      meta : cb_meta [E][S]
+ * with S = 2*batch (slot = 2*instance + part) for per-instance data and S = 2 for data shared by
+ * every instance of the batch.
+ *
+ * "_dev" functions take DEVICE pointers, enqueue kernels on `stream` (a cudaStream_t, may be
+ * NULL) and return without synchronising.  "_host" functions take HOST pointers in the same
+ * layout, copy in, run, copy out and synchronise: they are the end-to-end path.
+ *
+ * Every function returns 0 on success, a CB200_E* code (< 0) for rejected arguments, or a
+ * positive cudaError_t.  There is NO CPU fallback: without a usable CUDA device every compute
+ * entry point fails with the CUDA error.
+ */
+#ifndef CASCADE_B200_H
+#define CASCADE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "cb_format.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB200_EINVAL (-1)     /* bad argument (unsupported L, negative sizes, ...) */
+#define CB200_EVALUATION (-2) /* valuation >= 0: acb_ode_solve_fuchs is undefined there
+                                 (reference src/fuchs_solver.c:108-136 never terminates) */
+#define CB200_ERANGE (-3)     /* an integer factor b(b-1)...(b-i+1) would overflow int64 */
+#define CB200_ENOMEM (-4)     /* workspace too small */
+
+/* elementwise operation codes */
+#define CB200_OP_ADD 0     /* acb_add */
+#define CB200_OP_SUB 1     /* acb_sub        reference src/fuchs_solver.c:119 */
+#define CB200_OP_MUL 2     /* acb_mul        reference src/fuchs_solver.c:118 */
+#define CB200_OP_DIV 3     /* acb_div        reference src/fuchs_solver.c:137 */
+#define CB200_OP_INV 4     /* acb_inv */
+#define CB200_OP_MUL_SI 16 /* acb_mul_fmpz / acb_mul_si   reference src/fuchs_solver.c:130,135 */
+#define CB200_OP_ADD_SI 17 /* acb_add_si     reference src/frobenius_solver.c:58 */
+
+const char *cb200_version(void);
+/* number of CUDA devices visible; < 0: CUDA error (negated) */
+int cb200_device_count(void);
+/* kernels launched by this library in this process so far (all entry points) */
+uint64_t cb200_kernel_launches(void);
+
+/* ---- workspace sizes (bytes of device memory the _dev entry points need) ---- */
+size_t cb200_fuchs_workspace_bytes(int L, int64_t batch, int64_t n, int shared_ode);
+size_t cb200_frobenius_workspace_bytes(int L, int64_t batch);
+size_t cb200_horner_workspace_bytes(int L, int64_t npts);
+size_t cb200_ew_workspace_bytes(int L, int64_t n);
+
+/* ---- acb_ode_solve_fuchs for a batch (reference src/fuchs_solver.c:96-145) ----
+ * ode : (order+1)*(degree+1) entries, row-major as acb_ode_coeff (reference src/acb_ode.h:21-22),
+ *       S = 2*batch, or S = 2 when shared_ode != 0 (one operator for the whole batch).
+ * res : n+1 entries, S = 2*batch.  On entry, entries 0 .. -valuation-1 hold the initial values
+ *       (reference doc/source/cascade.rst:14-16); entries -valuation .. n are written.
+ * valuation must be the value acb_ode_valuation (reference src/acb_ode.c:159-181) returns. */
+int cb200_fuchs_batch_dev(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
+                          const uint32_t *ode_mant, const cb_meta *ode_meta, int shared_ode,
+                          uint32_t *res_mant, cb_meta *res_meta, void *workspace,
+                          size_t workspace_bytes, void *stream);
+int cb200_fuchs_batch_host(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
+                           const uint32_t *ode_mant, const cb_meta *ode_meta, int shared_ode,
+                           uint32_t *res_mant, cb_meta *res_meta, int device);
+
+/* ---- _acb_ode_solve_frobenius, homogeneous case, M = 1 (reference src/frobenius_solver.c:72-121)
+ * rho : 1 entry, S = 2*batch or 2 (shared_rho).  res: n+1 entries, all written (g_0 = 1). */
+int cb200_frobenius1_batch_dev(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
+                               const uint32_t *ode_mant, const cb_meta *ode_meta, int shared_ode,
+                               const uint32_t *rho_mant, const cb_meta *rho_meta, int shared_rho,
+                               uint32_t *res_mant, cb_meta *res_meta, void *workspace,
+                               size_t workspace_bytes, void *stream);
+int cb200_frobenius1_batch_host(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
+                                const uint32_t *ode_mant, const cb_meta *ode_meta, int shared_ode,
+                                const uint32_t *rho_mant, const cb_meta *rho_meta, int shared_rho,
+                                uint32_t *res_mant, cb_meta *res_meta, int device);
+
+/* ---- Horner evaluation batched over points (acb_poly_evaluate inside
+ * acb_ode_solution_evaluate, reference src/acb_ode_solution.c:40,45; and the first `nder`
+ * coefficients of acb_poly_taylor_shift, reference src/fuchs_solver.c:159).
+ * f : len entries, S = 2 (shared_f) or 2*npts.  pts: 1 entry, S = 2*npts.
+ * out : nder entries, S = 2*npts; out[k] = f^(k)(pt)/k!.  1 <= nder <= 4. */
+int cb200_horner_batch_dev(int L, int64_t len, int64_t npts, int nder, const uint32_t *f_mant,
+                           const cb_meta *f_meta, int shared_f, const uint32_t *pts_mant,
+                           const cb_meta *pts_meta, uint32_t *out_mant, cb_meta *out_meta,
+                           void *workspace, size_t workspace_bytes, void *stream);
+int cb200_horner_batch_host(int L, int64_t len, int64_t npts, int nder, const uint32_t *f_mant,
+                            const cb_meta *f_meta, int shared_f, const uint32_t *pts_mant,
+                            const cb_meta *pts_meta, uint32_t *out_mant, cb_meta *out_meta,
+                            int device);
+
+/* ---- elementwise ball operations over n complex balls (1 entry, S = 2*n each); k: n integers
+ * for the *_SI ops (device pointer in _dev, may be NULL otherwise); y ignored for INV/_SI. */
+int cb200_ew_dev(int op, int L, int64_t n, uint32_t *z_mant, cb_meta *z_meta, const uint32_t *x_mant,
+                 const cb_meta *x_meta, const uint32_t *y_mant, const cb_meta *y_meta,
+                 const int64_t *k, void *workspace, size_t workspace_bytes, void *stream);
+int cb200_ew_host(int op, int L, int64_t n, uint32_t *z_mant, cb_meta *z_meta, const uint32_t *x_mant,
+                  const cb_meta *x_meta, const uint32_t *y_mant, const cb_meta *y_meta,
+                  const int64_t *k, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,188 @@
+"""Shared parity cases: each takes a driver (host-sim or GPU) and compares with the oracle.
+
+The bar is BIT-EXACT agreement of every mantissa limb, exponent, flag and radius word.
+"""
+from __future__ import annotations
+
+from fractions import Fraction as F
+
+import numpy as np
+
+from cascade_b200 import api
+from cascade_b200.format import FLAG_NAN, FLAG_ZERO, Balls, from_complex, random_balls
+
+
+def assert_same(a: Balls, b: Balls, what: str):
+    bm = np.nonzero((a.mant != b.mant).any(axis=1))[0]
+    bt = np.nonzero((a.meta != b.meta).any(axis=1))[0]
+    assert len(bm) == 0 and len(bt) == 0, (
+        f"{what}: {len(bm)} mantissa and {len(bt)} meta slots differ "
+        f"(first: slot {(list(bm) + list(bt))[0]}: oracle meta {a.meta[(list(bm) + list(bt))[0]]} "
+        f"vs {b.meta[(list(bm) + list(bt))[0]]})")
+
+
+def adversarial_pair(rng, L: int, n: int):
+    """2n slots each: limb-boundary exponent gaps, exact and near cancellation, zeros, all-ones
+    mantissas, short (integer-like) mantissas, radii from 1 ulp to huge."""
+    x = random_balls(rng, 2 * n, L, -2, 2, "zero", short_frac=0.3)
+    y = random_balls(rng, 2 * n, L, -2, 2, "zero", short_frac=0.3)
+    gaps = rng.choice([0, 1, 2, 30, 31, 32, 33, 34, 63, 64, 65, 32 * L - 1, 32 * L, 32 * L + 1, 32 * L + 31,
+                       32 * L + 32, 32 * L + 33, 64 * L, 64 * L + 40, 64 * L + 64, 64 * L + 65, 64 * L + 100,
+                       5000], size=2 * n)
+    y.meta[:, 0] = x.meta[:, 0] - gaps * rng.choice([1, -1], size=2 * n)
+    for s in range(0, 2 * n, 5):
+        y.mant[s] = x.mant[s]
+        y.meta[s, 0] = x.meta[s, 0]
+        mode = rng.integers(0, 4)
+        if mode == 1:
+            y.mant[s, 0] ^= np.uint32(1)
+        if mode == 2:
+            y.mant[s, rng.integers(0, L)] ^= np.uint32(1 << int(rng.integers(0, 31)))
+        if mode == 3:
+            y.mant[s, : L // 2] = 0
+    for s in range(3, 2 * n, 17):
+        x.mant[s] = 0
+        x.meta[s] = (0, FLAG_ZERO, 0, 0)
+    for s in range(7, 2 * n, 23):
+        y.mant[s] = 0
+        y.meta[s] = (0, FLAG_ZERO, 0, 0)
+    for s in range(11, 2 * n, 29):
+        x.mant[s] = 0xFFFFFFFF
+    r = rng.random(2 * n) < 0.5
+    for b in (x, y):
+        idx = np.nonzero(r & ((b.meta[:, 1] & FLAG_ZERO) == 0))[0]
+        b.meta[idx, 2] = rng.integers(1 << 29, 1 << 30, size=len(idx))
+        b.meta[idx, 3] = b.meta[idx, 0] - rng.integers(1, 40 * L, size=len(idx))
+    return x, y
+
+
+def case_elementwise(oracle, drv, L: int, n: int, seed: int):
+    rng = np.random.default_rng(seed)
+    x, y = adversarial_pair(rng, L, n)
+    for op, name in ((0, "add"), (1, "sub"), (2, "mul"), (3, "div"), (4, "inv")):
+        zo = oracle.ew_binary(op, x, y)
+        zs = api.ew(op, x, None if op == 4 else y, driver=drv)
+        assert_same(zo, zs, f"{name} L={L}")
+    k = rng.integers(-2**62, 2**62, size=n)
+    k[:10] = [0, 1, -1, 2, 3, 2**62, -2**62, 5, 7, 10]
+    k[10:40] = rng.integers(-100, 100, size=min(30, n - 10))
+    for op, name in ((16, "mul_si"), (17, "add_si")):
+        assert_same(oracle.ew_scalar_si(op, x, k), api.ew(op, x, k=k, driver=drv), f"{name} L={L}")
+
+
+def case_readme_kat(oracle, drv):
+    """reference README.md:43-47,72-77: legendre(4), c0 = 0.375, 5 terms at 1024 bits."""
+    L = 32
+    ode = oracle.example("legendre", L, 4)
+    init = from_complex([F(3, 8), 0], L)
+    res = api.acb_ode_solve_fuchs_batch(ode, init, 2, 2, 5, 1, True, driver=drv)
+    assert [res.mid(2 * i) for i in range(6)] == [F(3, 8), 0, F(-15, 4), 0, F(35, 8), 0]
+    assert all(res.mid(2 * i + 1) == 0 for i in range(6))
+    rc, ro = oracle.fuchs_batch(2, 2, 5, ode, init, 1, True)
+    assert_same(ro, res, "README KAT")
+
+
+def case_fuchs_random(oracle, drv, L: int, seed: int, trials: int = 4, batch: int = 3):
+    """reference tests/fuchs.c:18-41: random operator (degree 3..9, order 2..degree-1), random
+    initial values, n = order + randint(32); parity with the oracle AND the reference's own
+    acceptance test acb_ode_solves (residual contains zero)."""
+    rng = np.random.default_rng(seed)
+    for _ in range(trials):
+        degree = 3 + int(rng.integers(0, 7))
+        order = 2 + int(rng.integers(0, degree - 2))
+        ne = (order + 1) * (degree + 1)
+        ode = random_balls(rng, batch * ne * 2, L, -4, 4, "ulp", short_frac=0.2)
+        n = order + int(rng.integers(0, 32))
+        init = random_balls(rng, batch * order * 2, L, -3, 3, "ulp")
+        rc, ro = oracle.fuchs_batch(order, degree, n, ode, init, batch, False)
+        assert rc == 0
+        rs = api.acb_ode_solve_fuchs_batch(ode, init, order, degree, n, batch, False, driver=drv)
+        assert_same(ro, rs, f"fuchs L={L} order={order} degree={degree} n={n}")
+        for i in range(batch):
+            assert oracle.ode_solves(order, degree, ode[i * ne * 2:(i + 1) * ne * 2],
+                                     rs[i * (n + 1) * 2:(i + 1) * (n + 1) * 2], n - order)
+
+
+def bessel_shifted(oracle, rng, L: int):
+    """BASELINE config 2's operator: Bessel with complex nu, shifted to a complex ordinary point
+    (acb_ode_bessel + acb_ode_shift, reference src/examples.c:13-22, src/acb_ode.c:124-135)."""
+    nu = random_balls(rng, 2, L, 0, 0, "zero")
+    ode0 = oracle.example("bessel", L, 0, nu)
+    a = random_balls(rng, 2, L, 0, 1, "zero")
+    return oracle.ode_shift(2, 2, ode0, a)
+
+
+def case_fuchs_bessel_shared(oracle, drv, L: int, seed: int, n: int, batch: int):
+    rng = np.random.default_rng(seed)
+    ode = bessel_shifted(oracle, rng, L)
+    assert api.acb_ode_valuation(ode, 2, 2) == -2
+    init = random_balls(rng, batch * 2 * 2, L, -1, 0, "zero")
+    rc, ro = oracle.fuchs_batch(2, 2, n, ode, init, batch, True)
+    rs = api.acb_ode_solve_fuchs_batch(ode, init, 2, 2, n, batch, True, driver=drv)
+    assert_same(ro, rs, f"bessel shared L={L}")
+
+
+def case_fuchs_hypgeom(oracle, drv, L: int, seed: int):
+    """valuation -1 (regular singular point at 0) with a shared operator; closed form
+    (a)_n (b)_n / ((c)_n n!) must lie inside every ball."""
+    a, b, c = F(1, 3), F(2, 5), F(7, 4)
+    ode = oracle.example("hypgeom", L, 0, from_complex([a, b, c], L))
+    # a, b, c are not dyadic: from_complex stored truncations with a radius, so use dyadic ones
+    a, b, c = F(3, 8), F(5, 16), F(7, 4)
+    ode = oracle.example("hypgeom", L, 0, from_complex([a, b, c], L))
+    init = from_complex([1], L)
+    n = 30
+    rs = api.acb_ode_solve_fuchs_batch(ode, init, 2, 2, n, 1, True, driver=drv)
+    rc, ro = oracle.fuchs_batch(2, 2, n, ode, init, 1, True)
+    assert_same(ro, rs, "hypgeom fuchs")
+    exact = [F(1)]
+    for k in range(n):
+        exact.append(exact[-1] * (a + k) * (b + k) / ((c + k) * (k + 1)))
+    for k in range(n + 1):
+        assert rs.contains(2 * k, exact[k]) and rs.contains(2 * k + 1, 0)
+
+
+def case_frobenius(oracle, drv, L: int, seed: int, n: int = 20, batch: int = 3):
+    """BASELINE config 3's path: hypgeom sweep, M = 1, rho = 0 and a generic rho."""
+    rng = np.random.default_rng(seed)
+    par = random_balls(rng, batch * 6, L, -1, 1, "zero")
+    odes = Balls.concat([oracle.example("hypgeom", L, 0, par[i * 6:(i + 1) * 6]) for i in range(batch)])
+    for rho in (Balls.zeros(batch * 2, L), random_balls(rng, batch * 2, L, -1, 1, "ulp")):
+        ro = oracle.frobenius1_batch(2, 2, n, odes, rho, batch, False)
+        rs = api.acb_ode_solve_frobenius1_batch(odes, rho, 2, 2, n, batch, False, False, driver=drv)
+        assert_same(ro, rs, f"frobenius L={L}")
+
+
+def case_frobenius_singleton(oracle, drv, L: int, seed: int, trials: int = 3):
+    """reference tests/singleton_frobenius.c:18-46: zero P[i][j] for j <= i, P[order][order] = 1,
+    rho = order - 1; the series shifted by rho must pass acb_ode_solves."""
+    rng = np.random.default_rng(seed)
+    for _ in range(trials):
+        degree = 3 + int(rng.integers(0, 7))
+        order = 2 + int(rng.integers(0, degree - 2))
+        ne = (order + 1) * (degree + 1)
+        ode = random_balls(rng, ne * 2, L, -4, 4, "ulp")
+        m = ode.mant.reshape(order + 1, degree + 1, 2, L)
+        t = ode.meta.reshape(order + 1, degree + 1, 2, 4)
+        for i in range(order + 1):
+            m[i, : i + 1] = 0
+            t[i, : i + 1] = (0, FLAG_ZERO, 0, 0)
+        one = from_complex([1], L)
+        m[order, order] = one.mant
+        t[order, order] = one.meta
+        n = 2 + int(rng.integers(0, 30))
+        rho = from_complex([order - 1], L)
+        ro = oracle.frobenius1_batch(order, degree, n, ode, rho, 1, True)
+        rs = api.acb_ode_solve_frobenius1_batch(ode, rho, order, degree, n, 1, True, True, driver=drv)
+        assert_same(ro, rs, f"singleton frobenius L={L} order={order} degree={degree}")
+        shifted = Balls.concat([Balls.zeros(2 * (order - 1), L), rs])
+        assert oracle.ode_solves(order, degree, ode, shifted, n - 1)
+
+
+def case_horner(oracle, drv, L: int, seed: int, length: int = 40, npts: int = 9):
+    rng = np.random.default_rng(seed)
+    f = random_balls(rng, 2 * length, L, -3, 3, "ulp")
+    pts = random_balls(rng, 2 * npts, L, -2, 0, "zero")
+    for nder in (1, 2, 3):
+        assert_same(oracle.horner_batch(f, pts, nder), api.acb_poly_evaluate_batch(f, pts, nder, driver=drv),
+                    f"horner L={L} nder={nder}")

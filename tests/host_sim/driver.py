@@ -1,0 +1,56 @@
+"""TEST INFRASTRUCTURE: drives tests/host_sim/libcbsim.so (the device thread bodies compiled for
+the host) through the same driver interface as cascade_b200.api.HostBufferDriver."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libcbsim.so")
+_SRC = os.path.join(_HERE, "host_sim.cpp")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_vp = C.c_void_p
+_lib = None
+
+
+def build(force: bool = False) -> None:
+    deps = [_SRC] + [os.path.join(_HERE, "..", "..", "cascade_b200", "csrc", f)
+                     for f in ("cb_arith.cuh", "cb_solvers.cuh", "cb_mul.cuh")]
+    if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
+        return
+    subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                    "-o", _SO, _SRC], check=True)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.cbsim_fuchs_batch.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p]
+        L.cbsim_frobenius1_batch.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int, _u32p, _i32p]
+        L.cbsim_horner_batch.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int, _u32p, _i32p, C.c_int, _u32p, _i32p, _u32p, _i32p]
+        L.cbsim_ew.argtypes = [C.c_int, C.c_int, C.c_int64, _u32p, _i32p, _u32p, _i32p, _vp, _vp, _vp]
+        _lib = L
+    return _lib
+
+
+class SimDriver:
+    def fuchs(self, L, order, degree, valuation, n, batch, ode_m, ode_t, shared, res_m, res_t):
+        return lib().cbsim_fuchs_batch(L, order, degree, valuation, n, batch, ode_m, ode_t, int(shared), res_m, res_t)
+
+    def frobenius1(self, L, order, degree, valuation, n, batch, ode_m, ode_t, shared, rho_m, rho_t,
+                   shared_rho, res_m, res_t):
+        return lib().cbsim_frobenius1_batch(L, order, degree, valuation, n, batch, ode_m, ode_t, int(shared),
+                                            rho_m, rho_t, int(shared_rho), res_m, res_t)
+
+    def horner(self, L, length, npts, nder, f_m, f_t, shared_f, p_m, p_t, o_m, o_t):
+        return lib().cbsim_horner_batch(L, length, npts, nder, f_m, f_t, int(shared_f), p_m, p_t, o_m, o_t)
+
+    def ew(self, op, L, n, z_m, z_t, x_m, x_t, y_m, y_t, k):
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        return lib().cbsim_ew(op, L, n, z_m, z_t, x_m, x_t, vp(y_m), vp(y_t), vp(k))

@@ -1,0 +1,105 @@
+// host_sim.cpp -- TEST INFRASTRUCTURE.  Compiles the per-thread bodies of the CUDA kernels
+// (cascade_b200/csrc/cb_solvers.cuh) for the host and runs them one "thread" after another, so
+// that the device LOGIC can be checked against the oracle on a machine without a GPU.  It is
+// never linked into libcascade_b200.so and nothing in the product loads it.
+// Same array layout and arguments as the *_dev entry points of include/cascade_b200.h.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/cascade_b200.h"
+#include "../../cascade_b200/csrc/cb_solvers.cuh"
+
+using namespace cb;
+
+namespace {
+struct Tmp {
+    std::vector<uint32_t> m;
+    std::vector<Meta> t;
+    CArr arr(int L, int64_t entries, int64_t S) {
+        m.assign((size_t)entries * L * S, 0u);
+        t.assign((size_t)entries * S, Meta{0, F_ZERO, 0, 0});
+        return CArr{m.data(), t.data(), (size_t)S};
+    }
+};
+template <int L, class F>
+void run(int64_t count, F body) {
+    std::vector<uint32_t> s0(2 * L + 3), s1(2 * L + 3);
+    Scratch<1> S0{s0.data()}, S1{s1.data()};
+    for (int64_t i = 0; i < count; i++) body(i, S0, S1);
+}
+#define SIM_DISPATCH(L_, CALL)                                \
+    switch (L_) {                                             \
+        case 4: { constexpr int L = 4; CALL; } break;         \
+        case 32: { constexpr int L = 32; CALL; } break;       \
+        case 64: { constexpr int L = 64; CALL; } break;       \
+        case 128: { constexpr int L = 128; CALL; } break;     \
+        default: return CB200_EINVAL;                         \
+    }
+}  // namespace
+
+extern "C" {
+
+int cbsim_fuchs_batch(int L_, int order, int degree, int valuation, int64_t n, int64_t batch,
+                      const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
+                      uint32_t* res_mant, cb_meta* res_meta) {
+    if (valuation >= 0) return CB200_EVALUATION;
+    FuchsParams p;
+    p.order = order; p.degree = degree; p.valuation = valuation; p.n = n; p.batch = batch;
+    p.ode = CArr{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta),
+                 shared_ode ? (size_t)2 : (size_t)(2 * batch)};
+    p.res = CArr{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
+    Tmp tmp;
+    p.tmp = tmp.arr(L_, FUCHS_NTMP, 2 * batch);
+    SIM_DISPATCH(L_, run<L>(batch, [&](int64_t i, Scratch<1> a, Scratch<1> b) { fuchs_thread<L>(p, i, a, b); }));
+    return 0;
+}
+
+int cbsim_frobenius1_batch(int L_, int order, int degree, int valuation, int64_t n, int64_t batch,
+                           const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
+                           const uint32_t* rho_mant, const cb_meta* rho_meta, int shared_rho,
+                           uint32_t* res_mant, cb_meta* res_meta) {
+    FrobParams p;
+    p.order = order; p.degree = degree; p.valuation = valuation; p.n = n; p.batch = batch;
+    p.ode = CArr{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta),
+                 shared_ode ? (size_t)2 : (size_t)(2 * batch)};
+    p.rho = CArr{const_cast<uint32_t*>(rho_mant), (Meta*)const_cast<cb_meta*>(rho_meta),
+                 shared_rho ? (size_t)2 : (size_t)(2 * batch)};
+    p.res = CArr{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
+    Tmp tmp;
+    p.tmp = tmp.arr(L_, FROB_NTMP, 2 * batch);
+    SIM_DISPATCH(L_, run<L>(batch, [&](int64_t i, Scratch<1> a, Scratch<1> b) { frobenius1_thread<L>(p, i, a, b); }));
+    return 0;
+}
+
+int cbsim_horner_batch(int L_, int64_t len, int64_t npts, int nder, const uint32_t* f_mant,
+                       const cb_meta* f_meta, int shared_f, const uint32_t* pts_mant,
+                       const cb_meta* pts_meta, uint32_t* out_mant, cb_meta* out_meta) {
+    if (nder < 1 || nder > HORNER_MAXDER) return CB200_EINVAL;
+    HornerParams p;
+    p.nder = nder; p.len = len; p.npts = npts;
+    p.f = CArr{const_cast<uint32_t*>(f_mant), (Meta*)const_cast<cb_meta*>(f_meta),
+               shared_f ? (size_t)2 : (size_t)(2 * npts)};
+    p.pts = CArr{const_cast<uint32_t*>(pts_mant), (Meta*)const_cast<cb_meta*>(pts_meta), (size_t)(2 * npts)};
+    p.out = CArr{out_mant, (Meta*)out_meta, (size_t)(2 * npts)};
+    Tmp tmp;
+    p.tmp = tmp.arr(L_, 1, 2 * npts);
+    SIM_DISPATCH(L_, run<L>(npts, [&](int64_t i, Scratch<1> a, Scratch<1> b) { horner_thread<L>(p, i, a, b); }));
+    return 0;
+}
+
+int cbsim_ew(int op, int L_, int64_t n, uint32_t* z_mant, cb_meta* z_meta, const uint32_t* x_mant,
+             const cb_meta* x_meta, const uint32_t* y_mant, const cb_meta* y_meta, const int64_t* k) {
+    EwParams p;
+    p.op = op; p.n = n;
+    p.z = CArr{z_mant, (Meta*)z_meta, (size_t)(2 * n)};
+    p.x = CArr{const_cast<uint32_t*>(x_mant), (Meta*)const_cast<cb_meta*>(x_meta), (size_t)(2 * n)};
+    p.y = y_mant ? CArr{const_cast<uint32_t*>(y_mant), (Meta*)const_cast<cb_meta*>(y_meta), (size_t)(2 * n)} : p.x;
+    p.k = k;
+    Tmp tmp;
+    p.tmp = tmp.arr(L_, 2, 2 * n);
+    SIM_DISPATCH(L_, run<L>(n, [&](int64_t i, Scratch<1> a, Scratch<1> b) { ew_thread<L>(p, i, a, b); }));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,42 @@
+"""CPU checks of the DEVICE code's logic: the per-thread kernel bodies compiled for the host
+(tests/host_sim) against the oracle, bit for bit.  No GPU needed; the GPU runs the same cases
+through the C ABI in tests/test_gpu_parity.py."""
+import pytest
+
+from tests import cases
+
+
+@pytest.mark.parametrize("L,n", [(4, 300), (32, 200), (64, 40), (128, 24)])
+def test_elementwise(oracle, sim_driver, L, n):
+    cases.case_elementwise(oracle, sim_driver, L, n, seed=100 + L)
+
+
+def test_readme_kat(oracle, sim_driver):
+    cases.case_readme_kat(oracle, sim_driver)
+
+
+@pytest.mark.parametrize("L", [4, 32])
+def test_fuchs_random(oracle, sim_driver, L):
+    cases.case_fuchs_random(oracle, sim_driver, L, seed=7 + L)
+
+
+def test_fuchs_bessel_shared(oracle, sim_driver):
+    cases.case_fuchs_bessel_shared(oracle, sim_driver, 32, seed=5, n=40, batch=3)
+
+
+def test_fuchs_hypgeom(oracle, sim_driver):
+    cases.case_fuchs_hypgeom(oracle, sim_driver, 32, seed=1)
+
+
+@pytest.mark.parametrize("L", [4, 32, 128])
+def test_frobenius(oracle, sim_driver, L):
+    cases.case_frobenius(oracle, sim_driver, L, seed=9, n=12 if L == 128 else 20, batch=2)
+
+
+def test_frobenius_singleton(oracle, sim_driver):
+    cases.case_frobenius_singleton(oracle, sim_driver, 4, seed=21)
+
+
+@pytest.mark.parametrize("L", [4, 64])
+def test_horner(oracle, sim_driver, L):
+    cases.case_horner(oracle, sim_driver, L, seed=13)

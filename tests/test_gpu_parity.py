@@ -1,0 +1,44 @@
+"""GPU parity tests proper: libcascade_b200.so through its C ABI (host buffers in and out)
+against the oracle, bit for bit, plus the reference's own acceptance properties."""
+import pytest
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("L,n", [(4, 1000), (32, 600), (64, 200), (128, 100)])
+def test_elementwise(oracle, gpu_driver, L, n):
+    cases.case_elementwise(oracle, gpu_driver, L, n, seed=200 + L)
+
+
+def test_readme_kat(oracle, gpu_driver):
+    cases.case_readme_kat(oracle, gpu_driver)
+
+
+@pytest.mark.parametrize("L", [4, 32, 64])
+def test_fuchs_random(oracle, gpu_driver, L):
+    cases.case_fuchs_random(oracle, gpu_driver, L, seed=17 + L, trials=5, batch=37)
+
+
+@pytest.mark.parametrize("L", [32, 64])
+def test_fuchs_bessel_shared(oracle, gpu_driver, L):
+    cases.case_fuchs_bessel_shared(oracle, gpu_driver, L, seed=5, n=60, batch=300)
+
+
+def test_fuchs_hypgeom(oracle, gpu_driver):
+    cases.case_fuchs_hypgeom(oracle, gpu_driver, 32, seed=1)
+
+
+@pytest.mark.parametrize("L", [4, 32, 128])
+def test_frobenius(oracle, gpu_driver, L):
+    cases.case_frobenius(oracle, gpu_driver, L, seed=9, n=16 if L == 128 else 24, batch=70)
+
+
+def test_frobenius_singleton(oracle, gpu_driver):
+    cases.case_frobenius_singleton(oracle, gpu_driver, 32, seed=21)
+
+
+@pytest.mark.parametrize("L", [4, 32, 64])
+def test_horner(oracle, gpu_driver, L):
+    cases.case_horner(oracle, gpu_driver, L, seed=13, length=60, npts=333)
