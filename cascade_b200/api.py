@@ -157,3 +157,89 @@ def ew(op: int, x: Balls, y: Balls | None = None, k=None, driver=None) -> Balls:
     z_t = np.zeros((1, 2 * n, 4), np.int32)
     _lib.check(drv.ew(op, L, n, z_m, z_t, x_m, x_t, y_m, y_t, kk), "ew")
     return unpack_entries(L, z_m, z_t)
+
+
+# ---------------------------------------------------------------- example operators (src/examples.c)
+def _neg(b: Balls) -> Balls:
+    out = b.copy()
+    nz = (out.meta[:, 1] & (FLAG_ZERO | FLAG_NAN)) == 0
+    out.meta[nz, 1] ^= 1
+    return out
+
+
+def _set_entry(ode: Balls, batch: int, ne: int, entry: int, val: Balls) -> None:
+    L = ode.L
+    ode.mant.reshape(batch, ne, 2, L)[:, entry] = val.mant.reshape(batch, 2, L)
+    ode.meta.reshape(batch, ne, 2, 4)[:, entry] = val.meta.reshape(batch, 2, 4)
+
+
+def _const(values, L: int) -> Balls:
+    from .format import from_complex
+    return from_complex(list(values), L)
+
+
+def acb_ode_legendre_batch(ns, L: int) -> Balls:
+    """``acb_ode_legendre(ODE, n)`` for every n in ``ns`` (reference src/examples.c:3-11):
+    (1 - z^2) y'' - 2 z y' + n(n+1) y.  Exact small integers, no arithmetic needed."""
+    ns = [int(n) for n in ns]
+    batch = len(ns)
+    ode = Balls.zeros(batch * 9 * 2, L)
+    _set_entry(ode, batch, 9, 0 * 3 + 0, _const([n * (n + 1) for n in ns], L))
+    _set_entry(ode, batch, 9, 1 * 3 + 1, _const([-2] * batch, L))
+    _set_entry(ode, batch, 9, 2 * 3 + 0, _const([1] * batch, L))
+    _set_entry(ode, batch, 9, 2 * 3 + 2, _const([-1] * batch, L))
+    return ode
+
+
+def acb_ode_bessel_batch(nu: Balls, driver=None) -> tuple[Balls, Balls]:
+    """``acb_ode_bessel(ODE, nu, bits)`` for a batch of nu (reference src/examples.c:13-22).
+    Returns (ode, nu_squared): the reference overwrites its ``nu`` argument with nu^2 (:20)."""
+    L, batch = nu.L, nu.n_slots // 2
+    nu2 = ew(OP_MUL, nu, nu, driver=driver)
+    ode = Balls.zeros(batch * 9 * 2, L)
+    one = _const([1] * batch, L)
+    _set_entry(ode, batch, 9, 2 * 3 + 2, one)
+    _set_entry(ode, batch, 9, 1 * 3 + 1, one)
+    _set_entry(ode, batch, 9, 0 * 3 + 2, one)
+    _set_entry(ode, batch, 9, 0 * 3 + 0, _neg(nu2))
+    return ode, nu2
+
+
+def acb_ode_hypgeom_batch(a: Balls, b: Balls, c: Balls, driver=None) -> Balls:
+    """``acb_ode_hypgeom(ODE, a, b, c, bits)`` for a batch (reference src/examples.c:24-44):
+    z(1-z) y'' + (c - (a+b+1) z) y' - a b y."""
+    L, batch = a.L, a.n_slots // 2
+    ode = Balls.zeros(batch * 9 * 2, L)
+    _set_entry(ode, batch, 9, 2 * 3 + 1, _const([1] * batch, L))
+    _set_entry(ode, batch, 9, 2 * 3 + 2, _const([-1] * batch, L))
+    _set_entry(ode, batch, 9, 1 * 3 + 0, c)
+    t = ew(OP_ADD, _const([1] * batch, L), a, driver=driver)
+    t = ew(OP_ADD, t, b, driver=driver)
+    _set_entry(ode, batch, 9, 1 * 3 + 1, _neg(t))
+    _set_entry(ode, batch, 9, 0 * 3 + 0, _neg(ew(OP_MUL, a, b, driver=driver)))
+    return ode
+
+
+def acb_ode_shift_batch(ode: Balls, a: Balls, order: int, degree: int, driver=None) -> Balls:
+    """``acb_ode_shift(out, in, a, bits)`` for a batch (reference src/acb_ode.c:124-135): every row
+    p_i(z) becomes p_i(z + a) by the Horner Taylor shift  p[j] += p[j+1] * a."""
+    L, batch = ode.L, a.n_slots // 2
+    ne = (order + 1) * (degree + 1)
+    out = ode.copy()
+    if degree == 0:
+        return out
+    m = out.mant.reshape(batch, order + 1, degree + 1, 2, L)
+    t = out.meta.reshape(batch, order + 1, degree + 1, 2, 4)
+    # all rows of all instances advance together: one MUL and one ADD launch per (i, j) step
+    rows = (order + 1) * batch
+    arow = Balls(L, np.repeat(a.mant.reshape(batch, 1, 2, L), order + 1, axis=1).reshape(-1, L),
+                 np.repeat(a.meta.reshape(batch, 1, 2, 4), order + 1, axis=1).reshape(-1, 4))
+    n = degree + 1
+    for i in range(n - 2, -1, -1):
+        for j in range(i, n - 1):
+            pj1 = Balls(L, m[:, :, j + 1].reshape(rows * 2, L).copy(), t[:, :, j + 1].reshape(rows * 2, 4).copy())
+            pj = Balls(L, m[:, :, j].reshape(rows * 2, L).copy(), t[:, :, j].reshape(rows * 2, 4).copy())
+            s = ew(OP_ADD, pj, ew(OP_MUL, pj1, arow, driver=driver), driver=driver)
+            m[:, :, j] = s.mant.reshape(batch, order + 1, 2, L)
+            t[:, :, j] = s.meta.reshape(batch, order + 1, 2, 4)
+    return out
