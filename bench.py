@@ -182,7 +182,7 @@ def main():
     d_init_t = torch.from_numpy(init_t).to(dev)
     d_res_m = torch.empty((n + 1, L, S), dtype=torch.int32, device=dev)
     d_res_t = torch.empty((n + 1, S, 4), dtype=torch.int32, device=dev)
-    ws_bytes = lib.cb200_fuchs_workspace_bytes(L, batch, n, 1)
+    ws_bytes = lib.cb200_fuchs_workspace_bytes(L, 2, 2, -2, n, batch, 1)
     d_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     p = lambda t: C.c_void_p(t.data_ptr())
     stream = torch.cuda.current_stream(dev)
@@ -251,7 +251,7 @@ def main():
         h_res_t = torch.empty((2, n + 1, St, 4), dtype=torch.int32).pin_memory()
         t_res_m = [torch.empty((n + 1, L, St), dtype=torch.int32, device=dev) for _ in range(2)]
         t_res_t = [torch.empty((n + 1, St, 4), dtype=torch.int32, device=dev) for _ in range(2)]
-        t_ws_bytes = lib.cb200_fuchs_workspace_bytes(L, tile, n, 1)
+        t_ws_bytes = lib.cb200_fuchs_workspace_bytes(L, 2, 2, -2, n, tile, 1)
         t_ws = [torch.empty(t_ws_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
         streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
         h2d = 2 * L * St * 4 + 2 * St * 16

@@ -50,7 +50,7 @@ def lib() -> C.CDLL:
     L.cb200_kernel_launches.restype = C.c_uint64
     for name in ("cb200_fuchs_workspace_bytes",):
         getattr(L, name).restype = C.c_size_t
-        getattr(L, name).argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int]
+        getattr(L, name).argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int]
     for name in ("cb200_frobenius_workspace_bytes", "cb200_horner_workspace_bytes", "cb200_ew_workspace_bytes"):
         getattr(L, name).restype = C.c_size_t
         getattr(L, name).argtypes = [C.c_int, C.c_int64]

@@ -74,8 +74,13 @@ int cb200_device_count(void) {
 
 uint64_t cb200_kernel_launches(void) { return g_launches.load(); }
 
-size_t cb200_fuchs_workspace_bytes(int L, int64_t batch, int64_t, int) {
-    return carve_bytes(L, FUCHS_NTMP, 2 * batch);
+size_t cb200_fuchs_workspace_bytes(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
+                                   int shared_ode) {
+    (void)order;
+    if (!shared_ode || valuation >= 0) return carve_bytes(L, FUCHS_NTMP, 2 * batch);
+    int64_t rows = n + 1 + valuation, W = degree - valuation;
+    if (rows < 0) rows = 0;
+    return carve_bytes(L, rows * (W + 2), 2) + carve_bytes(L, 2, 2 * rows) + align256(sizeof(int32_t) * (rows + 1));
 }
 size_t cb200_frobenius_workspace_bytes(int L, int64_t batch) { return carve_bytes(L, FROB_NTMP, 2 * batch); }
 size_t cb200_horner_workspace_bytes(int L, int64_t npts) { return carve_bytes(L, 1, 2 * npts); }
@@ -88,7 +93,38 @@ int cb200_fuchs_batch_dev(int L_, int order, int degree, int valuation, int64_t 
     if (!supported_L(L_) || order < 1 || degree < 0 || batch < 0 || n < 0) return CB200_EINVAL;
     if (valuation >= 0) return CB200_EVALUATION;
     if (!factor_fits(n, order)) return CB200_ERANGE;
-    if (workspace_bytes < cb200_fuchs_workspace_bytes(L_, batch, n, shared_ode)) return CB200_ENOMEM;
+    if (workspace_bytes < cb200_fuchs_workspace_bytes(L_, order, degree, valuation, n, batch, shared_ode))
+        return CB200_ENOMEM;
+    if (n < -valuation) return 0;  // nothing to compute
+    if (shared_ode) {
+        // one operator for the whole batch: multipliers/divisors once per coefficient index, then
+        // the per-instance recurrence with shared-memory resident accumulators
+        int64_t rows = n + 1 + valuation, W = degree - valuation;
+        char* w = (char*)workspace;
+        FuchsTableParams tp;
+        tp.order = order;
+        tp.degree = degree;
+        tp.valuation = valuation;
+        tp.n = n;
+        tp.ode = CArr{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta), (size_t)2};
+        tp.tbl = carve(w, L_, rows * (W + 2), 2);
+        tp.tmp = carve(w, L_, 2, 2 * rows);
+        tp.kind = (int32_t*)w;
+        g_launches.fetch_add(1);
+        int rc = table_for(L_)->fuchs_table(tp, (cudaStream_t)stream);
+        if (rc) return rc;
+        FuchsSharedParams sp;
+        sp.order = order;
+        sp.degree = degree;
+        sp.valuation = valuation;
+        sp.n = n;
+        sp.batch = batch;
+        sp.tbl = tp.tbl;
+        sp.res = CArr{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
+        sp.kind = tp.kind;
+        g_launches.fetch_add(batch > 0);
+        return table_for(L_)->fuchs_shared(sp, (cudaStream_t)stream);
+    }
     FuchsParams p;
     p.order = order;
     p.degree = degree;
@@ -185,7 +221,7 @@ int cb200_fuchs_batch_host(int L, int order, int degree, int valuation, int64_t 
     CK(cudaSetDevice(device));
     int64_t So = shared_ode ? 2 : 2 * batch, S = 2 * batch, ne = (int64_t)(order + 1) * (degree + 1);
     DevBuf om, ot, rm, rt, ws;
-    size_t wsb = cb200_fuchs_workspace_bytes(L, batch, n, shared_ode);
+    size_t wsb = cb200_fuchs_workspace_bytes(L, order, degree, valuation, n, batch, shared_ode);
     CK(om.alloc(arr_mant_bytes(L, ne, So)));
     CK(ot.alloc(arr_meta_bytes(ne, So)));
     CK(rm.alloc(arr_mant_bytes(L, n + 1, S)));

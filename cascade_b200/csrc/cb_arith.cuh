@@ -92,10 +92,12 @@ struct Scratch {
     __device__ __forceinline__ void st(int k, uint32_t v) const {
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(a + (uint32_t)(k * (STRIDE * 4))), "r"(v));
     }
+    __device__ __forceinline__ uint32_t a_or_p() const { return a; }
 #else
     uint32_t* p;
     uint32_t ld(int k) const { return p[(ptrdiff_t)k * STRIDE]; }
     void st(int k, uint32_t v) const { p[(ptrdiff_t)k * STRIDE] = v; }
+    const uint32_t* a_or_p() const { return p; }
 #endif
 };
 
@@ -210,10 +212,12 @@ CB_HD bool is_exact_zero(const Meta& t) { return (t.flags & F_ZERO) && t.rman ==
 struct RRef {
     const uint32_t* m;
     size_t stride;
+    CB_HD uint32_t ld(int j) const { return m[(size_t)j * stride]; }
 };
 struct WRef {
     uint32_t* m;
     size_t stride;
+    CB_HD void st(int j, uint32_t v) const { m[(size_t)j * stride] = v; }
 };
 
 // Rounded midpoint result description produced by extract()
@@ -228,13 +232,13 @@ struct Rounded {
 // R[0..hi] (scratch words, R[hi] != 0 unless the value is zero) is an unsigned integer V whose
 // bit 0 has weight 2^frame.  Writes the top 32 L bits of V to dst (truncation), returns exponent
 // and the exact inexact flag.  lo = index of the lowest nonzero word (or a value > hi if V == 0).
-template <int L, class SCR>
-CB_HD Rounded extract(WRef dst, SCR R, int hi, int lo, bool sticky, int64_t frame) {
+template <int L, class DST, class SCR>
+CB_HD Rounded extract(DST dst, SCR R, int hi, int lo, bool sticky, int64_t frame) {
     Rounded out;
     uint32_t top = (hi >= 0) ? R.ld(hi) : 0u;
     if (hi < 0 || top == 0) {
 #pragma unroll
-        for (int j = 0; j < L; j++) dst.m[j * dst.stride] = 0u;
+        for (int j = 0; j < L; j++) dst.st(j, 0u);
         out.exp = 0;
         out.zero = true;
         out.inexact = sticky;  // cannot happen with sticky (see align_add), kept for safety
@@ -251,7 +255,7 @@ CB_HD Rounded extract(WRef dst, SCR R, int hi, int lo, bool sticky, int64_t fram
     for (int j = 0; j < L; j++) {
         int idx = q + j + 1;
         uint32_t nxt = (idx >= 0 && idx <= hi) ? R.ld(idx) : 0u;
-        dst.m[j * dst.stride] = shr_pair(cur, nxt, r);
+        dst.st(j, shr_pair(cur, nxt, r));
         cur = nxt;
     }
     int64_t e = frame + bl;
@@ -267,18 +271,24 @@ CB_HD Rounded extract(WRef dst, SCR R, int hi, int lo, bool sticky, int64_t fram
 // Computes |R| = | sa*a + sb*b | exactly as far as truncation to 32 L bits can tell, into the
 // scratch column of the larger operand (words 0..N+1), and rounds it into dst.
 // Returns the rounded description and the result sign through *neg.
-template <int L, int N, class SCR>
-CB_HD Rounded align_add(WRef dst, SCR A, SCR B, int64_t ea, int64_t eb, bool nega, bool negb,
-                        bool za, bool zb, bool* neg) {
+// TO_SMALL: the rounded result is written to words 0..L-1 of the SMALLER operand's column (free
+// once the aligned sum has been formed) and *where reports that column; dst is then unused.
+template <int L, int N, bool TO_SMALL = false, class DST, class SCR>
+CB_HD Rounded align_add(DST dst, SCR A, SCR B, int64_t ea, int64_t eb, bool nega, bool negb,
+                        bool za, bool zb, bool* neg, SCR* where = nullptr) {
     // pick "big": the nonzero one, else the larger exponent (ties: A)
     bool swap = za ? true : (zb ? false : (eb > ea));
     SCR big = swap ? B : A, small = swap ? A : B;
     int64_t ebig = swap ? eb : ea, esm = swap ? ea : eb;
     bool nbig = swap ? negb : nega, nsm = swap ? nega : negb;
     bool zbig = swap ? zb : za, zsm = swap ? za : zb;
+    if constexpr (TO_SMALL) *where = small;
     if (zbig) {  // both zero
         *neg = false;
-        return extract<L>(dst, big, -1, 0, false, 0);
+        if constexpr (TO_SMALL)
+            return extract<L>(small, big, -1, 0, false, 0);
+        else
+            return extract<L>(dst, big, -1, 0, false, 0);
     }
     int64_t d64 = zsm ? 0 : (ebig - esm);
     bool far = d64 > 32 * (N + 2);  // small lies entirely below the window
@@ -357,19 +367,22 @@ CB_HD Rounded align_add(WRef dst, SCR A, SCR B, int64_t ea, int64_t eb, bool neg
         }
     }
     *neg = rneg;
-    return extract<L>(dst, big, hi, lo, sticky, ebig - 32 * (int64_t)N - 32);
+    if constexpr (TO_SMALL)
+        return extract<L>(small, big, hi, lo, sticky, ebig - 32 * (int64_t)N - 32);
+    else
+        return extract<L>(dst, big, hi, lo, sticky, ebig - 32 * (int64_t)N - 32);
 }
 
 // ---------------------------------------------------------------- products into scratch
 // P[0..2L) = x * y (exact), limbs read from memory
-template <int L, class SCR>
-CB_HD void product(SCR P, RRef x, RRef y) {
+template <int L, class SCR, class XS, class YS>
+CB_HD void product(SCR P, XS x, YS y) {
     if constexpr (L <= 32) {
         uint32_t a[L], b[L], r[2 * L];
 #pragma unroll
-        for (int j = 0; j < L; j++) a[j] = x.m[j * x.stride];
+        for (int j = 0; j < L; j++) a[j] = x.ld(j);
 #pragma unroll
-        for (int j = 0; j < L; j++) b[j] = y.m[j * y.stride];
+        for (int j = 0; j < L; j++) b[j] = y.ld(j);
         mul_full<L>(r, a, b);
 #pragma unroll
         for (int k = 0; k < 2 * L; k++) P.st(k, r[k]);
@@ -381,12 +394,12 @@ CB_HD void product(SCR P, RRef x, RRef y) {
         for (int bi = 0; bi < NB; bi++) {
             uint32_t a[32];
 #pragma unroll
-            for (int j = 0; j < 32; j++) a[j] = x.m[(32 * bi + j) * x.stride];
+            for (int j = 0; j < 32; j++) a[j] = x.ld(32 * bi + j);
 #pragma unroll 1
             for (int bj = 0; bj < NB; bj++) {
                 uint32_t b[32], r[64];
 #pragma unroll
-                for (int j = 0; j < 32; j++) b[j] = y.m[(32 * bj + j) * y.stride];
+                for (int j = 0; j < 32; j++) b[j] = y.ld(32 * bj + j);
                 mul_full<32>(r, a, b);
                 int off = 32 * (bi + bj);
                 uint32_t c = 0u;
@@ -408,13 +421,15 @@ CB_HD void product(SCR P, RRef x, RRef y) {
 }
 
 // one real operand: where its limbs are and its meta record
-struct Opd {
-    RRef r;
+template <class SRC>
+struct OpdT {
+    SRC r;  // anything with ld(j): RRef (global memory) or a Scratch column
     Meta t;
 };
-template <int L>
-CB_HD uint32_t top_limb(const Opd& o) {
-    return o.r.m[(L - 1) * o.r.stride];
+using Opd = OpdT<RRef>;
+template <int L, class SRC>
+CB_HD uint32_t top_limb(const OpdT<SRC>& o) {
+    return o.r.ld(L - 1);
 }
 
 template <int L>
@@ -433,16 +448,17 @@ CB_HD Meta finish(const Rounded& rr, bool neg, Mag rad) {
     t.rexp = rad.man ? rad.exp : 0;
     return t;
 }
-template <int L>
-CB_HD void store_nan(WRef dst) {
+template <int L, class DST>
+CB_HD void store_nan(DST dst) {
 #pragma unroll
-    for (int j = 0; j < L; j++) dst.m[j * dst.stride] = 0u;
+    for (int j = 0; j < L; j++) dst.st(j, 0u);
 }
 
 // ---------------------------------------------------------------- arb level
 // dst = x1*y1 + (neg2 ? -1 : 1) * x2*y2, one rounding.  S0/S1: two scratch columns of 2L+2 words.
-template <int L, class SCR>
-CB_NOINLINE Meta arb_fdot2(WRef dst, Opd x1, Opd y1, Opd x2, Opd y2, bool neg2, SCR S0, SCR S1) {
+template <int L, class SCR, class XS = RRef, class YS = RRef, class DST = WRef>
+CB_NOINLINE Meta arb_fdot2(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2, OpdT<YS> y2, bool neg2, SCR S0,
+                           SCR S1) {
     bool nan = is_nan(x1.t) || is_nan(y1.t) || is_nan(x2.t) || is_nan(y2.t);
     bool z1 = is_zero_mid(x1.t) || is_zero_mid(y1.t);
     bool z2 = is_zero_mid(x2.t) || is_zero_mid(y2.t);
@@ -469,14 +485,28 @@ CB_NOINLINE Meta arb_addsub(WRef dst, Opd x, Opd y, bool negy, SCR S0, SCR S1) {
     bool nan = is_nan(x.t) || is_nan(y.t);
     bool zx = is_zero_mid(x.t) || nan, zy = is_zero_mid(y.t) || nan;
 #pragma unroll
-    for (int j = 0; j < L; j++) S0.st(j, x.r.m[j * x.r.stride]);
+    for (int j = 0; j < L; j++) S0.st(j, x.r.ld(j));
 #pragma unroll
-    for (int j = 0; j < L; j++) S1.st(j, y.r.m[j * y.r.stride]);
+    for (int j = 0; j < L; j++) S1.st(j, y.r.ld(j));
     bool neg;
     Rounded rr = align_add<L, L>(dst, S0, S1, x.t.exp, y.t.exp, (x.t.flags & F_SIGN) != 0,
                                  ((y.t.flags & F_SIGN) != 0) != negy, zx, zy, &neg);
     if (nan) return meta_nan();
     return finish<L>(rr, neg, mag_add(mag_of(x.t), mag_of(y.t)));
+}
+
+// Column form used by the register/shared-memory resident recurrence: A and B are scratch columns
+// holding L-limb mantissas (words 0..L-1, room for L+2); the rounded x + (negb ? -b : b) lands in
+// words 0..L-1 of *where (the column of the smaller operand); the other column is left clobbered.
+template <int L, class SCR>
+CB_NOINLINE Meta arb_addsub_cols(SCR A, Meta ta, SCR B, Meta tb, bool negb, SCR* where) {
+    bool nan = is_nan(ta) || is_nan(tb);
+    bool zx = is_zero_mid(ta) || nan, zy = is_zero_mid(tb) || nan;
+    bool neg;
+    Rounded rr = align_add<L, L, true>(A, A, B, ta.exp, tb.exp, (ta.flags & F_SIGN) != 0,
+                                       ((tb.flags & F_SIGN) != 0) != negb, zx, zy, &neg, where);
+    if (nan) return meta_nan();
+    return finish<L>(rr, neg, mag_add(mag_of(ta), mag_of(tb)));
 }
 
 // dst = x * k, k a signed 64-bit integer (acb_mul_fmpz / acb_mul_si with a small integer)
@@ -501,7 +531,7 @@ CB_NOINLINE Meta arb_mul_si(WRef dst, Opd x, int64_t k, SCR S0) {
     int hi = -1, lo = 0x7FFFFFFF;
 #pragma unroll
     for (int j = 0; j < L + 2; j++) {
-        uint32_t xj = (j < L) ? x.r.m[j * x.r.stride] : 0u;
+        uint32_t xj = (j < L) ? x.r.ld(j) : 0u;
         uint64_t p0 = (uint64_t)xj * k0, p1 = (uint64_t)xj * k1;
         uint64_t t = (uint64_t)carry + (uint32_t)p0 + hi0_prev + lo1_prev + hi1_prev2;
         uint32_t v = z ? 0u : (uint32_t)t;
@@ -523,8 +553,8 @@ CB_NOINLINE Meta arb_mul_si(WRef dst, Opd x, int64_t k, SCR S0) {
 }
 
 // dst = x / y  (Knuth D on 32-bit limbs; numerator x * 2^(32L) in S0, divisor in S1)
-template <int L, class SCR>
-CB_NOINLINE Meta arb_div(WRef dst, Opd x, Opd y, SCR S0, SCR S1) {
+template <int L, class SCR, class XS = RRef, class YS = RRef, class DST = WRef>
+CB_NOINLINE Meta arb_div(DST dst, OpdT<XS> x, OpdT<YS> y, SCR S0, SCR S1) {
     bool nan = is_nan(x.t) || is_nan(y.t) || is_zero_mid(y.t);
     uint32_t ytop = top_limb<L>(y), xtop = top_limb<L>(x);
     Mag yl = mag_mid_lower(y.t, ytop);
@@ -541,10 +571,10 @@ CB_NOINLINE Meta arb_div(WRef dst, Opd x, Opd y, SCR S0, SCR S1) {
 #pragma unroll
     for (int j = 0; j < L; j++) S0.st(j, 0u);
 #pragma unroll
-    for (int j = 0; j < L; j++) S0.st(L + j, (zx || nan) ? 0u : x.r.m[j * x.r.stride]);
+    for (int j = 0; j < L; j++) S0.st(L + j, (zx || nan) ? 0u : x.r.ld(j));
     S0.st(2 * L, 0u);
 #pragma unroll
-    for (int j = 0; j < L; j++) S1.st(j, nan ? (j == L - 1 ? 0x80000000u : 0u) : y.r.m[j * y.r.stride]);
+    for (int j = 0; j < L; j++) S1.st(j, nan ? (j == L - 1 ? 0x80000000u : 0u) : y.r.ld(j));
     uint32_t d1 = S1.ld(L - 1), d0 = S1.ld(L - 2);
     // quotient words q_j are kept in the upper half of S1 (words L..2L)
     int hi = -1, lo = 0x7FFFFFFF;

@@ -14,9 +14,19 @@ template <> struct Cfg<32> { static constexpr int TPB = 224; };
 template <> struct Cfg<64> { static constexpr int TPB = 128; };
 template <> struct Cfg<128> { static constexpr int TPB = 64; };
 
+// threads per block of the shared-operator recurrence kernel (two product columns + three
+// accumulator columns per thread)
+template <int L> struct CfgShared;
+template <> struct CfgShared<4> { static constexpr int TPB = 128; };
+template <> struct CfgShared<32> { static constexpr int TPB = 224; };
+template <> struct CfgShared<64> { static constexpr int TPB = 96; };
+template <> struct CfgShared<128> { static constexpr int TPB = 32; };
+
 template <int L> struct Sizes {
-    static constexpr int WORDS = 2 * L + 3;  // words per scratch column
+    static constexpr int WORDS = 2 * L + 3;  // words per product scratch column
+    static constexpr int AWORDS = L + 2;     // words per accumulator column
     static constexpr size_t SMEM = (size_t)2 * WORDS * Cfg<L>::TPB * sizeof(uint32_t);
+    static constexpr size_t SMEM_SHARED = (size_t)(2 * WORDS + 3 * AWORDS) * CfgShared<L>::TPB * sizeof(uint32_t);
 };
 
 #define CB_KERNEL_PROLOGUE(COUNT)                                                              \
@@ -49,14 +59,33 @@ __global__ void __launch_bounds__(Cfg<L>::TPB, 1) ew_kernel(EwParams p) {
     ew_thread<L>(p, idx, S0, S1);
 }
 
+template <int L>
+__global__ void __launch_bounds__(Cfg<L>::TPB, 1) fuchs_table_kernel(FuchsTableParams p) {
+    CB_KERNEL_PROLOGUE(p.n + 1 + p.valuation)
+    fuchs_table_thread<L>(p, idx, S0, S1);
+}
+template <int L>
+__global__ void __launch_bounds__(CfgShared<L>::TPB, 1) fuchs_shared_kernel(FuchsSharedParams p) {
+    extern __shared__ uint32_t cb_smem[];
+    constexpr int TPB = CfgShared<L>::TPB;
+    constexpr uint32_t W = Sizes<L>::WORDS, AW = Sizes<L>::AWORDS;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cb_smem) + 4u * threadIdx.x;
+    Scratch<TPB> S0{sbase}, S1{sbase + 4u * W * TPB};
+    Scratch<TPB> A0{sbase + 4u * (2 * W) * TPB}, A1{sbase + 4u * (2 * W + AW) * TPB},
+        A2{sbase + 4u * (2 * W + 2 * AW) * TPB};
+    const int64_t idx = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (idx >= p.batch) return;
+    fuchs_shared_thread<L>(p, idx, S0, S1, A0, A1, A2);
+}
+
 template <int L, class P>
-int launch(void (*kern)(P), const P& p, int64_t count, cudaStream_t st) {
+int launch(void (*kern)(P), const P& p, int64_t count, cudaStream_t st, int tpb = Cfg<L>::TPB,
+           size_t smem = Sizes<L>::SMEM) {
     if (count <= 0) return 0;
-    constexpr int TPB = Cfg<L>::TPB;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sizes<L>::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    unsigned grid = (unsigned)((count + TPB - 1) / TPB);
-    kern<<<grid, TPB, Sizes<L>::SMEM, st>>>(p);
+    unsigned grid = (unsigned)((count + tpb - 1) / tpb);
+    kern<<<grid, tpb, smem, st>>>(p);
     return (int)cudaGetLastError();
 }
 
@@ -66,6 +95,8 @@ struct LaunchTable {
     int (*frobenius1)(const FrobParams&, cudaStream_t);
     int (*horner)(const HornerParams&, cudaStream_t);
     int (*ew)(const EwParams&, cudaStream_t);
+    int (*fuchs_table)(const FuchsTableParams&, cudaStream_t);
+    int (*fuchs_shared)(const FuchsSharedParams&, cudaStream_t);
 };
 
 #define CB_DEFINE_LAUNCH_TABLE(LL)                                                                         \
@@ -74,7 +105,13 @@ struct LaunchTable {
     static int frob_##LL(const FrobParams& p, cudaStream_t s) { return launch<LL>(frobenius1_kernel<LL>, p, p.batch, s); } \
     static int horner_##LL(const HornerParams& p, cudaStream_t s) { return launch<LL>(horner_kernel<LL>, p, p.npts, s); } \
     static int ew_##LL(const EwParams& p, cudaStream_t s) { return launch<LL>(ew_kernel<LL>, p, p.n, s); }                \
-    extern const LaunchTable launch_table_L##LL = {fuchs_##LL, frob_##LL, horner_##LL, ew_##LL};           \
+    static int ftab_##LL(const FuchsTableParams& p, cudaStream_t s) {                                      \
+        return launch<LL>(fuchs_table_kernel<LL>, p, p.n + 1 + p.valuation, s);                            \
+    }                                                                                                      \
+    static int fsh_##LL(const FuchsSharedParams& p, cudaStream_t s) {                                      \
+        return launch<LL>(fuchs_shared_kernel<LL>, p, p.batch, s, CfgShared<LL>::TPB, Sizes<LL>::SMEM_SHARED); \
+    }                                                                                                      \
+    extern const LaunchTable launch_table_L##LL = {fuchs_##LL, frob_##LL, horner_##LL, ew_##LL, ftab_##LL, fsh_##LL}; \
     }
 
 extern const LaunchTable launch_table_L4, launch_table_L32, launch_table_L64, launch_table_L128;

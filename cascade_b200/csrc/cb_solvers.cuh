@@ -206,6 +206,151 @@ CB_HD void fuchs_thread(const FuchsParams& p, int64_t inst, SCR S0, SCR S1) {
     }
 }
 
+// ================================================================ Fuchs, operator shared by the batch
+// When every instance has the same operator, the integer-weighted multipliers
+//   cur(bmax, b) = sum_i P[i][i+e-b] * fac ...   (reference src/fuchs_solver.c:114,121-135)
+// and the divisor are identical for all instances.  fuchs_table_thread computes them ONCE per
+// bmax with exactly the reference's operations (so every ball is bit-identical to what each
+// instance would have computed), including acb_inv of a complex divisor -- acb_div(x, y) is
+// acb_mul(x, acb_inv(y)) for complex y.  fuchs_shared_thread then runs only the per-instance
+// part: W complex multiply-subtracts and one multiply (or a division by a real divisor) per
+// coefficient, with the accumulator held in shared-memory columns.
+//
+// Table layout: shared-format array (S = 2), entry (bmax + v) * (W + 2) + slot, W = degree - v:
+//   slot k < cnt    multiplier for b = bmin + k          (cnt = bmax - bmin)
+//   slot cnt        the divisor
+//   slot W + 1      its inverse when kind[bmax + v] == 1 (complex divisor), unused for kind 0 (real)
+struct FuchsTableParams {
+    int order, degree, valuation;
+    int64_t n;
+    CArr ode;   // S = 2
+    CArr tbl;   // (n + 1 + v) * (W + 2) entries, S = 2
+    CArr tmp;   // 2 entries, S = 2 * (n + 1 + v)   (per table thread)
+    int32_t* kind;
+};
+
+template <int L, class SCR>
+CB_HD void fuchs_table_thread(const FuchsTableParams& p, int64_t row, SCR S0, SCR S1) {
+    const int v = p.valuation, D1 = p.degree + 1, W = p.degree - v;
+    const int64_t bmax = row - v;
+    const size_t tslot = 2 * (size_t)row;
+    CRef t1 = at<L>(p.tmp, 0, tslot), scratch = at<L>(p.tmp, 1, tslot);
+    int64_t e = bmax + v;
+    int64_t bmin = clampi(e - p.degree, 0, bmax);
+    int64_t base = row * (W + 2);
+    acb_set<L>(at<L>(p.tbl, base, 0), at<L>(p.ode, 0 * D1 + (e - bmin), 0));
+    int64_t b = bmin;
+    int k = 0;
+    CRef t2 = at<L>(p.tbl, base, 0);
+#pragma unroll 1
+    do {
+        k++;
+        b++;
+        t2 = at<L>(p.tbl, base + k, 0);
+        acb_zero<L>(t2);
+        int64_t fac = 1;
+        int64_t imin = clampi(b - e, 0, -v);
+        int64_t imax = clampi(b - bmin, 0, p.order);
+#pragma unroll 1
+        for (int64_t i = imin; i <= imax; i++) {
+            acb_mul_si<L>(t1, at<L>(p.ode, i * D1 + (i + e - b), 0), fac, S0);
+            acb_addsub<L>(t2, t2, t1, false, S0, S1);
+            fac *= (b - i);
+        }
+        fac = 1;
+        for (int64_t q = 0; q < imin; q++) fac *= (b - imin + 1 + q);
+        acb_mul_si<L>(t2, t2, fac, S0);
+    } while (b != bmax);
+    Meta dim = ld_meta(t2.t + 1);
+    if (is_exact_zero(dim)) {
+        p.kind[row] = 0;
+    } else {
+        p.kind[row] = 1;
+        acb_inv<L>(at<L>(p.tbl, base + W + 1, 0), t2, scratch, S0, S1);
+    }
+}
+
+struct FuchsSharedParams {
+    int order, degree, valuation;
+    int64_t n, batch;
+    CArr tbl;   // see above
+    CArr res;   // n+1 entries, S = 2*batch
+    const int32_t* kind;
+};
+
+// AC: three small scratch columns (L+2 words each) rotating between acc.re, acc.im and "free"
+template <int L, class SCR>
+CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0, SCR S1, SCR A0, SCR A1,
+                               SCR A2) {
+    const size_t slot = 2 * (size_t)inst;
+    const int v = p.valuation, W = p.degree - v;
+    SCR accRe = A0, accIm = A1, spare = A2;
+#pragma unroll 1
+    for (int64_t bmax = -v; bmax <= p.n; bmax++) {
+        int64_t e = bmax + v;
+        int64_t bmin = clampi(e - p.degree, 0, bmax);
+        int cnt = (int)(bmax - bmin);
+        int64_t base = (bmax + v) * (W + 2);
+        Meta tRe = meta_zero(), tIm = meta_zero();
+#pragma unroll 1
+        for (int k = 0; k < cnt; k++) {
+            CRef x = at<L>(p.res, bmin + k, slot), y = at<L>(p.tbl, base + k, 0);
+            Opd a = re_of(x), b = im_of(x), c = re_of(y), d = im_of(y);
+            // real part: acc.re -= a c - b d
+            Meta pr = arb_fdot2<L, SCR, RRef, RRef, SCR>(spare, a, c, b, d, true, S0, S1);
+            if (k == 0) {  // 0 - x = -x exactly: adopt the column, flip the sign
+                SCR t = accRe;
+                accRe = spare;
+                spare = t;
+                tRe = pr;
+                if (!is_nan(tRe) && !is_zero_mid(tRe)) tRe.flags ^= F_SIGN;
+            } else {
+                SCR where;
+                tRe = arb_addsub_cols<L>(accRe, tRe, spare, pr, true, &where);
+                if (where.a_or_p() == spare.a_or_p()) {
+                    SCR t = accRe;
+                    accRe = spare;
+                    spare = t;
+                }
+            }
+            // imaginary part: acc.im -= a d + b c
+            Meta pi = arb_fdot2<L, SCR, RRef, RRef, SCR>(spare, a, d, b, c, false, S0, S1);
+            if (k == 0) {
+                SCR t = accIm;
+                accIm = spare;
+                spare = t;
+                tIm = pi;
+                if (!is_nan(tIm) && !is_zero_mid(tIm)) tIm.flags ^= F_SIGN;
+            } else {
+                SCR where;
+                tIm = arb_addsub_cols<L>(accIm, tIm, spare, pi, true, &where);
+                if (where.a_or_p() == spare.a_or_p()) {
+                    SCR t = accIm;
+                    accIm = spare;
+                    spare = t;
+                }
+            }
+        }
+        CRef out = at<L>(p.res, bmax, slot);
+        OpdT<SCR> xa{accRe, tRe}, xb{accIm, tIm};
+        if (p.kind[bmax + v] == 1) {
+            CRef y = at<L>(p.tbl, base + W + 1, 0);
+            Opd c = re_of(y), d = im_of(y);
+            Meta tr = arb_fdot2<L, SCR, SCR, RRef, WRef>(wre(out), xa, c, xb, d, true, S0, S1);
+            Meta ti = arb_fdot2<L, SCR, SCR, RRef, WRef>(wim(out), xa, d, xb, c, false, S0, S1);
+            st_meta(out.t, tr);
+            st_meta(out.t + 1, ti);
+        } else {
+            CRef y = at<L>(p.tbl, base + cnt, 0);
+            Opd c = re_of(y);
+            Meta tr = arb_div<L, SCR, SCR, RRef, WRef>(wre(out), xa, c, S0, S1);
+            Meta ti = arb_div<L, SCR, SCR, RRef, WRef>(wim(out), xb, c, S0, S1);
+            st_meta(out.t, tr);
+            st_meta(out.t + 1, ti);
+        }
+    }
+}
+
 // ================================================================ Frobenius (M = 1)
 struct FrobParams {
     int order, degree, valuation;

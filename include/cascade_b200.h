@@ -57,7 +57,8 @@ int cb200_device_count(void);
 uint64_t cb200_kernel_launches(void);
 
 /* ---- workspace sizes (bytes of device memory the _dev entry points need) ---- */
-size_t cb200_fuchs_workspace_bytes(int L, int64_t batch, int64_t n, int shared_ode);
+size_t cb200_fuchs_workspace_bytes(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
+                                   int shared_ode);
 size_t cb200_frobenius_workspace_bytes(int L, int64_t batch);
 size_t cb200_horner_workspace_bytes(int L, int64_t npts);
 size_t cb200_ew_workspace_bytes(int L, int64_t n);

@@ -103,6 +103,34 @@ def case_fuchs_random(oracle, drv, L: int, seed: int, trials: int = 4, batch: in
                                      rs[i * (n + 1) * 2:(i + 1) * (n + 1) * 2], n - order)
 
 
+def case_fuchs_random_shared(oracle, drv, L: int, seed: int, trials: int = 4, batch: int = 5):
+    """As case_fuchs_random, but ONE random operator shared by the batch (the table + recurrence
+    kernels); includes operators whose leading coefficient is real (division path) and valuations
+    between -order and -1."""
+    rng = np.random.default_rng(seed)
+    for trial in range(trials):
+        degree = 3 + int(rng.integers(0, 7))
+        order = 2 + int(rng.integers(0, degree - 2))
+        ne = (order + 1) * (degree + 1)
+        ode = random_balls(rng, ne * 2, L, -4, 4, "ulp", short_frac=0.2)
+        m = ode.mant.reshape(order + 1, degree + 1, 2, L)
+        t = ode.meta.reshape(order + 1, degree + 1, 2, 4)
+        if trial % 2 == 1:  # real leading coefficient -> real divisor
+            m[order, 0, 1] = 0
+            t[order, 0, 1] = (0, FLAG_ZERO, 0, 0)
+        if trial % 3 == 2:  # kill the low columns of the top row: valuation > -order
+            m[order, 0] = 0
+            t[order, 0] = (0, FLAG_ZERO, 0, 0)
+        v = api.acb_ode_valuation(ode, order, degree)
+        assert v < 0
+        n = -v + int(rng.integers(0, 32))
+        init = random_balls(rng, batch * (-v) * 2, L, -3, 3, "ulp")
+        rc, ro = oracle.fuchs_batch(order, degree, n, ode, init, batch, True)
+        assert rc == 0
+        rs = api.acb_ode_solve_fuchs_batch(ode, init, order, degree, n, batch, True, driver=drv)
+        assert_same(ro, rs, f"fuchs shared L={L} order={order} degree={degree} v={v} n={n}")
+
+
 def bessel_shifted(oracle, rng, L: int):
     """BASELINE config 2's operator: Bessel with complex nu, shifted to a complex ordinary point
     (acb_ode_bessel + acb_ode_shift, reference src/examples.c:13-22, src/acb_ode.c:124-135)."""

@@ -50,6 +50,26 @@ int cbsim_fuchs_batch(int L_, int order, int degree, int valuation, int64_t n, i
                  shared_ode ? (size_t)2 : (size_t)(2 * batch)};
     p.res = CArr{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
     Tmp tmp;
+    if (shared_ode) {  // same two-phase path as cb200_fuchs_batch_dev
+        int64_t rows = n + 1 + valuation, W = degree - valuation;
+        if (rows <= 0) return 0;
+        Tmp tbl, ttmp;
+        std::vector<int32_t> kind(rows + 1);
+        FuchsTableParams tp;
+        tp.order = order; tp.degree = degree; tp.valuation = valuation; tp.n = n;
+        tp.ode = p.ode;
+        tp.tbl = tbl.arr(L_, rows * (W + 2), 2);
+        tp.tmp = ttmp.arr(L_, 2, 2 * rows);
+        tp.kind = kind.data();
+        SIM_DISPATCH(L_, run<L>(rows, [&](int64_t i, Scratch<1> a, Scratch<1> b) { fuchs_table_thread<L>(tp, i, a, b); }));
+        FuchsSharedParams sp;
+        sp.order = order; sp.degree = degree; sp.valuation = valuation; sp.n = n; sp.batch = batch;
+        sp.tbl = tp.tbl; sp.res = p.res; sp.kind = kind.data();
+        std::vector<uint32_t> c0(L_ + 2), c1(L_ + 2), c2(L_ + 2);
+        Scratch<1> A0{c0.data()}, A1{c1.data()}, A2{c2.data()};
+        SIM_DISPATCH(L_, run<L>(batch, [&](int64_t i, Scratch<1> a, Scratch<1> b) { fuchs_shared_thread<L>(sp, i, a, b, A0, A1, A2); }));
+        return 0;
+    }
     p.tmp = tmp.arr(L_, FUCHS_NTMP, 2 * batch);
     SIM_DISPATCH(L_, run<L>(batch, [&](int64_t i, Scratch<1> a, Scratch<1> b) { fuchs_thread<L>(p, i, a, b); }));
     return 0;

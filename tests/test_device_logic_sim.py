@@ -20,6 +20,11 @@ def test_fuchs_random(oracle, sim_driver, L):
     cases.case_fuchs_random(oracle, sim_driver, L, seed=7 + L)
 
 
+@pytest.mark.parametrize("L", [4, 32])
+def test_fuchs_random_shared(oracle, sim_driver, L):
+    cases.case_fuchs_random_shared(oracle, sim_driver, L, seed=31 + L, trials=6)
+
+
 def test_fuchs_bessel_shared(oracle, sim_driver):
     cases.case_fuchs_bessel_shared(oracle, sim_driver, 32, seed=5, n=40, batch=3)
 

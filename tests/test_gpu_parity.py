@@ -21,6 +21,11 @@ def test_fuchs_random(oracle, gpu_driver, L):
     cases.case_fuchs_random(oracle, gpu_driver, L, seed=17 + L, trials=5, batch=37)
 
 
+@pytest.mark.parametrize("L", [4, 32, 64, 128])
+def test_fuchs_random_shared(oracle, gpu_driver, L):
+    cases.case_fuchs_random_shared(oracle, gpu_driver, L, seed=41 + L, trials=6 if L < 128 else 3, batch=45)
+
+
 @pytest.mark.parametrize("L", [32, 64])
 def test_fuchs_bessel_shared(oracle, gpu_driver, L):
     cases.case_fuchs_bessel_shared(oracle, gpu_driver, L, seed=5, n=60, batch=300)

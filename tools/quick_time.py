@@ -28,7 +28,7 @@ def rand_arr(entries, S_):
 
 ode_m, ode_t = rand_arr(9, 2)
 res_m, res_t = rand_arr(n + 1, S)
-ws_bytes = lib.cb200_fuchs_workspace_bytes(L, batch, n, 1)
+ws_bytes = lib.cb200_fuchs_workspace_bytes(L, 2, 2, -2, n, batch, 1)
 ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
 p = lambda t: C.c_void_p(t.data_ptr())
 for it in range(3):
