@@ -93,11 +93,18 @@ struct Scratch {
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(a + (uint32_t)(k * (STRIDE * 4))), "r"(v));
     }
     __device__ __forceinline__ uint32_t a_or_p() const { return a; }
+    // generic-address view of the column, for code that is shared with global-memory operands
+    __device__ __forceinline__ uint32_t* generic() const {
+        return (uint32_t*)__cvta_shared_to_generic((size_t)a);
+    }
+    static constexpr size_t GSTRIDE = STRIDE;
 #else
     uint32_t* p;
     uint32_t ld(int k) const { return p[(ptrdiff_t)k * STRIDE]; }
     void st(int k, uint32_t v) const { p[(ptrdiff_t)k * STRIDE] = v; }
     const uint32_t* a_or_p() const { return p; }
+    uint32_t* generic() const { return p; }
+    static constexpr size_t GSTRIDE = STRIDE;
 #endif
 };
 
@@ -231,13 +238,13 @@ struct Rounded {
 // ---------------------------------------------------------------- extract
 // R[0..hi] (scratch words, R[hi] != 0 unless the value is zero) is an unsigned integer V whose
 // bit 0 has weight 2^frame.  Writes the top 32 L bits of V to dst (truncation), returns exponent
-// and the exact inexact flag.  lo = index of the lowest nonzero word (or a value > hi if V == 0).
+// and the exact inexact flag (found by looking at the discarded low words, normally just R[0]).
 template <int L, class DST, class SCR>
-CB_HD Rounded extract(DST dst, SCR R, int hi, int lo, bool sticky, int64_t frame) {
+CB_HD Rounded extract(DST dst, SCR R, int hi, bool sticky, int64_t frame) {
     Rounded out;
     uint32_t top = (hi >= 0) ? R.ld(hi) : 0u;
     if (hi < 0 || top == 0) {
-#pragma unroll
+#pragma unroll 4
         for (int j = 0; j < L; j++) dst.st(j, 0u);
         out.exp = 0;
         out.zero = true;
@@ -249,12 +256,14 @@ CB_HD Rounded extract(DST dst, SCR R, int hi, int lo, bool sticky, int64_t frame
     int off = bl - 32 * L;
     int q = off >> 5;  // arithmetic shift: floor
     int r = off & 31;
-    uint32_t cur = (q >= 0 && q <= hi) ? R.ld(q) : 0u;
-    bool inex = sticky || (lo < q) || (lo == q && r != 0 && (cur & ((1u << r) - 1u)) != 0u);
-#pragma unroll
+    uint32_t cur = ((unsigned)q <= (unsigned)hi) ? R.ld(q) : 0u;
+    // inexact iff any discarded bit is set: low r bits of R[q], or any of R[0..q-1]
+    bool inex = sticky || (r != 0 && (cur & ((1u << r) - 1u)) != 0u);
+    for (int k = 0; !inex && k < q; k++) inex = R.ld(k) != 0u;
+#pragma unroll 4
     for (int j = 0; j < L; j++) {
         int idx = q + j + 1;
-        uint32_t nxt = (idx >= 0 && idx <= hi) ? R.ld(idx) : 0u;
+        uint32_t nxt = ((unsigned)idx <= (unsigned)hi) ? R.ld(idx) : 0u;
         dst.st(j, shr_pair(cur, nxt, r));
         cur = nxt;
     }
@@ -267,10 +276,10 @@ CB_HD Rounded extract(DST dst, SCR R, int hi, int lo, bool sticky, int64_t frame
 }
 
 // ---------------------------------------------------------------- align_add
-// A and B hold N-limb magnitudes (words 0..N-1), top aligned: |a| = A * 2^(ea - 32 N).
-// Computes |R| = | sa*a + sb*b | exactly as far as truncation to 32 L bits can tell, into the
-// scratch column of the larger operand (words 0..N+1), and rounds it into dst.
-// Returns the rounded description and the result sign through *neg.
+// A and B hold N-limb magnitudes (words 0..N-1), top aligned: |a| = A * 2^(ea - 32 N); the top
+// word of a nonzero operand is nonzero.  Computes |R| = | sa*a + sb*b | exactly as far as
+// truncation to 32 L bits can tell, into the scratch column of the larger operand
+// (words 0..N+1), and rounds it into dst.  Returns the rounded description and the sign via *neg.
 // TO_SMALL: the rounded result is written to words 0..L-1 of the SMALLER operand's column (free
 // once the aligned sum has been formed) and *where reports that column; dst is then unused.
 template <int L, int N, bool TO_SMALL = false, class DST, class SCR>
@@ -286,64 +295,65 @@ CB_HD Rounded align_add(DST dst, SCR A, SCR B, int64_t ea, int64_t eb, bool nega
     if (zbig) {  // both zero
         *neg = false;
         if constexpr (TO_SMALL)
-            return extract<L>(small, big, -1, 0, false, 0);
+            return extract<L>(small, big, -1, false, 0);
         else
-            return extract<L>(dst, big, -1, 0, false, 0);
+            return extract<L>(dst, big, -1, false, 0);
     }
     int64_t d64 = zsm ? 0 : (ebig - esm);
     bool far = d64 > 32 * (N + 2);  // small lies entirely below the window
     int d = far ? 32 * (N + 2) : (int)d64;
     int q = d >> 5, r = d & 31;
     bool sub = (nbig != nsm) && !zsm;
-    // sticky: nonzero bits of T = small * 2^32 (N+1 words, T[0] = 0) below bit d
+    // T = small * 2^32 (N+1 words, T[0] = 0, T[i] = small[i-1]); S = T >> d.
+    // T[i] for i in 1..N is small[i-1]; everything else is 0 (also when small is zero).
+    const unsigned nlim = zsm ? 0u : (unsigned)N;
+    auto Tw = [&](int idx) -> uint32_t { return ((unsigned)(idx - 1) < nlim) ? small.ld(idx - 1) : 0u; };
+    // sticky: nonzero bits of T below bit d
     bool sticky = false;
-    if (warp_any(q >= 2 || far)) {
-        uint32_t acc = 0;
-#pragma unroll 8
-        for (int j = 0; j < N; j++) {  // T[j+1] = small[j]; fully below iff j+1 < q
-            uint32_t v = small.ld(j);
-            acc |= (j + 1 < q) ? v : 0u;
-        }
-        sticky = acc != 0u;
+    if (!zsm) {
+        if (r != 0) sticky = (Tw(q) & ((1u << r) - 1u)) != 0u;
+        int lim = q - 1 < N ? q - 1 : N;  // words T[1..lim] lie entirely below
+        for (int j = 0; !sticky && j < lim; j++) sticky = small.ld(j) != 0u;
     }
-    if (q >= 1 && q <= N && r != 0) sticky = sticky || ((small.ld(q - 1) & ((1u << r) - 1u)) != 0u);
-    if (zsm) sticky = false;
     // aligned top words decide the operand order of a subtraction (ties resolved by a fix-up)
-    auto Tw = [&](int idx) -> uint32_t { return (idx >= 1 && idx <= N && !zsm) ? small.ld(idx - 1) : 0u; };
     bool swapped = false;
     if (sub) {
-        uint32_t s_hi = shr_pair(Tw(N + q), Tw(N + q + 1), r);
-        uint32_t s_lo = shr_pair(Tw(N - 1 + q), Tw(N + q), r);
-        uint32_t w_hi = big.ld(N - 1), w_lo = (N >= 2) ? big.ld(N - 2) : 0u;
-        uint64_t s64 = ((uint64_t)s_hi << 32) | s_lo, w64 = ((uint64_t)w_hi << 32) | w_lo;
+        uint32_t t2 = Tw(N + q + 1), t1 = Tw(N + q), t0 = Tw(N + q - 1);
+        uint64_t s64 = ((uint64_t)shr_pair(t1, t2, r) << 32) | shr_pair(t0, t1, r);
+        uint64_t w64 = ((uint64_t)big.ld(N - 1) << 32) | ((N >= 2) ? big.ld(N - 2) : 0u);
         swapped = s64 > w64;
     }
-    uint32_t mw = (sub && swapped) ? 0xFFFFFFFFu : 0u;
-    uint32_t ms = (sub && !swapped) ? 0xFFFFFFFFu : 0u;
+    const uint32_t mw = (sub && swapped) ? 0xFFFFFFFFu : 0u;
+    const uint32_t ms = (sub && !swapped) ? 0xFFFFFFFFu : 0u;
     uint32_t carry = (sub && !sticky) ? 1u : 0u;
-    int hi = -1, lo = 0x7FFFFFFF;
-    uint32_t wprev = 0u;           // W[k] = big[k-1]
-    uint32_t tcur = Tw(q);         // T[k+q]
-#pragma unroll
-    for (int k = 0; k <= N; k++) {
-        uint32_t wnext = (k < N) ? big.ld(k) : 0u;  // read before the slot is overwritten
-        uint32_t tnxt = Tw(k + q + 1);
-        uint32_t s = shr_pair(tcur, tnxt, r);
-        uint64_t t = (uint64_t)(wprev ^ mw) + (uint64_t)(s ^ ms) + carry;
-        uint32_t v = (uint32_t)t;
+    uint32_t wprev = 0u;    // W[k] = big[k-1]
+    uint32_t tcur = Tw(q);  // T[k+q]
+    // in the loop T[k+q+1] = small[k+q] is in range iff k+q < nlim
+    const int tl = (int)nlim - q;
+#pragma unroll 4
+    for (int k = 0; k < N; k++) {
+        uint32_t wnext = big.ld(k);  // read before the slot is overwritten
+        uint32_t tnxt = (k < tl) ? small.ld(k + q) : 0u;
+        uint32_t sv = shr_pair(tcur, tnxt, r);
+        uint64_t t = (uint64_t)(wprev ^ mw) + (uint64_t)(sv ^ ms) + carry;
         carry = (uint32_t)(t >> 32);
-        big.st(k, v);
-        if (v != 0u) {
-            hi = k;
-            lo = lo < k ? lo : k;
-        }
+        big.st(k, (uint32_t)t);
         wprev = wnext;
         tcur = tnxt;
     }
+    {   // k = N (top word of the window)
+        uint32_t tnxt = (N < tl) ? small.ld(N + q) : 0u;
+        uint32_t sv = shr_pair(tcur, tnxt, r);
+        uint64_t t = (uint64_t)(wprev ^ mw) + (uint64_t)(sv ^ ms) + carry;
+        carry = (uint32_t)(t >> 32);
+        big.st(N, (uint32_t)t);
+    }
     bool rneg = nbig;
+    int hi;
     if (!sub) {
+        // W[N] != 0, so without a carry R[N] != 0; with one the top word is the carry itself
         big.st(N + 1, carry);
-        if (carry) hi = N + 1, lo = lo < N + 1 ? lo : N + 1;
+        hi = carry ? N + 1 : N;
     } else {
         big.st(N + 1, 0u);
         if (swapped) rneg = nsm;
@@ -351,26 +361,21 @@ CB_HD Rounded align_add(DST dst, SCR A, SCR B, int64_t ea, int64_t eb, bool nega
             // the order guess was wrong (top 64 aligned bits tied): negate in place
             rneg = !rneg;
             uint32_t c = 1u;
-            hi = -1;
-            lo = 0x7FFFFFFF;
 #pragma unroll 1
             for (int k = 0; k <= N; k++) {
                 uint64_t t = (uint64_t)(~big.ld(k)) + c;
-                uint32_t v = (uint32_t)t;
                 c = (uint32_t)(t >> 32);
-                big.st(k, v);
-                if (v != 0u) {
-                    hi = k;
-                    lo = lo < k ? lo : k;
-                }
+                big.st(k, (uint32_t)t);
             }
         }
+        hi = N;
+        while (hi >= 0 && big.ld(hi) == 0u) hi--;
     }
     *neg = rneg;
     if constexpr (TO_SMALL)
-        return extract<L>(small, big, hi, lo, sticky, ebig - 32 * (int64_t)N - 32);
+        return extract<L>(small, big, hi, sticky, ebig - 32 * (int64_t)N - 32);
     else
-        return extract<L>(dst, big, hi, lo, sticky, ebig - 32 * (int64_t)N - 32);
+        return extract<L>(dst, big, hi, sticky, ebig - 32 * (int64_t)N - 32);
 }
 
 // ---------------------------------------------------------------- products into scratch
@@ -528,7 +533,7 @@ CB_NOINLINE Meta arb_mul_si(WRef dst, Opd x, int64_t k, SCR S0) {
     // P[0..L+2) = x * ka, column by column:
     //   col j = lo(x_j k0) + hi(x_{j-1} k0) + lo(x_{j-1} k1) + hi(x_{j-2} k1) + carry
     uint32_t hi0_prev = 0u, lo1_prev = 0u, hi1_prev = 0u, hi1_prev2 = 0u, carry = 0u;
-    int hi = -1, lo = 0x7FFFFFFF;
+    int hi = -1;
 #pragma unroll
     for (int j = 0; j < L + 2; j++) {
         uint32_t xj = (j < L) ? x.r.ld(j) : 0u;
@@ -537,16 +542,13 @@ CB_NOINLINE Meta arb_mul_si(WRef dst, Opd x, int64_t k, SCR S0) {
         uint32_t v = z ? 0u : (uint32_t)t;
         carry = (uint32_t)(t >> 32);
         S0.st(j, v);
-        if (v != 0u) {
-            hi = j;
-            lo = lo < j ? lo : j;
-        }
+        if (v != 0u) hi = j;
         hi0_prev = (uint32_t)(p0 >> 32);
         hi1_prev2 = hi1_prev;
         hi1_prev = (uint32_t)(p1 >> 32);
         lo1_prev = (uint32_t)p1;
     }
-    Rounded rr = extract<L>(dst, S0, hi, lo, false, (int64_t)x.t.exp - 32 * L);
+    Rounded rr = extract<L>(dst, S0, hi, false, (int64_t)x.t.exp - 32 * L);
     if (nan) return meta_nan();
     bool neg = ((x.t.flags & F_SIGN) != 0) != (k < 0);
     return finish<L>(rr, neg, rad);
@@ -577,7 +579,7 @@ CB_NOINLINE Meta arb_div(DST dst, OpdT<XS> x, OpdT<YS> y, SCR S0, SCR S1) {
     for (int j = 0; j < L; j++) S1.st(j, nan ? (j == L - 1 ? 0x80000000u : 0u) : y.r.ld(j));
     uint32_t d1 = S1.ld(L - 1), d0 = S1.ld(L - 2);
     // quotient words q_j are kept in the upper half of S1 (words L..2L)
-    int hi = -1, lo = 0x7FFFFFFF;
+    int hi = -1;
 #pragma unroll 1
     for (int j = L; j >= 0; j--) {
         uint32_t u2 = S0.ld(j + L), u1 = S0.ld(j + L - 1), u0 = S0.ld(j + L - 2);
@@ -618,10 +620,7 @@ CB_NOINLINE Meta arb_div(DST dst, OpdT<XS> x, OpdT<YS> y, SCR S0, SCR S1) {
             S0.st(j + L, S0.ld(j + L) + c);
         }
         S1.st(L + j, qd);
-        if (qd != 0u) {
-            hi = hi < 0 ? j : hi;
-            lo = j;
-        }
+        if (qd != 0u && hi < 0) hi = j;
     }
     // remainder in U[0..L)
     uint32_t rem = 0u;
@@ -632,7 +631,7 @@ CB_NOINLINE Meta arb_div(DST dst, OpdT<XS> x, OpdT<YS> y, SCR S0, SCR S1) {
         SCR s;
         CB_HD uint32_t ld(int k) const { return s.ld(L + k); }
     } V{S1};
-    Rounded rr = extract<L>(dst, V, hi, lo, rem != 0u, (int64_t)x.t.exp - y.t.exp - 32 * L);
+    Rounded rr = extract<L>(dst, V, hi, rem != 0u, (int64_t)x.t.exp - y.t.exp - 32 * L);
     if (nan) {
         store_nan<L>(dst);
         return meta_nan();

@@ -297,7 +297,7 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
             CRef x = at<L>(p.res, bmin + k, slot), y = at<L>(p.tbl, base + k, 0);
             Opd a = re_of(x), b = im_of(x), c = re_of(y), d = im_of(y);
             // real part: acc.re -= a c - b d
-            Meta pr = arb_fdot2<L, SCR, RRef, RRef, SCR>(spare, a, c, b, d, true, S0, S1);
+            Meta pr = arb_fdot2<L>(WRef{spare.generic(), SCR::GSTRIDE}, a, c, b, d, true, S0, S1);
             if (k == 0) {  // 0 - x = -x exactly: adopt the column, flip the sign
                 SCR t = accRe;
                 accRe = spare;
@@ -314,7 +314,7 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
                 }
             }
             // imaginary part: acc.im -= a d + b c
-            Meta pi = arb_fdot2<L, SCR, RRef, RRef, SCR>(spare, a, d, b, c, false, S0, S1);
+            Meta pi = arb_fdot2<L>(WRef{spare.generic(), SCR::GSTRIDE}, a, d, b, c, false, S0, S1);
             if (k == 0) {
                 SCR t = accIm;
                 accIm = spare;
@@ -332,19 +332,19 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
             }
         }
         CRef out = at<L>(p.res, bmax, slot);
-        OpdT<SCR> xa{accRe, tRe}, xb{accIm, tIm};
+        Opd xa{RRef{accRe.generic(), SCR::GSTRIDE}, tRe}, xb{RRef{accIm.generic(), SCR::GSTRIDE}, tIm};
         if (p.kind[bmax + v] == 1) {
             CRef y = at<L>(p.tbl, base + W + 1, 0);
             Opd c = re_of(y), d = im_of(y);
-            Meta tr = arb_fdot2<L, SCR, SCR, RRef, WRef>(wre(out), xa, c, xb, d, true, S0, S1);
-            Meta ti = arb_fdot2<L, SCR, SCR, RRef, WRef>(wim(out), xa, d, xb, c, false, S0, S1);
+            Meta tr = arb_fdot2<L>(wre(out), xa, c, xb, d, true, S0, S1);
+            Meta ti = arb_fdot2<L>(wim(out), xa, d, xb, c, false, S0, S1);
             st_meta(out.t, tr);
             st_meta(out.t + 1, ti);
         } else {
             CRef y = at<L>(p.tbl, base + cnt, 0);
             Opd c = re_of(y);
-            Meta tr = arb_div<L, SCR, SCR, RRef, WRef>(wre(out), xa, c, S0, S1);
-            Meta ti = arb_div<L, SCR, SCR, RRef, WRef>(wim(out), xb, c, S0, S1);
+            Meta tr = arb_div<L>(wre(out), xa, c, S0, S1);
+            Meta ti = arb_div<L>(wim(out), xb, c, S0, S1);
             st_meta(out.t, tr);
             st_meta(out.t + 1, ti);
         }
