@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "../../include/cascade_b200.h"
 #include "cb_kernels.cuh"
@@ -122,6 +123,10 @@ int cb200_fuchs_batch_dev(int L_, int order, int degree, int valuation, int64_t 
         sp.tbl = tp.tbl;
         sp.res = CArr{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
         sp.kind = tp.kind;
+        {
+            const char* ds = getenv("CB200_DESYNC");
+            sp.desync_cycles = ds ? atoi(ds) : 0;
+        }
         g_launches.fetch_add(batch > 0);
         return table_for(L_)->fuchs_shared(sp, (cudaStream_t)stream);
     }

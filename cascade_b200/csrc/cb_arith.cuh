@@ -459,27 +459,154 @@ CB_HD void store_nan(DST dst) {
     for (int j = 0; j < L; j++) dst.st(j, 0u);
 }
 
+// ---------------------------------------------------------------- in-register fast path
+// The common case of an aligned add: both operands within 31 bits of each other (or one of them
+// zero) and at most about a limb of cancellation.  Everything is statically indexed, so the sum
+// lives in registers and only the final stores use a data-dependent offset.
+//   V_i = X_i * 2^(E - s_i - 32 N),  X_i given word by word by x_i(k), k in [0, N) (0 if zero).
+// Returns false without touching dst when the case is not the easy one (operand order guess of a
+// subtraction wrong, or more than a limb cancelled): the caller then takes the general path.
+template <int L, int N, class DST, class X1, class X2>
+CB_HD bool fast_add_round(DST dst, X1 x1, X2 x2, int s1, int s2, bool sub, bool n1, bool n2, int64_t E,
+                          Rounded* rr, bool* neg) {
+    uint32_t R[N + 2];
+    bool swapped = false;
+    if (sub) {  // compare the top 64 aligned bits: W_i[N], W_i[N-1] with T_i[k] = X_i[k-1]
+        uint32_t a2 = x1(N - 1), a1 = x1(N - 2), a0 = (N >= 3) ? x1(N - 3) : 0u;
+        uint32_t b2 = x2(N - 1), b1 = x2(N - 2), b0 = (N >= 3) ? x2(N - 3) : 0u;
+        uint64_t w1 = ((uint64_t)shr_pair(a2, 0u, s1) << 32) | shr_pair(a1, a2, s1);
+        uint64_t w2 = ((uint64_t)shr_pair(b2, 0u, s2) << 32) | shr_pair(b1, b2, s2);
+        (void)a0;
+        (void)b0;
+        swapped = w2 > w1;
+    }
+    const uint32_t m1 = (sub && swapped) ? 0xFFFFFFFFu : 0u;
+    const uint32_t m2 = (sub && !swapped) ? 0xFFFFFFFFu : 0u;
+    uint32_t carry = sub ? 1u : 0u;
+    uint32_t t1c = 0u, t2c = 0u;  // T_i[k]; T_i[0] = 0 (guard limb)
+#pragma unroll
+    for (int k = 0; k <= N; k++) {
+        uint32_t t1n = (k < N) ? x1(k) : 0u, t2n = (k < N) ? x2(k) : 0u;
+        uint32_t w1 = shr_pair(t1c, t1n, s1), w2 = shr_pair(t2c, t2n, s2);
+        uint64_t t = (uint64_t)(w1 ^ m1) + (uint64_t)(w2 ^ m2) + carry;
+        R[k] = (uint32_t)t;
+        carry = (uint32_t)(t >> 32);
+        t1c = t1n;
+        t2c = t2n;
+    }
+    if (sub && carry == 0u) return false;  // |W2| > |W1| after all (tie in the top 64 bits)
+    R[N + 1] = sub ? 0u : carry;
+    int hi;
+    uint32_t top;
+    if (R[N + 1]) {
+        hi = N + 1;
+        top = R[N + 1];
+    } else if (R[N]) {
+        hi = N;
+        top = R[N];
+    } else if (R[N - 1]) {
+        hi = N - 1;
+        top = R[N - 1];
+    } else {
+        return false;  // a limb or more cancelled (or the result is zero)
+    }
+    const int bl = 32 * hi + 32 - clz32(top);
+    const int off = bl - 32 * L;
+    const int q = off >> 5, r = off & 31;
+    constexpr int QMIN = N - 1 - L;  // q is in [QMIN, QMIN + 3]
+    auto Rx = [&](int idx) -> uint32_t { return (idx >= 0 && idx <= N + 1) ? R[idx] : 0u; };
+    // discarded bits: words below q, and the low r bits of word q
+    uint32_t low = 0u;
+#pragma unroll
+    for (int i = 0; i < QMIN; i++) low |= R[i];
+#pragma unroll
+    for (int i = QMIN; i < QMIN + 4; i++) {
+        uint32_t w = Rx(i);
+        low |= (i < q) ? w : 0u;
+        low |= (i == q) ? (w & ((1u << r) - 1u)) : 0u;
+    }
+    // dst[i - q] = bits [32 i + r, 32 i + r + 32) of R, for the L words with 0 <= i - q < L
+#pragma unroll
+    for (int i = QMIN; i < QMIN + L + 3; i++) {
+        uint32_t v = shr_pair(Rx(i), Rx(i + 1), r);
+        int j = i - q;
+        if ((unsigned)j < (unsigned)L) dst.st(j, v);
+    }
+    int64_t e = E - 32 * (int64_t)N - 32 + bl;
+    rr->overflow = (e > EXP_LIMIT || e < -EXP_LIMIT);
+    rr->exp = (int32_t)e;
+    rr->zero = false;
+    rr->inexact = low != 0u;
+    *neg = (sub && swapped) ? n2 : n1;
+    return true;
+}
+
 // ---------------------------------------------------------------- arb level
 // dst = x1*y1 + (neg2 ? -1 : 1) * x2*y2, one rounding.  S0/S1: two scratch columns of 2L+2 words.
 template <int L, class SCR, class XS = RRef, class YS = RRef, class DST = WRef>
 CB_NOINLINE Meta arb_fdot2(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2, OpdT<YS> y2, bool neg2, SCR S0,
                            SCR S1) {
     bool nan = is_nan(x1.t) || is_nan(y1.t) || is_nan(x2.t) || is_nan(y2.t);
-    bool z1 = is_zero_mid(x1.t) || is_zero_mid(y1.t);
-    bool z2 = is_zero_mid(x2.t) || is_zero_mid(y2.t);
+    bool z1 = is_zero_mid(x1.t) || is_zero_mid(y1.t) || nan;
+    bool z2 = is_zero_mid(x2.t) || is_zero_mid(y2.t) || nan;
     Mag rad = mul_rad(mag_zero(), x1.t, top_limb<L>(x1), y1.t, top_limb<L>(y1));
     rad = mul_rad(rad, x2.t, top_limb<L>(x2), y2.t, top_limb<L>(y2));
-    bool skip1 = warp_all(z1 || nan), skip2 = warp_all(z2 || nan);
-#pragma unroll 1
-    for (int term = 0; term < 2; term++) {  // a loop, so that the product code exists once
-        if (term ? skip2 : skip1) continue;
-        product<L>(term ? S1 : S0, term ? x2.r : x1.r, term ? y2.r : y1.r);
-    }
     bool n1 = ((x1.t.flags ^ y1.t.flags) & F_SIGN) != 0;
     bool n2 = (((x2.t.flags ^ y2.t.flags) & F_SIGN) != 0) != neg2;
+    const int64_t e1 = (int64_t)x1.t.exp + y1.t.exp, e2 = (int64_t)x2.t.exp + y2.t.exp;
+    bool skip1 = warp_all(z1), skip2 = warp_all(z2);
     bool neg;
-    Rounded rr = align_add<L, 2 * L>(dst, S0, S1, (int64_t)x1.t.exp + y1.t.exp,
-                                     (int64_t)x2.t.exp + y2.t.exp, n1, n2, z1 || nan, z2 || nan, &neg);
+    Rounded rr;
+    if constexpr (L <= 32) {
+        // products in registers; the first one is parked in S0 while the second is formed
+        uint32_t r[2 * L];
+#pragma unroll 1
+        for (int term = 0; term < 2; term++) {  // a loop, so that the product code exists once
+            if (term == 1) {
+#pragma unroll
+                for (int k = 0; k < 2 * L; k++) S0.st(k, r[k]);
+            }
+            if (term ? skip2 : skip1) {
+#pragma unroll
+                for (int k = 0; k < 2 * L; k++) r[k] = 0u;
+                continue;
+            }
+            uint32_t a[L], b[L];
+            XS xs = term ? x2.r : x1.r;
+            YS ys = term ? y2.r : y1.r;
+#pragma unroll
+            for (int j = 0; j < L; j++) a[j] = xs.ld(j);
+#pragma unroll
+            for (int j = 0; j < L; j++) b[j] = ys.ld(j);
+            mul_full<L>(r, a, b);
+        }
+        // easy: one term zero, or exponents within 31 bits
+        int64_t d = e1 - e2;
+        bool easy = !(z1 && z2) && (z1 || z2 || (d <= 31 && d >= -31));
+        bool done = false;  // per lane: lanes that are not easy take the general path below
+        if (easy) {
+            int64_t E = z1 ? e2 : (z2 ? e1 : (e1 > e2 ? e1 : e2));
+            int s1 = z1 ? 0 : (int)(E - e1), s2 = z2 ? 0 : (int)(E - e2);
+            bool sub = (n1 != n2) && !z1 && !z2;
+            // a zero term contributes zero words (its product registers / column may hold the
+            // product of a zero-flagged operand's stale limbs)
+            auto w1 = [&](int k) -> uint32_t { return z1 ? 0u : S0.ld(k); };
+            auto w2 = [&](int k) -> uint32_t { return z2 ? 0u : r[k]; };
+            done = fast_add_round<L, 2 * L>(dst, w1, w2, s1, s2, sub, z1 ? n2 : n1, z1 ? n1 : n2, E, &rr, &neg);
+        }
+        if (!done) {
+#pragma unroll
+            for (int k = 0; k < 2 * L; k++) S1.st(k, r[k]);
+            rr = align_add<L, 2 * L>(dst, S0, S1, e1, e2, n1, n2, z1, z2, &neg);
+        }
+    } else {
+#pragma unroll 1
+        for (int term = 0; term < 2; term++) {
+            if (term ? skip2 : skip1) continue;
+            product<L>(term ? S1 : S0, term ? x2.r : x1.r, term ? y2.r : y1.r);
+        }
+        rr = align_add<L, 2 * L>(dst, S0, S1, e1, e2, n1, n2, z1, z2, &neg);
+    }
     if (nan) return meta_nan();
     return finish<L>(rr, neg, rad);
 }
@@ -507,9 +634,26 @@ template <int L, class SCR>
 CB_NOINLINE Meta arb_addsub_cols(SCR A, Meta ta, SCR B, Meta tb, bool negb, SCR* where) {
     bool nan = is_nan(ta) || is_nan(tb);
     bool zx = is_zero_mid(ta) || nan, zy = is_zero_mid(tb) || nan;
+    bool na = (ta.flags & F_SIGN) != 0, nb = ((tb.flags & F_SIGN) != 0) != negb;
     bool neg;
-    Rounded rr = align_add<L, L, true>(A, A, B, ta.exp, tb.exp, (ta.flags & F_SIGN) != 0,
-                                       ((tb.flags & F_SIGN) != 0) != negb, zx, zy, &neg, where);
+    Rounded rr;
+    bool done = false;
+    if constexpr (L <= 32) {
+        int64_t d = (int64_t)ta.exp - tb.exp;
+        bool easy = !(zx && zy) && (zx || zy || (d <= 31 && d >= -31));
+        if (easy) {  // per lane; a lane that fails keeps its columns intact for the general path
+            int64_t E = zx ? tb.exp : (zy ? ta.exp : (ta.exp > tb.exp ? ta.exp : tb.exp));
+            int s1 = zx ? 0 : (int)(E - ta.exp), s2 = zy ? 0 : (int)(E - tb.exp);
+            bool sub = (na != nb) && !zx && !zy;
+            auto w1 = [&](int k) -> uint32_t { return zx ? 0u : A.ld(k); };
+            auto w2 = [&](int k) -> uint32_t { return zy ? 0u : B.ld(k); };
+            // both columns are fully read before anything is stored, so the result can go to B
+            done = fast_add_round<L, L>(B, w1, w2, s1, s2, sub, zx ? nb : na, zx ? na : nb, E, &rr, &neg);
+            if (done) *where = B;
+        }
+    }
+    if (!done)
+        rr = align_add<L, L, true>(A, A, B, ta.exp, tb.exp, na, nb, zx, zy, &neg, where);
     if (nan) return meta_nan();
     return finish<L>(rr, neg, mag_add(mag_of(ta), mag_of(tb)));
 }

@@ -75,6 +75,14 @@ __global__ void __launch_bounds__(CfgShared<L>::TPB, 1) fuchs_shared_kernel(Fuch
         A2{sbase + 4u * (2 * W + 2 * AW) * TPB};
     const int64_t idx = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (idx >= p.batch) return;
+    // All warps run the same instruction sequence, so left alone they hit the IMAD-bound product
+    // phases together and the ALU/LSU-bound alignment phases together.  Staggering the second
+    // warp of every scheduler by a fraction of a period lets one warp's products overlap the
+    // other's alignment work.
+    if (p.desync_cycles > 0 && ((threadIdx.x >> 5) & 4)) {
+        long long t0 = clock64();
+        while (clock64() - t0 < p.desync_cycles) {}
+    }
     fuchs_shared_thread<L>(p, idx, S0, S1, A0, A1, A2);
 }
 

@@ -276,6 +276,7 @@ struct FuchsSharedParams {
     CArr tbl;   // see above
     CArr res;   // n+1 entries, S = 2*batch
     const int32_t* kind;
+    int desync_cycles;  // start-up stagger between the warps of a scheduler (see fuchs_shared_kernel)
 };
 
 // AC: three small scratch columns (L+2 words each) rotating between acc.re, acc.im and "free"

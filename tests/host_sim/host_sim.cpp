@@ -64,7 +64,7 @@ int cbsim_fuchs_batch(int L_, int order, int degree, int valuation, int64_t n, i
         SIM_DISPATCH(L_, run<L>(rows, [&](int64_t i, Scratch<1> a, Scratch<1> b) { fuchs_table_thread<L>(tp, i, a, b); }));
         FuchsSharedParams sp;
         sp.order = order; sp.degree = degree; sp.valuation = valuation; sp.n = n; sp.batch = batch;
-        sp.tbl = tp.tbl; sp.res = p.res; sp.kind = kind.data();
+        sp.tbl = tp.tbl; sp.res = p.res; sp.kind = kind.data(); sp.desync_cycles = 0;
         std::vector<uint32_t> c0(L_ + 2), c1(L_ + 2), c2(L_ + 2);
         Scratch<1> A0{c0.data()}, A1{c1.data()}, A2{c2.data()};
         SIM_DISPATCH(L_, run<L>(batch, [&](int64_t i, Scratch<1> a, Scratch<1> b) { fuchs_shared_thread<L>(sp, i, a, b, A0, A1, A2); }));
