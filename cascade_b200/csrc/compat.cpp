@@ -1,0 +1,493 @@
+// compat.cpp -- host side of include/cascade_compat.h: Cascade's own API names over the batched
+// CUDA entry points (batch of one).  Marshalling and control flow only; every ball operation is a
+// call into the device library (there is no CPU arithmetic path).
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/cascade_compat.h"
+
+namespace {
+
+const slong UNDEFINED_VAL = -0xFFFF;  // reference src/acb_ode.c:3
+
+[[noreturn]] void die(const char* what, int rc) {
+    fprintf(stderr, "cascade_b200: %s failed (rc = %d); there is no CPU fallback\n", what, rc);
+    abort();
+}
+int limbs_of(slong prec) {
+    if (prec == 128 || prec == 1024 || prec == 2048 || prec == 4096) return (int)(prec / 32);
+    fprintf(stderr, "cascade_b200: precision %ld is not supported on the device (use 128, 1024, 2048 or 4096)\n", prec);
+    abort();
+}
+
+// compat ball (128 limbs, top aligned) -> device slot with L limbs (entry layout [L][S], slot s)
+void to_slot(const arb_struct* x, int L, uint32_t* mant, cb_meta* meta, size_t S, size_t s) {
+    bool lost = false;
+    for (int k = 0; k < CB_MAX_LIMBS - L; k++) lost |= x->mant[k] != 0;
+    for (int k = 0; k < L; k++) mant[(size_t)k * S + s] = x->mant[CB_MAX_LIMBS - L + k];
+    meta[s] = x->meta;
+    if (lost && !(x->meta.flags & CB_FLAG_NAN)) {
+        // the value carries more bits than the target precision: truncate and widen the radius
+        // by one ulp (what arb_set_round does); a 30-bit magnitude add, rounded up
+        uint32_t uman = 1u << 29;
+        int32_t uexp = x->meta.exp - 32 * L + 1;
+        cb_meta& t = meta[s];
+        if (t.rman == 0) {
+            t.rman = uman;
+            t.rexp = uexp;
+        } else {
+            int32_t sh = t.rexp - uexp;
+            uint32_t m;
+            int32_t e = t.rexp;
+            if (sh >= 0) {
+                m = t.rman + (sh >= 30 ? 0 : (uman >> sh)) + 1;
+            } else {
+                m = uman + ((-sh) >= 30 ? 0 : (t.rman >> (-sh))) + 1;
+                e = uexp;
+            }
+            if (m >> 30) {
+                m = (m >> 1) + (m & 1);
+                e += 1;
+            }
+            t.rman = m;
+            t.rexp = e;
+        }
+    }
+}
+void from_slot(arb_struct* x, int L, const uint32_t* mant, const cb_meta* meta, size_t S, size_t s) {
+    memset(x->mant, 0, sizeof(x->mant));
+    for (int k = 0; k < L; k++) x->mant[CB_MAX_LIMBS - L + k] = mant[(size_t)k * S + s];
+    x->meta = meta[s];
+}
+
+// one entry array of n complex balls (S = 2n)
+struct HostArr {
+    int L;
+    size_t entries, S;
+    std::vector<uint32_t> m;
+    std::vector<cb_meta> t;
+    HostArr(int L_, size_t entries_, size_t S_) : L(L_), entries(entries_), S(S_), m(entries_ * L_ * S_, 0u), t(entries_ * S_) {
+        for (auto& x : t) x = cb_meta{0, CB_FLAG_ZERO, 0, 0};
+    }
+    void put(size_t entry, size_t inst, const acb_struct* x) {
+        to_slot(&x->real, L, m.data() + entry * L * S, t.data() + entry * S, S, 2 * inst);
+        to_slot(&x->imag, L, m.data() + entry * L * S, t.data() + entry * S, S, 2 * inst + 1);
+    }
+    void get(size_t entry, size_t inst, acb_struct* x) const {
+        from_slot(&x->real, L, m.data() + entry * L * S, t.data() + entry * S, S, 2 * inst);
+        from_slot(&x->imag, L, m.data() + entry * L * S, t.data() + entry * S, S, 2 * inst + 1);
+    }
+};
+
+void ew(int op, acb_struct* z, const acb_struct* x, const acb_struct* y, const int64_t* k, slong prec) {
+    int L = limbs_of(prec);
+    HostArr hx(L, 1, 2), hy(L, 1, 2), hz(L, 1, 2);
+    hx.put(0, 0, x);
+    if (y) hy.put(0, 0, y);
+    int rc = cb200_ew_host(op, L, 1, hz.m.data(), hz.t.data(), hx.m.data(), hx.t.data(), y ? hy.m.data() : nullptr,
+                           y ? hy.t.data() : nullptr, k, 0);
+    if (rc) die("cb200_ew_host", rc);
+    hz.get(0, 0, z);
+}
+
+void arb_set_exact_u64(arb_struct* x, uint64_t v, int neg, int32_t exp2) {
+    // value = (-1)^neg * v * 2^exp2
+    memset(x, 0, sizeof(*x));
+    if (v == 0) {
+        x->meta.flags = CB_FLAG_ZERO;
+        return;
+    }
+    int sh = __builtin_clzll(v);
+    uint64_t n = v << sh;
+    x->mant[CB_MAX_LIMBS - 1] = (uint32_t)(n >> 32);
+    x->mant[CB_MAX_LIMBS - 2] = (uint32_t)n;
+    x->meta.exp = 64 - sh + exp2;
+    x->meta.flags = neg ? CB_FLAG_SIGN : 0;
+}
+void arb_set_double(arb_struct* x, double d) {
+    if (d == 0.0 || !isfinite(d)) {
+        memset(x, 0, sizeof(*x));
+        x->meta.flags = isfinite(d) ? CB_FLAG_ZERO : CB_FLAG_NAN;
+        if (!isfinite(d)) x->meta.rman = CB_MAG_INF_MAN;
+        return;
+    }
+    int e;
+    double f = frexp(fabs(d), &e);              // f in [0.5, 1)
+    uint64_t m = (uint64_t)ldexp(f, 53);        // 53-bit integer, exact
+    arb_set_exact_u64(x, m, d < 0, e - 53);
+}
+double arb_mid_d(const arb_struct* x) {
+    if (x->meta.flags & CB_FLAG_NAN) return NAN;
+    if (x->meta.flags & CB_FLAG_ZERO) return 0.0;
+    uint64_t top = ((uint64_t)x->mant[CB_MAX_LIMBS - 1] << 32) | x->mant[CB_MAX_LIMBS - 2];
+    double v = ldexp((double)top, x->meta.exp - 64);
+    return (x->meta.flags & CB_FLAG_SIGN) ? -v : v;
+}
+double arb_rad_d(const arb_struct* x) {
+    if (x->meta.flags & CB_FLAG_NAN) return INFINITY;
+    if (x->meta.rman == 0) return 0.0;
+    return ldexp((double)x->meta.rman, x->meta.rexp - 30);
+}
+bool arb_exact_zero(const arb_struct* x) { return (x->meta.flags & CB_FLAG_ZERO) && x->meta.rman == 0; }
+bool arb_has_zero(const arb_struct* x) {
+    if (x->meta.flags & (CB_FLAG_NAN | CB_FLAG_ZERO)) return true;
+    if (x->meta.rman == 0) return false;
+    if (x->meta.exp != x->meta.rexp) return x->meta.exp < x->meta.rexp;
+    uint32_t top30 = x->mant[CB_MAX_LIMBS - 1] >> 2;
+    if (top30 != x->meta.rman) return top30 < x->meta.rman;
+    if (x->mant[CB_MAX_LIMBS - 1] & 3u) return false;
+    for (int k = 0; k < CB_MAX_LIMBS - 1; k++)
+        if (x->mant[k]) return false;
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------ minimal acb / acb_poly
+void acb_init(acb_t x) { acb_zero(x); }
+void acb_clear(acb_t) {}
+void acb_zero(acb_t x) {
+    memset(x, 0, sizeof(acb_struct));
+    x->real.meta.flags = CB_FLAG_ZERO;
+    x->imag.meta.flags = CB_FLAG_ZERO;
+}
+void acb_one(acb_t x) { acb_set_si(x, 1); }
+void acb_set(acb_t z, const acb_t x) {
+    if (z != x) memcpy(z, x, sizeof(acb_struct));
+}
+void acb_set_si(acb_t z, slong v) {
+    acb_zero(z);
+    arb_set_exact_u64(&z->real, v < 0 ? (uint64_t)0 - (uint64_t)v : (uint64_t)v, v < 0, 0);
+}
+void acb_set_d(acb_t z, double v) { acb_set_d_d(z, v, 0.0); }
+void acb_set_d_d(acb_t z, double re, double im) {
+    arb_set_double(&z->real, re);
+    arb_set_double(&z->imag, im);
+}
+void acb_neg(acb_t z, const acb_t x) {
+    acb_set(z, x);
+    if (!(z->real.meta.flags & (CB_FLAG_ZERO | CB_FLAG_NAN))) z->real.meta.flags ^= CB_FLAG_SIGN;
+    if (!(z->imag.meta.flags & (CB_FLAG_ZERO | CB_FLAG_NAN))) z->imag.meta.flags ^= CB_FLAG_SIGN;
+}
+int acb_is_zero(const acb_t x) { return arb_exact_zero(&x->real) && arb_exact_zero(&x->imag); }
+int acb_is_finite(const acb_t x) { return !((x->real.meta.flags | x->imag.meta.flags) & CB_FLAG_NAN); }
+int acb_contains_zero(const acb_t x) { return arb_has_zero(&x->real) && arb_has_zero(&x->imag); }
+double acb_get_mid_re_d(const acb_t x) { return arb_mid_d(&x->real); }
+double acb_get_mid_im_d(const acb_t x) { return arb_mid_d(&x->imag); }
+double acb_get_rad_re_d(const acb_t x) { return arb_rad_d(&x->real); }
+void acb_printd(const acb_t x, slong digits) {
+    printf("(%.*g + %.*gj)  +/-  (%.3g, %.3gj)", (int)digits, arb_mid_d(&x->real), (int)digits, arb_mid_d(&x->imag),
+           arb_rad_d(&x->real), arb_rad_d(&x->imag));
+}
+acb_ptr _acb_vec_init(slong n) {
+    acb_ptr v = (acb_ptr)malloc(sizeof(acb_struct) * (n > 0 ? n : 1));
+    for (slong i = 0; i < n; i++) acb_zero(v + i);
+    return v;
+}
+void _acb_vec_clear(acb_ptr v, slong) { free(v); }
+
+void acb_poly_init(acb_poly_t p) {
+    p->coeffs = nullptr;
+    p->length = p->alloc = 0;
+}
+void acb_poly_clear(acb_poly_t p) {
+    free(p->coeffs);
+    p->coeffs = nullptr;
+    p->length = p->alloc = 0;
+}
+void acb_poly_fit_length(acb_poly_t p, slong len) {
+    if (len <= p->alloc) return;
+    slong na = len > 2 * p->alloc ? len : 2 * p->alloc;
+    p->coeffs = (acb_struct*)realloc(p->coeffs, sizeof(acb_struct) * na);
+    for (slong i = p->alloc; i < na; i++) acb_zero(p->coeffs + i);
+    p->alloc = na;
+}
+static void poly_normalise(acb_poly_t p) {
+    while (p->length > 0 && acb_is_zero(p->coeffs + p->length - 1)) p->length--;
+}
+void acb_poly_zero(acb_poly_t p) {
+    for (slong i = 0; i < p->length; i++) acb_zero(p->coeffs + i);
+    p->length = 0;
+}
+void acb_poly_one(acb_poly_t p) {
+    acb_poly_zero(p);
+    acb_poly_set_coeff_si(p, 0, 1);
+}
+slong acb_poly_length(const acb_poly_t p) { return p->length; }
+void acb_poly_set_coeff_acb(acb_poly_t p, slong n, const acb_t c) {
+    acb_poly_fit_length(p, n + 1);
+    if (n + 1 > p->length) {
+        for (slong i = p->length; i < n; i++) acb_zero(p->coeffs + i);
+        p->length = n + 1;
+    }
+    acb_set(p->coeffs + n, c);
+    poly_normalise(p);
+}
+void acb_poly_set_coeff_si(acb_poly_t p, slong n, slong c) {
+    acb_t t;
+    acb_set_si(t, c);
+    acb_poly_set_coeff_acb(p, n, t);
+}
+void acb_poly_get_coeff_acb(acb_t c, const acb_poly_t p, slong n) {
+    if (n < 0 || n >= p->length)
+        acb_zero(c);
+    else
+        acb_set(c, p->coeffs + n);
+}
+int acb_poly_is_zero(const acb_poly_t p) { return p->length == 0; }
+void acb_poly_printd(const acb_poly_t p, slong digits) {
+    printf("[");
+    for (slong i = 0; i < p->length; i++) {
+        acb_printd(p->coeffs + i, digits);
+        if (i + 1 < p->length) printf("\n");
+    }
+    printf("]\n");
+}
+void flint_cleanup(void) {}
+
+void acb_add(acb_t z, const acb_t x, const acb_t y, slong prec) { ew(CB200_OP_ADD, z, x, y, nullptr, prec); }
+void acb_sub(acb_t z, const acb_t x, const acb_t y, slong prec) { ew(CB200_OP_SUB, z, x, y, nullptr, prec); }
+void acb_mul(acb_t z, const acb_t x, const acb_t y, slong prec) { ew(CB200_OP_MUL, z, x, y, nullptr, prec); }
+void acb_div(acb_t z, const acb_t x, const acb_t y, slong prec) { ew(CB200_OP_DIV, z, x, y, nullptr, prec); }
+void acb_mul_si(acb_t z, const acb_t x, slong k, slong prec) {
+    int64_t kk = k;
+    ew(CB200_OP_MUL_SI, z, x, nullptr, &kk, prec);
+}
+void acb_add_si(acb_t z, const acb_t x, slong k, slong prec) {
+    int64_t kk = k;
+    ew(CB200_OP_ADD_SI, z, x, nullptr, &kk, prec);
+}
+void acb_poly_evaluate(acb_t y, const acb_poly_t f, const acb_t x, slong prec) {
+    int L = limbs_of(prec);
+    slong len = f->length;
+    HostArr hf(L, len > 0 ? len : 1, 2), hp(L, 1, 2), ho(L, 1, 2);
+    for (slong i = 0; i < len; i++) hf.put(i, 0, f->coeffs + i);
+    hp.put(0, 0, x);
+    int rc = cb200_horner_batch_host(L, len, 1, 1, hf.m.data(), hf.t.data(), 1, hp.m.data(), hp.t.data(), ho.m.data(),
+                                     ho.t.data(), 0);
+    if (rc) die("cb200_horner_batch_host", rc);
+    ho.get(0, 0, y);
+}
+
+// ------------------------------------------------------------------ operators
+void acb_ode_init_blank(acb_ode_t ODE, slong degree, slong order) {
+    ODE->order = order;
+    ODE->degree = degree;
+    ODE->polys = nullptr;
+    ODE->alloc = 0;
+    ODE->valuation = UNDEFINED_VAL;
+    if (degree < 0 || order <= 0) return;
+    ODE->alloc = (order + 1) * (degree + 1);
+    ODE->polys = _acb_vec_init(ODE->alloc);
+}
+void acb_ode_init(acb_ode_t ODE, acb_poly_t* polys, slong order) {
+    while (order > 0 && acb_poly_is_zero(polys[order])) order--;
+    slong deg = 0;
+    for (slong i = 0; i <= order; i++)
+        if (acb_poly_length(polys[i]) - 1 > deg) deg = acb_poly_length(polys[i]) - 1;
+    acb_ode_init_blank(ODE, order <= 0 ? -1 : deg, order);
+    for (slong i = 0; i <= order && ODE->polys; i++) {
+        for (slong j = 0; j < acb_poly_length(polys[i]); j++) acb_poly_get_coeff_acb(acb_ode_coeff(ODE, i, j), polys[i], j);
+    }
+}
+void acb_ode_clear(acb_ode_t ODE) {
+    if (ODE->alloc <= 0) return;
+    free(ODE->polys);
+    ODE->polys = nullptr;
+    ODE->alloc = 0;
+}
+void acb_ode_set(acb_ode_t out, acb_ode_t in) {
+    if (out->alloc < in->alloc) {
+        acb_ode_clear(out);
+        acb_ode_init_blank(out, in->degree, in->order);  // the intended argument order
+    }
+    memcpy(out->polys, in->polys, sizeof(acb_struct) * in->alloc);
+    out->degree = in->degree;
+    out->order = in->order;
+    out->valuation = acb_ode_valuation(in);
+}
+void acb_ode_dump(acb_ode_t ODE, char* file) {
+    FILE* out = file ? fopen(file, "w") : stdout;
+    if (!out) return;
+    fprintf(out, "Order: %ld\nDegree: %ld\n", ODE->order, ODE->degree);
+    for (slong i = 0; i <= ODE->order; i++) {
+        fprintf(out, "acb_ode_poly(ODE, %ld) = ", i);
+        for (slong j = 0; j <= ODE->degree; j++) {
+            const acb_struct* c = acb_ode_coeff(ODE, i, j);
+            fprintf(out, "(%.20g + %.20gj)  +/-  (%.3g, %.3gj)\t", arb_mid_d(&c->real), arb_mid_d(&c->imag),
+                    arb_rad_d(&c->real), arb_rad_d(&c->imag));
+        }
+        fprintf(out, "\n");
+    }
+    if (out != stdout) fclose(out);
+}
+slong acb_ode_valuation(acb_ode_t ODE) {
+    if (ODE->valuation != UNDEFINED_VAL) return ODE->valuation;
+    slong val = ODE->degree;
+    for (slong i = 0; i <= ODE->order; i++) {
+        slong v = 0;
+        while (v <= ODE->degree && acb_is_zero(acb_ode_coeff(ODE, i, v))) v++;
+        if (v - i < val) val = v - i;
+    }
+    ODE->valuation = val;
+    return val;
+}
+void acb_ode_shift(acb_ode_t out, acb_ode_t in, acb_srcptr a, slong bits) {
+    acb_ode_set(out, in);
+    if (acb_is_zero(a) || in->degree == 0) return;
+    slong n = out->degree + 1;
+    acb_t t;
+    for (slong row = 0; row <= out->order; row++) {
+        acb_ptr p = acb_ode_poly(out, row);
+        for (slong i = n - 2; i >= 0; i--)
+            for (slong j = i; j <= n - 2; j++) {  // p[j] += p[j+1] * a   (Horner Taylor shift)
+                acb_mul(t, p + j + 1, a, bits);
+                acb_add(p + j, p + j, t, bits);
+            }
+    }
+    out->valuation = UNDEFINED_VAL;
+}
+
+// ------------------------------------------------------------------ solutions
+void acb_ode_solution_init(acb_ode_solution_t sol, acb_t rho, slong mul, slong alpha) {
+    sol->mul = mul;
+    sol->M = mul + alpha;
+    acb_set(sol->rho, rho);
+    sol->gens = (acb_poly_struct*)malloc(sizeof(acb_poly_struct) * (sol->M > 0 ? sol->M : 1));
+    for (slong i = 0; i < sol->M; i++) acb_poly_init(sol->gens + i);
+}
+void acb_ode_solution_clear(acb_ode_solution_t sol) {
+    for (slong i = 0; i < sol->M; i++) acb_poly_clear(sol->gens + i);
+    free(sol->gens);
+    sol->gens = nullptr;
+}
+
+// ------------------------------------------------------------------ examples
+void acb_ode_legendre(acb_ode_t ODE, ulong n) {
+    acb_ode_init_blank(ODE, 2, 2);
+    acb_set_si(acb_ode_coeff(ODE, 0, 0), (slong)(n * (n + 1)));
+    acb_set_si(acb_ode_coeff(ODE, 1, 1), -2);
+    acb_set_si(acb_ode_coeff(ODE, 2, 0), 1);
+    acb_set_si(acb_ode_coeff(ODE, 2, 2), -1);
+}
+void acb_ode_bessel(acb_ode_t ODE, acb_t nu, slong bits) {
+    acb_ode_init_blank(ODE, 2, 2);
+    acb_set_si(acb_ode_coeff(ODE, 2, 2), 1);
+    acb_set_si(acb_ode_coeff(ODE, 1, 1), 1);
+    acb_set_si(acb_ode_coeff(ODE, 0, 2), 1);
+    acb_mul(nu, nu, nu, bits);
+    acb_neg(acb_ode_coeff(ODE, 0, 0), nu);
+}
+void acb_ode_hypgeom(acb_ode_t ODE, acb_t a, acb_t b, acb_t c, slong bits) {
+    acb_ode_init_blank(ODE, 2, 2);
+    acb_t temp;
+    acb_set_si(acb_ode_coeff(ODE, 2, 1), 1);
+    acb_set_si(acb_ode_coeff(ODE, 2, 2), -1);
+    acb_set(acb_ode_coeff(ODE, 1, 0), c);
+    acb_one(temp);
+    acb_add(temp, temp, a, bits);
+    acb_add(temp, temp, b, bits);
+    acb_neg(acb_ode_coeff(ODE, 1, 1), temp);
+    acb_mul(temp, a, b, bits);
+    acb_neg(acb_ode_coeff(ODE, 0, 0), temp);
+}
+
+// ------------------------------------------------------------------ solvers
+void acb_ode_solve_fuchs(acb_poly_t res, acb_ode_t ODE, slong deg, slong bits) {
+    int L = limbs_of(bits);
+    slong v = acb_ode_valuation(ODE);
+    slong ne = (ODE->order + 1) * (ODE->degree + 1);
+    HostArr ho(L, ne, 2), hr(L, deg + 1, 2);
+    for (slong e = 0; e < ne; e++) ho.put(e, 0, ODE->polys + e);
+    for (slong k = 0; k < -v && k <= deg; k++) {
+        acb_t c;
+        acb_poly_get_coeff_acb(c, res, k);
+        hr.put(k, 0, c);
+    }
+    int rc = cb200_fuchs_batch_host(L, (int)ODE->order, (int)ODE->degree, (int)v, deg, 1, ho.m.data(), ho.t.data(), 1,
+                                    hr.m.data(), hr.t.data(), 0);
+    if (rc) die("acb_ode_solve_fuchs (cb200_fuchs_batch_host)", rc);
+    acb_poly_fit_length(res, deg + 1);
+    for (slong k = 0; k <= deg; k++) hr.get(k, 0, res->coeffs + k);
+    if (res->length < deg + 1) res->length = deg + 1;
+    poly_normalise(res);
+}
+
+void analytic_continuation(acb_poly_t res, acb_ode_t ODE, acb_srcptr path, slong len, slong deg, slong bits) {
+    int L = limbs_of(bits);
+    acb_t a;
+    acb_ode_t shifted;
+    acb_ode_init_blank(shifted, ODE->degree, ODE->order);
+    for (slong time = 0; time + 1 < len; time++) {
+        acb_ode_shift(shifted, ODE, path + time, bits);
+        acb_ode_solve_fuchs(res, shifted, deg, bits);
+        acb_sub(a, path + time + 1, path + time, bits);
+        // res[k] <- y^(k)(a)/k!, k < order: Horner with derivatives on the device
+        int nder = (int)ODE->order;
+        if (nder > 4) die("analytic_continuation: order > 4", -1);
+        slong flen = res->length;
+        HostArr hf(L, flen > 0 ? flen : 1, 2), hp(L, 1, 2), hout(L, nder, 2);
+        for (slong i = 0; i < flen; i++) hf.put(i, 0, res->coeffs + i);
+        hp.put(0, 0, a);
+        int rc = cb200_horner_batch_host(L, flen, 1, nder, hf.m.data(), hf.t.data(), 1, hp.m.data(), hp.t.data(),
+                                         hout.m.data(), hout.t.data(), 0);
+        if (rc) die("analytic_continuation (cb200_horner_batch_host)", rc);
+        acb_poly_zero(res);
+        acb_poly_fit_length(res, nder);
+        for (int k = 0; k < nder; k++) hout.get(k, 0, res->coeffs + k);
+        res->length = nder;
+        poly_normalise(res);
+    }
+    acb_ode_clear(shifted);
+}
+
+void indicial_polynomial_evaluate(acb_t result, acb_ode_t ODE, slong nu, acb_t rho, slong shift, slong prec) {
+    nu += acb_ode_valuation(ODE);
+    if (nu > ODE->degree) {
+        acb_zero(result);
+        return;
+    }
+    acb_t temp1, out, prod;
+    acb_zero(out);
+    for (slong lambda = clamp(ODE->degree - nu, 0, ODE->order); lambda >= 0; lambda--) {
+        acb_add_si(temp1, rho, shift - lambda, prec);
+        acb_mul(prod, out, temp1, prec);
+        acb_set(out, prod);
+        if (lambda + nu < 0) continue;
+        acb_add(out, out, acb_ode_coeff(ODE, lambda, lambda + nu), prec);
+    }
+    acb_set(result, out);
+}
+
+void _acb_ode_solve_frobenius(acb_poly_t res, acb_ode_t ODE, acb_ode_solution_t rhs, slong sol_degree, slong prec) {
+    if (!acb_poly_is_zero(rhs->gens)) die("_acb_ode_solve_frobenius with a nonzero right-hand side (not on the device yet)", -1);
+    int L = limbs_of(prec);
+    slong v = acb_ode_valuation(ODE);
+    slong ne = (ODE->order + 1) * (ODE->degree + 1);
+    HostArr ho(L, ne, 2), hrho(L, 1, 2), hr(L, sol_degree + 1, 2);
+    for (slong e = 0; e < ne; e++) ho.put(e, 0, ODE->polys + e);
+    hrho.put(0, 0, rhs->rho);
+    int rc = cb200_frobenius1_batch_host(L, (int)ODE->order, (int)ODE->degree, (int)v, sol_degree, 1, ho.m.data(),
+                                         ho.t.data(), 1, hrho.m.data(), hrho.t.data(), 1, hr.m.data(), hr.t.data(), 0);
+    if (rc) die("_acb_ode_solve_frobenius (cb200_frobenius1_batch_host)", rc);
+    acb_poly_zero(res);
+    acb_poly_fit_length(res, sol_degree + 1);
+    for (slong k = 0; k <= sol_degree; k++) hr.get(k, 0, res->coeffs + k);
+    res->length = sol_degree + 1;
+    poly_normalise(res);
+}
+
+void acb_ode_solve_frobenius(acb_ode_solution_t sol, acb_ode_t ODE, slong sol_degree, slong prec) {
+    if (sol->M == 1) {
+        _acb_ode_solve_frobenius(sol->gens, ODE, sol, sol_degree, prec);
+        return;
+    }
+    die("acb_ode_solve_frobenius with M > 1 (logarithmic case: listed as next in DESIGN.md)", -1);
+}
+
+}  // extern "C"

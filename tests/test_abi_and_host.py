@@ -1,0 +1,83 @@
+"""CPU-side checks of the boundary: the C-ABI library loads and exports every symbol the headers
+declare (no compute calls without a GPU), refuses to run without a device, and the host logic
+(valuation, layout packing, partitioning) behaves as the reference's."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from cascade_b200 import _lib, api, sharding
+from cascade_b200.format import (FLAG_ZERO, Balls, entry_major_to_instance_major, from_complex,
+                                 instance_major_to_entry_major, pack_entries, random_balls, unpack_entries)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(cb200_\w+|acb_ode_\w+|_acb_ode_\w+|analytic_continuation|indicial_polynomial_evaluate)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.lib()
+    names = declared("cascade_b200.h")
+    assert set(_lib.SYMBOLS) <= set(names)
+    for name in names + [n for n in declared("cascade_compat.h") if not n.endswith("_struct")]:
+        if name in ("acb_ode_poly", "acb_ode_coeff", "acb_ode_t", "acb_ode_solution_t"):
+            continue  # macros / types
+        assert hasattr(lib, name), f"{name} is declared in include/ but not exported"
+    assert b"sm_100a" in lib.cb200_version()
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every compute entry point must fail loudly, never compute on the CPU."""
+    lib = _lib.lib()
+    if lib.cb200_device_count() > 0:
+        pytest.skip("a GPU is present")
+    x = from_complex([1, 2], 32)
+    with pytest.raises(_lib.CascadeB200Error):
+        api.ew(api.OP_MUL, x, x)
+
+
+def test_valuation_matches_reference_rule():
+    """reference src/acb_ode.c:159-181 on the three shipped examples (src/examples.c)."""
+    L = 32
+    assert api.acb_ode_valuation(api.acb_ode_legendre_batch([4], L), 2, 2) == -2
+    # hypgeom: z(1-z) y'' + ... : valuation -1;  Bessel at the origin: valuation 0
+    hyp = Balls.zeros(18, L)
+    one = from_complex([1], L)
+    for e in (2 * 3 + 1, 2 * 3 + 2, 1 * 3 + 0, 1 * 3 + 1, 0):
+        hyp.mant[2 * e:2 * e + 2] = one.mant
+        hyp.meta[2 * e:2 * e + 2] = one.meta
+    assert api.acb_ode_valuation(hyp, 2, 2) == -1
+    bes = Balls.zeros(18, L)
+    for e in (2 * 3 + 2, 1 * 3 + 1, 0 * 3 + 2, 0):
+        bes.mant[2 * e:2 * e + 2] = one.mant
+        bes.meta[2 * e:2 * e + 2] = one.meta
+    assert api.acb_ode_valuation(bes, 2, 2) == 0
+    with pytest.raises(_lib.CascadeB200Error):
+        api.acb_ode_solve_fuchs_batch(bes, Balls.zeros(0, L), 2, 2, 5, 1, True)
+
+
+def test_layout_roundtrip():
+    rng = np.random.default_rng(0)
+    b = random_balls(rng, 5 * 7 * 2, 4, -3, 3, "ulp")
+    e = instance_major_to_entry_major(b, 5, 7)
+    m, t = pack_entries(e, 7, 10)
+    assert m.shape == (7, 4, 10) and t.shape == (7, 10, 4)
+    # limb-major: limb k of slot s of entry e
+    assert m[3, 2, 5] == e.mant[3 * 10 + 5, 2]
+    back = entry_major_to_instance_major(unpack_entries(4, m, t), 5, 7)
+    assert back.same_as(b)
+
+
+def test_partition_covers_batch():
+    for batch in (1, 7, 64, 65536, 1000003):
+        for world in (1, 2, 4, 8):
+            spans = [sharding.partition(batch, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == batch
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1

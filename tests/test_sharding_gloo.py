@@ -1,0 +1,53 @@
+"""world_size-2 run of the N>1 path on CPU (gloo): each rank solves its block of the batch with
+the host-simulated device code, results are all-gathered, and must be BIT-IDENTICAL to the
+single-rank result (pure batch partitioning)."""
+import os
+import socket
+
+import numpy as np
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cascade_b200 import api, sharding
+from cascade_b200.format import random_balls
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import cbo
+    from tests.cases import bessel_shifted
+    from tests.host_sim.driver import SimDriver
+    rng = np.random.default_rng(99)
+    L, batch, n = 4, 7, 24  # odd batch: uneven shards
+    ode = bessel_shifted(cbo, rng, L)
+    init = random_balls(rng, batch * 4, L, -1, 0, "zero")
+    full = sharding.solve_fuchs_sharded(ode, init, 2, 2, n, batch, True, driver=SimDriver())
+    if rank == 0:
+        single = api.acb_ode_solve_fuchs_batch(ode, init, 2, 2, n, batch, True, driver=SimDriver())
+        rc, ref = cbo.fuchs_batch(2, 2, n, ode, init, batch, True)
+        out.put((full.same_as(single), full.same_as(ref)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_bit_identical():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    same_single, same_oracle = out.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert same_single and same_oracle
