@@ -81,7 +81,8 @@ size_t cb200_fuchs_workspace_bytes(int L, int order, int degree, int valuation, 
     if (!shared_ode || valuation >= 0) return carve_bytes(L, FUCHS_NTMP, 2 * batch);
     int64_t rows = n + 1 + valuation, W = degree - valuation;
     if (rows < 0) rows = 0;
-    return carve_bytes(L, rows * (W + 2), 2) + carve_bytes(L, 2, 2 * rows) + align256(sizeof(int32_t) * (rows + 1));
+    return carve_bytes(L, rows * (W + 2), 2) + carve_bytes(L, 2, 2 * rows) + align256(sizeof(int32_t) * (rows + 1)) +
+           align256((size_t)2 * (2 * L + 3) * batch * sizeof(uint32_t));
 }
 size_t cb200_frobenius_workspace_bytes(int L, int64_t batch) { return carve_bytes(L, FROB_NTMP, 2 * batch); }
 size_t cb200_horner_workspace_bytes(int L, int64_t npts) { return carve_bytes(L, 1, 2 * npts); }
@@ -111,6 +112,7 @@ int cb200_fuchs_batch_dev(int L_, int order, int degree, int valuation, int64_t 
         tp.tbl = carve(w, L_, rows * (W + 2), 2);
         tp.tmp = carve(w, L_, 2, 2 * rows);
         tp.kind = (int32_t*)w;
+        w += align256(sizeof(int32_t) * (rows + 1));
         g_launches.fetch_add(1);
         int rc = table_for(L_)->fuchs_table(tp, (cudaStream_t)stream);
         if (rc) return rc;
@@ -123,10 +125,7 @@ int cb200_fuchs_batch_dev(int L_, int order, int degree, int valuation, int64_t 
         sp.tbl = tp.tbl;
         sp.res = CArr{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
         sp.kind = tp.kind;
-        {
-            const char* ds = getenv("CB200_DESYNC");
-            sp.desync_cycles = ds ? atoi(ds) : 0;
-        }
+        sp.gcols = (uint32_t*)w;
         g_launches.fetch_add(batch > 0);
         return table_for(L_)->fuchs_shared(sp, (cudaStream_t)stream);
     }

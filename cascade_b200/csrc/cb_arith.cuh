@@ -26,9 +26,20 @@
 #define CB_NOINLINE __attribute__((noinline))
 #endif
 
+#if defined(CB_COUNT_PATHS) && !defined(__CUDA_ARCH__)
+extern "C" long long cb_path_counts[8];  // host-sim statistics: [0] fdot fast, [1] fdot general, [2] add fast, [3] add general
+#define CB_COUNT(i) (cb_path_counts[i]++)
+#else
+#define CB_COUNT(i) ((void)0)
+#endif
+
 namespace cb {
 
 constexpr uint32_t F_SIGN = 1u, F_ZERO = 2u, F_NAN = 4u;
+// Internal hint, never part of a result: bits 8..15 of flags may hold a lower bound on the number
+// of trailing zero LIMBS of the mantissa (set by the table kernel on the shared multipliers).
+constexpr int F_TZ_SHIFT = 8;
+CB_HD int tz_hint(uint32_t flags) { return (int)((flags >> F_TZ_SHIFT) & 0xFFu); }
 constexpr int32_t EXP_LIMIT = 1 << 28;
 
 struct Meta {
@@ -466,10 +477,19 @@ CB_HD void store_nan(DST dst) {
 //   V_i = X_i * 2^(E - s_i - 32 N),  X_i given word by word by x_i(k), k in [0, N) (0 if zero).
 // Returns false without touching dst when the case is not the easy one (operand order guess of a
 // subtraction wrong, or more than a limb cancelled): the caller then takes the general path.
-template <int L, int N, class DST, class X1, class X2>
+// KLOW > 0 (truncated products): words k < KLOW of both operands are not available -- the operands
+// are the high products of mul_high with K = KLOW dropped columns, i.e. each true operand exceeds the
+// given one by less than (K+1) 2^(32(K+1)) -- and the result is only accepted when the guard bits
+// just below the rounding position prove that the missing low part cannot change the truncated
+// mantissa (then the result is certainly inexact); otherwise false is returned.
+// trusted: the caller knows that nothing nonzero was dropped (both products have at least KLOW
+// trailing zero limbs in total), so the available words are exact and no guard check is needed.
+template <int L, int N, int KLOW = 0, class DST, class X1, class X2>
 CB_HD bool fast_add_round(DST dst, X1 x1, X2 x2, int s1, int s2, bool sub, bool n1, bool n2, int64_t E,
-                          Rounded* rr, bool* neg) {
-    uint32_t R[N + 2];
+                          Rounded* rr, bool* neg, bool trusted = false) {
+    constexpr bool TRUNC = KLOW > 0;
+    uint32_t Rs[N + 2 - KLOW];
+#define R_(i) Rs[(i) - KLOW]
     bool swapped = false;
     if (sub) {  // compare the top 64 aligned bits: W_i[N], W_i[N-1] with T_i[k] = X_i[k-1]
         uint32_t a2 = x1(N - 1), a1 = x1(N - 2), a0 = (N >= 3) ? x1(N - 3) : 0u;
@@ -483,30 +503,30 @@ CB_HD bool fast_add_round(DST dst, X1 x1, X2 x2, int s1, int s2, bool sub, bool 
     const uint32_t m1 = (sub && swapped) ? 0xFFFFFFFFu : 0u;
     const uint32_t m2 = (sub && !swapped) ? 0xFFFFFFFFu : 0u;
     uint32_t carry = sub ? 1u : 0u;
-    uint32_t t1c = 0u, t2c = 0u;  // T_i[k]; T_i[0] = 0 (guard limb)
+    uint32_t t1c = 0u, t2c = 0u;  // T_i[k]; T_i[KLOW] = 0 (guard limb / first dropped word)
 #pragma unroll
-    for (int k = 0; k <= N; k++) {
+    for (int k = KLOW; k <= N; k++) {
         uint32_t t1n = (k < N) ? x1(k) : 0u, t2n = (k < N) ? x2(k) : 0u;
         uint32_t w1 = shr_pair(t1c, t1n, s1), w2 = shr_pair(t2c, t2n, s2);
         uint64_t t = (uint64_t)(w1 ^ m1) + (uint64_t)(w2 ^ m2) + carry;
-        R[k] = (uint32_t)t;
+        R_(k) = (uint32_t)t;
         carry = (uint32_t)(t >> 32);
         t1c = t1n;
         t2c = t2n;
     }
     if (sub && carry == 0u) return false;  // |W2| > |W1| after all (tie in the top 64 bits)
-    R[N + 1] = sub ? 0u : carry;
+    R_(N + 1) = sub ? 0u : carry;
     int hi;
     uint32_t top;
-    if (R[N + 1]) {
+    if (R_(N + 1)) {
         hi = N + 1;
-        top = R[N + 1];
-    } else if (R[N]) {
+        top = R_(N + 1);
+    } else if (R_(N)) {
         hi = N;
-        top = R[N];
-    } else if (R[N - 1]) {
+        top = R_(N);
+    } else if (R_(N - 1)) {
         hi = N - 1;
-        top = R[N - 1];
+        top = R_(N - 1);
     } else {
         return false;  // a limb or more cancelled (or the result is zero)
     }
@@ -514,16 +534,48 @@ CB_HD bool fast_add_round(DST dst, X1 x1, X2 x2, int s1, int s2, bool sub, bool 
     const int off = bl - 32 * L;
     const int q = off >> 5, r = off & 31;
     constexpr int QMIN = N - 1 - L;  // q is in [QMIN, QMIN + 3]
-    auto Rx = [&](int idx) -> uint32_t { return (idx >= 0 && idx <= N + 1) ? R[idx] : 0u; };
-    // discarded bits: words below q, and the low r bits of word q
+    auto Rx = [&](int idx) -> uint32_t { return (idx >= KLOW && idx <= N + 1) ? R_(idx) : 0u; };
     uint32_t low = 0u;
+    if constexpr (TRUNC) {
+        // Error of the sum from the dropped columns: < 2 (K+1) 2^(32(K+2)) < 2^B.  The 24 bits just
+        // below the rounding position must be neither all zero nor all one.
+        constexpr int LOGK = (KLOW + 1 <= 2) ? 1 : (KLOW + 1 <= 4) ? 2 : (KLOW + 1 <= 8) ? 3 : (KLOW + 1 <= 16) ? 4
+                             : (KLOW + 1 <= 32) ? 5 : (KLOW + 1 <= 64) ? 6 : 7;
+        constexpr int B = 32 * (KLOW + 2) + 1 + LOGK;
+        static_assert(32 * (N - 1) + 1 - 32 * L - 24 >= B, "not enough guard bits for this truncation");
+        static_assert(QMIN - 1 >= KLOW, "guard word must be available");
+        uint32_t lo_w = 0u, hi_w = 0u;  // words q-1 and q
 #pragma unroll
-    for (int i = 0; i < QMIN; i++) low |= R[i];
+        for (int i = QMIN - 1; i < QMIN + 4; i++) {
+            uint32_t w = Rx(i);
+            lo_w = (i == q - 1) ? w : lo_w;
+            hi_w = (i == q) ? w : hi_w;
+        }
+        uint32_t g = shr_pair(lo_w, hi_w, r) >> 8;  // bits [off-24, off)
+        if (!trusted) {
+            if (g == 0u || g == 0xFFFFFFu) return false;
+            low = 1u;  // proven inexact
+        } else {
+            // exact words: discarded = words KLOW..q-1 and the low r bits of word q
 #pragma unroll
-    for (int i = QMIN; i < QMIN + 4; i++) {
-        uint32_t w = Rx(i);
-        low |= (i < q) ? w : 0u;
-        low |= (i == q) ? (w & ((1u << r) - 1u)) : 0u;
+            for (int i = KLOW; i < QMIN; i++) low |= R_(i);
+#pragma unroll
+            for (int i = QMIN; i < QMIN + 4; i++) {
+                uint32_t w = Rx(i);
+                low |= (i < q) ? w : 0u;
+                low |= (i == q) ? (w & ((1u << r) - 1u)) : 0u;
+            }
+        }
+    } else {
+        // discarded bits: words below q, and the low r bits of word q
+#pragma unroll
+        for (int i = 0; i < QMIN; i++) low |= R_(i);
+#pragma unroll
+        for (int i = QMIN; i < QMIN + 4; i++) {
+            uint32_t w = Rx(i);
+            low |= (i < q) ? w : 0u;
+            low |= (i == q) ? (w & ((1u << r) - 1u)) : 0u;
+        }
     }
     // dst[i - q] = bits [32 i + r, 32 i + r + 32) of R, for the L words with 0 <= i - q < L
 #pragma unroll
@@ -539,6 +591,7 @@ CB_HD bool fast_add_round(DST dst, X1 x1, X2 x2, int s1, int s2, bool sub, bool 
     rr->inexact = low != 0u;
     *neg = (sub && swapped) ? n2 : n1;
     return true;
+#undef R_
 }
 
 // ---------------------------------------------------------------- arb level
@@ -594,6 +647,7 @@ CB_NOINLINE Meta arb_fdot2(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2, OpdT<
             auto w2 = [&](int k) -> uint32_t { return z2 ? 0u : r[k]; };
             done = fast_add_round<L, 2 * L>(dst, w1, w2, s1, s2, sub, z1 ? n2 : n1, z1 ? n1 : n2, E, &rr, &neg);
         }
+        CB_COUNT(done ? 0 : 1);
         if (!done) {
 #pragma unroll
             for (int k = 0; k < 2 * L; k++) S1.st(k, r[k]);
@@ -607,6 +661,144 @@ CB_NOINLINE Meta arb_fdot2(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2, OpdT<
         }
         rr = align_add<L, 2 * L>(dst, S0, S1, e1, e2, n1, n2, z1, z2, &neg);
     }
+    if (nan) return meta_nan();
+    return finish<L>(rr, neg, rad);
+}
+
+// ---- the recurrence kernel's variant: truncated products first, exact general path as fallback
+// A column in global memory ([word][thread] layout like the shared ones): only the rarely taken
+// general path of the recurrence kernel uses it.
+struct GScratch {
+    uint32_t* p;
+    size_t stride;
+    CB_HD uint32_t ld(int k) const { return p[(size_t)k * stride]; }
+    CB_HD void st(int k, uint32_t v) const { p[(size_t)k * stride] = v; }
+};
+
+// P[0..2L) = x * y with BLK-limb register blocks accumulated in the column (few registers, slow)
+template <int L, int BLK, class SCR, class XS, class YS>
+CB_HD void product_blocked(SCR P, XS x, YS y) {
+    constexpr int NB = L / BLK;
+#pragma unroll 1
+    for (int k = 0; k < 2 * L; k++) P.st(k, 0u);
+#pragma unroll 1
+    for (int bi = 0; bi < NB; bi++) {
+        uint32_t a[BLK];
+#pragma unroll
+        for (int j = 0; j < BLK; j++) a[j] = x.ld(BLK * bi + j);
+#pragma unroll 1
+        for (int bj = 0; bj < NB; bj++) {
+            uint32_t b[BLK], r[2 * BLK];
+#pragma unroll
+            for (int j = 0; j < BLK; j++) b[j] = y.ld(BLK * bj + j);
+            mul_full<BLK>(r, a, b);
+            int off = BLK * (bi + bj);
+            uint32_t c = 0u;
+#pragma unroll
+            for (int k = 0; k < 2 * BLK; k++) {
+                uint64_t t = (uint64_t)P.ld(off + k) + r[k] + c;
+                P.st(off + k, (uint32_t)t);
+                c = (uint32_t)(t >> 32);
+            }
+#pragma unroll 1
+            for (int k = off + 2 * BLK; c != 0u && k < 2 * L; k++) {
+                uint64_t t = (uint64_t)P.ld(k) + c;
+                P.st(k, (uint32_t)t);
+                c = (uint32_t)(t >> 32);
+            }
+        }
+    }
+}
+
+// exact general fdot2 on two global-memory columns (any exponent gap, any cancellation)
+template <int L, class XS = RRef, class YS = RRef, class DST = WRef>
+CB_NOINLINE Meta arb_fdot2_general(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2, OpdT<YS> y2, bool neg2,
+                                   GScratch G0, GScratch G1) {
+    bool nan = is_nan(x1.t) || is_nan(y1.t) || is_nan(x2.t) || is_nan(y2.t);
+    bool z1 = is_zero_mid(x1.t) || is_zero_mid(y1.t) || nan;
+    bool z2 = is_zero_mid(x2.t) || is_zero_mid(y2.t) || nan;
+    Mag rad = mul_rad(mag_zero(), x1.t, top_limb<L>(x1), y1.t, top_limb<L>(y1));
+    rad = mul_rad(rad, x2.t, top_limb<L>(x2), y2.t, top_limb<L>(y2));
+    bool n1 = ((x1.t.flags ^ y1.t.flags) & F_SIGN) != 0;
+    bool n2 = (((x2.t.flags ^ y2.t.flags) & F_SIGN) != 0) != neg2;
+    const int64_t e1 = (int64_t)x1.t.exp + y1.t.exp, e2 = (int64_t)x2.t.exp + y2.t.exp;
+    constexpr int BLK = (L % 8 == 0) ? 8 : 4;
+#pragma unroll 1
+    for (int term = 0; term < 2; term++) {
+        if (term ? z2 : z1) continue;
+        product_blocked<L, BLK>(term ? G1 : G0, term ? x2.r : x1.r, term ? y2.r : y1.r);
+    }
+    bool neg;
+    Rounded rr = align_add<L, 2 * L>(dst, G0, G1, e1, e2, n1, n2, z1, z2, &neg);
+    if (nan) return meta_nan();
+    return finish<L>(rr, neg, rad);
+}
+
+// dst = x1*y1 +- x2*y2 from TRUNCATED products (columns below K = L-4 dropped: 40% fewer limb
+// products); *ok = false (dst untouched... or to be overwritten) when the result cannot be proven
+// equal to the exact one -- the caller then runs arb_fdot2_general.  S0: a shared column of
+// 2L-K+1 words.
+template <int L, class SCR, class XS = RRef, class YS = RRef, class DST = WRef>
+CB_NOINLINE Meta arb_fdot2_trunc(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2, OpdT<YS> y2, bool neg2, SCR S0,
+                                 bool* ok) {
+    static_assert(L >= 16 && L <= 32, "truncated products are used for 512..1024-bit mantissas");
+    constexpr int K = L - 4, PW = 2 * L - K;
+    bool nan = is_nan(x1.t) || is_nan(y1.t) || is_nan(x2.t) || is_nan(y2.t);
+    bool z1 = is_zero_mid(x1.t) || is_zero_mid(y1.t) || nan;
+    bool z2 = is_zero_mid(x2.t) || is_zero_mid(y2.t) || nan;
+    Mag rad = mul_rad(mag_zero(), x1.t, top_limb<L>(x1), y1.t, top_limb<L>(y1));
+    rad = mul_rad(rad, x2.t, top_limb<L>(x2), y2.t, top_limb<L>(y2));
+    bool n1 = ((x1.t.flags ^ y1.t.flags) & F_SIGN) != 0;
+    bool n2 = (((x2.t.flags ^ y2.t.flags) & F_SIGN) != 0) != neg2;
+    const int64_t e1 = (int64_t)x1.t.exp + y1.t.exp, e2 = (int64_t)x2.t.exp + y2.t.exp;
+    bool skip1 = warp_all(z1), skip2 = warp_all(z2);
+    uint32_t r[PW];
+#pragma unroll 1
+    for (int term = 0; term < 2; term++) {  // a loop, so that the product code exists once
+        if (term == 1) {
+#pragma unroll
+            for (int k = 0; k < PW; k++) S0.st(k, r[k]);
+        }
+        if (term ? skip2 : skip1) {
+#pragma unroll
+            for (int k = 0; k < PW; k++) r[k] = 0u;
+            continue;
+        }
+        uint32_t a[L], b[L];
+        XS xs = term ? x2.r : x1.r;
+        YS ys = term ? y2.r : y1.r;
+#pragma unroll
+        for (int j = 0; j < L; j++) a[j] = xs.ld(j);
+#pragma unroll
+        for (int j = 0; j < L; j++) b[j] = ys.ld(j);
+        mul_high<L, K>(r, a, b);
+    }
+    int64_t d = e1 - e2;
+    bool easy = !(z1 && z2) && (z1 || z2 || (d <= 31 && d >= -31));
+    bool done = false, neg = false;
+    Rounded rr;
+    rr.exp = 0;
+    rr.zero = true;
+    rr.inexact = false;
+    rr.overflow = false;
+    if (z1 && z2) {  // exact zero midpoint (also the indeterminate case): nothing to round
+#pragma unroll 4
+        for (int j = 0; j < L; j++) dst.st(j, 0u);
+        done = true;
+    } else if (easy) {
+        int64_t E = z1 ? e2 : (z2 ? e1 : (e1 > e2 ? e1 : e2));
+        int s1 = z1 ? 0 : (int)(E - e1), s2 = z2 ? 0 : (int)(E - e2);
+        bool sub = (n1 != n2) && !z1 && !z2;
+        // word k of the (truncated) product i, k in [K, 2L)
+        auto w1 = [&](int k) -> uint32_t { return z1 ? 0u : S0.ld(k - K); };
+        auto w2 = [&](int k) -> uint32_t { return z2 ? 0u : r[k - K]; };
+        // products whose operands have >= K trailing zero limbs in total lose nothing to truncation
+        bool trusted = (z1 || tz_hint(x1.t.flags) + tz_hint(y1.t.flags) >= K) &&
+                       (z2 || tz_hint(x2.t.flags) + tz_hint(y2.t.flags) >= K);
+        done = fast_add_round<L, 2 * L, K>(dst, w1, w2, s1, s2, sub, z1 ? n2 : n1, z1 ? n1 : n2, E, &rr, &neg,
+                                           trusted);
+    }
+    *ok = done;
     if (nan) return meta_nan();
     return finish<L>(rr, neg, rad);
 }
@@ -652,6 +844,7 @@ CB_NOINLINE Meta arb_addsub_cols(SCR A, Meta ta, SCR B, Meta tb, bool negb, SCR*
             if (done) *where = B;
         }
     }
+    CB_COUNT(done ? 2 : 3);
     if (!done)
         rr = align_add<L, L, true>(A, A, B, ta.exp, tb.exp, na, nb, zx, zy, &neg, where);
     if (nan) return meta_nan();

@@ -18,7 +18,10 @@ template <> struct Cfg<128> { static constexpr int TPB = 64; };
 // accumulator columns per thread)
 template <int L> struct CfgShared;
 template <> struct CfgShared<4> { static constexpr int TPB = 128; };
-template <> struct CfgShared<32> { static constexpr int TPB = 224; };
+#ifndef CB_TPB_SHARED_32
+#define CB_TPB_SHARED_32 320
+#endif
+template <> struct CfgShared<32> { static constexpr int TPB = CB_TPB_SHARED_32; };
 template <> struct CfgShared<64> { static constexpr int TPB = 96; };
 template <> struct CfgShared<128> { static constexpr int TPB = 32; };
 
@@ -26,7 +29,11 @@ template <int L> struct Sizes {
     static constexpr int WORDS = 2 * L + 3;  // words per product scratch column
     static constexpr int AWORDS = L + 2;     // words per accumulator column
     static constexpr size_t SMEM = (size_t)2 * WORDS * Cfg<L>::TPB * sizeof(uint32_t);
-    static constexpr size_t SMEM_SHARED = (size_t)(2 * WORDS + 3 * AWORDS) * CfgShared<L>::TPB * sizeof(uint32_t);
+    // recurrence kernel: with truncated products S0 only parks a high product (L+5 words) and the
+    // second full column lives in global memory (general path only)
+    static constexpr int S0WORDS = use_trunc<L>() ? (L + 5) : WORDS;
+    static constexpr int S1WORDS = use_trunc<L>() ? 0 : WORDS;
+    static constexpr size_t SMEM_SHARED = (size_t)(S0WORDS + S1WORDS + 3 * AWORDS) * CfgShared<L>::TPB * sizeof(uint32_t);
 };
 
 #define CB_KERNEL_PROLOGUE(COUNT)                                                              \
@@ -68,22 +75,16 @@ template <int L>
 __global__ void __launch_bounds__(CfgShared<L>::TPB, 1) fuchs_shared_kernel(FuchsSharedParams p) {
     extern __shared__ uint32_t cb_smem[];
     constexpr int TPB = CfgShared<L>::TPB;
-    constexpr uint32_t W = Sizes<L>::WORDS, AW = Sizes<L>::AWORDS;
+    constexpr uint32_t W0 = Sizes<L>::S0WORDS, W1 = Sizes<L>::S1WORDS, AW = Sizes<L>::AWORDS;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cb_smem) + 4u * threadIdx.x;
-    Scratch<TPB> S0{sbase}, S1{sbase + 4u * W * TPB};
-    Scratch<TPB> A0{sbase + 4u * (2 * W) * TPB}, A1{sbase + 4u * (2 * W + AW) * TPB},
-        A2{sbase + 4u * (2 * W + 2 * AW) * TPB};
+    Scratch<TPB> S0{sbase}, S1{sbase + 4u * W0 * TPB};
+    Scratch<TPB> A0{sbase + 4u * (W0 + W1) * TPB}, A1{sbase + 4u * (W0 + W1 + AW) * TPB},
+        A2{sbase + 4u * (W0 + W1 + 2 * AW) * TPB};
     const int64_t idx = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (idx >= p.batch) return;
-    // All warps run the same instruction sequence, so left alone they hit the IMAD-bound product
-    // phases together and the ALU/LSU-bound alignment phases together.  Staggering the second
-    // warp of every scheduler by a fraction of a period lets one warp's products overlap the
-    // other's alignment work.
-    if (p.desync_cycles > 0 && ((threadIdx.x >> 5) & 4)) {
-        long long t0 = clock64();
-        while (clock64() - t0 < p.desync_cycles) {}
-    }
-    fuchs_shared_thread<L>(p, idx, S0, S1, A0, A1, A2);
+    GScratch G0{p.gcols + idx, (size_t)p.batch};
+    GScratch G1{p.gcols + (size_t)Sizes<L>::WORDS * p.batch + idx, (size_t)p.batch};
+    fuchs_shared_thread<L>(p, idx, S0, S1, A0, A1, A2, G0, G1);
 }
 
 template <int L, class P>

@@ -64,6 +64,63 @@ __device__ __forceinline__ void mul_full(uint32_t (&r)[2 * L], const uint32_t (&
         asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r[k]) : "r"(ev[k]), "r"(od[k - 1]));
 }
 
+
+// ---------------------------------------------------------------- truncated ("high") product
+// r[0 .. 2L-K) = ( sum over limb products with i + j >= K of a[j] b[i] 2^(32 (i+j)) ) >> 32 K.
+// Whole limb products whose low word falls in a column below K are dropped (including the part of
+// their high word that would land in column K), so with P = a*b:
+//     0 <= P - (r << 32 K) < (K + 1) * 2^(32 (K + 1)).
+// Same even/odd carry-chain structure as mul_full; K must be even.
+template <int L, int K, int KIDX, int J0, int JS, int N>
+__device__ __forceinline__ void mulh_chain(uint32_t (&acc)[N], const uint32_t (&a)[L], uint32_t b) {
+    // products a[J0 + j] * b for even j in [JS, L), accumulated at acc[KIDX + j], acc[KIDX + j + 1]
+    if constexpr (JS < L) {
+        asm volatile("mad.lo.cc.u32 %0, %2, %3, %4; madc.hi.cc.u32 %1, %2, %3, %5;"
+                     : "=r"(acc[KIDX + JS]), "=r"(acc[KIDX + JS + 1])
+                     : "r"(a[J0 + JS]), "r"(b), "r"(acc[KIDX + JS]), "r"(acc[KIDX + JS + 1]));
+#pragma unroll
+        for (int j = JS + 2; j < L; j += 2)
+            asm volatile("madc.lo.cc.u32 %0, %2, %3, %4; madc.hi.cc.u32 %1, %2, %3, %5;"
+                         : "=r"(acc[KIDX + j]), "=r"(acc[KIDX + j + 1])
+                         : "r"(a[J0 + j]), "r"(b), "r"(acc[KIDX + j]), "r"(acc[KIDX + j + 1]));
+        if constexpr (KIDX + L < N) asm volatile("addc.u32 %0, %1, 0;" : "=r"(acc[KIDX + L]) : "r"(acc[KIDX + L]));
+    }
+}
+template <int L, int K, int I>
+struct MulHighRows {
+    template <int N>
+    static __device__ __forceinline__ void run(uint32_t (&ev)[N], uint32_t (&od)[N], const uint32_t (&a)[L],
+                                               const uint32_t (&b)[L]) {
+        if constexpr (I < L) {
+            if constexpr ((I & 1) == 0) {
+                constexpr int JS = (K - I) > 0 ? (K - I) : 0;
+                mulh_chain<L, K, I - K, 0, JS>(ev, a, b[I]);  // column I + j      -> ev[I + j - K]
+                mulh_chain<L, K, I - K, 1, JS>(od, a, b[I]);  // column I + 1 + j  -> od[I + j - K]
+            } else {
+                constexpr int JSO = (K + 1 - I) > 0 ? (K + 1 - I) : 0;
+                constexpr int JSE = (K - 1 - I) > 0 ? (K - 1 - I) : 0;
+                mulh_chain<L, K, I - 1 - K, 0, JSO>(od, a, b[I]);  // column I + j (odd) -> od[I + j - 1 - K]
+                mulh_chain<L, K, I + 1 - K, 1, JSE>(ev, a, b[I]);  // column I + 1 + j   -> ev[I + 1 + j - K]
+            }
+            MulHighRows<L, K, I + 1>::run(ev, od, a, b);
+        }
+    }
+};
+template <int L, int K>
+__device__ __forceinline__ void mul_high(uint32_t (&r)[2 * L - K], const uint32_t (&a)[L], const uint32_t (&b)[L]) {
+    static_assert(L % 2 == 0 && K % 2 == 0 && K >= 0 && K < L, "even limb counts");
+    constexpr int N = 2 * L - K + 2;
+    uint32_t ev[N], od[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) { ev[k] = 0; od[k] = 0; }
+    MulHighRows<L, K, 0>::run(ev, od, a, b);
+    r[0] = ev[0];
+    asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r[1]) : "r"(ev[1]), "r"(od[0]));
+#pragma unroll
+    for (int k = 2; k < 2 * L - K; k++)
+        asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r[k]) : "r"(ev[k]), "r"(od[k - 1]));
+}
+
 #else  // host build of the same interface (tests/host_sim only; never shipped in the library)
 
 template <int L>
@@ -78,6 +135,29 @@ inline void mul_full(uint32_t (&r)[2 * L], const uint32_t (&a)[L], const uint32_
         }
         r[i + L] = (uint32_t)c;
     }
+}
+
+
+template <int L, int K>
+inline void mul_high(uint32_t (&r)[2 * L - K], const uint32_t (&a)[L], const uint32_t (&b)[L]) {
+    uint32_t t[2 * L + 2];
+    for (int k = 0; k < 2 * L + 2; k++) t[k] = 0;
+    for (int i = 0; i < L; i++)
+        for (int j = 0; j < L; j++) {
+            if (i + j < K) continue;
+            uint64_t p = (uint64_t)a[j] * b[i];
+            uint64_t c = (uint32_t)p;
+            int k = i + j;
+            uint64_t s = (uint64_t)t[k] + c;
+            t[k] = (uint32_t)s;
+            uint64_t carry = (s >> 32) + (p >> 32);
+            for (k = k + 1; carry; k++) {
+                s = (uint64_t)t[k] + (uint32_t)carry;
+                t[k] = (uint32_t)s;
+                carry = (carry >> 32) + (s >> 32);
+            }
+        }
+    for (int k = 0; k < 2 * L - K; k++) r[k] = t[K + k];
 }
 
 #endif

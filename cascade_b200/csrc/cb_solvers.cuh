@@ -155,6 +155,21 @@ CB_HD void acb_div(const CRef& z, const CRef& x, const CRef& y, const CRef& inv,
     }
 }
 
+// record the number of trailing zero limbs of both parts in the hint bits of their flags
+// (internal tables only; see F_TZ_SHIFT)
+template <int L>
+CB_HD void acb_mark_tz(const CRef& z) {
+    for (int part = 0; part < 2; part++) {
+        Meta t = ld_meta(z.t + part);
+        int tz = 0;
+        if (!(t.flags & (F_ZERO | F_NAN))) {
+            while (tz < L - 1 && z.m[(size_t)tz * z.stride + part] == 0u) tz++;
+        }
+        t.flags = (t.flags & 0xFFu) | ((uint32_t)tz << F_TZ_SHIFT);
+        st_meta(z.t + part, t);
+    }
+}
+
 CB_HD int64_t clampi(int64_t x, int64_t lo, int64_t hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
 // ================================================================ Fuchs
@@ -267,7 +282,9 @@ CB_HD void fuchs_table_thread(const FuchsTableParams& p, int64_t row, SCR S0, SC
     } else {
         p.kind[row] = 1;
         acb_inv<L>(at<L>(p.tbl, base + W + 1, 0), t2, scratch, S0, S1);
+        acb_mark_tz<L>(at<L>(p.tbl, base + W + 1, 0));
     }
+    for (int s = 0; s <= k; s++) acb_mark_tz<L>(at<L>(p.tbl, base + s, 0));
 }
 
 struct FuchsSharedParams {
@@ -276,13 +293,32 @@ struct FuchsSharedParams {
     CArr tbl;   // see above
     CArr res;   // n+1 entries, S = 2*batch
     const int32_t* kind;
-    int desync_cycles;  // start-up stagger between the warps of a scheduler (see fuchs_shared_kernel)
+    uint32_t* gcols;  // 2 * (2L+3) words per instance, [word][instance]: columns of the general path
 };
+
+// does this precision use truncated products in the recurrence kernel?
+template <int L>
+constexpr bool use_trunc() { return L >= 16 && L <= 32; }
+
+// one fused dot product of the recurrence: truncated products with the exact general path as the
+// per-lane fallback (L = 16..32), or the exact in-shared-memory version (other precisions)
+template <int L, class SCR, class DST>
+CB_HD Meta rec_fdot2(DST dst, Opd x1, Opd y1, Opd x2, Opd y2, bool neg2, SCR S0, SCR S1, GScratch G0, GScratch G1) {
+    if constexpr (use_trunc<L>()) {
+        bool ok;
+        Meta t = arb_fdot2_trunc<L>(dst, x1, y1, x2, y2, neg2, S0, &ok);
+        CB_COUNT(ok ? 4 : 5);
+        if (!ok) t = arb_fdot2_general<L>(dst, x1, y1, x2, y2, neg2, G0, G1);
+        return t;
+    } else {
+        return arb_fdot2<L>(dst, x1, y1, x2, y2, neg2, S0, S1);
+    }
+}
 
 // AC: three small scratch columns (L+2 words each) rotating between acc.re, acc.im and "free"
 template <int L, class SCR>
 CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0, SCR S1, SCR A0, SCR A1,
-                               SCR A2) {
+                               SCR A2, GScratch G0, GScratch G1) {
     const size_t slot = 2 * (size_t)inst;
     const int v = p.valuation, W = p.degree - v;
     SCR accRe = A0, accIm = A1, spare = A2;
@@ -298,7 +334,7 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
             CRef x = at<L>(p.res, bmin + k, slot), y = at<L>(p.tbl, base + k, 0);
             Opd a = re_of(x), b = im_of(x), c = re_of(y), d = im_of(y);
             // real part: acc.re -= a c - b d
-            Meta pr = arb_fdot2<L>(WRef{spare.generic(), SCR::GSTRIDE}, a, c, b, d, true, S0, S1);
+            Meta pr = rec_fdot2<L>(WRef{spare.generic(), SCR::GSTRIDE}, a, c, b, d, true, S0, S1, G0, G1);
             if (k == 0) {  // 0 - x = -x exactly: adopt the column, flip the sign
                 SCR t = accRe;
                 accRe = spare;
@@ -315,7 +351,7 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
                 }
             }
             // imaginary part: acc.im -= a d + b c
-            Meta pi = arb_fdot2<L>(WRef{spare.generic(), SCR::GSTRIDE}, a, d, b, c, false, S0, S1);
+            Meta pi = rec_fdot2<L>(WRef{spare.generic(), SCR::GSTRIDE}, a, d, b, c, false, S0, S1, G0, G1);
             if (k == 0) {
                 SCR t = accIm;
                 accIm = spare;
@@ -337,15 +373,24 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
         if (p.kind[bmax + v] == 1) {
             CRef y = at<L>(p.tbl, base + W + 1, 0);
             Opd c = re_of(y), d = im_of(y);
-            Meta tr = arb_fdot2<L>(wre(out), xa, c, xb, d, true, S0, S1);
-            Meta ti = arb_fdot2<L>(wim(out), xa, d, xb, c, false, S0, S1);
+            Meta tr = rec_fdot2<L>(wre(out), xa, c, xb, d, true, S0, S1, G0, G1);
+            Meta ti = rec_fdot2<L>(wim(out), xa, d, xb, c, false, S0, S1, G0, G1);
             st_meta(out.t, tr);
             st_meta(out.t + 1, ti);
         } else {
             CRef y = at<L>(p.tbl, base + cnt, 0);
             Opd c = re_of(y);
-            Meta tr = arb_div<L>(wre(out), xa, c, S0, S1);
-            Meta ti = arb_div<L>(wim(out), xb, c, S0, S1);
+            // real divisor: long division needs two full-size columns; with truncated products the
+            // shared columns are short, so the global ones serve (this path is integer-operator
+            // territory, where the division dominates anyway)
+            Meta tr, ti;
+            if constexpr (use_trunc<L>()) {
+                tr = arb_div<L>(wre(out), xa, c, G0, G1);
+                ti = arb_div<L>(wim(out), xb, c, G0, G1);
+            } else {
+                tr = arb_div<L>(wre(out), xa, c, S0, S1);
+                ti = arb_div<L>(wim(out), xb, c, S0, S1);
+            }
             st_meta(out.t, tr);
             st_meta(out.t + 1, ti);
         }

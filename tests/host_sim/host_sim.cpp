@@ -64,10 +64,21 @@ int cbsim_fuchs_batch(int L_, int order, int degree, int valuation, int64_t n, i
         SIM_DISPATCH(L_, run<L>(rows, [&](int64_t i, Scratch<1> a, Scratch<1> b) { fuchs_table_thread<L>(tp, i, a, b); }));
         FuchsSharedParams sp;
         sp.order = order; sp.degree = degree; sp.valuation = valuation; sp.n = n; sp.batch = batch;
-        sp.tbl = tp.tbl; sp.res = p.res; sp.kind = kind.data(); sp.desync_cycles = 0;
-        std::vector<uint32_t> c0(L_ + 2), c1(L_ + 2), c2(L_ + 2);
-        Scratch<1> A0{c0.data()}, A1{c1.data()}, A2{c2.data()};
-        SIM_DISPATCH(L_, run<L>(batch, [&](int64_t i, Scratch<1> a, Scratch<1> b) { fuchs_shared_thread<L>(sp, i, a, b, A0, A1, A2); }));
+        sp.tbl = tp.tbl; sp.res = p.res; sp.kind = kind.data(); sp.gcols = nullptr;
+        // columns sized EXACTLY as on the device (cb_kernels.cuh Sizes<L>), each followed by a
+        // canary zone, so an out-of-column access is caught here and not only on the GPU
+        const bool trunc = (L_ >= 16 && L_ <= 32);
+        const size_t sizes[7] = {(size_t)(trunc ? L_ + 5 : 2 * L_ + 3), (size_t)(trunc ? 0 : 2 * L_ + 3), (size_t)L_ + 2,
+                                 (size_t)L_ + 2, (size_t)L_ + 2, (size_t)2 * L_ + 3, (size_t)2 * L_ + 3};
+        const size_t CAN = 64;
+        std::vector<uint32_t> col[7];
+        for (int c = 0; c < 7; c++) col[c].assign(sizes[c] + CAN, 0xDEADBEEFu);
+        Scratch<1> S0{col[0].data()}, S1{col[1].data()}, A0{col[2].data()}, A1{col[3].data()}, A2{col[4].data()};
+        GScratch G0{col[5].data(), 1}, G1{col[6].data(), 1};
+        SIM_DISPATCH(L_, for (int64_t i = 0; i < batch; i++) fuchs_shared_thread<L>(sp, i, S0, S1, A0, A1, A2, G0, G1));
+        for (int c = 0; c < 7; c++)
+            for (size_t k = sizes[c]; k < sizes[c] + CAN; k++)
+                if (col[c][k] != 0xDEADBEEFu) return -1000 - c;  // column overrun
         return 0;
     }
     p.tmp = tmp.arr(L_, FUCHS_NTMP, 2 * batch);
