@@ -17,23 +17,24 @@ template <> struct Cfg<128> { static constexpr int TPB = 64; };
 // threads per block of the shared-operator recurrence kernel (two product columns + three
 // accumulator columns per thread)
 template <int L> struct CfgShared;
-template <> struct CfgShared<4> { static constexpr int TPB = 128; };
-#ifndef CB_TPB_SHARED_32
-#define CB_TPB_SHARED_32 320
-#endif
-template <> struct CfgShared<32> { static constexpr int TPB = CB_TPB_SHARED_32; };
-template <> struct CfgShared<64> { static constexpr int TPB = 96; };
-template <> struct CfgShared<128> { static constexpr int TPB = 32; };
+template <> struct CfgShared<4> { static constexpr int TPB = 128; static constexpr int TPB_BIG = 128; };
+// 1024 bits: two block sizes, picked per launch to minimise the idle tail of the last wave
+// (7 warps at <= 255 registers, or 12 warps at 168 registers = 3 warps per scheduler)
+template <> struct CfgShared<32> { static constexpr int TPB = 224; static constexpr int TPB_BIG = 384; };
+template <> struct CfgShared<64> { static constexpr int TPB = 96; static constexpr int TPB_BIG = 96; };
+template <> struct CfgShared<128> { static constexpr int TPB = 32; static constexpr int TPB_BIG = 32; };
 
 template <int L> struct Sizes {
     static constexpr int WORDS = 2 * L + 3;  // words per product scratch column
-    static constexpr int AWORDS = L + 2;     // words per accumulator column
+    // words per accumulator column; with truncated products the spare one also parks a high
+    // product (L+4 words), so all three are L+5
+    static constexpr int AWORDS = use_trunc<L>() ? L + 5 : L + 2;
     static constexpr size_t SMEM = (size_t)2 * WORDS * Cfg<L>::TPB * sizeof(uint32_t);
     // recurrence kernel: with truncated products S0 only parks a high product (L+5 words) and the
     // second full column lives in global memory (general path only)
-    static constexpr int S0WORDS = use_trunc<L>() ? (L + 5) : WORDS;
+    static constexpr int S0WORDS = use_trunc<L>() ? 0 : WORDS;
     static constexpr int S1WORDS = use_trunc<L>() ? 0 : WORDS;
-    static constexpr size_t SMEM_SHARED = (size_t)(S0WORDS + S1WORDS + 3 * AWORDS) * CfgShared<L>::TPB * sizeof(uint32_t);
+    static constexpr size_t SMEM_SHARED_PER_THREAD = (size_t)(S0WORDS + S1WORDS + 3 * AWORDS) * sizeof(uint32_t);
 };
 
 #define CB_KERNEL_PROLOGUE(COUNT)                                                              \
@@ -71,10 +72,9 @@ __global__ void __launch_bounds__(Cfg<L>::TPB, 1) fuchs_table_kernel(FuchsTableP
     CB_KERNEL_PROLOGUE(p.n + 1 + p.valuation)
     fuchs_table_thread<L>(p, idx, S0, S1);
 }
-template <int L>
-__global__ void __launch_bounds__(CfgShared<L>::TPB, 1) fuchs_shared_kernel(FuchsSharedParams p) {
+template <int L, int TPB>
+__global__ void __launch_bounds__(TPB, 1) fuchs_shared_kernel(FuchsSharedParams p) {
     extern __shared__ uint32_t cb_smem[];
-    constexpr int TPB = CfgShared<L>::TPB;
     constexpr uint32_t W0 = Sizes<L>::S0WORDS, W1 = Sizes<L>::S1WORDS, AW = Sizes<L>::AWORDS;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cb_smem) + 4u * threadIdx.x;
     Scratch<TPB> S0{sbase}, S1{sbase + 4u * W0 * TPB};
@@ -85,6 +85,19 @@ __global__ void __launch_bounds__(CfgShared<L>::TPB, 1) fuchs_shared_kernel(Fuch
     GScratch G0{p.gcols + idx, (size_t)p.batch};
     GScratch G1{p.gcols + (size_t)Sizes<L>::WORDS * p.batch + idx, (size_t)p.batch};
     fuchs_shared_thread<L>(p, idx, S0, S1, A0, A1, A2, G0, G1);
+}
+
+// time of a launch is proportional to (number of waves) x (instances per SM per wave) / throughput;
+// measured on B200: 12 warps/SM sustain ~1.13x the throughput of 7 warps/SM
+template <int L>
+bool prefer_big_blocks(int64_t batch, int sms) {
+    if (CfgShared<L>::TPB_BIG == CfgShared<L>::TPB) return false;
+    auto cost = [&](int tpb, double thr) {
+        int64_t blocks = (batch + tpb - 1) / tpb;
+        int64_t waves = (blocks + sms - 1) / sms;
+        return (double)waves * tpb / thr;
+    };
+    return cost(CfgShared<L>::TPB_BIG, 1.13) < cost(CfgShared<L>::TPB, 1.0);
 }
 
 template <int L, class P>
@@ -118,7 +131,13 @@ struct LaunchTable {
         return launch<LL>(fuchs_table_kernel<LL>, p, p.n + 1 + p.valuation, s);                            \
     }                                                                                                      \
     static int fsh_##LL(const FuchsSharedParams& p, cudaStream_t s) {                                      \
-        return launch<LL>(fuchs_shared_kernel<LL>, p, p.batch, s, CfgShared<LL>::TPB, Sizes<LL>::SMEM_SHARED); \
+        int dev = 0, sms = 148;                                                                            \
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); \
+        if (prefer_big_blocks<LL>(p.batch, sms))                                                           \
+            return launch<LL>(fuchs_shared_kernel<LL, CfgShared<LL>::TPB_BIG>, p, p.batch, s, CfgShared<LL>::TPB_BIG, \
+                              Sizes<LL>::SMEM_SHARED_PER_THREAD * CfgShared<LL>::TPB_BIG);                 \
+        return launch<LL>(fuchs_shared_kernel<LL, CfgShared<LL>::TPB>, p, p.batch, s, CfgShared<LL>::TPB,  \
+                          Sizes<LL>::SMEM_SHARED_PER_THREAD * CfgShared<LL>::TPB);                         \
     }                                                                                                      \
     extern const LaunchTable launch_table_L##LL = {fuchs_##LL, frob_##LL, horner_##LL, ew_##LL, ftab_##LL, fsh_##LL}; \
     }

@@ -334,7 +334,8 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
             CRef x = at<L>(p.res, bmin + k, slot), y = at<L>(p.tbl, base + k, 0);
             Opd a = re_of(x), b = im_of(x), c = re_of(y), d = im_of(y);
             // real part: acc.re -= a c - b d
-            Meta pr = rec_fdot2<L>(WRef{spare.generic(), SCR::GSTRIDE}, a, c, b, d, true, S0, S1, G0, G1);
+            Meta pr = rec_fdot2<L>(WRef{spare.generic(), SCR::GSTRIDE}, a, c, b, d, true, use_trunc<L>() ? spare : S0,
+                                   S1, G0, G1);
             if (k == 0) {  // 0 - x = -x exactly: adopt the column, flip the sign
                 SCR t = accRe;
                 accRe = spare;
@@ -351,7 +352,8 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
                 }
             }
             // imaginary part: acc.im -= a d + b c
-            Meta pi = rec_fdot2<L>(WRef{spare.generic(), SCR::GSTRIDE}, a, d, b, c, false, S0, S1, G0, G1);
+            Meta pi = rec_fdot2<L>(WRef{spare.generic(), SCR::GSTRIDE}, a, d, b, c, false,
+                                   use_trunc<L>() ? spare : S0, S1, G0, G1);
             if (k == 0) {
                 SCR t = accIm;
                 accIm = spare;
@@ -373,8 +375,8 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
         if (p.kind[bmax + v] == 1) {
             CRef y = at<L>(p.tbl, base + W + 1, 0);
             Opd c = re_of(y), d = im_of(y);
-            Meta tr = rec_fdot2<L>(wre(out), xa, c, xb, d, true, S0, S1, G0, G1);
-            Meta ti = rec_fdot2<L>(wim(out), xa, d, xb, c, false, S0, S1, G0, G1);
+            Meta tr = rec_fdot2<L>(wre(out), xa, c, xb, d, true, use_trunc<L>() ? spare : S0, S1, G0, G1);
+            Meta ti = rec_fdot2<L>(wim(out), xa, d, xb, c, false, use_trunc<L>() ? spare : S0, S1, G0, G1);
             st_meta(out.t, tr);
             st_meta(out.t + 1, ti);
         } else {

@@ -68,8 +68,9 @@ int cbsim_fuchs_batch(int L_, int order, int degree, int valuation, int64_t n, i
         // columns sized EXACTLY as on the device (cb_kernels.cuh Sizes<L>), each followed by a
         // canary zone, so an out-of-column access is caught here and not only on the GPU
         const bool trunc = (L_ >= 16 && L_ <= 32);
-        const size_t sizes[7] = {(size_t)(trunc ? L_ + 5 : 2 * L_ + 3), (size_t)(trunc ? 0 : 2 * L_ + 3), (size_t)L_ + 2,
-                                 (size_t)L_ + 2, (size_t)L_ + 2, (size_t)2 * L_ + 3, (size_t)2 * L_ + 3};
+        const size_t aw = trunc ? L_ + 5 : L_ + 2;
+        const size_t sizes[7] = {(size_t)(trunc ? 0 : 2 * L_ + 3), (size_t)(trunc ? 0 : 2 * L_ + 3), aw, aw, aw,
+                                 (size_t)2 * L_ + 3, (size_t)2 * L_ + 3};
         const size_t CAN = 64;
         std::vector<uint32_t> col[7];
         for (int c = 0; c < 7; c++) col[c].assign(sizes[c] + CAN, 0xDEADBEEFu);
