@@ -242,7 +242,7 @@ def main():
     # ---- end to end: host buffers in, host buffers out, tile by tile, copies inside the timing
     e2e = None
     if not args.no_e2e:
-        tile = min(batch, 8192)
+        tile = min(batch, 16384)
         ntiles = (batch + tile - 1) // tile
         St = 2 * tile
         h_init_m = torch.from_numpy(init_m.view(np.int32)).pin_memory()

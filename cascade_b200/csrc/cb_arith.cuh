@@ -537,11 +537,14 @@ CB_HD bool fast_add_round(DST dst, X1 x1, X2 x2, int s1, int s2, bool sub, bool 
     auto Rx = [&](int idx) -> uint32_t { return (idx >= KLOW && idx <= N + 1) ? R_(idx) : 0u; };
     uint32_t low = 0u;
     if constexpr (TRUNC) {
-        // Error of the sum from the dropped columns: < 2 (K+1) 2^(32(K+2)) < 2^B.  The 24 bits just
-        // below the rounding position must be neither all zero nor all one.
+        // Error of the sum: each truncated product is short by < (K+1) 2^(32(K+2)) in this frame, and
+        // an operand moved down by whole words additionally loses < 2^(32 K): in total
+        // < 4 (K+1) 2^(32(K+2)) <= 2^B.  The 24 bits just below the rounding position must be
+        // neither all zero nor all one; then the missing part cannot carry into the kept bits and
+        // the result is certainly inexact.
         constexpr int LOGK = (KLOW + 1 <= 2) ? 1 : (KLOW + 1 <= 4) ? 2 : (KLOW + 1 <= 8) ? 3 : (KLOW + 1 <= 16) ? 4
                              : (KLOW + 1 <= 32) ? 5 : (KLOW + 1 <= 64) ? 6 : 7;
-        constexpr int B = 32 * (KLOW + 2) + 1 + LOGK;
+        constexpr int B = 32 * (KLOW + 2) + 2 + LOGK;
         static_assert(32 * (N - 1) + 1 - 32 * L - 24 >= B, "not enough guard bits for this truncation");
         static_assert(QMIN - 1 >= KLOW, "guard word must be available");
         uint32_t lo_w = 0u, hi_w = 0u;  // words q-1 and q
@@ -751,7 +754,18 @@ CB_NOINLINE Meta arb_fdot2_trunc(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2,
     bool n1 = ((x1.t.flags ^ y1.t.flags) & F_SIGN) != 0;
     bool n2 = (((x2.t.flags ^ y2.t.flags) & F_SIGN) != 0) != neg2;
     const int64_t e1 = (int64_t)x1.t.exp + y1.t.exp, e2 = (int64_t)x2.t.exp + y2.t.exp;
-    bool skip1 = warp_all(z1), skip2 = warp_all(z2);
+    // Per lane, term A is the one that may need a limb shift (the zero one, else the smaller
+    // exponent); its product is parked in the shared column, where a data-dependent word offset
+    // is cheap.  Term B (the larger) stays in registers and needs no shift at all.
+    const bool a_is_1 = z1 ? true : (z2 ? false : (e1 <= e2));
+    const bool zA = a_is_1 ? z1 : z2, zB = a_is_1 ? z2 : z1;
+    const bool nA = a_is_1 ? n1 : n2, nB = a_is_1 ? n2 : n1;
+    const int64_t eA = a_is_1 ? e1 : e2, eB = a_is_1 ? e2 : e1;
+    const XS xA = a_is_1 ? x1.r : x2.r, xB = a_is_1 ? x2.r : x1.r;
+    const YS yA = a_is_1 ? y1.r : y2.r, yB = a_is_1 ? y2.r : y1.r;
+    const int tzA = a_is_1 ? tz_hint(x1.t.flags) + tz_hint(y1.t.flags) : tz_hint(x2.t.flags) + tz_hint(y2.t.flags);
+    const int tzB = a_is_1 ? tz_hint(x2.t.flags) + tz_hint(y2.t.flags) : tz_hint(x1.t.flags) + tz_hint(y1.t.flags);
+    bool skipA = warp_all(zA), skipB = warp_all(zB);
     uint32_t r[PW];
 #pragma unroll 1
     for (int term = 0; term < 2; term++) {  // a loop, so that the product code exists once
@@ -759,44 +773,46 @@ CB_NOINLINE Meta arb_fdot2_trunc(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2,
 #pragma unroll
             for (int k = 0; k < PW; k++) S0.st(k, r[k]);
         }
-        if (term ? skip2 : skip1) {
+        if (term ? skipB : skipA) {
 #pragma unroll
             for (int k = 0; k < PW; k++) r[k] = 0u;
             continue;
         }
         uint32_t a[L], b[L];
-        XS xs = term ? x2.r : x1.r;
-        YS ys = term ? y2.r : y1.r;
+        XS xs = term ? xB : xA;
+        YS ys = term ? yB : yA;
 #pragma unroll
         for (int j = 0; j < L; j++) a[j] = xs.ld(j);
 #pragma unroll
         for (int j = 0; j < L; j++) b[j] = ys.ld(j);
         mul_high<L, K>(r, a, b);
     }
-    int64_t d = e1 - e2;
-    bool easy = !(z1 && z2) && (z1 || z2 || (d <= 31 && d >= -31));
     bool done = false, neg = false;
     Rounded rr;
     rr.exp = 0;
     rr.zero = true;
     rr.inexact = false;
     rr.overflow = false;
-    if (z1 && z2) {  // exact zero midpoint (also the indeterminate case): nothing to round
+    if (zA && zB) {  // exact zero midpoint (also the indeterminate case): nothing to round
 #pragma unroll 4
         for (int j = 0; j < L; j++) dst.st(j, 0u);
         done = true;
-    } else if (easy) {
-        int64_t E = z1 ? e2 : (z2 ? e1 : (e1 > e2 ? e1 : e2));
-        int s1 = z1 ? 0 : (int)(E - e1), s2 = z2 ? 0 : (int)(E - e2);
-        bool sub = (n1 != n2) && !z1 && !z2;
-        // word k of the (truncated) product i, k in [K, 2L)
-        auto w1 = [&](int k) -> uint32_t { return z1 ? 0u : S0.ld(k - K); };
-        auto w2 = [&](int k) -> uint32_t { return z2 ? 0u : r[k - K]; };
-        // products whose operands have >= K trailing zero limbs in total lose nothing to truncation
-        bool trusted = (z1 || tz_hint(x1.t.flags) + tz_hint(y1.t.flags) >= K) &&
-                       (z2 || tz_hint(x2.t.flags) + tz_hint(y2.t.flags) >= K);
-        done = fast_add_round<L, 2 * L, K>(dst, w1, w2, s1, s2, sub, z1 ? n2 : n1, z1 ? n1 : n2, E, &rr, &neg,
-                                           trusted);
+    } else {
+        // zB implies zA by construction of the order, so B is nonzero here
+        int64_t d = zA ? 0 : (eB - eA);              // >= 0
+        int m = d > 32 * 70 ? 70 : (int)(d >> 5);   // limb shift of A (70: entirely below the window)
+        int sA = (int)(d & 31);
+        bool sub = (nA != nB) && !zA;
+        // word k (k in [K, 2L)) of the product B, and of the product A moved down by m words
+        auto wB = [&](int k) -> uint32_t { return r[k - K]; };
+        auto wA = [&](int k) -> uint32_t {
+            int i = k + m - K;
+            return (zA || (unsigned)i >= (unsigned)PW) ? 0u : S0.ld(i);
+        };
+        // nothing is lost to truncation when every dropped column is zero: both products have
+        // >= K trailing zero limbs in total and A is not moved below the window
+        bool trusted = (zA || (tzA >= K && m == 0)) && tzB >= K;
+        done = fast_add_round<L, 2 * L, K>(dst, wB, wA, 0, sA, sub, nB, nA, eB, &rr, &neg, trusted);
     }
     *ok = done;
     if (nan) return meta_nan();

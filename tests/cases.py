@@ -131,6 +131,36 @@ def case_fuchs_random_shared(oracle, drv, L: int, seed: int, trials: int = 4, ba
         assert_same(ro, rs, f"fuchs shared L={L} order={order} degree={degree} v={v} n={n}")
 
 
+def case_fuchs_shared_adversarial(oracle, drv, L: int, seed: int, trials: int = 6, batch: int = 40):
+    """Shared operator with hostile data for the recurrence kernel's fast paths: real/imaginary
+    parts hundreds of bits apart, exact zeros, all-ones and short (integer-like) mantissas, huge
+    and tiny radii -- in the operator and in the initial values."""
+    rng = np.random.default_rng(seed)
+    for trial in range(trials):
+        order, degree = 2, 2 + trial % 2
+        ne = (order + 1) * (degree + 1)
+        ode, _ = adversarial_pair(rng, L, ne)
+        ode.meta[:, 0] = rng.integers(-3, 4, size=2 * ne) + rng.choice([0, 0, 0, 40, -70, 200], size=2 * ne)
+        lead = random_balls(rng, 2, L, -1, 1, "ulp")  # leading coefficient must not contain zero
+        if trial % 3 == 0:
+            lead.mant[1] = 0
+            lead.meta[1] = (0, FLAG_ZERO, 0, 0)
+        ode.mant[2 * (order * (degree + 1)):2 * (order * (degree + 1)) + 2] = lead.mant
+        ode.meta[2 * (order * (degree + 1)):2 * (order * (degree + 1)) + 2] = lead.meta
+        fix = (ode.meta[:, 1] & FLAG_ZERO) != 0  # zero midpoints keep exponent 0
+        ode.meta[fix, 0] = 0
+        v = api.acb_ode_valuation(ode, order, degree)
+        assert v == -order
+        init, _ = adversarial_pair(rng, L, batch * order)
+        init.meta[:, 0] += rng.choice([0, 0, 0, 33, -64, 150, -300], size=init.n_slots).astype(np.int32)
+        init.meta[(init.meta[:, 1] & FLAG_ZERO) != 0, 0] = 0
+        n = order + 12
+        rc, ro = oracle.fuchs_batch(order, degree, n, ode, init, batch, True)
+        assert rc == 0
+        rs = api.acb_ode_solve_fuchs_batch(ode, init, order, degree, n, batch, True, driver=drv)
+        assert_same(ro, rs, f"fuchs shared adversarial L={L} trial={trial}")
+
+
 def bessel_shifted(oracle, rng, L: int):
     """BASELINE config 2's operator: Bessel with complex nu, shifted to a complex ordinary point
     (acb_ode_bessel + acb_ode_shift, reference src/examples.c:13-22, src/acb_ode.c:124-135)."""

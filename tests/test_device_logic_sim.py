@@ -25,6 +25,11 @@ def test_fuchs_random_shared(oracle, sim_driver, L):
     cases.case_fuchs_random_shared(oracle, sim_driver, L, seed=31 + L, trials=6)
 
 
+@pytest.mark.parametrize("L", [4, 32])
+def test_fuchs_shared_adversarial(oracle, sim_driver, L):
+    cases.case_fuchs_shared_adversarial(oracle, sim_driver, L, seed=77 + L, batch=12)
+
+
 def test_fuchs_bessel_shared(oracle, sim_driver):
     cases.case_fuchs_bessel_shared(oracle, sim_driver, 32, seed=5, n=40, batch=3)
 
