@@ -1,0 +1,118 @@
+"""Device-resident timings of the other BASELINE.json configs (development report, not the bench
+contract): config 3 (hypergeometric Frobenius sweep, 4096 bits), config 4 (Legendre sweep, 1024
+bits, per-instance integer operators), config 5 (Horner evaluation at many points, 2048 bits).
+Random dense inputs of the right shape; sizes can be scaled down with --scale."""
+import argparse
+import ctypes as C
+import json
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from cascade_b200 import _lib, api
+from cascade_b200.format import instance_major_to_entry_major, pack_entries, random_balls
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--scale", type=float, default=1.0)
+args = ap.parse_args()
+lib = _lib.lib()
+dev = torch.device("cuda:0")
+p = lambda t: C.c_void_p(t.data_ptr())
+
+
+def dev_arr(mant, meta):
+    return torch.from_numpy(mant.view(np.int32)).to(dev), torch.from_numpy(meta).to(dev)
+
+
+def rand_dev(entries, L, S, seed):
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    m = torch.randint(0, 2**31 - 1, (entries, L, S), device=dev, dtype=torch.int32, generator=g) * 2 + 1
+    m[:, L - 1, :] |= -(2**31)
+    t = torch.zeros((entries, S, 4), device=dev, dtype=torch.int32)
+    return m, t
+
+
+def timed(fn, reps=2):
+    fn()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        assert rc == 0, rc
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+out = []
+# ---- config 3: Frobenius, hypergeometric sweep, 4096 bits, per-instance (a, b, c)
+L, n = 128, 256
+batch = max(64, int(16384 * args.scale))
+rng = np.random.default_rng(3)
+small = 64
+par = [random_balls(rng, small * 2, L, -1, 1, "zero") for _ in range(3)]
+odes = api.acb_ode_hypgeom_batch(*par)
+om, ot = pack_entries(instance_major_to_entry_major(odes, small, 9), 9, 2 * small)
+reps = batch // small
+d_om = torch.from_numpy(np.tile(om.view(np.int32), (1, 1, reps))).to(dev)
+d_ot = torch.from_numpy(np.tile(ot, (1, reps, 1))).to(dev)
+d_rm, d_rt = torch.zeros((1, L, 2 * batch), dtype=torch.int32, device=dev), torch.zeros((1, 2 * batch, 4), dtype=torch.int32, device=dev)
+d_rt[:, :, 1] = 2  # rho = 0
+d_res_m = torch.empty((n + 1, L, 2 * batch), dtype=torch.int32, device=dev)
+d_res_t = torch.empty((n + 1, 2 * batch, 4), dtype=torch.int32, device=dev)
+wsb = lib.cb200_frobenius_workspace_bytes(L, batch)
+ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+ms = timed(lambda: lib.cb200_frobenius1_batch_dev(L, 2, 2, -1, n, batch, p(d_om), p(d_ot), 0, p(d_rm), p(d_rt), 0,
+                                                  p(d_res_m), p(d_res_t), p(ws), wsb, None))
+coeffs = batch * n
+out.append({"config": 3, "what": f"hypgeom Frobenius M=1, 4096 bits, {batch} (a,b,c) triples, {n} terms", "ms": ms,
+            "ball_coeffs_per_s": coeffs / ms * 1e3, "T_limb_MAC_per_s_36L2": coeffs * 36 * L * L / ms * 1e3 / 1e12})
+del d_res_m, d_res_t, ws
+torch.cuda.empty_cache()
+
+# ---- config 4: Legendre sweep, per-instance integer operators, real data
+L, n = 32, 1000
+batch = max(1024, int(2**20 * args.scale))
+chunk = 4096
+ode_c = api.acb_ode_legendre_batch(range(chunk), L)
+om, ot = pack_entries(instance_major_to_entry_major(ode_c, chunk, 9), 9, 2 * chunk)
+reps = batch // chunk
+d_om = torch.from_numpy(np.tile(om.view(np.int32), (1, 1, reps))).to(dev)
+d_ot = torch.from_numpy(np.tile(ot, (1, reps, 1))).to(dev)
+d_res_m = torch.zeros((n + 1, L, 2 * batch), dtype=torch.int32, device=dev)
+d_res_t = torch.zeros((n + 1, 2 * batch, 4), dtype=torch.int32, device=dev)
+d_res_t[:, :, 1] = 2
+d_res_m[0:2, L - 1, 0::2] = -(2**31)  # c0 = c1 = 1
+d_res_t[0:2, 0::2, 0] = 1
+d_res_t[0:2, 0::2, 1] = 0
+wsb = lib.cb200_fuchs_workspace_bytes(L, 2, 2, -2, n, batch, 0)
+ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+ms = timed(lambda: lib.cb200_fuchs_batch_dev(L, 2, 2, -2, n, batch, p(d_om), p(d_ot), 0, p(d_res_m), p(d_res_t), p(ws), wsb, None), reps=1)
+coeffs = batch * (n - 1)
+out.append({"config": 4, "what": f"Legendre sweep n=0..{batch - 1}, 1024 bits, {n} terms, per-instance operators (general kernel)",
+            "ms": ms, "ball_coeffs_per_s": coeffs / ms * 1e3, "GB_per_s_written": coeffs * 288 / ms * 1e3 / 1e9})
+del d_res_m, d_res_t, ws
+torch.cuda.empty_cache()
+
+# ---- config 5: Horner at many points, 2048 bits, one 3504-term series
+L, length = 64, 3504
+npts = max(1024, int(10**6 * args.scale))
+f_m, f_t = rand_dev(length, L, 2, 5)
+pts_m, pts_t = rand_dev(1, L, 2 * npts, 6)
+pts_t[:, :, 0] = -2  # |x| < 1/4
+o_m = torch.empty((1, L, 2 * npts), dtype=torch.int32, device=dev)
+o_t = torch.empty((1, 2 * npts, 4), dtype=torch.int32, device=dev)
+wsb = lib.cb200_horner_workspace_bytes(L, npts)
+ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+ms = timed(lambda: lib.cb200_horner_batch_dev(L, length, npts, 1, p(f_m), p(f_t), 1, p(pts_m), p(pts_t), p(o_m), p(o_t), p(ws), wsb, None), reps=1)
+steps = npts * (length - 1)
+out.append({"config": 5, "what": f"Horner evaluation of a {length}-term series at {npts} points, 2048 bits", "ms": ms,
+            "horner_steps_per_s": steps / ms * 1e3, "T_limb_MAC_per_s_4L2": steps * 4 * L * L / ms * 1e3 / 1e12})
+for o in out:
+    print(json.dumps(o))
