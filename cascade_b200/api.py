@@ -33,6 +33,10 @@ class HostBufferDriver:
         return _lib.lib().cb200_fuchs_batch_host(L, order, degree, valuation, n, batch, ode_m, ode_t,
                                                  int(shared), res_m, res_t, self.device)
 
+    def fuchs_intop(self, L, order, degree, valuation, n, batch, ode_int, shared, res_m, res_t):
+        return _lib.lib().cb200_fuchs_intop_batch_host(L, order, degree, valuation, n, batch, ode_int, int(shared),
+                                                       res_m, res_t, self.device)
+
     def frobenius1(self, L, order, degree, valuation, n, batch, ode_m, ode_t, shared, rho_m, rho_t,
                    shared_rho, res_m, res_t):
         return _lib.lib().cb200_frobenius1_batch_host(L, order, degree, valuation, n, batch, ode_m, ode_t,
@@ -82,9 +86,42 @@ def _ode_to_device(ode: Balls, order: int, degree: int, batch: int, shared: bool
     return pack_entries(instance_major_to_entry_major(ode, nb, ne), ne, 2 * nb)
 
 
+def integer_operator(ode: Balls, order: int, degree: int, n: int):
+    """If every coefficient of every operator is an exact real integer and the integer
+    multipliers of the recurrence stay below 2^62, return them as int64 ``[instances][entries]``;
+    else None.  (Host-side inspection of the ball records only.)"""
+    ne = (order + 1) * (degree + 1)
+    L = ode.L
+    meta = ode.meta.reshape(-1, ne, 2, 4)
+    mant = ode.mant.reshape(-1, ne, 2, L)
+    flags = meta[..., 1]
+    if (meta[..., 2] != 0).any() or (flags & FLAG_NAN).any():
+        return None  # a radius somewhere
+    if not (((flags[:, :, 1] & FLAG_ZERO) != 0)).all():
+        return None  # an imaginary part
+    re_flags, re_exp, re_m = flags[:, :, 0], meta[:, :, 0, 0].astype(np.int64), mant[:, :, 0]
+    nz = (re_flags & FLAG_ZERO) == 0
+    if (re_m[..., : L - 2] != 0).any():
+        return None  # more than 64 significant bits
+    top = (re_m[..., L - 1].astype(np.uint64) << np.uint64(32)) | re_m[..., L - 2].astype(np.uint64)
+    if (nz & ((re_exp < 1) | (re_exp > 62))).any():
+        return None
+    sh = np.where(nz, 64 - re_exp, 0).astype(np.uint64)
+    val = np.where(nz, top >> sh, 0).astype(np.uint64)
+    if (np.where(nz, (val << sh) != top, False)).any():
+        return None  # fractional bits
+    out = val.astype(np.int64)
+    out = np.where((re_flags & 1) != 0, -out, out)
+    bound = float(np.abs(out).max(initial=0)) * float(n + 1) ** order * (order + 1)
+    if bound >= 2.0 ** 62:
+        return None
+    return np.ascontiguousarray(out)
+
+
 # ---------------------------------------------------------------- solvers
 def acb_ode_solve_fuchs_batch(ode: Balls, init: Balls, order: int, degree: int, n: int, batch: int,
-                              shared_ode: bool = True, valuation: int | None = None, driver=None) -> Balls:
+                              shared_ode: bool = True, valuation: int | None = None, driver=None,
+                              use_intop: bool = True) -> Balls:
     """Batched ``acb_ode_solve_fuchs(res, ODE, n, 32*L)`` (reference src/fuchs_solver.c:96-145).
 
     ``init``: ``[batch][-valuation]`` complex balls (``res[0..-v-1]`` of each call).
@@ -98,13 +135,19 @@ def acb_ode_solve_fuchs_batch(ode: Balls, init: Balls, order: int, degree: int, 
     ninit = -v
     assert init.n_slots == batch * ninit * 2, "need -valuation initial values per instance"
     assert n >= ninit - 1
-    ode_m, ode_t = _ode_to_device(ode, order, degree, batch, shared_ode)
     res = Balls.zeros(batch * (n + 1) * 2, L)
     res.mant.reshape(batch, n + 1, 2, L)[:, :ninit] = init.mant.reshape(batch, ninit, 2, L)
     res.meta.reshape(batch, n + 1, 2, 4)[:, :ninit] = init.meta.reshape(batch, ninit, 2, 4)
     res_m, res_t = pack_entries(instance_major_to_entry_major(res, batch, n + 1), n + 1, 2 * batch)
-    _lib.check(drv.fuchs(L, order, degree, v, n, batch, ode_m, ode_t, shared_ode, res_m, res_t),
-               "acb_ode_solve_fuchs_batch")
+    ints = integer_operator(ode, order, degree, n) if (use_intop and not shared_ode) else None
+    if ints is not None and (order + 1) * (degree + 1) <= 36:
+        # integer operators (Legendre sweeps): O(L) kernel, same balls
+        _lib.check(drv.fuchs_intop(L, order, degree, v, n, batch, np.ascontiguousarray(ints.T), False, res_m, res_t),
+                   "acb_ode_solve_fuchs_batch (integer operators)")
+    else:
+        ode_m, ode_t = _ode_to_device(ode, order, degree, batch, shared_ode)
+        _lib.check(drv.fuchs(L, order, degree, v, n, batch, ode_m, ode_t, shared_ode, res_m, res_t),
+                   "acb_ode_solve_fuchs_batch")
     return entry_major_to_instance_major(unpack_entries(L, res_m, res_t), batch, n + 1)
 
 

@@ -144,6 +144,27 @@ int cb200_fuchs_batch_dev(int L_, int order, int degree, int valuation, int64_t 
     return table_for(L_)->fuchs(p, (cudaStream_t)stream);
 }
 
+int cb200_fuchs_intop_batch_dev(int L_, int order, int degree, int valuation, int64_t n, int64_t batch,
+                                const int64_t* ode_int, int shared_ode, uint32_t* res_mant, cb_meta* res_meta,
+                                void* stream) {
+    if (!supported_L(L_) || order < 1 || degree < 0 || batch < 0 || n < 0) return CB200_EINVAL;
+    if ((order + 1) * (degree + 1) > INTOP_MAXENT) return CB200_EINVAL;
+    if (valuation >= 0) return CB200_EVALUATION;
+    if (!factor_fits(n, order)) return CB200_ERANGE;
+    if (n < -valuation) return 0;
+    FuchsIntParams p;
+    p.order = order;
+    p.degree = degree;
+    p.valuation = valuation;
+    p.n = n;
+    p.batch = batch;
+    p.ode = ode_int;
+    p.ostride = shared_ode ? 0 : (size_t)batch;
+    p.res = CArr{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
+    g_launches.fetch_add(batch > 0);
+    return table_for(L_)->fuchs_intop(p, (cudaStream_t)stream);
+}
+
 int cb200_frobenius1_batch_dev(int L_, int order, int degree, int valuation, int64_t n, int64_t batch,
                                const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
                                const uint32_t* rho_mant, const cb_meta* rho_meta, int shared_rho,
@@ -237,6 +258,29 @@ int cb200_fuchs_batch_host(int L, int order, int degree, int valuation, int64_t 
     CK(cudaMemcpy(rt.p, res_meta, arr_meta_bytes(n + 1, S), cudaMemcpyHostToDevice));
     int rc = cb200_fuchs_batch_dev(L, order, degree, valuation, n, batch, (uint32_t*)om.p, (cb_meta*)ot.p,
                                    shared_ode, (uint32_t*)rm.p, (cb_meta*)rt.p, ws.p, wsb, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(res_mant, rm.p, arr_mant_bytes(L, n + 1, S), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(res_meta, rt.p, arr_meta_bytes(n + 1, S), cudaMemcpyDeviceToHost));
+    return (int)cudaDeviceSynchronize();
+}
+
+int cb200_fuchs_intop_batch_host(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
+                                 const int64_t* ode_int, int shared_ode, uint32_t* res_mant, cb_meta* res_meta,
+                                 int device) {
+    if (!supported_L(L) || order < 1 || degree < 0 || batch < 0 || n < 0) return CB200_EINVAL;
+    if (valuation >= 0) return CB200_EVALUATION;
+    CK(cudaSetDevice(device));
+    int64_t S = 2 * batch, ne = (int64_t)(order + 1) * (degree + 1);
+    size_t ob = sizeof(int64_t) * ne * (shared_ode ? 1 : batch);
+    DevBuf om, rm, rt;
+    CK(om.alloc(ob));
+    CK(rm.alloc(arr_mant_bytes(L, n + 1, S)));
+    CK(rt.alloc(arr_meta_bytes(n + 1, S)));
+    CK(cudaMemcpy(om.p, ode_int, ob, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(rm.p, res_mant, arr_mant_bytes(L, n + 1, S), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(rt.p, res_meta, arr_meta_bytes(n + 1, S), cudaMemcpyHostToDevice));
+    int rc = cb200_fuchs_intop_batch_dev(L, order, degree, valuation, n, batch, (const int64_t*)om.p, shared_ode,
+                                         (uint32_t*)rm.p, (cb_meta*)rt.p, nullptr);
     if (rc) return rc;
     CK(cudaMemcpy(res_mant, rm.p, arr_mant_bytes(L, n + 1, S), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(res_meta, rt.p, arr_meta_bytes(n + 1, S), cudaMemcpyDeviceToHost));

@@ -993,4 +993,84 @@ CB_NOINLINE Meta arb_div(DST dst, OpdT<XS> x, OpdT<YS> y, SCR S0, SCR S1) {
     return finish<L>(rr, neg, rad);
 }
 
+// ---------------------------------------------------------------- division by a 64-bit integer
+// reciprocal of the normalised two-limb divisor (d1:d0), d1 >= 2^31 (Moller-Granlund 3-by-2)
+CB_HD uint32_t recip_3by2(uint32_t d1, uint32_t d0) {
+    uint32_t v = (uint32_t)((((uint64_t)(~d1) << 32) | 0xFFFFFFFFull) / d1);  // floor((B^2-1)/d1) - B
+    uint32_t p = d1 * v + d0;
+    if (p < d0) {
+        v--;
+        uint32_t mask = (p >= d1) ? 0xFFFFFFFFu : 0u;
+        p -= d1;
+        v += mask;
+        p -= mask & d1;
+    }
+    uint64_t t = (uint64_t)d0 * v;
+    uint32_t t1 = (uint32_t)(t >> 32), t0 = (uint32_t)t;
+    p += t1;
+    if (p < t1) {
+        v--;
+        if (p >= d1 && (p > d1 || t0 >= d0)) v--;
+    }
+    return v;
+}
+// (rem : u) / D with rem < D: returns the quotient digit, updates rem (64-bit remainder)
+CB_HD uint32_t div_3by2(uint64_t& rem, uint32_t u, uint64_t D, uint32_t v) {
+    const uint32_t d1 = (uint32_t)(D >> 32), d0 = (uint32_t)D;
+    const uint32_t n2 = (uint32_t)(rem >> 32), n1 = (uint32_t)rem;
+    uint64_t qq = (uint64_t)n2 * v + rem;
+    uint32_t q = (uint32_t)(qq >> 32), q0 = (uint32_t)qq;
+    uint32_t r1 = n1 - d1 * q;
+    uint64_t R = (((uint64_t)r1 << 32) | u) - D;
+    R -= (uint64_t)d0 * q;
+    q++;
+    if ((uint32_t)(R >> 32) >= q0) {
+        q--;
+        R += D;
+    }
+    if (R >= D) {
+        q++;
+        R -= D;
+    }
+    rem = R;
+    return q;
+}
+
+// dst = x / d for an exact integer divisor d (|d| < 2^63 given as magnitude + sign): the same ball
+// arb_div(x, ball(d)) produces, in O(L) instead of O(L^2).  S0: L+3 words.
+template <int L, class SCR, class XS = RRef, class DST = WRef>
+CB_NOINLINE Meta arb_div_u64(DST dst, OpdT<XS> x, uint64_t d, bool dneg, SCR S0) {
+    bool nan = is_nan(x.t) || d == 0;
+    int sh = d ? clz64(d) : 0;
+    uint64_t D = d ? (d << sh) : (1ull << 63);
+    uint32_t d1 = (uint32_t)(D >> 32);
+    Meta yt{64 - sh, dneg ? F_SIGN : 0u, 0u, 0};
+    Mag yl = mag_mid_lower(yt, d1);
+    Mag rad = mag_zero();
+    if (!nan && x.t.rman != 0) {
+        Mag num = mag_mul(mag_mid_upper(yt, d1), mag_of(x.t));
+        rad = mag_div(num, mag_mul_lower(yl, yl));
+    }
+    bool zx = is_zero_mid(x.t) || nan;
+    uint32_t v = recip_3by2(d1, (uint32_t)D);
+    // quotient digits L .. 0 of floor(mx * 2^64 / D) (digit L+1 is always 0)
+    uint64_t rem = 0;
+    int hi = -1;
+    (void)div_3by2(rem, zx ? 0u : x.r.ld(L - 1), D, v);
+#pragma unroll 4
+    for (int j = L; j >= 0; j--) {
+        uint32_t u = (j >= 2 && !zx) ? x.r.ld(j - 2) : 0u;
+        uint32_t q = div_3by2(rem, u, D, v);
+        S0.st(j, q);
+        if (q != 0u && hi < 0) hi = j;
+    }
+    Rounded rr = extract<L>(dst, S0, hi, rem != 0, (int64_t)x.t.exp - yt.exp - 32 * L);
+    if (nan) {
+        store_nan<L>(dst);
+        return meta_nan();
+    }
+    bool neg = ((x.t.flags & F_SIGN) != 0) != dneg;
+    return finish<L>(rr, neg, rad);
+}
+
 }  // namespace cb

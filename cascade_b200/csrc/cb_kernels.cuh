@@ -87,6 +87,21 @@ __global__ void __launch_bounds__(TPB, 1) fuchs_shared_kernel(FuchsSharedParams 
     fuchs_shared_thread<L>(p, idx, S0, S1, A0, A1, A2, G0, G1);
 }
 
+// integer-operator kernel: 4 columns of ~L+3 words per thread, light on registers
+template <int L> struct IntopCfg { static constexpr int TPB = L <= 32 ? 384 : (L == 64 ? 192 : 96); };
+template <int L>
+__global__ void __launch_bounds__(IntopCfg<L>::TPB, 1) fuchs_intop_kernel(FuchsIntParams p) {
+    extern __shared__ uint32_t cb_smem[];
+    constexpr int TPB = IntopCfg<L>::TPB;
+    constexpr uint32_t W0 = L + 3, AW = L + 2;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cb_smem) + 4u * threadIdx.x;
+    Scratch<TPB> S0{sbase}, A0{sbase + 4u * W0 * TPB}, A1{sbase + 4u * (W0 + AW) * TPB},
+        A2{sbase + 4u * (W0 + 2 * AW) * TPB};
+    const int64_t idx = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (idx >= p.batch) return;
+    fuchs_intop_thread<L>(p, idx, S0, A0, A1, A2);
+}
+
 // time of a launch is proportional to (number of waves) x (instances per SM per wave) / throughput;
 // measured on B200: 12 warps/SM sustain ~1.13x the throughput of 7 warps/SM
 template <int L>
@@ -119,6 +134,7 @@ struct LaunchTable {
     int (*ew)(const EwParams&, cudaStream_t);
     int (*fuchs_table)(const FuchsTableParams&, cudaStream_t);
     int (*fuchs_shared)(const FuchsSharedParams&, cudaStream_t);
+    int (*fuchs_intop)(const FuchsIntParams&, cudaStream_t);
 };
 
 #define CB_DEFINE_LAUNCH_TABLE(LL)                                                                         \
@@ -139,7 +155,11 @@ struct LaunchTable {
         return launch<LL>(fuchs_shared_kernel<LL, CfgShared<LL>::TPB>, p, p.batch, s, CfgShared<LL>::TPB,  \
                           Sizes<LL>::SMEM_SHARED_PER_THREAD * CfgShared<LL>::TPB);                         \
     }                                                                                                      \
-    extern const LaunchTable launch_table_L##LL = {fuchs_##LL, frob_##LL, horner_##LL, ew_##LL, ftab_##LL, fsh_##LL}; \
+    static int fint_##LL(const FuchsIntParams& p, cudaStream_t s) {                                        \
+        return launch<LL>(fuchs_intop_kernel<LL>, p, p.batch, s, IntopCfg<LL>::TPB,                          \
+                          (size_t)(LL + 3 + 3 * (LL + 2)) * IntopCfg<LL>::TPB * sizeof(uint32_t));           \
+    }                                                                                                      \
+    extern const LaunchTable launch_table_L##LL = {fuchs_##LL, frob_##LL, horner_##LL, ew_##LL, ftab_##LL, fsh_##LL, fint_##LL}; \
     }
 
 extern const LaunchTable launch_table_L4, launch_table_L32, launch_table_L64, launch_table_L128;

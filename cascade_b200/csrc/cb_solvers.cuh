@@ -399,6 +399,97 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
     }
 }
 
+// ================================================================ Fuchs, integer operators
+// Operators whose coefficients are exact real integers (Legendre: reference src/examples.c:3-11).
+// The multipliers of src/fuchs_solver.c:121-135 are then exact integers too -- the reference's
+// acb_mul_fmpz / acb_add produce them without rounding -- so they are formed in 64-bit integer
+// arithmetic per instance, acb_mul(res[b], temp2) becomes a ball x integer product and the final
+// acb_div a division by an integer: O(L) limb operations per coefficient instead of O(L^2), which
+// turns the sweep into a streaming problem.  The balls are the same as the general kernel's.
+// (The host checks that every multiplier stays below 2^62.)
+struct FuchsIntParams {
+    int order, degree, valuation;
+    int64_t n, batch;
+    const int64_t* ode;  // [(order+1)(degree+1)][batch] (ostride = batch) or [..][1] shared (ostride = 0)
+    size_t ostride;
+    CArr res;
+};
+constexpr int INTOP_MAXENT = 36;  // (order+1)(degree+1) <= 36
+
+template <int L, class SCR>
+CB_HD void fuchs_intop_thread(const FuchsIntParams& p, int64_t inst, SCR S0, SCR A0, SCR A1, SCR A2) {
+    const size_t slot = 2 * (size_t)inst;
+    const int v = p.valuation, D1 = p.degree + 1;
+    const int ne = (p.order + 1) * D1;
+    int64_t P[INTOP_MAXENT];
+    for (int e = 0; e < ne; e++) P[e] = p.ode[(size_t)e * (p.ostride ? p.ostride : 1) + (p.ostride ? (size_t)inst : 0)];
+    SCR accRe = A0, accIm = A1, spare = A2;
+#pragma unroll 1
+    for (int64_t bmax = -v; bmax <= p.n; bmax++) {
+        Meta tRe = meta_zero(), tIm = meta_zero();
+        int64_t e = bmax + v;
+        int64_t bmin = clampi(e - p.degree, 0, bmax);
+        int64_t cur = P[0 * D1 + (e - bmin)];
+        int64_t b = bmin;
+#pragma unroll 1
+        do {
+            if (!warp_all(cur == 0)) {  // x * 0 is an exact zero and acc - 0 leaves acc untouched
+                CRef x = at<L>(p.res, b, slot);
+                for (int part = 0; part < 2; part++) {
+                    Opd xp = part ? im_of(x) : re_of(x);
+                    Meta& tacc = part ? tIm : tRe;
+                    SCR& acc = part ? accIm : accRe;
+                    if (warp_all(is_exact_zero(xp.t))) continue;  // 0 * cur = 0
+                    Meta pr = arb_mul_si<L>(WRef{spare.generic(), SCR::GSTRIDE}, xp, cur, S0);
+                    if (warp_all(is_exact_zero(tacc))) {  // 0 - x = -x exactly
+                        SCR t = acc;
+                        acc = spare;
+                        spare = t;
+                        tacc = pr;
+                        if (!is_nan(tacc) && !is_zero_mid(tacc)) tacc.flags ^= F_SIGN;
+                    } else {
+                        SCR where;
+                        tacc = arb_addsub_cols<L>(acc, tacc, spare, pr, true, &where);
+                        if (where.a_or_p() == spare.a_or_p()) {
+                            SCR t = acc;
+                            acc = spare;
+                            spare = t;
+                        }
+                    }
+                }
+            }
+            // next multiplier, exactly as the reference forms temp2 (all integers)
+            int64_t t2 = 0, fac = 1;
+            b++;
+            int64_t imin = clampi(b - e, 0, -v);
+            int64_t imax = clampi(b - bmin, 0, p.order);
+            for (int64_t i = imin; i <= imax; i++) {
+                t2 += P[i * D1 + (i + e - b)] * fac;
+                fac *= (b - i);
+            }
+            fac = 1;
+            for (int64_t q = 0; q < imin; q++) fac *= (b - imin + 1 + q);
+            cur = t2 * fac;
+        } while (b != bmax);
+        CRef out = at<L>(p.res, bmax, slot);
+        uint64_t dmag = cur < 0 ? (uint64_t)0 - (uint64_t)cur : (uint64_t)cur;
+        for (int part = 0; part < 2; part++) {
+            Meta tacc = part ? tIm : tRe;
+            SCR acc = part ? accIm : accRe;
+            WRef dst = part ? wim(out) : wre(out);
+            Meta to;
+            if (warp_all(is_exact_zero(tacc) && cur != 0)) {
+                store_nan<L>(dst);  // zeros
+                to = meta_zero();
+            } else {
+                Opd xa{RRef{acc.generic(), SCR::GSTRIDE}, tacc};
+                to = arb_div_u64<L>(dst, xa, dmag, cur < 0, S0);
+            }
+            st_meta(out.t + part, to);
+        }
+    }
+}
+
 // ================================================================ Frobenius (M = 1)
 struct FrobParams {
     int order, degree, valuation;

@@ -77,6 +77,18 @@ int cb200_fuchs_batch_host(int L, int order, int degree, int valuation, int64_t 
                            const uint32_t *ode_mant, const cb_meta *ode_meta, int shared_ode,
                            uint32_t *res_mant, cb_meta *res_meta, int device);
 
+/* ---- acb_ode_solve_fuchs for operators with exact real INTEGER coefficients (acb_ode_legendre,
+ * reference src/examples.c:3-11): ode_int[(order+1)*(degree+1)][batch] int64 (entry-major; one column
+ * when shared_ode).  Same balls as cb200_fuchs_batch_*, computed with O(L) work per coefficient.
+ * Every multiplier the reference forms at src/fuchs_solver.c:121-135 must stay below 2^62 in magnitude:
+ * (order+1) * max|coefficient| * (n+1)^order < 2^62 (the caller checks; cascade_b200.api does). */
+int cb200_fuchs_intop_batch_dev(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
+                                const int64_t *ode_int, int shared_ode, uint32_t *res_mant,
+                                cb_meta *res_meta, void *stream);
+int cb200_fuchs_intop_batch_host(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
+                                 const int64_t *ode_int, int shared_ode, uint32_t *res_mant,
+                                 cb_meta *res_meta, int device);
+
 /* ---- _acb_ode_solve_frobenius, homogeneous case, M = 1 (reference src/frobenius_solver.c:72-121)
  * rho : 1 entry, S = 2*batch or 2 (shared_rho).  res: n+1 entries, all written (g_0 = 1). */
 int cb200_frobenius1_batch_dev(int L, int order, int degree, int valuation, int64_t n, int64_t batch,

@@ -161,6 +161,49 @@ def case_fuchs_shared_adversarial(oracle, drv, L: int, seed: int, trials: int = 
         assert_same(ro, rs, f"fuchs shared adversarial L={L} trial={trial}")
 
 
+def case_fuchs_integer_operators(oracle, drv, L: int, seed: int):
+    """BASELINE configs[3]'s path: Legendre sweep (acb_ode_legendre(n), reference src/examples.c:3-11)
+    and random integer operators with complex data, through the integer-operator kernel; must give
+    the same balls as the oracle's general loop (and as the general kernel)."""
+    rng = np.random.default_rng(seed)
+    ns = list(range(0, 40)) + [10**3, 2**20 - 1, 12345, 999999]
+    batch = len(ns)
+    ode = api.acb_ode_legendre_batch(ns, L)
+    assert api.integer_operator(ode, 2, 2, 60) is not None
+    init = from_complex([1, 1] * batch, L)  # c0 = c1 = 1 (SURVEY 8d config 4)
+    n = 60
+    rc, ro = oracle.fuchs_batch(2, 2, n, ode, init, batch, False)
+    rs = api.acb_ode_solve_fuchs_batch(ode, init, 2, 2, n, batch, False, driver=drv)
+    assert_same(ro, rs, f"legendre sweep L={L}")
+    rg = api.acb_ode_solve_fuchs_batch(ode, init, 2, 2, n, batch, False, driver=drv, use_intop=False)
+    assert_same(ro, rg, f"legendre sweep, general kernel L={L}")
+    # n = 4, c0 = c1 = 1: c2 = -(20 c0)/2 = -10, c3 = -(20 - 2) c1 / 6 = -3 exactly
+    k4 = ns.index(4)
+    assert rs.mid(2 * (k4 * (n + 1) + 2)) == -10 and rs.mid(2 * (k4 * (n + 1) + 3)) == -3
+    # random integer operators, complex balls with radii as data
+    for trial in range(4):
+        degree = 2 + int(rng.integers(0, 3))
+        order = 2 + int(rng.integers(0, degree - 1))
+        ne = (order + 1) * (degree + 1)
+        batch = 9
+        vals = rng.integers(-50, 50, size=(batch, ne))
+        vals[:, order * (degree + 1)] = rng.integers(1, 9, size=batch) * rng.choice([-1, 1], size=batch)  # leading != 0
+        vals[rng.random(vals.shape) < 0.3] = 0
+        vals[:, order * (degree + 1)] = np.where(vals[:, order * (degree + 1)] == 0, 3, vals[:, order * (degree + 1)])
+        ode = from_complex([int(x) for x in vals.reshape(-1)], L)
+        v = api.acb_ode_valuation(ode, order, degree)
+        if v >= 0:
+            continue
+        # all instances must share the valuation for one launch
+        if any(api.acb_ode_valuation(ode, order, degree, inst=i) != v for i in range(batch)):
+            continue
+        n = -v + 25
+        init = random_balls(rng, batch * (-v) * 2, L, -3, 3, "ulp", short_frac=0.3)
+        rc, ro = oracle.fuchs_batch(order, degree, n, ode, init, batch, False)
+        rs = api.acb_ode_solve_fuchs_batch(ode, init, order, degree, n, batch, False, driver=drv)
+        assert_same(ro, rs, f"integer operators L={L} order={order} degree={degree} v={v}")
+
+
 def bessel_shifted(oracle, rng, L: int):
     """BASELINE config 2's operator: Bessel with complex nu, shifted to a complex ordinary point
     (acb_ode_bessel + acb_ode_shift, reference src/examples.c:13-22, src/acb_ode.c:124-135)."""

@@ -87,6 +87,25 @@ int cbsim_fuchs_batch(int L_, int order, int degree, int valuation, int64_t n, i
     return 0;
 }
 
+int cbsim_fuchs_intop_batch(int L_, int order, int degree, int valuation, int64_t n, int64_t batch,
+                            const int64_t* ode_int, int shared_ode, uint32_t* res_mant, cb_meta* res_meta) {
+    if (valuation >= 0) return CB200_EVALUATION;
+    FuchsIntParams p;
+    p.order = order; p.degree = degree; p.valuation = valuation; p.n = n; p.batch = batch;
+    p.ode = ode_int; p.ostride = shared_ode ? 0 : (size_t)batch;
+    p.res = CArr{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
+    const size_t sizes[4] = {(size_t)L_ + 3, (size_t)L_ + 2, (size_t)L_ + 2, (size_t)L_ + 2};
+    const size_t CAN = 64;
+    std::vector<uint32_t> col[4];
+    for (int c = 0; c < 4; c++) col[c].assign(sizes[c] + CAN, 0xDEADBEEFu);
+    Scratch<1> S0{col[0].data()}, A0{col[1].data()}, A1{col[2].data()}, A2{col[3].data()};
+    SIM_DISPATCH(L_, for (int64_t i = 0; i < batch; i++) fuchs_intop_thread<L>(p, i, S0, A0, A1, A2));
+    for (int c = 0; c < 4; c++)
+        for (size_t k = sizes[c]; k < sizes[c] + CAN; k++)
+            if (col[c][k] != 0xDEADBEEFu) return -1000 - c;
+    return 0;
+}
+
 int cbsim_frobenius1_batch(int L_, int order, int degree, int valuation, int64_t n, int64_t batch,
                            const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
                            const uint32_t* rho_mant, const cb_meta* rho_meta, int shared_rho,

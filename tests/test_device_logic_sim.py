@@ -30,6 +30,11 @@ def test_fuchs_shared_adversarial(oracle, sim_driver, L):
     cases.case_fuchs_shared_adversarial(oracle, sim_driver, L, seed=77 + L, batch=12)
 
 
+@pytest.mark.parametrize("L", [4, 32, 64])
+def test_fuchs_integer_operators(oracle, sim_driver, L):
+    cases.case_fuchs_integer_operators(oracle, sim_driver, L, seed=5 + L)
+
+
 def test_fuchs_bessel_shared(oracle, sim_driver):
     cases.case_fuchs_bessel_shared(oracle, sim_driver, 32, seed=5, n=40, batch=3)
 

@@ -31,6 +31,11 @@ def test_fuchs_shared_adversarial(oracle, gpu_driver, L):
     cases.case_fuchs_shared_adversarial(oracle, gpu_driver, L, seed=87 + L, batch=70)
 
 
+@pytest.mark.parametrize("L", [4, 32, 64, 128])
+def test_fuchs_integer_operators(oracle, gpu_driver, L):
+    cases.case_fuchs_integer_operators(oracle, gpu_driver, L, seed=15 + L)
+
+
 @pytest.mark.parametrize("L", [32, 64])
 def test_fuchs_bessel_shared(oracle, gpu_driver, L):
     cases.case_fuchs_bessel_shared(oracle, gpu_driver, L, seed=5, n=60, batch=300)
