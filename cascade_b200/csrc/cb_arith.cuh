@@ -232,6 +232,35 @@ struct RRef {
     size_t stride;
     CB_HD uint32_t ld(int j) const { return m[(size_t)j * stride]; }
 };
+// limb k at m[k * STRIDE] with a compile-time stride (data shared by the batch: STRIDE = 2), so
+// every access is base + immediate
+template <int STRIDE>
+struct RFix {
+    const uint32_t* m;
+    CB_HD uint32_t ld(int j) const { return m[(size_t)j * STRIDE]; }
+    CB_HD RRef dyn() const { return RRef{m, (size_t)STRIDE}; }
+};
+// load L consecutive limbs of a source into registers; for a runtime stride the address is
+// advanced by pointer increments (two ALU instructions per limb) instead of a 64-bit multiply per
+// limb on the FMA pipe, which the limb products need
+template <int L>
+CB_HD void load_limbs(uint32_t (&a)[L], RRef x) {
+    const uint32_t* p = x.m;
+#pragma unroll
+    for (int j = 0; j < L; j++) {
+        a[j] = *p;
+        p += x.stride;
+#if defined(__CUDA_ARCH__)
+        asm volatile("" : "+l"(p));  // keep the increment chain (no re-materialised j * stride)
+#endif
+    }
+}
+template <int L, int STRIDE>
+CB_HD void load_limbs(uint32_t (&a)[L], RFix<STRIDE> x) {
+#pragma unroll
+    for (int j = 0; j < L; j++) a[j] = x.ld(j);
+}
+
 struct WRef {
     uint32_t* m;
     size_t stride;
@@ -779,12 +808,8 @@ CB_NOINLINE Meta arb_fdot2_trunc(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2,
             continue;
         }
         uint32_t a[L], b[L];
-        XS xs = term ? xB : xA;
-        YS ys = term ? yB : yA;
-#pragma unroll
-        for (int j = 0; j < L; j++) a[j] = xs.ld(j);
-#pragma unroll
-        for (int j = 0; j < L; j++) b[j] = ys.ld(j);
+        load_limbs<L>(a, term ? xB : xA);
+        load_limbs<L>(b, term ? yB : yA);
         mul_high<L, K>(r, a, b);
     }
     bool done = false, neg = false;

@@ -52,6 +52,11 @@ CB_HD void st_meta(Meta* p, const Meta& t) {
 }
 CB_HD Opd re_of(const CRef& x) { return Opd{RRef{x.m, x.stride}, ld_meta(x.t)}; }
 CB_HD Opd im_of(const CRef& x) { return Opd{RRef{x.m + 1, x.stride}, ld_meta(x.t + 1)}; }
+// shared-format entries (S = 2): fixed-stride views
+using OpdS = OpdT<RFix<2>>;
+CB_HD OpdS re_of_shared(const CRef& x) { return OpdS{RFix<2>{x.m}, ld_meta(x.t)}; }
+CB_HD OpdS im_of_shared(const CRef& x) { return OpdS{RFix<2>{x.m + 1}, ld_meta(x.t + 1)}; }
+CB_HD Opd dyn(const OpdS& o) { return Opd{o.r.dyn(), o.t}; }
 CB_HD WRef wre(const CRef& x) { return WRef{x.m, x.stride}; }
 CB_HD WRef wim(const CRef& x) { return WRef{x.m + 1, x.stride}; }
 
@@ -303,15 +308,15 @@ constexpr bool use_trunc() { return L >= 16 && L <= 32; }
 // one fused dot product of the recurrence: truncated products with the exact general path as the
 // per-lane fallback (L = 16..32), or the exact in-shared-memory version (other precisions)
 template <int L, class SCR, class DST>
-CB_HD Meta rec_fdot2(DST dst, Opd x1, Opd y1, Opd x2, Opd y2, bool neg2, SCR S0, SCR S1, GScratch G0, GScratch G1) {
+CB_HD Meta rec_fdot2(DST dst, Opd x1, OpdS y1, Opd x2, OpdS y2, bool neg2, SCR S0, SCR S1, GScratch G0, GScratch G1) {
     if constexpr (use_trunc<L>()) {
         bool ok;
-        Meta t = arb_fdot2_trunc<L>(dst, x1, y1, x2, y2, neg2, S0, &ok);
+        Meta t = arb_fdot2_trunc<L, SCR, RRef, RFix<2>>(dst, x1, y1, x2, y2, neg2, S0, &ok);
         CB_COUNT(ok ? 4 : 5);
-        if (!ok) t = arb_fdot2_general<L>(dst, x1, y1, x2, y2, neg2, G0, G1);
+        if (!ok) t = arb_fdot2_general<L>(dst, x1, dyn(y1), x2, dyn(y2), neg2, G0, G1);
         return t;
     } else {
-        return arb_fdot2<L>(dst, x1, y1, x2, y2, neg2, S0, S1);
+        return arb_fdot2<L>(dst, x1, dyn(y1), x2, dyn(y2), neg2, S0, S1);
     }
 }
 
@@ -332,7 +337,8 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
 #pragma unroll 1
         for (int k = 0; k < cnt; k++) {
             CRef x = at<L>(p.res, bmin + k, slot), y = at<L>(p.tbl, base + k, 0);
-            Opd a = re_of(x), b = im_of(x), c = re_of(y), d = im_of(y);
+            Opd a = re_of(x), b = im_of(x);
+            OpdS c = re_of_shared(y), d = im_of_shared(y);
             // real part: acc.re -= a c - b d
             Meta pr = rec_fdot2<L>(WRef{spare.generic(), SCR::GSTRIDE}, a, c, b, d, true, use_trunc<L>() ? spare : S0,
                                    S1, G0, G1);
@@ -374,7 +380,7 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
         Opd xa{RRef{accRe.generic(), SCR::GSTRIDE}, tRe}, xb{RRef{accIm.generic(), SCR::GSTRIDE}, tIm};
         if (p.kind[bmax + v] == 1) {
             CRef y = at<L>(p.tbl, base + W + 1, 0);
-            Opd c = re_of(y), d = im_of(y);
+            OpdS c = re_of_shared(y), d = im_of_shared(y);
             Meta tr = rec_fdot2<L>(wre(out), xa, c, xb, d, true, use_trunc<L>() ? spare : S0, S1, G0, G1);
             Meta ti = rec_fdot2<L>(wim(out), xa, d, xb, c, false, use_trunc<L>() ? spare : S0, S1, G0, G1);
             st_meta(out.t, tr);
