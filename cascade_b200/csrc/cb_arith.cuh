@@ -691,7 +691,21 @@ CB_NOINLINE Meta arb_fdot2(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2, OpdT<
             if (term ? skip2 : skip1) continue;
             product<L>(term ? S1 : S0, term ? x2.r : x1.r, term ? y2.r : y1.r);
         }
-        rr = align_add<L, 2 * L>(dst, S0, S1, e1, e2, n1, n2, z1, z2, &neg);
+        bool done = false;
+        if constexpr (L <= 64) {
+            // same in-register tail as above, reading both products from their columns
+            int64_t d = e1 - e2;
+            bool easy = !(z1 && z2) && (z1 || z2 || (d <= 31 && d >= -31));
+            if (easy) {
+                int64_t E = z1 ? e2 : (z2 ? e1 : (e1 > e2 ? e1 : e2));
+                int s1 = z1 ? 0 : (int)(E - e1), s2 = z2 ? 0 : (int)(E - e2);
+                bool sub = (n1 != n2) && !z1 && !z2;
+                auto w1 = [&](int k) -> uint32_t { return z1 ? 0u : S0.ld(k); };
+                auto w2 = [&](int k) -> uint32_t { return z2 ? 0u : S1.ld(k); };
+                done = fast_add_round<L, 2 * L>(dst, w1, w2, s1, s2, sub, z1 ? n2 : n1, z1 ? n1 : n2, E, &rr, &neg);
+            }
+        }
+        if (!done) rr = align_add<L, 2 * L>(dst, S0, S1, e1, e2, n1, n2, z1, z2, &neg);
     }
     if (nan) return meta_nan();
     return finish<L>(rr, neg, rad);
@@ -849,13 +863,31 @@ template <int L, class SCR>
 CB_NOINLINE Meta arb_addsub(WRef dst, Opd x, Opd y, bool negy, SCR S0, SCR S1) {
     bool nan = is_nan(x.t) || is_nan(y.t);
     bool zx = is_zero_mid(x.t) || nan, zy = is_zero_mid(y.t) || nan;
-#pragma unroll
-    for (int j = 0; j < L; j++) S0.st(j, x.r.ld(j));
-#pragma unroll
-    for (int j = 0; j < L; j++) S1.st(j, y.r.ld(j));
+    bool nx = (x.t.flags & F_SIGN) != 0, ny = ((y.t.flags & F_SIGN) != 0) != negy;
     bool neg;
-    Rounded rr = align_add<L, L>(dst, S0, S1, x.t.exp, y.t.exp, (x.t.flags & F_SIGN) != 0,
-                                 ((y.t.flags & F_SIGN) != 0) != negy, zx, zy, &neg);
+    Rounded rr;
+    bool done = false;
+    {
+        // operands within 31 bits of each other: statically indexed sum straight from memory
+        // (all limbs are read before dst is written, so dst may alias x or y)
+        int64_t d = (int64_t)x.t.exp - y.t.exp;
+        bool easy = !(zx && zy) && (zx || zy || (d <= 31 && d >= -31));
+        if (easy) {
+            int64_t E = zx ? y.t.exp : (zy ? x.t.exp : (x.t.exp > y.t.exp ? x.t.exp : y.t.exp));
+            int s1 = zx ? 0 : (int)(E - x.t.exp), s2 = zy ? 0 : (int)(E - y.t.exp);
+            bool sub = (nx != ny) && !zx && !zy;
+            auto w1 = [&](int k) -> uint32_t { return zx ? 0u : x.r.ld(k); };
+            auto w2 = [&](int k) -> uint32_t { return zy ? 0u : y.r.ld(k); };
+            done = fast_add_round<L, L>(dst, w1, w2, s1, s2, sub, zx ? ny : nx, zx ? nx : ny, E, &rr, &neg);
+        }
+    }
+    if (!done) {
+#pragma unroll 8
+        for (int j = 0; j < L; j++) S0.st(j, x.r.ld(j));
+#pragma unroll 8
+        for (int j = 0; j < L; j++) S1.st(j, y.r.ld(j));
+        rr = align_add<L, L>(dst, S0, S1, x.t.exp, y.t.exp, nx, ny, zx, zy, &neg);
+    }
     if (nan) return meta_nan();
     return finish<L>(rr, neg, mag_add(mag_of(x.t), mag_of(y.t)));
 }

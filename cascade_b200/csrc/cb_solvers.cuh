@@ -62,7 +62,7 @@ CB_HD WRef wim(const CRef& x) { return WRef{x.m + 1, x.stride}; }
 
 template <int L>
 CB_HD void acb_set(const CRef& z, const CRef& x) {
-#pragma unroll
+#pragma unroll 8
     for (int k = 0; k < L; k++) {
         z.m[k * z.stride] = x.m[k * x.stride];
         z.m[k * z.stride + 1] = x.m[k * x.stride + 1];
@@ -72,7 +72,7 @@ CB_HD void acb_set(const CRef& z, const CRef& x) {
 }
 template <int L>
 CB_HD void acb_zero(const CRef& z) {
-#pragma unroll
+#pragma unroll 8
     for (int k = 0; k < L; k++) {
         z.m[k * z.stride] = 0u;
         z.m[k * z.stride + 1] = 0u;
@@ -118,7 +118,7 @@ CB_HD void acb_add_si(const CRef& z, const CRef& x, int64_t k, const CRef& kball
     uint64_t ka = k < 0 ? (uint64_t)0 - (uint64_t)k : (uint64_t)k;
     int sh = clz64(ka);
     uint64_t kn = ka ? ka << sh : 0;
-#pragma unroll
+#pragma unroll 8
     for (int j = 0; j < L; j++) kball.m[j * kball.stride] = 0u;
     kball.m[(L - 1) * kball.stride] = (uint32_t)(kn >> 32);
     kball.m[(L - 2) * kball.stride] = (uint32_t)kn;
@@ -127,7 +127,7 @@ CB_HD void acb_add_si(const CRef& z, const CRef& x, int64_t k, const CRef& kball
     Meta tr = arb_addsub<L>(wre(z), re_of(x), ko, false, S0, S1);
     st_meta(z.t, tr);
     if (z.m != x.m) {
-#pragma unroll
+#pragma unroll 8
         for (int j = 0; j < L; j++) z.m[j * z.stride + 1] = x.m[j * x.stride + 1];
         st_meta(z.t + 1, ld_meta(x.t + 1));
     }
