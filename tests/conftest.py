@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # a fresh checkout has no built artefacts: build them once (nvcc cross-compiles without a GPU)
+    lib = os.path.join(ROOT, "cascade_b200", "libcascade_b200.so")
+    if not os.path.exists(lib):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 @pytest.fixture(scope="session")
