@@ -27,6 +27,7 @@ SYMBOLS = [
     "cb200_horner_workspace_bytes", "cb200_ew_workspace_bytes",
     "cb200_fuchs_batch_dev", "cb200_fuchs_batch_host",
     "cb200_fuchs_intop_batch_dev", "cb200_fuchs_intop_batch_host",
+    "cb200_continuation_workspace_bytes", "cb200_continuation_dev", "cb200_continuation_host",
     "cb200_frobenius1_batch_dev", "cb200_frobenius1_batch_host",
     "cb200_horner_batch_dev", "cb200_horner_batch_host",
     "cb200_ew_dev", "cb200_ew_host",
@@ -60,6 +61,12 @@ def lib() -> C.CDLL:
     _i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
     L.cb200_fuchs_intop_batch_dev.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_vp, C.c_int, _vp, _vp, _vp]
     L.cb200_fuchs_intop_batch_host.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_i64p, C.c_int, _u32p, _i32p, C.c_int]
+    L.cb200_continuation_workspace_bytes.restype = C.c_size_t
+    L.cb200_continuation_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64]
+    L.cb200_continuation_dev.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp,
+                                         _vp, _vp, _vp, _vp, C.c_size_t, _vp]
+    L.cb200_continuation_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, _u32p, _i32p,
+                                          _u32p, _i32p, _u32p, _i32p, C.c_int]
     L.cb200_frobenius1_batch_dev.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_size_t, _vp]
     L.cb200_frobenius1_batch_host.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int]
     L.cb200_horner_batch_dev.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]

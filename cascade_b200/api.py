@@ -37,6 +37,10 @@ class HostBufferDriver:
         return _lib.lib().cb200_fuchs_intop_batch_host(L, order, degree, valuation, n, batch, ode_int, int(shared),
                                                        res_m, res_t, self.device)
 
+    def continuation(self, L, order, degree, n, batch, path_len, ode_m, ode_t, path_m, path_t, y_m, y_t):
+        return _lib.lib().cb200_continuation_host(L, order, degree, n, batch, path_len, ode_m, ode_t, path_m, path_t,
+                                                  y_m, y_t, self.device)
+
     def frobenius1(self, L, order, degree, valuation, n, batch, ode_m, ode_t, shared, rho_m, rho_t,
                    shared_rho, res_m, res_t):
         return _lib.lib().cb200_frobenius1_batch_host(L, order, degree, valuation, n, batch, ode_m, ode_t,
@@ -167,6 +171,23 @@ def acb_ode_solve_frobenius1_batch(ode: Balls, rho: Balls, order: int, degree: i
     _lib.check(drv.frobenius1(L, order, degree, v, n, batch, ode_m, ode_t, shared_ode, rho_m, rho_t,
                               shared_rho, res_m, res_t), "acb_ode_solve_frobenius1_batch")
     return entry_major_to_instance_major(unpack_entries(L, res_m, res_t), batch, n + 1)
+
+
+def analytic_continuation_batch(ode: Balls, path: Balls, y0: Balls, order: int, degree: int, n: int, batch: int,
+                                driver=None) -> Balls:
+    """``analytic_continuation(res, ODE, path, len, n, bits)`` (reference src/fuchs_solver.c:147-163)
+    for ``batch`` solutions of one operator along one path, device resident.  ``y0``: ``[batch][order]``
+    Taylor coefficients at ``path[0]``; returns those at the last corner.  Every corner must be an
+    ordinary point of the operator."""
+    drv = driver or default_driver()
+    L = ode.L
+    plen = path.n_slots // 2
+    ode_m, ode_t = _ode_to_device(ode, order, degree, batch, True)
+    path_m, path_t = pack_entries(path, plen, 2)
+    y_m, y_t = pack_entries(instance_major_to_entry_major(y0, batch, order), order, 2 * batch)
+    _lib.check(drv.continuation(L, order, degree, n, batch, plen, ode_m, ode_t, path_m, path_t, y_m, y_t),
+               "analytic_continuation_batch")
+    return entry_major_to_instance_major(unpack_entries(L, y_m, y_t), batch, order)
 
 
 def acb_poly_evaluate_batch(f: Balls, pts: Balls, nder: int = 1, driver=None) -> Balls:

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <vector>
 
 #include "../../include/cascade_b200.h"
 #include "cb_kernels.cuh"
@@ -231,6 +232,95 @@ int cb200_ew_dev(int op, int L_, int64_t n, uint32_t* z_mant, cb_meta* z_meta, c
     return table_for(L_)->ew(p, (cudaStream_t)stream);
 }
 
+#define CUDA_RET(x)                          \
+    do {                                     \
+        cudaError_t e_ = (x);                \
+        if (e_ != cudaSuccess) return (int)e_; \
+    } while (0)
+
+// ------------------------------------------------------------------ analytic continuation
+size_t cb200_continuation_workspace_bytes(int L, int order, int degree, int64_t n, int64_t batch) {
+    int64_t ne = (int64_t)(order + 1) * (degree + 1);
+    return carve_bytes(L, ne, 2)            /* shifted operator */
+           + carve_bytes(L, 3, 2)           /* step, product and sum temporaries (single balls) */
+           + carve_bytes(L, n + 1, 2 * batch) /* the series of the current step */
+           + cb200_fuchs_workspace_bytes(L, order, degree, -order, n, batch, 1) + cb200_horner_workspace_bytes(L, batch) +
+           cb200_ew_workspace_bytes(L, 1) + 1024;
+}
+
+int cb200_continuation_dev(int L_, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
+                           const uint32_t* ode_mant, const cb_meta* ode_meta, const uint32_t* path_mant,
+                           const cb_meta* path_meta, const uint8_t* corner_is_zero, uint32_t* y_mant, cb_meta* y_meta,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+    if (!supported_L(L_) || order < 1 || order > HORNER_MAXDER || degree < 0 || batch < 0 || n < order || path_len < 1)
+        return CB200_EINVAL;
+    if (workspace_bytes < cb200_continuation_workspace_bytes(L_, order, degree, n, batch)) return CB200_ENOMEM;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t ne = (int64_t)(order + 1) * (degree + 1), S = 2 * batch;
+    char* w = (char*)workspace;
+    CArr sh = carve(w, L_, ne, 2);
+    CArr tb = carve(w, L_, 3, 2);  // [0] step a, [1] product, [2] sum
+    CArr ser = carve(w, L_, n + 1, S);
+    size_t fw = cb200_fuchs_workspace_bytes(L_, order, degree, -order, n, batch, 1);
+    void* fws = w;
+    w += align256(fw);
+    size_t hw = cb200_horner_workspace_bytes(L_, batch);
+    void* hws = w;
+    w += align256(hw);
+    size_t ew = cb200_ew_workspace_bytes(L_, 1);
+    void* ews = w;
+    auto ball_m = [&](const CArr& a, int64_t e) { return a.m + (size_t)e * L_ * a.S; };
+    auto ball_t = [&](const CArr& a, int64_t e) { return (cb_meta*)(a.t + (size_t)e * a.S); };
+    const size_t ball_mb = arr_mant_bytes(L_, 1, 2), ball_tb = arr_meta_bytes(1, 2);
+    for (int64_t t = 0; t + 1 < path_len; t++) {
+        // acb_ode_shift(ODE_shift, ODE, path + t): copy, then p[j] += p[j+1] * a (Horner Taylor shift)
+        CUDA_RET(cudaMemcpyAsync(sh.m, ode_mant, arr_mant_bytes(L_, ne, 2), cudaMemcpyDeviceToDevice, st));
+        CUDA_RET(cudaMemcpyAsync(sh.t, ode_meta, arr_meta_bytes(ne, 2), cudaMemcpyDeviceToDevice, st));
+        const uint32_t* am = path_mant + (size_t)t * L_ * 2;
+        const cb_meta* at_ = path_meta + (size_t)t * 2;
+        if (degree > 0 && !(corner_is_zero && corner_is_zero[t])) {
+            int D1 = degree + 1;
+            for (int row = 0; row <= order; row++)
+                for (int i = D1 - 2; i >= 0; i--)
+                    for (int j = i; j <= D1 - 2; j++) {
+                        int64_t ej = (int64_t)row * D1 + j;
+                        int rc = cb200_ew_dev(CB200_OP_MUL, L_, 1, ball_m(tb, 1), ball_t(tb, 1), ball_m(sh, ej + 1),
+                                              ball_t(sh, ej + 1), am, at_, nullptr, ews, ew, stream);
+                        if (rc) return rc;
+                        rc = cb200_ew_dev(CB200_OP_ADD, L_, 1, ball_m(tb, 2), ball_t(tb, 2), ball_m(sh, ej), ball_t(sh, ej),
+                                          ball_m(tb, 1), ball_t(tb, 1), nullptr, ews, ew, stream);
+                        if (rc) return rc;
+                        CUDA_RET(cudaMemcpyAsync(ball_m(sh, ej), ball_m(tb, 2), ball_mb, cudaMemcpyDeviceToDevice, st));
+                        CUDA_RET(cudaMemcpyAsync(ball_t(sh, ej), ball_t(tb, 2), ball_tb, cudaMemcpyDeviceToDevice, st));
+                    }
+        }
+        // acb_ode_solve_fuchs(res, ODE_shift, n): res[0..order-1] = y (an ordinary point: valuation = -order)
+        CUDA_RET(cudaMemcpyAsync(ser.m, y_mant, arr_mant_bytes(L_, order, S), cudaMemcpyDeviceToDevice, st));
+        CUDA_RET(cudaMemcpyAsync(ser.t, y_meta, arr_meta_bytes(order, S), cudaMemcpyDeviceToDevice, st));
+        int rc = cb200_fuchs_batch_dev(L_, order, degree, -order, n, batch, sh.m, (cb_meta*)sh.t, 1, ser.m, (cb_meta*)ser.t,
+                                       fws, fw, stream);
+        if (rc) return rc;
+        // a = path[t+1] - path[t]; y[k] = res^(k)(a)/k! for k < order (all that the next step reads)
+        rc = cb200_ew_dev(CB200_OP_SUB, L_, 1, ball_m(tb, 0), ball_t(tb, 0), path_mant + (size_t)(t + 1) * L_ * 2,
+                          path_meta + (size_t)(t + 1) * 2, am, at_, nullptr, ews, ew, stream);
+        if (rc) return rc;
+        HornerParams hp;
+        hp.nder = order;
+        hp.len = n + 1;
+        hp.npts = batch;
+        hp.f = ser;
+        hp.pts = CArr{ball_m(tb, 0), (Meta*)ball_t(tb, 0), (size_t)2};
+        hp.out = CArr{y_mant, (Meta*)y_meta, (size_t)S};
+        char* hwp = (char*)hws;
+        hp.tmp = carve(hwp, L_, 1, S);
+        g_launches.fetch_add(batch > 0);
+        rc = table_for(L_)->horner(hp, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+
 // ------------------------------------------------------------------ host-buffer (end-to-end) entry points
 #define CK(x)                                \
     do {                                     \
@@ -373,6 +463,40 @@ int cb200_ew_host(int op, int L, int64_t n, uint32_t* z_mant, cb_meta* z_meta, c
     if (rc) return rc;
     CK(cudaMemcpy(z_mant, zm.p, arr_mant_bytes(L, 1, S), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(z_meta, zt.p, arr_meta_bytes(1, S), cudaMemcpyDeviceToHost));
+    return (int)cudaDeviceSynchronize();
+}
+
+int cb200_continuation_host(int L, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
+                            const uint32_t* ode_mant, const cb_meta* ode_meta, const uint32_t* path_mant,
+                            const cb_meta* path_meta, uint32_t* y_mant, cb_meta* y_meta, int device) {
+    if (!supported_L(L) || order < 1 || degree < 0 || batch < 0 || n < order || path_len < 1) return CB200_EINVAL;
+    CK(cudaSetDevice(device));
+    int64_t ne = (int64_t)(order + 1) * (degree + 1), S = 2 * batch;
+    std::vector<uint8_t> zero(path_len);
+    for (int64_t t = 0; t < path_len; t++) {
+        const cb_meta* m = path_meta + 2 * t;
+        zero[t] = (m[0].flags & CB_FLAG_ZERO) && m[0].rman == 0 && (m[1].flags & CB_FLAG_ZERO) && m[1].rman == 0;
+    }
+    DevBuf om, ot, pm, pt, ym, yt, ws;
+    size_t wsb = cb200_continuation_workspace_bytes(L, order, degree, n, batch);
+    CK(om.alloc(arr_mant_bytes(L, ne, 2)));
+    CK(ot.alloc(arr_meta_bytes(ne, 2)));
+    CK(pm.alloc(arr_mant_bytes(L, path_len, 2)));
+    CK(pt.alloc(arr_meta_bytes(path_len, 2)));
+    CK(ym.alloc(arr_mant_bytes(L, order, S)));
+    CK(yt.alloc(arr_meta_bytes(order, S)));
+    CK(ws.alloc(wsb));
+    CK(cudaMemcpy(om.p, ode_mant, arr_mant_bytes(L, ne, 2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ot.p, ode_meta, arr_meta_bytes(ne, 2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pm.p, path_mant, arr_mant_bytes(L, path_len, 2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pt.p, path_meta, arr_meta_bytes(path_len, 2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ym.p, y_mant, arr_mant_bytes(L, order, S), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(yt.p, y_meta, arr_meta_bytes(order, S), cudaMemcpyHostToDevice));
+    int rc = cb200_continuation_dev(L, order, degree, n, batch, path_len, (uint32_t*)om.p, (cb_meta*)ot.p, (uint32_t*)pm.p,
+                                    (cb_meta*)pt.p, zero.data(), (uint32_t*)ym.p, (cb_meta*)yt.p, ws.p, wsb, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(y_mant, ym.p, arr_mant_bytes(L, order, S), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(y_meta, yt.p, arr_meta_bytes(order, S), cudaMemcpyDeviceToHost));
     return (int)cudaDeviceSynchronize();
 }
 

@@ -561,7 +561,7 @@ struct HornerParams {
     int64_t len;    // series length
     int64_t npts;   // evaluation points == threads
     CArr f;         // len entries; S = 2 (one series for all points) or 2*npts
-    CArr pts;       // 1 entry, S = 2*npts
+    CArr pts;       // 1 entry, S = 2*npts, or S = 2: one point for all series (continuation step)
     CArr out;       // nder entries, S = 2*npts
     CArr tmp;       // 1 entry, S = 2*npts
 };
@@ -571,7 +571,7 @@ template <int L, class SCR>
 CB_HD void horner_thread(const HornerParams& p, int64_t pt, SCR S0, SCR S1) {
     const size_t slot = 2 * (size_t)pt;
     const size_t fslot = (p.f.S == 2) ? 0 : slot;
-    CRef a = at<L>(p.pts, 0, slot), tmp = at<L>(p.tmp, 0, slot);
+    CRef a = at<L>(p.pts, 0, (p.pts.S == 2) ? 0 : slot), tmp = at<L>(p.tmp, 0, slot);
     for (int k = 0; k < p.nder; k++) acb_zero<L>(at<L>(p.out, k, slot));
     if (p.len <= 0) return;
     acb_set<L>(at<L>(p.out, 0, slot), at<L>(p.f, p.len - 1, fslot));

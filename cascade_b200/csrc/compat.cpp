@@ -420,30 +420,26 @@ void acb_ode_solve_fuchs(acb_poly_t res, acb_ode_t ODE, slong deg, slong bits) {
 
 void analytic_continuation(acb_poly_t res, acb_ode_t ODE, acb_srcptr path, slong len, slong deg, slong bits) {
     int L = limbs_of(bits);
-    acb_t a;
-    acb_ode_t shifted;
-    acb_ode_init_blank(shifted, ODE->degree, ODE->order);
-    for (slong time = 0; time + 1 < len; time++) {
-        acb_ode_shift(shifted, ODE, path + time, bits);
-        acb_ode_solve_fuchs(res, shifted, deg, bits);
-        acb_sub(a, path + time + 1, path + time, bits);
-        // res[k] <- y^(k)(a)/k!, k < order: Horner with derivatives on the device
-        int nder = (int)ODE->order;
-        if (nder > 4) die("analytic_continuation: order > 4", -1);
-        slong flen = res->length;
-        HostArr hf(L, flen > 0 ? flen : 1, 2), hp(L, 1, 2), hout(L, nder, 2);
-        for (slong i = 0; i < flen; i++) hf.put(i, 0, res->coeffs + i);
-        hp.put(0, 0, a);
-        int rc = cb200_horner_batch_host(L, flen, 1, nder, hf.m.data(), hf.t.data(), 1, hp.m.data(), hp.t.data(),
-                                         hout.m.data(), hout.t.data(), 0);
-        if (rc) die("analytic_continuation (cb200_horner_batch_host)", rc);
-        acb_poly_zero(res);
-        acb_poly_fit_length(res, nder);
-        for (int k = 0; k < nder; k++) hout.get(k, 0, res->coeffs + k);
-        res->length = nder;
-        poly_normalise(res);
+    int ord = (int)ODE->order;
+    if (len < 2) return;
+    if (ord > 4) die("analytic_continuation: order > 4", -1);
+    slong ne = (ODE->order + 1) * (ODE->degree + 1);
+    HostArr ho(L, ne, 2), hp(L, len, 2), hy(L, ord, 2);
+    for (slong e = 0; e < ne; e++) ho.put(e, 0, ODE->polys + e);
+    for (slong t = 0; t < len; t++) hp.put(t, 0, path + t);
+    for (int k = 0; k < ord; k++) {
+        acb_t c;
+        acb_poly_get_coeff_acb(c, res, k);
+        hy.put(k, 0, c);
     }
-    acb_ode_clear(shifted);
+    int rc = cb200_continuation_host(L, ord, (int)ODE->degree, deg, 1, len, ho.m.data(), ho.t.data(), hp.m.data(),
+                                     hp.t.data(), hy.m.data(), hy.t.data(), 0);
+    if (rc) die("analytic_continuation (cb200_continuation_host)", rc);
+    acb_poly_zero(res);
+    acb_poly_fit_length(res, ord);
+    for (int k = 0; k < ord; k++) hy.get(k, 0, res->coeffs + k);
+    res->length = ord;
+    poly_normalise(res);
 }
 
 void indicial_polynomial_evaluate(acb_t result, acb_ode_t ODE, slong nu, acb_t rho, slong shift, slong prec) {

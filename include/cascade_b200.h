@@ -115,6 +115,25 @@ int cb200_horner_batch_host(int L, int64_t len, int64_t npts, int nder, const ui
                             const cb_meta *pts_meta, uint32_t *out_mant, cb_meta *out_meta,
                             int device);
 
+/* ---- analytic_continuation (reference src/fuchs_solver.c:147-163) for a batch of solutions of ONE
+ * operator along ONE path, device resident: per corner acb_ode_shift (src/acb_ode.c:124-135),
+ * acb_ode_solve_fuchs with n terms, and the re-expansion at the next corner.  Only the first `order`
+ * Taylor coefficients survive a step (the next solve overwrites the rest), so the re-expansion is
+ * a Horner evaluation with `order` normalised derivatives instead of a full acb_poly_taylor_shift.
+ * ode : (order+1)(degree+1) entries, S = 2.  path : path_len entries (corners), S = 2.
+ * y   : order entries, S = 2*batch: Taylor coefficients at path[0] in, at path[path_len-1] out.
+ * Every corner must be an ordinary point (leading coefficient nonzero there: valuation -order).
+ * corner_is_zero (HOST pointer, may be NULL): path_len flags, 1 where a corner is the exact zero ball
+ * (acb_ode_shift then skips the shift, src/acb_ode.c:128). 1 <= order <= 4. */
+size_t cb200_continuation_workspace_bytes(int L, int order, int degree, int64_t n, int64_t batch);
+int cb200_continuation_dev(int L, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
+                           const uint32_t *ode_mant, const cb_meta *ode_meta, const uint32_t *path_mant,
+                           const cb_meta *path_meta, const uint8_t *corner_is_zero, uint32_t *y_mant,
+                           cb_meta *y_meta, void *workspace, size_t workspace_bytes, void *stream);
+int cb200_continuation_host(int L, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
+                            const uint32_t *ode_mant, const cb_meta *ode_meta, const uint32_t *path_mant,
+                            const cb_meta *path_meta, uint32_t *y_mant, cb_meta *y_meta, int device);
+
 /* ---- elementwise ball operations over n complex balls (1 entry, S = 2*n each); k: n integers
  * for the *_SI ops (device pointer in _dev, may be NULL otherwise); y ignored for INV/_SI. */
 int cb200_ew_dev(int op, int L, int64_t n, uint32_t *z_mant, cb_meta *z_meta, const uint32_t *x_mant,

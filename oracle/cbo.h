@@ -139,6 +139,9 @@ int cbo_ode_solves_flat(int L, int order, int degree, const uint32_t *ode_m, con
                         const uint32_t *res_m, const int32_t *res_t, int64_t len, int64_t deg);
 int cbo_example_flat(int which, int L, uint64_t n, const uint32_t *par_m, const int32_t *par_t,
                      uint32_t *out_m, int32_t *out_t);
+int cbo_continuation_flat(int L, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
+                          const uint32_t *ode_m, const int32_t *ode_t, const uint32_t *path_m,
+                          const int32_t *path_t, uint32_t *y_m, int32_t *y_t);
 const char *cbo_backend(void); /* "gmp-mpn" or "plain-c" */
 
 #ifdef __cplusplus

@@ -48,6 +48,8 @@ def lib(plain: bool = False) -> C.CDLL:
     L.cbo_ode_shift_flat.argtypes = [C.c_int, C.c_int, C.c_int, _u32p, _i32p, _u32p, _i32p, _u32p, _i32p]
     L.cbo_ode_solves_flat.argtypes = [C.c_int, C.c_int, C.c_int, _u32p, _i32p, _u32p, _i32p,
                                       C.c_int64, C.c_int64]
+    L.cbo_continuation_flat.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, _u32p, _i32p,
+                                        _u32p, _i32p, _u32p, _i32p]
     L.cbo_example_flat.argtypes = [C.c_int, C.c_int, C.c_uint64, _u32p, _i32p, _u32p, _i32p]
     _LIBS[name] = L
     return L
@@ -133,3 +135,13 @@ def example(which: str, L: int, n: int = 0, params: Balls | None = None, plain: 
     rc = lib(plain).cbo_example_flat(code, L, n, params.mant, params.meta, out.mant, out.meta)
     assert rc == 0
     return out
+
+
+def continuation(order: int, degree: int, n: int, ode: Balls, path: Balls, y0: Balls, batch: int,
+                 plain: bool = False) -> Balls:
+    """analytic_continuation for ``batch`` solutions: y0 is [batch][order]; returns the same shape."""
+    y = y0.copy()
+    rc = lib(plain).cbo_continuation_flat(ode.L, order, degree, n, batch, path.n_slots // 2, ode.mant, ode.meta,
+                                          path.mant, path.meta, y.mant, y.meta)
+    assert rc == 0
+    return y

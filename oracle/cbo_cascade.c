@@ -406,6 +406,38 @@ int cbo_ode_solves_flat(int L, int order, int degree, const uint32_t *ode_m, con
     return ok;
 }
 
+/* analytic_continuation (reference src/fuchs_solver.c:147-163) for `batch` solutions of one operator
+ * along one path.  y: [batch][order] Taylor coefficients at path[0] in, at the last corner out.
+ * Per corner: acb_ode_shift, acb_ode_solve_fuchs (n terms), then the first `order` coefficients of
+ * the series re-expanded at the next corner, by Horner evaluation with derivatives (SURVEY.md 3.2:
+ * the rest of acb_poly_taylor_shift's output is overwritten by the next solve before it is read). */
+int cbo_continuation_flat(int L, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
+                          const uint32_t *ode_m, const int32_t *ode_t, const uint32_t *path_m,
+                          const int32_t *path_t, uint32_t *y_m, int32_t *y_t) {
+    cbo_ode *o = load_ode(L, order, degree, ode_m, ode_t, 0);
+    cbo_ode *sh = cbo_ode_new(degree, order);
+    cbo_acb *res = (cbo_acb *)malloc(sizeof(cbo_acb) * (n + 1));
+    int rc = 0;
+    for (int64_t t = 0; t + 1 < path_len && rc == 0; t++) {
+        cbo_acb c0, c1, a, out[8];
+        load_acb(&c0, path_m, path_t, t, L);
+        load_acb(&c1, path_m, path_t, t + 1, L);
+        cbo_ode_shift(sh, o, &c0, L);
+        cbo_acb_sub(&a, &c1, &c0, L);
+        for (int64_t s = 0; s < batch; s++) {
+            for (int k = 0; k < order; k++) load_acb(res + k, y_m, y_t, s * order + k, L);
+            sh->valuation = -order; /* ordinary point by contract (as the device path) */
+            if (cbo_solve_fuchs(res, sh, n, L) != 0) rc = -1;
+            cbo_poly_evaluate_horner(out, res, n + 1, &a, order, L);
+            for (int k = 0; k < order; k++) store_acb(y_m, y_t, s * order + k, out + k, L);
+        }
+    }
+    free(res);
+    cbo_ode_free(o);
+    cbo_ode_free(sh);
+    return rc;
+}
+
 /* which: 0 legendre(n), 1 bessel(par[0]) (par[0] is overwritten with nu^2), 2 hypgeom(par[0..2]) */
 int cbo_example_flat(int which, int L, uint64_t n, const uint32_t *par_m, const int32_t *par_t,
                      uint32_t *out_m, int32_t *out_t) {

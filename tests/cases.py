@@ -280,6 +280,30 @@ def case_frobenius_singleton(oracle, drv, L: int, seed: int, trials: int = 3):
         assert oracle.ode_solves(order, degree, ode, shifted, n - 1)
 
 
+def case_continuation(oracle, drv, L: int, seed: int, steps: int = 5, n: int = 30, batch: int = 3):
+    """BASELINE configs[4]'s driver: analytic_continuation (reference src/fuchs_solver.c:147-163) of
+    `batch` solutions of the hypergeometric operator along a polygon that avoids 0 and 1; includes
+    an exact-zero corner (acb_ode_shift then skips the shift, src/acb_ode.c:128)."""
+    rng = np.random.default_rng(seed)
+    par = random_balls(rng, 6, L, -1, 1, "zero")
+    ode = oracle.example("hypgeom", L, 0, par)
+    th = np.linspace(0.3, 2.0, steps + 1)
+    corners = [(F(float(0.5 + 0.25 * np.cos(t))).limit_denominator(2**20), F(float(0.3 * np.sin(t))).limit_denominator(2**20))
+               for t in th]
+    path = from_complex(corners, L)
+    y0 = random_balls(rng, batch * 2 * 2, L, -1, 0, "zero")
+    yo = oracle.continuation(2, 2, n, ode, path, y0, batch)
+    ys = api.analytic_continuation_batch(ode, path, y0, 2, 2, n, batch, driver=drv)
+    assert_same(yo, ys, f"analytic continuation L={L}")
+    assert not (ys.meta[:, 1] & FLAG_NAN).any()
+    # Legendre operator from the regular point 0 (an exact-zero corner) to 1/4
+    leg = oracle.example("legendre", L, 3)
+    path0 = from_complex([0, F(1, 8), F(1, 4)], L)
+    yo = oracle.continuation(2, 2, n, leg, path0, y0, batch)
+    ys = api.analytic_continuation_batch(leg, path0, y0, 2, 2, n, batch, driver=drv)
+    assert_same(yo, ys, f"analytic continuation from the origin L={L}")
+
+
 def case_horner(oracle, drv, L: int, seed: int, length: int = 40, npts: int = 9):
     rng = np.random.default_rng(seed)
     f = random_balls(rng, 2 * length, L, -3, 3, "ulp")

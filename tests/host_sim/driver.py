@@ -33,6 +33,7 @@ def lib():
         L = C.CDLL(_SO)
         L.cbsim_fuchs_batch.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p]
         L.cbsim_fuchs_intop_batch.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS"), C.c_int, _u32p, _i32p]
+        L.cbsim_continuation.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, _u32p, _i32p, _u32p, _i32p, _u32p, _i32p]
         L.cbsim_frobenius1_batch.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int, _u32p, _i32p]
         L.cbsim_horner_batch.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int, _u32p, _i32p, C.c_int, _u32p, _i32p, _u32p, _i32p]
         L.cbsim_ew.argtypes = [C.c_int, C.c_int, C.c_int64, _u32p, _i32p, _u32p, _i32p, _vp, _vp, _vp]
@@ -46,6 +47,9 @@ class SimDriver:
 
     def fuchs_intop(self, L, order, degree, valuation, n, batch, ode_int, shared, res_m, res_t):
         return lib().cbsim_fuchs_intop_batch(L, order, degree, valuation, n, batch, ode_int, int(shared), res_m, res_t)
+
+    def continuation(self, L, order, degree, n, batch, path_len, ode_m, ode_t, path_m, path_t, y_m, y_t):
+        return lib().cbsim_continuation(L, order, degree, n, batch, path_len, ode_m, ode_t, path_m, path_t, y_m, y_t)
 
     def frobenius1(self, L, order, degree, valuation, n, batch, ode_m, ode_t, shared, rho_m, rho_t,
                    shared_rho, res_m, res_t):

@@ -153,4 +153,50 @@ int cbsim_ew(int op, int L_, int64_t n, uint32_t* z_mant, cb_meta* z_meta, const
     return 0;
 }
 
+
+int cbsim_continuation(int L_, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
+                       const uint32_t* ode_mant, const cb_meta* ode_meta, const uint32_t* path_mant,
+                       const cb_meta* path_meta, uint32_t* y_mant, cb_meta* y_meta) {
+    // same sequence of operations as cb200_continuation_dev, on host memory
+    const int64_t ne = (int64_t)(order + 1) * (degree + 1), S = 2 * batch;
+    std::vector<uint32_t> shm((size_t)ne * L_ * 2), serm((size_t)(n + 1) * L_ * S), tbm((size_t)3 * L_ * 2);
+    std::vector<cb_meta> sht((size_t)ne * 2), sert((size_t)(n + 1) * S), tbt(6);
+    auto bm = [&](std::vector<uint32_t>& v, int64_t e) { return v.data() + (size_t)e * L_ * 2; };
+    auto bt = [&](std::vector<cb_meta>& v, int64_t e) { return v.data() + (size_t)e * 2; };
+    for (int64_t t = 0; t + 1 < path_len; t++) {
+        memcpy(shm.data(), ode_mant, shm.size() * 4);
+        memcpy(sht.data(), ode_meta, sht.size() * sizeof(cb_meta));
+        const uint32_t* am = path_mant + (size_t)t * L_ * 2;
+        const cb_meta* at_ = path_meta + (size_t)t * 2;
+        bool zero = (at_[0].flags & CB_FLAG_ZERO) && at_[0].rman == 0 && (at_[1].flags & CB_FLAG_ZERO) && at_[1].rman == 0;
+        if (degree > 0 && !zero) {
+            int D1 = degree + 1;
+            for (int row = 0; row <= order; row++)
+                for (int i = D1 - 2; i >= 0; i--)
+                    for (int j = i; j <= D1 - 2; j++) {
+                        int64_t ej = (int64_t)row * D1 + j;
+                        cbsim_ew(CB200_OP_MUL, L_, 1, bm(tbm, 1), bt(tbt, 1), bm(shm, ej + 1), bt(sht, ej + 1), am, at_, nullptr);
+                        cbsim_ew(CB200_OP_ADD, L_, 1, bm(tbm, 2), bt(tbt, 2), bm(shm, ej), bt(sht, ej), bm(tbm, 1), bt(tbt, 1), nullptr);
+                        memcpy(bm(shm, ej), bm(tbm, 2), (size_t)L_ * 2 * 4);
+                        memcpy(bt(sht, ej), bt(tbt, 2), 2 * sizeof(cb_meta));
+                    }
+        }
+        memcpy(serm.data(), y_mant, (size_t)order * L_ * S * 4);
+        memcpy(sert.data(), y_meta, (size_t)order * S * sizeof(cb_meta));
+        int rc = cbsim_fuchs_batch(L_, order, degree, -order, n, batch, shm.data(), sht.data(), 1, serm.data(), sert.data());
+        if (rc) return rc;
+        cbsim_ew(CB200_OP_SUB, L_, 1, bm(tbm, 0), bt(tbt, 0), path_mant + (size_t)(t + 1) * L_ * 2, path_meta + (size_t)(t + 1) * 2,
+                 am, at_, nullptr);
+        HornerParams hp;
+        hp.nder = order; hp.len = n + 1; hp.npts = batch;
+        hp.f = CArr{serm.data(), (Meta*)sert.data(), (size_t)S};
+        hp.pts = CArr{bm(tbm, 0), (Meta*)bt(tbt, 0), (size_t)2};
+        hp.out = CArr{y_mant, (Meta*)y_meta, (size_t)S};
+        Tmp tmp;
+        hp.tmp = tmp.arr(L_, 1, S);
+        SIM_DISPATCH(L_, run<L>(batch, [&](int64_t i, Scratch<1> a, Scratch<1> b) { horner_thread<L>(hp, i, a, b); }));
+    }
+    return 0;
+}
+
 }  // extern "C"

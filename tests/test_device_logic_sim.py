@@ -55,3 +55,8 @@ def test_frobenius_singleton(oracle, sim_driver):
 @pytest.mark.parametrize("L", [4, 64])
 def test_horner(oracle, sim_driver, L):
     cases.case_horner(oracle, sim_driver, L, seed=13)
+
+
+@pytest.mark.parametrize("L", [4, 32])
+def test_continuation(oracle, sim_driver, L):
+    cases.case_continuation(oracle, sim_driver, L, seed=3 + L)

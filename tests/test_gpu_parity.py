@@ -57,3 +57,8 @@ def test_frobenius_singleton(oracle, gpu_driver):
 @pytest.mark.parametrize("L", [4, 32, 64])
 def test_horner(oracle, gpu_driver, L):
     cases.case_horner(oracle, gpu_driver, L, seed=13, length=60, npts=333)
+
+
+@pytest.mark.parametrize("L", [32, 64])
+def test_continuation(oracle, gpu_driver, L):
+    cases.case_continuation(oracle, gpu_driver, L, seed=23 + L, steps=6, n=40, batch=5)
