@@ -812,19 +812,19 @@ CB_NOINLINE Meta arb_fdot2_trunc(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2,
     uint32_t r[PW];
 #pragma unroll 1
     for (int term = 0; term < 2; term++) {  // a loop, so that the product code exists once
-        if (term == 1) {
-#pragma unroll
-            for (int k = 0; k < PW; k++) S0.st(k, r[k]);
-        }
         if (term ? skipB : skipA) {
 #pragma unroll
             for (int k = 0; k < PW; k++) r[k] = 0u;
-            continue;
+        } else {
+            uint32_t a[L], b[L];
+            load_limbs<L>(a, term ? xB : xA);
+            load_limbs<L>(b, term ? yB : yA);
+            mul_high<L, K>(r, a, b);
         }
-        uint32_t a[L], b[L];
-        load_limbs<L>(a, term ? xB : xA);
-        load_limbs<L>(b, term ? yB : yA);
-        mul_high<L, K>(r, a, b);
+        if (term == 0) {  // park product A; nothing of r is live across the back edge
+#pragma unroll
+            for (int k = 0; k < PW; k++) S0.st(k, r[k]);
+        }
     }
     bool done = false, neg = false;
     Rounded rr;
@@ -843,6 +843,8 @@ CB_NOINLINE Meta arb_fdot2_trunc(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2,
         int sA = (int)(d & 31);
         bool sub = (nA != nB) && !zA;
         // word k (k in [K, 2L)) of the product B, and of the product A moved down by m words
+        // zero-flagged operands are masked explicitly, so a non-canonical zero (flag set, stale
+        // limbs) behaves like the oracle's
         auto wB = [&](int k) -> uint32_t { return r[k - K]; };
         auto wA = [&](int k) -> uint32_t {
             int i = k + m - K;

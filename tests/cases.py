@@ -154,6 +154,11 @@ def case_fuchs_shared_adversarial(oracle, drv, L: int, seed: int, trials: int = 
         init, _ = adversarial_pair(rng, L, batch * order)
         init.meta[:, 0] += rng.choice([0, 0, 0, 33, -64, 150, -300], size=init.n_slots).astype(np.int32)
         init.meta[(init.meta[:, 1] & FLAG_ZERO) != 0, 0] = 0
+        # non-canonical zeros (flag set, stale limbs) must behave as zeros, as they do in the oracle
+        init.mant[5] = 0xFFFFFFFF
+        init.meta[5] = (0, FLAG_ZERO, 0, 0)
+        ode.mant[3] = 0x12345678
+        ode.meta[3] = (0, FLAG_ZERO, 0, 0)
         n = order + 12
         rc, ro = oracle.fuchs_batch(order, degree, n, ode, init, batch, True)
         assert rc == 0
