@@ -200,12 +200,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
     stop, samples = threading.Event(), []
     th = threading.Thread(target=clocks_sampler, args=(stop, samples, local_rank), daemon=True)
-    th.start()
+    for i in range(args.warmup):
+        if i == args.warmup - 1:
+            th.start()  # sampler start-up (nvidia-smi spawn) happens during the last warm-up step
+        step_device()
+    if not th.is_alive():
+        th.start()
+    barrier()
+    samples.clear()
     launches0 = lib.cb200_kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -242,7 +246,17 @@ def main():
     # ---- end to end: host buffers in, host buffers out, tile by tile, copies inside the timing
     e2e = None
     if not args.no_e2e:
+        # pinned ring of two result tiles per rank; keep all ranks of the box within a quarter of
+        # the free host memory (a real caller would own a full-size result buffer)
+        per_inst = (n + 1) * 2 * (L * 4 + 16)
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = 64 << 30
         tile = min(batch, 16384)
+        while tile > 1024 and 2 * tile * per_inst * world > avail // 4:
+            tile //= 2
         ntiles = (batch + tile - 1) // tile
         St = 2 * tile
         h_init_m = torch.from_numpy(init_m.view(np.int32)).pin_memory()
