@@ -300,7 +300,7 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * coeffs_per_gpu / float(tt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(h2d * ntiles), "d2h_bytes_per_step": int(d2h * ntiles),
+               "h2d_bytes_per_step": int(h2d * ntiles) * world, "d2h_bytes_per_step": int(d2h * ntiles) * world,
                "how": f"{ntiles} tiles of {tile} instances, 2 streams, pinned host buffers, result series copied back"}
 
     if rank != 0:
