@@ -16,6 +16,7 @@ from cascade_b200.format import instance_major_to_entry_major, pack_entries, ran
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=float, default=1.0)
+ap.add_argument("--continuation", action="store_true", help="also time the (slow, sequential) continuation leg")
 args = ap.parse_args()
 lib = _lib.lib()
 dev = torch.device("cuda:0")
@@ -113,26 +114,27 @@ ms = timed(lambda: lib.cb200_horner_batch_dev(L, length, npts, 1, p(f_m), p(f_t)
 steps = npts * (length - 1)
 out.append({"config": 5, "what": f"Horner evaluation of a {length}-term series at {npts} points, 2048 bits", "ms": ms,
             "horner_steps_per_s": steps / ms * 1e3, "T_limb_MAC_per_s_4L2": steps * 4 * L * L / ms * 1e3 / 1e12})
-# ---- config 5, continuation leg: 64-corner path, ~3504 terms per step, 2048 bits, `order` solutions
-L, n, steps = 64, 3504, max(4, int(64 * min(1.0, args.scale * 4)))
-rng = np.random.default_rng(5)
-par = random_balls(rng, 6, L, -1, 1, "zero")
-ode = api.acb_ode_hypgeom_batch(par[0:2], par[2:4], par[4:6])
-from fractions import Fraction as F
-from cascade_b200.format import from_complex
-th = np.linspace(0.0, 2 * np.pi, steps + 1)
-path = from_complex([(F(float(0.5 + 0.25 * np.cos(t))).limit_denominator(2**30), F(float(0.25 * np.sin(t))).limit_denominator(2**30)) for t in th], L)
-y0 = from_complex([1, 0, 0, 1], L)
-om, ot = api._ode_to_device(ode, 2, 2, 2, True)
-pm, pt = pack_entries(path, steps + 1, 2)
-ym, yt = pack_entries(instance_major_to_entry_major(y0, 2, 2), 2, 4)
-d_om, d_ot = dev_arr(om, ot)
-d_pm, d_pt = dev_arr(pm, pt)
-d_ym, d_yt = dev_arr(ym, yt)
-wsb = lib.cb200_continuation_workspace_bytes(L, 2, 2, n, 2)
-ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-ms = timed(lambda: lib.cb200_continuation_dev(L, 2, 2, n, 2, steps + 1, p(d_om), p(d_ot), p(d_pm), p(d_pt), None, p(d_ym), p(d_yt), p(ws), wsb, None), reps=1)
-out.append({"config": 5, "what": f"analytic continuation, {steps}-step path, {n} terms per step, 2048 bits, 2 solutions (sequential: latency bound)",
-            "ms": ms, "ball_coeffs_per_s": 2 * steps * (n - 1) / ms * 1e3, "ms_per_step": ms / steps})
+if args.continuation:
+    # ---- config 5, continuation leg (slow: sequential; run with --continuation): 64-corner path, ~3504 terms per step, 2048 bits, `order` solutions
+    L, n, steps = 64, 3504, max(4, int(64 * min(1.0, args.scale * 4)))
+    rng = np.random.default_rng(5)
+    par = random_balls(rng, 6, L, -1, 1, "zero")
+    ode = api.acb_ode_hypgeom_batch(par[0:2], par[2:4], par[4:6])
+    from fractions import Fraction as F
+    from cascade_b200.format import from_complex
+    th = np.linspace(0.0, 2 * np.pi, steps + 1)
+    path = from_complex([(F(float(0.5 + 0.25 * np.cos(t))).limit_denominator(2**30), F(float(0.25 * np.sin(t))).limit_denominator(2**30)) for t in th], L)
+    y0 = from_complex([1, 0, 0, 1], L)
+    om, ot = api._ode_to_device(ode, 2, 2, 2, True)
+    pm, pt = pack_entries(path, steps + 1, 2)
+    ym, yt = pack_entries(instance_major_to_entry_major(y0, 2, 2), 2, 4)
+    d_om, d_ot = dev_arr(om, ot)
+    d_pm, d_pt = dev_arr(pm, pt)
+    d_ym, d_yt = dev_arr(ym, yt)
+    wsb = lib.cb200_continuation_workspace_bytes(L, 2, 2, n, 2)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: lib.cb200_continuation_dev(L, 2, 2, n, 2, steps + 1, p(d_om), p(d_ot), p(d_pm), p(d_pt), None, p(d_ym), p(d_yt), p(ws), wsb, None), reps=1)
+    out.append({"config": 5, "what": f"analytic continuation, {steps}-step path, {n} terms per step, 2048 bits, 2 solutions (sequential: latency bound)",
+                "ms": ms, "ball_coeffs_per_s": 2 * steps * (n - 1) / ms * 1e3, "ms_per_step": ms / steps})
 for o in out:
     print(json.dumps(o))
