@@ -447,13 +447,12 @@ CB_HD void product(SCR P, XS x, YS y) {
                 for (int j = 0; j < 32; j++) b[j] = y.ld(32 * bj + j);
                 mul_full<32>(r, a, b);
                 int off = 32 * (bi + bj);
-                uint32_t c = 0u;
+                uint32_t o[64];
 #pragma unroll
-                for (int k = 0; k < 64; k++) {
-                    uint64_t t = (uint64_t)P.ld(off + k) + r[k] + c;
-                    P.st(off + k, (uint32_t)t);
-                    c = (uint32_t)(t >> 32);
-                }
+                for (int k = 0; k < 64; k++) o[k] = P.ld(off + k);
+                uint32_t c = add_chain<64>(o, r);
+#pragma unroll
+                for (int k = 0; k < 64; k++) P.st(off + k, o[k]);
 #pragma unroll 1
                 for (int k = off + 64; c != 0u && k < 2 * L; k++) {
                     uint64_t t = (uint64_t)P.ld(k) + c;

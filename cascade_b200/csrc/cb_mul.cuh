@@ -65,6 +65,19 @@ __device__ __forceinline__ void mul_full(uint32_t (&r)[2 * L], const uint32_t (&
 }
 
 
+// o[0..N) += r[0..N): one add.cc/addc.cc chain; returns the carry out.  (Written in PTX on purpose:
+// a C-level 64-bit carry chain right after mul_full makes ptxas interleave it with the product's
+// chains and spill their carry predicates -- 4x the instructions, measured.)
+template <int N>
+__device__ __forceinline__ uint32_t add_chain(uint32_t (&o)[N], const uint32_t (&r)[N]) {
+    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(o[0]) : "r"(r[0]));
+#pragma unroll
+    for (int k = 1; k < N; k++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(o[k]) : "r"(r[k]));
+    uint32_t c;
+    asm volatile("addc.u32 %0, 0, 0;" : "=r"(c));
+    return c;
+}
+
 // ---------------------------------------------------------------- truncated ("high") product
 // r[0 .. 2L-K) = ( sum over limb products with i + j >= K of a[j] b[i] 2^(32 (i+j)) ) >> 32 K.
 // Whole limb products whose low word falls in a column below K are dropped (including the part of
@@ -137,6 +150,17 @@ inline void mul_full(uint32_t (&r)[2 * L], const uint32_t (&a)[L], const uint32_
     }
 }
 
+
+template <int N>
+inline uint32_t add_chain(uint32_t (&o)[N], const uint32_t (&r)[N]) {
+    uint32_t c = 0;
+    for (int k = 0; k < N; k++) {
+        uint64_t t = (uint64_t)o[k] + r[k] + c;
+        o[k] = (uint32_t)t;
+        c = (uint32_t)(t >> 32);
+    }
+    return c;
+}
 
 template <int L, int K>
 inline void mul_high(uint32_t (&r)[2 * L - K], const uint32_t (&a)[L], const uint32_t (&b)[L]) {
