@@ -12,7 +12,7 @@ template <int L> struct Cfg;
 template <> struct Cfg<4> { static constexpr int TPB = 128; };
 template <> struct Cfg<32> { static constexpr int TPB = 224; };
 template <> struct Cfg<64> { static constexpr int TPB = 192; };
-template <> struct Cfg<128> { static constexpr int TPB = 96; };
+template <> struct Cfg<128> { static constexpr int TPB = 112; };
 
 // threads per block of the shared-operator recurrence kernel (two product columns + three
 // accumulator columns per thread)

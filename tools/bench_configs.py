@@ -16,6 +16,7 @@ from cascade_b200.format import instance_major_to_entry_major, pack_entries, ran
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=float, default=1.0)
+ap.add_argument("--only", type=int, default=0, help="run only this config (3, 4 or 5)")
 ap.add_argument("--continuation", action="store_true", help="also time the (slow, sequential) continuation leg")
 args = ap.parse_args()
 lib = _lib.lib()
@@ -52,68 +53,80 @@ def timed(fn, reps=2):
 
 
 out = []
-# ---- config 3: Frobenius, hypergeometric sweep, 4096 bits, per-instance (a, b, c)
-L, n = 128, 256
-batch = max(64, int(16384 * args.scale))
-rng = np.random.default_rng(3)
-small = 64
-par = [random_balls(rng, small * 2, L, -1, 1, "zero") for _ in range(3)]
-odes = api.acb_ode_hypgeom_batch(*par)
-om, ot = pack_entries(instance_major_to_entry_major(odes, small, 9), 9, 2 * small)
-reps = batch // small
-d_om = torch.from_numpy(np.tile(om.view(np.int32), (1, 1, reps))).to(dev)
-d_ot = torch.from_numpy(np.tile(ot, (1, reps, 1))).to(dev)
-d_rm, d_rt = torch.zeros((1, L, 2 * batch), dtype=torch.int32, device=dev), torch.zeros((1, 2 * batch, 4), dtype=torch.int32, device=dev)
-d_rt[:, :, 1] = 2  # rho = 0
-d_res_m = torch.empty((n + 1, L, 2 * batch), dtype=torch.int32, device=dev)
-d_res_t = torch.empty((n + 1, 2 * batch, 4), dtype=torch.int32, device=dev)
-wsb = lib.cb200_frobenius_workspace_bytes(L, batch)
-ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-ms = timed(lambda: lib.cb200_frobenius1_batch_dev(L, 2, 2, -1, n, batch, p(d_om), p(d_ot), 0, p(d_rm), p(d_rt), 0,
-                                                  p(d_res_m), p(d_res_t), p(ws), wsb, None))
-coeffs = batch * n
-out.append({"config": 3, "what": f"hypgeom Frobenius M=1, 4096 bits, {batch} (a,b,c) triples, {n} terms", "ms": ms,
-            "ball_coeffs_per_s": coeffs / ms * 1e3, "T_limb_MAC_per_s_36L2": coeffs * 36 * L * L / ms * 1e3 / 1e12})
-del d_res_m, d_res_t, ws
-torch.cuda.empty_cache()
+def config3():
+    # ---- config 3: Frobenius, hypergeometric sweep, 4096 bits, per-instance (a, b, c)
+    L, n = 128, 256
+    batch = max(64, int(16384 * args.scale))
+    rng = np.random.default_rng(3)
+    small = 64
+    par = [random_balls(rng, small * 2, L, -1, 1, "zero") for _ in range(3)]
+    odes = api.acb_ode_hypgeom_batch(*par)
+    om, ot = pack_entries(instance_major_to_entry_major(odes, small, 9), 9, 2 * small)
+    reps = batch // small
+    d_om = torch.from_numpy(np.tile(om.view(np.int32), (1, 1, reps))).to(dev)
+    d_ot = torch.from_numpy(np.tile(ot, (1, reps, 1))).to(dev)
+    d_rm, d_rt = torch.zeros((1, L, 2 * batch), dtype=torch.int32, device=dev), torch.zeros((1, 2 * batch, 4), dtype=torch.int32, device=dev)
+    d_rt[:, :, 1] = 2  # rho = 0
+    d_res_m = torch.empty((n + 1, L, 2 * batch), dtype=torch.int32, device=dev)
+    d_res_t = torch.empty((n + 1, 2 * batch, 4), dtype=torch.int32, device=dev)
+    wsb = lib.cb200_frobenius_workspace_bytes(L, batch)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: lib.cb200_frobenius1_batch_dev(L, 2, 2, -1, n, batch, p(d_om), p(d_ot), 0, p(d_rm), p(d_rt), 0,
+                                                      p(d_res_m), p(d_res_t), p(ws), wsb, None))
+    coeffs = batch * n
+    out.append({"config": 3, "what": f"hypgeom Frobenius M=1, 4096 bits, {batch} (a,b,c) triples, {n} terms", "ms": ms,
+                "ball_coeffs_per_s": coeffs / ms * 1e3, "T_limb_MAC_per_s_36L2": coeffs * 36 * L * L / ms * 1e3 / 1e12})
+    del d_res_m, d_res_t, ws
+    torch.cuda.empty_cache()
 
-# ---- config 4: Legendre sweep, per-instance integer operators, real data (integer-operator kernel)
-L, n = 32, 1000
-batch = max(1024, int(2**20 * args.scale))
-ns = np.arange(batch, dtype=np.int64)
-ode_int = np.zeros((9, batch), np.int64)
-ode_int[0] = ns * (ns + 1)
-ode_int[4] = -2
-ode_int[6] = 1
-ode_int[8] = -1
-d_oi = torch.from_numpy(ode_int).to(dev)
-d_res_m = torch.zeros((n + 1, L, 2 * batch), dtype=torch.int32, device=dev)
-d_res_t = torch.zeros((n + 1, 2 * batch, 4), dtype=torch.int32, device=dev)
-d_res_t[:, :, 1] = 2
-d_res_m[0:2, L - 1, 0::2] = -(2**31)  # c0 = c1 = 1
-d_res_t[0:2, 0::2, 0] = 1
-d_res_t[0:2, 0::2, 1] = 0
-ms = timed(lambda: lib.cb200_fuchs_intop_batch_dev(L, 2, 2, -2, n, batch, p(d_oi), 0, p(d_res_m), p(d_res_t), None), reps=2)
-coeffs = batch * (n - 1)
-out.append({"config": 4, "what": f"Legendre sweep n=0..{batch - 1}, 1024 bits, {n} terms, integer-operator kernel",
-            "ms": ms, "ball_coeffs_per_s": coeffs / ms * 1e3, "GB_per_s_written": coeffs * 288 / ms * 1e3 / 1e9})
-del d_res_m, d_res_t
-torch.cuda.empty_cache()
 
-# ---- config 5: Horner at many points, 2048 bits, one 3504-term series
-L, length = 64, 3504
-npts = max(1024, int(10**6 * args.scale))
-f_m, f_t = rand_dev(length, L, 2, 5)
-pts_m, pts_t = rand_dev(1, L, 2 * npts, 6)
-pts_t[:, :, 0] = -2  # |x| < 1/4
-o_m = torch.empty((1, L, 2 * npts), dtype=torch.int32, device=dev)
-o_t = torch.empty((1, 2 * npts, 4), dtype=torch.int32, device=dev)
-wsb = lib.cb200_horner_workspace_bytes(L, npts)
-ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-ms = timed(lambda: lib.cb200_horner_batch_dev(L, length, npts, 1, p(f_m), p(f_t), 1, p(pts_m), p(pts_t), p(o_m), p(o_t), p(ws), wsb, None), reps=1)
-steps = npts * (length - 1)
-out.append({"config": 5, "what": f"Horner evaluation of a {length}-term series at {npts} points, 2048 bits", "ms": ms,
-            "horner_steps_per_s": steps / ms * 1e3, "T_limb_MAC_per_s_4L2": steps * 4 * L * L / ms * 1e3 / 1e12})
+def config4():
+    # ---- config 4: Legendre sweep, per-instance integer operators, real data (integer-operator kernel)
+    L, n = 32, 1000
+    batch = max(1024, int(2**20 * args.scale))
+    ns = np.arange(batch, dtype=np.int64)
+    ode_int = np.zeros((9, batch), np.int64)
+    ode_int[0] = ns * (ns + 1)
+    ode_int[4] = -2
+    ode_int[6] = 1
+    ode_int[8] = -1
+    d_oi = torch.from_numpy(ode_int).to(dev)
+    d_res_m = torch.zeros((n + 1, L, 2 * batch), dtype=torch.int32, device=dev)
+    d_res_t = torch.zeros((n + 1, 2 * batch, 4), dtype=torch.int32, device=dev)
+    d_res_t[:, :, 1] = 2
+    d_res_m[0:2, L - 1, 0::2] = -(2**31)  # c0 = c1 = 1
+    d_res_t[0:2, 0::2, 0] = 1
+    d_res_t[0:2, 0::2, 1] = 0
+    ms = timed(lambda: lib.cb200_fuchs_intop_batch_dev(L, 2, 2, -2, n, batch, p(d_oi), 0, p(d_res_m), p(d_res_t), None), reps=2)
+    coeffs = batch * (n - 1)
+    out.append({"config": 4, "what": f"Legendre sweep n=0..{batch - 1}, 1024 bits, {n} terms, integer-operator kernel",
+                "ms": ms, "ball_coeffs_per_s": coeffs / ms * 1e3, "GB_per_s_written": coeffs * 288 / ms * 1e3 / 1e9})
+    del d_res_m, d_res_t
+    torch.cuda.empty_cache()
+
+
+def config5():
+    # ---- config 5: Horner at many points, 2048 bits, one 3504-term series
+    L, length = 64, 3504
+    npts = max(1024, int(10**6 * args.scale))
+    f_m, f_t = rand_dev(length, L, 2, 5)
+    pts_m, pts_t = rand_dev(1, L, 2 * npts, 6)
+    pts_t[:, :, 0] = -2  # |x| < 1/4
+    o_m = torch.empty((1, L, 2 * npts), dtype=torch.int32, device=dev)
+    o_t = torch.empty((1, 2 * npts, 4), dtype=torch.int32, device=dev)
+    wsb = lib.cb200_horner_workspace_bytes(L, npts)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: lib.cb200_horner_batch_dev(L, length, npts, 1, p(f_m), p(f_t), 1, p(pts_m), p(pts_t), p(o_m), p(o_t), p(ws), wsb, None), reps=1)
+    steps = npts * (length - 1)
+    out.append({"config": 5, "what": f"Horner evaluation of a {length}-term series at {npts} points, 2048 bits", "ms": ms,
+                "horner_steps_per_s": steps / ms * 1e3, "T_limb_MAC_per_s_4L2": steps * 4 * L * L / ms * 1e3 / 1e12})
+
+if args.only in (0, 3):
+    config3()
+if args.only in (0, 4):
+    config4()
+if args.only in (0, 5):
+    config5()
 if args.continuation:
     # ---- config 5, continuation leg (slow: sequential; run with --continuation): 64-corner path, ~3504 terms per step, 2048 bits, `order` solutions
     L, n, steps = 64, 3504, max(4, int(64 * min(1.0, args.scale * 4)))
