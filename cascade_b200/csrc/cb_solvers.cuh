@@ -60,6 +60,24 @@ CB_HD Opd dyn(const OpdS& o) { return Opd{o.r.dyn(), o.t}; }
 CB_HD WRef wre(const CRef& x) { return WRef{x.m, x.stride}; }
 CB_HD WRef wim(const CRef& x) { return WRef{x.m + 1, x.stride}; }
 
+// does this precision use truncated products (with the exact path as per-lane fallback)?
+template <int L>
+constexpr bool use_trunc() { return L >= 16 && L <= 32; }
+
+// fused dot product of the general kernels: truncated products first (S0 parks the first one),
+// the exact shared-memory version when the guard-bit proof fails
+template <int L, class SCR>
+CB_HD Meta fdot2_auto(WRef dst, Opd x1, Opd y1, Opd x2, Opd y2, bool neg2, SCR S0, SCR S1) {
+    if constexpr (use_trunc<L>()) {
+        bool ok;
+        Meta t = arb_fdot2_trunc<L>(dst, x1, y1, x2, y2, neg2, S0, &ok);
+        if (!ok) t = arb_fdot2<L>(dst, x1, y1, x2, y2, neg2, S0, S1);
+        return t;
+    } else {
+        return arb_fdot2<L>(dst, x1, y1, x2, y2, neg2, S0, S1);
+    }
+}
+
 template <int L>
 CB_HD void acb_set(const CRef& z, const CRef& x) {
 #pragma unroll 8
@@ -91,8 +109,8 @@ CB_HD void acb_one(const CRef& z) {
 template <int L, class SCR>
 CB_HD void acb_mul(const CRef& z, const CRef& x, const CRef& y, SCR S0, SCR S1) {
     Opd a = re_of(x), b = im_of(x), c = re_of(y), d = im_of(y);
-    Meta tr = arb_fdot2<L>(wre(z), a, c, b, d, true, S0, S1);
-    Meta ti = arb_fdot2<L>(wim(z), a, d, b, c, false, S0, S1);
+    Meta tr = fdot2_auto<L>(wre(z), a, c, b, d, true, S0, S1);
+    Meta ti = fdot2_auto<L>(wim(z), a, d, b, c, false, S0, S1);
     st_meta(z.t, tr);
     st_meta(z.t + 1, ti);
 }
@@ -136,7 +154,7 @@ CB_HD void acb_add_si(const CRef& z, const CRef& x, int64_t k, const CRef& kball
 template <int L, class SCR>
 CB_HD void acb_inv(const CRef& z, const CRef& y, const CRef& tmp, SCR S0, SCR S1) {
     Opd c = re_of(y), d = im_of(y);
-    Meta tt = arb_fdot2<L>(wre(tmp), c, c, d, d, false, S0, S1);
+    Meta tt = fdot2_auto<L>(wre(tmp), c, c, d, d, false, S0, S1);
     Opd t{RRef{tmp.m, tmp.stride}, tt};
     Meta tr = arb_div<L>(wre(z), c, t, S0, S1);
     Meta ti = arb_div<L>(wim(z), d, t, S0, S1);
@@ -301,9 +319,6 @@ struct FuchsSharedParams {
     uint32_t* gcols;  // 2 * (2L+3) words per instance, [word][instance]: columns of the general path
 };
 
-// does this precision use truncated products in the recurrence kernel?
-template <int L>
-constexpr bool use_trunc() { return L >= 16 && L <= 32; }
 
 // one fused dot product of the recurrence: truncated products with the exact general path as the
 // per-lane fallback (L = 16..32), or the exact in-shared-memory version (other precisions)
