@@ -1,4 +1,5 @@
-// cb_mul.cuh -- exact L x L -> 2L limb product held entirely in registers (sm_100a).
+// cb_mul.cuh -- limb products held entirely in registers (sm_100a): mul_full (exact L x L -> 2L),
+// mul_high (the columns >= K only, with a stated error bound) and add_chain (PTX carry chain).
 //
 // Replaces the mpn_mul_n calls that Arb's arf_mul / arf_complex_mul make underneath
 // acb_mul at reference src/fuchs_solver.c:118 and src/frobenius_solver.c:59,107.
