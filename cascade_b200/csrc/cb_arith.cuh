@@ -494,8 +494,15 @@ CB_HD Meta finish(const Rounded& rr, bool neg, Mag rad) {
 }
 template <int L, class DST>
 CB_HD void store_nan(DST dst) {
-#pragma unroll
+#pragma unroll 8
     for (int j = 0; j < L; j++) dst.st(j, 0u);
+}
+// finish + canonical form of an indeterminate result (exponent overflow): all-zero mantissa
+template <int L, class DST>
+CB_HD Meta finish_to(DST dst, const Rounded& rr, bool neg, Mag rad) {
+    Meta t = finish<L>(rr, neg, rad);
+    if (is_nan(t)) store_nan<L>(dst);
+    return t;
 }
 
 // ---------------------------------------------------------------- in-register fast path
@@ -707,7 +714,7 @@ CB_NOINLINE Meta arb_fdot2(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2, OpdT<
         if (!done) rr = align_add<L, 2 * L>(dst, S0, S1, e1, e2, n1, n2, z1, z2, &neg);
     }
     if (nan) return meta_nan();
-    return finish<L>(rr, neg, rad);
+    return finish_to<L>(dst, rr, neg, rad);
 }
 
 // ---- the recurrence kernel's variant: truncated products first, exact general path as fallback
@@ -776,7 +783,7 @@ CB_NOINLINE Meta arb_fdot2_general(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x
     bool neg;
     Rounded rr = align_add<L, 2 * L>(dst, G0, G1, e1, e2, n1, n2, z1, z2, &neg);
     if (nan) return meta_nan();
-    return finish<L>(rr, neg, rad);
+    return finish_to<L>(dst, rr, neg, rad);
 }
 
 // dst = x1*y1 +- x2*y2 from TRUNCATED products (columns below K = L-4 dropped: 40% fewer limb
@@ -856,7 +863,7 @@ CB_NOINLINE Meta arb_fdot2_trunc(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2,
     }
     *ok = done;
     if (nan) return meta_nan();
-    return finish<L>(rr, neg, rad);
+    return finish_to<L>(dst, rr, neg, rad);
 }
 
 // dst = x + (negy ? -y : y)
@@ -890,7 +897,7 @@ CB_NOINLINE Meta arb_addsub(WRef dst, Opd x, Opd y, bool negy, SCR S0, SCR S1) {
         rr = align_add<L, L>(dst, S0, S1, x.t.exp, y.t.exp, nx, ny, zx, zy, &neg);
     }
     if (nan) return meta_nan();
-    return finish<L>(rr, neg, mag_add(mag_of(x.t), mag_of(y.t)));
+    return finish_to<L>(dst, rr, neg, mag_add(mag_of(x.t), mag_of(y.t)));
 }
 
 // Column form used by the register/shared-memory resident recurrence: A and B are scratch columns
@@ -922,7 +929,7 @@ CB_NOINLINE Meta arb_addsub_cols(SCR A, Meta ta, SCR B, Meta tb, bool negb, SCR*
     if (!done)
         rr = align_add<L, L, true>(A, A, B, ta.exp, tb.exp, na, nb, zx, zy, &neg, where);
     if (nan) return meta_nan();
-    return finish<L>(rr, neg, mag_add(mag_of(ta), mag_of(tb)));
+    return finish_to<L>(*where, rr, neg, mag_add(mag_of(ta), mag_of(tb)));
 }
 
 // dst = x * k, k a signed 64-bit integer (acb_mul_fmpz / acb_mul_si with a small integer)
@@ -962,7 +969,7 @@ CB_NOINLINE Meta arb_mul_si(WRef dst, Opd x, int64_t k, SCR S0) {
     Rounded rr = extract<L>(dst, S0, hi, false, (int64_t)x.t.exp - 32 * L);
     if (nan) return meta_nan();
     bool neg = ((x.t.flags & F_SIGN) != 0) != (k < 0);
-    return finish<L>(rr, neg, rad);
+    return finish_to<L>(dst, rr, neg, rad);
 }
 
 // dst = x / y  (Knuth D on 32-bit limbs; numerator x * 2^(32L) in S0, divisor in S1)
@@ -1048,7 +1055,7 @@ CB_NOINLINE Meta arb_div(DST dst, OpdT<XS> x, OpdT<YS> y, SCR S0, SCR S1) {
         return meta_nan();
     }
     bool neg = ((x.t.flags ^ y.t.flags) & F_SIGN) != 0;
-    return finish<L>(rr, neg, rad);
+    return finish_to<L>(dst, rr, neg, rad);
 }
 
 // ---------------------------------------------------------------- division by a 64-bit integer
@@ -1128,7 +1135,7 @@ CB_NOINLINE Meta arb_div_u64(DST dst, OpdT<XS> x, uint64_t d, bool dneg, SCR S0)
         return meta_nan();
     }
     bool neg = ((x.t.flags & F_SIGN) != 0) != dneg;
-    return finish<L>(rr, neg, rad);
+    return finish_to<L>(dst, rr, neg, rad);
 }
 
 }  // namespace cb

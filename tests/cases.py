@@ -70,6 +70,29 @@ def case_elementwise(oracle, drv, L: int, n: int, seed: int):
         assert_same(oracle.ew_scalar_si(op, x, k), api.ew(op, x, k=k, driver=drv), f"{name} L={L}")
 
 
+def case_exponent_overflow(oracle, drv, L: int):
+    """Midpoint exponents beyond +-2^28 make the ball indeterminate (device exponents are 32-bit);
+    the oracle applies the same rule, and an indeterminate ball has an all-zero mantissa."""
+    rng = np.random.default_rng(L)
+    n = 40
+    x = random_balls(rng, 2 * n, L, -2, 2, "ulp")
+    y = random_balls(rng, 2 * n, L, -2, 2, "ulp")
+    big = (1 << 27) + 5
+    x.meta[:, 0] += np.where(np.arange(2 * n) % 3 == 0, big, 0).astype(np.int32)
+    y.meta[:, 0] += np.where(np.arange(2 * n) % 3 == 0, big, 0).astype(np.int32)
+    x.meta[:, 3] = x.meta[:, 0] - 32 * L
+    y.meta[:, 3] = y.meta[:, 0] - 32 * L
+    ys = y.copy()
+    ys.meta[:, 0] -= np.where(np.arange(2 * n) % 3 == 0, 2 * big, 0).astype(np.int32)
+    ys.meta[:, 3] = ys.meta[:, 0] - 32 * L
+    for op, name, yy in ((2, "mul", y), (3, "div", ys), (0, "add", y)):
+        zo = oracle.ew_binary(op, x, yy)
+        zs = api.ew(op, x, yy, driver=drv)
+        assert_same(zo, zs, f"overflow {name} L={L}")
+        if op == 2:
+            assert (zo.meta[:, 1] & FLAG_NAN).any()
+
+
 def case_readme_kat(oracle, drv):
     """reference README.md:43-47,72-77: legendre(4), c0 = 0.375, 5 terms at 1024 bits."""
     L = 32

@@ -60,3 +60,8 @@ def test_horner(oracle, sim_driver, L):
 @pytest.mark.parametrize("L", [4, 32])
 def test_continuation(oracle, sim_driver, L):
     cases.case_continuation(oracle, sim_driver, L, seed=3 + L)
+
+
+@pytest.mark.parametrize("L", [4, 32, 64])
+def test_exponent_overflow(oracle, sim_driver, L):
+    cases.case_exponent_overflow(oracle, sim_driver, L)

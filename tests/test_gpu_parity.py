@@ -62,3 +62,8 @@ def test_horner(oracle, gpu_driver, L):
 @pytest.mark.parametrize("L", [32, 64])
 def test_continuation(oracle, gpu_driver, L):
     cases.case_continuation(oracle, gpu_driver, L, seed=23 + L, steps=6, n=40, batch=5)
+
+
+@pytest.mark.parametrize("L", [4, 32, 64, 128])
+def test_exponent_overflow(oracle, gpu_driver, L):
+    cases.case_exponent_overflow(oracle, gpu_driver, L)
