@@ -866,6 +866,133 @@ CB_NOINLINE Meta arb_fdot2_trunc(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2,
     return finish_to<L>(dst, rr, neg, rad);
 }
 
+// ---- 2048 bits: truncated product from 32-limb blocks, both products in shared columns
+// Ph[k] = word K + k of the truncated product (K = 2*32 - 4 = 60), k in [0, 68): every limb product
+// whose column is below K is dropped, exactly the set mul_high drops for an unblocked product, so
+// the same error bound (K+1) 2^(32(K+1)) holds.  x = x1 B + x0, y = y1 B + y0, B = 2^1024:
+//   x1 y1            full block            -> words 64..127
+//   x1 y0, x0 y1     high blocks (K' = 28) -> words 60..95
+//   x0 y0            only the 6 limb products with i + j >= 60
+template <class SCR, class XS, class YS>
+CB_HD void product_trunc64(SCR Ph, XS x, YS y) {
+    constexpr int PW = 68;
+    {
+        uint32_t a[32], b[32], r[64];
+#pragma unroll
+        for (int j = 0; j < 32; j++) a[j] = x.ld(32 + j);
+#pragma unroll
+        for (int j = 0; j < 32; j++) b[j] = y.ld(32 + j);
+        mul_full<32>(r, a, b);
+#pragma unroll
+        for (int k = 0; k < 4; k++) Ph.st(k, 0u);
+#pragma unroll
+        for (int k = 0; k < 64; k++) Ph.st(4 + k, r[k]);
+    }
+#pragma unroll 1
+    for (int t = 0; t < 2; t++) {  // the two cross blocks share one code instance
+        uint32_t a[32], b[32], r[36], o[36];
+#pragma unroll
+        for (int j = 0; j < 32; j++) a[j] = x.ld((t ? 0 : 32) + j);
+#pragma unroll
+        for (int j = 0; j < 32; j++) b[j] = y.ld((t ? 32 : 0) + j);
+        mul_high<32, 28>(r, a, b);
+#pragma unroll
+        for (int k = 0; k < 36; k++) o[k] = Ph.ld(k);
+        uint32_t c = add_chain<36>(o, r);
+#pragma unroll
+        for (int k = 0; k < 36; k++) Ph.st(k, o[k]);
+#pragma unroll 1
+        for (int k = 36; c != 0u && k < PW; k++) {
+            uint64_t s = (uint64_t)Ph.ld(k) + c;
+            Ph.st(k, (uint32_t)s);
+            c = (uint32_t)(s >> 32);
+        }
+    }
+    {   // x0 y0: columns 60, 61, 62 (high words reach column 63)
+        uint32_t x29 = x.ld(29), x30 = x.ld(30), x31 = x.ld(31), y29 = y.ld(29), y30 = y.ld(30), y31 = y.ld(31);
+        uint64_t p;
+        uint64_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;  // column sums (each < 2^35)
+        p = (uint64_t)x29 * y31; c0 += (uint32_t)p; c1 += p >> 32;
+        p = (uint64_t)x30 * y30; c0 += (uint32_t)p; c1 += p >> 32;
+        p = (uint64_t)x31 * y29; c0 += (uint32_t)p; c1 += p >> 32;
+        p = (uint64_t)x30 * y31; c1 += (uint32_t)p; c2 += p >> 32;
+        p = (uint64_t)x31 * y30; c1 += (uint32_t)p; c2 += p >> 32;
+        p = (uint64_t)x31 * y31; c2 += (uint32_t)p; c3 += p >> 32;
+        uint64_t cols[4] = {c0, c1, c2, c3};
+        uint64_t carry = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint64_t s = (uint64_t)Ph.ld(k) + (uint32_t)cols[k] + (uint32_t)carry;
+            carry = (carry >> 32) + (cols[k] >> 32) + (s >> 32);
+            Ph.st(k, (uint32_t)s);
+        }
+#pragma unroll 1
+        for (int k = 4; carry != 0u && k < PW; k++) {
+            uint64_t s = (uint64_t)Ph.ld(k) + (uint32_t)carry;
+            carry = (carry >> 32) + (s >> 32);
+            Ph.st(k, (uint32_t)s);
+        }
+    }
+}
+
+// dst = x1*y1 +- x2*y2 at 2048 bits from truncated blocked products (45% fewer limb products);
+// *ok = false when the guard bits cannot prove the result (the caller then runs the exact path).
+// S0, S1: shared columns of at least 68 words.
+template <class SCR, class XS = RRef, class YS = RRef, class DST = WRef>
+CB_NOINLINE Meta arb_fdot2_trunc64(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2, OpdT<YS> y2, bool neg2, SCR S0,
+                                   SCR S1, bool* ok) {
+    constexpr int L = 64, K = 60, PW = 68;
+    bool nan = is_nan(x1.t) || is_nan(y1.t) || is_nan(x2.t) || is_nan(y2.t);
+    bool z1 = is_zero_mid(x1.t) || is_zero_mid(y1.t) || nan;
+    bool z2 = is_zero_mid(x2.t) || is_zero_mid(y2.t) || nan;
+    Mag rad = mul_rad(mag_zero(), x1.t, top_limb<L>(x1), y1.t, top_limb<L>(y1));
+    rad = mul_rad(rad, x2.t, top_limb<L>(x2), y2.t, top_limb<L>(y2));
+    bool n1 = ((x1.t.flags ^ y1.t.flags) & F_SIGN) != 0;
+    bool n2 = (((x2.t.flags ^ y2.t.flags) & F_SIGN) != 0) != neg2;
+    const int64_t e1 = (int64_t)x1.t.exp + y1.t.exp, e2 = (int64_t)x2.t.exp + y2.t.exp;
+    // term A (zero, else smaller exponent) goes to S0 and may be read with a word offset
+    const bool a_is_1 = z1 ? true : (z2 ? false : (e1 <= e2));
+    const bool zA = a_is_1 ? z1 : z2, zB = a_is_1 ? z2 : z1;
+    const bool nA = a_is_1 ? n1 : n2, nB = a_is_1 ? n2 : n1;
+    const int64_t eA = a_is_1 ? e1 : e2, eB = a_is_1 ? e2 : e1;
+    const XS xA = a_is_1 ? x1.r : x2.r, xB = a_is_1 ? x2.r : x1.r;
+    const YS yA = a_is_1 ? y1.r : y2.r, yB = a_is_1 ? y2.r : y1.r;
+    bool skipA = warp_all(zA), skipB = warp_all(zB);
+#pragma unroll 1
+    for (int term = 0; term < 2; term++) {
+        if (term ? skipB : skipA) continue;
+        product_trunc64(term ? S1 : S0, term ? xB : xA, term ? yB : yA);
+    }
+    bool done = false, neg = false;
+    Rounded rr;
+    rr.exp = 0;
+    rr.zero = true;
+    rr.inexact = false;
+    rr.overflow = false;
+    if (zA && zB) {
+#pragma unroll 8
+        for (int j = 0; j < L; j++) dst.st(j, 0u);
+        done = true;
+    } else {
+        int64_t d = zA ? 0 : (eB - eA);
+        int m = d > 32 * 140 ? 140 : (int)(d >> 5);
+        int sA = (int)(d & 31);
+        bool sub = (nA != nB) && !zA;
+        auto wB = [&](int k) -> uint32_t { return zB ? 0u : S1.ld(k - K); };
+        auto wA = [&](int k) -> uint32_t {
+            int i = k + m - K;
+            return (zA || (unsigned)i >= (unsigned)PW) ? 0u : S0.ld(i);
+        };
+        done = fast_add_round<L, 2 * L, K>(dst, wB, wA, 0, sA, sub, nB, nA, eB, &rr, &neg, false);
+    }
+    *ok = done;
+    if (nan) {
+        store_nan<L>(dst);
+        return meta_nan();
+    }
+    return finish_to<L>(dst, rr, neg, rad);
+}
+
 // dst = x + (negy ? -y : y)
 template <int L, class SCR>
 CB_NOINLINE Meta arb_addsub(WRef dst, Opd x, Opd y, bool negy, SCR S0, SCR S1) {

@@ -73,6 +73,11 @@ CB_HD Meta fdot2_auto(WRef dst, Opd x1, Opd y1, Opd x2, Opd y2, bool neg2, SCR S
         Meta t = arb_fdot2_trunc<L>(dst, x1, y1, x2, y2, neg2, S0, &ok);
         if (!ok) t = arb_fdot2<L>(dst, x1, y1, x2, y2, neg2, S0, S1);
         return t;
+    } else if constexpr (L == 64) {
+        bool ok;
+        Meta t = arb_fdot2_trunc64(dst, x1, y1, x2, y2, neg2, S0, S1, &ok);
+        if (!ok) t = arb_fdot2<L>(dst, x1, y1, x2, y2, neg2, S0, S1);
+        return t;
     } else {
         return arb_fdot2<L>(dst, x1, y1, x2, y2, neg2, S0, S1);
     }
@@ -331,7 +336,7 @@ CB_HD Meta rec_fdot2(DST dst, Opd x1, OpdS y1, Opd x2, OpdS y2, bool neg2, SCR S
         if (!ok) t = arb_fdot2_general<L>(dst, x1, dyn(y1), x2, dyn(y2), neg2, G0, G1);
         return t;
     } else {
-        return arb_fdot2<L>(dst, x1, dyn(y1), x2, dyn(y2), neg2, S0, S1);
+        return fdot2_auto<L>(dst, x1, dyn(y1), x2, dyn(y2), neg2, S0, S1);
     }
 }
 
