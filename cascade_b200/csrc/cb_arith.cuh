@@ -40,6 +40,14 @@ constexpr uint32_t F_SIGN = 1u, F_ZERO = 2u, F_NAN = 4u;
 // of trailing zero LIMBS of the mantissa (set by the table kernel on the shared multipliers).
 constexpr int F_TZ_SHIFT = 8;
 CB_HD int tz_hint(uint32_t flags) { return (int)((flags >> F_TZ_SHIFT) & 0xFFu); }
+// fill in the hint of an operand that has none: dense operands cost one load, short ones a scan
+template <int L, class O>
+CB_HD void tz_scan(O& o) {
+    if (tz_hint(o.t.flags) != 0 || (o.t.flags & (F_ZERO | F_NAN))) return;
+    int tz = 0;
+    while (tz < L - 1 && o.r.ld(tz) == 0u) tz++;
+    o.t.flags |= (uint32_t)tz << F_TZ_SHIFT;
+}
 constexpr int32_t EXP_LIMIT = 1 << 28;
 
 struct Meta {
@@ -790,7 +798,9 @@ CB_NOINLINE Meta arb_fdot2_general(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x
 // products); *ok = false (dst untouched... or to be overwritten) when the result cannot be proven
 // equal to the exact one -- the caller then runs arb_fdot2_general.  S0: a shared column of
 // 2L-K+1 words.
-template <int L, class SCR, class XS = RRef, class YS = RRef, class DST = WRef>
+// SCAN_TZ: look for short operands in the loaded limbs (general kernels); the recurrence kernel
+// gets the hints of its shared multipliers from the table kernel and leaves this off.
+template <int L, class SCR, class XS = RRef, class YS = RRef, class DST = WRef, bool SCAN_TZ = false>
 CB_NOINLINE Meta arb_fdot2_trunc(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2, OpdT<YS> y2, bool neg2, SCR S0,
                                  bool* ok) {
     static_assert(L >= 16 && L <= 32, "truncated products are used for 512..1024-bit mantissas");
@@ -812,8 +822,8 @@ CB_NOINLINE Meta arb_fdot2_trunc(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2,
     const int64_t eA = a_is_1 ? e1 : e2, eB = a_is_1 ? e2 : e1;
     const XS xA = a_is_1 ? x1.r : x2.r, xB = a_is_1 ? x2.r : x1.r;
     const YS yA = a_is_1 ? y1.r : y2.r, yB = a_is_1 ? y2.r : y1.r;
-    const int tzA = a_is_1 ? tz_hint(x1.t.flags) + tz_hint(y1.t.flags) : tz_hint(x2.t.flags) + tz_hint(y2.t.flags);
-    const int tzB = a_is_1 ? tz_hint(x2.t.flags) + tz_hint(y2.t.flags) : tz_hint(x1.t.flags) + tz_hint(y1.t.flags);
+    int tzA = a_is_1 ? tz_hint(x1.t.flags) + tz_hint(y1.t.flags) : tz_hint(x2.t.flags) + tz_hint(y2.t.flags);
+    int tzB = a_is_1 ? tz_hint(x2.t.flags) + tz_hint(y2.t.flags) : tz_hint(x1.t.flags) + tz_hint(y1.t.flags);
     bool skipA = warp_all(zA), skipB = warp_all(zB);
     uint32_t r[PW];
 #pragma unroll 1
@@ -825,6 +835,18 @@ CB_NOINLINE Meta arb_fdot2_trunc(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2,
             uint32_t a[L], b[L];
             load_limbs<L>(a, term ? xB : xA);
             load_limbs<L>(b, term ? yB : yA);
+            // short (integer-like) operands: count their trailing zero limbs while they are in
+            // registers (exact products carry no information in their guard bits)
+            if (SCAN_TZ && (a[0] == 0u || b[0] == 0u)) {
+                int ta = L - 1, tb = L - 1;
+#pragma unroll
+                for (int j = L - 2; j >= 0; j--) {
+                    ta = a[j] ? j : ta;
+                    tb = b[j] ? j : tb;
+                }
+                int t = ta + tb;
+                if (term) tzB = tzB > t ? tzB : t; else tzA = tzA > t ? tzA : t;
+            }
             mul_high<L, K>(r, a, b);
         }
         if (term == 0) {  // park product A; nothing of r is live across the back edge
@@ -866,52 +888,75 @@ CB_NOINLINE Meta arb_fdot2_trunc(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2,
     return finish_to<L>(dst, rr, neg, rad);
 }
 
-// ---- 2048 bits: truncated product from 32-limb blocks, both products in shared columns
-// Ph[k] = word K + k of the truncated product (K = 2*32 - 4 = 60), k in [0, 68): every limb product
-// whose column is below K is dropped, exactly the set mul_high drops for an unblocked product, so
-// the same error bound (K+1) 2^(32(K+1)) holds.  x = x1 B + x0, y = y1 B + y0, B = 2^1024:
-//   x1 y1            full block            -> words 64..127
-//   x1 y0, x0 y1     high blocks (K' = 28) -> words 60..95
-//   x0 y0            only the 6 limb products with i + j >= 60
-template <class SCR, class XS, class YS>
-CB_HD void product_trunc64(SCR Ph, XS x, YS y) {
-    constexpr int PW = 68;
-    {
-        uint32_t a[32], b[32], r[64];
-#pragma unroll
-        for (int j = 0; j < 32; j++) a[j] = x.ld(32 + j);
-#pragma unroll
-        for (int j = 0; j < 32; j++) b[j] = y.ld(32 + j);
-        mul_full<32>(r, a, b);
-#pragma unroll
-        for (int k = 0; k < 4; k++) Ph.st(k, 0u);
-#pragma unroll
-        for (int k = 0; k < 64; k++) Ph.st(4 + k, r[k]);
-    }
+// ---- above 1024 bits: truncated product from 32-limb blocks, both products in shared columns
+// Ph[k] = word K + k of the truncated product, K = L - 4, k in [0, L + 4): every limb product whose
+// column is below K is dropped, exactly the set mul_high drops for an unblocked product, so the
+// same error bound (K+1) 2^(32(K+1)) holds.  With NB = L/32 blocks per operand and s = bi + bj:
+//   s >= NB      full 32x32 block                     -> product words 32 s .. 32 s + 63
+//   s == NB - 1  high block (mul_high<32, 28>)        -> product words K .. K + 35
+//   s == NB - 2  only the 6 limb products with i + j >= 60 inside the block -> words K .. K + 3
+//   s <  NB - 2  dropped entirely
+// (2048 bits: 2 266 limb multiplies instead of 4 096; 4096 bits: 8 634 instead of 16 384.)
+template <class SCR>
+CB_HD void ripple(SCR Ph, int k, int top, uint32_t c) {
 #pragma unroll 1
-    for (int t = 0; t < 2; t++) {  // the two cross blocks share one code instance
+    for (; c != 0u && k < top; k++) {
+        uint64_t s = (uint64_t)Ph.ld(k) + c;
+        Ph.st(k, (uint32_t)s);
+        c = (uint32_t)(s >> 32);
+    }
+}
+template <int L, class SCR, class XS, class YS>
+CB_HD void product_trunc_blocked(SCR Ph, XS x, YS y) {
+    constexpr int NB = L / 32, K = L - 4, PW = L + 4;
+    static_assert(L % 32 == 0 && NB >= 2, "blocked truncated product");
+#pragma unroll 8
+    for (int k = 0; k < PW; k++) Ph.st(k, 0u);
+    // full blocks
+#pragma unroll 1
+    for (int bi = 1; bi < NB; bi++) {
+        uint32_t a[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) a[j] = x.ld(32 * bi + j);
+#pragma unroll 1
+        for (int bj = NB - bi; bj < NB; bj++) {
+            uint32_t b[32], r[64], o[64];
+#pragma unroll
+            for (int j = 0; j < 32; j++) b[j] = y.ld(32 * bj + j);
+            mul_full<32>(r, a, b);
+            int off = 32 * (bi + bj) - K;
+#pragma unroll
+            for (int k = 0; k < 64; k++) o[k] = Ph.ld(off + k);
+            uint32_t c = add_chain<64>(o, r);
+#pragma unroll
+            for (int k = 0; k < 64; k++) Ph.st(off + k, o[k]);
+            ripple(Ph, off + 64, PW, c);
+        }
+    }
+    // high blocks: bi + bj == NB - 1
+#pragma unroll 1
+    for (int bi = 0; bi < NB; bi++) {
+        int bj = NB - 1 - bi;
         uint32_t a[32], b[32], r[36], o[36];
 #pragma unroll
-        for (int j = 0; j < 32; j++) a[j] = x.ld((t ? 0 : 32) + j);
+        for (int j = 0; j < 32; j++) a[j] = x.ld(32 * bi + j);
 #pragma unroll
-        for (int j = 0; j < 32; j++) b[j] = y.ld((t ? 32 : 0) + j);
+        for (int j = 0; j < 32; j++) b[j] = y.ld(32 * bj + j);
         mul_high<32, 28>(r, a, b);
 #pragma unroll
         for (int k = 0; k < 36; k++) o[k] = Ph.ld(k);
         uint32_t c = add_chain<36>(o, r);
 #pragma unroll
         for (int k = 0; k < 36; k++) Ph.st(k, o[k]);
-#pragma unroll 1
-        for (int k = 36; c != 0u && k < PW; k++) {
-            uint64_t s = (uint64_t)Ph.ld(k) + c;
-            Ph.st(k, (uint32_t)s);
-            c = (uint32_t)(s >> 32);
-        }
+        ripple(Ph, 36, PW, c);
     }
-    {   // x0 y0: columns 60, 61, 62 (high words reach column 63)
-        uint32_t x29 = x.ld(29), x30 = x.ld(30), x31 = x.ld(31), y29 = y.ld(29), y30 = y.ld(30), y31 = y.ld(31);
-        uint64_t p;
-        uint64_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;  // column sums (each < 2^35)
+    // corners: bi + bj == NB - 2, limb products with i + j in {60, 61, 62}
+#pragma unroll 1
+    for (int bi = 0; bi <= NB - 2; bi++) {
+        int bj = NB - 2 - bi;
+        uint32_t x29 = x.ld(32 * bi + 29), x30 = x.ld(32 * bi + 30), x31 = x.ld(32 * bi + 31);
+        uint32_t y29 = y.ld(32 * bj + 29), y30 = y.ld(32 * bj + 30), y31 = y.ld(32 * bj + 31);
+        uint64_t p, c0 = 0, c1 = 0, c2 = 0, c3 = 0;  // column sums (each < 2^35)
         p = (uint64_t)x29 * y31; c0 += (uint32_t)p; c1 += p >> 32;
         p = (uint64_t)x30 * y30; c0 += (uint32_t)p; c1 += p >> 32;
         p = (uint64_t)x31 * y29; c0 += (uint32_t)p; c1 += p >> 32;
@@ -922,26 +967,26 @@ CB_HD void product_trunc64(SCR Ph, XS x, YS y) {
         uint64_t carry = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            uint64_t s = (uint64_t)Ph.ld(k) + (uint32_t)cols[k] + (uint32_t)carry;
-            carry = (carry >> 32) + (cols[k] >> 32) + (s >> 32);
-            Ph.st(k, (uint32_t)s);
+            uint64_t sum = (uint64_t)Ph.ld(k) + (uint32_t)cols[k] + (uint32_t)carry;
+            carry = (carry >> 32) + (cols[k] >> 32) + (sum >> 32);
+            Ph.st(k, (uint32_t)sum);
         }
 #pragma unroll 1
         for (int k = 4; carry != 0u && k < PW; k++) {
-            uint64_t s = (uint64_t)Ph.ld(k) + (uint32_t)carry;
-            carry = (carry >> 32) + (s >> 32);
-            Ph.st(k, (uint32_t)s);
+            uint64_t sum = (uint64_t)Ph.ld(k) + (uint32_t)carry;
+            carry = (carry >> 32) + (sum >> 32);
+            Ph.st(k, (uint32_t)sum);
         }
     }
 }
 
-// dst = x1*y1 +- x2*y2 at 2048 bits from truncated blocked products (45% fewer limb products);
+// dst = x1*y1 +- x2*y2 above 1024 bits from truncated blocked products;
 // *ok = false when the guard bits cannot prove the result (the caller then runs the exact path).
-// S0, S1: shared columns of at least 68 words.
-template <class SCR, class XS = RRef, class YS = RRef, class DST = WRef>
-CB_NOINLINE Meta arb_fdot2_trunc64(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2, OpdT<YS> y2, bool neg2, SCR S0,
-                                   SCR S1, bool* ok) {
-    constexpr int L = 64, K = 60, PW = 68;
+// S0, S1: shared columns of at least L + 4 words.
+template <int L, class SCR, class XS = RRef, class YS = RRef, class DST = WRef>
+CB_NOINLINE Meta arb_fdot2_trunc_blocked(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2, OpdT<YS> y2, bool neg2,
+                                         SCR S0, SCR S1, bool* ok) {
+    constexpr int K = L - 4, PW = L + 4;
     bool nan = is_nan(x1.t) || is_nan(y1.t) || is_nan(x2.t) || is_nan(y2.t);
     bool z1 = is_zero_mid(x1.t) || is_zero_mid(y1.t) || nan;
     bool z2 = is_zero_mid(x2.t) || is_zero_mid(y2.t) || nan;
@@ -961,7 +1006,7 @@ CB_NOINLINE Meta arb_fdot2_trunc64(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x
 #pragma unroll 1
     for (int term = 0; term < 2; term++) {
         if (term ? skipB : skipA) continue;
-        product_trunc64(term ? S1 : S0, term ? xB : xA, term ? yB : yA);
+        product_trunc_blocked<L>(term ? S1 : S0, term ? xB : xA, term ? yB : yA);
     }
     bool done = false, neg = false;
     Rounded rr;
@@ -975,7 +1020,7 @@ CB_NOINLINE Meta arb_fdot2_trunc64(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x
         done = true;
     } else {
         int64_t d = zA ? 0 : (eB - eA);
-        int m = d > 32 * 140 ? 140 : (int)(d >> 5);
+        int m = d > 32 * (2 * L + 8) ? (2 * L + 8) : (int)(d >> 5);
         int sA = (int)(d & 31);
         bool sub = (nA != nB) && !zA;
         auto wB = [&](int k) -> uint32_t { return zB ? 0u : S1.ld(k - K); };
@@ -983,7 +1028,10 @@ CB_NOINLINE Meta arb_fdot2_trunc64(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x
             int i = k + m - K;
             return (zA || (unsigned)i >= (unsigned)PW) ? 0u : S0.ld(i);
         };
-        done = fast_add_round<L, 2 * L, K>(dst, wB, wA, 0, sA, sub, nB, nA, eB, &rr, &neg, false);
+        const int tzA = a_is_1 ? tz_hint(x1.t.flags) + tz_hint(y1.t.flags) : tz_hint(x2.t.flags) + tz_hint(y2.t.flags);
+        const int tzB = a_is_1 ? tz_hint(x2.t.flags) + tz_hint(y2.t.flags) : tz_hint(x1.t.flags) + tz_hint(y1.t.flags);
+        bool trusted = (zA || (tzA >= K && m == 0)) && tzB >= K;
+        done = fast_add_round<L, 2 * L, K>(dst, wB, wA, 0, sA, sub, nB, nA, eB, &rr, &neg, trusted);
     }
     *ok = done;
     if (nan) {

@@ -68,14 +68,24 @@ constexpr bool use_trunc() { return L >= 16 && L <= 32; }
 // the exact shared-memory version when the guard-bit proof fails
 template <int L, class SCR>
 CB_HD Meta fdot2_auto(WRef dst, Opd x1, Opd y1, Opd x2, Opd y2, bool neg2, SCR S0, SCR S1) {
+    if constexpr (L == 64 || L == 128) {
+        // short (integer-like) operands make exact products, whose guard bits prove nothing:
+        // knowing their trailing zero limbs lets the truncated path accept them as exact
+        // (at 1024 bits arb_fdot2_trunc finds them itself from the limbs it has in registers)
+        tz_scan<L>(x1);
+        tz_scan<L>(y1);
+        tz_scan<L>(x2);
+        tz_scan<L>(y2);
+    }
     if constexpr (use_trunc<L>()) {
         bool ok;
-        Meta t = arb_fdot2_trunc<L>(dst, x1, y1, x2, y2, neg2, S0, &ok);
+        Meta t = arb_fdot2_trunc<L, SCR, RRef, RRef, WRef, true>(dst, x1, y1, x2, y2, neg2, S0, &ok);
         if (!ok) t = arb_fdot2<L>(dst, x1, y1, x2, y2, neg2, S0, S1);
         return t;
-    } else if constexpr (L == 64) {
+    } else if constexpr (L == 64 || L == 128) {
         bool ok;
-        Meta t = arb_fdot2_trunc64(dst, x1, y1, x2, y2, neg2, S0, S1, &ok);
+        Meta t = arb_fdot2_trunc_blocked<L>(dst, x1, y1, x2, y2, neg2, S0, S1, &ok);
+        CB_COUNT(ok ? 4 : 5);
         if (!ok) t = arb_fdot2<L>(dst, x1, y1, x2, y2, neg2, S0, S1);
         return t;
     } else {
