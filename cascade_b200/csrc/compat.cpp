@@ -367,6 +367,46 @@ void acb_ode_solution_clear(acb_ode_solution_t sol) {
     sol->gens = nullptr;
 }
 
+void acb_ode_solution_evaluate(acb_t out, acb_ode_solution_t sol, acb_t a, slong prec) {
+    if (acb_is_zero(a)) {  // reference :29-33: indeterminate at the expansion point
+        acb_zero(out);
+        out->real.meta = cb_meta{0, CB_FLAG_NAN, CB_MAG_INF_MAN, 0};
+        out->imag.meta = cb_meta{0, CB_FLAG_NAN, CB_MAG_INF_MAN, 0};
+        return;
+    }
+    if (sol->M != 1) die("acb_ode_solution_evaluate with M > 1 (needs acb_log: listed as next in DESIGN.md)", -1);
+    // rho must be an exact non-negative integer below 2^31: a^rho by binary exponentiation
+    const arb_struct* r = &sol->rho->real;
+    bool ok = arb_exact_zero(&sol->rho->imag) && r->meta.rman == 0 && !(r->meta.flags & (CB_FLAG_NAN | CB_FLAG_SIGN));
+    uint64_t e = 0;
+    if (ok && !(r->meta.flags & CB_FLAG_ZERO)) {
+        ok = r->meta.exp >= 1 && r->meta.exp <= 31;
+        for (int k = 0; ok && k < CB_MAX_LIMBS - 1; k++) ok = r->mant[k] == 0;
+        if (ok) {
+            uint32_t top = r->mant[CB_MAX_LIMBS - 1];
+            e = top >> (32 - r->meta.exp);
+            ok = ((uint64_t)e << (32 - r->meta.exp)) == top;
+        }
+    }
+    if (!ok) die("acb_ode_solution_evaluate with a non-integer exponent (needs acb_pow: listed as next in DESIGN.md)", -1);
+    acb_t res, p, t;
+    acb_poly_evaluate(res, sol->gens, a, prec);
+    acb_one(p);
+    if (e > 0) {
+        acb_set(p, a);
+        int top = 63 - __builtin_clzll(e);
+        for (int bit = top - 1; bit >= 0; bit--) {
+            acb_mul(t, p, p, prec);
+            acb_set(p, t);
+            if ((e >> bit) & 1) {
+                acb_mul(t, p, a, prec);
+                acb_set(p, t);
+            }
+        }
+    }
+    acb_mul(out, res, p, prec);
+}
+
 // ------------------------------------------------------------------ examples
 void acb_ode_legendre(acb_ode_t ODE, ulong n) {
     acb_ode_init_blank(ODE, 2, 2);

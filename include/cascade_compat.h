@@ -130,6 +130,11 @@ typedef acb_ode_solution_struct acb_ode_solution_t[1];
 
 void acb_ode_solution_init(acb_ode_solution_t sol, acb_t rho, slong mul, slong alpha);
 void acb_ode_solution_clear(acb_ode_solution_t sol);
+/* a^rho * gens[0](a) (reference src/acb_ode_solution.c:24-58) for M == 1 and an exact non-negative
+ * integer rho: Horner evaluation and the power (binary exponentiation) run on the device.  The
+ * logarithmic case M > 1 and non-integer rho need acb_log / acb_pow, which are listed as next in
+ * DESIGN.md; they abort here. */
+void acb_ode_solution_evaluate(acb_t res, acb_ode_solution_t sol, acb_t x, slong prec);
 
 /* ================================ Examples (reference src/examples.c) ========================= */
 void acb_ode_legendre(acb_ode_t ODE, ulong n);

@@ -19,6 +19,8 @@ int main ()
     acb_set_d(x, 0.125);
     acb_poly_evaluate(y, sol->gens, x, prec);
     printf("hyp2f1 %.17g %.3g\n", acb_get_mid_re_d(y), acb_get_rad_re_d(y));
+    acb_ode_solution_evaluate(y, sol, x, prec); /* rho = 0: a^0 * gens[0](a) */
+    printf("hyp2f1_eval %.17g %.3g\n", acb_get_mid_re_d(y), acb_get_rad_re_d(y));
     acb_ode_solution_clear(sol);
     acb_ode_clear(ODE);
 

@@ -32,6 +32,7 @@ def test_frobenius_continuation_evaluate():
     vals = {line.split()[0]: [float(v) for v in line.split()[1:]] for line in out.strip().splitlines()}
     # 2F1(1/2, 1/4; 3/2; 1/8), reference value from mpmath at 50 digits
     assert abs(vals["hyp2f1"][0] - 1.0109404757371801) < 1e-15 and vals["hyp2f1"][1] < 1e-30
+    assert vals["hyp2f1_eval"][0] == vals["hyp2f1"][0]
     # J0(1.5), J0'(1.5) = -J1(1.5); inputs were doubles, so agreement to ~1e-15
     assert abs(vals["J0(1.5)"][0] - 0.5118276717359181) < 1e-13
     assert abs(vals["J0'(1.5)"][0] - (-0.5579365079100996)) < 1e-13
