@@ -31,6 +31,10 @@ SYMBOLS = [
     "cb200_frobenius1_batch_dev", "cb200_frobenius1_batch_host",
     "cb200_horner_batch_dev", "cb200_horner_batch_host",
     "cb200_ew_dev", "cb200_ew_host",
+    "cb200_frobenius_general_workspace_bytes", "cb200_frobenius_general_batch_dev",
+    "cb200_frobenius_general_batch_host",
+    "cb200_solution_op_workspace_bytes", "cb200_solution_op_dev", "cb200_solution_op_host",
+    "cb200_indicial_polynomial_dev", "cb200_indicial_polynomial_host",
 ]
 
 
@@ -73,6 +77,22 @@ def lib() -> C.CDLL:
     L.cb200_horner_batch_host.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int, _u32p, _i32p, C.c_int, _u32p, _i32p, _u32p, _i32p, C.c_int]
     L.cb200_ew_dev.argtypes = [C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]
     L.cb200_ew_host.argtypes = [C.c_int, C.c_int, C.c_int64, _u32p, _i32p, _u32p, _i32p, _vp, _vp, _vp, C.c_int]
+    L.cb200_frobenius_general_workspace_bytes.restype = C.c_size_t
+    L.cb200_frobenius_general_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64]
+    L.cb200_frobenius_general_batch_dev.argtypes = ([C.c_int] * 4 + [C.c_int64] * 2 + [_vp, _vp, C.c_int, _vp, _vp, C.c_int,
+                                                    C.c_int, C.c_int, _vp, _vp, _vp, C.c_size_t, _vp])
+    L.cb200_frobenius_general_batch_host.argtypes = ([C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p,
+                                                     C.c_int, C.c_int, C.c_int, _u32p, _i32p, C.c_int])
+    L.cb200_solution_op_workspace_bytes.restype = C.c_size_t
+    L.cb200_solution_op_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int64]
+    L.cb200_solution_op_dev.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64, _vp, _vp, _vp,
+                                        _vp, _vp, _vp, C.c_int64, _vp, C.c_size_t, _vp]
+    L.cb200_solution_op_host.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64, _u32p, _i32p,
+                                         _u32p, _i32p, _u32p, _i32p, C.c_int64, C.c_int]
+    L.cb200_indicial_polynomial_dev.argtypes = [C.c_int] * 4 + [C.c_int64, _vp, _vp, C.c_int, C.c_int64, C.c_int64, _vp, _vp,
+                                                                _vp, C.c_size_t, _vp]
+    L.cb200_indicial_polynomial_host.argtypes = [C.c_int] * 4 + [C.c_int64, _u32p, _i32p, C.c_int, C.c_int64, C.c_int64,
+                                                                 _u32p, _i32p, C.c_int]
     _lib = L
     return L
 

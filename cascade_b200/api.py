@@ -47,6 +47,20 @@ class HostBufferDriver:
                                                       int(shared), rho_m, rho_t, int(shared_rho), res_m,
                                                       res_t, self.device)
 
+    def frobenius_general(self, L, order, degree, valuation, n, batch, ode_m, ode_t, shared, rho_m, rho_t,
+                          shared_rho, mul, M, gens_m, gens_t):
+        return _lib.lib().cb200_frobenius_general_batch_host(L, order, degree, valuation, n, batch, ode_m, ode_t,
+                                                             int(shared), rho_m, rho_t, int(shared_rho), mul, M,
+                                                             gens_m, gens_t, self.device)
+
+    def solution_op(self, which, L, batch, mul, M, cap, nu, rho_m, rho_t, gens_m, gens_t, f_m, f_t, fcap):
+        return _lib.lib().cb200_solution_op_host(which, L, batch, mul, M, cap, nu, rho_m, rho_t, gens_m, gens_t,
+                                                 f_m, f_t, fcap, self.device)
+
+    def indicial_polynomial(self, L, order, degree, valuation, batch, ode_m, ode_t, shared, nu, shift, out_m, out_t):
+        return _lib.lib().cb200_indicial_polynomial_host(L, order, degree, valuation, batch, ode_m, ode_t, int(shared),
+                                                         nu, shift, out_m, out_t, self.device)
+
     def horner(self, L, length, npts, nder, f_m, f_t, shared_f, p_m, p_t, o_m, o_t):
         return _lib.lib().cb200_horner_batch_host(L, length, npts, nder, f_m, f_t, int(shared_f), p_m, p_t,
                                                   o_m, o_t, self.device)
@@ -171,6 +185,67 @@ def acb_ode_solve_frobenius1_batch(ode: Balls, rho: Balls, order: int, degree: i
     _lib.check(drv.frobenius1(L, order, degree, v, n, batch, ode_m, ode_t, shared_ode, rho_m, rho_t,
                               shared_rho, res_m, res_t), "acb_ode_solve_frobenius1_batch")
     return entry_major_to_instance_major(unpack_entries(L, res_m, res_t), batch, n + 1)
+
+
+def acb_ode_solve_frobenius_batch(ode: Balls, rho: Balls, mul: int, alpha: int, order: int, degree: int, n: int,
+                                  batch: int, shared_ode: bool = True, shared_rho: bool = False,
+                                  valuation: int | None = None, driver=None) -> Balls:
+    """Batched ``acb_ode_solve_frobenius(sol, ODE, n, prec)`` after ``acb_ode_solution_init(sol, rho, mul,
+    alpha)`` (reference src/frobenius_solver.c:123-205).  Returns ``sol->gens`` as ``[batch][M][n+1]``
+    complex balls, ``M = mul + alpha``: the M = 1 recurrence or the polynomial-in-rho (logarithmic) one."""
+    drv = driver or default_driver()
+    M = mul + alpha
+    if M == 1:
+        return acb_ode_solve_frobenius1_batch(ode, rho, order, degree, n, batch, shared_ode, shared_rho, valuation, drv)
+    L = ode.L
+    v = acb_ode_valuation(ode, order, degree) if valuation is None else valuation
+    ode_m, ode_t = _ode_to_device(ode, order, degree, batch, shared_ode)
+    rho_m, rho_t = pack_entries(rho, 1, 2 * (1 if shared_rho else batch))
+    ng = M * (n + 1)
+    g_m = np.zeros((ng, L, 2 * batch), np.uint32)
+    g_t = np.zeros((ng, 2 * batch, 4), np.int32)
+    _lib.check(drv.frobenius_general(L, order, degree, v, n, batch, ode_m, ode_t, shared_ode, rho_m, rho_t,
+                                     shared_rho, mul, M, g_m, g_t), "acb_ode_solve_frobenius_batch")
+    return entry_major_to_instance_major(unpack_entries(L, g_m, g_t), batch, ng)
+
+
+SOL_EXTEND, SOL_UPDATE, SOL_NORMALIZE = 0, 1, 2
+
+
+def acb_ode_solution_op_batch(which: int, rho: Balls, gens: Balls, batch: int, mul: int, M: int,
+                              f: Balls | None = None, nu: int = 0, driver=None):
+    """``_acb_ode_solution_extend`` / ``_update`` / ``_normalize`` (reference src/acb_ode_solution.c:60-123)
+    for a batch of solutions.  ``gens``: ``[batch][M][cap]``; ``f``: ``[batch][fcap]`` coefficients of the
+    polynomial in rho, consumed as in the reference.  Returns ``(gens, f)`` after the call."""
+    drv = driver or default_driver()
+    L = gens.L
+    cap = gens.n_slots // (2 * batch * max(M, 1)) if M > 0 else 0
+    ff = Balls.zeros(2 * batch, L) if f is None else f.copy()  # the call consumes its polynomial
+    fcap = ff.n_slots // (2 * batch)
+    g_m, g_t = pack_entries(instance_major_to_entry_major(gens.copy(), batch, M * cap), M * cap, 2 * batch)
+    f_m, f_t = pack_entries(instance_major_to_entry_major(ff, batch, fcap), fcap, 2 * batch)
+    rho_m, rho_t = pack_entries(rho, 1, 2 * batch)
+    _lib.check(drv.solution_op(which, L, batch, mul, M, cap, nu, rho_m, rho_t, g_m, g_t, f_m, f_t, fcap),
+               "acb_ode_solution_op_batch")
+    return (entry_major_to_instance_major(unpack_entries(L, g_m, g_t), batch, M * cap),
+            entry_major_to_instance_major(unpack_entries(L, f_m, f_t), batch, fcap))
+
+
+def indicial_polynomial_batch(ode: Balls, order: int, degree: int, nu: int, shift: int, batch: int,
+                              shared_ode: bool = True, valuation: int | None = None, driver=None) -> Balls:
+    """``indicial_polynomial(result, ODE, nu, shift, prec)`` (reference src/frobenius_solver.c:4-39):
+    ``[batch][order+1]`` coefficients of f_nu(rho + shift) as a polynomial in rho."""
+    drv = driver or default_driver()
+    L = ode.L
+    v = acb_ode_valuation(ode, order, degree) if valuation is None else valuation
+    ode_m, ode_t = _ode_to_device(ode, order, degree, batch, shared_ode)
+    o_m = np.zeros((order + 2, L, 2 * batch), np.uint32)
+    o_t = np.zeros((order + 2, 2 * batch, 4), np.int32)
+    _lib.check(drv.indicial_polynomial(L, order, degree, v, batch, ode_m, ode_t, shared_ode, nu, shift, o_m, o_t),
+               "indicial_polynomial_batch")
+    full = entry_major_to_instance_major(unpack_entries(L, o_m, o_t), batch, order + 2)
+    keep = np.arange(batch * (order + 2) * 2).reshape(batch, order + 2, 2)[:, : order + 1].reshape(-1)
+    return Balls(L, full.mant[keep].copy(), full.meta[keep].copy())
 
 
 def analytic_continuation_batch(ode: Balls, path: Balls, y0: Balls, order: int, degree: int, n: int, batch: int,

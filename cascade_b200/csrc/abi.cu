@@ -190,6 +190,91 @@ int cb200_frobenius1_batch_dev(int L_, int order, int degree, int valuation, int
     return table_for(L_)->frobenius1(p, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------ general Frobenius (M > 1)
+static int64_t frobg_plen(int order, int64_t n) { return (int64_t)order * n + order + 2; }
+size_t cb200_frobenius_general_workspace_bytes(int L, int order, int degree, int M, int64_t n, int64_t batch) {
+    return carve_bytes(L, (int64_t)(degree + 3) * frobg_plen(order, n) + FROBG_NTMP + M, 2 * batch);
+}
+int cb200_frobenius_general_batch_dev(int L_, int order, int degree, int valuation, int64_t n, int64_t batch,
+                                      const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
+                                      const uint32_t* rho_mant, const cb_meta* rho_meta, int shared_rho, int mul,
+                                      int M, uint32_t* gens_mant, cb_meta* gens_meta, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+    if (!supported_L(L_) || order < 1 || degree < 1 || degree > FROBG_MAXD || batch < 0 || n < 0 || M < 1 ||
+        M > FROBG_MAXM || mul < 1 || mul > M)
+        return CB200_EINVAL;
+    if (workspace_bytes < cb200_frobenius_general_workspace_bytes(L_, order, degree, M, n, batch)) return CB200_ENOMEM;
+    FrobGenParams p;
+    p.order = order;
+    p.degree = degree;
+    p.valuation = valuation;
+    p.M = M;
+    p.mul = mul;
+    p.n = n;
+    p.batch = batch;
+    p.plen = frobg_plen(order, n);
+    p.ode = CArr{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta),
+                 shared_ode ? (size_t)2 : (size_t)(2 * batch)};
+    p.rho = CArr{const_cast<uint32_t*>(rho_mant), (Meta*)const_cast<cb_meta*>(rho_meta),
+                 shared_rho ? (size_t)2 : (size_t)(2 * batch)};
+    p.gens = CArr{gens_mant, (Meta*)gens_meta, (size_t)(2 * batch)};
+    char* w = (char*)workspace;
+    p.wp = carve(w, L_, (int64_t)(degree + 3) * p.plen + FROBG_NTMP + M, 2 * batch);
+    g_launches.fetch_add(batch > 0);
+    return table_for(L_)->frobenius_general(p, (cudaStream_t)stream);
+}
+
+size_t cb200_solution_op_workspace_bytes(int L, int M, int64_t batch) {
+    return carve_bytes(L, FROBG_NTMP + (M > 0 ? M : 0), 2 * batch);
+}
+int cb200_solution_op_dev(int which, int L_, int64_t batch, int mul, int M, int64_t cap, int64_t nu,
+                          const uint32_t* rho_mant, const cb_meta* rho_meta, uint32_t* gens_mant, cb_meta* gens_meta,
+                          uint32_t* f_mant, cb_meta* f_meta, int64_t fcap, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+    if (!supported_L(L_) || batch < 0 || M < 0 || M > FROBG_MAXM || cap < 0 || fcap < 0) return CB200_EINVAL;
+    if (which != CB200_SOL_EXTEND && which != CB200_SOL_UPDATE && which != CB200_SOL_NORMALIZE) return CB200_EINVAL;
+    if (which == CB200_SOL_EXTEND && (nu < 0 || nu >= cap)) return CB200_EINVAL;
+    if (which == CB200_SOL_NORMALIZE && (mul < 1 || mul > M)) return CB200_EINVAL;
+    if (workspace_bytes < cb200_solution_op_workspace_bytes(L_, M, batch)) return CB200_ENOMEM;
+    SolOpParams p;
+    p.which = which;
+    p.M = M;
+    p.mul = mul;
+    p.batch = batch;
+    p.cap = cap;
+    p.fcap = which == CB200_SOL_NORMALIZE ? 0 : fcap;
+    p.nu = nu;
+    p.rho = CArr{const_cast<uint32_t*>(rho_mant), (Meta*)const_cast<cb_meta*>(rho_meta), (size_t)(2 * batch)};
+    p.gens = CArr{gens_mant, (Meta*)gens_meta, (size_t)(2 * batch)};
+    p.f = CArr{f_mant, (Meta*)f_meta, (size_t)(2 * batch)};
+    char* w = (char*)workspace;
+    p.wp = carve(w, L_, FROBG_NTMP + M, 2 * batch);
+    g_launches.fetch_add(batch > 0);
+    return table_for(L_)->solution_op(p, (cudaStream_t)stream);
+}
+
+int cb200_indicial_polynomial_dev(int L_, int order, int degree, int valuation, int64_t batch,
+                                  const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode, int64_t nu,
+                                  int64_t shift, uint32_t* out_mant, cb_meta* out_meta, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+    if (!supported_L(L_) || order < 1 || degree < 0 || batch < 0) return CB200_EINVAL;
+    if (workspace_bytes < cb200_solution_op_workspace_bytes(L_, 0, batch)) return CB200_ENOMEM;
+    IndicialParams p;
+    p.order = order;
+    p.degree = degree;
+    p.valuation = valuation;
+    p.batch = batch;
+    p.nu = nu;
+    p.shift = shift;
+    p.ode = CArr{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta),
+                 shared_ode ? (size_t)2 : (size_t)(2 * batch)};
+    p.out = CArr{out_mant, (Meta*)out_meta, (size_t)(2 * batch)};
+    char* w = (char*)workspace;
+    p.wp = carve(w, L_, FROBG_NTMP, 2 * batch);
+    g_launches.fetch_add(batch > 0);
+    return table_for(L_)->indicial_poly(p, (cudaStream_t)stream);
+}
+
 int cb200_horner_batch_dev(int L_, int64_t len, int64_t npts, int nder, const uint32_t* f_mant,
                            const cb_meta* f_meta, int shared_f, const uint32_t* pts_mant,
                            const cb_meta* pts_meta, uint32_t* out_mant, cb_meta* out_meta,
@@ -404,6 +489,97 @@ int cb200_frobenius1_batch_host(int L, int order, int degree, int valuation, int
     if (rc) return rc;
     CK(cudaMemcpy(res_mant, rm.p, arr_mant_bytes(L, n + 1, S), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(res_meta, rt.p, arr_meta_bytes(n + 1, S), cudaMemcpyDeviceToHost));
+    return (int)cudaDeviceSynchronize();
+}
+
+int cb200_frobenius_general_batch_host(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
+                                       const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
+                                       const uint32_t* rho_mant, const cb_meta* rho_meta, int shared_rho, int mul,
+                                       int M, uint32_t* gens_mant, cb_meta* gens_meta, int device) {
+    if (!supported_L(L) || order < 1 || degree < 1 || degree > FROBG_MAXD || batch < 0 || n < 0 || M < 1 ||
+        M > FROBG_MAXM || mul < 1 || mul > M)
+        return CB200_EINVAL;
+    CK(cudaSetDevice(device));
+    int64_t So = shared_ode ? 2 : 2 * batch, Sr = shared_rho ? 2 : 2 * batch, S = 2 * batch;
+    int64_t ne = (int64_t)(order + 1) * (degree + 1), ng = (int64_t)M * (n + 1);
+    DevBuf om, ot, pm, pt, gm, gt, ws;
+    size_t wsb = cb200_frobenius_general_workspace_bytes(L, order, degree, M, n, batch);
+    CK(om.alloc(arr_mant_bytes(L, ne, So)));
+    CK(ot.alloc(arr_meta_bytes(ne, So)));
+    CK(pm.alloc(arr_mant_bytes(L, 1, Sr)));
+    CK(pt.alloc(arr_meta_bytes(1, Sr)));
+    CK(gm.alloc(arr_mant_bytes(L, ng, S)));
+    CK(gt.alloc(arr_meta_bytes(ng, S)));
+    CK(ws.alloc(wsb));
+    CK(cudaMemcpy(om.p, ode_mant, arr_mant_bytes(L, ne, So), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ot.p, ode_meta, arr_meta_bytes(ne, So), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pm.p, rho_mant, arr_mant_bytes(L, 1, Sr), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pt.p, rho_meta, arr_meta_bytes(1, Sr), cudaMemcpyHostToDevice));
+    int rc = cb200_frobenius_general_batch_dev(L, order, degree, valuation, n, batch, (uint32_t*)om.p, (cb_meta*)ot.p,
+                                               shared_ode, (uint32_t*)pm.p, (cb_meta*)pt.p, shared_rho, mul, M,
+                                               (uint32_t*)gm.p, (cb_meta*)gt.p, ws.p, wsb, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(gens_mant, gm.p, arr_mant_bytes(L, ng, S), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(gens_meta, gt.p, arr_meta_bytes(ng, S), cudaMemcpyDeviceToHost));
+    return (int)cudaDeviceSynchronize();
+}
+
+int cb200_solution_op_host(int which, int L, int64_t batch, int mul, int M, int64_t cap, int64_t nu,
+                           const uint32_t* rho_mant, const cb_meta* rho_meta, uint32_t* gens_mant, cb_meta* gens_meta,
+                           uint32_t* f_mant, cb_meta* f_meta, int64_t fcap, int device) {
+    if (!supported_L(L) || batch < 0 || M < 0 || M > FROBG_MAXM || cap < 0 || fcap < 0) return CB200_EINVAL;
+    CK(cudaSetDevice(device));
+    int64_t S = 2 * batch, ng = (int64_t)M * cap;
+    bool hasf = which != CB200_SOL_NORMALIZE;
+    DevBuf pm, pt, gm, gt, fm, ft, ws;
+    size_t wsb = cb200_solution_op_workspace_bytes(L, M, batch);
+    CK(pm.alloc(arr_mant_bytes(L, 1, S)));
+    CK(pt.alloc(arr_meta_bytes(1, S)));
+    CK(gm.alloc(arr_mant_bytes(L, ng, S)));
+    CK(gt.alloc(arr_meta_bytes(ng, S)));
+    CK(fm.alloc(arr_mant_bytes(L, hasf ? fcap : 0, S)));
+    CK(ft.alloc(arr_meta_bytes(hasf ? fcap : 0, S)));
+    CK(ws.alloc(wsb));
+    CK(cudaMemcpy(pm.p, rho_mant, arr_mant_bytes(L, 1, S), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pt.p, rho_meta, arr_meta_bytes(1, S), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(gm.p, gens_mant, arr_mant_bytes(L, ng, S), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(gt.p, gens_meta, arr_meta_bytes(ng, S), cudaMemcpyHostToDevice));
+    if (hasf) {
+        CK(cudaMemcpy(fm.p, f_mant, arr_mant_bytes(L, fcap, S), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ft.p, f_meta, arr_meta_bytes(fcap, S), cudaMemcpyHostToDevice));
+    }
+    int rc = cb200_solution_op_dev(which, L, batch, mul, M, cap, nu, (uint32_t*)pm.p, (cb_meta*)pt.p, (uint32_t*)gm.p,
+                                   (cb_meta*)gt.p, (uint32_t*)fm.p, (cb_meta*)ft.p, fcap, ws.p, wsb, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(gens_mant, gm.p, arr_mant_bytes(L, ng, S), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(gens_meta, gt.p, arr_meta_bytes(ng, S), cudaMemcpyDeviceToHost));
+    if (hasf) {
+        CK(cudaMemcpy(f_mant, fm.p, arr_mant_bytes(L, fcap, S), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(f_meta, ft.p, arr_meta_bytes(fcap, S), cudaMemcpyDeviceToHost));
+    }
+    return (int)cudaDeviceSynchronize();
+}
+
+int cb200_indicial_polynomial_host(int L, int order, int degree, int valuation, int64_t batch,
+                                   const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode, int64_t nu,
+                                   int64_t shift, uint32_t* out_mant, cb_meta* out_meta, int device) {
+    if (!supported_L(L) || order < 1 || degree < 0 || batch < 0) return CB200_EINVAL;
+    CK(cudaSetDevice(device));
+    int64_t So = shared_ode ? 2 : 2 * batch, S = 2 * batch, ne = (int64_t)(order + 1) * (degree + 1);
+    DevBuf om, ot, rm, rt, ws;
+    size_t wsb = cb200_solution_op_workspace_bytes(L, 0, batch);
+    CK(om.alloc(arr_mant_bytes(L, ne, So)));
+    CK(ot.alloc(arr_meta_bytes(ne, So)));
+    CK(rm.alloc(arr_mant_bytes(L, order + 2, S)));
+    CK(rt.alloc(arr_meta_bytes(order + 2, S)));
+    CK(ws.alloc(wsb));
+    CK(cudaMemcpy(om.p, ode_mant, arr_mant_bytes(L, ne, So), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ot.p, ode_meta, arr_meta_bytes(ne, So), cudaMemcpyHostToDevice));
+    int rc = cb200_indicial_polynomial_dev(L, order, degree, valuation, batch, (uint32_t*)om.p, (cb_meta*)ot.p,
+                                           shared_ode, nu, shift, (uint32_t*)rm.p, (cb_meta*)rt.p, ws.p, wsb, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(out_mant, rm.p, arr_mant_bytes(L, order + 2, S), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out_meta, rt.p, arr_meta_bytes(order + 2, S), cudaMemcpyDeviceToHost));
     return (int)cudaDeviceSynchronize();
 }
 

@@ -57,6 +57,21 @@ __global__ void __launch_bounds__(Cfg<L>::TPB, 1) frobenius1_kernel(FrobParams p
     frobenius1_thread<L>(p, idx, S0, S1);
 }
 template <int L>
+__global__ void __launch_bounds__(Cfg<L>::TPB, 1) frobenius_general_kernel(FrobGenParams p) {
+    CB_KERNEL_PROLOGUE(p.batch)
+    frobenius_general_thread<L>(p, idx, S0, S1);
+}
+template <int L>
+__global__ void __launch_bounds__(Cfg<L>::TPB, 1) solution_op_kernel(SolOpParams p) {
+    CB_KERNEL_PROLOGUE(p.batch)
+    solution_op_thread<L>(p, idx, S0, S1);
+}
+template <int L>
+__global__ void __launch_bounds__(Cfg<L>::TPB, 1) indicial_poly_kernel(IndicialParams p) {
+    CB_KERNEL_PROLOGUE(p.batch)
+    indicial_poly_thread<L>(p, idx, S0, S1);
+}
+template <int L>
 __global__ void __launch_bounds__(Cfg<L>::TPB, 1) horner_kernel(HornerParams p) {
     CB_KERNEL_PROLOGUE(p.npts)
     horner_thread<L>(p, idx, S0, S1);
@@ -135,6 +150,9 @@ struct LaunchTable {
     int (*fuchs_table)(const FuchsTableParams&, cudaStream_t);
     int (*fuchs_shared)(const FuchsSharedParams&, cudaStream_t);
     int (*fuchs_intop)(const FuchsIntParams&, cudaStream_t);
+    int (*frobenius_general)(const FrobGenParams&, cudaStream_t);
+    int (*solution_op)(const SolOpParams&, cudaStream_t);
+    int (*indicial_poly)(const IndicialParams&, cudaStream_t);
 };
 
 #define CB_DEFINE_LAUNCH_TABLE(LL)                                                                         \
@@ -159,7 +177,11 @@ struct LaunchTable {
         return launch<LL>(fuchs_intop_kernel<LL>, p, p.batch, s, IntopCfg<LL>::TPB,                          \
                           (size_t)(LL + 3 + 3 * (LL + 2)) * IntopCfg<LL>::TPB * sizeof(uint32_t));           \
     }                                                                                                      \
-    extern const LaunchTable launch_table_L##LL = {fuchs_##LL, frob_##LL, horner_##LL, ew_##LL, ftab_##LL, fsh_##LL, fint_##LL}; \
+    static int frobg_##LL(const FrobGenParams& p, cudaStream_t s) { return launch<LL>(frobenius_general_kernel<LL>, p, p.batch, s); } \
+    static int solop_##LL(const SolOpParams& p, cudaStream_t s) { return launch<LL>(solution_op_kernel<LL>, p, p.batch, s); } \
+    static int indp_##LL(const IndicialParams& p, cudaStream_t s) { return launch<LL>(indicial_poly_kernel<LL>, p, p.batch, s); } \
+    extern const LaunchTable launch_table_L##LL = {fuchs_##LL, frob_##LL, horner_##LL, ew_##LL, ftab_##LL, fsh_##LL, fint_##LL, \
+                                                   frobg_##LL, solop_##LL, indp_##LL};                     \
     }
 
 extern const LaunchTable launch_table_L4, launch_table_L32, launch_table_L64, launch_table_L128;

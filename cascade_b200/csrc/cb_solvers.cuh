@@ -538,8 +538,8 @@ struct FrobParams {
 constexpr int FROB_NTMP = 6;
 
 // result may be one of (o1, o2): returns which holds f_nu(rho + shift)
-template <int L, class SCR>
-CB_HD CRef indicial_eval(const FrobParams& p, size_t oslot, int64_t nu, const CRef& rho, int64_t shift,
+template <int L, class SCR, class PRM>
+CB_HD CRef indicial_eval(const PRM& p, size_t oslot, int64_t nu, const CRef& rho, int64_t shift,
                          CRef o1, CRef o2, const CRef& t, const CRef& kb, SCR S0, SCR S1) {
     const int D1 = p.degree + 1;
     nu += p.valuation;
@@ -583,6 +583,432 @@ CB_HD void frobenius1_thread(const FrobParams& p, int64_t inst, SCR S0, SCR S1) 
         CRef spare = (ind.m == o1.m) ? o2 : o1;
         acb_div<L>(at<L>(p.res, nu, slot), gnew, ind, spare, S0, S1);
     }
+}
+
+// ================================================================ Frobenius, general (M > 1)
+// acb_ode_solve_frobenius for M = mul + alpha > 1 (reference src/frobenius_solver.c:131-205):
+// the recurrence carried as polynomials in rho, with indicial_polynomial (:4-39) and the solution
+// bookkeeping _acb_ode_solution_update / _extend / _normalize (src/acb_ode_solution.c:60-123).
+// One thread per instance; every polynomial in rho is a run of `plen` entries of the workspace
+// array plus a length held by the thread, with Arb's conventions: the length is normalised
+// (trailing EXACT zeros stripped) wherever Arb normalises, and reads beyond it give zero.
+// The Arb sub-algorithms behind acb_poly_* are the ones restated in oracle/cbo_cascade.c
+// (classical product, longer operand first; Horner evaluation; coefficientwise scalar ops).
+constexpr int FROBG_MAXM = 16, FROBG_MAXD = 8;
+constexpr int FROBG_NTMP = 6;  // t1, t2, kb, inv, tmp, f0
+struct FrobGenParams {
+    int order, degree, valuation, M, mul;
+    int64_t n, batch;
+    int64_t plen;  // capacity of a polynomial in rho: order * n + order + 2
+    CArr ode;      // S = 2*batch or 2
+    CArr rho;      // 1 entry, S = 2*batch or 2
+    CArr gens;     // M * (n + 1) entries (gens[i][j] at i * (n + 1) + j), S = 2*batch: all written
+    CArr wp;       // (degree + 3) * plen + FROBG_NTMP + M entries, S = 2*batch
+};
+
+CB_HD bool acb_is_exact_zero(const CRef& x) { return is_exact_zero(ld_meta(x.t)) && is_exact_zero(ld_meta(x.t + 1)); }
+// exact |mid| <= rad (arb_contains_zero); an indeterminate ball contains everything
+template <int L>
+CB_HD bool arb_contains_zero(const uint32_t* m, size_t stride, const Meta& t) {
+    if (t.flags & (F_NAN | F_ZERO)) return true;
+    if (t.rman == 0) return false;
+    if (t.exp != t.rexp) return t.exp < t.rexp;
+    uint32_t top = m[(size_t)(L - 1) * stride];
+    if ((top >> 2) != t.rman) return (top >> 2) < t.rman;
+    if (top & 3u) return false;
+    for (int k = 0; k < L - 1; k++)
+        if (m[(size_t)k * stride]) return false;
+    return true;
+}
+template <int L>
+CB_HD bool acb_contains_zero(const CRef& x) {
+    return arb_contains_zero<L>(x.m, x.stride, ld_meta(x.t)) && arb_contains_zero<L>(x.m + 1, x.stride, ld_meta(x.t + 1));
+}
+CB_HD void acb_neg_inplace(const CRef& z) {
+    for (int part = 0; part < 2; part++) {
+        Meta t = ld_meta(z.t + part);
+        if (!(t.flags & (F_ZERO | F_NAN))) {
+            t.flags ^= F_SIGN;
+            st_meta(z.t + part, t);
+        }
+    }
+}
+// z = x / k for an integer k (acb_div_si as acb_div by the exact ball k); z may alias x
+template <int L, class SCR>
+CB_HD void acb_div_si(const CRef& z, const CRef& x, int64_t k, SCR S0) {
+    uint64_t ka = k < 0 ? (uint64_t)0 - (uint64_t)k : (uint64_t)k;
+    Meta tr = arb_div_u64<L>(wre(z), re_of(x), ka, k < 0, S0);
+    Meta ti = arb_div_u64<L>(wim(z), im_of(x), ka, k < 0, S0);
+    st_meta(z.t, tr);
+    st_meta(z.t + 1, ti);
+}
+
+// the polynomial workspace of one instance
+template <int L, class SCR>
+struct PolyCtx {
+    CArr A;
+    size_t slot;
+    SCR S0, S1;
+    CRef t1, t2, kb, inv, tmp;
+    CB_HD CRef c(int64_t e0, int64_t j) const { return at<L>(A, e0 + j, slot); }
+    CB_HD int64_t norm(int64_t e0, int64_t len) const {
+        while (len > 0 && acb_is_exact_zero(c(e0, len - 1))) len--;
+        return len;
+    }
+};
+
+// acb_poly_mul(dst, a, b), dst distinct from both; returns the normalised length
+template <int L, class SCR>
+CB_HD int64_t poly_mul(const PolyCtx<L, SCR>& pc, int64_t eD, int64_t eA, int64_t la, int64_t eB, int64_t lb) {
+    if (la == 0 || lb == 0) return 0;
+    if (la < lb) {
+        int64_t t = eA; eA = eB; eB = t;
+        t = la; la = lb; lb = t;
+    }
+#pragma unroll 1
+    for (int64_t i = 0; i < la; i++) acb_mul<L>(pc.c(eD, i), pc.c(eA, i), pc.c(eB, 0), pc.S0, pc.S1);
+#pragma unroll 1
+    for (int64_t j = 1; j < lb; j++) acb_mul<L>(pc.c(eD, la - 1 + j), pc.c(eA, la - 1), pc.c(eB, j), pc.S0, pc.S1);
+#pragma unroll 1
+    for (int64_t i = 0; i < la - 1; i++)
+#pragma unroll 1
+        for (int64_t j = 1; j < lb; j++) {
+            acb_mul<L>(pc.tmp, pc.c(eA, i), pc.c(eB, j), pc.S0, pc.S1);
+            acb_addsub<L>(pc.c(eD, i + j), pc.c(eD, i + j), pc.tmp, false, pc.S0, pc.S1);
+        }
+    return pc.norm(eD, la + lb - 1);
+}
+// a -= b in place (acb_poly_sub(a, a, b)); returns the new length of a
+template <int L, class SCR>
+CB_HD int64_t poly_sub_inplace(const PolyCtx<L, SCR>& pc, int64_t eA, int64_t la, int64_t eB, int64_t lb) {
+    int64_t mn = la < lb ? la : lb, mx = la < lb ? lb : la;
+#pragma unroll 1
+    for (int64_t i = 0; i < mn; i++) acb_addsub<L>(pc.c(eA, i), pc.c(eA, i), pc.c(eB, i), true, pc.S0, pc.S1);
+#pragma unroll 1
+    for (int64_t i = mn; i < lb; i++) {
+        acb_set<L>(pc.c(eA, i), pc.c(eB, i));
+        acb_neg_inplace(pc.c(eA, i));
+    }
+    return pc.norm(eA, mx);
+}
+// p /= y coefficientwise (acb_poly_scalar_div): acb_div(x, y) is x * acb_inv(y) for a complex y and
+// the inverse is the same ball every time, so it is formed once
+template <int L, class SCR>
+CB_HD int64_t poly_scalar_div(const PolyCtx<L, SCR>& pc, int64_t e0, int64_t len, const CRef& y) {
+    if (len == 0) return 0;
+    bool real = is_exact_zero(ld_meta(y.t + 1));
+    if (!real) acb_inv<L>(pc.inv, y, pc.t1, pc.S0, pc.S1);
+#pragma unroll 1
+    for (int64_t i = 0; i < len; i++) {
+        CRef x = pc.c(e0, i);
+        if (real) {
+            Opd c = re_of(y);
+            Meta tr = arb_div<L>(wre(pc.t1), re_of(x), c, pc.S0, pc.S1);
+            Meta ti = arb_div<L>(wim(pc.t1), im_of(x), c, pc.S0, pc.S1);
+            st_meta(pc.t1.t, tr);
+            st_meta(pc.t1.t + 1, ti);
+        } else {
+            acb_mul<L>(pc.t1, x, pc.inv, pc.S0, pc.S1);
+        }
+        acb_set<L>(x, pc.t1);
+    }
+    return pc.norm(e0, len);
+}
+// p *= y coefficientwise (acb_poly_scalar_mul), in place
+template <int L, class SCR>
+CB_HD int64_t poly_scalar_mul(const PolyCtx<L, SCR>& pc, const CArr& A, int64_t e0, int64_t len, const CRef& y) {
+#pragma unroll 1
+    for (int64_t i = 0; i < len; i++) {
+        CRef x = at<L>(A, e0 + i, pc.slot);
+        acb_mul<L>(pc.t1, x, y, pc.S0, pc.S1);
+        acb_set<L>(x, pc.t1);
+    }
+    while (len > 0 && acb_is_exact_zero(at<L>(A, e0 + len - 1, pc.slot))) len--;
+    return len;
+}
+// out = p(x) (acb_poly_evaluate -> Horner; out must not be t1)
+template <int L, class SCR>
+CB_HD void poly_eval(const PolyCtx<L, SCR>& pc, const CRef& out, int64_t e0, int64_t len, const CRef& x) {
+    if (len == 0) {
+        acb_zero<L>(out);
+        return;
+    }
+    acb_set<L>(out, pc.c(e0, len - 1));
+    if (len == 1 || acb_is_exact_zero(x)) {
+        if (len > 1) acb_set<L>(out, pc.c(e0, 0));
+        return;
+    }
+#pragma unroll 1
+    for (int64_t j = len - 2; j >= 0; j--) {
+        acb_mul<L>(pc.t1, out, x, pc.S0, pc.S1);
+        acb_addsub<L>(out, pc.t1, pc.c(e0, j), false, pc.S0, pc.S1);
+    }
+}
+// p = p' in place (acb_poly_derivative); returns the new length
+template <int L, class SCR>
+CB_HD int64_t poly_derivative(const PolyCtx<L, SCR>& pc, int64_t e0, int64_t len) {
+#pragma unroll 1
+    for (int64_t i = 1; i < len; i++) acb_mul_si<L>(pc.c(e0, i - 1), pc.c(e0, i), i, pc.S0);
+    return pc.norm(e0, len > 0 ? len - 1 : 0);
+}
+// indicial_polynomial (src/frobenius_solver.c:4-39) into the run at eR; returns its length
+template <int L, class SCR, class PRM>
+CB_HD int64_t indicial_poly(const PolyCtx<L, SCR>& pc, const PRM& p, size_t oslot, int64_t eR, int64_t nu, int64_t shift) {
+    const int D1 = p.degree + 1;
+    int64_t len = 0;
+    nu += p.valuation;
+    if (nu > p.degree) return 0;
+    // entries at and beyond the length are kept as exact zeros, so "reads as zero" is a plain read
+    for (int j = 0; j <= p.order + 1; j++) acb_zero<L>(pc.c(eR, j));
+#pragma unroll 1
+    for (int64_t lam = clampi(p.degree - nu, 0, p.order); lam >= 0; lam--) {
+#pragma unroll 1
+        for (int64_t j = len; j > 0; j--) {
+            // result[j] = result[j-1] + result[j] * (shift - lam)
+            acb_mul_si<L>(pc.t1, pc.c(eR, j), shift - lam, pc.S0);
+            acb_addsub<L>(pc.c(eR, j), pc.c(eR, j - 1), pc.t1, false, pc.S0, pc.S1);
+            if (j + 1 > len) len = j + 1;
+            len = pc.norm(eR, len);
+        }
+        CRef r0 = pc.c(eR, 0);
+        acb_mul_si<L>(r0, r0, shift - lam, pc.S0);
+        if (lam + nu >= 0) acb_addsub<L>(r0, r0, at<L>(p.ode, lam * D1 + (lam + nu), oslot), false, pc.S0, pc.S1);
+        if (len == 0) len = 1;
+        len = pc.norm(eR, len);
+    }
+    return len;
+}
+
+// the solution bookkeeping of one instance: gens[i] is the run i*cap .. i*cap+cap-1 of G
+template <int L, class SCR>
+struct SolCtx {
+    CArr G;
+    int64_t cap;
+    int M, mul;
+    CRef rho;
+    int64_t glen[FROBG_MAXM];
+    CB_HD CRef g(const PolyCtx<L, SCR>& pc, int i, int64_t j) const { return at<L>(G, (int64_t)i * cap + j, pc.slot); }
+};
+// _acb_ode_solution_extend (src/acb_ode_solution.c:97-109): consumes the polynomial at eG
+template <int L, class SCR>
+CB_HD void solution_extend(const PolyCtx<L, SCR>& pc, SolCtx<L, SCR>& sc, int64_t nu, int64_t eG, int64_t lenG) {
+#pragma unroll 1
+    for (int i = 0; i < sc.M; i++) {
+        poly_eval<L>(pc, pc.t2, eG, lenG, sc.rho);
+        // acb_poly_set_coeff_acb(gens + i, nu, t2)
+        bool z = acb_is_exact_zero(pc.t2);
+        if (nu < sc.glen[i] || !z) {
+            acb_set<L>(sc.g(pc, i, nu), pc.t2);
+            if (nu + 1 > sc.glen[i]) sc.glen[i] = nu + 1;
+            while (sc.glen[i] > 0 && acb_is_exact_zero(sc.g(pc, i, sc.glen[i] - 1))) sc.glen[i]--;
+        }
+        lenG = poly_derivative<L>(pc, eG, lenG);
+    }
+}
+// _acb_ode_solution_update (:60-95), second half: the Leibniz combination with F[k] = C(M-1,k) f^(k)(rho)
+// held in the M balls at eFs of pc.A
+template <int L, class SCR>
+CB_HD void solution_update_apply(const PolyCtx<L, SCR>& pc, SolCtx<L, SCR>& sc, int64_t eFs) {
+#pragma unroll 1
+    for (int n = sc.M - 1; n >= 0; n--) {
+        sc.glen[n] = poly_scalar_mul<L>(pc, sc.G, (int64_t)n * sc.cap, sc.glen[n], pc.c(eFs, 0));
+#pragma unroll 1
+        for (int k = 1; k <= n; k++) {
+            CRef Fk = pc.c(eFs, k);
+            // f = gens[n-k] * F[k]; gens[n] += f  (coefficientwise, so fused per coefficient)
+            int64_t lf = sc.glen[n - k], lg = sc.glen[n];
+            // (f's trailing coefficients that come out exactly zero are not part of f; adding an
+            // exact zero leaves gens[n] unchanged, so only the length bookkeeping sees the difference)
+            int64_t top = -1;
+#pragma unroll 1
+            for (int64_t j = 0; j < lf; j++) {
+                acb_mul<L>(pc.t1, sc.g(pc, n - k, j), Fk, pc.S0, pc.S1);
+                bool fz = acb_is_exact_zero(pc.t1);
+                if (!fz) top = j;
+                if (j < lg) {
+                    acb_addsub<L>(sc.g(pc, n, j), sc.g(pc, n, j), pc.t1, false, pc.S0, pc.S1);
+                } else {
+                    acb_set<L>(sc.g(pc, n, j), pc.t1);
+                }
+            }
+            int64_t lfn = top + 1;
+            int64_t mx = lg > lfn ? lg : lfn;
+            while (mx > 0 && acb_is_exact_zero(sc.g(pc, n, mx - 1))) mx--;
+            sc.glen[n] = mx;
+            acb_mul_si<L>(Fk, Fk, n - k, pc.S0);
+            acb_div_si<L>(Fk, Fk, n, pc.S0);
+        }
+    }
+}
+// _acb_ode_solution_update (:60-95): consumes the polynomial at eF; F: M scratch balls at eFs
+template <int L, class SCR>
+CB_HD void solution_update(const PolyCtx<L, SCR>& pc, SolCtx<L, SCR>& sc, int64_t eF, int64_t lenF, int64_t eFs) {
+    int64_t binom = 1;
+#pragma unroll 1
+    for (int k = 0; k < sc.M; k++) {
+        CRef Fk = pc.c(eFs, k);
+        poly_eval<L>(pc, Fk, eF, lenF, sc.rho);
+        lenF = poly_derivative<L>(pc, eF, lenF);
+        acb_mul_si<L>(Fk, Fk, binom, pc.S0);
+        binom = (binom * (sc.M - 1 - k)) / (k + 1);
+    }
+    solution_update_apply<L>(pc, sc, eFs);
+}
+// _acb_ode_solution_normalize (:111-123)
+template <int L, class SCR>
+CB_HD void solution_normalize(const PolyCtx<L, SCR>& pc, SolCtx<L, SCR>& sc) {
+    int alpha = sc.M - sc.mul;
+    if (sc.glen[alpha] > 0) acb_set<L>(pc.t2, sc.g(pc, alpha, 0));
+    else acb_zero<L>(pc.t2);
+    PolyCtx<L, SCR> gc = pc;
+    gc.A = sc.G;
+#pragma unroll 1
+    for (int i = 0; i < sc.M; i++) sc.glen[i] = poly_scalar_div<L>(gc, (int64_t)i * sc.cap, sc.glen[i], pc.t2);
+}
+
+template <int L, class SCR>
+CB_HD void frobenius_general_thread(const FrobGenParams& p, int64_t inst, SCR S0, SCR S1) {
+    const size_t slot = 2 * (size_t)inst;
+    const size_t oslot = (p.ode.S == 2) ? 0 : slot;
+    const int d = p.degree;
+    const int64_t tb = (int64_t)(d + 3) * p.plen;  // first temporary
+    PolyCtx<L, SCR> pc{p.wp, slot, S0, S1, at<L>(p.wp, tb + 0, slot), at<L>(p.wp, tb + 1, slot),
+                       at<L>(p.wp, tb + 2, slot), at<L>(p.wp, tb + 3, slot), at<L>(p.wp, tb + 4, slot)};
+    CRef f0 = at<L>(p.wp, tb + 5, slot);
+    const int64_t eFs = tb + FROBG_NTMP;
+    SolCtx<L, SCR> sc;
+    sc.G = p.gens;
+    sc.cap = p.n + 1;
+    sc.M = p.M;
+    sc.mul = p.mul;
+    sc.rho = at<L>(p.rho, 0, (p.rho.S == 2) ? 0 : slot);
+    int64_t eInd = 0, eNew = p.plen, eProd = 2 * p.plen, lInd = 0, lNew = 0;
+    int64_t eRho[FROBG_MAXD], lRho[FROBG_MAXD];
+    for (int i = 0; i < d; i++) {
+        eRho[i] = (int64_t)(3 + i) * p.plen;
+        lRho[i] = 0;
+    }
+    acb_one<L>(pc.c(eRho[0], 0));
+    lRho[0] = 1;
+    for (int i = 0; i < p.M; i++) {
+        sc.glen[i] = 0;
+#pragma unroll 1
+        for (int64_t j = 0; j <= p.n; j++) acb_zero<L>(sc.g(pc, i, j));
+    }
+    acb_one<L>(sc.g(pc, 0, 0));
+    sc.glen[0] = 1;
+#pragma unroll 1
+    for (int64_t nu = 1; nu <= p.n; nu++) {
+        int64_t i = clampi(nu, 1, d);
+        lInd = indicial_poly<L>(pc, p, oslot, eInd, i, nu - i);
+#pragma unroll 1
+        do {
+            int64_t lp = poly_mul<L>(pc, eProd, eInd, lInd, eRho[i - 1], lRho[i - 1]);
+            {  // acb_poly_mul(indicial, indicial, ...) lands in indicial
+                int64_t t = eInd; eInd = eProd; eProd = t;
+                lInd = lp;
+            }
+            lNew = poly_sub_inplace<L>(pc, eNew, lNew, eInd, lInd);
+            i--;
+            lInd = indicial_poly<L>(pc, p, oslot, eInd, i, nu - i);
+        } while (i > 0);
+        // rescale by f_0(rho + nu) (:170-176)
+        {
+            CRef o1 = pc.t2, o2 = pc.tmp;
+            CRef r = indicial_eval<L>(p, oslot, 0, sc.rho, nu, o1, o2, pc.t1, pc.kb, S0, S1);
+            acb_set<L>(f0, r);
+        }
+        if (!acb_contains_zero<L>(f0)) {
+            lInd = poly_scalar_div<L>(pc, eInd, lInd, f0);
+            lNew = poly_scalar_div<L>(pc, eNew, lNew, f0);
+        }
+        bool all_zero = lNew == 0;
+#pragma unroll 1
+        for (int k = d - 1; k > 0; k--) {
+            lRho[k] = poly_mul<L>(pc, eRho[k], eRho[k - 1], lRho[k - 1], eInd, lInd);
+            all_zero = all_zero && lRho[k] == 0;
+        }
+#pragma unroll 1
+        for (int64_t j = 0; j < lNew; j++) acb_set<L>(pc.c(eRho[0], j), pc.c(eNew, j));
+        lRho[0] = lNew;
+        solution_update<L>(pc, sc, eInd, lInd, eFs);
+        lInd = 0;
+        solution_extend<L>(pc, sc, nu, eNew, lNew);
+        lNew = 0;
+        if (all_zero) break;
+    }
+    solution_normalize<L>(pc, sc);
+}
+
+// ---- the bookkeeping steps and indicial_polynomial as entry points of their own (the reference
+// exports them: src/acb_ode.h:58-60, src/cascade.h:22).  Polynomials cross the interface as
+// fixed-capacity coefficient arrays; their length is implied (trailing exact zeros do not count).
+enum { SOLOP_EXTEND = 0, SOLOP_UPDATE = 1, SOLOP_NORMALIZE = 2 };
+struct SolOpParams {
+    int which, M, mul;
+    int64_t batch, cap, fcap, nu;
+    CArr rho;   // 1 entry, S = 2*batch or 2
+    CArr gens;  // M * cap entries, S = 2*batch, in/out
+    CArr f;     // fcap entries, S = 2*batch, in/out (consumed: comes back zero)
+    CArr wp;    // FROBG_NTMP + M entries, S = 2*batch
+};
+template <int L, class SCR>
+CB_HD void solution_op_thread(const SolOpParams& p, int64_t inst, SCR S0, SCR S1) {
+    const size_t slot = 2 * (size_t)inst;
+    PolyCtx<L, SCR> pc{p.f, slot, S0, S1, at<L>(p.wp, 0, slot), at<L>(p.wp, 1, slot), at<L>(p.wp, 2, slot),
+                       at<L>(p.wp, 3, slot), at<L>(p.wp, 4, slot)};
+    SolCtx<L, SCR> sc;
+    sc.G = p.gens;
+    sc.cap = p.cap;
+    sc.M = p.M;
+    sc.mul = p.mul;
+    sc.rho = at<L>(p.rho, 0, (p.rho.S == 2) ? 0 : slot);
+    for (int i = 0; i < p.M; i++) {
+        int64_t len = p.cap;
+        while (len > 0 && acb_is_exact_zero(sc.g(pc, i, len - 1))) len--;
+        sc.glen[i] = len;
+    }
+    int64_t lf = 0;
+    if (p.which != SOLOP_NORMALIZE) lf = pc.norm(0, p.fcap);
+    if (p.which == SOLOP_EXTEND) {
+        solution_extend<L>(pc, sc, p.nu, 0, lf);
+    } else if (p.which == SOLOP_UPDATE) {
+        // F[k] = C(M-1,k) f^(k)(rho) go behind the temporaries of the workspace array
+        int64_t binom = 1;
+#pragma unroll 1
+        for (int k = 0; k < sc.M; k++) {
+            CRef Fk = at<L>(p.wp, FROBG_NTMP + k, slot);
+            poly_eval<L>(pc, Fk, 0, lf, sc.rho);
+            lf = poly_derivative<L>(pc, 0, lf);
+            acb_mul_si<L>(Fk, Fk, binom, S0);
+            binom = (binom * (sc.M - 1 - k)) / (k + 1);
+        }
+        PolyCtx<L, SCR> wc = pc;
+        wc.A = p.wp;
+        solution_update_apply<L>(wc, sc, FROBG_NTMP);
+    } else {
+        solution_normalize<L>(pc, sc);
+    }
+    if (p.which != SOLOP_NORMALIZE) {  // acb_poly_zero(f)
+#pragma unroll 1
+        for (int64_t j = 0; j < p.fcap; j++) acb_zero<L>(pc.c(0, j));
+    }
+}
+
+struct IndicialParams {
+    int order, degree, valuation;
+    int64_t batch, nu, shift;
+    CArr ode;  // S = 2*batch or 2
+    CArr out;  // order + 2 entries, S = 2*batch (the last one is scratch and comes back zero)
+    CArr wp;   // FROBG_NTMP entries
+};
+template <int L, class SCR>
+CB_HD void indicial_poly_thread(const IndicialParams& p, int64_t inst, SCR S0, SCR S1) {
+    const size_t slot = 2 * (size_t)inst;
+    PolyCtx<L, SCR> pc{p.out, slot, S0, S1, at<L>(p.wp, 0, slot), at<L>(p.wp, 1, slot), at<L>(p.wp, 2, slot),
+                       at<L>(p.wp, 3, slot), at<L>(p.wp, 4, slot)};
+    for (int j = 0; j <= p.order + 1; j++) acb_zero<L>(pc.c(0, j));
+    indicial_poly<L>(pc, p, (p.ode.S == 2) ? 0 : slot, 0, p.nu, p.shift);
 }
 
 // ================================================================ Horner

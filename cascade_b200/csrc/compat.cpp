@@ -518,12 +518,87 @@ void _acb_ode_solve_frobenius(acb_poly_t res, acb_ode_t ODE, acb_ode_solution_t 
     poly_normalise(res);
 }
 
+// sol->gens <-> device array [M * cap entries][S = 2]
+static void gens_put(HostArr& h, const acb_ode_solution_struct* sol, slong cap) {
+    for (slong i = 0; i < sol->M; i++)
+        for (slong j = 0; j < cap && j < sol->gens[i].length; j++) h.put((size_t)(i * cap + j), 0, sol->gens[i].coeffs + j);
+}
+static void gens_get(const HostArr& h, acb_ode_solution_struct* sol, slong cap) {
+    for (slong i = 0; i < sol->M; i++) {
+        acb_poly_struct* g = sol->gens + i;
+        acb_poly_zero(g);
+        acb_poly_fit_length(g, cap);
+        for (slong j = 0; j < cap; j++) h.get((size_t)(i * cap + j), 0, g->coeffs + j);
+        g->length = cap;
+        poly_normalise(g);
+    }
+}
+static slong gens_cap(const acb_ode_solution_struct* sol, slong at_least) {
+    slong cap = at_least;
+    for (slong i = 0; i < sol->M; i++)
+        if (sol->gens[i].length > cap) cap = sol->gens[i].length;
+    return cap > 0 ? cap : 1;
+}
+static void solution_op(int which, acb_ode_solution_struct* sol, slong nu, acb_poly_struct* f, slong prec, const char* what) {
+    int L = limbs_of(prec);
+    if (sol->M > 16) die("solution bookkeeping with M > 16", -1);
+    slong cap = gens_cap(sol, which == CB200_SOL_EXTEND ? nu + 1 : 1);
+    slong fcap = (f && f->length > 0) ? f->length : 1;
+    HostArr hg(L, (size_t)(sol->M > 0 ? sol->M * cap : 1), 2), hf(L, (size_t)fcap, 2), hrho(L, 1, 2);
+    gens_put(hg, sol, cap);
+    hrho.put(0, 0, sol->rho);
+    if (f)
+        for (slong j = 0; j < f->length; j++) hf.put((size_t)j, 0, f->coeffs + j);
+    int rc = cb200_solution_op_host(which, L, 1, (int)sol->mul, (int)sol->M, cap, nu, hrho.m.data(), hrho.t.data(),
+                                    hg.m.data(), hg.t.data(), hf.m.data(), hf.t.data(), fcap, 0);
+    if (rc) die(what, rc);
+    gens_get(hg, sol, cap);
+    if (f) acb_poly_zero(f);  // consumed, as in the reference (src/acb_ode_solution.c:93,107)
+}
+void _acb_ode_solution_update(acb_ode_solution_t sol, acb_poly_t f, slong prec) {
+    solution_op(CB200_SOL_UPDATE, sol, 0, f, prec, "_acb_ode_solution_update (cb200_solution_op_host)");
+}
+void _acb_ode_solution_extend(acb_ode_solution_t sol, slong nu, acb_poly_t g_nu, slong prec) {
+    solution_op(CB200_SOL_EXTEND, sol, nu, g_nu, prec, "_acb_ode_solution_extend (cb200_solution_op_host)");
+}
+void _acb_ode_solution_normalize(acb_ode_solution_t sol, slong prec) {
+    solution_op(CB200_SOL_NORMALIZE, sol, 0, nullptr, prec, "_acb_ode_solution_normalize (cb200_solution_op_host)");
+}
+
+void indicial_polynomial(acb_poly_t result, acb_ode_t ODE, slong nu, slong shift, slong prec) {
+    int L = limbs_of(prec);
+    slong v = acb_ode_valuation(ODE);
+    slong ne = (ODE->order + 1) * (ODE->degree + 1), ord = ODE->order;
+    HostArr ho(L, ne, 2), hr(L, ord + 2, 2);
+    for (slong e = 0; e < ne; e++) ho.put(e, 0, ODE->polys + e);
+    int rc = cb200_indicial_polynomial_host(L, (int)ord, (int)ODE->degree, (int)v, 1, ho.m.data(), ho.t.data(), 1, nu, shift,
+                                            hr.m.data(), hr.t.data(), 0);
+    if (rc) die("indicial_polynomial (cb200_indicial_polynomial_host)", rc);
+    acb_poly_zero(result);
+    acb_poly_fit_length(result, ord + 1);
+    for (slong k = 0; k <= ord; k++) hr.get(k, 0, result->coeffs + k);
+    result->length = ord + 1;
+    poly_normalise(result);
+}
+
 void acb_ode_solve_frobenius(acb_ode_solution_t sol, acb_ode_t ODE, slong sol_degree, slong prec) {
     if (sol->M == 1) {
         _acb_ode_solve_frobenius(sol->gens, ODE, sol, sol_degree, prec);
         return;
     }
-    die("acb_ode_solve_frobenius with M > 1 (logarithmic case: listed as next in DESIGN.md)", -1);
+    // M > 1: the polynomial-in-rho recurrence (reference src/frobenius_solver.c:131-205), one launch
+    int L = limbs_of(prec);
+    if (sol->M > 16 || ODE->degree > 8 || ODE->degree < 1) die("acb_ode_solve_frobenius: M > 16 or degree outside 1..8", -1);
+    slong v = acb_ode_valuation(ODE);
+    slong ne = (ODE->order + 1) * (ODE->degree + 1), cap = sol_degree + 1;
+    HostArr ho(L, ne, 2), hrho(L, 1, 2), hg(L, (size_t)(sol->M * cap), 2);
+    for (slong e = 0; e < ne; e++) ho.put(e, 0, ODE->polys + e);
+    hrho.put(0, 0, sol->rho);
+    int rc = cb200_frobenius_general_batch_host(L, (int)ODE->order, (int)ODE->degree, (int)v, sol_degree, 1, ho.m.data(),
+                                                ho.t.data(), 1, hrho.m.data(), hrho.t.data(), 1, (int)sol->mul, (int)sol->M,
+                                                hg.m.data(), hg.t.data(), 0);
+    if (rc) die("acb_ode_solve_frobenius (cb200_frobenius_general_batch_host)", rc);
+    gens_get(hg, sol, cap);
 }
 
 }  // extern "C"

@@ -101,6 +101,56 @@ int cb200_frobenius1_batch_host(int L, int order, int degree, int valuation, int
                                 const uint32_t *rho_mant, const cb_meta *rho_meta, int shared_rho,
                                 uint32_t *res_mant, cb_meta *res_meta, int device);
 
+/* ---- acb_ode_solve_frobenius for M = mul + alpha > 1 (the logarithmic case; reference
+ * src/frobenius_solver.c:131-205 with indicial_polynomial :4-39 and _acb_ode_solution_update /
+ * _extend / _normalize, src/acb_ode_solution.c:60-123).  The recurrence is carried as polynomials
+ * in rho per instance, in device workspace.
+ * rho  : 1 entry, S = 2*batch or 2 (shared_rho).
+ * gens : M*(n+1) entries, S = 2*batch, all written: gens[i][j] (sol->gens + i, coefficient j) is
+ *        entry i*(n+1) + j.  1 <= M <= 16, 1 <= mul <= M, 1 <= degree <= 8. */
+size_t cb200_frobenius_general_workspace_bytes(int L, int order, int degree, int M, int64_t n, int64_t batch);
+int cb200_frobenius_general_batch_dev(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
+                                      const uint32_t *ode_mant, const cb_meta *ode_meta, int shared_ode,
+                                      const uint32_t *rho_mant, const cb_meta *rho_meta, int shared_rho,
+                                      int mul, int M, uint32_t *gens_mant, cb_meta *gens_meta, void *workspace,
+                                      size_t workspace_bytes, void *stream);
+int cb200_frobenius_general_batch_host(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
+                                       const uint32_t *ode_mant, const cb_meta *ode_meta, int shared_ode,
+                                       const uint32_t *rho_mant, const cb_meta *rho_meta, int shared_rho,
+                                       int mul, int M, uint32_t *gens_mant, cb_meta *gens_meta, int device);
+
+/* ---- the solution bookkeeping steps on their own, for a batch of solutions
+ * (reference src/acb_ode.h:58-60).  Polynomials cross this interface as fixed-capacity coefficient
+ * arrays; their length is implied (trailing exact zeros do not count), as acb_poly normalises.
+ * which: CB200_SOL_EXTEND  _acb_ode_solution_extend(sol, nu, g_nu)   src/acb_ode_solution.c:97-109
+ *        CB200_SOL_UPDATE  _acb_ode_solution_update(sol, f)          src/acb_ode_solution.c:60-95
+ *        CB200_SOL_NORMALIZE _acb_ode_solution_normalize(sol)        src/acb_ode_solution.c:111-123
+ * gens : M*cap entries (gens[i][j] = entry i*cap + j), S = 2*batch, in/out.
+ * f    : fcap entries, S = 2*batch: the polynomial g_nu / f in rho, CONSUMED (comes back zero) as in
+ *        the reference; ignored for NORMALIZE.  rho: 1 entry, S = 2*batch.  0 <= M <= 16. */
+#define CB200_SOL_EXTEND 0
+#define CB200_SOL_UPDATE 1
+#define CB200_SOL_NORMALIZE 2
+size_t cb200_solution_op_workspace_bytes(int L, int M, int64_t batch);
+int cb200_solution_op_dev(int which, int L, int64_t batch, int mul, int M, int64_t cap, int64_t nu,
+                          const uint32_t *rho_mant, const cb_meta *rho_meta, uint32_t *gens_mant,
+                          cb_meta *gens_meta, uint32_t *f_mant, cb_meta *f_meta, int64_t fcap, void *workspace,
+                          size_t workspace_bytes, void *stream);
+int cb200_solution_op_host(int which, int L, int64_t batch, int mul, int M, int64_t cap, int64_t nu,
+                           const uint32_t *rho_mant, const cb_meta *rho_meta, uint32_t *gens_mant,
+                           cb_meta *gens_meta, uint32_t *f_mant, cb_meta *f_meta, int64_t fcap, int device);
+
+/* ---- indicial_polynomial(result, ODE, nu, shift) (reference src/frobenius_solver.c:4-39) for a
+ * batch of operators: out = order+2 entries, S = 2*batch (coefficients of rho^0 .. rho^order; the
+ * last entry is scratch and comes back zero). */
+int cb200_indicial_polynomial_dev(int L, int order, int degree, int valuation, int64_t batch,
+                                  const uint32_t *ode_mant, const cb_meta *ode_meta, int shared_ode, int64_t nu,
+                                  int64_t shift, uint32_t *out_mant, cb_meta *out_meta, void *workspace,
+                                  size_t workspace_bytes, void *stream);
+int cb200_indicial_polynomial_host(int L, int order, int degree, int valuation, int64_t batch,
+                                   const uint32_t *ode_mant, const cb_meta *ode_meta, int shared_ode, int64_t nu,
+                                   int64_t shift, uint32_t *out_mant, cb_meta *out_meta, int device);
+
 /* ---- Horner evaluation batched over points (acb_poly_evaluate inside
  * acb_ode_solution_evaluate, reference src/acb_ode_solution.c:40,45; and the first `nder`
  * coefficients of acb_poly_taylor_shift, reference src/fuchs_solver.c:159).

@@ -135,6 +135,11 @@ void acb_ode_solution_clear(acb_ode_solution_t sol);
  * logarithmic case M > 1 and non-integer rho need acb_log / acb_pow, which are listed as next in
  * DESIGN.md; they abort here. */
 void acb_ode_solution_evaluate(acb_t res, acb_ode_solution_t sol, acb_t x, slong prec);
+/* the rho-derivative bookkeeping of the Frobenius solver (reference src/acb_ode_solution.c:60-123);
+ * _update consumes f and _extend consumes g_nu (they come back as zero polynomials), as in the reference */
+void _acb_ode_solution_update(acb_ode_solution_t sol, acb_poly_t f, slong prec);
+void _acb_ode_solution_extend(acb_ode_solution_t sol, slong nu, acb_poly_t g_nu, slong prec);
+void _acb_ode_solution_normalize(acb_ode_solution_t sol, slong prec);
 
 /* ================================ Examples (reference src/examples.c) ========================= */
 void acb_ode_legendre(acb_ode_t ODE, ulong n);
@@ -149,8 +154,10 @@ void acb_ode_solve_fuchs(acb_poly_t res, acb_ode_t ODE, slong deg, slong bits);
 void analytic_continuation(acb_poly_t res, acb_ode_t ODE, acb_srcptr path, slong len, slong deg, slong bits);
 void indicial_polynomial_evaluate(acb_t result, acb_ode_t ODE, slong nu, acb_t rho, slong shift, slong prec);
 void _acb_ode_solve_frobenius(acb_poly_t res, acb_ode_t ODE, acb_ode_solution_t rhs, slong sol_degree, slong prec);
-/* M == 1 only (the hot path of SURVEY.md 8); M > 1 is listed under "next" and aborts here */
+/* M == 1: the scalar recurrence; M > 1: the polynomial-in-rho (logarithmic) recurrence of
+ * src/frobenius_solver.c:131-205, one device launch (M <= 16, 1 <= degree <= 8) */
 void acb_ode_solve_frobenius(acb_ode_solution_t sol, acb_ode_t ODE, slong sol_degree, slong prec);
+void indicial_polynomial(acb_poly_t result, acb_ode_t ODE, slong nu, slong shift, slong prec); /* :4-39 */
 
 static inline slong clamp(slong in, slong min, slong max) {
     if (in < min)

@@ -142,6 +142,23 @@ int cbo_example_flat(int which, int L, uint64_t n, const uint32_t *par_m, const 
 int cbo_continuation_flat(int L, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
                           const uint32_t *ode_m, const int32_t *ode_t, const uint32_t *path_m,
                           const int32_t *path_t, uint32_t *y_m, int32_t *y_t);
+/* general Frobenius (M = mul + alpha > 1), reference src/frobenius_solver.c:131-205.
+ * gens out: [batch][M][n+1] complex balls */
+int cbo_frobenius_general_batch(int L, int order, int degree, int64_t n, int64_t batch, int shared_ode,
+                                const uint32_t *ode_m, const int32_t *ode_t, const uint32_t *rho_m,
+                                const int32_t *rho_t, int shared_rho, int64_t mul, int64_t M,
+                                uint32_t *gens_m, int32_t *gens_t, int nthreads);
+/* indicial_polynomial (src/frobenius_solver.c:4-39): out = order+1 coefficients */
+int cbo_indicial_polynomial_flat(int L, int order, int degree, const uint32_t *ode_m, const int32_t *ode_t,
+                                 int64_t nu, int64_t shift, uint32_t *out_m, int32_t *out_t);
+int cbo_indicial_polynomial_evaluate_flat(int L, int order, int degree, const uint32_t *ode_m,
+                                          const int32_t *ode_t, int64_t nu, const uint32_t *rho_m,
+                                          const int32_t *rho_t, int64_t shift, uint32_t *out_m, int32_t *out_t);
+/* which: 0 _acb_ode_solution_extend, 1 _update, 2 _normalize (src/acb_ode_solution.c:60-123).
+ * gens [batch][M][cap] in/out; f [batch][fcap] in/out (consumed: comes back zero); rho [batch] */
+int cbo_solution_op_flat(int which, int L, int64_t batch, int64_t mul, int64_t M, int64_t cap, int64_t nu,
+                         const uint32_t *rho_m, const int32_t *rho_t, uint32_t *gens_m, int32_t *gens_t,
+                         uint32_t *f_m, int32_t *f_t, int64_t fcap);
 const char *cbo_backend(void); /* "gmp-mpn" or "plain-c" */
 
 #ifdef __cplusplus

@@ -51,6 +51,14 @@ def lib(plain: bool = False) -> C.CDLL:
     L.cbo_continuation_flat.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, _u32p, _i32p,
                                         _u32p, _i32p, _u32p, _i32p]
     L.cbo_example_flat.argtypes = [C.c_int, C.c_int, C.c_uint64, _u32p, _i32p, _u32p, _i32p]
+    L.cbo_frobenius_general_batch.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, _u32p, _i32p,
+                                              _u32p, _i32p, C.c_int, C.c_int64, C.c_int64, _u32p, _i32p, C.c_int]
+    L.cbo_indicial_polynomial_flat.argtypes = [C.c_int, C.c_int, C.c_int, _u32p, _i32p, C.c_int64, C.c_int64,
+                                               _u32p, _i32p]
+    L.cbo_indicial_polynomial_evaluate_flat.argtypes = [C.c_int, C.c_int, C.c_int, _u32p, _i32p, C.c_int64, _u32p,
+                                                        _i32p, C.c_int64, _u32p, _i32p]
+    L.cbo_solution_op_flat.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                       _u32p, _i32p, _u32p, _i32p, _u32p, _i32p, C.c_int64]
     _LIBS[name] = L
     return L
 
@@ -145,3 +153,47 @@ def continuation(order: int, degree: int, n: int, ode: Balls, path: Balls, y0: B
                                           path.mant, path.meta, y.mant, y.meta)
     assert rc == 0
     return y
+
+
+def frobenius_general_batch(order: int, degree: int, n: int, ode: Balls, rho: Balls, batch: int, shared_ode: bool,
+                            shared_rho: bool, mul: int, M: int, nthreads: int = 1, plain: bool = False) -> Balls:
+    """acb_ode_solve_frobenius for M = mul + alpha > 1 (reference src/frobenius_solver.c:131-205).
+    Returns sol->gens as [batch][M][n+1] complex balls."""
+    gens = Balls.zeros(batch * M * (n + 1) * 2, ode.L)
+    rc = lib(plain).cbo_frobenius_general_batch(ode.L, order, degree, n, batch, int(shared_ode), ode.mant, ode.meta,
+                                                rho.mant, rho.meta, int(shared_rho), mul, M, gens.mant, gens.meta,
+                                                nthreads)
+    assert rc == 0
+    return gens
+
+
+def indicial_polynomial(order: int, degree: int, ode: Balls, nu: int, shift: int, plain: bool = False) -> Balls:
+    out = Balls.zeros(2 * (order + 1), ode.L)
+    rc = lib(plain).cbo_indicial_polynomial_flat(ode.L, order, degree, ode.mant, ode.meta, nu, shift, out.mant, out.meta)
+    assert rc == 0
+    return out
+
+
+def indicial_polynomial_evaluate(order: int, degree: int, ode: Balls, nu: int, rho: Balls, shift: int,
+                                 plain: bool = False) -> Balls:
+    out = Balls.zeros(2, ode.L)
+    rc = lib(plain).cbo_indicial_polynomial_evaluate_flat(ode.L, order, degree, ode.mant, ode.meta, nu, rho.mant,
+                                                          rho.meta, shift, out.mant, out.meta)
+    assert rc == 0
+    return out
+
+
+def solution_op(which: str, rho: Balls, gens: Balls, batch: int, mul: int, M: int, f: Balls | None = None,
+                nu: int = 0, plain: bool = False):
+    """_acb_ode_solution_extend / _update / _normalize on [batch][M][cap] series; f: [batch][fcap]
+    coefficients of the polynomial in rho (consumed).  Returns (gens, f) after the call."""
+    code = {"extend": 0, "update": 1, "normalize": 2}[which]
+    L = gens.L
+    cap = gens.n_slots // (2 * batch * M)
+    g = gens.copy()
+    ff = Balls.zeros(2 * batch, L) if f is None else f.copy()
+    fcap = ff.n_slots // (2 * batch)
+    rc = lib(plain).cbo_solution_op_flat(code, L, batch, mul, M, cap, nu, rho.mant, rho.meta, g.mant, g.meta,
+                                         ff.mant, ff.meta, fcap)
+    assert rc == 0
+    return g, ff

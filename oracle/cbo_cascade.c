@@ -459,3 +459,345 @@ int cbo_example_flat(int which, int L, uint64_t n, const uint32_t *par_m, const 
     cbo_ode_free(o);
     return 0;
 }
+
+/* ================================================================ general Frobenius (M > 1)
+ * acb_ode_solve_frobenius, reference src/frobenius_solver.c:131-205, with indicial_polynomial
+ * (:4-39) and the solution bookkeeping _acb_ode_solution_update / _extend / _normalize
+ * (src/acb_ode_solution.c:60-123).  Polynomials in rho are acb_poly objects in the reference;
+ * cbo_poly keeps Arb's conventions: a normalised length (trailing EXACT zeros stripped after
+ * every operation that Arb normalises after), reads beyond the length give zero.
+ *
+ * Arb sub-algorithms the reference reaches through acb_poly_* (Arb version unpinned, so these are
+ * restated choices -- each is an algorithm Arb ships):
+ *   acb_poly_mul        -> longer operand first, _acb_poly_mullow_classical in its acb_mul /
+ *                          acb_addmul form: res[i] = a[i] b[0]; res[la-1+j] = a[la-1] b[j];
+ *                          then res[i+j] += a[i] b[j]  (i < la-1, 1 <= j < lb).  Arb picks the
+ *                          classical algorithm whenever the shorter operand has <= 15 terms at
+ *                          1024 bits; here it is the indicial polynomial, order+1 terms.
+ *   acb_poly_evaluate   -> _acb_poly_evaluate_horner (cbo_poly_evaluate_horner above)
+ *   acb_poly_scalar_mul/div, acb_poly_add/sub, acb_poly_derivative -> coefficientwise
+ *   acb_div_si(x, n)    -> acb_div by the exact ball n */
+typedef struct {
+    cbo_acb *c;
+    int64_t len, alloc;
+} cbo_poly;
+
+static void poly_init(cbo_poly *p) { p->c = NULL; p->len = p->alloc = 0; }
+static void poly_clear(cbo_poly *p) { free(p->c); poly_init(p); }
+static void poly_fit(cbo_poly *p, int64_t n) {
+    if (n > p->alloc) {
+        int64_t na = n > 2 * p->alloc ? n : 2 * p->alloc;
+        p->c = (cbo_acb *)realloc(p->c, sizeof(cbo_acb) * na);
+        for (int64_t i = p->alloc; i < na; i++) cbo_acb_zero(p->c + i);
+        p->alloc = na;
+    }
+}
+static void poly_normalise(cbo_poly *p) {
+    while (p->len > 0 && cbo_acb_is_zero(p->c + p->len - 1)) p->len--;
+}
+static void poly_zero(cbo_poly *p) { p->len = 0; }
+static void poly_one(cbo_poly *p, int L) {
+    poly_fit(p, 1);
+    cbo_acb_one(p->c, L);
+    p->len = 1;
+}
+static void poly_get(cbo_acb *z, const cbo_poly *p, int64_t n) { /* acb_poly_get_coeff_acb */
+    if (n < p->len) *z = p->c[n]; else cbo_acb_zero(z);
+}
+static void poly_set_coeff(cbo_poly *p, int64_t n, const cbo_acb *x) { /* acb_poly_set_coeff_acb */
+    poly_fit(p, n + 1);
+    if (n + 1 > p->len) {
+        for (int64_t i = p->len; i < n; i++) cbo_acb_zero(p->c + i);
+        p->len = n + 1;
+    }
+    p->c[n] = *x;
+    poly_normalise(p);
+}
+static void poly_set(cbo_poly *z, const cbo_poly *x) {
+    poly_fit(z, x->len);
+    memcpy(z->c, x->c, sizeof(cbo_acb) * x->len);
+    z->len = x->len;
+}
+static void poly_mul(cbo_poly *res, const cbo_poly *p1, const cbo_poly *p2, int L) { /* acb_poly_mul */
+    if (p1->len == 0 || p2->len == 0) {
+        poly_zero(res);
+        return;
+    }
+    const cbo_poly *a = p1->len >= p2->len ? p1 : p2, *b = p1->len >= p2->len ? p2 : p1;
+    int64_t la = a->len, lb = b->len, n = la + lb - 1;
+    cbo_poly t;
+    poly_init(&t);
+    poly_fit(&t, n);
+    for (int64_t i = 0; i < la; i++) cbo_acb_mul(t.c + i, a->c + i, b->c, L);
+    for (int64_t j = 1; j < lb; j++) cbo_acb_mul(t.c + la - 1 + j, a->c + la - 1, b->c + j, L);
+    for (int64_t i = 0; i < la - 1; i++)
+        for (int64_t j = 1; j < lb; j++) cbo_acb_addmul(t.c + i + j, a->c + i, b->c + j, L);
+    t.len = n;
+    poly_normalise(&t);
+    poly_clear(res); /* acb_poly_swap(res, t) */
+    *res = t;
+}
+static void poly_addsub(cbo_poly *res, const cbo_poly *a, const cbo_poly *b, int sub, int L) {
+    int64_t la = a->len, lb = b->len, mn = la < lb ? la : lb, mx = la < lb ? lb : la;
+    poly_fit(res, mx);
+    for (int64_t i = 0; i < mn; i++) {
+        if (sub) cbo_acb_sub(res->c + i, a->c + i, b->c + i, L);
+        else cbo_acb_add(res->c + i, a->c + i, b->c + i, L);
+    }
+    for (int64_t i = mn; i < la; i++) res->c[i] = a->c[i];
+    for (int64_t i = mn; i < lb; i++) {
+        if (sub) cbo_acb_neg(res->c + i, b->c + i);
+        else res->c[i] = b->c[i];
+    }
+    res->len = mx;
+    poly_normalise(res);
+}
+static void poly_scalar_mul(cbo_poly *res, const cbo_poly *p, const cbo_acb *c, int L) {
+    poly_fit(res, p->len);
+    for (int64_t i = 0; i < p->len; i++) cbo_acb_mul(res->c + i, p->c + i, c, L);
+    res->len = p->len;
+    poly_normalise(res);
+}
+static void poly_scalar_div(cbo_poly *res, const cbo_poly *p, const cbo_acb *c, int L) {
+    poly_fit(res, p->len);
+    for (int64_t i = 0; i < p->len; i++) cbo_acb_div(res->c + i, p->c + i, c, L);
+    res->len = p->len;
+    poly_normalise(res);
+}
+static void poly_derivative(cbo_poly *p, int L) { /* in place, as every call site uses it */
+    for (int64_t i = 1; i < p->len; i++) cbo_acb_mul_si(p->c + i - 1, p->c + i, i, L);
+    if (p->len > 0) p->len--;
+    poly_normalise(p);
+}
+static void poly_evaluate(cbo_acb *y, const cbo_poly *p, const cbo_acb *x, int L) {
+    if (p->len == 0) {
+        cbo_acb_zero(y);
+    } else if (p->len == 1 || cbo_acb_is_zero(x)) {
+        *y = p->c[0];
+    } else {
+        cbo_acb out;
+        cbo_poly_evaluate_horner(&out, p->c, p->len, x, 1, L);
+        *y = out;
+    }
+}
+
+/* indicial_polynomial, src/frobenius_solver.c:4-39 */
+static void indicial_polynomial(cbo_poly *result, cbo_ode *o, int64_t nu, int64_t shift, int L) {
+    poly_zero(result);
+    nu += cbo_ode_valuation(o);
+    if (nu > o->degree) return;
+    cbo_acb t1, t2;
+    poly_fit(result, o->order + 1);
+    for (int64_t lam = clampi(o->degree - nu, 0, o->order); lam >= 0; lam--) {
+        for (int64_t j = result->len; j > 0; j--) {
+            poly_get(&t1, result, j);
+            poly_get(&t2, result, j - 1);
+            cbo_acb_mul_si(&t1, &t1, shift - lam, L);
+            cbo_acb_add(&t1, &t2, &t1, L);
+            poly_set_coeff(result, j, &t1);
+        }
+        poly_get(&t1, result, 0);
+        cbo_acb_mul_si(&t1, &t1, shift - lam, L);
+        if (lam + nu >= 0) cbo_acb_add(&t1, &t1, COEFF(o, lam, lam + nu), L);
+        poly_set_coeff(result, 0, &t1);
+    }
+}
+
+typedef struct {
+    cbo_acb rho;
+    int64_t mul, M;
+    cbo_poly *gens;
+} cbo_solution;
+
+static void acb_div_si(cbo_acb *z, const cbo_acb *x, int64_t n, int L) {
+    cbo_acb k;
+    cbo_acb_set_si(&k, n, L);
+    cbo_acb_div(z, x, &k, L);
+}
+
+/* _acb_ode_solution_update, src/acb_ode_solution.c:60-95 (consumes f) */
+static void solution_update(cbo_solution *sol, cbo_poly *f, int L) {
+    int64_t M = sol->M, binom = 1;
+    cbo_acb *F = (cbo_acb *)malloc(sizeof(cbo_acb) * (M > 0 ? M : 1));
+    for (int64_t k = 0; k < M; k++) {
+        poly_evaluate(F + k, f, &sol->rho, L);
+        poly_derivative(f, L);
+        cbo_acb_mul_si(F + k, F + k, binom, L);
+        binom = (binom * (M - 1 - k)) / (k + 1);
+    }
+    for (int64_t n = M - 1; n >= 0; n--) {
+        poly_scalar_mul(sol->gens + n, sol->gens + n, F + 0, L);
+        for (int64_t k = 1; k <= n; k++) {
+            poly_scalar_mul(f, sol->gens + (n - k), F + k, L);
+            poly_addsub(sol->gens + n, sol->gens + n, f, 0, L);
+            cbo_acb_mul_si(F + k, F + k, n - k, L);
+            acb_div_si(F + k, F + k, n, L);
+        }
+    }
+    poly_zero(f);
+    free(F);
+}
+/* _acb_ode_solution_extend, :97-109 (consumes g_nu) */
+static void solution_extend(cbo_solution *sol, int64_t nu, cbo_poly *g_nu, int L) {
+    cbo_acb t;
+    for (int64_t i = 0; i < sol->M; i++) {
+        poly_evaluate(&t, g_nu, &sol->rho, L);
+        poly_set_coeff(sol->gens + i, nu, &t);
+        poly_derivative(g_nu, L);
+    }
+    poly_zero(g_nu);
+}
+/* _acb_ode_solution_normalize, :111-123 */
+static void solution_normalize(cbo_solution *sol, int L) {
+    cbo_acb t;
+    int64_t alpha = sol->M - sol->mul;
+    poly_get(&t, sol->gens + alpha, 0);
+    for (int64_t i = 0; i < sol->M; i++) poly_scalar_div(sol->gens + i, sol->gens + i, &t, L);
+}
+
+/* acb_ode_solve_frobenius for M > 1, src/frobenius_solver.c:131-205 */
+static void solve_frobenius_general(cbo_solution *sol, cbo_ode *o, int64_t n, int L) {
+    int d = o->degree;
+    cbo_acb temp;
+    cbo_poly indicial, g_new, *g_rho = (cbo_poly *)malloc(sizeof(cbo_poly) * (d > 0 ? d : 1));
+    poly_init(&indicial);
+    poly_init(&g_new);
+    for (int i = 0; i < d; i++) poly_init(g_rho + i);
+    poly_one(g_rho, L);
+    for (int64_t i = 0; i < sol->M; i++) {
+        poly_zero(sol->gens + i);
+        poly_fit(sol->gens + i, n + 1);
+    }
+    poly_one(sol->gens, L);
+    for (int64_t nu = 1; nu <= n; nu++) {
+        int64_t i = clampi(nu, 1, d);
+        indicial_polynomial(&indicial, o, i, nu - i, L); /* :156 */
+        do {
+            poly_mul(&indicial, &indicial, g_rho + (i - 1), L);
+            poly_addsub(&g_new, &g_new, &indicial, 1, L);
+            i--;
+            indicial_polynomial(&indicial, o, i, nu - i, L);
+        } while (i > 0);
+        cbo_indicial_polynomial_evaluate(&temp, o, 0, &sol->rho, nu, L); /* :170 */
+        if (!cbo_acb_contains_zero(&temp)) {
+            poly_scalar_div(&indicial, &indicial, &temp, L);
+            poly_scalar_div(&g_new, &g_new, &temp, L);
+        }
+        int all_zero = g_new.len == 0;
+        for (i = d - 1; i > 0; i--) {
+            poly_mul(g_rho + i, g_rho + (i - 1), &indicial, L);
+            all_zero &= g_rho[i].len == 0;
+        }
+        poly_set(g_rho, &g_new);
+        solution_update(sol, &indicial, L);
+        solution_extend(sol, nu, &g_new, L);
+        if (all_zero) break;
+    }
+    solution_normalize(sol, L);
+    poly_clear(&indicial);
+    poly_clear(&g_new);
+    for (int i = 0; i < d; i++) poly_clear(g_rho + i);
+    free(g_rho);
+}
+
+/* ---- flat entry points.  Polynomials travel as fixed-capacity coefficient arrays whose length is
+ * implied (trailing exact zeros do not count), as on the device interface. */
+static void load_poly(cbo_poly *p, const uint32_t *m, const int32_t *t, int64_t first, int64_t cap, int L) {
+    poly_fit(p, cap);
+    for (int64_t j = 0; j < cap; j++) load_acb(p->c + j, m, t, first + j, L);
+    p->len = cap;
+    poly_normalise(p);
+}
+static void store_poly(uint32_t *m, int32_t *t, int64_t first, int64_t cap, const cbo_poly *p, int L) {
+    cbo_acb z;
+    cbo_acb_zero(&z);
+    for (int64_t j = 0; j < cap; j++) store_acb(m, t, first + j, j < p->len ? p->c + j : &z, L);
+}
+static void sol_alloc(cbo_solution *s, int64_t mul, int64_t M) {
+    s->mul = mul;
+    s->M = M;
+    s->gens = (cbo_poly *)malloc(sizeof(cbo_poly) * (M > 0 ? M : 1));
+    for (int64_t i = 0; i < M; i++) poly_init(s->gens + i);
+}
+static void sol_free(cbo_solution *s) {
+    for (int64_t i = 0; i < s->M; i++) poly_clear(s->gens + i);
+    free(s->gens);
+}
+
+typedef struct {
+    int L, order, degree, shared_ode, shared_rho;
+    int64_t n, mul, M;
+    const uint32_t *ode_m, *rho_m;
+    const int32_t *ode_t, *rho_t;
+    uint32_t *gens_m;
+    int32_t *gens_t;
+} frobg_ctx;
+static void frobg_body(int64_t s, void *vc) {
+    frobg_ctx *c = (frobg_ctx *)vc;
+    int L = c->L;
+    cbo_ode *o = load_ode(L, c->order, c->degree, c->ode_m, c->ode_t, c->shared_ode ? 0 : s);
+    cbo_solution sol;
+    sol_alloc(&sol, c->mul, c->M);
+    load_acb(&sol.rho, c->rho_m, c->rho_t, c->shared_rho ? 0 : s, L);
+    solve_frobenius_general(&sol, o, c->n, L);
+    for (int64_t i = 0; i < c->M; i++)
+        store_poly(c->gens_m, c->gens_t, (s * c->M + i) * (c->n + 1), c->n + 1, sol.gens + i, L);
+    sol_free(&sol);
+    cbo_ode_free(o);
+}
+/* gens: [batch][M][n+1] complex balls out */
+int cbo_frobenius_general_batch(int L, int order, int degree, int64_t n, int64_t batch, int shared_ode,
+                                const uint32_t *ode_m, const int32_t *ode_t, const uint32_t *rho_m,
+                                const int32_t *rho_t, int shared_rho, int64_t mul, int64_t M,
+                                uint32_t *gens_m, int32_t *gens_t, int nthreads) {
+    frobg_ctx c = {L, order, degree, shared_ode, shared_rho, n, mul, M, ode_m, rho_m, ode_t, rho_t, gens_m, gens_t};
+    parallel_for(batch, nthreads, frobg_body, &c);
+    return 0;
+}
+
+/* indicial_polynomial for one operator: out has order+1 coefficients */
+int cbo_indicial_polynomial_flat(int L, int order, int degree, const uint32_t *ode_m, const int32_t *ode_t,
+                                 int64_t nu, int64_t shift, uint32_t *out_m, int32_t *out_t) {
+    cbo_ode *o = load_ode(L, order, degree, ode_m, ode_t, 0);
+    cbo_poly r;
+    poly_init(&r);
+    indicial_polynomial(&r, o, nu, shift, L);
+    store_poly(out_m, out_t, 0, order + 1, &r, L);
+    poly_clear(&r);
+    cbo_ode_free(o);
+    return 0;
+}
+int cbo_indicial_polynomial_evaluate_flat(int L, int order, int degree, const uint32_t *ode_m,
+                                          const int32_t *ode_t, int64_t nu, const uint32_t *rho_m,
+                                          const int32_t *rho_t, int64_t shift, uint32_t *out_m, int32_t *out_t) {
+    cbo_ode *o = load_ode(L, order, degree, ode_m, ode_t, 0);
+    cbo_acb rho, out;
+    load_acb(&rho, rho_m, rho_t, 0, L);
+    cbo_indicial_polynomial_evaluate(&out, o, nu, &rho, shift, L);
+    store_acb(out_m, out_t, 0, &out, L);
+    cbo_ode_free(o);
+    return 0;
+}
+
+/* the three solution bookkeeping steps for a batch: gens [batch][M][cap], f/g [batch][fcap], rho [batch] */
+int cbo_solution_op_flat(int which, int L, int64_t batch, int64_t mul, int64_t M, int64_t cap, int64_t nu,
+                         const uint32_t *rho_m, const int32_t *rho_t, uint32_t *gens_m, int32_t *gens_t,
+                         uint32_t *f_m, int32_t *f_t, int64_t fcap) {
+    for (int64_t s = 0; s < batch; s++) {
+        cbo_solution sol;
+        sol_alloc(&sol, mul, M);
+        load_acb(&sol.rho, rho_m, rho_t, s, L);
+        for (int64_t i = 0; i < M; i++) load_poly(sol.gens + i, gens_m, gens_t, (s * M + i) * cap, cap, L);
+        cbo_poly f;
+        poly_init(&f);
+        if (which != 2) load_poly(&f, f_m, f_t, s * fcap, fcap, L);
+        if (which == 0) solution_extend(&sol, nu, &f, L);
+        else if (which == 1) solution_update(&sol, &f, L);
+        else solution_normalize(&sol, L);
+        if (which != 2) store_poly(f_m, f_t, s * fcap, fcap, &f, L);
+        for (int64_t i = 0; i < M; i++) store_poly(gens_m, gens_t, (s * M + i) * cap, cap, sol.gens + i, L);
+        poly_clear(&f);
+        sol_free(&sol);
+    }
+    return 0;
+}

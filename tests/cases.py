@@ -339,3 +339,134 @@ def case_horner(oracle, drv, L: int, seed: int, length: int = 40, npts: int = 9)
     for nder in (1, 2, 3):
         assert_same(oracle.horner_batch(f, pts, nder), api.acb_poly_evaluate_batch(f, pts, nder, driver=drv),
                     f"horner L={L} nder={nder}")
+
+
+def _frobenius_test_operator(rng, L: int, order: int, degree: int, dyadic: bool = False):
+    """reference tests/frobenius.c:24-31: random operator with P[i][j] = 0 for j <= i and
+    P[order][order] = P[order-1][order-1] = 1: valuation 0, rho = order - 2 a double indicial root."""
+    ne = (order + 1) * (degree + 1)
+    if dyadic:
+        vals = [(F(int(rng.integers(-40, 40)), 8), F(int(rng.integers(-40, 40)), 8)) for _ in range(ne)]
+        ode = from_complex(vals, L)
+    else:
+        ode = random_balls(rng, ne * 2, L, -4, 4, "ulp")
+    m = ode.mant.reshape(order + 1, degree + 1, 2, L)
+    t = ode.meta.reshape(order + 1, degree + 1, 2, 4)
+    for i in range(order + 1):
+        m[i, : i + 1] = 0
+        t[i, : i + 1] = (0, FLAG_ZERO, 0, 0)
+    one = from_complex([1], L)
+    for i in (order, order - 1):
+        m[i, i] = one.mant
+        t[i, i] = one.meta
+    return ode
+
+
+def case_frobenius_general(oracle, drv, L: int, seed: int, trials: int = 3):
+    """acb_ode_solve_frobenius with M = 2 (reference src/frobenius_solver.c:131-205) on the operators
+    of reference tests/frobenius.c: bit-exact against the oracle, and gens[0] shifted by rho passes
+    the reference's own acceptance test acb_ode_solves (tests/frobenius.c:37-40)."""
+    rng = np.random.default_rng(seed)
+    for _ in range(trials):
+        degree = 3 + int(rng.integers(0, 4))
+        order = 2 + int(rng.integers(0, degree - 2))
+        ode = _frobenius_test_operator(rng, L, order, degree)
+        n = 2 + int(rng.integers(0, 12))
+        s_rho = order - 2
+        rho = from_complex([s_rho], L)
+        go = oracle.frobenius_general_batch(order, degree, n, ode, rho, 1, True, True, 2, 2)
+        gs = api.acb_ode_solve_frobenius_batch(ode, rho, 2, 0, order, degree, n, 1, True, True, driver=drv)
+        assert_same(go, gs, f"general frobenius L={L} order={order} degree={degree} n={n}")
+        shifted = Balls.concat([Balls.zeros(2 * s_rho, L), gs[0:2 * (n + 1)]])
+        assert oracle.ode_solves(order, degree, ode, shifted, n)
+
+
+def case_frobenius_general_sweep(oracle, drv, L: int, seed: int, n: int = 8, batch: int = 4):
+    """M = 2 and M = 3 (mul + alpha) on per-instance hypergeometric operators with per-instance complex
+    rho (nothing special about rho: the recurrence and the rho-derivative bookkeeping are generic),
+    plus the exact double root rho = 0 of c = 1."""
+    rng = np.random.default_rng(seed)
+    par = random_balls(rng, batch * 6, L, -1, 1, "zero")
+    odes = Balls.concat([oracle.example("hypgeom", L, 0, par[i * 6:(i + 1) * 6]) for i in range(batch)])
+    rho = random_balls(rng, batch * 2, L, -1, 1, "ulp")
+    for mul, alpha in ((2, 0), (2, 1), (1, 1)):
+        M = mul + alpha
+        go = oracle.frobenius_general_batch(2, 2, n, odes, rho, batch, False, False, mul, M)
+        gs = api.acb_ode_solve_frobenius_batch(odes, rho, mul, alpha, 2, 2, n, batch, False, False, driver=drv)
+        assert_same(go, gs, f"general frobenius sweep L={L} mul={mul} alpha={alpha}")
+    # c = 1: rho = 0 is a double root, gens[1] carries the coefficient of the logarithmic solution
+    ode = oracle.example("hypgeom", L, 0, from_complex([F(3, 8), F(5, 16), 1], L))
+    rho0 = from_complex([0], L)
+    go = oracle.frobenius_general_batch(2, 2, n, ode, rho0, 1, True, True, 2, 2)
+    gs = api.acb_ode_solve_frobenius_batch(ode, rho0, 2, 0, 2, 2, n, 1, True, True, driver=drv)
+    assert_same(go, gs, f"general frobenius c=1 L={L}")
+    a, b = F(3, 8), F(5, 16)
+    ex = F(1)
+    for k in range(n):  # gens[0] = 2F1(a, b; 1; z)
+        assert gs.contains(2 * k, ex)
+        ex = ex * (a + k) * (b + k) / ((k + 1) * (k + 1))
+
+
+def case_solution_ops(oracle, drv, L: int, seed: int, batch: int = 3):
+    """reference tests/solution_extend.c and tests/solution_update.c: _acb_ode_solution_extend,
+    _update and _normalize on random polynomials (length <= 20) and random rho, bit-exact against
+    the oracle; extend's defining property gens[j][i] == f^(j)(rho) is checked with the oracle's
+    Horner evaluation (the reference test uses acb_equal against acb_poly_evaluate)."""
+    rng = np.random.default_rng(seed)
+    for trial in range(3):
+        M = 1 + int(rng.integers(0, 5))
+        cap = 2 + int(rng.integers(0, 8))
+        rho = random_balls(rng, batch * 2, L, -2, 2, "ulp")
+        gens = Balls.zeros(batch * M * cap * 2, L)
+        for nu in range(cap):
+            flen = 1 + int(rng.integers(0, 20))
+            f = random_balls(rng, batch * flen * 2, L, -3, 3, "ulp", short_frac=0.2)
+            go, fo = oracle.solution_op("extend", rho, gens, batch, M, M, f, nu)
+            gs, fs = api.acb_ode_solution_op_batch(api.SOL_EXTEND, rho, gens, batch, M, M, f, nu, driver=drv)
+            assert_same(go, gs, f"solution_extend L={L} M={M} nu={nu}")
+            assert_same(fo, fs, "solution_extend consumes g_nu")
+            assert (fs.meta[:, 1] & FLAG_ZERO).all()
+            for s in range(batch):  # gens[0][nu] = f(rho)
+                val = oracle.horner_batch(f[s * flen * 2:(s + 1) * flen * 2], rho[2 * s:2 * s + 2], 1)
+                got = gs[2 * ((s * M + 0) * cap + nu):2 * ((s * M + 0) * cap + nu) + 2]
+                assert_same(val, got, "extend: gens[0][nu] == f(rho)")
+            gens = gs
+        flen = 1 + int(rng.integers(0, 20))
+        f = random_balls(rng, batch * flen * 2, L, -3, 3, "ulp", short_frac=0.2)
+        go, fo = oracle.solution_op("update", rho, gens, batch, M, M, f)
+        gs, fs = api.acb_ode_solution_op_batch(api.SOL_UPDATE, rho, gens, batch, M, M, f, driver=drv)
+        assert_same(go, gs, f"solution_update L={L} M={M}")
+        assert_same(fo, fs, "solution_update consumes f")
+        mul = 1 + int(rng.integers(0, M))
+        go, _ = oracle.solution_op("normalize", rho, gs, batch, mul, M)
+        gn, _ = api.acb_ode_solution_op_batch(api.SOL_NORMALIZE, rho, gs, batch, mul, M, driver=drv)
+        assert_same(go, gn, f"solution_normalize L={L} M={M} mul={mul}")
+
+
+def case_indicial_polynomial(oracle, drv, L: int, seed: int, trials: int = 4):
+    """reference tests/indicial_polynomial.c:18-96: the polynomial f_nu(rho + shift), bit-exact against
+    the oracle, and consistent with indicial_polynomial_evaluate at an integer rho (overlap)."""
+    rng = np.random.default_rng(seed)
+    for trial in range(trials):
+        degree = 3 + int(rng.integers(0, 5))
+        order = 2 + int(rng.integers(0, degree - 2))
+        ne = (order + 1) * (degree + 1)
+        ode = random_balls(rng, ne * 2, L, -4, 4, "ulp", short_frac=0.2)
+        m = ode.mant.reshape(order + 1, degree + 1, 2, L)
+        t = ode.meta.reshape(order + 1, degree + 1, 2, 4)
+        for i in range(order + 1):
+            m[i, :i] = 0
+            t[i, :i] = (0, FLAG_ZERO, 0, 0)
+        v = api.acb_ode_valuation(ode, order, degree)
+        r = 4 + int(rng.integers(0, 10))
+        for nu in range(degree + 2):
+            for shift in (0, r):
+                po = oracle.indicial_polynomial(order, degree, ode, nu, shift)
+                ps = api.indicial_polynomial_batch(ode, order, degree, nu, shift, 1, True, driver=drv)
+                assert_same(po, ps, f"indicial_polynomial L={L} nu={nu} shift={shift}")
+                # f_nu(r) both ways: Horner of the polynomial at rho = r - shift vs direct evaluation
+                at_ = from_complex([r - shift], L)
+                hv = oracle.horner_batch(ps, at_, 1)
+                ev = oracle.indicial_polynomial_evaluate(order, degree, ode, nu, from_complex([r], L), 0)
+                for part in (0, 1):
+                    assert abs(hv.mid(part) - ev.mid(part)) <= hv.rad(part) + ev.rad(part)

@@ -81,3 +81,108 @@ class C:
         o = o if isinstance(o, C) else C(o)
         d = o.re * o.re + o.im * o.im
         return C((self.re * o.re + self.im * o.im) / d, (self.im * o.re - self.re * o.im) / d)
+
+
+# ---------------------------------------------------------------- general Frobenius, exact
+# The method of reference src/frobenius_solver.c:131-205 in exact arithmetic: polynomials in rho
+# are lists of C (lowest degree first).  Written from the mathematics (Frobenius' method with the
+# rescaling by f_0(rho + nu)), not from oracle/: used to check that every oracle ball contains the
+# exact value.
+def _ptrim(p):
+    while p and p[-1].re == 0 and p[-1].im == 0:
+        p = p[:-1]
+    return p
+
+
+def _padd(p, q, sign=1):
+    n = max(len(p), len(q))
+    out = []
+    for i in range(n):
+        a = p[i] if i < len(p) else C(0)
+        b = q[i] if i < len(q) else C(0)
+        out.append(a + b if sign > 0 else a - b)
+    return _ptrim(out)
+
+
+def _pmul(p, q):
+    if not p or not q:
+        return []
+    out = [C(0)] * (len(p) + len(q) - 1)
+    for i, a in enumerate(p):
+        for j, b in enumerate(q):
+            out[i + j] = out[i + j] + a * b
+    return _ptrim(out)
+
+
+def _peval(p, x):
+    r = C(0)
+    for a in reversed(p):
+        r = r * x + a
+    return r
+
+
+def _pder(p):
+    return _ptrim([p[i] * i for i in range(1, len(p))])
+
+
+def indicial_poly_exact(P, v, nu, shift):
+    """f_nu(rho + shift) as a polynomial in rho: sum_lam P[lam][lam+nu+v] (rho+shift)(rho+shift-1)...(lam factors)."""
+    order, degree = len(P) - 1, len(P[0]) - 1
+    k = nu + v
+    out = []
+    for lam in range(order + 1):
+        if not (0 <= lam + k <= degree):
+            continue
+        term = [P[lam][lam + k]]
+        for t in range(lam):
+            term = _pmul(term, [C(shift - t), C(1)])
+        out = _padd(out, term)
+    return out
+
+
+def frobenius_general_exact(P, v, rho, mul, M, n):
+    """gens[i][nu] (i < M, nu <= n) exactly as the reference's algorithm defines them."""
+    order, degree = len(P) - 1, len(P[0]) - 1
+    g_rho = [[] for _ in range(degree)]
+    g_rho[0] = [C(1)]
+    gens = [[C(0)] * (n + 1) for _ in range(M)]
+    gens[0][0] = C(1)
+    for nu in range(1, n + 1):
+        g_new = []
+        i = min(max(nu, 1), degree)
+        while i > 0:
+            g_new = _padd(g_new, _pmul(indicial_poly_exact(P, v, i, nu - i), g_rho[i - 1]), -1)
+            i -= 1
+        ind = indicial_poly_exact(P, v, 0, nu)
+        temp = _peval(ind, rho)
+        if not (temp.re == 0 and temp.im == 0):
+            ind = [a / temp for a in ind]
+            g_new = [a / temp for a in g_new]
+        all_zero = not g_new
+        for i in range(degree - 1, 0, -1):
+            g_rho[i] = _pmul(g_rho[i - 1], ind)
+            all_zero = all_zero and not g_rho[i]
+        g_rho[0] = list(g_new)
+        # update: gens[m] <- sum_k C(m,k) ind^(k)(rho) gens[m-k]   (Leibniz)
+        derivs, f = [], list(ind)
+        for k in range(M):
+            derivs.append(_peval(f, rho))
+            f = _pder(f)
+        from math import comb
+        new = []
+        for m in range(M):
+            row = [C(0)] * (n + 1)
+            for k in range(m + 1):
+                for j in range(n + 1):
+                    row[j] = row[j] + derivs[k] * comb(m, k) * gens[m - k][j]
+            new.append(row)
+        gens = new
+        # extend: gens[i][nu] = g_new^(i)(rho)
+        f = list(g_new)
+        for i in range(M):
+            gens[i][nu] = _peval(f, rho)
+            f = _pder(f)
+        if all_zero:
+            break
+    t = gens[M - mul][0]
+    return [[a / t for a in row] for row in gens]

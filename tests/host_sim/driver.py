@@ -37,6 +37,12 @@ def lib():
         L.cbsim_frobenius1_batch.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int, _u32p, _i32p]
         L.cbsim_horner_batch.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int, _u32p, _i32p, C.c_int, _u32p, _i32p, _u32p, _i32p]
         L.cbsim_ew.argtypes = [C.c_int, C.c_int, C.c_int64, _u32p, _i32p, _u32p, _i32p, _vp, _vp, _vp]
+        L.cbsim_frobenius_general_batch.argtypes = ([C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p,
+                                                    C.c_int, C.c_int, C.c_int, _u32p, _i32p])
+        L.cbsim_solution_op.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64, _u32p, _i32p,
+                                        _u32p, _i32p, _u32p, _i32p, C.c_int64]
+        L.cbsim_indicial_polynomial.argtypes = [C.c_int] * 4 + [C.c_int64, _u32p, _i32p, C.c_int, C.c_int64, C.c_int64,
+                                                                _u32p, _i32p]
         _lib = L
     return _lib
 
@@ -55,6 +61,18 @@ class SimDriver:
                    shared_rho, res_m, res_t):
         return lib().cbsim_frobenius1_batch(L, order, degree, valuation, n, batch, ode_m, ode_t, int(shared),
                                             rho_m, rho_t, int(shared_rho), res_m, res_t)
+
+    def frobenius_general(self, L, order, degree, valuation, n, batch, ode_m, ode_t, shared, rho_m, rho_t,
+                          shared_rho, mul, M, gens_m, gens_t):
+        return lib().cbsim_frobenius_general_batch(L, order, degree, valuation, n, batch, ode_m, ode_t, int(shared),
+                                                   rho_m, rho_t, int(shared_rho), mul, M, gens_m, gens_t)
+
+    def solution_op(self, which, L, batch, mul, M, cap, nu, rho_m, rho_t, gens_m, gens_t, f_m, f_t, fcap):
+        return lib().cbsim_solution_op(which, L, batch, mul, M, cap, nu, rho_m, rho_t, gens_m, gens_t, f_m, f_t, fcap)
+
+    def indicial_polynomial(self, L, order, degree, valuation, batch, ode_m, ode_t, shared, nu, shift, out_m, out_t):
+        return lib().cbsim_indicial_polynomial(L, order, degree, valuation, batch, ode_m, ode_t, int(shared), nu, shift,
+                                               out_m, out_t)
 
     def horner(self, L, length, npts, nder, f_m, f_t, shared_f, p_m, p_t, o_m, o_t):
         return lib().cbsim_horner_batch(L, length, npts, nder, f_m, f_t, int(shared_f), p_m, p_t, o_m, o_t)

@@ -3,6 +3,7 @@
 // that the device LOGIC can be checked against the oracle on a machine without a GPU.  It is
 // never linked into libcascade_b200.so and nothing in the product loads it.
 // Same array layout and arguments as the *_dev entry points of include/cascade_b200.h.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -120,6 +121,56 @@ int cbsim_frobenius1_batch(int L_, int order, int degree, int valuation, int64_t
     Tmp tmp;
     p.tmp = tmp.arr(L_, FROB_NTMP, 2 * batch);
     SIM_DISPATCH(L_, run<L>(batch, [&](int64_t i, Scratch<1> a, Scratch<1> b) { frobenius1_thread<L>(p, i, a, b); }));
+    return 0;
+}
+
+int cbsim_frobenius_general_batch(int L_, int order, int degree, int valuation, int64_t n, int64_t batch,
+                                  const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
+                                  const uint32_t* rho_mant, const cb_meta* rho_meta, int shared_rho, int mul, int M,
+                                  uint32_t* gens_mant, cb_meta* gens_meta) {
+    if (degree < 1 || degree > FROBG_MAXD || M < 1 || M > FROBG_MAXM || mul < 1 || mul > M) return CB200_EINVAL;
+    FrobGenParams p;
+    p.order = order; p.degree = degree; p.valuation = valuation; p.M = M; p.mul = mul; p.n = n; p.batch = batch;
+    p.plen = (int64_t)order * n + order + 2;
+    p.ode = CArr{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta),
+                 shared_ode ? (size_t)2 : (size_t)(2 * batch)};
+    p.rho = CArr{const_cast<uint32_t*>(rho_mant), (Meta*)const_cast<cb_meta*>(rho_meta),
+                 shared_rho ? (size_t)2 : (size_t)(2 * batch)};
+    p.gens = CArr{gens_mant, (Meta*)gens_meta, (size_t)(2 * batch)};
+    Tmp tmp;
+    p.wp = tmp.arr(L_, (int64_t)(degree + 3) * p.plen + FROBG_NTMP + M, 2 * batch);
+    // poison the polynomial workspace: reads beyond a polynomial's length must never happen
+    std::fill(tmp.m.begin(), tmp.m.end(), 0xDEADBEEFu);
+    SIM_DISPATCH(L_, run<L>(batch, [&](int64_t i, Scratch<1> a, Scratch<1> b) { frobenius_general_thread<L>(p, i, a, b); }));
+    return 0;
+}
+
+int cbsim_solution_op(int which, int L_, int64_t batch, int mul, int M, int64_t cap, int64_t nu,
+                      const uint32_t* rho_mant, const cb_meta* rho_meta, uint32_t* gens_mant, cb_meta* gens_meta,
+                      uint32_t* f_mant, cb_meta* f_meta, int64_t fcap) {
+    if (M < 0 || M > FROBG_MAXM) return CB200_EINVAL;
+    SolOpParams p;
+    p.which = which; p.M = M; p.mul = mul; p.batch = batch; p.cap = cap; p.fcap = which == 2 ? 0 : fcap; p.nu = nu;
+    p.rho = CArr{const_cast<uint32_t*>(rho_mant), (Meta*)const_cast<cb_meta*>(rho_meta), (size_t)(2 * batch)};
+    p.gens = CArr{gens_mant, (Meta*)gens_meta, (size_t)(2 * batch)};
+    p.f = CArr{f_mant, (Meta*)f_meta, (size_t)(2 * batch)};
+    Tmp tmp;
+    p.wp = tmp.arr(L_, FROBG_NTMP + M, 2 * batch);
+    SIM_DISPATCH(L_, run<L>(batch, [&](int64_t i, Scratch<1> a, Scratch<1> b) { solution_op_thread<L>(p, i, a, b); }));
+    return 0;
+}
+
+int cbsim_indicial_polynomial(int L_, int order, int degree, int valuation, int64_t batch, const uint32_t* ode_mant,
+                              const cb_meta* ode_meta, int shared_ode, int64_t nu, int64_t shift, uint32_t* out_mant,
+                              cb_meta* out_meta) {
+    IndicialParams p;
+    p.order = order; p.degree = degree; p.valuation = valuation; p.batch = batch; p.nu = nu; p.shift = shift;
+    p.ode = CArr{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta),
+                 shared_ode ? (size_t)2 : (size_t)(2 * batch)};
+    p.out = CArr{out_mant, (Meta*)out_meta, (size_t)(2 * batch)};
+    Tmp tmp;
+    p.wp = tmp.arr(L_, FROBG_NTMP, 2 * batch);
+    SIM_DISPATCH(L_, run<L>(batch, [&](int64_t i, Scratch<1> a, Scratch<1> b) { indicial_poly_thread<L>(p, i, a, b); }));
     return 0;
 }
 

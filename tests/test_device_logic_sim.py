@@ -65,3 +65,23 @@ def test_continuation(oracle, sim_driver, L):
 @pytest.mark.parametrize("L", [4, 32, 64])
 def test_exponent_overflow(oracle, sim_driver, L):
     cases.case_exponent_overflow(oracle, sim_driver, L)
+
+
+@pytest.mark.parametrize("L", [4, 32])
+def test_frobenius_general(oracle, sim_driver, L):
+    cases.case_frobenius_general(oracle, sim_driver, L, seed=41 + L, trials=4 if L == 4 else 2)
+
+
+@pytest.mark.parametrize("L", [4, 32])
+def test_frobenius_general_sweep(oracle, sim_driver, L):
+    cases.case_frobenius_general_sweep(oracle, sim_driver, L, seed=43 + L, n=8 if L == 4 else 6, batch=3)
+
+
+@pytest.mark.parametrize("L", [4, 32])
+def test_solution_ops(oracle, sim_driver, L):
+    cases.case_solution_ops(oracle, sim_driver, L, seed=47 + L, batch=2)
+
+
+@pytest.mark.parametrize("L", [4, 32])
+def test_indicial_polynomial(oracle, sim_driver, L):
+    cases.case_indicial_polynomial(oracle, sim_driver, L, seed=53 + L, trials=3 if L == 4 else 1)

@@ -36,3 +36,33 @@ def test_frobenius_continuation_evaluate():
     # J0(1.5), J0'(1.5) = -J1(1.5); inputs were doubles, so agreement to ~1e-15
     assert abs(vals["J0(1.5)"][0] - 0.5118276717359181) < 1e-13
     assert abs(vals["J0'(1.5)"][0] - (-0.5579365079100996)) < 1e-13
+
+
+def test_logarithmic_frobenius_and_solution_bookkeeping():
+    """acb_ode_solve_frobenius with M = 2, indicial_polynomial, _acb_ode_solution_extend/_update/_normalize
+    through the reference's names (reference tests/frobenius.c, tests/indicial_polynomial.c,
+    tests/solution_extend.c, tests/solution_update.c)."""
+    from fractions import Fraction as F
+    out = build_and_run("frobenius_log_example")
+    rows = [line.split() for line in out.strip().splitlines()]
+    gens = {int(r[1]): (float(r[2]), float(r[3]), float(r[4])) for r in rows if r[0] == "gens"}
+    a, b, n = F(3, 8), F(5, 16), 12
+    g, dg = F(1), F(0)
+    dP = sum(F(2, nu) for nu in range(1, n + 1))  # the reference's rescaling, see tests/test_oracle_golden.py
+    for k in range(n + 1):
+        assert abs(gens[k][0] - float(g)) <= 1e-15 * abs(float(g))
+        want = float(dg + dP * g)
+        assert abs(gens[k][1] - want) <= 1e-14 * max(1.0, abs(want)) and gens[k][2] < 1e-290
+        ld = 1 / (k + a) + 1 / (k + b) - F(2, k + 1)
+        fac = (k + a) * (k + b) / F((k + 1) ** 2)
+        dg = dg * fac + g * fac * ld
+        g = g * fac
+    vals = {r[0] + (r[1] if r[0] in ("indicial", "extend", "update") else ""): r for r in rows if r[0] != "gens"}
+    assert vals["indicial_len"][1] == "3"
+    assert [float(vals[f"indicial{k}"][2]) for k in range(3)] == [9.0, 6.0, 1.0]
+    assert float(vals["indicial_at_2"][1]) == 25.0 and float(vals["indicial_at_2"][2]) == 25.0
+    assert [float(vals[f"extend{i}"][2]) for i in range(3)] == [2.75, 5.0, 6.0]
+    assert all(vals[f"extend{i}"][3] == "5" for i in range(3)) and vals["extend_consumed"][1] == "0"
+    # Leibniz with f = rho at 1/2: [f g, f g' + f' g, f g'' + 2 f' g'] = [1.375, 5.25, 13]
+    assert [float(vals[f"update{i}"][2]) for i in range(3)] == [1.375, 5.25, 13.0]
+    assert vals["update_consumed"][1] == "0" and vals["normalize_finite"][1] == "0"

@@ -67,3 +67,23 @@ def test_continuation(oracle, gpu_driver, L):
 @pytest.mark.parametrize("L", [4, 32, 64, 128])
 def test_exponent_overflow(oracle, gpu_driver, L):
     cases.case_exponent_overflow(oracle, gpu_driver, L)
+
+
+@pytest.mark.parametrize("L", [4, 32, 64])
+def test_frobenius_general(oracle, gpu_driver, L):
+    cases.case_frobenius_general(oracle, gpu_driver, L, seed=41 + L, trials=4 if L < 64 else 2)
+
+
+@pytest.mark.parametrize("L", [4, 32, 128])
+def test_frobenius_general_sweep(oracle, gpu_driver, L):
+    cases.case_frobenius_general_sweep(oracle, gpu_driver, L, seed=43 + L, n=10 if L < 128 else 5, batch=40)
+
+
+@pytest.mark.parametrize("L", [4, 32, 64])
+def test_solution_ops(oracle, gpu_driver, L):
+    cases.case_solution_ops(oracle, gpu_driver, L, seed=47 + L, batch=35)
+
+
+@pytest.mark.parametrize("L", [4, 32])
+def test_indicial_polynomial(oracle, gpu_driver, L):
+    cases.case_indicial_polynomial(oracle, gpu_driver, L, seed=53 + L, trials=3)

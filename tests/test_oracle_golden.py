@@ -134,3 +134,63 @@ def test_gmp_and_plain_backends_agree(oracle):
     a = oracle.fuchs_batch(2, 2, 30, ode, init, 2, True)[1]
     b = oracle.fuchs_batch(2, 2, 30, ode, init, 2, True, plain=True)[1]
     assert a.same_as(b)
+
+
+@pytest.mark.parametrize("L", [4, 32])
+def test_general_frobenius_contains_exact_rationals(oracle, L):
+    """acb_ode_solve_frobenius with M = 2 on the operators of reference tests/frobenius.c:24-31
+    (dyadic coefficients): every ball of gens[0], gens[1] must contain the exact value of the same
+    method carried out in rational arithmetic (tests/exact_model.py), and gens[0] shifted by rho
+    must pass the reference's acceptance test acb_ode_solves (tests/frobenius.c:37-40)."""
+    from tests.cases import _frobenius_test_operator
+    from tests.exact_model import frobenius_general_exact
+    rng = np.random.default_rng(3)
+    for trial in range(4):
+        degree = 3 + int(rng.integers(0, 3))
+        order = 2 + int(rng.integers(0, degree - 2))
+        ode = _frobenius_test_operator(rng, L, order, degree, dyadic=True)
+        P = [[C(ode.mid(2 * (i * (degree + 1) + j)), ode.mid(2 * (i * (degree + 1) + j) + 1))
+              for j in range(degree + 1)] for i in range(order + 1)]
+        s_rho, n = order - 2, 2 + int(rng.integers(0, 9))
+        gens = oracle.frobenius_general_batch(order, degree, n, ode, from_complex([s_rho], L), 1, True, True, 2, 2)
+        ex = frobenius_general_exact(P, 0, C(s_rho), 2, 2, n)
+        for i in range(2):
+            for k in range(n + 1):
+                s = 2 * (i * (n + 1) + k)
+                assert gens.contains(s, ex[i][k].re) and gens.contains(s + 1, ex[i][k].im), (trial, i, k)
+        shifted = Balls.concat([Balls.zeros(2 * s_rho, L), gens[0:2 * (n + 1)]])
+        assert oracle.ode_solves(order, degree, ode, shifted, n)
+
+
+def test_general_frobenius_log_solution_of_hypgeom(oracle):
+    """c = 1: rho = 0 is a double indicial root of the hypergeometric equation.  gens[0] must be
+    2F1(a, b; 1; z).  The reference rescales by f_0(rho + nu) / f_0(rho_0 + nu) at every step
+    (src/frobenius_solver.c:170-176, :188), i.e. it differentiates P(rho) g_k(rho) with
+    P = prod_nu f_0(rho + nu) / f_0(nu), P(0) = 1, P'(0) = sum_{nu <= n} 2 / nu (f_0(rho) = rho^2 here):
+    gens[1][k] = g_k'(0) + P'(0) g_k(0) -- the second solution plus a multiple of the first."""
+    L = 32
+    a, b = F(3, 8), F(5, 16)
+    ode = oracle.example("hypgeom", L, 0, from_complex([a, b, 1], L))
+    n = 12
+    gens = oracle.frobenius_general_batch(2, 2, n, ode, from_complex([0], L), 1, True, True, 2, 2)
+    # g_k(rho) = prod_{j<k} (rho + j + a)(rho + j + b) / (rho + j + 1)^2; gens[0][k] = g_k(0), gens[1][k] = g_k'(0)
+    g, dg = F(1), F(0)
+    dP = sum(F(2, nu) for nu in range(1, n + 1))
+    for k in range(n + 1):
+        assert gens.contains(2 * k, g), k
+        assert gens.contains(2 * ((n + 1) + k), dg + dP * g), k
+        # logarithmic derivative of the next factor at rho = 0
+        ld = 1 / (k + a) + 1 / (k + b) - F(2, k + 1)
+        fac = (k + a) * (k + b) / F((k + 1) ** 2)
+        dg = dg * fac + g * fac * ld
+        g = g * fac
+
+
+def test_gmp_and_plain_backends_agree_general_frobenius(oracle):
+    from tests.cases import _frobenius_test_operator
+    rng = np.random.default_rng(11)
+    ode = _frobenius_test_operator(rng, 32, 2, 4)
+    rho = from_complex([0], 32)
+    a = oracle.frobenius_general_batch(2, 4, 9, ode, rho, 1, True, True, 2, 3)
+    b = oracle.frobenius_general_batch(2, 4, 9, ode, rho, 1, True, True, 2, 3, plain=True)
+    assert a.same_as(b)
