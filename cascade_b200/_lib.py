@@ -22,13 +22,14 @@ _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 _vp = C.c_void_p
 
 SYMBOLS = [
-    "cb200_version", "cb200_device_count", "cb200_kernel_launches",
+    "cb200_version", "cb200_device_count", "cb200_kernel_launches", "cb200_debug_rr_stats",
     "cb200_fuchs_workspace_bytes", "cb200_frobenius_workspace_bytes",
     "cb200_horner_workspace_bytes", "cb200_ew_workspace_bytes",
     "cb200_fuchs_batch_dev", "cb200_fuchs_batch_host",
     "cb200_fuchs_intop_batch_dev", "cb200_fuchs_intop_batch_host",
     "cb200_continuation_workspace_bytes", "cb200_continuation_dev", "cb200_continuation_host",
     "cb200_frobenius1_batch_dev", "cb200_frobenius1_batch_host",
+    "cb200_frobenius1_rhs_batch_dev", "cb200_frobenius1_rhs_batch_host",
     "cb200_horner_batch_dev", "cb200_horner_batch_host",
     "cb200_ew_dev", "cb200_ew_host",
     "cb200_frobenius_general_workspace_bytes", "cb200_frobenius_general_batch_dev",
@@ -73,6 +74,8 @@ def lib() -> C.CDLL:
                                           _u32p, _i32p, _u32p, _i32p, C.c_int]
     L.cb200_frobenius1_batch_dev.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_size_t, _vp]
     L.cb200_frobenius1_batch_host.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int]
+    L.cb200_frobenius1_rhs_batch_dev.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_int64, C.c_int, _vp, _vp, _vp, C.c_size_t, _vp]
+    L.cb200_frobenius1_rhs_batch_host.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int, _vp, _vp, C.c_int64, C.c_int, _u32p, _i32p, C.c_int]
     L.cb200_horner_batch_dev.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]
     L.cb200_horner_batch_host.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int, _u32p, _i32p, C.c_int, _u32p, _i32p, _u32p, _i32p, C.c_int]
     L.cb200_ew_dev.argtypes = [C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]

@@ -42,10 +42,12 @@ class HostBufferDriver:
                                                   y_m, y_t, self.device)
 
     def frobenius1(self, L, order, degree, valuation, n, batch, ode_m, ode_t, shared, rho_m, rho_t,
-                   shared_rho, res_m, res_t):
-        return _lib.lib().cb200_frobenius1_batch_host(L, order, degree, valuation, n, batch, ode_m, ode_t,
-                                                      int(shared), rho_m, rho_t, int(shared_rho), res_m,
-                                                      res_t, self.device)
+                   shared_rho, res_m, res_t, rhs_m=None, rhs_t=None, rhs_len=0, shared_rhs=False):
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        return _lib.lib().cb200_frobenius1_rhs_batch_host(L, order, degree, valuation, n, batch, ode_m, ode_t,
+                                                          int(shared), rho_m, rho_t, int(shared_rho), vp(rhs_m),
+                                                          vp(rhs_t), rhs_len, int(shared_rhs), res_m, res_t,
+                                                          self.device)
 
     def frobenius_general(self, L, order, degree, valuation, n, batch, ode_m, ode_t, shared, rho_m, rho_t,
                           shared_rho, mul, M, gens_m, gens_t):
@@ -171,9 +173,11 @@ def acb_ode_solve_fuchs_batch(ode: Balls, init: Balls, order: int, degree: int, 
 
 def acb_ode_solve_frobenius1_batch(ode: Balls, rho: Balls, order: int, degree: int, n: int, batch: int,
                                    shared_ode: bool = True, shared_rho: bool = False,
-                                   valuation: int | None = None, driver=None) -> Balls:
-    """Batched ``_acb_ode_solve_frobenius`` with a zero right-hand side and ``M == 1``
-    (reference src/frobenius_solver.c:72-121).  ``rho``: ``[batch or 1]`` complex balls."""
+                                   valuation: int | None = None, driver=None, rhs: Balls | None = None) -> Balls:
+    """Batched ``_acb_ode_solve_frobenius`` with ``M == 1`` (reference src/frobenius_solver.c:72-121).
+    ``rho``: ``[batch or 1]`` complex balls.  ``rhs``: optional right-hand side series, ``[batch][rhs_len]``;
+    instances whose rhs is the zero polynomial take the homogeneous branch (g_0 = 1), the others use
+    rho - valuation and g_0 = rhs_0 / f_0(rho) as the reference does (:86-96)."""
     drv = driver or default_driver()
     L = ode.L
     v = acb_ode_valuation(ode, order, degree) if valuation is None else valuation
@@ -182,8 +186,14 @@ def acb_ode_solve_frobenius1_batch(ode: Balls, rho: Balls, order: int, degree: i
     rho_m, rho_t = pack_entries(rho, 1, 2 * nr)
     res_m = np.zeros((n + 1, L, 2 * batch), np.uint32)
     res_t = np.zeros((n + 1, 2 * batch, 4), np.int32)
-    _lib.check(drv.frobenius1(L, order, degree, v, n, batch, ode_m, ode_t, shared_ode, rho_m, rho_t,
-                              shared_rho, res_m, res_t), "acb_ode_solve_frobenius1_batch")
+    if rhs is None:
+        rc = drv.frobenius1(L, order, degree, v, n, batch, ode_m, ode_t, shared_ode, rho_m, rho_t, shared_rho, res_m, res_t)
+    else:
+        hl = rhs.n_slots // (2 * batch)
+        h_m, h_t = pack_entries(instance_major_to_entry_major(rhs, batch, hl), hl, 2 * batch)
+        rc = drv.frobenius1(L, order, degree, v, n, batch, ode_m, ode_t, shared_ode, rho_m, rho_t, shared_rho, res_m,
+                            res_t, h_m, h_t, hl, False)
+    _lib.check(rc, "acb_ode_solve_frobenius1_batch")
     return entry_major_to_instance_major(unpack_entries(L, res_m, res_t), batch, n + 1)
 
 

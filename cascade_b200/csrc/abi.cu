@@ -17,6 +17,7 @@ static_assert(sizeof(cb_meta) == sizeof(Meta), "meta layout");
 namespace {
 
 std::atomic<uint64_t> g_launches{0};
+unsigned long long* g_rr_stats = nullptr;  // development counters, see CB200_RR_STATS
 
 const LaunchTable* table_for(int L) {
     switch (L) {
@@ -76,6 +77,18 @@ int cb200_device_count(void) {
 
 uint64_t cb200_kernel_launches(void) { return g_launches.load(); }
 
+// development aid: counters of the reduced-radix fused dot product (CB200_RR_STATS=1); out[0] accepted, out[1] rejected
+int cb200_debug_rr_stats(uint64_t* out) {
+    out[0] = out[1] = 0;
+    if (!g_rr_stats) return 0;
+    unsigned long long h[4];
+    cudaError_t e = cudaMemcpy(h, g_rr_stats, sizeof(h), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return (int)e;
+    out[0] = h[0];
+    out[1] = h[1];
+    return 0;
+}
+
 size_t cb200_fuchs_workspace_bytes(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
                                    int shared_ode) {
     (void)order;
@@ -127,6 +140,21 @@ int cb200_fuchs_batch_dev(int L_, int order, int degree, int valuation, int64_t 
         sp.res = CArr{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
         sp.kind = tp.kind;
         sp.gcols = (uint32_t*)w;
+        {
+            // the reduced-radix fused dot product (cb_rr.cuh) is bit-identical but measured slower than
+            // the carry-chain path inside this kernel: opt-in for experiments
+            const char* e = getenv("CB200_RR");
+            sp.no_rr = (e && e[0] == '1') ? 0 : 1;
+            sp.stats = nullptr;
+            const char* st = getenv("CB200_RR_STATS");
+            if (st && st[0] == '1') {
+                static unsigned long long* dstats = nullptr;
+                if (!dstats && cudaMalloc(&dstats, 4 * sizeof(unsigned long long)) == cudaSuccess)
+                    cudaMemset(dstats, 0, 4 * sizeof(unsigned long long));
+                sp.stats = dstats;
+                g_rr_stats = dstats;
+            }
+        }
         g_launches.fetch_add(batch > 0);
         return table_for(L_)->fuchs_shared(sp, (cudaStream_t)stream);
     }
@@ -166,12 +194,14 @@ int cb200_fuchs_intop_batch_dev(int L_, int order, int degree, int valuation, in
     return table_for(L_)->fuchs_intop(p, (cudaStream_t)stream);
 }
 
-int cb200_frobenius1_batch_dev(int L_, int order, int degree, int valuation, int64_t n, int64_t batch,
-                               const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
-                               const uint32_t* rho_mant, const cb_meta* rho_meta, int shared_rho,
-                               uint32_t* res_mant, cb_meta* res_meta, void* workspace,
-                               size_t workspace_bytes, void* stream) {
-    if (!supported_L(L_) || order < 1 || degree < 1 || batch < 0 || n < 0) return CB200_EINVAL;
+int cb200_frobenius1_rhs_batch_dev(int L_, int order, int degree, int valuation, int64_t n, int64_t batch,
+                                   const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
+                                   const uint32_t* rho_mant, const cb_meta* rho_meta, int shared_rho,
+                                   const uint32_t* rhs_mant, const cb_meta* rhs_meta, int64_t rhs_len, int shared_rhs,
+                                   uint32_t* res_mant, cb_meta* res_meta, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+    if (!supported_L(L_) || order < 1 || degree < 1 || batch < 0 || n < 0 || rhs_len < 0) return CB200_EINVAL;
+    if (rhs_len > 0 && (!rhs_mant || !rhs_meta)) return CB200_EINVAL;
     if (workspace_bytes < cb200_frobenius_workspace_bytes(L_, batch)) return CB200_ENOMEM;
     FrobParams p;
     p.order = order;
@@ -184,10 +214,22 @@ int cb200_frobenius1_batch_dev(int L_, int order, int degree, int valuation, int
     p.rho = CArr{const_cast<uint32_t*>(rho_mant), (Meta*)const_cast<cb_meta*>(rho_meta),
                  shared_rho ? (size_t)2 : (size_t)(2 * batch)};
     p.res = CArr{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
+    p.rhs = CArr{const_cast<uint32_t*>(rhs_mant), (Meta*)const_cast<cb_meta*>(rhs_meta),
+                 shared_rhs ? (size_t)2 : (size_t)(2 * batch)};
+    p.rhs_len = rhs_len;
     char* w = (char*)workspace;
     p.tmp = carve(w, L_, FROB_NTMP, 2 * batch);
     g_launches.fetch_add(batch > 0);
     return table_for(L_)->frobenius1(p, (cudaStream_t)stream);
+}
+int cb200_frobenius1_batch_dev(int L_, int order, int degree, int valuation, int64_t n, int64_t batch,
+                               const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
+                               const uint32_t* rho_mant, const cb_meta* rho_meta, int shared_rho,
+                               uint32_t* res_mant, cb_meta* res_meta, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    return cb200_frobenius1_rhs_batch_dev(L_, order, degree, valuation, n, batch, ode_mant, ode_meta, shared_ode, rho_mant,
+                                          rho_meta, shared_rho, nullptr, nullptr, 0, 0, res_mant, res_meta, workspace,
+                                          workspace_bytes, stream);
 }
 
 // ------------------------------------------------------------------ general Frobenius (M > 1)
@@ -462,20 +504,23 @@ int cb200_fuchs_intop_batch_host(int L, int order, int degree, int valuation, in
     return (int)cudaDeviceSynchronize();
 }
 
-int cb200_frobenius1_batch_host(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
-                                const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
-                                const uint32_t* rho_mant, const cb_meta* rho_meta, int shared_rho,
-                                uint32_t* res_mant, cb_meta* res_meta, int device) {
-    if (!supported_L(L) || order < 1 || degree < 1 || batch < 0 || n < 0) return CB200_EINVAL;
+int cb200_frobenius1_rhs_batch_host(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
+                                    const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
+                                    const uint32_t* rho_mant, const cb_meta* rho_meta, int shared_rho,
+                                    const uint32_t* rhs_mant, const cb_meta* rhs_meta, int64_t rhs_len, int shared_rhs,
+                                    uint32_t* res_mant, cb_meta* res_meta, int device) {
+    if (!supported_L(L) || order < 1 || degree < 1 || batch < 0 || n < 0 || rhs_len < 0) return CB200_EINVAL;
     CK(cudaSetDevice(device));
-    int64_t So = shared_ode ? 2 : 2 * batch, Sr = shared_rho ? 2 : 2 * batch, S = 2 * batch;
+    int64_t So = shared_ode ? 2 : 2 * batch, Sr = shared_rho ? 2 : 2 * batch, Sh = shared_rhs ? 2 : 2 * batch, S = 2 * batch;
     int64_t ne = (int64_t)(order + 1) * (degree + 1);
-    DevBuf om, ot, pm, pt, rm, rt, ws;
+    DevBuf om, ot, pm, pt, hm, ht, rm, rt, ws;
     size_t wsb = cb200_frobenius_workspace_bytes(L, batch);
     CK(om.alloc(arr_mant_bytes(L, ne, So)));
     CK(ot.alloc(arr_meta_bytes(ne, So)));
     CK(pm.alloc(arr_mant_bytes(L, 1, Sr)));
     CK(pt.alloc(arr_meta_bytes(1, Sr)));
+    CK(hm.alloc(arr_mant_bytes(L, rhs_len, Sh)));
+    CK(ht.alloc(arr_meta_bytes(rhs_len, Sh)));
     CK(rm.alloc(arr_mant_bytes(L, n + 1, S)));
     CK(rt.alloc(arr_meta_bytes(n + 1, S)));
     CK(ws.alloc(wsb));
@@ -483,13 +528,25 @@ int cb200_frobenius1_batch_host(int L, int order, int degree, int valuation, int
     CK(cudaMemcpy(ot.p, ode_meta, arr_meta_bytes(ne, So), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(pm.p, rho_mant, arr_mant_bytes(L, 1, Sr), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(pt.p, rho_meta, arr_meta_bytes(1, Sr), cudaMemcpyHostToDevice));
-    int rc = cb200_frobenius1_batch_dev(L, order, degree, valuation, n, batch, (uint32_t*)om.p, (cb_meta*)ot.p,
-                                        shared_ode, (uint32_t*)pm.p, (cb_meta*)pt.p, shared_rho,
-                                        (uint32_t*)rm.p, (cb_meta*)rt.p, ws.p, wsb, nullptr);
+    if (rhs_len > 0) {
+        CK(cudaMemcpy(hm.p, rhs_mant, arr_mant_bytes(L, rhs_len, Sh), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ht.p, rhs_meta, arr_meta_bytes(rhs_len, Sh), cudaMemcpyHostToDevice));
+    }
+    int rc = cb200_frobenius1_rhs_batch_dev(L, order, degree, valuation, n, batch, (uint32_t*)om.p, (cb_meta*)ot.p,
+                                            shared_ode, (uint32_t*)pm.p, (cb_meta*)pt.p, shared_rho, (uint32_t*)hm.p,
+                                            (cb_meta*)ht.p, rhs_len, shared_rhs, (uint32_t*)rm.p, (cb_meta*)rt.p, ws.p, wsb,
+                                            nullptr);
     if (rc) return rc;
     CK(cudaMemcpy(res_mant, rm.p, arr_mant_bytes(L, n + 1, S), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(res_meta, rt.p, arr_meta_bytes(n + 1, S), cudaMemcpyDeviceToHost));
     return (int)cudaDeviceSynchronize();
+}
+int cb200_frobenius1_batch_host(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
+                                const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
+                                const uint32_t* rho_mant, const cb_meta* rho_meta, int shared_rho,
+                                uint32_t* res_mant, cb_meta* res_meta, int device) {
+    return cb200_frobenius1_rhs_batch_host(L, order, degree, valuation, n, batch, ode_mant, ode_meta, shared_ode, rho_mant,
+                                           rho_meta, shared_rho, nullptr, nullptr, 0, 0, res_mant, res_meta, device);
 }
 
 int cb200_frobenius_general_batch_host(int L, int order, int degree, int valuation, int64_t n, int64_t batch,

@@ -1314,3 +1314,5 @@ CB_NOINLINE Meta arb_div_u64(DST dst, OpdT<XS> x, uint64_t d, bool dneg, SCR S0)
 }
 
 }  // namespace cb
+
+#include "cb_rr.cuh"

@@ -63,6 +63,9 @@ CB_HD WRef wim(const CRef& x) { return WRef{x.m + 1, x.stride}; }
 // does this precision use truncated products (with the exact path as per-lane fallback)?
 template <int L>
 constexpr bool use_trunc() { return L >= 16 && L <= 32; }
+// does the recurrence kernel try the reduced-radix fused dot product (cb_rr.cuh) first?
+template <int L>
+constexpr bool use_rr() { return L == 32; }
 
 // fused dot product of the general kernels: truncated products first (S0 parks the first one),
 // the exact shared-memory version when the guard-bit proof fails
@@ -113,6 +116,7 @@ CB_HD void acb_zero(const CRef& z) {
     st_meta(z.t, meta_zero());
     st_meta(z.t + 1, meta_zero());
 }
+CB_HD bool acb_is_exact_zero(const CRef& x) { return is_exact_zero(ld_meta(x.t)) && is_exact_zero(ld_meta(x.t + 1)); }
 template <int L>
 CB_HD void acb_one(const CRef& z) {
     acb_zero<L>(z);
@@ -332,18 +336,42 @@ struct FuchsSharedParams {
     CArr res;   // n+1 entries, S = 2*batch
     const int32_t* kind;
     uint32_t* gcols;  // 2 * (2L+3) words per instance, [word][instance]: columns of the general path
+    int no_rr;        // development switch (CB200_NO_RR=1): skip the reduced-radix products
+    unsigned long long* stats;  // development counters (CB200_RR_STATS=1) or nullptr: [0] rr accepted, [1] rr rejected
+};
+struct RecCtl {
+    bool rr;
+    unsigned long long* stats;
 };
 
 
 // one fused dot product of the recurrence: truncated products with the exact general path as the
 // per-lane fallback (L = 16..32), or the exact in-shared-memory version (other precisions)
 template <int L, class SCR, class DST>
-CB_HD Meta rec_fdot2(DST dst, Opd x1, OpdS y1, Opd x2, OpdS y2, bool neg2, SCR S0, SCR S1, GScratch G0, GScratch G1) {
+CB_HD Meta rec_fdot2(DST dst, Opd x1, OpdS y1, Opd x2, OpdS y2, bool neg2, SCR S0, SCR S1, GScratch G0, GScratch G1,
+                     RecCtl ctl = RecCtl{true, nullptr}) {
     if constexpr (use_trunc<L>()) {
-        bool ok;
-        Meta t = arb_fdot2_trunc<L, SCR, RRef, RFix<2>>(dst, x1, y1, x2, y2, neg2, S0, &ok);
-        CB_COUNT(ok ? 4 : 5);
-        if (!ok) t = arb_fdot2_general<L>(dst, x1, dyn(y1), x2, dyn(y2), neg2, G0, G1);
+        bool ok = false;
+        Meta t;
+        if constexpr (use_rr<L>()) {
+            // reduced-radix products (plain IMAD.WIDE, no carry chains) first -- unless a shared
+            // multiplier is zero or short (exact products: the carry-chain path knows how to trust
+            // them); y1, y2 are the same for every lane, so this choice does not diverge
+            const bool dense = !(is_zero_mid(y1.t) || is_zero_mid(y2.t) || is_nan(y1.t) || is_nan(y2.t) ||
+                                 tz_hint(y1.t.flags) + tz_hint(y2.t.flags) > 0);
+            if (dense && ctl.rr) {
+                t = arb_fdot2_rr<L, RRef, RFix<2>>(dst, x1, y1, x2, y2, neg2, &ok);
+                CB_COUNT(ok ? 6 : 7);
+#if defined(__CUDA_ARCH__)
+                if (ctl.stats) atomicAdd(ctl.stats + (ok ? 0 : 1), 1ull);
+#endif
+            }
+        }
+        if (!ok) {
+            t = arb_fdot2_trunc<L, SCR, RRef, RFix<2>>(dst, x1, y1, x2, y2, neg2, S0, &ok);
+            CB_COUNT(ok ? 4 : 5);
+            if (!ok) t = arb_fdot2_general<L>(dst, x1, dyn(y1), x2, dyn(y2), neg2, G0, G1);
+        }
         return t;
     } else {
         return fdot2_auto<L>(dst, x1, dyn(y1), x2, dyn(y2), neg2, S0, S1);
@@ -357,6 +385,7 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
     const size_t slot = 2 * (size_t)inst;
     const int v = p.valuation, W = p.degree - v;
     SCR accRe = A0, accIm = A1, spare = A2;
+    const RecCtl ctl{p.no_rr == 0, p.stats};
 #pragma unroll 1
     for (int64_t bmax = -v; bmax <= p.n; bmax++) {
         int64_t e = bmax + v;
@@ -371,7 +400,7 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
             OpdS c = re_of_shared(y), d = im_of_shared(y);
             // real part: acc.re -= a c - b d
             Meta pr = rec_fdot2<L>(WRef{spare.generic(), SCR::GSTRIDE}, a, c, b, d, true, use_trunc<L>() ? spare : S0,
-                                   S1, G0, G1);
+                                   S1, G0, G1, ctl);
             if (k == 0) {  // 0 - x = -x exactly: adopt the column, flip the sign
                 SCR t = accRe;
                 accRe = spare;
@@ -389,7 +418,7 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
             }
             // imaginary part: acc.im -= a d + b c
             Meta pi = rec_fdot2<L>(WRef{spare.generic(), SCR::GSTRIDE}, a, d, b, c, false,
-                                   use_trunc<L>() ? spare : S0, S1, G0, G1);
+                                   use_trunc<L>() ? spare : S0, S1, G0, G1, ctl);
             if (k == 0) {
                 SCR t = accIm;
                 accIm = spare;
@@ -411,8 +440,8 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
         if (p.kind[bmax + v] == 1) {
             CRef y = at<L>(p.tbl, base + W + 1, 0);
             OpdS c = re_of_shared(y), d = im_of_shared(y);
-            Meta tr = rec_fdot2<L>(wre(out), xa, c, xb, d, true, use_trunc<L>() ? spare : S0, S1, G0, G1);
-            Meta ti = rec_fdot2<L>(wim(out), xa, d, xb, c, false, use_trunc<L>() ? spare : S0, S1, G0, G1);
+            Meta tr = rec_fdot2<L>(wre(out), xa, c, xb, d, true, use_trunc<L>() ? spare : S0, S1, G0, G1, ctl);
+            Meta ti = rec_fdot2<L>(wim(out), xa, d, xb, c, false, use_trunc<L>() ? spare : S0, S1, G0, G1, ctl);
             st_meta(out.t, tr);
             st_meta(out.t + 1, ti);
         } else {
@@ -534,8 +563,10 @@ struct FrobParams {
     CArr rho;  // 1 entry, S = 2*batch or 2
     CArr res;  // n+1 entries
     CArr tmp;  // FROB_NTMP entries
+    CArr rhs;  // right-hand side series: rhs_len entries, S = 2*batch or 2 (ignored when rhs_len == 0)
+    int64_t rhs_len;
 };
-constexpr int FROB_NTMP = 6;
+constexpr int FROB_NTMP = 7;
 
 // result may be one of (o1, o2): returns which holds f_nu(rho + shift)
 template <int L, class SCR, class PRM>
@@ -566,10 +597,25 @@ CB_HD void frobenius1_thread(const FrobParams& p, int64_t inst, SCR S0, SCR S1) 
     CRef gnew = at<L>(p.tmp, 0, slot), o1 = at<L>(p.tmp, 1, slot), o2 = at<L>(p.tmp, 2, slot),
          t = at<L>(p.tmp, 3, slot), kb = at<L>(p.tmp, 4, slot), prod = at<L>(p.tmp, 5, slot);
     CRef rho = at<L>(p.rho, 0, rslot);
-    acb_one<L>(at<L>(p.res, 0, slot));  // homogeneous case: g_0 = 1 (src/frobenius_solver.c:84-85)
+    // length of the right-hand side as acb_poly sees it (trailing exact zeros do not count)
+    const size_t hslot = (p.rhs_len > 0 && p.rhs.S == 2) ? 0 : slot;
+    int64_t rl = p.rhs_len;
+    while (rl > 0 && acb_is_exact_zero(at<L>(p.rhs, rl - 1, hslot))) rl--;
+    if (rl == 0) {
+        acb_one<L>(at<L>(p.res, 0, slot));  // homogeneous case: g_0 = 1 (src/frobenius_solver.c:84-85)
+    } else {
+        // rho -= v; g_0 = rhs_0 / f_0(rho)   (src/frobenius_solver.c:88-95)
+        CRef radj = at<L>(p.tmp, 6, slot);
+        acb_add_si<L>(radj, rho, -(int64_t)p.valuation, kb, S0, S1);
+        rho = radj;
+        CRef ind = indicial_eval<L>(p, oslot, 0, rho, 0, o1, o2, t, kb, S0, S1);
+        CRef spare = (ind.m == o1.m) ? o2 : o1;
+        acb_div<L>(at<L>(p.res, 0, slot), at<L>(p.rhs, 0, hslot), ind, spare, S0, S1);
+    }
 #pragma unroll 1
     for (int64_t nu = 1; nu <= p.n; nu++) {
-        acb_zero<L>(gnew);
+        if (nu < rl) acb_set<L>(gnew, at<L>(p.rhs, nu, hslot));
+        else acb_zero<L>(gnew);
         int64_t i = clampi(nu, 1, p.degree);
         CRef ind = indicial_eval<L>(p, oslot, i, rho, nu - i, o1, o2, t, kb, S0, S1);
 #pragma unroll 1
@@ -606,7 +652,6 @@ struct FrobGenParams {
     CArr wp;       // (degree + 3) * plen + FROBG_NTMP + M entries, S = 2*batch
 };
 
-CB_HD bool acb_is_exact_zero(const CRef& x) { return is_exact_zero(ld_meta(x.t)) && is_exact_zero(ld_meta(x.t + 1)); }
 // exact |mid| <= rad (arb_contains_zero); an indeterminate ball contains everything
 template <int L>
 CB_HD bool arb_contains_zero(const uint32_t* m, size_t stride, const Meta& t) {

@@ -501,16 +501,20 @@ void indicial_polynomial_evaluate(acb_t result, acb_ode_t ODE, slong nu, acb_t r
 }
 
 void _acb_ode_solve_frobenius(acb_poly_t res, acb_ode_t ODE, acb_ode_solution_t rhs, slong sol_degree, slong prec) {
-    if (!acb_poly_is_zero(rhs->gens)) die("_acb_ode_solve_frobenius with a nonzero right-hand side (not on the device yet)", -1);
     int L = limbs_of(prec);
     slong v = acb_ode_valuation(ODE);
     slong ne = (ODE->order + 1) * (ODE->degree + 1);
-    HostArr ho(L, ne, 2), hrho(L, 1, 2), hr(L, sol_degree + 1, 2);
+    // the right-hand side is marshalled before res is written: res may alias rhs->gens
+    // (reference src/frobenius_solver.c:127 passes sol->gens as both)
+    slong hl = rhs->gens->length;
+    HostArr ho(L, ne, 2), hrho(L, 1, 2), hr(L, sol_degree + 1, 2), hh(L, hl > 0 ? hl : 1, 2);
     for (slong e = 0; e < ne; e++) ho.put(e, 0, ODE->polys + e);
+    for (slong k = 0; k < hl; k++) hh.put(k, 0, rhs->gens->coeffs + k);
     hrho.put(0, 0, rhs->rho);
-    int rc = cb200_frobenius1_batch_host(L, (int)ODE->order, (int)ODE->degree, (int)v, sol_degree, 1, ho.m.data(),
-                                         ho.t.data(), 1, hrho.m.data(), hrho.t.data(), 1, hr.m.data(), hr.t.data(), 0);
-    if (rc) die("_acb_ode_solve_frobenius (cb200_frobenius1_batch_host)", rc);
+    int rc = cb200_frobenius1_rhs_batch_host(L, (int)ODE->order, (int)ODE->degree, (int)v, sol_degree, 1, ho.m.data(),
+                                             ho.t.data(), 1, hrho.m.data(), hrho.t.data(), 1, hh.m.data(), hh.t.data(), hl, 1,
+                                             hr.m.data(), hr.t.data(), 0);
+    if (rc) die("_acb_ode_solve_frobenius (cb200_frobenius1_rhs_batch_host)", rc);
     acb_poly_zero(res);
     acb_poly_fit_length(res, sol_degree + 1);
     for (slong k = 0; k <= sol_degree; k++) hr.get(k, 0, res->coeffs + k);

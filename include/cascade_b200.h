@@ -56,6 +56,11 @@ int cb200_device_count(void);
 /* kernels launched by this library in this process so far (all entry points) */
 uint64_t cb200_kernel_launches(void);
 
+/* development aid: CB200_RR=1 in the environment makes the shared-operator recurrence try the reduced-radix
+ * fused dot product (cascade_b200/csrc/cb_rr.cuh; same balls, measured slower: DESIGN.md section 4) before the
+ * carry-chain one; with CB200_RR_STATS=1 as well, out[0] / out[1] = those products accepted / rejected so far */
+int cb200_debug_rr_stats(uint64_t *out);
+
 /* ---- workspace sizes (bytes of device memory the _dev entry points need) ---- */
 size_t cb200_fuchs_workspace_bytes(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
                                    int shared_ode);
@@ -100,6 +105,22 @@ int cb200_frobenius1_batch_host(int L, int order, int degree, int valuation, int
                                 const uint32_t *ode_mant, const cb_meta *ode_meta, int shared_ode,
                                 const uint32_t *rho_mant, const cb_meta *rho_meta, int shared_rho,
                                 uint32_t *res_mant, cb_meta *res_meta, int device);
+
+/* ---- _acb_ode_solve_frobenius with a right-hand side series (reference src/frobenius_solver.c:86-96,
+ * :100): rhs = rhs_len entries, S = 2*batch or 2 (shared_rhs).  An instance whose rhs is the zero
+ * polynomial takes the homogeneous branch (g_0 = 1); otherwise rho is replaced by rho - valuation and
+ * g_0 = rhs_0 / f_0(rho), as the reference does.  rhs must not alias res. */
+int cb200_frobenius1_rhs_batch_dev(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
+                                   const uint32_t *ode_mant, const cb_meta *ode_meta, int shared_ode,
+                                   const uint32_t *rho_mant, const cb_meta *rho_meta, int shared_rho,
+                                   const uint32_t *rhs_mant, const cb_meta *rhs_meta, int64_t rhs_len,
+                                   int shared_rhs, uint32_t *res_mant, cb_meta *res_meta, void *workspace,
+                                   size_t workspace_bytes, void *stream);
+int cb200_frobenius1_rhs_batch_host(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
+                                    const uint32_t *ode_mant, const cb_meta *ode_meta, int shared_ode,
+                                    const uint32_t *rho_mant, const cb_meta *rho_meta, int shared_rho,
+                                    const uint32_t *rhs_mant, const cb_meta *rhs_meta, int64_t rhs_len,
+                                    int shared_rhs, uint32_t *res_mant, cb_meta *res_meta, int device);
 
 /* ---- acb_ode_solve_frobenius for M = mul + alpha > 1 (the logarithmic case; reference
  * src/frobenius_solver.c:131-205 with indicial_polynomial :4-39 and _acb_ode_solution_update /

@@ -142,6 +142,10 @@ int cbo_example_flat(int which, int L, uint64_t n, const uint32_t *par_m, const 
 int cbo_continuation_flat(int L, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
                           const uint32_t *ode_m, const int32_t *ode_t, const uint32_t *path_m,
                           const int32_t *path_t, uint32_t *y_m, int32_t *y_t);
+int cbo_frobenius1_rhs_batch(int L, int order, int degree, int64_t n, int64_t batch, int shared_ode,
+                             const uint32_t *ode_m, const int32_t *ode_t, const uint32_t *rho_m,
+                             const int32_t *rho_t, const uint32_t *rhs_m, const int32_t *rhs_t, int64_t rhs_len,
+                             uint32_t *res_m, int32_t *res_t);
 /* general Frobenius (M = mul + alpha > 1), reference src/frobenius_solver.c:131-205.
  * gens out: [batch][M][n+1] complex balls */
 int cbo_frobenius_general_batch(int L, int order, int degree, int64_t n, int64_t batch, int shared_ode,

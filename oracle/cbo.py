@@ -51,6 +51,8 @@ def lib(plain: bool = False) -> C.CDLL:
     L.cbo_continuation_flat.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, _u32p, _i32p,
                                         _u32p, _i32p, _u32p, _i32p]
     L.cbo_example_flat.argtypes = [C.c_int, C.c_int, C.c_uint64, _u32p, _i32p, _u32p, _i32p]
+    L.cbo_frobenius1_rhs_batch.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, _u32p, _i32p,
+                                           _u32p, _i32p, _u32p, _i32p, C.c_int64, _u32p, _i32p]
     L.cbo_frobenius_general_batch.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, _u32p, _i32p,
                                               _u32p, _i32p, C.c_int, C.c_int64, C.c_int64, _u32p, _i32p, C.c_int]
     L.cbo_indicial_polynomial_flat.argtypes = [C.c_int, C.c_int, C.c_int, _u32p, _i32p, C.c_int64, C.c_int64,
@@ -153,6 +155,17 @@ def continuation(order: int, degree: int, n: int, ode: Balls, path: Balls, y0: B
                                           path.mant, path.meta, y.mant, y.meta)
     assert rc == 0
     return y
+
+
+def frobenius1_rhs_batch(order: int, degree: int, n: int, ode: Balls, rho: Balls, rhs: Balls, batch: int,
+                         shared_ode: bool, plain: bool = False) -> Balls:
+    """_acb_ode_solve_frobenius with right-hand sides rhs[batch][rhs_len] (reference src/frobenius_solver.c:72-121)."""
+    res = Balls.zeros(batch * (n + 1) * 2, ode.L)
+    rc = lib(plain).cbo_frobenius1_rhs_batch(ode.L, order, degree, n, batch, int(shared_ode), ode.mant, ode.meta,
+                                             rho.mant, rho.meta, rhs.mant, rhs.meta, rhs.n_slots // (2 * batch),
+                                             res.mant, res.meta)
+    assert rc == 0
+    return res
 
 
 def frobenius_general_batch(order: int, degree: int, n: int, ode: Balls, rho: Balls, batch: int, shared_ode: bool,

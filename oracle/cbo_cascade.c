@@ -700,6 +700,27 @@ static void solve_frobenius_general(cbo_solution *sol, cbo_ode *o, int64_t n, in
     free(g_rho);
 }
 
+/* _acb_ode_solve_frobenius with right-hand sides: rhs [batch][rhs_len], rho [batch], res [batch][n+1] */
+int cbo_frobenius1_rhs_batch(int L, int order, int degree, int64_t n, int64_t batch, int shared_ode,
+                             const uint32_t *ode_m, const int32_t *ode_t, const uint32_t *rho_m,
+                             const int32_t *rho_t, const uint32_t *rhs_m, const int32_t *rhs_t, int64_t rhs_len,
+                             uint32_t *res_m, int32_t *res_t) {
+    for (int64_t s = 0; s < batch; s++) {
+        cbo_ode *o = load_ode(L, order, degree, ode_m, ode_t, shared_ode ? 0 : s);
+        cbo_acb *res = (cbo_acb *)malloc(sizeof(cbo_acb) * (n + 1));
+        cbo_acb *rhs = (cbo_acb *)malloc(sizeof(cbo_acb) * (rhs_len > 0 ? rhs_len : 1));
+        cbo_acb rho;
+        load_acb(&rho, rho_m, rho_t, s, L);
+        for (int64_t k = 0; k < rhs_len; k++) load_acb(rhs + k, rhs_m, rhs_t, s * rhs_len + k, L);
+        cbo_solve_frobenius1(res, o, &rho, rhs, rhs_len, n, L);
+        for (int64_t k = 0; k <= n; k++) store_acb(res_m, res_t, s * (n + 1) + k, res + k, L);
+        free(res);
+        free(rhs);
+        cbo_ode_free(o);
+    }
+    return 0;
+}
+
 /* ---- flat entry points.  Polynomials travel as fixed-capacity coefficient arrays whose length is
  * implied (trailing exact zeros do not count), as on the device interface. */
 static void load_poly(cbo_poly *p, const uint32_t *m, const int32_t *t, int64_t first, int64_t cap, int L) {

@@ -470,3 +470,27 @@ def case_indicial_polynomial(oracle, drv, L: int, seed: int, trials: int = 4):
                 ev = oracle.indicial_polynomial_evaluate(order, degree, ode, nu, from_complex([r], L), 0)
                 for part in (0, 1):
                     assert abs(hv.mid(part) - ev.mid(part)) <= hv.rad(part) + ev.rad(part)
+
+
+def case_frobenius_rhs(oracle, drv, L: int, seed: int, n: int = 14, batch: int = 4):
+    """_acb_ode_solve_frobenius with a right-hand side (reference src/frobenius_solver.c:86-96,100):
+    per-instance rhs series of different effective lengths, one instance with a zero rhs (it must
+    take the homogeneous branch g_0 = 1), hypergeometric operators, generic complex rho."""
+    rng = np.random.default_rng(seed)
+    par = random_balls(rng, batch * 6, L, -1, 1, "zero")
+    odes = Balls.concat([oracle.example("hypgeom", L, 0, par[i * 6:(i + 1) * 6]) for i in range(batch)])
+    rho = random_balls(rng, batch * 2, L, -1, 1, "ulp")
+    hl = 6
+    rhs = random_balls(rng, batch * hl * 2, L, -2, 2, "ulp")
+    m = rhs.mant.reshape(batch, hl, 2, L)
+    t = rhs.meta.reshape(batch, hl, 2, 4)
+    m[1, 3:] = 0
+    t[1, 3:] = (0, FLAG_ZERO, 0, 0)  # shorter right-hand side
+    m[2] = 0
+    t[2] = (0, FLAG_ZERO, 0, 0)      # zero right-hand side: homogeneous branch
+    m[3, 0] = 0
+    t[3, 0] = (0, FLAG_ZERO, 0, 0)   # rhs_0 = 0 but rhs != 0
+    ro = oracle.frobenius1_rhs_batch(2, 2, n, odes, rho, rhs, batch, False)
+    rs = api.acb_ode_solve_frobenius1_batch(odes, rho, 2, 2, n, batch, False, False, driver=drv, rhs=rhs)
+    assert_same(ro, rs, f"frobenius with rhs L={L}")
+    assert rs.mid(2 * (2 * (n + 1))) == 1  # instance 2: g_0 = 1

@@ -19,7 +19,7 @@ _lib = None
 
 def build(force: bool = False) -> None:
     deps = [_SRC] + [os.path.join(_HERE, "..", "..", "cascade_b200", "csrc", f)
-                     for f in ("cb_arith.cuh", "cb_solvers.cuh", "cb_mul.cuh")]
+                     for f in ("cb_arith.cuh", "cb_solvers.cuh", "cb_mul.cuh", "cb_rr.cuh")]
     if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
         return
     subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
@@ -34,7 +34,7 @@ def lib():
         L.cbsim_fuchs_batch.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p]
         L.cbsim_fuchs_intop_batch.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS"), C.c_int, _u32p, _i32p]
         L.cbsim_continuation.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, _u32p, _i32p, _u32p, _i32p, _u32p, _i32p]
-        L.cbsim_frobenius1_batch.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int, _u32p, _i32p]
+        L.cbsim_frobenius1_batch.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int, _vp, _vp, C.c_int64, C.c_int, _u32p, _i32p]
         L.cbsim_horner_batch.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int, _u32p, _i32p, C.c_int, _u32p, _i32p, _u32p, _i32p]
         L.cbsim_ew.argtypes = [C.c_int, C.c_int, C.c_int64, _u32p, _i32p, _u32p, _i32p, _vp, _vp, _vp]
         L.cbsim_frobenius_general_batch.argtypes = ([C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p,
@@ -58,9 +58,11 @@ class SimDriver:
         return lib().cbsim_continuation(L, order, degree, n, batch, path_len, ode_m, ode_t, path_m, path_t, y_m, y_t)
 
     def frobenius1(self, L, order, degree, valuation, n, batch, ode_m, ode_t, shared, rho_m, rho_t,
-                   shared_rho, res_m, res_t):
+                   shared_rho, res_m, res_t, rhs_m=None, rhs_t=None, rhs_len=0, shared_rhs=False):
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
         return lib().cbsim_frobenius1_batch(L, order, degree, valuation, n, batch, ode_m, ode_t, int(shared),
-                                            rho_m, rho_t, int(shared_rho), res_m, res_t)
+                                            rho_m, rho_t, int(shared_rho), vp(rhs_m), vp(rhs_t), rhs_len,
+                                            int(shared_rhs), res_m, res_t)
 
     def frobenius_general(self, L, order, degree, valuation, n, batch, ode_m, ode_t, shared, rho_m, rho_t,
                           shared_rho, mul, M, gens_m, gens_t):

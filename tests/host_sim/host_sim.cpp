@@ -65,7 +65,8 @@ int cbsim_fuchs_batch(int L_, int order, int degree, int valuation, int64_t n, i
         SIM_DISPATCH(L_, run<L>(rows, [&](int64_t i, Scratch<1> a, Scratch<1> b) { fuchs_table_thread<L>(tp, i, a, b); }));
         FuchsSharedParams sp;
         sp.order = order; sp.degree = degree; sp.valuation = valuation; sp.n = n; sp.batch = batch;
-        sp.tbl = tp.tbl; sp.res = p.res; sp.kind = kind.data(); sp.gcols = nullptr;
+        sp.tbl = tp.tbl; sp.res = p.res; sp.kind = kind.data(); sp.gcols = nullptr; sp.stats = nullptr;
+        { const char* e = getenv("CB200_RR"); sp.no_rr = (e && e[0] == '1') ? 0 : 1; }  // as cb200_fuchs_batch_dev
         // columns sized EXACTLY as on the device (cb_kernels.cuh Sizes<L>), each followed by a
         // canary zone, so an out-of-column access is caught here and not only on the GPU
         const bool trunc = (L_ >= 16 && L_ <= 32);
@@ -110,8 +111,12 @@ int cbsim_fuchs_intop_batch(int L_, int order, int degree, int valuation, int64_
 int cbsim_frobenius1_batch(int L_, int order, int degree, int valuation, int64_t n, int64_t batch,
                            const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
                            const uint32_t* rho_mant, const cb_meta* rho_meta, int shared_rho,
+                           const uint32_t* rhs_mant, const cb_meta* rhs_meta, int64_t rhs_len, int shared_rhs,
                            uint32_t* res_mant, cb_meta* res_meta) {
     FrobParams p;
+    p.rhs = CArr{const_cast<uint32_t*>(rhs_mant), (Meta*)const_cast<cb_meta*>(rhs_meta),
+                 shared_rhs ? (size_t)2 : (size_t)(2 * batch)};
+    p.rhs_len = rhs_len;
     p.order = order; p.degree = degree; p.valuation = valuation; p.n = n; p.batch = batch;
     p.ode = CArr{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta),
                  shared_ode ? (size_t)2 : (size_t)(2 * batch)};

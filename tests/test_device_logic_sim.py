@@ -85,3 +85,17 @@ def test_solution_ops(oracle, sim_driver, L):
 @pytest.mark.parametrize("L", [4, 32])
 def test_indicial_polynomial(oracle, sim_driver, L):
     cases.case_indicial_polynomial(oracle, sim_driver, L, seed=53 + L, trials=3 if L == 4 else 1)
+
+
+@pytest.mark.parametrize("L", [4, 32])
+def test_frobenius_rhs(oracle, sim_driver, L):
+    cases.case_frobenius_rhs(oracle, sim_driver, L, seed=59 + L, n=10)
+
+
+def test_reduced_radix_products(oracle, sim_driver, monkeypatch):
+    """The reduced-radix fused dot product (cb_rr.cuh, opt-in with CB200_RR=1) must give the same balls:
+    dense, shared-operator and adversarial cases through the recurrence kernel's logic."""
+    monkeypatch.setenv("CB200_RR", "1")
+    cases.case_fuchs_bessel_shared(oracle, sim_driver, 32, seed=5, n=40, batch=3)
+    cases.case_fuchs_random_shared(oracle, sim_driver, 32, seed=63, trials=6)
+    cases.case_fuchs_shared_adversarial(oracle, sim_driver, 32, seed=109, batch=12)

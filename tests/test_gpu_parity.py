@@ -87,3 +87,16 @@ def test_solution_ops(oracle, gpu_driver, L):
 @pytest.mark.parametrize("L", [4, 32])
 def test_indicial_polynomial(oracle, gpu_driver, L):
     cases.case_indicial_polynomial(oracle, gpu_driver, L, seed=53 + L, trials=3)
+
+
+@pytest.mark.parametrize("L", [4, 32, 128])
+def test_frobenius_rhs(oracle, gpu_driver, L):
+    cases.case_frobenius_rhs(oracle, gpu_driver, L, seed=59 + L, n=14 if L < 128 else 8, batch=33)
+
+
+def test_reduced_radix_products(oracle, gpu_driver, monkeypatch):
+    """cb_rr.cuh (opt-in, CB200_RR=1): same balls as the oracle on the GPU."""
+    monkeypatch.setenv("CB200_RR", "1")
+    cases.case_fuchs_bessel_shared(oracle, gpu_driver, 32, seed=5, n=60, batch=300)
+    cases.case_fuchs_random_shared(oracle, gpu_driver, 32, seed=63, trials=6, batch=45)
+    cases.case_fuchs_shared_adversarial(oracle, gpu_driver, 32, seed=109, batch=70)

@@ -43,3 +43,7 @@ for it in range(3):
     coeffs = batch * (n - 1)
     print(f"L={L} batch={batch} n={n}: {ms:.2f} ms, {coeffs / ms * 1e3:.3e} coeff/s, "
           f"{coeffs * 24 * L * L / ms * 1e3 / 1e12:.3f} T limb-MAC/s (24L^2 convention)")
+
+st = (C.c_uint64 * 2)()
+lib.cb200_debug_rr_stats(st)
+print("rr accepted / rejected:", st[0], st[1])
