@@ -36,6 +36,8 @@ SYMBOLS = [
     "cb200_frobenius_general_batch_host",
     "cb200_solution_op_workspace_bytes", "cb200_solution_op_dev", "cb200_solution_op_host",
     "cb200_indicial_polynomial_dev", "cb200_indicial_polynomial_host",
+    "cb200_evaluate_workspace_bytes", "cb200_solution_evaluate_dev", "cb200_solution_evaluate_host",
+    "cb200_trans_dev", "cb200_trans_host",
 ]
 
 
@@ -96,6 +98,14 @@ def lib() -> C.CDLL:
                                                                 _vp, C.c_size_t, _vp]
     L.cb200_indicial_polynomial_host.argtypes = [C.c_int] * 4 + [C.c_int64, _u32p, _i32p, C.c_int, C.c_int64, C.c_int64,
                                                                  _u32p, _i32p, C.c_int]
+    L.cb200_evaluate_workspace_bytes.restype = C.c_size_t
+    L.cb200_evaluate_workspace_bytes.argtypes = [C.c_int, C.c_int64]
+    L.cb200_solution_evaluate_dev.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_uint64,
+                                              _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]
+    L.cb200_solution_evaluate_host.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int64, _u32p, _i32p, _u32p, _i32p, C.c_int,
+                                               C.c_uint64, _u32p, _i32p, _u32p, _i32p, C.c_int]
+    L.cb200_trans_dev.argtypes = [C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]
+    L.cb200_trans_host.argtypes = [C.c_int, C.c_int, C.c_int64, _u32p, _i32p, _u32p, _i32p, C.c_int]
     _lib = L
     return L
 

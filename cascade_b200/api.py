@@ -63,6 +63,13 @@ class HostBufferDriver:
         return _lib.lib().cb200_indicial_polynomial_host(L, order, degree, valuation, batch, ode_m, ode_t, int(shared),
                                                          nu, shift, out_m, out_t, self.device)
 
+    def solution_evaluate(self, L, M, cap, npts, g_m, g_t, rho_m, rho_t, pow_mode, pow_e, p_m, p_t, o_m, o_t):
+        return _lib.lib().cb200_solution_evaluate_host(L, M, cap, npts, g_m, g_t, rho_m, rho_t, pow_mode, pow_e, p_m, p_t,
+                                                       o_m, o_t, self.device)
+
+    def trans(self, which, L, n, z_m, z_t, x_m, x_t):
+        return _lib.lib().cb200_trans_host(which, L, n, z_m, z_t, x_m, x_t, self.device)
+
     def horner(self, L, length, npts, nder, f_m, f_t, shared_f, p_m, p_t, o_m, o_t):
         return _lib.lib().cb200_horner_batch_host(L, length, npts, nder, f_m, f_t, int(shared_f), p_m, p_t,
                                                   o_m, o_t, self.device)
@@ -289,6 +296,60 @@ def acb_poly_evaluate_batch(f: Balls, pts: Balls, nder: int = 1, driver=None) ->
     o_t = np.zeros((nder, 2 * npts, 4), np.int32)
     _lib.check(drv.horner(L, length, npts, nder, f_m, f_t, True, p_m, p_t, o_m, o_t), "acb_poly_evaluate_batch")
     return entry_major_to_instance_major(unpack_entries(L, o_m, o_t), npts, nder)
+
+
+def pow_mode_of(rho: Balls):
+    """How ``acb_pow(a, rho)`` is computed for this exponent (host-side inspection of one complex ball):
+    (0, 0) rho is the exact zero; (1, e) rho is the exact integer 0 <= e < 2^31; (2, 0) general."""
+    L = rho.L
+    re_t, im_t = rho.meta[0], rho.meta[1]
+    exact = re_t[2] == 0 and im_t[2] == 0 and not ((re_t[1] | im_t[1]) & FLAG_NAN)
+    if not exact or not (im_t[1] & FLAG_ZERO):
+        return 2, 0
+    if re_t[1] & FLAG_ZERO:
+        return 0, 0
+    if (re_t[1] & 1) or not (1 <= re_t[0] <= 31) or rho.mant[0, : L - 1].any():
+        return 2, 0
+    top = int(rho.mant[0, L - 1])
+    e = top >> (32 - int(re_t[0]))
+    if (e << (32 - int(re_t[0]))) != top:
+        return 2, 0
+    return 1, e
+
+
+def acb_ode_solution_evaluate_batch(gens: Balls, M: int, rho: Balls, pts: Balls, driver=None) -> Balls:
+    """``acb_ode_solution_evaluate(out, sol, a, prec)`` (reference src/acb_ode_solution.c:24-58) of one solution
+    (``gens``: ``[M][cap]`` series, ``rho``) at every point of ``pts``; ``acb_log`` / ``acb_pow`` run on the device."""
+    drv = driver or default_driver()
+    L = gens.L
+    cap, npts = gens.n_slots // (2 * M), pts.n_slots // 2
+    mode, e = pow_mode_of(rho)
+    g_m, g_t = pack_entries(gens, M * cap, 2)
+    r_m, r_t = pack_entries(rho, 1, 2)
+    p_m, p_t = pack_entries(pts, 1, 2 * npts)
+    o_m = np.zeros((1, L, 2 * npts), np.uint32)
+    o_t = np.zeros((1, 2 * npts, 4), np.int32)
+    _lib.check(drv.solution_evaluate(L, M, cap, npts, g_m, g_t, r_m, r_t, mode, e, p_m, p_t, o_m, o_t),
+               "acb_ode_solution_evaluate_batch")
+    return unpack_entries(L, o_m, o_t)
+
+
+def acb_exp_batch(x: Balls, driver=None) -> Balls:
+    return _trans(0, x, driver)
+
+
+def acb_log_batch(x: Balls, driver=None) -> Balls:
+    return _trans(1, x, driver)
+
+
+def _trans(which: int, x: Balls, driver=None) -> Balls:
+    drv = driver or default_driver()
+    L, n = x.L, x.n_slots // 2
+    x_m, x_t = pack_entries(x, 1, 2 * n)
+    z_m = np.zeros((1, L, 2 * n), np.uint32)
+    z_t = np.zeros((1, 2 * n, 4), np.int32)
+    _lib.check(drv.trans(which, L, n, z_m, z_t, x_m, x_t), "acb_exp/acb_log")
+    return unpack_entries(L, z_m, z_t)
 
 
 def ew(op: int, x: Balls, y: Balls | None = None, k=None, driver=None) -> Balls:

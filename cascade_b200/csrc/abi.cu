@@ -317,6 +317,46 @@ int cb200_indicial_polynomial_dev(int L_, int order, int degree, int valuation, 
     return table_for(L_)->indicial_poly(p, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------ acb_ode_solution_evaluate, acb_exp / acb_log
+size_t cb200_evaluate_workspace_bytes(int L, int64_t npts) { return carve_bytes(L, TRANS_NTMP + 4, 2 * npts); }
+int cb200_solution_evaluate_dev(int L_, int M, int64_t cap, int64_t npts, const uint32_t* gens_mant,
+                                const cb_meta* gens_meta, const uint32_t* rho_mant, const cb_meta* rho_meta, int pow_mode,
+                                uint64_t pow_e, const uint32_t* pts_mant, const cb_meta* pts_meta, uint32_t* out_mant,
+                                cb_meta* out_meta, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!supported_L(L_) || M < 1 || M > FROBG_MAXM || cap < 1 || npts < 0 || pow_mode < 0 || pow_mode > 2 ||
+        (pow_mode == 1 && pow_e >= (1ull << 31)))
+        return CB200_EINVAL;
+    if (workspace_bytes < cb200_evaluate_workspace_bytes(L_, npts)) return CB200_ENOMEM;
+    EvalParams p;
+    p.M = M;
+    p.pow_mode = pow_mode;
+    p.pow_e = pow_e;
+    p.cap = cap;
+    p.npts = npts;
+    p.gens = CArr{const_cast<uint32_t*>(gens_mant), (Meta*)const_cast<cb_meta*>(gens_meta), (size_t)2};
+    p.rho = CArr{const_cast<uint32_t*>(rho_mant), (Meta*)const_cast<cb_meta*>(rho_meta), (size_t)2};
+    p.pts = CArr{const_cast<uint32_t*>(pts_mant), (Meta*)const_cast<cb_meta*>(pts_meta), (size_t)(2 * npts)};
+    p.out = CArr{out_mant, (Meta*)out_meta, (size_t)(2 * npts)};
+    char* w = (char*)workspace;
+    p.wp = carve(w, L_, TRANS_NTMP + 4, 2 * npts);
+    g_launches.fetch_add(npts > 0);
+    return table_for(L_)->evaluate(p, (cudaStream_t)stream);
+}
+int cb200_trans_dev(int which, int L_, int64_t n, uint32_t* z_mant, cb_meta* z_meta, const uint32_t* x_mant,
+                    const cb_meta* x_meta, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!supported_L(L_) || n < 0 || (which != CB200_TRANS_EXP && which != CB200_TRANS_LOG)) return CB200_EINVAL;
+    if (workspace_bytes < cb200_evaluate_workspace_bytes(L_, n)) return CB200_ENOMEM;
+    TransParams p;
+    p.which = which;
+    p.n = n;
+    p.z = CArr{z_mant, (Meta*)z_meta, (size_t)(2 * n)};
+    p.x = CArr{const_cast<uint32_t*>(x_mant), (Meta*)const_cast<cb_meta*>(x_meta), (size_t)(2 * n)};
+    char* w = (char*)workspace;
+    p.wp = carve(w, L_, TRANS_NTMP, 2 * n);
+    g_launches.fetch_add(n > 0);
+    return table_for(L_)->trans(p, (cudaStream_t)stream);
+}
+
 int cb200_horner_batch_dev(int L_, int64_t len, int64_t npts, int nder, const uint32_t* f_mant,
                            const cb_meta* f_meta, int shared_f, const uint32_t* pts_mant,
                            const cb_meta* pts_meta, uint32_t* out_mant, cb_meta* out_meta,
@@ -637,6 +677,59 @@ int cb200_indicial_polynomial_host(int L, int order, int degree, int valuation, 
     if (rc) return rc;
     CK(cudaMemcpy(out_mant, rm.p, arr_mant_bytes(L, order + 2, S), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(out_meta, rt.p, arr_meta_bytes(order + 2, S), cudaMemcpyDeviceToHost));
+    return (int)cudaDeviceSynchronize();
+}
+
+int cb200_solution_evaluate_host(int L, int M, int64_t cap, int64_t npts, const uint32_t* gens_mant,
+                                 const cb_meta* gens_meta, const uint32_t* rho_mant, const cb_meta* rho_meta, int pow_mode,
+                                 uint64_t pow_e, const uint32_t* pts_mant, const cb_meta* pts_meta, uint32_t* out_mant,
+                                 cb_meta* out_meta, int device) {
+    if (!supported_L(L) || M < 1 || M > FROBG_MAXM || cap < 1 || npts < 0) return CB200_EINVAL;
+    CK(cudaSetDevice(device));
+    int64_t S = 2 * npts, ng = (int64_t)M * cap;
+    DevBuf gm, gt, rm, rt, pm, pt, om, ot, ws;
+    size_t wsb = cb200_evaluate_workspace_bytes(L, npts);
+    CK(gm.alloc(arr_mant_bytes(L, ng, 2)));
+    CK(gt.alloc(arr_meta_bytes(ng, 2)));
+    CK(rm.alloc(arr_mant_bytes(L, 1, 2)));
+    CK(rt.alloc(arr_meta_bytes(1, 2)));
+    CK(pm.alloc(arr_mant_bytes(L, 1, S)));
+    CK(pt.alloc(arr_meta_bytes(1, S)));
+    CK(om.alloc(arr_mant_bytes(L, 1, S)));
+    CK(ot.alloc(arr_meta_bytes(1, S)));
+    CK(ws.alloc(wsb));
+    CK(cudaMemcpy(gm.p, gens_mant, arr_mant_bytes(L, ng, 2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(gt.p, gens_meta, arr_meta_bytes(ng, 2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(rm.p, rho_mant, arr_mant_bytes(L, 1, 2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(rt.p, rho_meta, arr_meta_bytes(1, 2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pm.p, pts_mant, arr_mant_bytes(L, 1, S), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pt.p, pts_meta, arr_meta_bytes(1, S), cudaMemcpyHostToDevice));
+    int rc = cb200_solution_evaluate_dev(L, M, cap, npts, (uint32_t*)gm.p, (cb_meta*)gt.p, (uint32_t*)rm.p, (cb_meta*)rt.p,
+                                         pow_mode, pow_e, (uint32_t*)pm.p, (cb_meta*)pt.p, (uint32_t*)om.p, (cb_meta*)ot.p,
+                                         ws.p, wsb, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(out_mant, om.p, arr_mant_bytes(L, 1, S), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out_meta, ot.p, arr_meta_bytes(1, S), cudaMemcpyDeviceToHost));
+    return (int)cudaDeviceSynchronize();
+}
+int cb200_trans_host(int which, int L, int64_t n, uint32_t* z_mant, cb_meta* z_meta, const uint32_t* x_mant,
+                     const cb_meta* x_meta, int device) {
+    if (!supported_L(L) || n < 0) return CB200_EINVAL;
+    CK(cudaSetDevice(device));
+    int64_t S = 2 * n;
+    DevBuf zm, zt, xm, xt, ws;
+    size_t wsb = cb200_evaluate_workspace_bytes(L, n);
+    CK(zm.alloc(arr_mant_bytes(L, 1, S)));
+    CK(zt.alloc(arr_meta_bytes(1, S)));
+    CK(xm.alloc(arr_mant_bytes(L, 1, S)));
+    CK(xt.alloc(arr_meta_bytes(1, S)));
+    CK(ws.alloc(wsb));
+    CK(cudaMemcpy(xm.p, x_mant, arr_mant_bytes(L, 1, S), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(xt.p, x_meta, arr_meta_bytes(1, S), cudaMemcpyHostToDevice));
+    int rc = cb200_trans_dev(which, L, n, (uint32_t*)zm.p, (cb_meta*)zt.p, (uint32_t*)xm.p, (cb_meta*)xt.p, ws.p, wsb, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(z_mant, zm.p, arr_mant_bytes(L, 1, S), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(z_meta, zt.p, arr_meta_bytes(1, S), cudaMemcpyDeviceToHost));
     return (int)cudaDeviceSynchronize();
 }
 

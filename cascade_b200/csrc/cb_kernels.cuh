@@ -72,6 +72,16 @@ __global__ void __launch_bounds__(Cfg<L>::TPB, 1) indicial_poly_kernel(IndicialP
     indicial_poly_thread<L>(p, idx, S0, S1);
 }
 template <int L>
+__global__ void __launch_bounds__(Cfg<L>::TPB, 1) evaluate_kernel(EvalParams p) {
+    CB_KERNEL_PROLOGUE(p.npts)
+    evaluate_thread<L>(p, idx, S0, S1);
+}
+template <int L>
+__global__ void __launch_bounds__(Cfg<L>::TPB, 1) trans_kernel(TransParams p) {
+    CB_KERNEL_PROLOGUE(p.n)
+    trans_thread<L>(p, idx, S0, S1);
+}
+template <int L>
 __global__ void __launch_bounds__(Cfg<L>::TPB, 1) horner_kernel(HornerParams p) {
     CB_KERNEL_PROLOGUE(p.npts)
     horner_thread<L>(p, idx, S0, S1);
@@ -153,6 +163,8 @@ struct LaunchTable {
     int (*frobenius_general)(const FrobGenParams&, cudaStream_t);
     int (*solution_op)(const SolOpParams&, cudaStream_t);
     int (*indicial_poly)(const IndicialParams&, cudaStream_t);
+    int (*evaluate)(const EvalParams&, cudaStream_t);
+    int (*trans)(const TransParams&, cudaStream_t);
 };
 
 #define CB_DEFINE_LAUNCH_TABLE(LL)                                                                         \
@@ -180,8 +192,10 @@ struct LaunchTable {
     static int frobg_##LL(const FrobGenParams& p, cudaStream_t s) { return launch<LL>(frobenius_general_kernel<LL>, p, p.batch, s); } \
     static int solop_##LL(const SolOpParams& p, cudaStream_t s) { return launch<LL>(solution_op_kernel<LL>, p, p.batch, s); } \
     static int indp_##LL(const IndicialParams& p, cudaStream_t s) { return launch<LL>(indicial_poly_kernel<LL>, p, p.batch, s); } \
+    static int eval_##LL(const EvalParams& p, cudaStream_t s) { return launch<LL>(evaluate_kernel<LL>, p, p.npts, s); } \
+    static int trans_##LL(const TransParams& p, cudaStream_t s) { return launch<LL>(trans_kernel<LL>, p, p.n, s); } \
     extern const LaunchTable launch_table_L##LL = {fuchs_##LL, frob_##LL, horner_##LL, ew_##LL, ftab_##LL, fsh_##LL, fint_##LL, \
-                                                   frobg_##LL, solop_##LL, indp_##LL};                     \
+                                                   frobg_##LL, solop_##LL, indp_##LL, eval_##LL, trans_##LL}; \
     }
 
 extern const LaunchTable launch_table_L4, launch_table_L32, launch_table_L64, launch_table_L128;

@@ -1117,3 +1117,5 @@ CB_HD void ew_thread(const EwParams& p, int64_t i, SCR S0, SCR S1) {
 }
 
 }  // namespace cb
+
+#include "cb_trans.cuh"

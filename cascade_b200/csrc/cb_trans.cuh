@@ -1,0 +1,323 @@
+// cb_trans.cuh -- the transcendental part of acb_ode_solution_evaluate on the device
+// (reference src/acb_ode_solution.c:24-58): acb_log(a), acb_pow(a, rho) and the Horner-in-log(a)
+// combination of the M series of a solution, one thread per evaluation point.
+//
+// Arb's acb_log / acb_exp are not correctly rounded, so there is no unique ball to reproduce; the
+// algorithms are the ones stated in oracle/cbo_trans.c, built from the ball primitives of
+// cb_arith.cuh in the SAME order, so device and oracle agree bit for bit:
+//   exp(z): w = z / 2^k, |w| < 2^-16; Taylor polynomial by Horner; remainder into the radius; k squarings
+//   log(a): y0 = double-precision seed from IEEE +,-,*,/ only (round-to-nearest intrinsics, so no FMA
+//           contraction: identical bits on CPU and GPU); t = a exp(-y0); u = t - 1; v = u / (u + 2);
+//           log(a) = y0 + 2 atanh(v) by its Taylor series
+//   pow:    rho = 0 -> 1; exact integer 0 <= rho < 2^31 -> binary exponentiation; else exp(rho log a)
+#pragma once
+#include <string.h>
+
+namespace cb {
+
+#if defined(__CUDA_ARCH__)
+#define CB_DMUL(a, b) __dmul_rn((a), (b))
+#define CB_DADD(a, b) __dadd_rn((a), (b))
+#define CB_DSUB(a, b) __dsub_rn((a), (b))
+#define CB_DDIV(a, b) __ddiv_rn((a), (b))
+#else  // host build (tests/host_sim): compiled with -ffp-contract=off
+#define CB_DMUL(a, b) ((a) * (b))
+#define CB_DADD(a, b) ((a) + (b))
+#define CB_DSUB(a, b) ((a) - (b))
+#define CB_DDIV(a, b) ((a) / (b))
+#endif
+
+constexpr int64_t TR_BIG = ((int64_t)1) << 40;
+constexpr int TRANS_NTMP = 16;  // complex temporaries of acb_exp (4) + acb_log (10) + evaluate (2)
+
+template <int L>
+CB_HD void acb_set_nan(const CRef& z) {
+    store_nan<L>(wre(z));
+    store_nan<L>(wim(z));
+    st_meta(z.t, meta_nan());
+    st_meta(z.t + 1, meta_nan());
+}
+// E with |z| < 2^E; TR_BIG for an indeterminate ball, -TR_BIG for the exact zero
+CB_HD int64_t acb_bound_exp(const CRef& z) {
+    int64_t e = -TR_BIG;
+    for (int part = 0; part < 2; part++) {
+        Meta t = ld_meta(z.t + part);
+        if (is_nan(t)) return TR_BIG;
+        if (!is_zero_mid(t) && t.exp > e) e = t.exp;
+        if (t.rman && t.rexp > e) e = t.rexp;
+    }
+    return e == -TR_BIG ? -TR_BIG : e + 2;
+}
+CB_HD void acb_mul_2exp(const CRef& z, int64_t k) {
+    for (int part = 0; part < 2; part++) {
+        Meta t = ld_meta(z.t + part);
+        if (is_nan(t)) continue;
+        if (!is_zero_mid(t)) t.exp = (int32_t)(t.exp + k);
+        if (t.rman) t.rexp = (int32_t)(t.rexp + k);
+        st_meta(z.t + part, t);
+    }
+}
+CB_HD void acb_add_error_2exp(const CRef& z, int64_t e) {
+    for (int part = 0; part < 2; part++) {
+        Meta t = ld_meta(z.t + part);
+        if (is_nan(t)) continue;
+        Mag r = mag_add(mag_of(t), Mag{1u << 29, (int32_t)(e + 1)});
+        t.rman = r.man;
+        t.rexp = r.man ? r.exp : 0;
+        st_meta(z.t + part, t);
+    }
+}
+CB_HD int tr_floor_log2(int64_t n) {
+    int r = 0;
+    while (n > 1) {
+        n >>= 1;
+        r++;
+    }
+    return r;
+}
+
+// res = exp(z).  T[0..3]: w, s, t, kball.  res may alias z.
+template <int L, class SCR>
+CB_HD void acb_exp(const CRef& res, const CRef& z, const CRef* T, SCR S0, SCR S1) {
+    int64_t E = acb_bound_exp(z);
+    if (E > 36) {
+        acb_set_nan<L>(res);
+        return;
+    }
+    if (E == -TR_BIG) {
+        acb_one<L>(res);
+        return;
+    }
+    const int r = 16;
+    int64_t k = E + r;
+    if (k < 0) k = 0;
+    CRef w = T[0], s = T[1], t = T[2], kb = T[3];
+    acb_set<L>(w, z);
+    acb_mul_2exp(w, -k);
+    int64_t q = k > 0 ? r : -E;
+    if (q > 8192) q = 8192;
+    int64_t target = 32 * (int64_t)L + 8, bits = 0, N = 0;
+    while (bits < target) {
+        N++;
+        bits += q + tr_floor_log2(N);
+    }
+    acb_one<L>(s);
+#pragma unroll 1
+    for (int64_t n = N - 1; n >= 1; n--) {
+        acb_mul<L>(t, s, w, S0, S1);
+        acb_div_si<L>(s, t, n, S0);
+        acb_add_si<L>(s, s, 1, kb, S0, S1);
+    }
+    acb_add_error_2exp(s, -(32 * (int64_t)L + 7));
+#pragma unroll 1
+    for (int64_t i = 0; i < k; i++) {
+        acb_mul<L>(t, s, s, S0, S1);
+        CRef sw = s;
+        s = t;
+        t = sw;
+    }
+    acb_set<L>(res, s);
+}
+
+CB_HD double tr_pow2(int64_t k) {  // 2^k, -1022 <= k <= 1023
+    uint64_t b = (uint64_t)(k + 1023) << 52;
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+}
+template <int L>
+CB_HD double tr_top53(const uint32_t* m, size_t stride, const Meta& t) {  // mid / 2^exp: +-[1/2, 1) or 0
+    if (t.flags & (F_ZERO | F_NAN)) return 0.0;
+    uint64_t mm = ((uint64_t)m[(size_t)(L - 1) * stride] << 32) | m[(size_t)(L - 2) * stride];
+    double d = CB_DMUL((double)(int64_t)(mm >> 11), tr_pow2(-53));
+    return (t.flags & F_SIGN) ? -d : d;
+}
+constexpr int TR_SEED_TERMS = 24;
+template <int L>
+CB_HD void tr_seed_log(double* yr, double* yi, const CRef& a) {
+    const double PI = 3.141592653589793, HALF_PI = 1.5707963267948966, LN2 = 0.6931471805599453;
+    Meta tr = ld_meta(a.t), ti = ld_meta(a.t + 1);
+    bool zr0 = is_zero_mid(tr), zi0 = is_zero_mid(ti);
+    int64_t er = tr.exp, ei = ti.exp;
+    int64_t E = zr0 ? ei : (zi0 ? er : (er > ei ? er : ei));
+    double xr = (zr0 || er - E < -200) ? 0.0 : CB_DMUL(tr_top53<L>(a.m, a.stride, tr), tr_pow2(er - E));
+    double xi = (zi0 || ei - E < -200) ? 0.0 : CB_DMUL(tr_top53<L>(a.m + 1, a.stride, ti), tr_pow2(ei - E));
+    double ar = xr < 0 ? -xr : xr, ai = xi < 0 ? -xi : xi;
+    double pr, pi, rot;
+    if (ar >= ai) {
+        if (xr > 0) {
+            pr = xr; pi = xi; rot = 0.0;
+        } else {
+            pr = -xr; pi = -xi; rot = xi >= 0 ? PI : -PI;
+        }
+    } else if (xi > 0) {
+        pr = xi; pi = -xr; rot = HALF_PI;
+    } else {
+        pr = -xi; pi = xr; rot = -HALF_PI;
+    }
+    double nr = CB_DSUB(pr, 1.0), ni = pi, dr = CB_DADD(pr, 1.0), di = pi;
+    double den = CB_DADD(CB_DMUL(dr, dr), CB_DMUL(di, di));
+    double wr = CB_DDIV(CB_DADD(CB_DMUL(nr, dr), CB_DMUL(ni, di)), den);
+    double wi = CB_DDIV(CB_DSUB(CB_DMUL(ni, dr), CB_DMUL(nr, di)), den);
+    double w2r = CB_DSUB(CB_DMUL(wr, wr), CB_DMUL(wi, wi)), w2i = CB_DMUL(2.0, CB_DMUL(wr, wi));
+    double sr = CB_DDIV(1.0, (double)(2 * TR_SEED_TERMS - 1)), si = 0.0;
+#pragma unroll 1
+    for (int j = TR_SEED_TERMS - 2; j >= 0; j--) {
+        double t_r = CB_DSUB(CB_DMUL(sr, w2r), CB_DMUL(si, w2i)), t_i = CB_DADD(CB_DMUL(sr, w2i), CB_DMUL(si, w2r));
+        sr = CB_DADD(t_r, CB_DDIV(1.0, (double)(2 * j + 1)));
+        si = t_i;
+    }
+    double lr = CB_DSUB(CB_DMUL(sr, wr), CB_DMUL(si, wi)), li = CB_DADD(CB_DMUL(sr, wi), CB_DMUL(si, wr));
+    *yr = CB_DADD(CB_DMUL(2.0, lr), CB_DMUL((double)E, LN2));
+    *yi = CB_DADD(CB_DMUL(2.0, li), rot);
+}
+// exact ball of a double (subnormals flush to zero); part 0 re, 1 im
+template <int L>
+CB_HD void arb_set_d(const CRef& z, int part, double d) {
+    uint64_t b;
+    memcpy(&b, &d, 8);
+    int e11 = (int)((b >> 52) & 0x7FF);
+#pragma unroll 8
+    for (int k = 0; k < L; k++) z.m[(size_t)k * z.stride + part] = 0u;
+    if (e11 == 0 || e11 == 0x7FF) {
+        st_meta(z.t + part, meta_zero());
+        return;
+    }
+    uint64_t m64 = ((b & 0xFFFFFFFFFFFFFull) | (1ull << 52)) << 11;
+    z.m[(size_t)(L - 1) * z.stride + part] = (uint32_t)(m64 >> 32);
+    z.m[(size_t)(L - 2) * z.stride + part] = (uint32_t)m64;
+    st_meta(z.t + part, Meta{e11 - 1022, (b >> 63) ? F_SIGN : 0u, 0u, 0});
+}
+
+// res = log(a).  T[0..13]: exp's four, then y0, e, t, u, d, v, v2, s, c, one.  res must not alias a.
+template <int L, class SCR>
+CB_HD void acb_log(const CRef& res, const CRef& a, const CRef* T, SCR S0, SCR S1) {
+    if (acb_bound_exp(a) == TR_BIG || acb_contains_zero<L>(a)) {
+        acb_set_nan<L>(res);
+        return;
+    }
+    double yr, yi;
+    tr_seed_log<L>(&yr, &yi, a);
+    CRef kb = T[3], y0 = T[4], e = T[5], t = T[6], u = T[7], d = T[8], v = T[9], v2 = T[10], s = T[11], c = T[12],
+         one = T[13];
+    arb_set_d<L>(y0, 0, yr);
+    arb_set_d<L>(y0, 1, yi);
+    acb_set<L>(t, y0);
+    acb_neg_inplace(t);
+    acb_exp<L>(e, t, T, S0, S1);
+    acb_mul<L>(t, a, e, S0, S1);
+    acb_add_si<L>(u, t, -1, kb, S0, S1);
+    int64_t Eu = acb_bound_exp(u);
+    if (Eu > -8) {
+        acb_set_nan<L>(res);
+        return;
+    }
+    if (Eu == -TR_BIG) {
+        acb_set<L>(res, y0);
+        return;
+    }
+    acb_add_si<L>(d, u, 2, kb, S0, S1);
+    acb_div<L>(v, u, d, e, S0, S1);  // e is free again: the inverse of a complex divisor goes there
+    int64_t q = -Eu;
+    if (q > 8192) q = 8192;
+    int64_t target = 32 * (int64_t)L + 10, K = 1;
+    while (q * (2 * K + 1) < target) K++;
+    acb_mul<L>(v2, v, v, S0, S1);
+    acb_one<L>(one);
+    acb_div_si<L>(s, one, 2 * K - 1, S0);
+#pragma unroll 1
+    for (int64_t j = K - 2; j >= 0; j--) {
+        acb_mul<L>(t, s, v2, S0, S1);
+        acb_div_si<L>(c, one, 2 * j + 1, S0);
+        acb_addsub<L>(s, t, c, false, S0, S1);
+    }
+    acb_mul<L>(t, s, v, S0, S1);
+    acb_mul_2exp(t, 1);
+    acb_add_error_2exp(t, -(32 * (int64_t)L + 8));
+    acb_addsub<L>(res, y0, t, false, S0, S1);
+}
+
+// acb_ode_solution_evaluate for one solution at many points
+struct EvalParams {
+    int M, pow_mode;     // pow_mode: 0 rho == 0; 1 exact integer pow_e; 2 general
+    uint64_t pow_e;
+    int64_t cap, npts;
+    CArr gens;  // M * cap entries, S = 2 (one solution for all points)
+    CArr rho;   // 1 entry, S = 2
+    CArr pts;   // 1 entry, S = 2*npts
+    CArr out;   // 1 entry, S = 2*npts
+    CArr wp;    // TRANS_NTMP + 4 entries, S = 2*npts
+};
+template <int L, class SCR>
+CB_HD void evaluate_thread(const EvalParams& p, int64_t pt, SCR S0, SCR S1) {
+    const size_t slot = 2 * (size_t)pt;
+    CRef T[TRANS_NTMP];
+    for (int i = 0; i < TRANS_NTMP; i++) T[i] = at<L>(p.wp, i, slot);
+    CRef lg = at<L>(p.wp, TRANS_NTMP, slot), res = at<L>(p.wp, TRANS_NTMP + 1, slot),
+         qv = at<L>(p.wp, TRANS_NTMP + 2, slot), pw = at<L>(p.wp, TRANS_NTMP + 3, slot);
+    CRef a = at<L>(p.pts, 0, slot), out = at<L>(p.out, 0, slot), rho = at<L>(p.rho, 0, 0);
+    if (acb_is_exact_zero(a)) {  // reference :29-33
+        acb_set_nan<L>(out);
+        return;
+    }
+    const bool have_log = p.M > 1 || p.pow_mode == 2;
+    if (have_log) acb_log<L>(lg, a, T, S0, S1);
+    // the series live in the shared array: a polynomial context on it (slot 0), temporaries per point
+    PolyCtx<L, SCR> pc{p.gens, 0, S0, S1, T[0], T[1], T[2], T[3], T[4]};
+    auto series_eval = [&](const CRef& y, int i) {
+        int64_t e0 = (int64_t)i * p.cap;
+        poly_eval<L>(pc, y, e0, pc.norm(e0, p.cap), a);
+    };
+    series_eval(res, 0);
+    int64_t binom = 1;
+#pragma unroll 1
+    for (int i = 1; i < p.M; i++) {
+        acb_mul<L>(T[5], res, lg, S0, S1);
+        series_eval(qv, i);
+        binom = (binom * (p.M - i + 1)) / i;
+        acb_mul_si<L>(qv, qv, binom, S0);
+        acb_addsub<L>(res, T[5], qv, false, S0, S1);
+    }
+    // a^rho
+    if (p.pow_mode == 0 || (p.pow_mode == 1 && p.pow_e == 0)) {
+        acb_one<L>(pw);
+    } else if (p.pow_mode == 1) {
+        CRef pp = pw, tt = T[5];
+        acb_set<L>(pp, a);
+        int top = 63;
+        while (!((p.pow_e >> top) & 1)) top--;
+#pragma unroll 1
+        for (int bit = top - 1; bit >= 0; bit--) {
+            acb_mul<L>(tt, pp, pp, S0, S1);
+            CRef sw = pp; pp = tt; tt = sw;
+            if ((p.pow_e >> bit) & 1) {
+                acb_mul<L>(tt, pp, a, S0, S1);
+                sw = pp; pp = tt; tt = sw;
+            }
+        }
+        if (pp.m != pw.m) acb_set<L>(pw, pp);
+    } else {
+        acb_mul<L>(T[5], lg, rho, S0, S1);
+        acb_exp<L>(pw, T[5], T, S0, S1);
+    }
+    acb_mul<L>(out, res, pw, S0, S1);
+}
+
+// elementwise acb_exp / acb_log (unit-test surface and the compat layer's acb_log / acb_exp)
+struct TransParams {
+    int which;  // 0 exp, 1 log
+    int64_t n;
+    CArr z, x;  // 1 entry each, S = 2*n
+    CArr wp;    // TRANS_NTMP entries
+};
+template <int L, class SCR>
+CB_HD void trans_thread(const TransParams& p, int64_t i, SCR S0, SCR S1) {
+    const size_t slot = 2 * (size_t)i;
+    CRef T[TRANS_NTMP];
+    for (int k = 0; k < TRANS_NTMP; k++) T[k] = at<L>(p.wp, k, slot);
+    CRef z = at<L>(p.z, 0, slot), x = at<L>(p.x, 0, slot);
+    if (p.which == 0) acb_exp<L>(z, x, T, S0, S1);
+    else acb_log<L>(z, x, T, S0, S1);
+}
+
+}  // namespace cb

@@ -354,6 +354,8 @@ void acb_ode_shift(acb_ode_t out, acb_ode_t in, acb_srcptr a, slong bits) {
 }
 
 // ------------------------------------------------------------------ solutions
+static void gens_put(HostArr& h, const acb_ode_solution_struct* sol, slong cap);
+static slong gens_cap(const acb_ode_solution_struct* sol, slong at_least);
 void acb_ode_solution_init(acb_ode_solution_t sol, acb_t rho, slong mul, slong alpha) {
     sol->mul = mul;
     sol->M = mul + alpha;
@@ -367,45 +369,49 @@ void acb_ode_solution_clear(acb_ode_solution_t sol) {
     sol->gens = nullptr;
 }
 
-void acb_ode_solution_evaluate(acb_t out, acb_ode_solution_t sol, acb_t a, slong prec) {
-    if (acb_is_zero(a)) {  // reference :29-33: indeterminate at the expansion point
-        acb_zero(out);
-        out->real.meta = cb_meta{0, CB_FLAG_NAN, CB_MAG_INF_MAN, 0};
-        out->imag.meta = cb_meta{0, CB_FLAG_NAN, CB_MAG_INF_MAN, 0};
-        return;
-    }
-    if (sol->M != 1) die("acb_ode_solution_evaluate with M > 1 (needs acb_log: listed as next in DESIGN.md)", -1);
-    // rho must be an exact non-negative integer below 2^31: a^rho by binary exponentiation
-    const arb_struct* r = &sol->rho->real;
-    bool ok = arb_exact_zero(&sol->rho->imag) && r->meta.rman == 0 && !(r->meta.flags & (CB_FLAG_NAN | CB_FLAG_SIGN));
-    uint64_t e = 0;
-    if (ok && !(r->meta.flags & CB_FLAG_ZERO)) {
-        ok = r->meta.exp >= 1 && r->meta.exp <= 31;
-        for (int k = 0; ok && k < CB_MAX_LIMBS - 1; k++) ok = r->mant[k] == 0;
-        if (ok) {
-            uint32_t top = r->mant[CB_MAX_LIMBS - 1];
-            e = top >> (32 - r->meta.exp);
-            ok = ((uint64_t)e << (32 - r->meta.exp)) == top;
-        }
-    }
-    if (!ok) die("acb_ode_solution_evaluate with a non-integer exponent (needs acb_pow: listed as next in DESIGN.md)", -1);
-    acb_t res, p, t;
-    acb_poly_evaluate(res, sol->gens, a, prec);
-    acb_one(p);
-    if (e > 0) {
-        acb_set(p, a);
-        int top = 63 - __builtin_clzll(e);
-        for (int bit = top - 1; bit >= 0; bit--) {
-            acb_mul(t, p, p, prec);
-            acb_set(p, t);
-            if ((e >> bit) & 1) {
-                acb_mul(t, p, a, prec);
-                acb_set(p, t);
-            }
-        }
-    }
-    acb_mul(out, res, p, prec);
+// how acb_pow treats the exponent: 0 exact zero, 1 exact integer 0 <= e < 2^31, 2 general
+static int pow_mode_of(const acb_struct* rho, uint64_t* e_out) {
+    const arb_struct* r = &rho->real;
+    *e_out = 0;
+    bool exact = arb_exact_zero(&rho->imag) && r->meta.rman == 0 && !(r->meta.flags & CB_FLAG_NAN);
+    if (!exact) return 2;
+    if (r->meta.flags & CB_FLAG_ZERO) return 0;
+    if ((r->meta.flags & CB_FLAG_SIGN) || r->meta.exp < 1 || r->meta.exp > 31) return 2;
+    for (int k = 0; k < CB_MAX_LIMBS - 1; k++)
+        if (r->mant[k]) return 2;
+    uint32_t top = r->mant[CB_MAX_LIMBS - 1];
+    uint64_t e = top >> (32 - r->meta.exp);
+    if ((e << (32 - r->meta.exp)) != top) return 2;
+    *e_out = e;
+    return 1;
 }
+// reference src/acb_ode_solution.c:24-58: Horner evaluation of the M series, acb_log, acb_pow and the
+// combination all run in ONE device launch (cb200_solution_evaluate_host)
+void acb_ode_solution_evaluate(acb_t out, acb_ode_solution_t sol, acb_t a, slong prec) {
+    int L = limbs_of(prec);
+    if (sol->M < 1 || sol->M > 16) die("acb_ode_solution_evaluate: M outside 1..16", -1);
+    slong cap = gens_cap(sol, 1);
+    HostArr hg(L, (size_t)(sol->M * cap), 2), hrho(L, 1, 2), hp(L, 1, 2), ho(L, 1, 2);
+    gens_put(hg, sol, cap);
+    hrho.put(0, 0, sol->rho);
+    hp.put(0, 0, a);
+    uint64_t e = 0;
+    int mode = pow_mode_of(sol->rho, &e);
+    int rc = cb200_solution_evaluate_host(L, (int)sol->M, cap, 1, hg.m.data(), hg.t.data(), hrho.m.data(), hrho.t.data(), mode,
+                                          e, hp.m.data(), hp.t.data(), ho.m.data(), ho.t.data(), 0);
+    if (rc) die("acb_ode_solution_evaluate (cb200_solution_evaluate_host)", rc);
+    ho.get(0, 0, out);
+}
+static void trans1(int which, acb_struct* z, const acb_struct* x, slong prec, const char* what) {
+    int L = limbs_of(prec);
+    HostArr hx(L, 1, 2), hz(L, 1, 2);
+    hx.put(0, 0, x);
+    int rc = cb200_trans_host(which, L, 1, hz.m.data(), hz.t.data(), hx.m.data(), hx.t.data(), 0);
+    if (rc) die(what, rc);
+    hz.get(0, 0, z);
+}
+void acb_exp(acb_t z, const acb_t x, slong prec) { trans1(CB200_TRANS_EXP, z, x, prec, "acb_exp (cb200_trans_host)"); }
+void acb_log(acb_t z, const acb_t x, slong prec) { trans1(CB200_TRANS_LOG, z, x, prec, "acb_log (cb200_trans_host)"); }
 
 // ------------------------------------------------------------------ examples
 void acb_ode_legendre(acb_ode_t ODE, ulong n) {

@@ -172,6 +172,33 @@ int cb200_indicial_polynomial_host(int L, int order, int degree, int valuation, 
                                    const uint32_t *ode_mant, const cb_meta *ode_meta, int shared_ode, int64_t nu,
                                    int64_t shift, uint32_t *out_mant, cb_meta *out_meta, int device);
 
+/* ---- acb_ode_solution_evaluate (reference src/acb_ode_solution.c:24-58) of ONE solution at npts points:
+ *   out = a^rho * sum_i C(M,i)-weighted gens[i](a) log(a)^(M-1-i)   (the weights as the reference codes them)
+ * with acb_log and acb_pow computed on the device (algorithms: oracle/cbo_trans.c, cascade_b200/csrc/cb_trans.cuh;
+ * Arb's own log/exp balls are implementation defined, any rigorous enclosure is admissible).
+ * gens : M*cap entries, S = 2 (gens[i][j] = entry i*cap + j; lengths implied by trailing exact zeros).
+ * rho  : 1 entry, S = 2.  pow_mode: 0 rho is the exact zero (a^rho = 1); 1 rho is the exact integer pow_e,
+ *        0 <= pow_e < 2^31 (binary exponentiation); 2 general (exp(rho log a)).  The caller inspects rho.
+ * pts  : 1 entry, S = 2*npts.  out: 1 entry, S = 2*npts.  An exactly zero point gives an indeterminate ball
+ * (reference :29-33); so does a point whose ball contains zero when a logarithm is needed. */
+size_t cb200_evaluate_workspace_bytes(int L, int64_t npts);
+int cb200_solution_evaluate_dev(int L, int M, int64_t cap, int64_t npts, const uint32_t *gens_mant,
+                                const cb_meta *gens_meta, const uint32_t *rho_mant, const cb_meta *rho_meta,
+                                int pow_mode, uint64_t pow_e, const uint32_t *pts_mant, const cb_meta *pts_meta,
+                                uint32_t *out_mant, cb_meta *out_meta, void *workspace, size_t workspace_bytes,
+                                void *stream);
+int cb200_solution_evaluate_host(int L, int M, int64_t cap, int64_t npts, const uint32_t *gens_mant,
+                                 const cb_meta *gens_meta, const uint32_t *rho_mant, const cb_meta *rho_meta,
+                                 int pow_mode, uint64_t pow_e, const uint32_t *pts_mant, const cb_meta *pts_meta,
+                                 uint32_t *out_mant, cb_meta *out_meta, int device);
+/* elementwise acb_exp (which = 0) / acb_log (which = 1) over n complex balls (1 entry, S = 2*n each) */
+#define CB200_TRANS_EXP 0
+#define CB200_TRANS_LOG 1
+int cb200_trans_dev(int which, int L, int64_t n, uint32_t *z_mant, cb_meta *z_meta, const uint32_t *x_mant,
+                    const cb_meta *x_meta, void *workspace, size_t workspace_bytes, void *stream);
+int cb200_trans_host(int which, int L, int64_t n, uint32_t *z_mant, cb_meta *z_meta, const uint32_t *x_mant,
+                     const cb_meta *x_meta, int device);
+
 /* ---- Horner evaluation batched over points (acb_poly_evaluate inside
  * acb_ode_solution_evaluate, reference src/acb_ode_solution.c:40,45; and the first `nder`
  * coefficients of acb_poly_taylor_shift, reference src/fuchs_solver.c:159).

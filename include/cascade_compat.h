@@ -94,6 +94,8 @@ void acb_div(acb_t z, const acb_t x, const acb_t y, slong prec);
 void acb_mul_si(acb_t z, const acb_t x, slong k, slong prec);
 void acb_add_si(acb_t z, const acb_t x, slong k, slong prec);
 void acb_poly_evaluate(acb_t y, const acb_poly_t f, const acb_t x, slong prec);
+void acb_exp(acb_t z, const acb_t x, slong prec);
+void acb_log(acb_t z, const acb_t x, slong prec);
 #endif /* ACB_H */
 
 /* ========================= Differential Operators (reference src/acb_ode.h:9-41) ============== */
@@ -130,10 +132,10 @@ typedef acb_ode_solution_struct acb_ode_solution_t[1];
 
 void acb_ode_solution_init(acb_ode_solution_t sol, acb_t rho, slong mul, slong alpha);
 void acb_ode_solution_clear(acb_ode_solution_t sol);
-/* a^rho * gens[0](a) (reference src/acb_ode_solution.c:24-58) for M == 1 and an exact non-negative
- * integer rho: Horner evaluation and the power (binary exponentiation) run on the device.  The
- * logarithmic case M > 1 and non-integer rho need acb_log / acb_pow, which are listed as next in
- * DESIGN.md; they abort here. */
+/* a^rho * sum_i w_i gens[i](a) log(a)^(M-1-i) (reference src/acb_ode_solution.c:24-58): the Horner
+ * evaluations, acb_log, acb_pow and the combination run in one device launch.  acb_log / acb_exp are
+ * the enclosure algorithms of cascade_b200/csrc/cb_trans.cuh (Arb's are not correctly rounded
+ * functions: the ball is a rigorous enclosure, a few tens of bits wider than the precision). */
 void acb_ode_solution_evaluate(acb_t res, acb_ode_solution_t sol, acb_t x, slong prec);
 /* the rho-derivative bookkeeping of the Frobenius solver (reference src/acb_ode_solution.c:60-123);
  * _update consumes f and _extend consumes g_nu (they come back as zero polynomials), as in the reference */

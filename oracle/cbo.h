@@ -163,6 +163,16 @@ int cbo_indicial_polynomial_evaluate_flat(int L, int order, int degree, const ui
 int cbo_solution_op_flat(int which, int L, int64_t batch, int64_t mul, int64_t M, int64_t cap, int64_t nu,
                          const uint32_t *rho_m, const int32_t *rho_t, uint32_t *gens_m, int32_t *gens_t,
                          uint32_t *f_m, int32_t *f_t, int64_t fcap);
+/* transcendental part of acb_ode_solution_evaluate (reference src/acb_ode_solution.c:24-58); see cbo_trans.c */
+void cbo_acb_exp(cbo_acb *res, const cbo_acb *z, int L);
+void cbo_acb_log(cbo_acb *res, const cbo_acb *a, int L);
+void cbo_acb_pow_mode(cbo_acb *res, const cbo_acb *a, const cbo_acb *rho, int mode, uint64_t e,
+                      const cbo_acb *lg, int L);
+int cbo_solution_evaluate_flat(int L, int64_t M, int64_t cap, int64_t npts, const uint32_t *gens_m,
+                               const int32_t *gens_t, const uint32_t *rho_m, const int32_t *rho_t,
+                               int pow_mode, uint64_t pow_e, const uint32_t *a_m, const int32_t *a_t,
+                               uint32_t *out_m, int32_t *out_t);
+int cbo_ew_trans(int which, int L, int64_t n, uint32_t *zm, int32_t *zt, const uint32_t *xm, const int32_t *xt);
 const char *cbo_backend(void); /* "gmp-mpn" or "plain-c" */
 
 #ifdef __cplusplus

@@ -51,6 +51,9 @@ def lib(plain: bool = False) -> C.CDLL:
     L.cbo_continuation_flat.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, _u32p, _i32p,
                                         _u32p, _i32p, _u32p, _i32p]
     L.cbo_example_flat.argtypes = [C.c_int, C.c_int, C.c_uint64, _u32p, _i32p, _u32p, _i32p]
+    L.cbo_ew_trans.argtypes = [C.c_int, C.c_int, C.c_int64, _u32p, _i32p, _u32p, _i32p]
+    L.cbo_solution_evaluate_flat.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int64, _u32p, _i32p, _u32p, _i32p, C.c_int,
+                                             C.c_uint64, _u32p, _i32p, _u32p, _i32p]
     L.cbo_frobenius1_rhs_batch.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, _u32p, _i32p,
                                            _u32p, _i32p, _u32p, _i32p, C.c_int64, _u32p, _i32p]
     L.cbo_frobenius_general_batch.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, _u32p, _i32p,
@@ -210,3 +213,23 @@ def solution_op(which: str, rho: Balls, gens: Balls, batch: int, mul: int, M: in
                                          ff.mant, ff.meta, fcap)
     assert rc == 0
     return g, ff
+
+
+def ew_trans(which: str, x: Balls, plain: bool = False) -> Balls:
+    """acb_exp / acb_log of n complex balls (the oracle's algorithms, see oracle/cbo_trans.c)."""
+    z = Balls.zeros(x.n_slots, x.L)
+    rc = lib(plain).cbo_ew_trans({"exp": 0, "log": 1}[which], x.L, x.n_slots // 2, z.mant, z.meta, x.mant, x.meta)
+    assert rc == 0
+    return z
+
+
+def solution_evaluate(gens: Balls, M: int, rho: Balls, pow_mode: int, pow_e: int, pts: Balls, plain: bool = False) -> Balls:
+    """acb_ode_solution_evaluate (reference src/acb_ode_solution.c:24-58) of one solution (gens[M][cap], rho)
+    at every point of pts."""
+    cap = gens.n_slots // (2 * M)
+    npts = pts.n_slots // 2
+    out = Balls.zeros(2 * npts, gens.L)
+    rc = lib(plain).cbo_solution_evaluate_flat(gens.L, M, cap, npts, gens.mant, gens.meta, rho.mant, rho.meta, pow_mode,
+                                               pow_e, pts.mant, pts.meta, out.mant, out.meta)
+    assert rc == 0
+    return out

@@ -759,3 +759,20 @@ int cbo_ew_scalar_si(int op, int L, int64_t n, uint32_t *zm, int32_t *zt, const 
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------ helpers of cbo_trans.c */
+void cbo_arb_set_nan(cbo_arb *z) { arb_set_nan(z); }
+/* radius += 2^e (rounded up) */
+void cbo_arb_add_error_2exp(cbo_arb *z, int64_t e) {
+    if (is_nan(z)) return;
+    mg u;
+    u.man = MAG_ONE_HALF;
+    u.exp = e + 1;
+    set_rad(z, mg_add(mg_of(z), u));
+}
+/* z *= 2^k, exact */
+void cbo_arb_mul_2exp(cbo_arb *z, int64_t k) {
+    if (is_nan(z)) return;
+    if (!(z->flags & CBO_ZERO)) z->exp = (int32_t)(z->exp + k);
+    if (z->rman) z->rexp = (int32_t)(z->rexp + k);
+}

@@ -25,6 +25,16 @@ int main ()
         acb_poly_get_coeff_acb(z, sol->gens + 1, k);
         printf("gens %ld %.17g %.17g %.3g\n", k, acb_get_mid_re_d(y), acb_get_mid_re_d(z), acb_get_rad_re_d(z));
     }
+    /* acb_ode_solution_evaluate with M = 2: gens[0](x) log(x) + 2 gens[1](x) at x = 1/8 (rho = 0), and
+     * acb_log / acb_exp on their own */
+    acb_set_d(z, 0.125);
+    acb_ode_solution_evaluate(y, sol, z, prec);
+    printf("eval2 %.17g %.17g %.3g\n", acb_get_mid_re_d(y), acb_get_mid_im_d(y), acb_get_rad_re_d(y));
+    acb_set_d_d(z, -0.125, 0.0);
+    acb_log(y, z, prec);
+    printf("log %.17g %.17g %.3g\n", acb_get_mid_re_d(y), acb_get_mid_im_d(y), acb_get_rad_re_d(y));
+    acb_exp(y, y, prec);
+    printf("explog %.17g %.17g %.3g\n", acb_get_mid_re_d(y), acb_get_mid_im_d(y), acb_get_rad_re_d(y));
     acb_ode_solution_clear(sol);
 
     acb_poly_init(f);

@@ -494,3 +494,60 @@ def case_frobenius_rhs(oracle, drv, L: int, seed: int, n: int = 14, batch: int =
     rs = api.acb_ode_solve_frobenius1_batch(odes, rho, 2, 2, n, batch, False, False, driver=drv, rhs=rhs)
     assert_same(ro, rs, f"frobenius with rhs L={L}")
     assert rs.mid(2 * (2 * (n + 1))) == 1  # instance 2: g_0 = 1
+
+
+def trans_inputs(rng, L: int, n: int) -> Balls:
+    """Complex balls for exp/log: generic, real, imaginary, tiny, large, negative real axis (branch cut side),
+    wide radii, an exact zero and a ball containing zero."""
+    x = random_balls(rng, 2 * n, L, -3, 3, "ulp")
+    special = [(F(3, 2), F(1, 4)), (F(-5, 8), F(7, 3)), (F(1, 1024), 0), (-3, 0), (0, F(-9, 4)), (F(12345, 7), -100),
+               (F(1, 3), F(1, 10**6)), (20, 0), (F(-1, 2**40), F(1, 2**60)), (1, 0), (0, 0), (F(1, 2**300), 0)]
+    sp = from_complex(special, L)
+    k = min(len(special), n)
+    x.mant[: 2 * k] = sp.mant[: 2 * k]
+    x.meta[: 2 * k] = sp.meta[: 2 * k]
+    if n > k + 2:  # a wide ball, and a ball containing zero
+        x.meta[2 * k, 2], x.meta[2 * k, 3] = 1 << 29, x.meta[2 * k, 0] - 20
+        x.meta[2 * k + 2, 2], x.meta[2 * k + 2, 3] = 1 << 29, x.meta[2 * k + 2, 0] + 3
+        x.meta[2 * k + 3, 2], x.meta[2 * k + 3, 3] = 1 << 29, x.meta[2 * k + 3, 0] + 3
+    return x
+
+
+def case_exp_log(oracle, drv, L: int, seed: int, n: int = 24):
+    """acb_exp / acb_log on the device against the oracle's algorithms (bit-exact: same ball operations in
+    the same order, double-precision seed from IEEE +,-,*,/ only), plus exp(log(a)) overlapping a."""
+    rng = np.random.default_rng(seed)
+    x = trans_inputs(rng, L, n)
+    le = api.acb_exp_batch(x, driver=drv)
+    assert_same(oracle.ew_trans("exp", x), le, f"acb_exp L={L}")
+    ll = api.acb_log_batch(x, driver=drv)
+    assert_same(oracle.ew_trans("log", x), ll, f"acb_log L={L}")
+    back = api.acb_exp_batch(ll, driver=drv)
+    for i in range(n):
+        if (int(ll.meta[2 * i, 1]) | int(ll.meta[2 * i + 1, 1])) & FLAG_NAN:
+            continue
+        for part in (0, 1):
+            s = 2 * i + part
+            assert abs(back.mid(s) - x.mid(s)) <= back.rad(s) + x.rad(s), (i, part)
+
+
+def case_solution_evaluate(oracle, drv, L: int, seed: int, npts: int = 7, cap: int = 12):
+    """acb_ode_solution_evaluate (reference src/acb_ode_solution.c:24-58; reference tests/solution_eval.c):
+    M = 1..3, rho zero / small integer / generic complex, points including an exact zero."""
+    rng = np.random.default_rng(seed)
+    pts = random_balls(rng, 2 * npts, L, -2, 0, "zero")
+    pts.mant[2:4] = 0
+    pts.meta[2:4] = (0, FLAG_ZERO, 0, 0)  # point 1 is exactly zero: indeterminate result
+    for M in (1, 2, 3):
+        gens = random_balls(rng, 2 * M * cap, L, -2, 2, "ulp")
+        g = gens.mant.reshape(M, cap, 2, L)
+        t = gens.meta.reshape(M, cap, 2, 4)
+        g[M - 1, cap - 3:] = 0
+        t[M - 1, cap - 3:] = (0, FLAG_ZERO, 0, 0)  # a shorter series
+        for rho in (from_complex([0], L), from_complex([5], L), from_complex([(F(1, 3), F(-1, 7))], L),
+                    random_balls(rng, 2, L, -1, 1, "ulp")):
+            mode, e = api.pow_mode_of(rho)
+            want = oracle.solution_evaluate(gens, M, rho, mode, e, pts)
+            got = api.acb_ode_solution_evaluate_batch(gens, M, rho, pts, driver=drv)
+            assert_same(want, got, f"solution_evaluate L={L} M={M} mode={mode}")
+            assert int(got.meta[2, 1]) & FLAG_NAN

@@ -19,10 +19,10 @@ _lib = None
 
 def build(force: bool = False) -> None:
     deps = [_SRC] + [os.path.join(_HERE, "..", "..", "cascade_b200", "csrc", f)
-                     for f in ("cb_arith.cuh", "cb_solvers.cuh", "cb_mul.cuh", "cb_rr.cuh")]
+                     for f in ("cb_arith.cuh", "cb_solvers.cuh", "cb_mul.cuh", "cb_rr.cuh", "cb_trans.cuh")]
     if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
         return
-    subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+    subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-ffp-contract=off",
                     "-o", _SO, _SRC], check=True)
 
 
@@ -43,6 +43,9 @@ def lib():
                                         _u32p, _i32p, _u32p, _i32p, C.c_int64]
         L.cbsim_indicial_polynomial.argtypes = [C.c_int] * 4 + [C.c_int64, _u32p, _i32p, C.c_int, C.c_int64, C.c_int64,
                                                                 _u32p, _i32p]
+        L.cbsim_solution_evaluate.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int64, _u32p, _i32p, _u32p, _i32p, C.c_int,
+                                              C.c_uint64, _u32p, _i32p, _u32p, _i32p]
+        L.cbsim_trans.argtypes = [C.c_int, C.c_int, C.c_int64, _u32p, _i32p, _u32p, _i32p]
         _lib = L
     return _lib
 
@@ -75,6 +78,12 @@ class SimDriver:
     def indicial_polynomial(self, L, order, degree, valuation, batch, ode_m, ode_t, shared, nu, shift, out_m, out_t):
         return lib().cbsim_indicial_polynomial(L, order, degree, valuation, batch, ode_m, ode_t, int(shared), nu, shift,
                                                out_m, out_t)
+
+    def solution_evaluate(self, L, M, cap, npts, g_m, g_t, rho_m, rho_t, pow_mode, pow_e, p_m, p_t, o_m, o_t):
+        return lib().cbsim_solution_evaluate(L, M, cap, npts, g_m, g_t, rho_m, rho_t, pow_mode, pow_e, p_m, p_t, o_m, o_t)
+
+    def trans(self, which, L, n, z_m, z_t, x_m, x_t):
+        return lib().cbsim_trans(which, L, n, z_m, z_t, x_m, x_t)
 
     def horner(self, L, length, npts, nder, f_m, f_t, shared_f, p_m, p_t, o_m, o_t):
         return lib().cbsim_horner_batch(L, length, npts, nder, f_m, f_t, int(shared_f), p_m, p_t, o_m, o_t)

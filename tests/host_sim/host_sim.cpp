@@ -179,6 +179,33 @@ int cbsim_indicial_polynomial(int L_, int order, int degree, int valuation, int6
     return 0;
 }
 
+int cbsim_solution_evaluate(int L_, int M, int64_t cap, int64_t npts, const uint32_t* gens_mant, const cb_meta* gens_meta,
+                            const uint32_t* rho_mant, const cb_meta* rho_meta, int pow_mode, uint64_t pow_e,
+                            const uint32_t* pts_mant, const cb_meta* pts_meta, uint32_t* out_mant, cb_meta* out_meta) {
+    if (M < 1 || M > FROBG_MAXM) return CB200_EINVAL;
+    EvalParams p;
+    p.M = M; p.pow_mode = pow_mode; p.pow_e = pow_e; p.cap = cap; p.npts = npts;
+    p.gens = CArr{const_cast<uint32_t*>(gens_mant), (Meta*)const_cast<cb_meta*>(gens_meta), (size_t)2};
+    p.rho = CArr{const_cast<uint32_t*>(rho_mant), (Meta*)const_cast<cb_meta*>(rho_meta), (size_t)2};
+    p.pts = CArr{const_cast<uint32_t*>(pts_mant), (Meta*)const_cast<cb_meta*>(pts_meta), (size_t)(2 * npts)};
+    p.out = CArr{out_mant, (Meta*)out_meta, (size_t)(2 * npts)};
+    Tmp tmp;
+    p.wp = tmp.arr(L_, TRANS_NTMP + 4, 2 * npts);
+    SIM_DISPATCH(L_, run<L>(npts, [&](int64_t i, Scratch<1> a, Scratch<1> b) { evaluate_thread<L>(p, i, a, b); }));
+    return 0;
+}
+
+int cbsim_trans(int which, int L_, int64_t n, uint32_t* z_mant, cb_meta* z_meta, const uint32_t* x_mant, const cb_meta* x_meta) {
+    TransParams p;
+    p.which = which; p.n = n;
+    p.z = CArr{z_mant, (Meta*)z_meta, (size_t)(2 * n)};
+    p.x = CArr{const_cast<uint32_t*>(x_mant), (Meta*)const_cast<cb_meta*>(x_meta), (size_t)(2 * n)};
+    Tmp tmp;
+    p.wp = tmp.arr(L_, TRANS_NTMP, 2 * n);
+    SIM_DISPATCH(L_, run<L>(n, [&](int64_t i, Scratch<1> a, Scratch<1> b) { trans_thread<L>(p, i, a, b); }));
+    return 0;
+}
+
 int cbsim_horner_batch(int L_, int64_t len, int64_t npts, int nder, const uint32_t* f_mant,
                        const cb_meta* f_meta, int shared_f, const uint32_t* pts_mant,
                        const cb_meta* pts_meta, uint32_t* out_mant, cb_meta* out_meta) {

@@ -99,3 +99,13 @@ def test_reduced_radix_products(oracle, sim_driver, monkeypatch):
     cases.case_fuchs_bessel_shared(oracle, sim_driver, 32, seed=5, n=40, batch=3)
     cases.case_fuchs_random_shared(oracle, sim_driver, 32, seed=63, trials=6)
     cases.case_fuchs_shared_adversarial(oracle, sim_driver, 32, seed=109, batch=12)
+
+
+@pytest.mark.parametrize("L", [4, 32])
+def test_exp_log(oracle, sim_driver, L):
+    cases.case_exp_log(oracle, sim_driver, L, seed=61 + L, n=20 if L == 4 else 16)
+
+
+@pytest.mark.parametrize("L", [4, 32])
+def test_solution_evaluate(oracle, sim_driver, L):
+    cases.case_solution_evaluate(oracle, sim_driver, L, seed=67 + L, npts=4, cap=8 if L == 32 else 12)

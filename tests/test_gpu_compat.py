@@ -57,7 +57,16 @@ def test_logarithmic_frobenius_and_solution_bookkeeping():
         fac = (k + a) * (k + b) / F((k + 1) ** 2)
         dg = dg * fac + g * fac * ld
         g = g * fac
-    vals = {r[0] + (r[1] if r[0] in ("indicial", "extend", "update") else ""): r for r in rows if r[0] != "gens"}
+    # acb_ode_solution_evaluate, M = 2, rho = 0: gens[0](x) log(x) + 2 gens[1](x) with the printed coefficients
+    x = 0.125
+    want = sum(gens[k][0] * x ** k for k in range(n + 1)) * math.log(x) + 2 * sum(gens[k][1] * x ** k for k in range(n + 1))
+    ev = [float(v) for v in next(r for r in rows if r[0] == "eval2")[1:]]
+    assert abs(ev[0] - want) < 1e-13 * abs(want) and ev[1] == 0.0 and ev[2] < 1e-290
+    lg = [float(v) for v in next(r for r in rows if r[0] == "log")[1:]]
+    assert abs(lg[0] - math.log(0.125)) < 1e-15 and abs(lg[1] - math.pi) < 1e-15 and lg[2] < 1e-290
+    el = [float(v) for v in next(r for r in rows if r[0] == "explog")[1:]]
+    assert abs(el[0] + 0.125) < 1e-16 and abs(el[1]) < 1e-290
+    vals = {r[0] + (r[1] if r[0] in ("indicial", "extend", "update") else ""): r for r in rows if r[0] not in ("gens", "eval2", "log", "explog")}
     assert vals["indicial_len"][1] == "3"
     assert [float(vals[f"indicial{k}"][2]) for k in range(3)] == [9.0, 6.0, 1.0]
     assert float(vals["indicial_at_2"][1]) == 25.0 and float(vals["indicial_at_2"][2]) == 25.0

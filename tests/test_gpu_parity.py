@@ -100,3 +100,13 @@ def test_reduced_radix_products(oracle, gpu_driver, monkeypatch):
     cases.case_fuchs_bessel_shared(oracle, gpu_driver, 32, seed=5, n=60, batch=300)
     cases.case_fuchs_random_shared(oracle, gpu_driver, 32, seed=63, trials=6, batch=45)
     cases.case_fuchs_shared_adversarial(oracle, gpu_driver, 32, seed=109, batch=70)
+
+
+@pytest.mark.parametrize("L", [4, 32, 64, 128])
+def test_exp_log(oracle, gpu_driver, L):
+    cases.case_exp_log(oracle, gpu_driver, L, seed=61 + L, n=40 if L < 128 else 24)
+
+
+@pytest.mark.parametrize("L", [4, 32, 64])
+def test_solution_evaluate(oracle, gpu_driver, L):
+    cases.case_solution_evaluate(oracle, gpu_driver, L, seed=67 + L, npts=40, cap=16)
