@@ -611,4 +611,162 @@ void acb_ode_solve_frobenius(acb_ode_solution_t sol, acb_ode_t ODE, slong sol_de
     gens_get(hg, sol, cap);
 }
 
+
+// ------------------------------------------------------------------ monodromy (reference src/fuchs_solver.c:3-94,165-206)
+// Control-plane scalars (the convergence radius that sizes the path and the truncation order) are
+// formed in double precision on the host: the reference uses them only through arb_get_mid_arb
+// (:178) and as an integer count (:190), and its own continuation adds no truncation bound, so no
+// rigour hangs on them.  Every BALL of the computation -- the 256 path corners exp(2 pi i k / 256),
+// the shifted operators, the series and their re-expansions -- is computed on the device.
+void arb_init(arb_t x) { memset(x, 0, sizeof(arb_struct)); x->meta.flags = CB_FLAG_ZERO; }
+void arb_clear(arb_t) {}
+void arb_set_d(arb_t x, double v) { arb_set_double(x, v); }
+double arb_get_mid_d(const arb_t x) { return arb_mid_d(x); }
+double arb_get_rad_d(const arb_t x) { return arb_rad_d(x); }
+int arb_is_finite(const arb_t x) { return !(x->meta.flags & CB_FLAG_NAN); }
+
+void acb_mat_init(acb_mat_t m, slong r, slong c) {
+    m->r = r;
+    m->c = c;
+    m->entries = _acb_vec_init(r * c);
+    m->rows = (acb_ptr*)malloc(sizeof(acb_ptr) * (r > 0 ? r : 1));
+    for (slong i = 0; i < r; i++) m->rows[i] = m->entries + i * c;
+}
+void acb_mat_clear(acb_mat_t m) {
+    _acb_vec_clear(m->entries, m->r * m->c);
+    free(m->rows);
+}
+
+// min |root| of the polynomial sum_k c[k] z^k (c[0] != 0, c[n] != 0), Durand-Kerner in complex long double
+static long double min_root_modulus(const long double* cr, const long double* ci, int n) {
+    struct Z { long double r, i; };
+    auto mul = [](Z a, Z b) { return Z{a.r * b.r - a.i * b.i, a.r * b.i + a.i * b.r}; };
+    auto divz = [](Z a, Z b) { long double d = b.r * b.r + b.i * b.i; return Z{(a.r * b.r + a.i * b.i) / d, (a.i * b.r - a.r * b.i) / d}; };
+    std::vector<Z> z(n);
+    long double scale = 0;
+    for (int k = 0; k <= n; k++) scale = fmaxl(scale, hypotl(cr[k], ci[k]));
+    long double R = 1 + scale / hypotl(cr[n], ci[n]);  // Cauchy bound
+    for (int k = 0; k < n; k++) z[k] = Z{0.5L * R * cosl(0.7L + 2.0L * 3.14159265358979323846L * k / n), 0.5L * R * sinl(0.7L + 2.0L * 3.14159265358979323846L * k / n)};
+    for (int it = 0; it < 500; it++) {
+        long double move = 0;
+        for (int k = 0; k < n; k++) {
+            Z p{cr[n], ci[n]};
+            for (int j = n - 1; j >= 0; j--) { p = mul(p, z[k]); p.r += cr[j]; p.i += ci[j]; }
+            Z q{cr[n], ci[n]};
+            for (int j = 0; j < n; j++) if (j != k) q = mul(q, Z{z[k].r - z[j].r, z[k].i - z[j].i});
+            if (q.r == 0 && q.i == 0) { z[k].r += 1e-9L; continue; }
+            Z d = divz(p, q);
+            z[k].r -= d.r;
+            z[k].i -= d.i;
+            move = fmaxl(move, hypotl(d.r, d.i));
+        }
+        if (move < 1e-17L * R) break;
+    }
+    long double m = INFINITY;
+    for (int k = 0; k < n; k++) m = fminl(m, hypotl(z[k].r, z[k].i));
+    return m;
+}
+
+void radius_of_convergence(arb_t rad_of_conv, acb_ode_t ODE, slong n, slong bits) {
+    (void)n;
+    (void)bits;
+    // the leading polynomial without its factor z^i (reference :11-15: a singularity at zero does not count)
+    slong ord = ODE->order, deg = ODE->degree, low = -1;
+    for (slong i = deg; i >= 0; i--)
+        if (!acb_is_zero(acb_ode_coeff(ODE, ord, i))) low = i;
+    slong top = -1;
+    for (slong i = 0; i <= deg; i++)
+        if (!acb_is_zero(acb_ode_coeff(ODE, ord, i))) top = i;
+    if (low < 0 || top - low < 1) {  // no singularities away from zero: indeterminate (reference :17-22)
+        memset(rad_of_conv, 0, sizeof(arb_struct));
+        rad_of_conv->meta.flags = CB_FLAG_NAN;
+        rad_of_conv->meta.rman = CB_MAG_INF_MAN;
+        return;
+    }
+    int m = (int)(top - low);
+    std::vector<long double> cr(m + 1), ci(m + 1);
+    for (int k = 0; k <= m; k++) {
+        cr[k] = acb_get_mid_re_d(acb_ode_coeff(ODE, ord, low + k));
+        ci[k] = acb_get_mid_im_d(acb_ode_coeff(ODE, ord, low + k));
+    }
+    double r = (double)min_root_modulus(cr.data(), ci.data(), m);
+    // a lower estimate with a visible error bar (2^-30 relative), as the reference's enclosure has
+    arb_set_double(rad_of_conv, r * (1.0 - ldexp(1.0, -30)));
+    int e;
+    frexp(r, &e);
+    rad_of_conv->meta.rman = 1u << 29;
+    rad_of_conv->meta.rexp = e - 30 + 1;
+}
+
+slong truncation_order(arb_t eta, arb_t alpha, slong bits) {  // reference :56-94
+    if (!arb_is_finite(eta) || !arb_is_finite(alpha)) return 2 * bits;
+    long double e = arb_mid_d(eta), a = arb_mid_d(alpha);
+    if (!(e + arb_rad_d(eta) < a - arb_rad_d(alpha))) return 0;
+    long double r = e / ((e + a) / 2);
+    long double N = (logl(1 - r) - (long double)bits * logl(2.0L)) / logl(r);
+    return (slong)ceill(N);
+}
+
+void find_monodromy_matrix(acb_mat_t mono, acb_ode_t ODE, slong bits) {
+    int L = limbs_of(bits);
+    arb_t rad;
+    radius_of_convergence(rad, ODE, 40, bits);
+    double r;
+    if (arb_exact_zero(rad)) return;
+    if (!arb_is_finite(rad)) r = 1.0;                // reference :173-174
+    else r = arb_mid_d(rad) / 2;                      // :176-178 (midpoint of half the radius)
+    const slong steps = 256;
+    slong ord = ODE->order;
+    if (ord > 4) die("find_monodromy_matrix: order > 4", -1);
+    // corners r * exp(2 pi i k / steps): i pi = log(-1), theta_k = (i pi) * k / 128, one batched exp launch
+    acb_t minus1, ipi;
+    acb_set_si(minus1, -1);
+    acb_log(ipi, minus1, bits);
+    HostArr hx(L, 1, 2 * steps), hk(L, 1, 2 * steps), hz(L, 1, 2 * steps), hr(L, 1, 2 * steps);
+    std::vector<int64_t> kk(steps);
+    acb_t rb;
+    acb_set_d(rb, r);
+    for (slong k = 0; k < steps; k++) {
+        hx.put(0, k, ipi);
+        hr.put(0, k, rb);
+        kk[k] = k;
+    }
+    int rc = cb200_ew_host(CB200_OP_MUL_SI, L, steps, hk.m.data(), hk.t.data(), hx.m.data(), hx.t.data(), nullptr, nullptr,
+                           kk.data(), 0);
+    if (rc) die("find_monodromy_matrix (cb200_ew_host)", rc);
+    for (auto& t : hk.t) {  // divide by 128: an exact exponent shift
+        if (!(t.flags & (CB_FLAG_ZERO | CB_FLAG_NAN))) t.exp -= 7;
+        if (t.rman) t.rexp -= 7;
+    }
+    rc = cb200_trans_host(CB200_TRANS_EXP, L, steps, hz.m.data(), hz.t.data(), hk.m.data(), hk.t.data(), 0);
+    if (rc) die("find_monodromy_matrix (cb200_trans_host)", rc);
+    rc = cb200_ew_host(CB200_OP_MUL, L, steps, hx.m.data(), hx.t.data(), hz.m.data(), hz.t.data(), hr.m.data(), hr.t.data(),
+                       nullptr, 0);
+    if (rc) die("find_monodromy_matrix (cb200_ew_host)", rc);
+    acb_ptr path = _acb_vec_init(steps + 1);
+    for (slong k = 0; k < steps; k++) hx.get(0, k, path + k);
+    acb_set(path + steps, path);  // closed loop (:191)
+    // number of coefficients: eta = |path[0] - path[1]|, alpha = r (:187-190)
+    arb_t eta, alpha;
+    arb_set_double(eta, 2 * r * sin(3.14159265358979323846 / steps));
+    arb_set_double(alpha, r);
+    slong n = truncation_order(eta, alpha, bits);
+    if (n < ord) n = ord;
+    // the `order` unit initial vectors continue together: one batch along the path (:195-202)
+    slong ne = (ODE->order + 1) * (ODE->degree + 1);
+    HostArr ho(L, ne, 2), hp(L, steps + 1, 2), hy(L, ord, 2 * ord);
+    for (slong e = 0; e < ne; e++) ho.put(e, 0, ODE->polys + e);
+    for (slong t = 0; t <= steps; t++) hp.put(t, 0, path + t);
+    acb_t one;
+    acb_one(one);
+    for (slong i = 0; i < ord; i++) hy.put(i, i, one);  // instance i starts from res = z^i
+    rc = cb200_continuation_host(L, (int)ord, (int)ODE->degree, n, ord, steps + 1, ho.m.data(), ho.t.data(), hp.m.data(),
+                                 hp.t.data(), hy.m.data(), hy.t.data(), 0);
+    if (rc) die("find_monodromy_matrix (cb200_continuation_host)", rc);
+    // row i of the reference's matrix before the transpose = the order Taylor coefficients of solution i
+    for (slong i = 0; i < ord; i++)
+        for (slong k = 0; k < ord; k++) hy.get(k, i, mono->rows[k] + i);
+    _acb_vec_clear(path, steps + 1);
+}
+
 }  // extern "C"

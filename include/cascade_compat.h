@@ -96,6 +96,21 @@ void acb_add_si(acb_t z, const acb_t x, slong k, slong prec);
 void acb_poly_evaluate(acb_t y, const acb_poly_t f, const acb_t x, slong prec);
 void acb_exp(acb_t z, const acb_t x, slong prec);
 void acb_log(acb_t z, const acb_t x, slong prec);
+void arb_init(arb_t x);
+void arb_clear(arb_t x);
+void arb_set_d(arb_t x, double v);
+double arb_get_mid_d(const arb_t x);
+double arb_get_rad_d(const arb_t x);
+int arb_is_finite(const arb_t x);
+typedef struct {
+    acb_ptr entries;
+    slong r, c;
+    acb_ptr *rows;
+} acb_mat_struct;
+typedef acb_mat_struct acb_mat_t[1];
+#define acb_mat_entry(mat, i, j) ((mat)->rows[i] + (j))
+void acb_mat_init(acb_mat_t m, slong r, slong c);
+void acb_mat_clear(acb_mat_t m);
 #endif /* ACB_H */
 
 /* ========================= Differential Operators (reference src/acb_ode.h:9-41) ============== */
@@ -154,6 +169,13 @@ void acb_ode_solve_fuchs(acb_poly_t res, acb_ode_t ODE, slong deg, slong bits);
  * Taylor coefficients survive into the next step; they are produced by Horner
  * evaluation on the device.  On return res holds those `order` coefficients at the last corner. */
 void analytic_continuation(acb_poly_t res, acb_ode_t ODE, acb_srcptr path, slong len, slong deg, slong bits);
+/* Monodromy around the origin along the 256-gon of half the convergence radius (reference
+ * src/fuchs_solver.c:165-206): the `order` unit initial vectors continue together as one device-resident
+ * batch.  radius_of_convergence / truncation_order (src/fuchs_solver.c:3-94) are control-plane scalars and
+ * are formed in double precision on the host (the reference consumes only a midpoint and an integer). */
+void radius_of_convergence(arb_t rad_of_conv, acb_ode_t ODE, slong n, slong bits);
+slong truncation_order(arb_t eta, arb_t alpha, slong bits);
+void find_monodromy_matrix(acb_mat_t mono, acb_ode_t ODE, slong bits);
 void indicial_polynomial_evaluate(acb_t result, acb_ode_t ODE, slong nu, acb_t rho, slong shift, slong prec);
 void _acb_ode_solve_frobenius(acb_poly_t res, acb_ode_t ODE, acb_ode_solution_t rhs, slong sol_degree, slong prec);
 /* M == 1: the scalar recurrence; M > 1: the polynomial-in-rho (logarithmic) recurrence of

@@ -75,3 +75,15 @@ def test_logarithmic_frobenius_and_solution_bookkeeping():
     # Leibniz with f = rho at 1/2: [f g, f g' + f' g, f g'' + 2 f' g'] = [1.375, 5.25, 13]
     assert [float(vals[f"update{i}"][2]) for i in range(3)] == [1.375, 5.25, 13.0]
     assert vals["update_consumed"][1] == "0" and vals["normalize_finite"][1] == "0"
+
+
+def test_monodromy_matrix():
+    """find_monodromy_matrix (reference src/fuchs_solver.c:165-206) for 2F1(1/2, 1/4; 3/4): eigenvalues 1 and
+    exp(2 pi i / 4) = i.  The reference's continuation adds no truncation bound, so the test compares midpoints
+    (the truncation order leaves about 2^-1024) and checks that the balls stayed tight over 256 steps."""
+    out = build_and_run("monodromy_example")
+    v = {line.split()[0]: [float(x) for x in line.split()[1:]] for line in out.strip().splitlines()}
+    assert abs(v["radius"][0] - 1.0) < 1e-8 and v["radius"][0] <= 1.0
+    assert 200 <= v["truncation_order"][0] <= 260
+    assert abs(v["trace"][0] - 1.0) < 1e-13 and abs(v["trace"][1] - 1.0) < 1e-13 and v["trace"][2] < 1e-200
+    assert abs(v["det"][0]) < 1e-13 and abs(v["det"][1] - 1.0) < 1e-13 and v["det"][2] < 1e-200
