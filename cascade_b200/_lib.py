@@ -38,6 +38,7 @@ SYMBOLS = [
     "cb200_indicial_polynomial_dev", "cb200_indicial_polynomial_host",
     "cb200_evaluate_workspace_bytes", "cb200_solution_evaluate_dev", "cb200_solution_evaluate_host",
     "cb200_trans_dev", "cb200_trans_host",
+    "cb200_ode_apply_workspace_bytes", "cb200_ode_apply_dev", "cb200_ode_apply_host",
 ]
 
 
@@ -106,6 +107,12 @@ def lib() -> C.CDLL:
                                                C.c_uint64, _u32p, _i32p, _u32p, _i32p, C.c_int]
     L.cb200_trans_dev.argtypes = [C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]
     L.cb200_trans_host.argtypes = [C.c_int, C.c_int, C.c_int64, _u32p, _i32p, _u32p, _i32p, C.c_int]
+    L.cb200_ode_apply_workspace_bytes.restype = C.c_size_t
+    L.cb200_ode_apply_workspace_bytes.argtypes = [C.c_int, C.c_int64, C.c_int64]
+    L.cb200_ode_apply_dev.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, _vp, _vp, C.c_int, _vp, _vp, C.c_int64, _vp, _vp,
+                                      C.c_int64, C.c_int64, _vp, _vp, C.c_size_t, _vp]
+    L.cb200_ode_apply_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, _u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int64,
+                                       _u32p, _i32p, C.c_int64, C.c_int64, _i32p, C.c_int]
     _lib = L
     return L
 

@@ -70,6 +70,10 @@ class HostBufferDriver:
     def trans(self, which, L, n, z_m, z_t, x_m, x_t):
         return _lib.lib().cb200_trans_host(which, L, n, z_m, z_t, x_m, x_t, self.device)
 
+    def ode_apply(self, L, order, degree, batch, ode_m, ode_t, shared, in_m, in_t, len_in, o_m, o_t, out_len, deg, solved):
+        return _lib.lib().cb200_ode_apply_host(L, order, degree, batch, ode_m, ode_t, int(shared), in_m, in_t, len_in, o_m,
+                                               o_t, out_len, deg, solved, self.device)
+
     def horner(self, L, length, npts, nder, f_m, f_t, shared_f, p_m, p_t, o_m, o_t):
         return _lib.lib().cb200_horner_batch_host(L, length, npts, nder, f_m, f_t, int(shared_f), p_m, p_t,
                                                   o_m, o_t, self.device)
@@ -296,6 +300,26 @@ def acb_poly_evaluate_batch(f: Balls, pts: Balls, nder: int = 1, driver=None) ->
     o_t = np.zeros((nder, 2 * npts, 4), np.int32)
     _lib.check(drv.horner(L, length, npts, nder, f_m, f_t, True, p_m, p_t, o_m, o_t), "acb_poly_evaluate_batch")
     return entry_major_to_instance_major(unpack_entries(L, o_m, o_t), npts, nder)
+
+
+def acb_ode_apply_batch(ode: Balls, series: Balls, order: int, degree: int, batch: int, shared_ode: bool = True,
+                        deg: int | None = None, driver=None):
+    """``acb_ode_apply`` / ``acb_ode_solves`` (reference src/acb_ode.c:185-240) for a batch, on the device.
+    ``series``: ``[batch][len]``.  Returns (residual ``[batch][len + degree]``, solved ``bool[batch]``) where solved
+    is the reference's acceptance test on the first ``deg`` residual coefficients."""
+    drv = driver or default_driver()
+    L = ode.L
+    length = series.n_slots // (2 * batch)
+    out_len = length + degree
+    deg = length - order if deg is None else deg
+    ode_m, ode_t = _ode_to_device(ode, order, degree, batch, shared_ode)
+    in_m, in_t = pack_entries(instance_major_to_entry_major(series, batch, length), length, 2 * batch)
+    o_m = np.zeros((out_len, L, 2 * batch), np.uint32)
+    o_t = np.zeros((out_len, 2 * batch, 4), np.int32)
+    solved = np.zeros(batch, np.int32)
+    _lib.check(drv.ode_apply(L, order, degree, batch, ode_m, ode_t, shared_ode, in_m, in_t, length, o_m, o_t, out_len,
+                             max(deg, 0), solved), "acb_ode_apply_batch")
+    return entry_major_to_instance_major(unpack_entries(L, o_m, o_t), batch, out_len), solved.astype(bool)
 
 
 def pow_mode_of(rho: Balls):

@@ -357,6 +357,31 @@ int cb200_trans_dev(int which, int L_, int64_t n, uint32_t* z_mant, cb_meta* z_m
     return table_for(L_)->trans(p, (cudaStream_t)stream);
 }
 
+size_t cb200_ode_apply_workspace_bytes(int L, int64_t len_in, int64_t batch) { return carve_bytes(L, len_in + 1, 2 * batch); }
+int cb200_ode_apply_dev(int L_, int order, int degree, int64_t batch, const uint32_t* ode_mant, const cb_meta* ode_meta,
+                        int shared_ode, const uint32_t* in_mant, const cb_meta* in_meta, int64_t len_in, uint32_t* out_mant,
+                        cb_meta* out_meta, int64_t out_len, int64_t deg, int32_t* solved, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+    if (!supported_L(L_) || order < 0 || degree < 0 || batch < 0 || len_in < 0 || out_len < 0 || deg < 0) return CB200_EINVAL;
+    if (workspace_bytes < cb200_ode_apply_workspace_bytes(L_, len_in, batch)) return CB200_ENOMEM;
+    ApplyParams p;
+    p.order = order;
+    p.degree = degree;
+    p.batch = batch;
+    p.len_in = len_in;
+    p.out_len = out_len;
+    p.deg = deg;
+    p.ode = CArr{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta),
+                 shared_ode ? (size_t)2 : (size_t)(2 * batch)};
+    p.in = CArr{const_cast<uint32_t*>(in_mant), (Meta*)const_cast<cb_meta*>(in_meta), (size_t)(2 * batch)};
+    p.out = CArr{out_mant, (Meta*)out_meta, (size_t)(2 * batch)};
+    char* w = (char*)workspace;
+    p.wp = carve(w, L_, len_in + 1, 2 * batch);
+    p.solved = solved;
+    g_launches.fetch_add(batch > 0);
+    return table_for(L_)->apply(p, (cudaStream_t)stream);
+}
+
 int cb200_horner_batch_dev(int L_, int64_t len, int64_t npts, int nder, const uint32_t* f_mant,
                            const cb_meta* f_meta, int shared_f, const uint32_t* pts_mant,
                            const cb_meta* pts_meta, uint32_t* out_mant, cb_meta* out_meta,
@@ -730,6 +755,36 @@ int cb200_trans_host(int which, int L, int64_t n, uint32_t* z_mant, cb_meta* z_m
     if (rc) return rc;
     CK(cudaMemcpy(z_mant, zm.p, arr_mant_bytes(L, 1, S), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(z_meta, zt.p, arr_meta_bytes(1, S), cudaMemcpyDeviceToHost));
+    return (int)cudaDeviceSynchronize();
+}
+
+int cb200_ode_apply_host(int L, int order, int degree, int64_t batch, const uint32_t* ode_mant, const cb_meta* ode_meta,
+                         int shared_ode, const uint32_t* in_mant, const cb_meta* in_meta, int64_t len_in, uint32_t* out_mant,
+                         cb_meta* out_meta, int64_t out_len, int64_t deg, int32_t* solved, int device) {
+    if (!supported_L(L) || order < 0 || degree < 0 || batch < 0 || len_in < 0 || out_len < 0) return CB200_EINVAL;
+    CK(cudaSetDevice(device));
+    int64_t So = shared_ode ? 2 : 2 * batch, S = 2 * batch, ne = (int64_t)(order + 1) * (degree + 1);
+    DevBuf om, ot, im, it, rm, rt, sv, ws;
+    size_t wsb = cb200_ode_apply_workspace_bytes(L, len_in, batch);
+    CK(om.alloc(arr_mant_bytes(L, ne, So)));
+    CK(ot.alloc(arr_meta_bytes(ne, So)));
+    CK(im.alloc(arr_mant_bytes(L, len_in, S)));
+    CK(it.alloc(arr_meta_bytes(len_in, S)));
+    CK(rm.alloc(arr_mant_bytes(L, out_len, S)));
+    CK(rt.alloc(arr_meta_bytes(out_len, S)));
+    CK(sv.alloc(sizeof(int32_t) * batch));
+    CK(ws.alloc(wsb));
+    CK(cudaMemcpy(om.p, ode_mant, arr_mant_bytes(L, ne, So), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ot.p, ode_meta, arr_meta_bytes(ne, So), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(im.p, in_mant, arr_mant_bytes(L, len_in, S), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(it.p, in_meta, arr_meta_bytes(len_in, S), cudaMemcpyHostToDevice));
+    int rc = cb200_ode_apply_dev(L, order, degree, batch, (uint32_t*)om.p, (cb_meta*)ot.p, shared_ode, (uint32_t*)im.p,
+                                 (cb_meta*)it.p, len_in, (uint32_t*)rm.p, (cb_meta*)rt.p, out_len, deg,
+                                 solved ? (int32_t*)sv.p : nullptr, ws.p, wsb, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(out_mant, rm.p, arr_mant_bytes(L, out_len, S), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out_meta, rt.p, arr_meta_bytes(out_len, S), cudaMemcpyDeviceToHost));
+    if (solved) CK(cudaMemcpy(solved, sv.p, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost));
     return (int)cudaDeviceSynchronize();
 }
 

@@ -77,6 +77,11 @@ __global__ void __launch_bounds__(Cfg<L>::TPB, 1) evaluate_kernel(EvalParams p) 
     evaluate_thread<L>(p, idx, S0, S1);
 }
 template <int L>
+__global__ void __launch_bounds__(Cfg<L>::TPB, 1) apply_kernel(ApplyParams p) {
+    CB_KERNEL_PROLOGUE(p.batch)
+    apply_thread<L>(p, idx, S0, S1);
+}
+template <int L>
 __global__ void __launch_bounds__(Cfg<L>::TPB, 1) trans_kernel(TransParams p) {
     CB_KERNEL_PROLOGUE(p.n)
     trans_thread<L>(p, idx, S0, S1);
@@ -165,6 +170,7 @@ struct LaunchTable {
     int (*indicial_poly)(const IndicialParams&, cudaStream_t);
     int (*evaluate)(const EvalParams&, cudaStream_t);
     int (*trans)(const TransParams&, cudaStream_t);
+    int (*apply)(const ApplyParams&, cudaStream_t);
 };
 
 #define CB_DEFINE_LAUNCH_TABLE(LL)                                                                         \
@@ -194,8 +200,9 @@ struct LaunchTable {
     static int indp_##LL(const IndicialParams& p, cudaStream_t s) { return launch<LL>(indicial_poly_kernel<LL>, p, p.batch, s); } \
     static int eval_##LL(const EvalParams& p, cudaStream_t s) { return launch<LL>(evaluate_kernel<LL>, p, p.npts, s); } \
     static int trans_##LL(const TransParams& p, cudaStream_t s) { return launch<LL>(trans_kernel<LL>, p, p.n, s); } \
+    static int apply_##LL(const ApplyParams& p, cudaStream_t s) { return launch<LL>(apply_kernel<LL>, p, p.batch, s); } \
     extern const LaunchTable launch_table_L##LL = {fuchs_##LL, frob_##LL, horner_##LL, ew_##LL, ftab_##LL, fsh_##LL, fint_##LL, \
-                                                   frobg_##LL, solop_##LL, indp_##LL, eval_##LL, trans_##LL}; \
+                                                   frobg_##LL, solop_##LL, indp_##LL, eval_##LL, trans_##LL, apply_##LL}; \
     }
 
 extern const LaunchTable launch_table_L4, launch_table_L32, launch_table_L64, launch_table_L128;

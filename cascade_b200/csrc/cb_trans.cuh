@@ -320,4 +320,59 @@ CB_HD void trans_thread(const TransParams& p, int64_t i, SCR S0, SCR S1) {
     else acb_log<L>(z, x, T, S0, S1);
 }
 
+// ---------------------------------------------------------------- residual check on the device
+// acb_ode_apply / acb_ode_solves (reference src/acb_ode.c:185-240), the reference's own acceptance test
+// for both solvers, for a batch: out = sum_i p_i * in^(i) truncated to out_len coefficients, and
+// solved[instance] = every one of the first `deg` residual coefficients is finite and contains zero.
+// Same operation order as the oracle's cbo_ode_apply (classical products, row by row).
+struct ApplyParams {
+    int order, degree;
+    int64_t batch, len_in, out_len, deg;
+    CArr ode;  // S = 2*batch or 2
+    CArr in;   // len_in entries, S = 2*batch
+    CArr out;  // out_len entries, S = 2*batch
+    CArr wp;   // len_in + 1 entries, S = 2*batch: the running derivative and one product
+    int32_t* solved;  // [batch] or nullptr
+};
+template <int L, class SCR>
+CB_HD void apply_thread(const ApplyParams& p, int64_t inst, SCR S0, SCR S1) {
+    const size_t slot = 2 * (size_t)inst;
+    const size_t oslot = (p.ode.S == 2) ? 0 : slot;
+    const int D1 = p.degree + 1;
+    CRef t = at<L>(p.wp, p.len_in, slot);
+#pragma unroll 1
+    for (int64_t k = 0; k < p.len_in; k++) acb_set<L>(at<L>(p.wp, k, slot), at<L>(p.in, k, slot));
+#pragma unroll 1
+    for (int64_t k = 0; k < p.out_len; k++) acb_zero<L>(at<L>(p.out, k, slot));
+    int64_t dl = p.len_in;
+#pragma unroll 1
+    for (int i = 0; i <= p.order; i++) {
+#pragma unroll 1
+        for (int j = 0; j <= p.degree; j++) {
+            CRef c = at<L>(p.ode, i * D1 + j, oslot);
+            if (acb_is_exact_zero(c)) continue;
+#pragma unroll 1
+            for (int64_t k = 0; k < dl && j + k < p.out_len; k++) {
+                acb_mul<L>(t, c, at<L>(p.wp, k, slot), S0, S1);
+                CRef o = at<L>(p.out, j + k, slot);
+                acb_addsub<L>(o, o, t, false, S0, S1);
+            }
+        }
+#pragma unroll 1
+        for (int64_t k = 1; k < dl; k++) acb_mul_si<L>(at<L>(p.wp, k - 1, slot), at<L>(p.wp, k, slot), k, S0);
+        if (dl > 0) dl--;
+    }
+    if (p.solved) {
+        int ok = 1;
+        for (int64_t k = 0; k < p.deg && k < p.out_len; k++) {
+            CRef o = at<L>(p.out, k, slot);
+            if (acb_bound_exp(o) == TR_BIG || !acb_contains_zero<L>(o)) {
+                ok = 0;
+                break;
+            }
+        }
+        p.solved[inst] = ok;
+    }
+}
+
 }  // namespace cb

@@ -326,6 +326,30 @@ void acb_ode_dump(acb_ode_t ODE, char* file) {
     }
     if (out != stdout) fclose(out);
 }
+// reference src/acb_ode.c:137-157: divide every polynomial by the largest common power of z.  The reference
+// scans only the rows below the leading one (i < order) and repacks the rows at the new stride in place.
+slong acb_ode_reduce(acb_ode_t ODE) {
+    slong reduced = 0;
+    int all_zero = 1;
+    do {
+        for (slong i = 0; i < ODE->order; i++) {
+            if (reduced > ODE->degree) { all_zero = 0; break; }
+            all_zero &= acb_is_zero(acb_ode_coeff(ODE, i, reduced));
+        }
+        reduced++;
+    } while (all_zero && reduced <= ODE->degree + 1);
+    reduced -= 1;
+    if (reduced <= 0) return 0;
+    slong new_deg = ODE->degree - reduced;
+    if (new_deg < 0) return 0;
+    for (slong i = 0; i <= ODE->order; i++)
+        for (slong j = 0; j <= new_deg; j++)
+            acb_set(ODE->polys + i * (new_deg + 1) + j, ODE->polys + i * (ODE->degree + 1) + j + reduced);
+    ODE->degree = new_deg;
+    ODE->valuation = UNDEFINED_VAL;
+    return reduced;
+}
+
 slong acb_ode_valuation(acb_ode_t ODE) {
     if (ODE->valuation != UNDEFINED_VAL) return ODE->valuation;
     slong val = ODE->degree;

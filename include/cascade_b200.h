@@ -199,6 +199,21 @@ int cb200_trans_dev(int which, int L, int64_t n, uint32_t *z_mant, cb_meta *z_me
 int cb200_trans_host(int which, int L, int64_t n, uint32_t *z_mant, cb_meta *z_meta, const uint32_t *x_mant,
                      const cb_meta *x_meta, int device);
 
+/* ---- acb_ode_apply / acb_ode_solves (reference src/acb_ode.c:185-240) for a batch: the reference's own
+ * acceptance test of both solvers, on the device, so a sweep can verify itself without copying series back.
+ * in  : len_in entries, S = 2*batch (the series).  out: out_len entries, S = 2*batch: the first out_len
+ *       coefficients of sum_i p_i * in^(i).  solved (may be NULL): int32[batch], 1 where each of the first `deg`
+ *       coefficients of out is finite and contains zero (acb_ode_solves(ODE, res, deg)). */
+size_t cb200_ode_apply_workspace_bytes(int L, int64_t len_in, int64_t batch);
+int cb200_ode_apply_dev(int L, int order, int degree, int64_t batch, const uint32_t *ode_mant, const cb_meta *ode_meta,
+                        int shared_ode, const uint32_t *in_mant, const cb_meta *in_meta, int64_t len_in,
+                        uint32_t *out_mant, cb_meta *out_meta, int64_t out_len, int64_t deg, int32_t *solved,
+                        void *workspace, size_t workspace_bytes, void *stream);
+int cb200_ode_apply_host(int L, int order, int degree, int64_t batch, const uint32_t *ode_mant, const cb_meta *ode_meta,
+                         int shared_ode, const uint32_t *in_mant, const cb_meta *in_meta, int64_t len_in,
+                         uint32_t *out_mant, cb_meta *out_meta, int64_t out_len, int64_t deg, int32_t *solved,
+                         int device);
+
 /* ---- Horner evaluation batched over points (acb_poly_evaluate inside
  * acb_ode_solution_evaluate, reference src/acb_ode_solution.c:40,45; and the first `nder`
  * coefficients of acb_poly_taylor_shift, reference src/fuchs_solver.c:159).

@@ -135,6 +135,7 @@ void acb_ode_set(acb_ode_t ODE_out, acb_ode_t ODE_in);             /* src/acb_od
 void acb_ode_dump(acb_ode_t ODE, char *file);                      /* src/acb_ode.c:99-120 */
 void acb_ode_shift(acb_ode_t ODE_out, acb_ode_t ODE_in, acb_srcptr a, slong bits); /* :124-135 */
 slong acb_ode_valuation(acb_ode_t ODE);                            /* src/acb_ode.c:159-181 */
+slong acb_ode_reduce(acb_ode_t ODE);                               /* src/acb_ode.c:137-157 */
 
 /* =============================== Solutions (reference src/acb_ode.h:45-61) ==================== */
 typedef struct {

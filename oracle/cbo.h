@@ -137,6 +137,8 @@ int cbo_ode_shift_flat(int L, int order, int degree, const uint32_t *in_m, const
                        const uint32_t *a_m, const int32_t *a_t, uint32_t *out_m, int32_t *out_t);
 int cbo_ode_solves_flat(int L, int order, int degree, const uint32_t *ode_m, const int32_t *ode_t,
                         const uint32_t *res_m, const int32_t *res_t, int64_t len, int64_t deg);
+int cbo_ode_apply_flat(int L, int order, int degree, const uint32_t *ode_m, const int32_t *ode_t,
+                       const uint32_t *res_m, const int32_t *res_t, int64_t len, uint32_t *out_m, int32_t *out_t);
 int cbo_example_flat(int which, int L, uint64_t n, const uint32_t *par_m, const int32_t *par_t,
                      uint32_t *out_m, int32_t *out_t);
 int cbo_continuation_flat(int L, int order, int degree, int64_t n, int64_t batch, int64_t path_len,

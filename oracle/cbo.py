@@ -51,6 +51,7 @@ def lib(plain: bool = False) -> C.CDLL:
     L.cbo_continuation_flat.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, _u32p, _i32p,
                                         _u32p, _i32p, _u32p, _i32p]
     L.cbo_example_flat.argtypes = [C.c_int, C.c_int, C.c_uint64, _u32p, _i32p, _u32p, _i32p]
+    L.cbo_ode_apply_flat.argtypes = [C.c_int, C.c_int, C.c_int, _u32p, _i32p, _u32p, _i32p, C.c_int64, _u32p, _i32p]
     L.cbo_ew_trans.argtypes = [C.c_int, C.c_int, C.c_int64, _u32p, _i32p, _u32p, _i32p]
     L.cbo_solution_evaluate_flat.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int64, _u32p, _i32p, _u32p, _i32p, C.c_int,
                                              C.c_uint64, _u32p, _i32p, _u32p, _i32p]
@@ -231,5 +232,14 @@ def solution_evaluate(gens: Balls, M: int, rho: Balls, pow_mode: int, pow_e: int
     out = Balls.zeros(2 * npts, gens.L)
     rc = lib(plain).cbo_solution_evaluate_flat(gens.L, M, cap, npts, gens.mant, gens.meta, rho.mant, rho.meta, pow_mode,
                                                pow_e, pts.mant, pts.meta, out.mant, out.meta)
+    assert rc == 0
+    return out
+
+
+def ode_apply(order: int, degree: int, ode: Balls, res: Balls, plain: bool = False) -> Balls:
+    """acb_ode_apply (reference src/acb_ode.c:185-206): the residual series, len(res) + degree coefficients."""
+    length = res.n_slots // 2
+    out = Balls.zeros(2 * (length + degree), ode.L)
+    rc = lib(plain).cbo_ode_apply_flat(ode.L, order, degree, ode.mant, ode.meta, res.mant, res.meta, length, out.mant, out.meta)
     assert rc == 0
     return out

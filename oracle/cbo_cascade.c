@@ -406,6 +406,22 @@ int cbo_ode_solves_flat(int L, int order, int degree, const uint32_t *ode_m, con
     return ok;
 }
 
+/* residual of one series: out[0 .. len + degree) */
+int cbo_ode_apply_flat(int L, int order, int degree, const uint32_t *ode_m, const int32_t *ode_t,
+                       const uint32_t *res_m, const int32_t *res_t, int64_t len, uint32_t *out_m, int32_t *out_t) {
+    cbo_ode *o = load_ode(L, order, degree, ode_m, ode_t, 0);
+    int64_t out_len = len + degree;
+    cbo_acb *res = (cbo_acb *)malloc(sizeof(cbo_acb) * (len > 0 ? len : 1));
+    cbo_acb *out = (cbo_acb *)malloc(sizeof(cbo_acb) * (out_len > 0 ? out_len : 1));
+    for (int64_t k = 0; k < len; k++) load_acb(res + k, res_m, res_t, k, L);
+    cbo_ode_apply(out, out_len, o, res, len, L);
+    for (int64_t k = 0; k < out_len; k++) store_acb(out_m, out_t, k, out + k, L);
+    free(res);
+    free(out);
+    cbo_ode_free(o);
+    return 0;
+}
+
 /* analytic_continuation (reference src/fuchs_solver.c:147-163) for `batch` solutions of one operator
  * along one path.  y: [batch][order] Taylor coefficients at path[0] in, at the last corner out.
  * Per corner: acb_ode_shift, acb_ode_solve_fuchs (n terms), then the first `order` coefficients of

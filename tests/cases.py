@@ -551,3 +551,24 @@ def case_solution_evaluate(oracle, drv, L: int, seed: int, npts: int = 7, cap: i
             got = api.acb_ode_solution_evaluate_batch(gens, M, rho, pts, driver=drv)
             assert_same(want, got, f"solution_evaluate L={L} M={M} mode={mode}")
             assert int(got.meta[2, 1]) & FLAG_NAN
+
+
+def case_ode_apply(oracle, drv, L: int, seed: int, batch: int = 3):
+    """acb_ode_apply / acb_ode_solves on the device (reference src/acb_ode.c:185-240): the residual of computed
+    Fuchs series is bit-identical to the oracle's and passes the acceptance test; a perturbed series fails it."""
+    rng = np.random.default_rng(seed)
+    degree, order = 4, 2
+    ne = (order + 1) * (degree + 1)
+    ode = random_balls(rng, batch * ne * 2, L, -4, 4, "ulp", short_frac=0.2)
+    n = order + 14
+    init = random_balls(rng, batch * order * 2, L, -3, 3, "ulp")
+    rs = api.acb_ode_solve_fuchs_batch(ode, init, order, degree, n, batch, False, driver=drv)
+    out, solved = api.acb_ode_apply_batch(ode, rs, order, degree, batch, False, deg=n - order, driver=drv)
+    for i in range(batch):
+        want = oracle.ode_apply(order, degree, ode[i * ne * 2:(i + 1) * ne * 2], rs[i * (n + 1) * 2:(i + 1) * (n + 1) * 2])
+        assert_same(want, out[i * (n + 1 + degree) * 2:(i + 1) * (n + 1 + degree) * 2], f"ode_apply L={L} instance {i}")
+    assert solved.all()
+    bad = rs.copy()
+    bad.mant[2 * (n + 1) + 10, L - 1] ^= np.uint32(1 << 20)  # instance 1, coefficient 5: off by 2^-11 relative
+    _, solved = api.acb_ode_apply_batch(ode, bad, order, degree, batch, False, deg=n - order, driver=drv)
+    assert list(solved) == [True, False] + [True] * (batch - 2)

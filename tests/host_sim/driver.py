@@ -45,6 +45,8 @@ def lib():
                                                                 _u32p, _i32p]
         L.cbsim_solution_evaluate.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int64, _u32p, _i32p, _u32p, _i32p, C.c_int,
                                               C.c_uint64, _u32p, _i32p, _u32p, _i32p]
+        L.cbsim_ode_apply.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, _u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int64,
+                                      _u32p, _i32p, C.c_int64, C.c_int64, _i32p]
         L.cbsim_trans.argtypes = [C.c_int, C.c_int, C.c_int64, _u32p, _i32p, _u32p, _i32p]
         _lib = L
     return _lib
@@ -84,6 +86,10 @@ class SimDriver:
 
     def trans(self, which, L, n, z_m, z_t, x_m, x_t):
         return lib().cbsim_trans(which, L, n, z_m, z_t, x_m, x_t)
+
+    def ode_apply(self, L, order, degree, batch, ode_m, ode_t, shared, in_m, in_t, len_in, o_m, o_t, out_len, deg, solved):
+        return lib().cbsim_ode_apply(L, order, degree, batch, ode_m, ode_t, int(shared), in_m, in_t, len_in, o_m, o_t,
+                                     out_len, deg, solved)
 
     def horner(self, L, length, npts, nder, f_m, f_t, shared_f, p_m, p_t, o_m, o_t):
         return lib().cbsim_horner_batch(L, length, npts, nder, f_m, f_t, int(shared_f), p_m, p_t, o_m, o_t)

@@ -206,6 +206,22 @@ int cbsim_trans(int which, int L_, int64_t n, uint32_t* z_mant, cb_meta* z_meta,
     return 0;
 }
 
+int cbsim_ode_apply(int L_, int order, int degree, int64_t batch, const uint32_t* ode_mant, const cb_meta* ode_meta,
+                    int shared_ode, const uint32_t* in_mant, const cb_meta* in_meta, int64_t len_in, uint32_t* out_mant,
+                    cb_meta* out_meta, int64_t out_len, int64_t deg, int32_t* solved) {
+    ApplyParams p;
+    p.order = order; p.degree = degree; p.batch = batch; p.len_in = len_in; p.out_len = out_len; p.deg = deg;
+    p.ode = CArr{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta),
+                 shared_ode ? (size_t)2 : (size_t)(2 * batch)};
+    p.in = CArr{const_cast<uint32_t*>(in_mant), (Meta*)const_cast<cb_meta*>(in_meta), (size_t)(2 * batch)};
+    p.out = CArr{out_mant, (Meta*)out_meta, (size_t)(2 * batch)};
+    Tmp tmp;
+    p.wp = tmp.arr(L_, len_in + 1, 2 * batch);
+    p.solved = solved;
+    SIM_DISPATCH(L_, run<L>(batch, [&](int64_t i, Scratch<1> a, Scratch<1> b) { apply_thread<L>(p, i, a, b); }));
+    return 0;
+}
+
 int cbsim_horner_batch(int L_, int64_t len, int64_t npts, int nder, const uint32_t* f_mant,
                        const cb_meta* f_meta, int shared_f, const uint32_t* pts_mant,
                        const cb_meta* pts_meta, uint32_t* out_mant, cb_meta* out_meta) {

@@ -109,3 +109,8 @@ def test_exp_log(oracle, sim_driver, L):
 @pytest.mark.parametrize("L", [4, 32])
 def test_solution_evaluate(oracle, sim_driver, L):
     cases.case_solution_evaluate(oracle, sim_driver, L, seed=67 + L, npts=4, cap=8 if L == 32 else 12)
+
+
+@pytest.mark.parametrize("L", [4, 32])
+def test_ode_apply(oracle, sim_driver, L):
+    cases.case_ode_apply(oracle, sim_driver, L, seed=71 + L)

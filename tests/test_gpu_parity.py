@@ -110,3 +110,8 @@ def test_exp_log(oracle, gpu_driver, L):
 @pytest.mark.parametrize("L", [4, 32, 64])
 def test_solution_evaluate(oracle, gpu_driver, L):
     cases.case_solution_evaluate(oracle, gpu_driver, L, seed=67 + L, npts=40, cap=16)
+
+
+@pytest.mark.parametrize("L", [4, 32, 64])
+def test_ode_apply(oracle, gpu_driver, L):
+    cases.case_ode_apply(oracle, gpu_driver, L, seed=71 + L, batch=40)

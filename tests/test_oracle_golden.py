@@ -194,3 +194,31 @@ def test_gmp_and_plain_backends_agree_general_frobenius(oracle):
     a = oracle.frobenius_general_batch(2, 4, 9, ode, rho, 1, True, True, 2, 3)
     b = oracle.frobenius_general_batch(2, 4, 9, ode, rho, 1, True, True, 2, 3, plain=True)
     assert a.same_as(b)
+
+
+@pytest.mark.parametrize("L", [4, 32])
+def test_exp_log_enclose_mpmath(oracle, L):
+    """The oracle's acb_exp / acb_log (oracle/cbo_trans.c) are rigorous enclosures: the true value computed by
+    mpmath at a much higher precision lies inside every ball, and the balls stay within ~2^-(prec-40) relative."""
+    import mpmath as mp
+    from tests.cases import trans_inputs
+    mp.mp.prec = 32 * L + 300
+    rng = np.random.default_rng(9)
+    n = 30
+    x = trans_inputs(rng, L, n)
+    x.meta[:, 2] = 0  # exact inputs, so that mpmath sees the same numbers
+    x.meta[:, 3] = 0
+    to_mp = lambda q: mp.mpf(q.numerator) / q.denominator
+    for name, fn in (("exp", mp.exp), ("log", mp.log)):
+        z = oracle.ew_trans(name, x)
+        for i in range(n):
+            if (int(z.meta[2 * i, 1]) | int(z.meta[2 * i + 1, 1])) & FLAG_NAN:
+                assert name == "log" and x.mid(2 * i) == 0 and x.mid(2 * i + 1) == 0 or name == "exp"
+                continue
+            tv = fn(mp.mpc(to_mp(x.mid(2 * i)), to_mp(x.mid(2 * i + 1))))
+            for part, t in ((0, tv.real), (1, tv.imag)):
+                s = 2 * i + part
+                assert abs(to_mp(z.mid(s)) - t) <= to_mp(z.rad(s)), (name, i, part)
+            mag = abs(tv)
+            if mag != 0:
+                assert to_mp(z.rad(2 * i)) <= mag * mp.mpf(2) ** (-(32 * L - 40)), (name, i)
