@@ -52,7 +52,13 @@ def timed(fn, reps=2):
     return best
 
 
-out = []
+class _Out(list):
+    def append(self, o):
+        print(json.dumps(o), flush=True)
+        super().append(o)
+
+
+out = _Out()
 def config3():
     # ---- config 3: Frobenius, hypergeometric sweep, 4096 bits, per-instance (a, b, c)
     L, n = 128, 256
@@ -83,7 +89,8 @@ def config3():
 def config4():
     # ---- config 4: Legendre sweep, per-instance integer operators, real data (integer-operator kernel)
     L, n = 32, 1000
-    batch = max(1024, int(2**20 * args.scale))
+    # the full 2^20 x 1000 sweep is 302 GB of complex results: more than one B200 holds; cap at 2^17 instances per launch
+    batch = max(1024, min(2**17, int(2**20 * args.scale)))
     ns = np.arange(batch, dtype=np.int64)
     ode_int = np.zeros((9, batch), np.int64)
     ode_int[0] = ns * (ns + 1)
@@ -121,8 +128,54 @@ def config5():
     out.append({"config": 5, "what": f"Horner evaluation of a {length}-term series at {npts} points, 2048 bits", "ms": ms,
                 "horner_steps_per_s": steps / ms * 1e3, "T_limb_MAC_per_s_4L2": steps * 4 * L * L / ms * 1e3 / 1e12})
 
+def config3_log():
+    # ---- config 3, logarithmic variant: acb_ode_solve_frobenius with M = 2 (polynomial-in-rho recurrence), 1024 bits
+    L, n, M = 32, 48, 2
+    batch = max(256, int(16384 * args.scale))
+    rng = np.random.default_rng(33)
+    small = 64
+    par = [random_balls(rng, small * 2, L, -1, 1, "zero") for _ in range(3)]
+    odes = api.acb_ode_hypgeom_batch(*par)
+    om, ot = pack_entries(instance_major_to_entry_major(odes, small, 9), 9, 2 * small)
+    reps = batch // small
+    d_om = torch.from_numpy(np.tile(om.view(np.int32), (1, 1, reps))).to(dev)
+    d_ot = torch.from_numpy(np.tile(ot, (1, reps, 1))).to(dev)
+    d_rm, d_rt = rand_dev(1, L, 2 * batch, 34)  # generic complex rho per instance
+    d_gm = torch.empty((M * (n + 1), L, 2 * batch), dtype=torch.int32, device=dev)
+    d_gt = torch.empty((M * (n + 1), 2 * batch, 4), dtype=torch.int32, device=dev)
+    wsb = lib.cb200_frobenius_general_workspace_bytes(L, 2, 2, M, n, batch)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: lib.cb200_frobenius_general_batch_dev(L, 2, 2, -1, n, batch, p(d_om), p(d_ot), 0, p(d_rm), p(d_rt), 0,
+                                                             M, M, p(d_gm), p(d_gt), p(ws), wsb, None), reps=1)
+    out.append({"config": "3-log", "what": f"hypgeom Frobenius M=2 (polynomials in rho), 1024 bits, {batch} triples, {n} terms",
+                "ms": ms, "ball_coeffs_per_s": batch * n * M / ms * 1e3, "workspace_GB": wsb / 1e9})
+    del d_gm, d_gt, ws
+    torch.cuda.empty_cache()
+
+
+def config5_eval():
+    # ---- config 5, full acb_ode_solution_evaluate (Horner of M = 2 series + acb_log + acb_pow), 1024 bits
+    L, cap, M = 32, 256, 2
+    npts = max(1024, int(131072 * args.scale))
+    g_m, g_t = rand_dev(M * cap, L, 2, 7)
+    r_m, r_t = rand_dev(1, L, 2, 8)
+    pts_m, pts_t = rand_dev(1, L, 2 * npts, 9)
+    pts_t[:, :, 0] = -2
+    o_m = torch.empty((1, L, 2 * npts), dtype=torch.int32, device=dev)
+    o_t = torch.empty((1, 2 * npts, 4), dtype=torch.int32, device=dev)
+    wsb = lib.cb200_evaluate_workspace_bytes(L, npts)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: lib.cb200_solution_evaluate_dev(L, M, cap, npts, p(g_m), p(g_t), p(r_m), p(r_t), 2, 0, p(pts_m), p(pts_t),
+                                                       p(o_m), p(o_t), p(ws), wsb, None), reps=1)
+    out.append({"config": "5-eval", "what": f"acb_ode_solution_evaluate, M=2, {cap}-term series, generic rho (log + pow), {npts} points, 1024 bits",
+                "ms": ms, "points_per_s": npts / ms * 1e3})
+
+
 if args.only in (0, 3):
     config3()
+    config3_log()
+if args.only in (0, 5):
+    config5_eval()
 if args.only in (0, 4):
     config4()
 if args.only in (0, 5):
@@ -149,5 +202,4 @@ if args.continuation:
     ms = timed(lambda: lib.cb200_continuation_dev(L, 2, 2, n, 2, steps + 1, p(d_om), p(d_ot), p(d_pm), p(d_pt), None, p(d_ym), p(d_yt), p(ws), wsb, None), reps=1)
     out.append({"config": 5, "what": f"analytic continuation, {steps}-step path, {n} terms per step, 2048 bits, 2 solutions (sequential: latency bound)",
                 "ms": ms, "ball_coeffs_per_s": 2 * steps * (n - 1) / ms * 1e3, "ms_per_step": ms / steps})
-for o in out:
-    print(json.dumps(o))
+
