@@ -11,7 +11,8 @@ by the batch.  A "step" is one full solve of the batch.  Metric: ball-coefficien
 
   value : device-resident (inputs already in HBM, CUDA events around the kernels)
   e2e   : through the host-buffer path -- pinned host inputs copied H2D and the full result
-          series copied D2H inside the timed region, tile by tile
+          series copied D2H inside the timed region, one coefficient range after the other while
+          the next range is being computed
   roofline : integer pipe.  achieved = 24 L^2 limb multiply-adds per coefficient
           x coefficients / kernel time; peak = measured plain IMAD.WIDE rate
           (profiles/imad_peak_r01.json).  The HBM view (bytes written / time vs the measured copy
@@ -246,47 +247,49 @@ def main():
     # ---- end to end: host buffers in, host buffers out, tile by tile, copies inside the timing
     e2e = None
     if not args.no_e2e:
-        # pinned ring of two result tiles per rank; keep all ranks of the box within a quarter of
-        # the free host memory (a real caller would own a full-size result buffer)
-        per_inst = (n + 1) * 2 * (L * 4 + 16)
+        # The solve runs over the whole batch in coefficient RANGES (cb200_fuchs_batch_range_dev: the recurrence
+        # resumes from the rows already in HBM); the finished rows of a range -- contiguous in the
+        # [coefficient][limb][slot] layout -- go to pinned host memory on a second stream while the next range is
+        # being computed.  Pinned ring of two range buffers per rank, kept within a quarter of the free host memory
+        # across the ranks of the box (a real caller would own a full-size result buffer).
+        row_bytes = S * (L * 4 + 16)
         try:
             import psutil
             avail = psutil.virtual_memory().available
         except Exception:
             avail = 64 << 30
-        tile = min(batch, 16384)
-        while tile > 1024 and 2 * tile * per_inst * world > avail // 4:
-            tile //= 2
-        ntiles = (batch + tile - 1) // tile
-        St = 2 * tile
+        rows = 250
+        while rows > 10 and 2 * rows * row_bytes * world > avail // 4:
+            rows //= 2
+        bounds = list(range(0, n + 1, rows)) + [n + 1]
+        nchunks = len(bounds) - 1
         h_init_m = torch.from_numpy(init_m.view(np.int32)).pin_memory()
         h_init_t = torch.from_numpy(init_t).pin_memory()
-        h_res_m = torch.empty((2, n + 1, L, St), dtype=torch.int32).pin_memory()
-        h_res_t = torch.empty((2, n + 1, St, 4), dtype=torch.int32).pin_memory()
-        t_res_m = [torch.empty((n + 1, L, St), dtype=torch.int32, device=dev) for _ in range(2)]
-        t_res_t = [torch.empty((n + 1, St, 4), dtype=torch.int32, device=dev) for _ in range(2)]
-        t_ws_bytes = lib.cb200_fuchs_workspace_bytes(L, 2, 2, -2, n, tile, 1)
-        t_ws = [torch.empty(t_ws_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
-        streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
-        h2d = 2 * L * St * 4 + 2 * St * 16
-        d2h = (n + 1) * L * St * 4 + (n + 1) * St * 16
+        h_res_m = torch.empty((2, rows, L, S), dtype=torch.int32).pin_memory()
+        h_res_t = torch.empty((2, rows, S, 4), dtype=torch.int32).pin_memory()
+        s_comp, s_copy = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        ev = [torch.cuda.Event() for _ in range(nchunks)]
+        h2d = 2 * L * S * 4 + 2 * S * 16
+        d2h = (n + 1) * row_bytes
 
         def e2e_step():
-            for ti in range(ntiles):
-                s = streams[ti % 2]
-                buf = ti % 2
-                lo = 2 * ti * tile
-                with torch.cuda.stream(s):
-                    t_res_m[buf][:2].copy_(h_init_m[:, :, lo:lo + St], non_blocking=True)
-                    t_res_t[buf][:2].copy_(h_init_t[:, lo:lo + St], non_blocking=True)
-                    rc = lib.cb200_fuchs_batch_dev(L, ORDER, DEGREE, -2, n, tile, p(d_ode_m), p(d_ode_t), 1,
-                                                   p(t_res_m[buf]), p(t_res_t[buf]), p(t_ws[buf]), t_ws_bytes,
-                                                   C.c_void_p(s.cuda_stream))
+            with torch.cuda.stream(s_comp):
+                d_res_m[:2].copy_(h_init_m, non_blocking=True)
+                d_res_t[:2].copy_(h_init_t, non_blocking=True)
+            for c in range(nchunks):
+                lo, hi = bounds[c], bounds[c + 1]
+                with torch.cuda.stream(s_comp):
+                    rc = lib.cb200_fuchs_batch_range_dev(L, ORDER, DEGREE, -2, lo, hi - 1, batch, p(d_ode_m), p(d_ode_t), 1,
+                                                         p(d_res_m), p(d_res_t), p(d_ws), ws_bytes,
+                                                         C.c_void_p(s_comp.cuda_stream))
                     assert rc == 0
-                    h_res_m[buf].copy_(t_res_m[buf], non_blocking=True)
-                    h_res_t[buf].copy_(t_res_t[buf], non_blocking=True)
-            for s in streams:
-                s.synchronize()
+                    ev[c].record(s_comp)
+                with torch.cuda.stream(s_copy):
+                    s_copy.wait_event(ev[c])
+                    h_res_m[c % 2, : hi - lo].copy_(d_res_m[lo:hi], non_blocking=True)
+                    h_res_t[c % 2, : hi - lo].copy_(d_res_t[lo:hi], non_blocking=True)
+            s_comp.synchronize()
+            s_copy.synchronize()
 
         e2e_step()
         barrier()
@@ -300,8 +303,9 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * coeffs_per_gpu / float(tt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(h2d * ntiles) * world, "d2h_bytes_per_step": int(d2h * ntiles) * world,
-               "how": f"{ntiles} tiles of {tile} instances, 2 streams, pinned host buffers, result series copied back"}
+               "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
+               "how": f"{nchunks} coefficient ranges of {rows} rows over the whole batch, compute and copy streams, "
+                      "pinned host buffers, the full result series copied back"}
 
     if rank != 0:
         if world > 1:

@@ -25,7 +25,7 @@ SYMBOLS = [
     "cb200_version", "cb200_device_count", "cb200_kernel_launches", "cb200_debug_rr_stats",
     "cb200_fuchs_workspace_bytes", "cb200_frobenius_workspace_bytes",
     "cb200_horner_workspace_bytes", "cb200_ew_workspace_bytes",
-    "cb200_fuchs_batch_dev", "cb200_fuchs_batch_host",
+    "cb200_fuchs_batch_dev", "cb200_fuchs_batch_host", "cb200_fuchs_batch_range_dev",
     "cb200_fuchs_intop_batch_dev", "cb200_fuchs_intop_batch_host",
     "cb200_continuation_workspace_bytes", "cb200_continuation_dev", "cb200_continuation_host",
     "cb200_frobenius1_batch_dev", "cb200_frobenius1_batch_host",
@@ -65,6 +65,7 @@ def lib() -> C.CDLL:
         getattr(L, name).restype = C.c_size_t
         getattr(L, name).argtypes = [C.c_int, C.c_int64]
     L.cb200_fuchs_batch_dev.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_vp, _vp, C.c_int, _vp, _vp, _vp, C.c_size_t, _vp]
+    L.cb200_fuchs_batch_range_dev.argtypes = [C.c_int] * 4 + [C.c_int64] * 3 + [_vp, _vp, C.c_int, _vp, _vp, _vp, C.c_size_t, _vp]
     L.cb200_fuchs_batch_host.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int]
     _i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
     L.cb200_fuchs_intop_batch_dev.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_vp, C.c_int, _vp, _vp, _vp]

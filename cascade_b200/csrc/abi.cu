@@ -106,8 +106,18 @@ int cb200_fuchs_batch_dev(int L_, int order, int degree, int valuation, int64_t 
                           const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
                           uint32_t* res_mant, cb_meta* res_meta, void* workspace,
                           size_t workspace_bytes, void* stream) {
-    if (!supported_L(L_) || order < 1 || degree < 0 || batch < 0 || n < 0) return CB200_EINVAL;
+    return cb200_fuchs_batch_range_dev(L_, order, degree, valuation, 0, n, batch, ode_mant, ode_meta, shared_ode, res_mant,
+                                       res_meta, workspace, workspace_bytes, stream);
+}
+
+int cb200_fuchs_batch_range_dev(int L_, int order, int degree, int valuation, int64_t n_begin, int64_t n, int64_t batch,
+                                const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode, uint32_t* res_mant,
+                                cb_meta* res_meta, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!supported_L(L_) || order < 1 || degree < 0 || batch < 0 || n < 0 || n_begin < 0) return CB200_EINVAL;
     if (valuation >= 0) return CB200_EVALUATION;
+    if (!shared_ode && n_begin > -valuation) return CB200_EINVAL;  // ranges: shared-operator path only
+    if (n_begin < -valuation) n_begin = -valuation;
+    if (n_begin > n) return 0;
     if (!factor_fits(n, order)) return CB200_ERANGE;
     if (workspace_bytes < cb200_fuchs_workspace_bytes(L_, order, degree, valuation, n, batch, shared_ode))
         return CB200_ENOMEM;
@@ -126,6 +136,7 @@ int cb200_fuchs_batch_dev(int L_, int order, int degree, int valuation, int64_t 
         tp.tbl = carve(w, L_, rows * (W + 2), 2);
         tp.tmp = carve(w, L_, 2, 2 * rows);
         tp.kind = (int32_t*)w;
+        tp.row0 = n_begin + valuation;
         w += align256(sizeof(int32_t) * (rows + 1));
         g_launches.fetch_add(1);
         int rc = table_for(L_)->fuchs_table(tp, (cudaStream_t)stream);
@@ -140,6 +151,7 @@ int cb200_fuchs_batch_dev(int L_, int order, int degree, int valuation, int64_t 
         sp.res = CArr{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
         sp.kind = tp.kind;
         sp.gcols = (uint32_t*)w;
+        sp.n_begin = n_begin;
         {
             // the reduced-radix fused dot product (cb_rr.cuh) is bit-identical but measured slower than
             // the carry-chain path inside this kernel: opt-in for experiments

@@ -2,6 +2,7 @@
 // Included by one translation unit per precision (kern_L*.cu) so the precisions compile in parallel.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include "cb_solvers.cuh"
 
 namespace cb {
@@ -17,12 +18,12 @@ template <> struct Cfg<128> { static constexpr int TPB = 112; };
 // threads per block of the shared-operator recurrence kernel (two product columns + three
 // accumulator columns per thread)
 template <int L> struct CfgShared;
-template <> struct CfgShared<4> { static constexpr int TPB = 128; static constexpr int TPB_BIG = 128; };
+template <> struct CfgShared<4> { static constexpr int TPB = 128; static constexpr int TPB_BIG = 128; static constexpr int TPB_HUGE = 128; };
 // 1024 bits: two block sizes, picked per launch to minimise the idle tail of the last wave
 // (7 warps at <= 255 registers, or 12 warps at 168 registers = 3 warps per scheduler)
-template <> struct CfgShared<32> { static constexpr int TPB = 224; static constexpr int TPB_BIG = 384; };
-template <> struct CfgShared<64> { static constexpr int TPB = 96; static constexpr int TPB_BIG = 96; };
-template <> struct CfgShared<128> { static constexpr int TPB = 32; static constexpr int TPB_BIG = 32; };
+template <> struct CfgShared<32> { static constexpr int TPB = 224; static constexpr int TPB_BIG = 384; static constexpr int TPB_HUGE = 448; };
+template <> struct CfgShared<64> { static constexpr int TPB = 96; static constexpr int TPB_BIG = 96; static constexpr int TPB_HUGE = 96; };
+template <> struct CfgShared<128> { static constexpr int TPB = 32; static constexpr int TPB_BIG = 32; static constexpr int TPB_HUGE = 32; };
 
 template <int L> struct Sizes {
     static constexpr int WORDS = 2 * L + 3;  // words per product scratch column
@@ -99,10 +100,10 @@ __global__ void __launch_bounds__(Cfg<L>::TPB, 1) ew_kernel(EwParams p) {
 
 template <int L>
 __global__ void __launch_bounds__(Cfg<L>::TPB, 1) fuchs_table_kernel(FuchsTableParams p) {
-    CB_KERNEL_PROLOGUE(p.n + 1 + p.valuation)
-    fuchs_table_thread<L>(p, idx, S0, S1);
+    CB_KERNEL_PROLOGUE(p.n + 1 + p.valuation - p.row0)
+    fuchs_table_thread<L>(p, idx + p.row0, S0, S1);
 }
-template <int L, int TPB>
+template <int L, int TPB, bool RR = false>
 __global__ void __launch_bounds__(TPB, 1) fuchs_shared_kernel(FuchsSharedParams p) {
     extern __shared__ uint32_t cb_smem[];
     constexpr uint32_t W0 = Sizes<L>::S0WORDS, W1 = Sizes<L>::S1WORDS, AW = Sizes<L>::AWORDS;
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(TPB, 1) fuchs_shared_kernel(FuchsSharedParams 
     if (idx >= p.batch) return;
     GScratch G0{p.gcols + idx, (size_t)p.batch};
     GScratch G1{p.gcols + (size_t)Sizes<L>::WORDS * p.batch + idx, (size_t)p.batch};
-    fuchs_shared_thread<L>(p, idx, S0, S1, A0, A1, A2, G0, G1);
+    fuchs_shared_thread<L, RR>(p, idx, S0, S1, A0, A1, A2, G0, G1);
 }
 
 // integer-operator kernel: 4 columns of ~L+3 words per thread, light on registers
@@ -133,16 +134,28 @@ __global__ void __launch_bounds__(IntopCfg<L>::TPB, 1) fuchs_intop_kernel(FuchsI
 }
 
 // time of a launch is proportional to (number of waves) x (instances per SM per wave) / throughput;
-// measured on B200: 12 warps/SM sustain ~1.13x the throughput of 7 warps/SM
+// relative per-SM throughputs measured on B200 (7, 12 and 14 warps per SM)
+// (measured, 65 536-instance runs of 98 coefficients: 224 threads 21.9 instances/ms/SM, 384 threads 23.6,
+// 448 threads -- 128 registers, 532 B of spills -- 21.4: the 14-warp variant buys nothing and is not chosen)
+constexpr double THR_BIG = 1.08, THR_HUGE = 0.98;
+// 0: TPB, 1: TPB_BIG, 2: TPB_HUGE.  CB200_TPB_CHOICE=0/1/2 in the environment overrides (development)
 template <int L>
-bool prefer_big_blocks(int64_t batch, int sms) {
-    if (CfgShared<L>::TPB_BIG == CfgShared<L>::TPB) return false;
+int choose_block_size(int64_t batch, int sms) {
+    const char* e = getenv("CB200_TPB_CHOICE");
+    if (e && e[0] >= '0' && e[0] <= '2') return e[0] - '0';
     auto cost = [&](int tpb, double thr) {
         int64_t blocks = (batch + tpb - 1) / tpb;
         int64_t waves = (blocks + sms - 1) / sms;
         return (double)waves * tpb / thr;
     };
-    return cost(CfgShared<L>::TPB_BIG, 1.13) < cost(CfgShared<L>::TPB, 1.0);
+    int best = 0;
+    double c = cost(CfgShared<L>::TPB, 1.0);
+    if (CfgShared<L>::TPB_BIG != CfgShared<L>::TPB && cost(CfgShared<L>::TPB_BIG, THR_BIG) < c) {
+        best = 1;
+        c = cost(CfgShared<L>::TPB_BIG, THR_BIG);
+    }
+    if (CfgShared<L>::TPB_HUGE != CfgShared<L>::TPB && cost(CfgShared<L>::TPB_HUGE, THR_HUGE) < c) best = 2;
+    return best;
 }
 
 template <int L, class P>
@@ -180,12 +193,19 @@ struct LaunchTable {
     static int horner_##LL(const HornerParams& p, cudaStream_t s) { return launch<LL>(horner_kernel<LL>, p, p.npts, s); } \
     static int ew_##LL(const EwParams& p, cudaStream_t s) { return launch<LL>(ew_kernel<LL>, p, p.n, s); }                \
     static int ftab_##LL(const FuchsTableParams& p, cudaStream_t s) {                                      \
-        return launch<LL>(fuchs_table_kernel<LL>, p, p.n + 1 + p.valuation, s);                            \
+        return launch<LL>(fuchs_table_kernel<LL>, p, p.n + 1 + p.valuation - p.row0, s);                            \
     }                                                                                                      \
     static int fsh_##LL(const FuchsSharedParams& p, cudaStream_t s) {                                      \
         int dev = 0, sms = 148;                                                                            \
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); \
-        if (prefer_big_blocks<LL>(p.batch, sms))                                                           \
+        if (use_rr<LL>() && !p.no_rr) /* opt-in experiment (CB200_RR=1): its own instantiation */          \
+            return launch<LL>(fuchs_shared_kernel<LL, CfgShared<LL>::TPB, true>, p, p.batch, s, CfgShared<LL>::TPB, \
+                              Sizes<LL>::SMEM_SHARED_PER_THREAD * CfgShared<LL>::TPB);                     \
+        int choice = choose_block_size<LL>(p.batch, sms);                                                  \
+        if (choice == 2)                                                                                   \
+            return launch<LL>(fuchs_shared_kernel<LL, CfgShared<LL>::TPB_HUGE>, p, p.batch, s, CfgShared<LL>::TPB_HUGE, \
+                              Sizes<LL>::SMEM_SHARED_PER_THREAD * CfgShared<LL>::TPB_HUGE);                \
+        if (choice == 1)                                                                                   \
             return launch<LL>(fuchs_shared_kernel<LL, CfgShared<LL>::TPB_BIG>, p, p.batch, s, CfgShared<LL>::TPB_BIG, \
                               Sizes<LL>::SMEM_SHARED_PER_THREAD * CfgShared<LL>::TPB_BIG);                 \
         return launch<LL>(fuchs_shared_kernel<LL, CfgShared<LL>::TPB>, p, p.batch, s, CfgShared<LL>::TPB,  \

@@ -16,6 +16,17 @@
 #pragma once
 #include "cb_arith.cuh"
 
+// Block-wide phase alignment of the recurrence kernel (an experiment, off by default; build with
+// -DCB_PHASE_SYNC_ON): the hot loop is ~64 KB of straight-line code, twice the 32 KB L1.5 instruction cache,
+// and warps that drift apart each stream it through the GPC-level instruction cache on their own.  A barrier
+// before every long call keeps the warps of a block on the same cache lines.  (Exited threads of a ragged
+// last block do not take part in the barrier.)  Measured: +10 % at 12 warps per SM, nothing at 7.
+#if defined(__CUDA_ARCH__) && defined(CB_PHASE_SYNC_ON)
+#define CB_PHASE_SYNC() __syncthreads()
+#else
+#define CB_PHASE_SYNC() ((void)0)
+#endif
+
 namespace cb {
 
 // a complex ball in memory
@@ -284,6 +295,7 @@ struct FuchsTableParams {
     CArr tbl;   // (n + 1 + v) * (W + 2) entries, S = 2
     CArr tmp;   // 2 entries, S = 2 * (n + 1 + v)   (per table thread)
     int32_t* kind;
+    int64_t row0;  // first table row computed by this launch (rows row0 .. n + v)
 };
 
 template <int L, class SCR>
@@ -338,6 +350,7 @@ struct FuchsSharedParams {
     uint32_t* gcols;  // 2 * (2L+3) words per instance, [word][instance]: columns of the general path
     int no_rr;        // development switch (CB200_NO_RR=1): skip the reduced-radix products
     unsigned long long* stats;  // development counters (CB200_RR_STATS=1) or nullptr: [0] rr accepted, [1] rr rejected
+    int64_t n_begin;  // first coefficient this launch computes (>= -valuation); earlier ones are already in res
 };
 struct RecCtl {
     bool rr;
@@ -347,13 +360,13 @@ struct RecCtl {
 
 // one fused dot product of the recurrence: truncated products with the exact general path as the
 // per-lane fallback (L = 16..32), or the exact in-shared-memory version (other precisions)
-template <int L, class SCR, class DST>
+template <int L, bool RR, class SCR, class DST>
 CB_HD Meta rec_fdot2(DST dst, Opd x1, OpdS y1, Opd x2, OpdS y2, bool neg2, SCR S0, SCR S1, GScratch G0, GScratch G1,
                      RecCtl ctl = RecCtl{true, nullptr}) {
     if constexpr (use_trunc<L>()) {
         bool ok = false;
         Meta t;
-        if constexpr (use_rr<L>()) {
+        if constexpr (RR && use_rr<L>()) {
             // reduced-radix products (plain IMAD.WIDE, no carry chains) first -- unless a shared
             // multiplier is zero or short (exact products: the carry-chain path knows how to trust
             // them); y1, y2 are the same for every lane, so this choice does not diverge
@@ -379,15 +392,19 @@ CB_HD Meta rec_fdot2(DST dst, Opd x1, OpdS y1, Opd x2, OpdS y2, bool neg2, SCR S
 }
 
 // AC: three small scratch columns (L+2 words each) rotating between acc.re, acc.im and "free"
-template <int L, class SCR>
+// RR: instantiate the reduced-radix attempt (a separate kernel: merely having the call in the code costs the
+// default kernel 50 registers and spills)
+template <int L, bool RR = false, class SCR>
 CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0, SCR S1, SCR A0, SCR A1,
                                SCR A2, GScratch G0, GScratch G1) {
     const size_t slot = 2 * (size_t)inst;
     const int v = p.valuation, W = p.degree - v;
     SCR accRe = A0, accIm = A1, spare = A2;
     const RecCtl ctl{p.no_rr == 0, p.stats};
+    // every coefficient is formed from the W previous ones read back from res, so the recurrence can be
+    // resumed at any index: a caller may solve in coefficient ranges and stream finished rows out meanwhile
 #pragma unroll 1
-    for (int64_t bmax = -v; bmax <= p.n; bmax++) {
+    for (int64_t bmax = (p.n_begin > -v ? p.n_begin : -v); bmax <= p.n; bmax++) {
         int64_t e = bmax + v;
         int64_t bmin = clampi(e - p.degree, 0, bmax);
         int cnt = (int)(bmax - bmin);
@@ -399,7 +416,8 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
             Opd a = re_of(x), b = im_of(x);
             OpdS c = re_of_shared(y), d = im_of_shared(y);
             // real part: acc.re -= a c - b d
-            Meta pr = rec_fdot2<L>(WRef{spare.generic(), SCR::GSTRIDE}, a, c, b, d, true, use_trunc<L>() ? spare : S0,
+            CB_PHASE_SYNC();
+            Meta pr = rec_fdot2<L, RR>(WRef{spare.generic(), SCR::GSTRIDE}, a, c, b, d, true, use_trunc<L>() ? spare : S0,
                                    S1, G0, G1, ctl);
             if (k == 0) {  // 0 - x = -x exactly: adopt the column, flip the sign
                 SCR t = accRe;
@@ -409,6 +427,7 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
                 if (!is_nan(tRe) && !is_zero_mid(tRe)) tRe.flags ^= F_SIGN;
             } else {
                 SCR where;
+                CB_PHASE_SYNC();
                 tRe = arb_addsub_cols<L>(accRe, tRe, spare, pr, true, &where);
                 if (where.a_or_p() == spare.a_or_p()) {
                     SCR t = accRe;
@@ -417,7 +436,8 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
                 }
             }
             // imaginary part: acc.im -= a d + b c
-            Meta pi = rec_fdot2<L>(WRef{spare.generic(), SCR::GSTRIDE}, a, d, b, c, false,
+            CB_PHASE_SYNC();
+            Meta pi = rec_fdot2<L, RR>(WRef{spare.generic(), SCR::GSTRIDE}, a, d, b, c, false,
                                    use_trunc<L>() ? spare : S0, S1, G0, G1, ctl);
             if (k == 0) {
                 SCR t = accIm;
@@ -427,6 +447,7 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
                 if (!is_nan(tIm) && !is_zero_mid(tIm)) tIm.flags ^= F_SIGN;
             } else {
                 SCR where;
+                CB_PHASE_SYNC();
                 tIm = arb_addsub_cols<L>(accIm, tIm, spare, pi, true, &where);
                 if (where.a_or_p() == spare.a_or_p()) {
                     SCR t = accIm;
@@ -440,8 +461,10 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
         if (p.kind[bmax + v] == 1) {
             CRef y = at<L>(p.tbl, base + W + 1, 0);
             OpdS c = re_of_shared(y), d = im_of_shared(y);
-            Meta tr = rec_fdot2<L>(wre(out), xa, c, xb, d, true, use_trunc<L>() ? spare : S0, S1, G0, G1, ctl);
-            Meta ti = rec_fdot2<L>(wim(out), xa, d, xb, c, false, use_trunc<L>() ? spare : S0, S1, G0, G1, ctl);
+            CB_PHASE_SYNC();
+            Meta tr = rec_fdot2<L, RR>(wre(out), xa, c, xb, d, true, use_trunc<L>() ? spare : S0, S1, G0, G1, ctl);
+            CB_PHASE_SYNC();
+            Meta ti = rec_fdot2<L, RR>(wim(out), xa, d, xb, c, false, use_trunc<L>() ? spare : S0, S1, G0, G1, ctl);
             st_meta(out.t, tr);
             st_meta(out.t + 1, ti);
         } else {

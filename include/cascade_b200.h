@@ -78,6 +78,15 @@ int cb200_fuchs_batch_dev(int L, int order, int degree, int valuation, int64_t n
                           const uint32_t *ode_mant, const cb_meta *ode_meta, int shared_ode,
                           uint32_t *res_mant, cb_meta *res_meta, void *workspace,
                           size_t workspace_bytes, void *stream);
+/* The same solve restricted to coefficients n_begin .. n (shared operator only): res[0 .. n_begin-1] must
+ * already hold the earlier coefficients (every coefficient is formed from the previous order+degree ones read
+ * back from res, so the recurrence resumes anywhere).  Lets a caller solve in coefficient ranges and copy the
+ * finished rows of res -- contiguous in this layout -- to the host while the next range is being computed
+ * (bench.py's end-to-end leg).  Ranges give bit-identical results to one full call. */
+int cb200_fuchs_batch_range_dev(int L, int order, int degree, int valuation, int64_t n_begin, int64_t n, int64_t batch,
+                                const uint32_t *ode_mant, const cb_meta *ode_meta, int shared_ode,
+                                uint32_t *res_mant, cb_meta *res_meta, void *workspace, size_t workspace_bytes,
+                                void *stream);
 int cb200_fuchs_batch_host(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
                            const uint32_t *ode_mant, const cb_meta *ode_meta, int shared_ode,
                            uint32_t *res_mant, cb_meta *res_meta, int device);

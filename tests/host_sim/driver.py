@@ -32,6 +32,7 @@ def lib():
         build()
         L = C.CDLL(_SO)
         L.cbsim_fuchs_batch.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p]
+        L.cbsim_fuchs_batch_range.argtypes = [C.c_int] * 4 + [C.c_int64] * 3 + [_u32p, _i32p, C.c_int, _u32p, _i32p]
         L.cbsim_fuchs_intop_batch.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS"), C.c_int, _u32p, _i32p]
         L.cbsim_continuation.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, _u32p, _i32p, _u32p, _i32p, _u32p, _i32p]
         L.cbsim_frobenius1_batch.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int, _vp, _vp, C.c_int64, C.c_int, _u32p, _i32p]
@@ -55,6 +56,10 @@ def lib():
 class SimDriver:
     def fuchs(self, L, order, degree, valuation, n, batch, ode_m, ode_t, shared, res_m, res_t):
         return lib().cbsim_fuchs_batch(L, order, degree, valuation, n, batch, ode_m, ode_t, int(shared), res_m, res_t)
+
+    def fuchs_range(self, L, order, degree, valuation, n_begin, n, batch, ode_m, ode_t, shared, res_m, res_t):
+        return lib().cbsim_fuchs_batch_range(L, order, degree, valuation, n_begin, n, batch, ode_m, ode_t, int(shared),
+                                             res_m, res_t)
 
     def fuchs_intop(self, L, order, degree, valuation, n, batch, ode_int, shared, res_m, res_t):
         return lib().cbsim_fuchs_intop_batch(L, order, degree, valuation, n, batch, ode_int, int(shared), res_m, res_t)

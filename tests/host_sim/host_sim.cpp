@@ -41,10 +41,20 @@ void run(int64_t count, F body) {
 
 extern "C" {
 
+int cbsim_fuchs_batch_range(int L_, int order, int degree, int valuation, int64_t n_begin, int64_t n, int64_t batch,
+                            const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
+                            uint32_t* res_mant, cb_meta* res_meta);
 int cbsim_fuchs_batch(int L_, int order, int degree, int valuation, int64_t n, int64_t batch,
                       const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
                       uint32_t* res_mant, cb_meta* res_meta) {
+    return cbsim_fuchs_batch_range(L_, order, degree, valuation, 0, n, batch, ode_mant, ode_meta, shared_ode, res_mant, res_meta);
+}
+int cbsim_fuchs_batch_range(int L_, int order, int degree, int valuation, int64_t n_begin, int64_t n, int64_t batch,
+                            const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
+                            uint32_t* res_mant, cb_meta* res_meta) {
     if (valuation >= 0) return CB200_EVALUATION;
+    if (n_begin < -valuation) n_begin = -valuation;
+    if (n_begin > n) return 0;
     FuchsParams p;
     p.order = order; p.degree = degree; p.valuation = valuation; p.n = n; p.batch = batch;
     p.ode = CArr{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta),
@@ -61,11 +71,11 @@ int cbsim_fuchs_batch(int L_, int order, int degree, int valuation, int64_t n, i
         tp.ode = p.ode;
         tp.tbl = tbl.arr(L_, rows * (W + 2), 2);
         tp.tmp = ttmp.arr(L_, 2, 2 * rows);
-        tp.kind = kind.data();
-        SIM_DISPATCH(L_, run<L>(rows, [&](int64_t i, Scratch<1> a, Scratch<1> b) { fuchs_table_thread<L>(tp, i, a, b); }));
+        tp.kind = kind.data(); tp.row0 = n_begin + valuation;
+        SIM_DISPATCH(L_, run<L>(rows - tp.row0, [&](int64_t i, Scratch<1> a, Scratch<1> b) { fuchs_table_thread<L>(tp, i + tp.row0, a, b); }));
         FuchsSharedParams sp;
         sp.order = order; sp.degree = degree; sp.valuation = valuation; sp.n = n; sp.batch = batch;
-        sp.tbl = tp.tbl; sp.res = p.res; sp.kind = kind.data(); sp.gcols = nullptr; sp.stats = nullptr;
+        sp.tbl = tp.tbl; sp.res = p.res; sp.kind = kind.data(); sp.gcols = nullptr; sp.stats = nullptr; sp.n_begin = n_begin;
         { const char* e = getenv("CB200_RR"); sp.no_rr = (e && e[0] == '1') ? 0 : 1; }  // as cb200_fuchs_batch_dev
         // columns sized EXACTLY as on the device (cb_kernels.cuh Sizes<L>), each followed by a
         // canary zone, so an out-of-column access is caught here and not only on the GPU
@@ -78,7 +88,11 @@ int cbsim_fuchs_batch(int L_, int order, int degree, int valuation, int64_t n, i
         for (int c = 0; c < 7; c++) col[c].assign(sizes[c] + CAN, 0xDEADBEEFu);
         Scratch<1> S0{col[0].data()}, S1{col[1].data()}, A0{col[2].data()}, A1{col[3].data()}, A2{col[4].data()};
         GScratch G0{col[5].data(), 1}, G1{col[6].data(), 1};
-        SIM_DISPATCH(L_, for (int64_t i = 0; i < batch; i++) fuchs_shared_thread<L>(sp, i, S0, S1, A0, A1, A2, G0, G1));
+        if (sp.no_rr) {
+            SIM_DISPATCH(L_, for (int64_t i = 0; i < batch; i++) (fuchs_shared_thread<L, false>)(sp, i, S0, S1, A0, A1, A2, G0, G1));
+        } else {
+            SIM_DISPATCH(L_, for (int64_t i = 0; i < batch; i++) (fuchs_shared_thread<L, true>)(sp, i, S0, S1, A0, A1, A2, G0, G1));
+        }
         for (int c = 0; c < 7; c++)
             for (size_t k = sizes[c]; k < sizes[c] + CAN; k++)
                 if (col[c][k] != 0xDEADBEEFu) return -1000 - c;  // column overrun

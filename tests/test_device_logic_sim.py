@@ -114,3 +114,23 @@ def test_solution_evaluate(oracle, sim_driver, L):
 @pytest.mark.parametrize("L", [4, 32])
 def test_ode_apply(oracle, sim_driver, L):
     cases.case_ode_apply(oracle, sim_driver, L, seed=71 + L)
+
+
+def test_fuchs_coefficient_ranges(oracle, sim_driver):
+    """Solving in coefficient ranges (cb200_fuchs_batch_range_dev: the recurrence resumes from res) gives the
+    same balls as one call."""
+    import numpy as np
+    from cascade_b200 import api
+    from cascade_b200.format import entry_major_to_instance_major, instance_major_to_entry_major, pack_entries, random_balls, unpack_entries
+    rng = np.random.default_rng(5)
+    L, n, batch = 32, 45, 3
+    ode = cases.bessel_shifted(oracle, rng, L)
+    init = random_balls(rng, batch * 4, L, -1, 0, "zero")
+    rc, want = oracle.fuchs_batch(2, 2, n, ode, init, batch, True)
+    res = oracle._series_with_init(init, batch, n, 2)
+    res_m, res_t = pack_entries(instance_major_to_entry_major(res, batch, n + 1), n + 1, 2 * batch)
+    ode_m, ode_t = api._ode_to_device(ode, 2, 2, batch, True)
+    for lo, hi in ((0, 7), (8, 8), (9, 30), (31, 45)):
+        assert sim_driver.fuchs_range(L, 2, 2, -2, lo, hi, batch, ode_m, ode_t, True, res_m, res_t) == 0
+    got = entry_major_to_instance_major(unpack_entries(L, res_m, res_t), batch, n + 1)
+    cases.assert_same(want, got, "fuchs in coefficient ranges")

@@ -58,3 +58,39 @@ def test_full_config_sampled_parity(oracle):
     for k in (0, len(sample) - 1):
         series = got[k * (n + 1) * 2:(k + 1) * (n + 1) * 2]
         assert oracle.ode_solves(2, 2, ode, series, 200)
+
+
+def test_coefficient_ranges_match_one_call():
+    """cb200_fuchs_batch_range_dev: solving coefficient ranges one after the other (what bench.py's end-to-end
+    leg does to overlap the copy-out) leaves exactly the bytes of a single full call."""
+    import torch
+
+    import bench
+    from cascade_b200 import _lib, api
+    from cascade_b200.format import instance_major_to_entry_major, pack_entries
+
+    lib = _lib.lib()
+    L, n, batch = bench.L, 300, 4096
+    dev = torch.device("cuda:0")
+    ode, init = bench.make_inputs(batch, n, api.HostBufferDriver(0))
+    S = 2 * batch
+    ode_m, ode_t = api._ode_to_device(ode, 2, 2, batch, True)
+    init_m, init_t = pack_entries(instance_major_to_entry_major(init, batch, 2), 2, S)
+    d_ode_m = torch.from_numpy(ode_m.view(np.int32)).to(dev)
+    d_ode_t = torch.from_numpy(ode_t).to(dev)
+    wsb = lib.cb200_fuchs_workspace_bytes(L, 2, 2, -2, n, batch, 1)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    outs = []
+    for ranges in ([(0, n)], [(0, 50), (51, 51), (52, 199), (200, n)]):
+        d_res_m = torch.zeros((n + 1, L, S), dtype=torch.int32, device=dev)
+        d_res_t = torch.zeros((n + 1, S, 4), dtype=torch.int32, device=dev)
+        d_res_m[:2].copy_(torch.from_numpy(init_m.view(np.int32)))
+        d_res_t[:2].copy_(torch.from_numpy(init_t))
+        for lo, hi in ranges:
+            rc = lib.cb200_fuchs_batch_range_dev(L, 2, 2, -2, lo, hi, batch, p(d_ode_m), p(d_ode_t), 1, p(d_res_m),
+                                                 p(d_res_t), p(ws), wsb, None)
+            assert rc == 0
+        torch.cuda.synchronize()
+        outs.append((d_res_m.cpu(), d_res_t.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
