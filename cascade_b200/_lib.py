@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcascade_b200.so")
+LIB_PATH = os.environ.get("CB200_LIB") or os.path.join(_HERE, "libcascade_b200.so")  # CB200_LIB: a development build
 _lib = None
 
 EINVAL, EVALUATION, ERANGE, ENOMEM = -1, -2, -3, -4
