@@ -70,3 +70,39 @@ def solve_fuchs_sharded(ode: Balls, init: Balls, order: int, degree: int, n: int
     if not gather:
         return local
     return gather_instances(local, batch, n + 1, group=group)
+
+
+def solve_frobenius_sharded(ode: Balls, rho: Balls, mul: int, alpha: int, order: int, degree: int, n: int, batch: int,
+                            shared_ode: bool = False, shared_rho: bool = False, driver=None, group=None,
+                            gather: bool = True):
+    """Parameter sweep of ``acb_ode_solve_frobenius`` (BASELINE configs[2]): each rank solves its block of the
+    (operator, rho) instances, any ``M = mul + alpha``; optionally all-gather ``sol->gens`` (``[batch][M][n+1]``)."""
+    import torch.distributed as dist
+
+    from . import api
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = partition(batch, world, rank)
+    ne = (order + 1) * (degree + 1)
+    v = api.acb_ode_valuation(ode, order, degree)
+    my_ode = ode if shared_ode else shard_instances(ode, batch, ne, lo, hi)
+    my_rho = rho if shared_rho else shard_instances(rho, batch, 1, lo, hi)
+    local = api.acb_ode_solve_frobenius_batch(my_ode, my_rho, mul, alpha, order, degree, n, hi - lo, shared_ode,
+                                              shared_rho, valuation=v, driver=driver)
+    if not gather:
+        return local
+    return gather_instances(local, batch, (mul + alpha) * (n + 1), group=group)
+
+
+def evaluate_sharded(gens: Balls, M: int, rho: Balls, pts: Balls, driver=None, group=None, gather: bool = True):
+    """``acb_ode_solution_evaluate`` of one solution at many points (BASELINE configs[4]): the points are
+    partitioned, the series are replicated (a few MB); optionally all-gather the values."""
+    import torch.distributed as dist
+
+    from . import api
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    npts = pts.n_slots // 2
+    lo, hi = partition(npts, world, rank)
+    local = api.acb_ode_solution_evaluate_batch(gens, M, rho, shard_instances(pts, npts, 1, lo, hi), driver=driver)
+    if not gather:
+        return local
+    return gather_instances(local, npts, 1, group=group)

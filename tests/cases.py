@@ -572,3 +572,30 @@ def case_ode_apply(oracle, drv, L: int, seed: int, batch: int = 3):
     bad.mant[2 * (n + 1) + 10, L - 1] ^= np.uint32(1 << 20)  # instance 1, coefficient 5: off by 2^-11 relative
     _, solved = api.acb_ode_apply_batch(ode, bad, order, degree, batch, False, deg=n - order, driver=drv)
     assert list(solved) == [True, False] + [True] * (batch - 2)
+
+
+def case_frobenius_general_edge(oracle, drv, L: int):
+    """Edge cases of the polynomial-in-rho recurrence where lengths shrink and the loop ends early
+    (reference src/frobenius_solver.c:193-194): integer operators with polynomial solutions (Legendre at an
+    ordinary point: the series terminates and g_new becomes the zero polynomial), an operator whose rescaling
+    value f_0(rho + nu) contains zero (the rescaling is skipped, :171), M = 4, and a shared operator with
+    per-instance rho."""
+    for n_leg, rho_v, mul, alpha in ((4, 0, 1, 1), (3, 1, 1, 1), (6, 0, 2, 0)):
+        ode = oracle.example("legendre", L, n_leg)
+        rho = from_complex([rho_v], L)
+        M = mul + alpha
+        go = oracle.frobenius_general_batch(2, 2, 14, ode, rho, 1, True, True, mul, M)
+        gs = api.acb_ode_solve_frobenius_batch(ode, rho, mul, alpha, 2, 2, 14, 1, True, True, driver=drv)
+        assert_same(go, gs, f"general frobenius, legendre({n_leg}) rho={rho_v} L={L}")
+    # f_0(rho + nu) = (rho + nu)(rho + nu - 1 + c) vanishes at nu = 2 for rho = -2: the division is skipped there
+    ode = oracle.example("hypgeom", L, 0, from_complex([F(3, 8), F(5, 16), F(7, 4)], L))
+    rho = from_complex([-2], L)
+    go = oracle.frobenius_general_batch(2, 2, 6, ode, rho, 1, True, True, 2, 2)
+    gs = api.acb_ode_solve_frobenius_batch(ode, rho, 2, 0, 2, 2, 6, 1, True, True, driver=drv)
+    assert_same(go, gs, f"general frobenius through a zero of f_0 L={L}")
+    # M = 4, shared operator, per-instance rho
+    rng = np.random.default_rng(17 + L)
+    rho = random_balls(rng, 3 * 2, L, -1, 1, "ulp")
+    go = oracle.frobenius_general_batch(2, 2, 5, ode, rho, 3, True, False, 3, 4)
+    gs = api.acb_ode_solve_frobenius_batch(ode, rho, 3, 1, 2, 2, 5, 3, True, False, driver=drv)
+    assert_same(go, gs, f"general frobenius M=4 L={L}")

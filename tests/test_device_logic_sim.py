@@ -134,3 +134,8 @@ def test_fuchs_coefficient_ranges(oracle, sim_driver):
         assert sim_driver.fuchs_range(L, 2, 2, -2, lo, hi, batch, ode_m, ode_t, True, res_m, res_t) == 0
     got = entry_major_to_instance_major(unpack_entries(L, res_m, res_t), batch, n + 1)
     cases.assert_same(want, got, "fuchs in coefficient ranges")
+
+
+@pytest.mark.parametrize("L", [4, 32])
+def test_frobenius_general_edge(oracle, sim_driver, L):
+    cases.case_frobenius_general_edge(oracle, sim_driver, L)

@@ -115,3 +115,8 @@ def test_solution_evaluate(oracle, gpu_driver, L):
 @pytest.mark.parametrize("L", [4, 32, 64])
 def test_ode_apply(oracle, gpu_driver, L):
     cases.case_ode_apply(oracle, gpu_driver, L, seed=71 + L, batch=40)
+
+
+@pytest.mark.parametrize("L", [4, 32, 64])
+def test_frobenius_general_edge(oracle, gpu_driver, L):
+    cases.case_frobenius_general_edge(oracle, gpu_driver, L)

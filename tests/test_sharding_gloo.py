@@ -31,10 +31,22 @@ def _worker(rank, world, port, out):
     ode = bessel_shifted(cbo, rng, L)
     init = random_balls(rng, batch * 4, L, -1, 0, "zero")
     full = sharding.solve_fuchs_sharded(ode, init, 2, 2, n, batch, True, driver=SimDriver())
+    # parameter sweep of the (logarithmic) Frobenius solver and a point sweep of the evaluation
+    from cascade_b200.format import Balls
+    par = random_balls(rng, batch * 6, L, -1, 1, "zero")
+    odes = Balls.concat([cbo.example("hypgeom", L, 0, par[i * 6:(i + 1) * 6]) for i in range(batch)])
+    rho = random_balls(rng, batch * 2, L, -1, 1, "ulp")
+    gens = sharding.solve_frobenius_sharded(odes, rho, 2, 0, 2, 2, 6, batch, driver=SimDriver())
+    pts = random_balls(rng, 2 * 5, L, -2, 0, "zero")
+    g0 = gens[0:2 * 2 * 7]  # the two series of instance 0
+    vals = sharding.evaluate_sharded(g0, 2, rho[0:2], pts, driver=SimDriver())
     if rank == 0:
         single = api.acb_ode_solve_fuchs_batch(ode, init, 2, 2, n, batch, True, driver=SimDriver())
         rc, ref = cbo.fuchs_batch(2, 2, n, ode, init, batch, True)
-        out.put((full.same_as(single), full.same_as(ref)))
+        gref = cbo.frobenius_general_batch(2, 2, 6, odes, rho, batch, False, False, 2, 2)
+        mode, e = api.pow_mode_of(rho[0:2])
+        vref = cbo.solution_evaluate(g0, 2, rho[0:2], mode, e, pts)
+        out.put((full.same_as(single), full.same_as(ref) and gens.same_as(gref) and vals.same_as(vref)))
     dist.barrier()
     dist.destroy_process_group()
 
