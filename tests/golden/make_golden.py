@@ -58,6 +58,24 @@ def main():
     put("horner_f", f)
     put("horner_pts", pts)
     put("horner_out", cbo.horner_batch(f, pts, 2))
+    # logarithmic Frobenius (M = 2), right-hand side, bookkeeping steps, exp/log, full evaluate, residual
+    gens = cbo.frobenius_general_batch(2, 2, 10, hyp, rho, 1, True, True, 2, 2)
+    put("frobg_gens", gens)
+    rhs = random_balls(rng, 2 * 5, L, -2, 2, "ulp")
+    put("frob_rhs", rhs)
+    put("frob_rhs_res", cbo.frobenius1_rhs_batch(2, 2, 12, hyp, rho, rhs, 1, True))
+    fpoly = random_balls(rng, 2 * 7, L, -3, 3, "ulp")
+    put("sol_f", fpoly)
+    put("sol_updated", cbo.solution_op("update", rho, gens, 1, 2, 2, fpoly)[0])
+    put("indicial", cbo.indicial_polynomial(2, 2, hyp, 1, 3))
+    x = random_balls(rng, 2 * 6, L, -3, 3, "ulp")
+    put("trans_x", x)
+    put("trans_exp", cbo.ew_trans("exp", x))
+    put("trans_log", cbo.ew_trans("log", x))
+    put("eval_out", cbo.solution_evaluate(gens, 2, rho, 2, 0, pts))
+    series = cbo.fuchs_batch(2, 2, 12, hyp, from_complex([1], L), 1, True)[1]
+    put("apply_in", series)
+    put("apply_out", cbo.ode_apply(2, 2, hyp, series))
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "vectors.npz"), **out)
     print("wrote", len(out), "arrays")
 
