@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(Cfg<L>::TPB, 1) fuchs_table_kernel(FuchsTableP
     CB_KERNEL_PROLOGUE(p.n + 1 + p.valuation - p.row0)
     fuchs_table_thread<L>(p, idx + p.row0, S0, S1);
 }
-template <int L, int TPB, bool RR = false>
+template <int L, int TPB, bool RR = false, bool SYNC = false>
 __global__ void __launch_bounds__(TPB, 1) fuchs_shared_kernel(FuchsSharedParams p) {
     extern __shared__ uint32_t cb_smem[];
     constexpr uint32_t W0 = Sizes<L>::S0WORDS, W1 = Sizes<L>::S1WORDS, AW = Sizes<L>::AWORDS;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(TPB, 1) fuchs_shared_kernel(FuchsSharedParams 
     if (idx >= p.batch) return;
     GScratch G0{p.gcols + idx, (size_t)p.batch};
     GScratch G1{p.gcols + (size_t)Sizes<L>::WORDS * p.batch + idx, (size_t)p.batch};
-    fuchs_shared_thread<L, RR>(p, idx, S0, S1, A0, A1, A2, G0, G1);
+    fuchs_shared_thread<L, RR, SYNC>(p, idx, S0, S1, A0, A1, A2, G0, G1);
 }
 
 // integer-operator kernel: 4 columns of ~L+3 words per thread, light on registers
@@ -135,9 +135,9 @@ __global__ void __launch_bounds__(IntopCfg<L>::TPB, 1) fuchs_intop_kernel(FuchsI
 
 // time of a launch is proportional to (number of waves) x (instances per SM per wave) / throughput;
 // relative per-SM throughputs measured on B200 (7, 12 and 14 warps per SM)
-// (measured, 65 536-instance runs of 98 coefficients: 224 threads 21.9 instances/ms/SM, 384 threads 23.6,
-// 448 threads -- 128 registers, 532 B of spills -- 21.4: the 14-warp variant buys nothing and is not chosen)
-constexpr double THR_BIG = 1.08, THR_HUGE = 0.98;
+// (measured, 98-coefficient runs: 224 threads 21.7 instances/ms/SM, 384 threads 23.4 -- 25.9 with the phase
+// barriers it is built with --, 448 threads -- 128 registers, 532 B of spills -- 21.4: never chosen)
+constexpr double THR_BIG = 1.19, THR_HUGE = 0.98;
 // 0: TPB, 1: TPB_BIG, 2: TPB_HUGE.  CB200_TPB_CHOICE=0/1/2 in the environment overrides (development)
 template <int L>
 int choose_block_size(int64_t batch, int sms) {
@@ -206,7 +206,7 @@ struct LaunchTable {
             return launch<LL>(fuchs_shared_kernel<LL, CfgShared<LL>::TPB_HUGE>, p, p.batch, s, CfgShared<LL>::TPB_HUGE, \
                               Sizes<LL>::SMEM_SHARED_PER_THREAD * CfgShared<LL>::TPB_HUGE);                \
         if (choice == 1)                                                                                   \
-            return launch<LL>(fuchs_shared_kernel<LL, CfgShared<LL>::TPB_BIG>, p, p.batch, s, CfgShared<LL>::TPB_BIG, \
+            return launch<LL>(fuchs_shared_kernel<LL, CfgShared<LL>::TPB_BIG, false, true>, p, p.batch, s, CfgShared<LL>::TPB_BIG, \
                               Sizes<LL>::SMEM_SHARED_PER_THREAD * CfgShared<LL>::TPB_BIG);                 \
         return launch<LL>(fuchs_shared_kernel<LL, CfgShared<LL>::TPB>, p, p.batch, s, CfgShared<LL>::TPB,  \
                           Sizes<LL>::SMEM_SHARED_PER_THREAD * CfgShared<LL>::TPB);                         \

@@ -16,16 +16,18 @@
 #pragma once
 #include "cb_arith.cuh"
 
-// Block-wide phase alignment of the recurrence kernel (an experiment, off by default; build with
-// -DCB_PHASE_SYNC_ON): the hot loop is ~64 KB of straight-line code, twice the 32 KB L1.5 instruction cache,
-// and warps that drift apart each stream it through the GPC-level instruction cache on their own.  A barrier
-// before every long call keeps the warps of a block on the same cache lines.  (Exited threads of a ragged
-// last block do not take part in the barrier.)  Measured: +10 % at 12 warps per SM, nothing at 7.
-#if defined(__CUDA_ARCH__) && defined(CB_PHASE_SYNC_ON)
-#define CB_PHASE_SYNC() __syncthreads()
-#else
-#define CB_PHASE_SYNC() ((void)0)
+// Block-wide phase alignment of the recurrence kernel: the hot loop is ~64 KB of straight-line code, twice the
+// 32 KB L1.5 instruction cache, and warps that drift apart each stream it through the GPC-level instruction
+// cache on their own.  A barrier before every long call keeps the warps of a block on the same cache lines.
+// (Exited threads of a ragged last block do not take part in the barrier.)  Measured:
+// +10 % at 12 warps per SM, nothing at 7 -- so only the 384-thread variant is built with it.
+template <bool SYNC>
+CB_HD void phase_sync() {
+#if defined(__CUDA_ARCH__)
+    if constexpr (SYNC) __syncthreads();
 #endif
+}
+#define CB_PHASE_SYNC() phase_sync<SYNC>()
 
 namespace cb {
 
@@ -394,7 +396,7 @@ CB_HD Meta rec_fdot2(DST dst, Opd x1, OpdS y1, Opd x2, OpdS y2, bool neg2, SCR S
 // AC: three small scratch columns (L+2 words each) rotating between acc.re, acc.im and "free"
 // RR: instantiate the reduced-radix attempt (a separate kernel: merely having the call in the code costs the
 // default kernel 50 registers and spills)
-template <int L, bool RR = false, class SCR>
+template <int L, bool RR = false, bool SYNC = false, class SCR>
 CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0, SCR S1, SCR A0, SCR A1,
                                SCR A2, GScratch G0, GScratch G1) {
     const size_t slot = 2 * (size_t)inst;

@@ -434,6 +434,23 @@ static void trans1(int which, acb_struct* z, const acb_struct* x, slong prec, co
     if (rc) die(what, rc);
     hz.get(0, 0, z);
 }
+// acb_pow(z, x, y): 1 for y = 0, binary exponentiation for an exact integer 0 <= y < 2^31, exp(y log x) otherwise --
+// the evaluate kernel with the constant series 1 (out = 1 * x^y; the product with the exact 1 is exact)
+void acb_pow(acb_t z, const acb_t x, const acb_t y, slong prec) {
+    int L = limbs_of(prec);
+    HostArr hg(L, 1, 2), hrho(L, 1, 2), hp(L, 1, 2), ho(L, 1, 2);
+    acb_t one;
+    acb_one(one);
+    hg.put(0, 0, one);
+    hrho.put(0, 0, y);
+    hp.put(0, 0, x);
+    uint64_t e = 0;
+    int mode = pow_mode_of(y, &e);
+    int rc = cb200_solution_evaluate_host(L, 1, 1, 1, hg.m.data(), hg.t.data(), hrho.m.data(), hrho.t.data(), mode, e,
+                                          hp.m.data(), hp.t.data(), ho.m.data(), ho.t.data(), 0);
+    if (rc) die("acb_pow (cb200_solution_evaluate_host)", rc);
+    ho.get(0, 0, z);
+}
 void acb_exp(acb_t z, const acb_t x, slong prec) { trans1(CB200_TRANS_EXP, z, x, prec, "acb_exp (cb200_trans_host)"); }
 void acb_log(acb_t z, const acb_t x, slong prec) { trans1(CB200_TRANS_LOG, z, x, prec, "acb_log (cb200_trans_host)"); }
 

@@ -96,6 +96,7 @@ void acb_add_si(acb_t z, const acb_t x, slong k, slong prec);
 void acb_poly_evaluate(acb_t y, const acb_poly_t f, const acb_t x, slong prec);
 void acb_exp(acb_t z, const acb_t x, slong prec);
 void acb_log(acb_t z, const acb_t x, slong prec);
+void acb_pow(acb_t z, const acb_t x, const acb_t y, slong prec);
 void arb_init(arb_t x);
 void arb_clear(arb_t x);
 void arb_set_d(arb_t x, double v);

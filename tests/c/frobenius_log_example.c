@@ -33,6 +33,9 @@ int main ()
     acb_set_d_d(z, -0.125, 0.0);
     acb_log(y, z, prec);
     printf("log %.17g %.17g %.3g\n", acb_get_mid_re_d(y), acb_get_mid_im_d(y), acb_get_rad_re_d(y));
+    acb_set_d(c, 0.5);
+    acb_pow(a, z, c, prec); /* (-1/8)^(1/2) = i / sqrt(8) */
+    printf("pow %.17g %.17g %.3g\n", acb_get_mid_re_d(a), acb_get_mid_im_d(a), acb_get_rad_re_d(a));
     acb_exp(y, y, prec);
     printf("explog %.17g %.17g %.3g\n", acb_get_mid_re_d(y), acb_get_mid_im_d(y), acb_get_rad_re_d(y));
     acb_ode_solution_clear(sol);

@@ -64,9 +64,11 @@ def test_logarithmic_frobenius_and_solution_bookkeeping():
     assert abs(ev[0] - want) < 1e-13 * abs(want) and ev[1] == 0.0 and ev[2] < 1e-290
     lg = [float(v) for v in next(r for r in rows if r[0] == "log")[1:]]
     assert abs(lg[0] - math.log(0.125)) < 1e-15 and abs(lg[1] - math.pi) < 1e-15 and lg[2] < 1e-290
+    pw = [float(v) for v in next(r for r in rows if r[0] == "pow")[1:]]
+    assert abs(pw[0]) < 1e-290 and abs(pw[1] - 1 / math.sqrt(8)) < 1e-16 and pw[2] < 1e-290
     el = [float(v) for v in next(r for r in rows if r[0] == "explog")[1:]]
     assert abs(el[0] + 0.125) < 1e-16 and abs(el[1]) < 1e-290
-    vals = {r[0] + (r[1] if r[0] in ("indicial", "extend", "update") else ""): r for r in rows if r[0] not in ("gens", "eval2", "log", "explog")}
+    vals = {r[0] + (r[1] if r[0] in ("indicial", "extend", "update") else ""): r for r in rows if r[0] not in ("gens", "eval2", "log", "explog", "pow")}
     assert vals["indicial_len"][1] == "3"
     assert [float(vals[f"indicial{k}"][2]) for k in range(3)] == [9.0, 6.0, 1.0]
     assert float(vals["indicial_at_2"][1]) == 25.0 and float(vals["indicial_at_2"][2]) == 25.0
