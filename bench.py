@@ -340,8 +340,10 @@ def main():
     cpu = None
     if not args.no_cpu:
         v, sb, dt = cpu_port(ncores, target_seconds=10.0)
+        v1, sb1, dt1 = cpu_port(1, target_seconds=3.0)  # the reference is single-threaded as shipped
         cpu = {"value": v, "unit": UNIT, "cores": ncores, "kind": "port",
-               "sample": f"{sb} instances x {n - 1} coefficients, oracle port (Cascade loops on GMP 6.3 mpn), {dt:.1f} s"}
+               "sample": f"{sb} instances x {n - 1} coefficients, oracle port (Cascade loops on GMP 6.3 mpn), {dt:.1f} s",
+               "single_core": {"value": v1, "sample": f"{sb1} instances, {dt1:.1f} s"}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32 limbs (1024-bit ball)", "data": "synthetic", "config": config,
