@@ -810,4 +810,78 @@ void find_monodromy_matrix(acb_mat_t mono, acb_ode_t ODE, slong bits) {
     _acb_vec_clear(path, steps + 1);
 }
 
+
+// ------------------------------------------------------------------ residual check (reference src/acb_ode.c:185-240)
+// out = sum_i p_i * in^(i) with all len(in) + degree coefficients; the products run on the device
+void acb_ode_apply(acb_poly_t out, acb_ode_t ODE, acb_poly_t in, slong prec) {
+    int L = limbs_of(prec);
+    slong ne = (ODE->order + 1) * (ODE->degree + 1), len = in->length, out_len = len + ODE->degree;
+    HostArr ho(L, ne, 2), hi(L, len > 0 ? len : 1, 2), hr(L, out_len > 0 ? out_len : 1, 2);
+    for (slong e = 0; e < ne; e++) ho.put(e, 0, ODE->polys + e);
+    for (slong k = 0; k < len; k++) hi.put(k, 0, in->coeffs + k);  // marshalled first: out may alias in
+    int rc = cb200_ode_apply_host(L, (int)ODE->order, (int)ODE->degree, 1, ho.m.data(), ho.t.data(), 1, hi.m.data(),
+                                  hi.t.data(), len, hr.m.data(), hr.t.data(), out_len, 0, nullptr, 0);
+    if (rc) die("acb_ode_apply (cb200_ode_apply_host)", rc);
+    acb_poly_zero(out);
+    acb_poly_fit_length(out, out_len);
+    for (slong k = 0; k < out_len; k++) hr.get(k, 0, out->coeffs + k);
+    out->length = out_len;
+    poly_normalise(out);
+}
+int acb_ode_solves(acb_ode_t ODE, acb_poly_t res, slong deg, slong prec) {
+    int L = limbs_of(prec);
+    slong ne = (ODE->order + 1) * (ODE->degree + 1), len = res->length, out_len = len + ODE->degree;
+    HostArr ho(L, ne, 2), hi(L, len > 0 ? len : 1, 2), hr(L, out_len > 0 ? out_len : 1, 2);
+    for (slong e = 0; e < ne; e++) ho.put(e, 0, ODE->polys + e);
+    for (slong k = 0; k < len; k++) hi.put(k, 0, res->coeffs + k);
+    int32_t solved = 0;
+    int rc = cb200_ode_apply_host(L, (int)ODE->order, (int)ODE->degree, 1, ho.m.data(), ho.t.data(), 1, hi.m.data(),
+                                  hi.t.data(), len, hr.m.data(), hr.t.data(), out_len, deg, &solved, 0);
+    if (rc) die("acb_ode_solves (cb200_ode_apply_host)", rc);
+    return solved;
+}
+
+// ------------------------------------------------------------------ acb_ode_random (reference src/acb_ode.c:83-95)
+// FLINT's generator is not available: a splitmix64 stream stands in (same shape of the distribution:
+// degree 3..9, order 2..degree-1, coefficients with up to prec significant bits and exponents within +-16)
+void flint_randinit(flint_rand_t state) { state->s = 0x9E3779B97F4A7C15ull; }
+void flint_randclear(flint_rand_t) {}
+static uint64_t next64(flint_rand_struct* st) {
+    uint64_t z = (st->s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+ulong n_randint(flint_rand_t state, ulong limit) { return limit ? (ulong)(next64(state) % limit) : 0; }
+static void arb_random(arb_struct* x, flint_rand_struct* st, slong prec) {
+    memset(x, 0, sizeof(*x));
+    if (next64(st) % 8 == 0) {  // exact zeros are part of acb_randtest's distribution
+        x->meta.flags = CB_FLAG_ZERO;
+        return;
+    }
+    slong bits = 1 + (slong)(next64(st) % (uint64_t)(prec > 4096 ? 4096 : prec));
+    slong limbs = (bits + 31) / 32;
+    for (slong k = 0; k < limbs; k++) x->mant[CB_MAX_LIMBS - 1 - k] = (uint32_t)next64(st);
+    x->mant[CB_MAX_LIMBS - 1] |= 0x80000000u;
+    slong drop = 32 * limbs - bits;  // clear the bits below the chosen length
+    if (drop) x->mant[CB_MAX_LIMBS - limbs] &= ~((1u << drop) - 1u);
+    if (limbs == 1 && drop) x->mant[CB_MAX_LIMBS - 1] |= 0x80000000u;
+    x->meta.exp = (int32_t)(next64(st) % 33) - 16;
+    x->meta.flags = (next64(st) & 1) ? CB_FLAG_SIGN : 0;
+    if (next64(st) % 2 == 0) {  // a radius of about one ulp at the working precision
+        x->meta.rman = 1u << 29;
+        x->meta.rexp = x->meta.exp - (int32_t)prec + 1;
+    }
+}
+void acb_ode_random(acb_ode_t ode, flint_rand_t state, slong prec) {
+    slong degree = 3 + (slong)n_randint(state, 7);
+    slong order = 2 + (slong)n_randint(state, (ulong)(degree - 2));
+    acb_ode_init_blank(ode, degree, order);
+    for (slong i = 0; i <= order; i++)
+        for (slong j = 0; j <= degree; j++) {
+            arb_random(&acb_ode_coeff(ode, i, j)->real, state, prec);
+            arb_random(&acb_ode_coeff(ode, i, j)->imag, state, prec);
+        }
+}
+
 }  // extern "C"

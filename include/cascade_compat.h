@@ -112,6 +112,14 @@ typedef acb_mat_struct acb_mat_t[1];
 #define acb_mat_entry(mat, i, j) ((mat)->rows[i] + (j))
 void acb_mat_init(acb_mat_t m, slong r, slong c);
 void acb_mat_clear(acb_mat_t m);
+/* stand-in for FLINT's generator (used by acb_ode_random only) */
+typedef struct {
+    uint64_t s;
+} flint_rand_struct;
+typedef flint_rand_struct flint_rand_t[1];
+void flint_randinit(flint_rand_t state);
+void flint_randclear(flint_rand_t state);
+ulong n_randint(flint_rand_t state, ulong limit);
 #endif /* ACB_H */
 
 /* ========================= Differential Operators (reference src/acb_ode.h:9-41) ============== */
@@ -137,6 +145,10 @@ void acb_ode_dump(acb_ode_t ODE, char *file);                      /* src/acb_od
 void acb_ode_shift(acb_ode_t ODE_out, acb_ode_t ODE_in, acb_srcptr a, slong bits); /* :124-135 */
 slong acb_ode_valuation(acb_ode_t ODE);                            /* src/acb_ode.c:159-181 */
 slong acb_ode_reduce(acb_ode_t ODE);                               /* src/acb_ode.c:137-157 */
+void acb_ode_random(acb_ode_t ode, flint_rand_t state, slong prec); /* src/acb_ode.c:83-95 (own generator) */
+/* the reference's acceptance test of both solvers, on the device (src/acb_ode.c:185-240) */
+void acb_ode_apply(acb_poly_t out, acb_ode_t ODE, acb_poly_t in, slong prec);
+int acb_ode_solves(acb_ode_t ODE, acb_poly_t res, slong deg, slong prec);
 
 /* =============================== Solutions (reference src/acb_ode.h:45-61) ==================== */
 typedef struct {

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared(header):
     txt = open(os.path.join(ROOT, "include", header)).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(cb200_\w+|acb_ode_\w+|_acb_ode_\w+|analytic_continuation|indicial_polynomial(?:_evaluate)?|find_monodromy_matrix|radius_of_convergence|truncation_order)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(cb200_\w+|acb_ode_\w+|_acb_ode_\w+|analytic_continuation|indicial_polynomial(?:_evaluate)?|find_monodromy_matrix|radius_of_convergence|truncation_order|flint_rand\w+|n_randint)\s*\(", txt)))
 
 
 def test_library_exports_every_declared_symbol():

@@ -89,3 +89,12 @@ def test_monodromy_matrix():
     assert 200 <= v["truncation_order"][0] <= 260
     assert abs(v["trace"][0] - 1.0) < 1e-13 and abs(v["trace"][1] - 1.0) < 1e-13 and v["trace"][2] < 1e-200
     assert abs(v["det"][0]) < 1e-13 and abs(v["det"][1] - 1.0) < 1e-13 and v["det"][2] < 1e-200
+
+
+def test_reference_fuchs_test_program():
+    """reference tests/fuchs.c through the compat names: acb_ode_random operators, acb_ode_solve_fuchs and the
+    reference's own acceptance test acb_ode_solves, all on the device."""
+    out = build_and_run("fuchs_random_example")
+    lines = out.strip().splitlines()
+    assert lines[-1] == "failures 0"
+    assert sum(1 for line in lines if line.startswith("iter") and line.endswith("solves 1")) >= 6
