@@ -56,6 +56,11 @@ bool factor_fits(int64_t n, int order) {
     return v < 4.0e18L;
 }
 
+// columns of the general-path scratch: the batch padded to whole blocks of the persistent launch (which gives the
+// idle lanes of a ragged last block columns of their own)
+static_assert(CfgShared<32>::TPB_BIG == 384, "gcols_columns pads to the persistent block size");
+size_t gcols_columns(int64_t batch) { return (size_t)((batch + 383) / 384 * 384); }
+
 struct DevBuf {
     void* p = nullptr;
     ~DevBuf() { if (p) cudaFree(p); }
@@ -96,7 +101,8 @@ size_t cb200_fuchs_workspace_bytes(int L, int order, int degree, int valuation, 
     int64_t rows = n + 1 + valuation, W = degree - valuation;
     if (rows < 0) rows = 0;
     return carve_bytes(L, rows * (W + 2), 2) + carve_bytes(L, 2, 2 * rows) + align256(sizeof(int32_t) * (rows + 1)) +
-           align256((size_t)2 * (2 * L + 3) * batch * sizeof(uint32_t));
+           align256((size_t)2 * (2 * L + 3) * gcols_columns(batch) * sizeof(uint32_t)) +
+           align256(sizeof(int) * (size_t)(batch / 32 + 2));
 }
 size_t cb200_frobenius_workspace_bytes(int L, int64_t batch) { return carve_bytes(L, FROB_NTMP, 2 * batch); }
 size_t cb200_horner_workspace_bytes(int L, int64_t npts) { return carve_bytes(L, 1, 2 * npts); }
@@ -151,6 +157,9 @@ int cb200_fuchs_batch_range_dev(int L_, int order, int degree, int valuation, in
         sp.res = CArr{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
         sp.kind = tp.kind;
         sp.gcols = (uint32_t*)w;
+        w += align256((size_t)2 * (2 * L_ + 3) * gcols_columns(batch) * sizeof(uint32_t));
+        sp.sched = (int*)w;  // unit counter + one progress word per instance block (persistent launch)
+        sp.range_len = 32;
         sp.n_begin = n_begin;
         {
             // the reduced-radix fused dot product (cb_rr.cuh) is bit-identical but measured slower than

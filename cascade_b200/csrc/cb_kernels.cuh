@@ -118,6 +118,57 @@ __global__ void __launch_bounds__(TPB, 1) fuchs_shared_kernel(FuchsSharedParams 
     fuchs_shared_thread<L, RR, SYNC>(p, idx, S0, S1, A0, A1, A2, G0, G1);
 }
 
+// Persistent form of the recurrence kernel.  Every coefficient is formed from coefficients read back from res, so
+// the work of an instance block can be cut anywhere along the coefficient index: a work unit is (block of TPB
+// instances, range of range_len coefficients).  One CTA per SM takes units from a counter in coefficient-major
+// order; unit (b, r) waits for (b, r - 1), which was handed out one full round earlier.  This removes the
+// last-wave tail for ANY batch size, so the 12-warp variant (with phase barriers: 1.19x per SM) can serve batches
+// that are not a multiple of 148 * 384 instances -- BASELINE's 65 536 included.
+// Idle lanes of a ragged last block recompute the last valid instance (identical stores), so that every thread
+// of the CTA reaches every barrier.
+template <int L, int TPB>
+__global__ void __launch_bounds__(TPB, 1) fuchs_shared_persistent_kernel(FuchsSharedParams p) {
+    extern __shared__ uint32_t cb_smem[];
+    __shared__ int unit_s;
+    constexpr uint32_t W0 = Sizes<L>::S0WORDS, W1 = Sizes<L>::S1WORDS, AW = Sizes<L>::AWORDS;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cb_smem) + 4u * threadIdx.x;
+    Scratch<TPB> S0{sbase}, S1{sbase + 4u * W0 * TPB};
+    Scratch<TPB> A0{sbase + 4u * (W0 + W1) * TPB}, A1{sbase + 4u * (W0 + W1 + AW) * TPB},
+        A2{sbase + 4u * (W0 + W1 + 2 * AW) * TPB};
+    const int64_t nblocks = (p.batch + TPB - 1) / TPB;
+    const int64_t first = p.n_begin > -p.valuation ? p.n_begin : -p.valuation;
+    const int64_t nranges = (p.n - first + p.range_len) / p.range_len;
+    const int64_t total = nblocks * nranges;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            int u = atomicAdd(p.sched, 1);
+            if (u < total) {
+                int64_t b = u % nblocks, r = u / nblocks;
+                while (r > 0 && atomicAdd(p.sched + 1 + b, 0) < (int)r) __nanosleep(200);
+                __threadfence();
+            }
+            unit_s = u;
+        }
+        __syncthreads();
+        const int64_t u = unit_s;
+        if (u >= total) break;
+        const int64_t b = u % nblocks, r = u / nblocks;
+        int64_t inst = b * TPB + threadIdx.x;
+        if (inst >= p.batch) inst = p.batch - 1;
+        FuchsSharedParams q = p;
+        q.n_begin = first + r * p.range_len;
+        q.n = q.n_begin + p.range_len - 1 < p.n ? q.n_begin + p.range_len - 1 : p.n;
+        // every thread -- idle lanes included -- owns a column of the (padded) general-path scratch
+        const size_t gstride = (size_t)nblocks * TPB, gi = (size_t)b * TPB + threadIdx.x;
+        GScratch G0{p.gcols + gi, gstride};
+        GScratch G1{p.gcols + (size_t)Sizes<L>::WORDS * gstride + gi, gstride};
+        fuchs_shared_thread<L, false, true>(q, inst, S0, S1, A0, A1, A2, G0, G1);
+        __threadfence();  // this thread's coefficients are visible device-wide before the block reports the range
+        __syncthreads();
+        if (threadIdx.x == 0) atomicExch(p.sched + 1 + b, (int)(r + 1));
+    }
+}
+
 // integer-operator kernel: 4 columns of ~L+3 words per thread, light on registers
 template <int L> struct IntopCfg { static constexpr int TPB = L <= 32 ? 384 : (L == 64 ? 192 : 96); };
 template <int L>
@@ -156,6 +207,28 @@ int choose_block_size(int64_t batch, int sms) {
     }
     if (CfgShared<L>::TPB_HUGE != CfgShared<L>::TPB && cost(CfgShared<L>::TPB_HUGE, THR_HUGE) < c) best = 2;
     return best;
+}
+
+// persistent launch: worthwhile when the batch is more than one wave of the big blocks and the fractional-wave cost
+// of the 12-warp variant beats the best whole-wave choice.  CB200_PERSISTENT=0/1 in the environment overrides.
+template <int L>
+bool use_persistent(int64_t batch, int sms) {
+    if (L != 32 || CfgShared<L>::TPB_BIG == CfgShared<L>::TPB) return false;
+    const char* e = getenv("CB200_PERSISTENT");
+    if (e && e[0] == '0') return false;
+    if (e && e[0] == '1') return true;
+    auto cost = [&](int tpb, double thr) {
+        int64_t blocks = (batch + tpb - 1) / tpb;
+        int64_t waves = (blocks + sms - 1) / sms;
+        return (double)waves * tpb / thr;
+    };
+    double best = cost(CfgShared<L>::TPB, 1.0);
+    double big = cost(CfgShared<L>::TPB_BIG, THR_BIG);
+    if (big < best) best = big;
+    int64_t blocks = (batch + CfgShared<L>::TPB_BIG - 1) / CfgShared<L>::TPB_BIG;
+    if (blocks <= sms) return false;
+    double pers = (double)blocks * CfgShared<L>::TPB_BIG / sms / THR_BIG * 1.02;  // 2 % for the ragged last round
+    return pers < best;
 }
 
 template <int L, class P>
@@ -201,6 +274,19 @@ struct LaunchTable {
         if (use_rr<LL>() && !p.no_rr) /* opt-in experiment (CB200_RR=1): its own instantiation */          \
             return launch<LL>(fuchs_shared_kernel<LL, CfgShared<LL>::TPB, true>, p, p.batch, s, CfgShared<LL>::TPB, \
                               Sizes<LL>::SMEM_SHARED_PER_THREAD * CfgShared<LL>::TPB);                     \
+        if (p.sched && use_persistent<LL>(p.batch, sms)) {                                                 \
+            constexpr int PT = CfgShared<LL>::TPB_BIG;                                                     \
+            cudaError_t e = cudaFuncSetAttribute(fuchs_shared_persistent_kernel<LL, PT>,                   \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                                 (int)(Sizes<LL>::SMEM_SHARED_PER_THREAD * PT));            \
+            if (e != cudaSuccess) return (int)e;                                                           \
+            int64_t nblocks = (p.batch + PT - 1) / PT;                                                     \
+            e = cudaMemsetAsync(p.sched, 0, sizeof(int) * (size_t)(nblocks + 1), s);                       \
+            if (e != cudaSuccess) return (int)e;                                                           \
+            int grid = (int)(nblocks < sms ? nblocks : sms);                                               \
+            fuchs_shared_persistent_kernel<LL, PT><<<grid, PT, Sizes<LL>::SMEM_SHARED_PER_THREAD * PT, s>>>(p); \
+            return (int)cudaGetLastError();                                                                \
+        }                                                                                                  \
         int choice = choose_block_size<LL>(p.batch, sms);                                                  \
         if (choice == 2)                                                                                   \
             return launch<LL>(fuchs_shared_kernel<LL, CfgShared<LL>::TPB_HUGE>, p, p.batch, s, CfgShared<LL>::TPB_HUGE, \

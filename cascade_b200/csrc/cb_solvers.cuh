@@ -353,6 +353,9 @@ struct FuchsSharedParams {
     int no_rr;        // development switch (CB200_NO_RR=1): skip the reduced-radix products
     unsigned long long* stats;  // development counters (CB200_RR_STATS=1) or nullptr: [0] rr accepted, [1] rr rejected
     int64_t n_begin;  // first coefficient this launch computes (>= -valuation); earlier ones are already in res
+    // persistent launch (cb_kernels.cuh): work units of range_len coefficients x one block of instances
+    int64_t range_len;
+    int* sched;  // [0] unit counter, [1 + b] ranges completed for instance block b (zeroed before the launch)
 };
 struct RecCtl {
     bool rr;

@@ -75,7 +75,7 @@ int cbsim_fuchs_batch_range(int L_, int order, int degree, int valuation, int64_
         SIM_DISPATCH(L_, run<L>(rows - tp.row0, [&](int64_t i, Scratch<1> a, Scratch<1> b) { fuchs_table_thread<L>(tp, i + tp.row0, a, b); }));
         FuchsSharedParams sp;
         sp.order = order; sp.degree = degree; sp.valuation = valuation; sp.n = n; sp.batch = batch;
-        sp.tbl = tp.tbl; sp.res = p.res; sp.kind = kind.data(); sp.gcols = nullptr; sp.stats = nullptr; sp.n_begin = n_begin;
+        sp.tbl = tp.tbl; sp.res = p.res; sp.kind = kind.data(); sp.gcols = nullptr; sp.stats = nullptr; sp.n_begin = n_begin; sp.sched = nullptr; sp.range_len = 32;
         { const char* e = getenv("CB200_RR"); sp.no_rr = (e && e[0] == '1') ? 0 : 1; }  // as cb200_fuchs_batch_dev
         // columns sized EXACTLY as on the device (cb_kernels.cuh Sizes<L>), each followed by a
         // canary zone, so an out-of-column access is caught here and not only on the GPU

@@ -120,3 +120,13 @@ def test_ode_apply(oracle, gpu_driver, L):
 @pytest.mark.parametrize("L", [4, 32, 64])
 def test_frobenius_general_edge(oracle, gpu_driver, L):
     cases.case_frobenius_general_edge(oracle, gpu_driver, L)
+
+
+@pytest.mark.parametrize("batch", [385, 1000])
+def test_persistent_recurrence_kernel(oracle, gpu_driver, monkeypatch, batch):
+    """The persistent form of the recurrence kernel (work units = instance block x coefficient range, one CTA per
+    SM; chosen by itself for batches beyond one wave of 384-thread blocks) forced onto small ragged batches:
+    several ranges, idle lanes in the last block, bit-identical to the oracle."""
+    monkeypatch.setenv("CB200_PERSISTENT", "1")
+    cases.case_fuchs_bessel_shared(oracle, gpu_driver, 32, seed=5, n=75, batch=batch)
+    cases.case_fuchs_shared_adversarial(oracle, gpu_driver, 32, seed=109, batch=70)
