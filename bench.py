@@ -326,9 +326,10 @@ def main():
     achieved = macs / (kernel_ms * 1e-3) / 1e12
     bytes_out = coeffs_per_gpu * 2 * (4 * L + 16)
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    # DRAM bytes per launch of the recurrence kernel, ncu --set full on this exact config
-    # (profiles/ncu_fuchs_shared_bench_r01.txt: 0.30 GB read + 37.78 GB written); null for other sizes
-    traffic = 38.08e9 if (batch == BATCH and n == N_TERMS) else None
+    # DRAM bytes per launch of the recurrence kernel, ncu on this exact config (profiles/ncu_fuchs_shared_bench_r01.txt:
+    # persistent kernel, 10.2 GB read + 41.2 GB written: work units migrate between SMs, so part of the 4-coefficient
+    # window comes back from DRAM instead of L2); null for other sizes
+    traffic = 51.47e9 if (batch == BATCH and n == N_TERMS) else None
     roofline = {"bound": "imad", "achieved": achieved, "peak": imad_peak, "unit": "T limb-MAC/s",
                 "frac": achieved / imad_peak, "traffic": traffic, "algorithmic_bytes": bytes_out,
                 "peak_source": "measured plain IMAD.WIDE.U32 rate, profiles/imad_peak_r01.json "

@@ -59,7 +59,7 @@ bool factor_fits(int64_t n, int order) {
 // columns of the general-path scratch: the batch padded to whole blocks of the persistent launch (which gives the
 // idle lanes of a ragged last block columns of their own)
 static_assert(CfgShared<32>::TPB_BIG == 384, "gcols_columns pads to the persistent block size");
-size_t gcols_columns(int64_t batch) { return (size_t)((batch + 383) / 384 * 384); }
+size_t gcols_columns(int64_t batch) { return (size_t)(batch + 512); }
 
 struct DevBuf {
     void* p = nullptr;

@@ -155,14 +155,13 @@ __global__ void __launch_bounds__(TPB, 1) fuchs_shared_persistent_kernel(FuchsSh
         const int64_t b = u % nblocks, r = u / nblocks;
         int64_t inst = b * TPB + threadIdx.x;
         if (inst >= p.batch) inst = p.batch - 1;
-        FuchsSharedParams q = p;
-        q.n_begin = first + r * p.range_len;
-        q.n = q.n_begin + p.range_len - 1 < p.n ? q.n_begin + p.range_len - 1 : p.n;
+        const int64_t lo = first + r * p.range_len;
+        const int64_t hi = lo + p.range_len - 1 < p.n ? lo + p.range_len - 1 : p.n;
         // every thread -- idle lanes included -- owns a column of the (padded) general-path scratch
         const size_t gstride = (size_t)nblocks * TPB, gi = (size_t)b * TPB + threadIdx.x;
         GScratch G0{p.gcols + gi, gstride};
         GScratch G1{p.gcols + (size_t)Sizes<L>::WORDS * gstride + gi, gstride};
-        fuchs_shared_thread<L, false, true>(q, inst, S0, S1, A0, A1, A2, G0, G1);
+        fuchs_shared_thread<L, false, true>(p, inst, S0, S1, A0, A1, A2, G0, G1, lo, hi);
         __threadfence();  // this thread's coefficients are visible device-wide before the block reports the range
         __syncthreads();
         if (threadIdx.x == 0) atomicExch(p.sched + 1 + b, (int)(r + 1));
@@ -187,7 +186,8 @@ __global__ void __launch_bounds__(IntopCfg<L>::TPB, 1) fuchs_intop_kernel(FuchsI
 // time of a launch is proportional to (number of waves) x (instances per SM per wave) / throughput;
 // relative per-SM throughputs measured on B200 (7, 12 and 14 warps per SM)
 // (measured, 98-coefficient runs: 224 threads 21.7 instances/ms/SM, 384 threads 23.4 -- 25.9 with the phase
-// barriers it is built with --, 448 threads -- 128 registers, 532 B of spills -- 21.4: never chosen)
+// barriers it is built with --, 448 threads -- 128 registers, 532 B of spills -- 21.4: never chosen; persistent
+// launches at the full BASELINE size: 384 threads 317 ms, 352 340 ms, 416 400 ms, 448 382 ms)
 constexpr double THR_BIG = 1.19, THR_HUGE = 0.98;
 // 0: TPB, 1: TPB_BIG, 2: TPB_HUGE.  CB200_TPB_CHOICE=0/1/2 in the environment overrides (development)
 template <int L>
@@ -207,6 +207,19 @@ int choose_block_size(int64_t batch, int sms) {
     }
     if (CfgShared<L>::TPB_HUGE != CfgShared<L>::TPB && cost(CfgShared<L>::TPB_HUGE, THR_HUGE) < c) best = 2;
     return best;
+}
+
+template <int L, int PT>
+int launch_persistent(const FuchsSharedParams& p, int sms, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(fuchs_shared_persistent_kernel<L, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(Sizes<L>::SMEM_SHARED_PER_THREAD * PT));
+    if (e != cudaSuccess) return (int)e;
+    int64_t nblocks = (p.batch + PT - 1) / PT;
+    e = cudaMemsetAsync(p.sched, 0, sizeof(int) * (size_t)(nblocks + 1), s);
+    if (e != cudaSuccess) return (int)e;
+    int grid = (int)(nblocks < sms ? nblocks : sms);
+    fuchs_shared_persistent_kernel<L, PT><<<grid, PT, Sizes<L>::SMEM_SHARED_PER_THREAD * PT, s>>>(p);
+    return (int)cudaGetLastError();
 }
 
 // persistent launch: worthwhile when the batch is more than one wave of the big blocks and the fractional-wave cost
@@ -275,17 +288,7 @@ struct LaunchTable {
             return launch<LL>(fuchs_shared_kernel<LL, CfgShared<LL>::TPB, true>, p, p.batch, s, CfgShared<LL>::TPB, \
                               Sizes<LL>::SMEM_SHARED_PER_THREAD * CfgShared<LL>::TPB);                     \
         if (p.sched && use_persistent<LL>(p.batch, sms)) {                                                 \
-            constexpr int PT = CfgShared<LL>::TPB_BIG;                                                     \
-            cudaError_t e = cudaFuncSetAttribute(fuchs_shared_persistent_kernel<LL, PT>,                   \
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,              \
-                                                 (int)(Sizes<LL>::SMEM_SHARED_PER_THREAD * PT));            \
-            if (e != cudaSuccess) return (int)e;                                                           \
-            int64_t nblocks = (p.batch + PT - 1) / PT;                                                     \
-            e = cudaMemsetAsync(p.sched, 0, sizeof(int) * (size_t)(nblocks + 1), s);                       \
-            if (e != cudaSuccess) return (int)e;                                                           \
-            int grid = (int)(nblocks < sms ? nblocks : sms);                                               \
-            fuchs_shared_persistent_kernel<LL, PT><<<grid, PT, Sizes<LL>::SMEM_SHARED_PER_THREAD * PT, s>>>(p); \
-            return (int)cudaGetLastError();                                                                \
+            return launch_persistent<LL, CfgShared<LL>::TPB_BIG>(p, sms, s);                               \
         }                                                                                                  \
         int choice = choose_block_size<LL>(p.batch, sms);                                                  \
         if (choice == 2)                                                                                   \

@@ -401,15 +401,18 @@ CB_HD Meta rec_fdot2(DST dst, Opd x1, OpdS y1, Opd x2, OpdS y2, bool neg2, SCR S
 // default kernel 50 registers and spills)
 template <int L, bool RR = false, bool SYNC = false, class SCR>
 CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0, SCR S1, SCR A0, SCR A1,
-                               SCR A2, GScratch G0, GScratch G1) {
+                               SCR A2, GScratch G0, GScratch G1, int64_t n_from = -1, int64_t n_to = -1) {
     const size_t slot = 2 * (size_t)inst;
     const int v = p.valuation, W = p.degree - v;
     SCR accRe = A0, accIm = A1, spare = A2;
     const RecCtl ctl{p.no_rr == 0, p.stats};
     // every coefficient is formed from the W previous ones read back from res, so the recurrence can be
     // resumed at any index: a caller may solve in coefficient ranges and stream finished rows out meanwhile
+    // (n_from, n_to): the coefficient range of a persistent work unit; otherwise the launch's own range
+    const int64_t b_first = n_from >= 0 ? n_from : (p.n_begin > -v ? p.n_begin : -v);
+    const int64_t b_last = n_from >= 0 ? n_to : p.n;
 #pragma unroll 1
-    for (int64_t bmax = (p.n_begin > -v ? p.n_begin : -v); bmax <= p.n; bmax++) {
+    for (int64_t bmax = b_first; bmax <= b_last; bmax++) {
         int64_t e = bmax + v;
         int64_t bmin = clampi(e - p.degree, 0, bmax);
         int cnt = (int)(bmax - bmin);
