@@ -69,6 +69,12 @@ struct DevBuf {
 
 }  // namespace
 
+#define CUDA_RET(x)                          \
+    do {                                     \
+        cudaError_t e_ = (x);                \
+        if (e_ != cudaSuccess) return (int)e_; \
+    } while (0)
+
 extern "C" {
 
 const char* cb200_version(void) { return "cascade_b200 0.1 (sm_100a)"; }
@@ -211,7 +217,33 @@ int cb200_fuchs_intop_batch_dev(int L_, int order, int degree, int valuation, in
     p.ode = ode_int;
     p.ostride = shared_ode ? 0 : (size_t)batch;
     p.res = CArr{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
+    p.range_len = 32;
+    p.sched = nullptr;
     g_launches.fetch_add(batch > 0);
+    // more than one wave of blocks with a ragged last wave: run the persistent form (work units of one instance
+    // block x 32 coefficients, one CTA per SM) on a stream-ordered scheduling buffer
+    {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int tpb = L_ <= 32 ? 384 : (L_ == 64 ? 192 : 96);  // IntopCfg<L>::TPB
+        int64_t nblocks = (batch + tpb - 1) / tpb, waves = (nblocks + sms - 1) / sms;
+        const char* e = getenv("CB200_PERSISTENT");
+        bool want = nblocks > sms && (double)(waves * sms - nblocks) > 0.04 * (double)nblocks;
+        if (e && e[0] == '0') want = false;
+        if (e && e[0] == '1') want = true;
+        if (want) {
+            int* sched = nullptr;
+            cudaStream_t st = (cudaStream_t)stream;
+            if (cudaMallocAsync((void**)&sched, sizeof(int) * (size_t)(nblocks + 1), st) == cudaSuccess) {
+                CUDA_RET(cudaMemsetAsync(sched, 0, sizeof(int) * (size_t)(nblocks + 1), st));
+                p.sched = sched;
+                int rc = table_for(L_)->fuchs_intop(p, st);
+                cudaFreeAsync(sched, st);
+                return rc;
+            }
+            (void)cudaGetLastError();  // no stream-ordered allocator: fall through to the whole-wave launch
+        }
+    }
     return table_for(L_)->fuchs_intop(p, (cudaStream_t)stream);
 }
 
@@ -444,12 +476,6 @@ int cb200_ew_dev(int op, int L_, int64_t n, uint32_t* z_mant, cb_meta* z_meta, c
     g_launches.fetch_add(n > 0);
     return table_for(L_)->ew(p, (cudaStream_t)stream);
 }
-
-#define CUDA_RET(x)                          \
-    do {                                     \
-        cudaError_t e_ = (x);                \
-        if (e_ != cudaSuccess) return (int)e_; \
-    } while (0)
 
 // ------------------------------------------------------------------ analytic continuation
 size_t cb200_continuation_workspace_bytes(int L, int order, int degree, int64_t n, int64_t batch) {

@@ -183,6 +183,45 @@ __global__ void __launch_bounds__(IntopCfg<L>::TPB, 1) fuchs_intop_kernel(FuchsI
     fuchs_intop_thread<L>(p, idx, S0, A0, A1, A2);
 }
 
+// persistent form of the integer-operator kernel (same work-unit scheme as fuchs_shared_persistent_kernel; the
+// thread body has no barriers, so idle lanes of a ragged last block simply skip the work)
+template <int L>
+__global__ void __launch_bounds__(IntopCfg<L>::TPB, 1) fuchs_intop_persistent_kernel(FuchsIntParams p) {
+    extern __shared__ uint32_t cb_smem[];
+    __shared__ int unit_s;
+    constexpr int TPB = IntopCfg<L>::TPB;
+    constexpr uint32_t W0 = L + 3, AW = L + 2;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cb_smem) + 4u * threadIdx.x;
+    Scratch<TPB> S0{sbase}, A0{sbase + 4u * W0 * TPB}, A1{sbase + 4u * (W0 + AW) * TPB},
+        A2{sbase + 4u * (W0 + 2 * AW) * TPB};
+    const int64_t nblocks = (p.batch + TPB - 1) / TPB;
+    const int64_t first = -p.valuation;
+    const int64_t nranges = (p.n - first + p.range_len) / p.range_len;
+    const int64_t total = nblocks * nranges;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            int u = atomicAdd(p.sched, 1);
+            if (u < total) {
+                int64_t b = u % nblocks, r = u / nblocks;
+                while (r > 0 && atomicAdd(p.sched + 1 + b, 0) < (int)r) __nanosleep(200);
+                __threadfence();
+            }
+            unit_s = u;
+        }
+        __syncthreads();
+        const int64_t u = unit_s;
+        if (u >= total) break;
+        const int64_t b = u % nblocks, r = u / nblocks;
+        const int64_t inst = b * TPB + threadIdx.x;
+        const int64_t lo = first + r * p.range_len;
+        const int64_t hi = lo + p.range_len - 1 < p.n ? lo + p.range_len - 1 : p.n;
+        if (inst < p.batch) fuchs_intop_thread<L>(p, inst, S0, A0, A1, A2, lo, hi);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicExch(p.sched + 1 + b, (int)(r + 1));
+    }
+}
+
 // time of a launch is proportional to (number of waves) x (instances per SM per wave) / throughput;
 // relative per-SM throughputs measured on B200 (7, 12 and 14 warps per SM)
 // (measured, 98-coefficient runs: 224 threads 21.7 instances/ms/SM, 384 threads 23.4 -- 25.9 with the phase
@@ -301,8 +340,19 @@ struct LaunchTable {
                           Sizes<LL>::SMEM_SHARED_PER_THREAD * CfgShared<LL>::TPB);                         \
     }                                                                                                      \
     static int fint_##LL(const FuchsIntParams& p, cudaStream_t s) {                                        \
-        return launch<LL>(fuchs_intop_kernel<LL>, p, p.batch, s, IntopCfg<LL>::TPB,                          \
-                          (size_t)(LL + 3 + 3 * (LL + 2)) * IntopCfg<LL>::TPB * sizeof(uint32_t));           \
+        const size_t smem = (size_t)(LL + 3 + 3 * (LL + 2)) * IntopCfg<LL>::TPB * sizeof(uint32_t);        \
+        if (p.sched) { /* persistent launch: no last-wave tail */                                          \
+            int dev = 0, sms = 148;                                                                        \
+            if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); \
+            cudaError_t e = cudaFuncSetAttribute(fuchs_intop_persistent_kernel<LL>,                        \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+            if (e != cudaSuccess) return (int)e;                                                           \
+            int64_t nblocks = (p.batch + IntopCfg<LL>::TPB - 1) / IntopCfg<LL>::TPB;                       \
+            int grid = (int)(nblocks < sms ? nblocks : sms);                                               \
+            fuchs_intop_persistent_kernel<LL><<<grid, IntopCfg<LL>::TPB, smem, s>>>(p);                    \
+            return (int)cudaGetLastError();                                                                \
+        }                                                                                                  \
+        return launch<LL>(fuchs_intop_kernel<LL>, p, p.batch, s, IntopCfg<LL>::TPB, smem);                 \
     }                                                                                                      \
     static int frobg_##LL(const FrobGenParams& p, cudaStream_t s) { return launch<LL>(frobenius_general_kernel<LL>, p, p.batch, s); } \
     static int solop_##LL(const SolOpParams& p, cudaStream_t s) { return launch<LL>(solution_op_kernel<LL>, p, p.batch, s); } \

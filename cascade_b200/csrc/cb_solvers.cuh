@@ -509,19 +509,25 @@ struct FuchsIntParams {
     const int64_t* ode;  // [(order+1)(degree+1)][batch] (ostride = batch) or [..][1] shared (ostride = 0)
     size_t ostride;
     CArr res;
+    // persistent launch (cb_kernels.cuh): see FuchsSharedParams
+    int64_t range_len;
+    int* sched;
 };
 constexpr int INTOP_MAXENT = 36;  // (order+1)(degree+1) <= 36
 
 template <int L, class SCR>
-CB_HD void fuchs_intop_thread(const FuchsIntParams& p, int64_t inst, SCR S0, SCR A0, SCR A1, SCR A2) {
+CB_HD void fuchs_intop_thread(const FuchsIntParams& p, int64_t inst, SCR S0, SCR A0, SCR A1, SCR A2,
+                              int64_t n_from = -1, int64_t n_to = -1) {
     const size_t slot = 2 * (size_t)inst;
     const int v = p.valuation, D1 = p.degree + 1;
     const int ne = (p.order + 1) * D1;
     int64_t P[INTOP_MAXENT];
     for (int e = 0; e < ne; e++) P[e] = p.ode[(size_t)e * (p.ostride ? p.ostride : 1) + (p.ostride ? (size_t)inst : 0)];
     SCR accRe = A0, accIm = A1, spare = A2;
+    // (n_from, n_to): the coefficient range of a persistent work unit (the recurrence resumes from res)
+    const int64_t b_first = n_from >= 0 ? n_from : -v, b_last = n_from >= 0 ? n_to : p.n;
 #pragma unroll 1
-    for (int64_t bmax = -v; bmax <= p.n; bmax++) {
+    for (int64_t bmax = b_first; bmax <= b_last; bmax++) {
         Meta tRe = meta_zero(), tIm = meta_zero();
         int64_t e = bmax + v;
         int64_t bmin = clampi(e - p.degree, 0, bmax);

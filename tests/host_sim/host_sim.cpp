@@ -108,7 +108,7 @@ int cbsim_fuchs_intop_batch(int L_, int order, int degree, int valuation, int64_
     if (valuation >= 0) return CB200_EVALUATION;
     FuchsIntParams p;
     p.order = order; p.degree = degree; p.valuation = valuation; p.n = n; p.batch = batch;
-    p.ode = ode_int; p.ostride = shared_ode ? 0 : (size_t)batch;
+    p.ode = ode_int; p.ostride = shared_ode ? 0 : (size_t)batch; p.sched = nullptr; p.range_len = 32;
     p.res = CArr{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
     const size_t sizes[4] = {(size_t)L_ + 3, (size_t)L_ + 2, (size_t)L_ + 2, (size_t)L_ + 2};
     const size_t CAN = 64;

@@ -130,3 +130,10 @@ def test_persistent_recurrence_kernel(oracle, gpu_driver, monkeypatch, batch):
     monkeypatch.setenv("CB200_PERSISTENT", "1")
     cases.case_fuchs_bessel_shared(oracle, gpu_driver, 32, seed=5, n=75, batch=batch)
     cases.case_fuchs_shared_adversarial(oracle, gpu_driver, 32, seed=109, batch=70)
+
+
+@pytest.mark.parametrize("L", [32, 64])
+def test_persistent_integer_operator_kernel(oracle, gpu_driver, monkeypatch, L):
+    """The persistent form of the integer-operator (Legendre sweep) kernel, forced onto a small batch."""
+    monkeypatch.setenv("CB200_PERSISTENT", "1")
+    cases.case_fuchs_integer_operators(oracle, gpu_driver, L, seed=15 + L)
