@@ -125,6 +125,14 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
 
+    # exactly ONE line on stdout: everything libraries print (NCCL's version banner, warnings) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -152,7 +160,7 @@ def main():
                                  "sample": f"{sample_batch} instances x {args.terms - 1} coefficients per step, "
                                            "oracle port (Cascade loops on GMP 6.3 mpn); Cascade+Arb itself is not buildable here"},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -350,7 +358,7 @@ def main():
             "vs_baseline": None, "dtype": "u32 limbs (1024-bit ball)", "data": "synthetic", "config": config,
             "clocks": summarise_clocks(samples), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
