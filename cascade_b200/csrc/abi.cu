@@ -166,6 +166,7 @@ int cb200_fuchs_batch_range_dev(int L_, int order, int degree, int valuation, in
         w += align256((size_t)2 * (2 * L_ + 3) * gcols_columns(batch) * sizeof(uint32_t));
         sp.sched = (int*)w;  // unit counter + one progress word per instance block (persistent launch)
         sp.range_len = 32;
+        if (const char* re = getenv("CB200_RANGE")) { int v = atoi(re); if (v >= 4 && v <= 4096) sp.range_len = v; }  // development
         sp.n_begin = n_begin;
         {
             // the reduced-radix fused dot product (cb_rr.cuh) is bit-identical but measured slower than

@@ -60,10 +60,14 @@ def test_full_config_sampled_parity(oracle):
         assert oracle.ode_solves(2, 2, ode, series, 200)
 
 
-def test_coefficient_ranges_match_one_call():
+@pytest.mark.parametrize("persistent", ["0", "1"])
+def test_coefficient_ranges_match_one_call(monkeypatch, persistent):
     """cb200_fuchs_batch_range_dev: solving coefficient ranges one after the other (what bench.py's end-to-end
-    leg does to overlap the copy-out) leaves exactly the bytes of a single full call."""
+    leg does to overlap the copy-out) leaves exactly the bytes of a single full call -- with whole-wave launches
+    and with the persistent kernel (whose work units then start at the range's first coefficient)."""
     import torch
+
+    monkeypatch.setenv("CB200_PERSISTENT", persistent)
 
     import bench
     from cascade_b200 import _lib, api
