@@ -222,3 +222,38 @@ def test_exp_log_enclose_mpmath(oracle, L):
             mag = abs(tv)
             if mag != 0:
                 assert to_mp(z.rad(2 * i)) <= mag * mp.mpf(2) ** (-(32 * L - 40)), (name, i)
+
+
+def test_solution_evaluate_encloses_mpmath(oracle):
+    """acb_ode_solution_evaluate (reference src/acb_ode_solution.c:24-58; property of reference
+    tests/solution_eval.c): a^rho * sum_i w_i gens[i](a) log(a)^(M-1-i) with the weights the reference codes,
+    w_0 = 1, w_i = w_{i-1} (M - i + 1) / i, evaluated independently with mpmath on exact (dyadic) inputs."""
+    import mpmath as mp
+    from cascade_b200 import api
+    L, M, cap = 32, 3, 6
+    mp.mp.prec = 32 * L + 300
+    rng = np.random.default_rng(21)
+    dy = lambda: (F(int(rng.integers(-64, 64)), 32), F(int(rng.integers(-64, 64)), 32))
+    gvals = [[dy() for _ in range(cap)] for _ in range(M)]
+    gens = from_complex([v for row in gvals for v in row], L)
+    pts_v = [(F(3, 4), F(1, 8)), (F(-5, 16), F(7, 8)), (F(1, 2), 0)]
+    pts = from_complex(pts_v, L)
+    to_mp = lambda q: mp.mpf(q.numerator) / q.denominator
+    for rho_v in ((F(0), F(0)), (F(3), F(0)), (F(1, 4), F(-3, 8))):
+        rho = from_complex([rho_v], L)
+        mode, e = api.pow_mode_of(rho)
+        out = oracle.solution_evaluate(gens, M, rho, mode, e, pts)
+        for p, (ar, ai) in enumerate(pts_v):
+            a = mp.mpc(to_mp(ar), to_mp(ai))
+            la = mp.log(a)
+            tot, w = mp.mpc(0), 1
+            for i in range(M):
+                if i:
+                    w = w * (M - i + 1) // i
+                gi = sum(mp.mpc(to_mp(c[0]), to_mp(c[1])) * a ** k for k, c in enumerate(gvals[i]))
+                tot += w * gi * la ** (M - 1 - i)
+            tot *= a ** mp.mpc(to_mp(rho_v[0]), to_mp(rho_v[1]))
+            for part, t in ((0, tot.real), (1, tot.imag)):
+                s = 2 * p + part
+                assert abs(to_mp(out.mid(s)) - t) <= to_mp(out.rad(s)), (rho_v, p, part)
+                assert to_mp(out.rad(s)) <= abs(tot) * mp.mpf(2) ** (-(32 * L - 60))
