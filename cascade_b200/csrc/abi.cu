@@ -61,6 +61,15 @@ bool factor_fits(int64_t n, int order) {
 static_assert(CfgShared<32>::TPB_BIG == 384, "gcols_columns pads to the persistent block size");
 size_t gcols_columns(int64_t batch) { return (size_t)(batch + 512); }
 
+// rows of the per-instance table held at a time: about 4 GB of table, at least 8 rows, at most all of them
+int64_t pi_table_rows(int L, int64_t W, int64_t rows, int64_t batch) {
+    double per_row = (double)(W + 2) * 2.0 * batch * (4.0 * L + 16.0);
+    int64_t rt = (int64_t)(4.0e9 / (per_row > 1 ? per_row : 1));
+    if (rt < 8) rt = 8;
+    if (rt > rows) rt = rows;
+    return rt > 0 ? rt : 1;
+}
+
 struct DevBuf {
     void* p = nullptr;
     ~DevBuf() { if (p) cudaFree(p); }
@@ -103,7 +112,14 @@ int cb200_debug_rr_stats(uint64_t* out) {
 size_t cb200_fuchs_workspace_bytes(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
                                    int shared_ode) {
     (void)order;
-    if (!shared_ode || valuation >= 0) return carve_bytes(L, FUCHS_NTMP, 2 * batch);
+    if (valuation >= 0) return carve_bytes(L, FUCHS_NTMP, 2 * batch);
+    if (!shared_ode) {
+        // a table row per instance, built for one range of coefficient rows at a time
+        int64_t W = degree - valuation, rt = pi_table_rows(L, W, n + 1 + valuation, batch);
+        return carve_bytes(L, rt * (W + 2), 2 * batch) + carve_bytes(L, 2, 2 * rt * batch) +
+               align256(sizeof(int32_t) * (size_t)(rt * batch + 1)) +
+               align256((size_t)2 * (2 * L + 3) * gcols_columns(batch) * sizeof(uint32_t));
+    }
     int64_t rows = n + 1 + valuation, W = degree - valuation;
     if (rows < 0) rows = 0;
     return carve_bytes(L, rows * (W + 2), 2) + carve_bytes(L, 2, 2 * rows) + align256(sizeof(int32_t) * (rows + 1)) +
@@ -127,7 +143,6 @@ int cb200_fuchs_batch_range_dev(int L_, int order, int degree, int valuation, in
                                 cb_meta* res_meta, void* workspace, size_t workspace_bytes, void* stream) {
     if (!supported_L(L_) || order < 1 || degree < 0 || batch < 0 || n < 0 || n_begin < 0) return CB200_EINVAL;
     if (valuation >= 0) return CB200_EVALUATION;
-    if (!shared_ode && n_begin > -valuation) return CB200_EINVAL;  // ranges: shared-operator path only
     if (n_begin < -valuation) n_begin = -valuation;
     if (n_begin > n) return 0;
     if (!factor_fits(n, order)) return CB200_ERANGE;
@@ -149,6 +164,9 @@ int cb200_fuchs_batch_range_dev(int L_, int order, int degree, int valuation, in
         tp.tmp = carve(w, L_, 2, 2 * rows);
         tp.kind = (int32_t*)w;
         tp.row0 = n_begin + valuation;
+        tp.nrows = rows - tp.row0;
+        tp.ninst = 1;
+        tp.tbl_row0 = 0;
         w += align256(sizeof(int32_t) * (rows + 1));
         g_launches.fetch_add(1);
         int rc = table_for(L_)->fuchs_table(tp, (cudaStream_t)stream);
@@ -165,6 +183,9 @@ int cb200_fuchs_batch_range_dev(int L_, int order, int degree, int valuation, in
         sp.gcols = (uint32_t*)w;
         w += align256((size_t)2 * (2 * L_ + 3) * gcols_columns(batch) * sizeof(uint32_t));
         sp.sched = (int*)w;  // unit counter + one progress word per instance block (persistent launch)
+        sp.tbl_row0 = 0;
+        sp.kind_stride = 1;
+        sp.per_inst = 0;
         sp.range_len = 32;
         if (const char* re = getenv("CB200_RANGE")) { int v = atoi(re); if (v >= 4 && v <= 4096) sp.range_len = v; }  // development
         sp.n_begin = n_begin;
@@ -186,19 +207,60 @@ int cb200_fuchs_batch_range_dev(int L_, int order, int degree, int valuation, in
         g_launches.fetch_add(batch > 0);
         return table_for(L_)->fuchs_shared(sp, (cudaStream_t)stream);
     }
-    FuchsParams p;
-    p.order = order;
-    p.degree = degree;
-    p.valuation = valuation;
-    p.n = n;
-    p.batch = batch;
-    p.ode = CArr{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta),
-                 shared_ode ? (size_t)2 : (size_t)(2 * batch)};
-    p.res = CArr{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
-    char* w = (char*)workspace;
-    p.tmp = carve(w, L_, FUCHS_NTMP, 2 * batch);
-    g_launches.fetch_add(batch > 0);
-    return table_for(L_)->fuchs(p, (cudaStream_t)stream);
+    // an operator per instance (parameter sweeps): the same two kernels, with a table row per instance built for
+    // one range of coefficients at a time (the rows of a range are independent of each other, so the divisions of
+    // src/fuchs_solver.c:137 run massively parallel instead of inside the sequential recurrence)
+    {
+        const int64_t rows = n + 1 + valuation, W = degree - valuation, S = 2 * batch;
+        const int64_t rt = pi_table_rows(L_, W, rows, batch);
+        char* w = (char*)workspace;
+        CArr tbl = carve(w, L_, rt * (W + 2), S);
+        CArr ttmp = carve(w, L_, 2, 2 * rt * batch);
+        int32_t* kind = (int32_t*)w;
+        w += align256(sizeof(int32_t) * (size_t)(rt * batch + 1));
+        uint32_t* gcols = (uint32_t*)w;
+        for (int64_t lo = n_begin; lo <= n; lo += rt) {
+            const int64_t hi = lo + rt - 1 < n ? lo + rt - 1 : n;
+            FuchsTableParams tp;
+            tp.order = order;
+            tp.degree = degree;
+            tp.valuation = valuation;
+            tp.n = n;
+            tp.ode = CArr{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta), (size_t)S};
+            tp.tbl = tbl;
+            tp.tmp = ttmp;
+            tp.kind = kind;
+            tp.row0 = lo + valuation;
+            tp.nrows = hi - lo + 1;
+            tp.ninst = batch;
+            tp.tbl_row0 = lo + valuation;
+            g_launches.fetch_add(batch > 0);
+            int rc = table_for(L_)->fuchs_table(tp, (cudaStream_t)stream);
+            if (rc) return rc;
+            FuchsSharedParams sp;
+            sp.order = order;
+            sp.degree = degree;
+            sp.valuation = valuation;
+            sp.n = hi;
+            sp.batch = batch;
+            sp.tbl = tbl;
+            sp.res = CArr{res_mant, (Meta*)res_meta, (size_t)S};
+            sp.kind = kind;
+            sp.gcols = gcols;
+            sp.no_rr = 1;
+            sp.stats = nullptr;
+            sp.n_begin = lo;
+            sp.range_len = 32;
+            sp.sched = nullptr;
+            sp.tbl_row0 = lo + valuation;
+            sp.kind_stride = batch;
+            sp.per_inst = 1;
+            g_launches.fetch_add(batch > 0);
+            rc = table_for(L_)->fuchs_shared(sp, (cudaStream_t)stream);
+            if (rc) return rc;
+        }
+        return 0;
+    }
 }
 
 int cb200_fuchs_intop_batch_dev(int L_, int order, int degree, int valuation, int64_t n, int64_t batch,

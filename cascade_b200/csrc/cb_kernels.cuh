@@ -100,10 +100,10 @@ __global__ void __launch_bounds__(Cfg<L>::TPB, 1) ew_kernel(EwParams p) {
 
 template <int L>
 __global__ void __launch_bounds__(Cfg<L>::TPB, 1) fuchs_table_kernel(FuchsTableParams p) {
-    CB_KERNEL_PROLOGUE(p.n + 1 + p.valuation - p.row0)
-    fuchs_table_thread<L>(p, idx + p.row0, S0, S1);
+    CB_KERNEL_PROLOGUE(p.nrows * p.ninst)
+    fuchs_table_thread<L>(p, idx, S0, S1);
 }
-template <int L, int TPB, bool RR = false, bool SYNC = false>
+template <int L, int TPB, bool RR = false, bool SYNC = false, bool PI = false>
 __global__ void __launch_bounds__(TPB, 1) fuchs_shared_kernel(FuchsSharedParams p) {
     extern __shared__ uint32_t cb_smem[];
     constexpr uint32_t W0 = Sizes<L>::S0WORDS, W1 = Sizes<L>::S1WORDS, AW = Sizes<L>::AWORDS;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(TPB, 1) fuchs_shared_kernel(FuchsSharedParams 
     if (idx >= p.batch) return;
     GScratch G0{p.gcols + idx, (size_t)p.batch};
     GScratch G1{p.gcols + (size_t)Sizes<L>::WORDS * p.batch + idx, (size_t)p.batch};
-    fuchs_shared_thread<L, RR, SYNC>(p, idx, S0, S1, A0, A1, A2, G0, G1);
+    fuchs_shared_thread<L, RR, SYNC, PI>(p, idx, S0, S1, A0, A1, A2, G0, G1);
 }
 
 // Persistent form of the recurrence kernel.  Every coefficient is formed from coefficients read back from res, so
@@ -318,11 +318,14 @@ struct LaunchTable {
     static int horner_##LL(const HornerParams& p, cudaStream_t s) { return launch<LL>(horner_kernel<LL>, p, p.npts, s); } \
     static int ew_##LL(const EwParams& p, cudaStream_t s) { return launch<LL>(ew_kernel<LL>, p, p.n, s); }                \
     static int ftab_##LL(const FuchsTableParams& p, cudaStream_t s) {                                      \
-        return launch<LL>(fuchs_table_kernel<LL>, p, p.n + 1 + p.valuation - p.row0, s);                            \
+        return launch<LL>(fuchs_table_kernel<LL>, p, p.nrows * p.ninst, s);                            \
     }                                                                                                      \
     static int fsh_##LL(const FuchsSharedParams& p, cudaStream_t s) {                                      \
         int dev = 0, sms = 148;                                                                            \
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); \
+        if (p.per_inst) /* a table row per instance (operators differ between instances) */                \
+            return launch<LL>(fuchs_shared_kernel<LL, CfgShared<LL>::TPB, false, false, true>, p, p.batch, s,       \
+                              CfgShared<LL>::TPB, Sizes<LL>::SMEM_SHARED_PER_THREAD * CfgShared<LL>::TPB);  \
         if (use_rr<LL>() && !p.no_rr) /* opt-in experiment (CB200_RR=1): its own instantiation */          \
             return launch<LL>(fuchs_shared_kernel<LL, CfgShared<LL>::TPB, true>, p, p.batch, s, CfgShared<LL>::TPB, \
                               Sizes<LL>::SMEM_SHARED_PER_THREAD * CfgShared<LL>::TPB);                     \

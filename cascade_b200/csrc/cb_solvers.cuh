@@ -14,6 +14,7 @@
 // the whole batch.  A thread reads/writes only its own slots (and shared data), so no
 // synchronisation between threads is needed anywhere.
 #pragma once
+#include <type_traits>
 #include "cb_arith.cuh"
 
 // Block-wide phase alignment of the recurrence kernel: the hot loop is ~64 KB of straight-line code, twice the
@@ -72,6 +73,14 @@ CB_HD OpdS im_of_shared(const CRef& x) { return OpdS{RFix<2>{x.m + 1}, ld_meta(x
 CB_HD Opd dyn(const OpdS& o) { return Opd{o.r.dyn(), o.t}; }
 CB_HD WRef wre(const CRef& x) { return WRef{x.m, x.stride}; }
 CB_HD WRef wim(const CRef& x) { return WRef{x.m + 1, x.stride}; }
+
+// a table operand: fixed-stride view for a table shared by the batch, strided view for a per-instance table
+template <class YO> CB_HD YO y_re(const CRef& x);
+template <class YO> CB_HD YO y_im(const CRef& x);
+template <> CB_HD OpdS y_re<OpdS>(const CRef& x) { return re_of_shared(x); }
+template <> CB_HD OpdS y_im<OpdS>(const CRef& x) { return im_of_shared(x); }
+template <> CB_HD Opd y_re<Opd>(const CRef& x) { return re_of(x); }
+template <> CB_HD Opd y_im<Opd>(const CRef& x) { return im_of(x); }
 
 // does this precision use truncated products (with the exact path as per-lane fallback)?
 template <int L>
@@ -293,38 +302,44 @@ CB_HD void fuchs_thread(const FuchsParams& p, int64_t inst, SCR S0, SCR S1) {
 struct FuchsTableParams {
     int order, degree, valuation;
     int64_t n;
-    CArr ode;   // S = 2
-    CArr tbl;   // (n + 1 + v) * (W + 2) entries, S = 2
-    CArr tmp;   // 2 entries, S = 2 * (n + 1 + v)   (per table thread)
-    int32_t* kind;
-    int64_t row0;  // first table row computed by this launch (rows row0 .. n + v)
+    CArr ode;   // S = 2 (one operator for the batch) or 2 * ninst (an operator per instance)
+    CArr tbl;   // (rows held) * (W + 2) entries, S = 2 or 2 * ninst
+    CArr tmp;   // 2 entries, S = 2 * (rows of this launch * ninst)   (per table thread)
+    int32_t* kind;  // [rows held][ninst]
+    int64_t row0;   // first table row computed by this launch (rows row0 .. row0 + nrows - 1)
+    int64_t nrows;
+    int64_t ninst;     // 1: shared operator; else the batch size (per-instance operators)
+    int64_t tbl_row0;  // table row stored at entry 0 (0 for the whole-solve table; the range start for a range table)
 };
 
+// one thread per (table row, instance): idx = (row - row0) * ninst + instance
 template <int L, class SCR>
-CB_HD void fuchs_table_thread(const FuchsTableParams& p, int64_t row, SCR S0, SCR S1) {
+CB_HD void fuchs_table_thread(const FuchsTableParams& p, int64_t idx, SCR S0, SCR S1) {
     const int v = p.valuation, D1 = p.degree + 1, W = p.degree - v;
+    const int64_t inst = idx % p.ninst, row = p.row0 + idx / p.ninst;
+    const size_t oslot = (p.ode.S == 2) ? 0 : 2 * (size_t)inst, qslot = (p.tbl.S == 2) ? 0 : 2 * (size_t)inst;
     const int64_t bmax = row - v;
-    const size_t tslot = 2 * (size_t)row;
+    const size_t tslot = 2 * (size_t)idx;
     CRef t1 = at<L>(p.tmp, 0, tslot), scratch = at<L>(p.tmp, 1, tslot);
     int64_t e = bmax + v;
     int64_t bmin = clampi(e - p.degree, 0, bmax);
-    int64_t base = row * (W + 2);
-    acb_set<L>(at<L>(p.tbl, base, 0), at<L>(p.ode, 0 * D1 + (e - bmin), 0));
+    int64_t base = (row - p.tbl_row0) * (W + 2);
+    acb_set<L>(at<L>(p.tbl, base, qslot), at<L>(p.ode, 0 * D1 + (e - bmin), oslot));
     int64_t b = bmin;
     int k = 0;
-    CRef t2 = at<L>(p.tbl, base, 0);
+    CRef t2 = at<L>(p.tbl, base, qslot);
 #pragma unroll 1
     do {
         k++;
         b++;
-        t2 = at<L>(p.tbl, base + k, 0);
+        t2 = at<L>(p.tbl, base + k, qslot);
         acb_zero<L>(t2);
         int64_t fac = 1;
         int64_t imin = clampi(b - e, 0, -v);
         int64_t imax = clampi(b - bmin, 0, p.order);
 #pragma unroll 1
         for (int64_t i = imin; i <= imax; i++) {
-            acb_mul_si<L>(t1, at<L>(p.ode, i * D1 + (i + e - b), 0), fac, S0);
+            acb_mul_si<L>(t1, at<L>(p.ode, i * D1 + (i + e - b), oslot), fac, S0);
             acb_addsub<L>(t2, t2, t1, false, S0, S1);
             fac *= (b - i);
         }
@@ -333,14 +348,15 @@ CB_HD void fuchs_table_thread(const FuchsTableParams& p, int64_t row, SCR S0, SC
         acb_mul_si<L>(t2, t2, fac, S0);
     } while (b != bmax);
     Meta dim = ld_meta(t2.t + 1);
+    int32_t* kind = p.kind + (row - p.tbl_row0) * p.ninst + inst;
     if (is_exact_zero(dim)) {
-        p.kind[row] = 0;
+        *kind = 0;
     } else {
-        p.kind[row] = 1;
-        acb_inv<L>(at<L>(p.tbl, base + W + 1, 0), t2, scratch, S0, S1);
-        acb_mark_tz<L>(at<L>(p.tbl, base + W + 1, 0));
+        *kind = 1;
+        acb_inv<L>(at<L>(p.tbl, base + W + 1, qslot), t2, scratch, S0, S1);
+        acb_mark_tz<L>(at<L>(p.tbl, base + W + 1, qslot));
     }
-    for (int s = 0; s <= k; s++) acb_mark_tz<L>(at<L>(p.tbl, base + s, 0));
+    for (int s = 0; s <= k; s++) acb_mark_tz<L>(at<L>(p.tbl, base + s, qslot));
 }
 
 struct FuchsSharedParams {
@@ -356,6 +372,9 @@ struct FuchsSharedParams {
     // persistent launch (cb_kernels.cuh): work units of range_len coefficients x one block of instances
     int64_t range_len;
     int* sched;  // [0] unit counter, [1 + b] ranges completed for instance block b (zeroed before the launch)
+    // table addressing: entry 0 holds row tbl_row0; kind is [rows held][kind_stride] (kind_stride = 1 or batch)
+    int64_t tbl_row0, kind_stride;
+    int per_inst;  // the table holds a row per instance (launches the PI instantiation)
 };
 struct RecCtl {
     bool rr;
@@ -365,13 +384,19 @@ struct RecCtl {
 
 // one fused dot product of the recurrence: truncated products with the exact general path as the
 // per-lane fallback (L = 16..32), or the exact in-shared-memory version (other precisions)
-template <int L, bool RR, class SCR, class DST>
-CB_HD Meta rec_fdot2(DST dst, Opd x1, OpdS y1, Opd x2, OpdS y2, bool neg2, SCR S0, SCR S1, GScratch G0, GScratch G1,
+CB_HD Opd dyn(const Opd& o) { return o; }
+template <class YO> struct y_src;
+template <> struct y_src<OpdS> { using type = RFix<2>; };
+template <> struct y_src<Opd> { using type = RRef; };
+
+template <int L, bool RR, class SCR, class DST, class YO>
+CB_HD Meta rec_fdot2(DST dst, Opd x1, YO y1, Opd x2, YO y2, bool neg2, SCR S0, SCR S1, GScratch G0, GScratch G1,
                      RecCtl ctl = RecCtl{true, nullptr}) {
+    using YS = typename y_src<YO>::type;
     if constexpr (use_trunc<L>()) {
         bool ok = false;
         Meta t;
-        if constexpr (RR && use_rr<L>()) {
+        if constexpr (RR && use_rr<L>() && std::is_same<YO, OpdS>::value) {
             // reduced-radix products (plain IMAD.WIDE, no carry chains) first -- unless a shared
             // multiplier is zero or short (exact products: the carry-chain path knows how to trust
             // them); y1, y2 are the same for every lane, so this choice does not diverge
@@ -386,7 +411,7 @@ CB_HD Meta rec_fdot2(DST dst, Opd x1, OpdS y1, Opd x2, OpdS y2, bool neg2, SCR S
             }
         }
         if (!ok) {
-            t = arb_fdot2_trunc<L, SCR, RRef, RFix<2>>(dst, x1, y1, x2, y2, neg2, S0, &ok);
+            t = arb_fdot2_trunc<L, SCR, RRef, YS>(dst, x1, y1, x2, y2, neg2, S0, &ok);
             CB_COUNT(ok ? 4 : 5);
             if (!ok) t = arb_fdot2_general<L>(dst, x1, dyn(y1), x2, dyn(y2), neg2, G0, G1);
         }
@@ -399,10 +424,12 @@ CB_HD Meta rec_fdot2(DST dst, Opd x1, OpdS y1, Opd x2, OpdS y2, bool neg2, SCR S
 // AC: three small scratch columns (L+2 words each) rotating between acc.re, acc.im and "free"
 // RR: instantiate the reduced-radix attempt (a separate kernel: merely having the call in the code costs the
 // default kernel 50 registers and spills)
-template <int L, bool RR = false, bool SYNC = false, class SCR>
+// PI: the table holds rows per instance (operators that differ between instances: parameter sweeps)
+template <int L, bool RR = false, bool SYNC = false, bool PI = false, class SCR>
 CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0, SCR S1, SCR A0, SCR A1,
                                SCR A2, GScratch G0, GScratch G1, int64_t n_from = -1, int64_t n_to = -1) {
-    const size_t slot = 2 * (size_t)inst;
+    const size_t slot = 2 * (size_t)inst, qslot = PI ? slot : 0;
+    using YO = typename std::conditional<PI, Opd, OpdS>::type;
     const int v = p.valuation, W = p.degree - v;
     SCR accRe = A0, accIm = A1, spare = A2;
     const RecCtl ctl{p.no_rr == 0, p.stats};
@@ -416,13 +443,13 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
         int64_t e = bmax + v;
         int64_t bmin = clampi(e - p.degree, 0, bmax);
         int cnt = (int)(bmax - bmin);
-        int64_t base = (bmax + v) * (W + 2);
+        int64_t base = (bmax + v - p.tbl_row0) * (W + 2);
         Meta tRe = meta_zero(), tIm = meta_zero();
 #pragma unroll 1
         for (int k = 0; k < cnt; k++) {
-            CRef x = at<L>(p.res, bmin + k, slot), y = at<L>(p.tbl, base + k, 0);
+            CRef x = at<L>(p.res, bmin + k, slot), y = at<L>(p.tbl, base + k, qslot);
             Opd a = re_of(x), b = im_of(x);
-            OpdS c = re_of_shared(y), d = im_of_shared(y);
+            YO c = y_re<YO>(y), d = y_im<YO>(y);
             // real part: acc.re -= a c - b d
             CB_PHASE_SYNC();
             Meta pr = rec_fdot2<L, RR>(WRef{spare.generic(), SCR::GSTRIDE}, a, c, b, d, true, use_trunc<L>() ? spare : S0,
@@ -466,9 +493,9 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
         }
         CRef out = at<L>(p.res, bmax, slot);
         Opd xa{RRef{accRe.generic(), SCR::GSTRIDE}, tRe}, xb{RRef{accIm.generic(), SCR::GSTRIDE}, tIm};
-        if (p.kind[bmax + v] == 1) {
-            CRef y = at<L>(p.tbl, base + W + 1, 0);
-            OpdS c = re_of_shared(y), d = im_of_shared(y);
+        if (p.kind[(bmax + v - p.tbl_row0) * p.kind_stride + (PI ? inst : 0)] == 1) {
+            CRef y = at<L>(p.tbl, base + W + 1, qslot);
+            YO c = y_re<YO>(y), d = y_im<YO>(y);
             CB_PHASE_SYNC();
             Meta tr = rec_fdot2<L, RR>(wre(out), xa, c, xb, d, true, use_trunc<L>() ? spare : S0, S1, G0, G1, ctl);
             CB_PHASE_SYNC();
@@ -476,7 +503,7 @@ CB_HD void fuchs_shared_thread(const FuchsSharedParams& p, int64_t inst, SCR S0,
             st_meta(out.t, tr);
             st_meta(out.t + 1, ti);
         } else {
-            CRef y = at<L>(p.tbl, base + cnt, 0);
+            CRef y = at<L>(p.tbl, base + cnt, qslot);
             Opd c = re_of(y);
             // real divisor: long division needs two full-size columns; with truncated products the
             // shared columns are short, so the global ones serve (this path is integer-operator

@@ -55,52 +55,66 @@ int cbsim_fuchs_batch_range(int L_, int order, int degree, int valuation, int64_
     if (valuation >= 0) return CB200_EVALUATION;
     if (n_begin < -valuation) n_begin = -valuation;
     if (n_begin > n) return 0;
-    FuchsParams p;
-    p.order = order; p.degree = degree; p.valuation = valuation; p.n = n; p.batch = batch;
-    p.ode = CArr{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta),
-                 shared_ode ? (size_t)2 : (size_t)(2 * batch)};
-    p.res = CArr{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
-    Tmp tmp;
-    if (shared_ode) {  // same two-phase path as cb200_fuchs_batch_dev
-        int64_t rows = n + 1 + valuation, W = degree - valuation;
-        if (rows <= 0) return 0;
+    CArr odeA{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta),
+              shared_ode ? (size_t)2 : (size_t)(2 * batch)};
+    CArr resA{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
+    const int64_t rows = n + 1 + valuation, W = degree - valuation;
+    if (rows <= 0) return 0;
+    // columns sized EXACTLY as on the device (cb_kernels.cuh Sizes<L>), each followed by a canary zone, so an
+    // out-of-column access is caught here and not only on the GPU
+    const bool trunc = (L_ >= 16 && L_ <= 32);
+    const size_t aw = trunc ? L_ + 5 : L_ + 2;
+    const size_t sizes[7] = {(size_t)(trunc ? 0 : 2 * L_ + 3), (size_t)(trunc ? 0 : 2 * L_ + 3), aw, aw, aw,
+                             (size_t)2 * L_ + 3, (size_t)2 * L_ + 3};
+    const size_t CAN = 64;
+    std::vector<uint32_t> col[7];
+    for (int c = 0; c < 7; c++) col[c].assign(sizes[c] + CAN, 0xDEADBEEFu);
+    Scratch<1> S0{col[0].data()}, S1{col[1].data()}, A0{col[2].data()}, A1{col[3].data()}, A2{col[4].data()};
+    GScratch G0{col[5].data(), 1}, G1{col[6].data(), 1};
+    auto canaries_ok = [&]() {
+        for (int c = 0; c < 7; c++)
+            for (size_t k = sizes[c]; k < sizes[c] + CAN; k++)
+                if (col[c][k] != 0xDEADBEEFu) return -1000 - c;
+        return 0;
+    };
+    FuchsSharedParams sp;
+    sp.order = order; sp.degree = degree; sp.valuation = valuation; sp.batch = batch;
+    sp.res = resA; sp.gcols = nullptr; sp.stats = nullptr; sp.sched = nullptr; sp.range_len = 32;
+    { const char* e = getenv("CB200_RR"); sp.no_rr = (e && e[0] == '1') ? 0 : 1; }  // as cb200_fuchs_batch_dev
+    FuchsTableParams tp;
+    tp.order = order; tp.degree = degree; tp.valuation = valuation; tp.n = n; tp.ode = odeA;
+    if (shared_ode) {  // same two-phase path as cb200_fuchs_batch_range_dev
         Tmp tbl, ttmp;
         std::vector<int32_t> kind(rows + 1);
-        FuchsTableParams tp;
-        tp.order = order; tp.degree = degree; tp.valuation = valuation; tp.n = n;
-        tp.ode = p.ode;
         tp.tbl = tbl.arr(L_, rows * (W + 2), 2);
         tp.tmp = ttmp.arr(L_, 2, 2 * rows);
-        tp.kind = kind.data(); tp.row0 = n_begin + valuation;
-        SIM_DISPATCH(L_, run<L>(rows - tp.row0, [&](int64_t i, Scratch<1> a, Scratch<1> b) { fuchs_table_thread<L>(tp, i + tp.row0, a, b); }));
-        FuchsSharedParams sp;
-        sp.order = order; sp.degree = degree; sp.valuation = valuation; sp.n = n; sp.batch = batch;
-        sp.tbl = tp.tbl; sp.res = p.res; sp.kind = kind.data(); sp.gcols = nullptr; sp.stats = nullptr; sp.n_begin = n_begin; sp.sched = nullptr; sp.range_len = 32;
-        { const char* e = getenv("CB200_RR"); sp.no_rr = (e && e[0] == '1') ? 0 : 1; }  // as cb200_fuchs_batch_dev
-        // columns sized EXACTLY as on the device (cb_kernels.cuh Sizes<L>), each followed by a
-        // canary zone, so an out-of-column access is caught here and not only on the GPU
-        const bool trunc = (L_ >= 16 && L_ <= 32);
-        const size_t aw = trunc ? L_ + 5 : L_ + 2;
-        const size_t sizes[7] = {(size_t)(trunc ? 0 : 2 * L_ + 3), (size_t)(trunc ? 0 : 2 * L_ + 3), aw, aw, aw,
-                                 (size_t)2 * L_ + 3, (size_t)2 * L_ + 3};
-        const size_t CAN = 64;
-        std::vector<uint32_t> col[7];
-        for (int c = 0; c < 7; c++) col[c].assign(sizes[c] + CAN, 0xDEADBEEFu);
-        Scratch<1> S0{col[0].data()}, S1{col[1].data()}, A0{col[2].data()}, A1{col[3].data()}, A2{col[4].data()};
-        GScratch G0{col[5].data(), 1}, G1{col[6].data(), 1};
+        tp.kind = kind.data(); tp.row0 = n_begin + valuation; tp.nrows = rows - tp.row0; tp.ninst = 1; tp.tbl_row0 = 0;
+        SIM_DISPATCH(L_, run<L>(tp.nrows, [&](int64_t i, Scratch<1> a, Scratch<1> b) { fuchs_table_thread<L>(tp, i, a, b); }));
+        sp.n = n; sp.tbl = tp.tbl; sp.kind = kind.data(); sp.n_begin = n_begin; sp.tbl_row0 = 0; sp.kind_stride = 1; sp.per_inst = 0;
         if (sp.no_rr) {
             SIM_DISPATCH(L_, for (int64_t i = 0; i < batch; i++) (fuchs_shared_thread<L, false>)(sp, i, S0, S1, A0, A1, A2, G0, G1));
         } else {
             SIM_DISPATCH(L_, for (int64_t i = 0; i < batch; i++) (fuchs_shared_thread<L, true>)(sp, i, S0, S1, A0, A1, A2, G0, G1));
         }
-        for (int c = 0; c < 7; c++)
-            for (size_t k = sizes[c]; k < sizes[c] + CAN; k++)
-                if (col[c][k] != 0xDEADBEEFu) return -1000 - c;  // column overrun
-        return 0;
+        return canaries_ok();
     }
-    p.tmp = tmp.arr(L_, FUCHS_NTMP, 2 * batch);
-    SIM_DISPATCH(L_, run<L>(batch, [&](int64_t i, Scratch<1> a, Scratch<1> b) { fuchs_thread<L>(p, i, a, b); }));
-    return 0;
+    // an operator per instance: a table row per instance, a few rows at a time (deliberately small here, so that
+    // the range loop of cb200_fuchs_batch_range_dev is exercised)
+    const int64_t rt = rows < 7 ? rows : 7;
+    Tmp tbl, ttmp;
+    std::vector<int32_t> kind(rt * batch + 1);
+    tp.tbl = tbl.arr(L_, rt * (W + 2), 2 * batch);
+    tp.tmp = ttmp.arr(L_, 2, 2 * rt * batch);
+    tp.kind = kind.data(); tp.ninst = batch;
+    for (int64_t lo = n_begin; lo <= n; lo += rt) {
+        const int64_t hi = lo + rt - 1 < n ? lo + rt - 1 : n;
+        tp.row0 = lo + valuation; tp.nrows = hi - lo + 1; tp.tbl_row0 = lo + valuation;
+        SIM_DISPATCH(L_, run<L>(tp.nrows * batch, [&](int64_t i, Scratch<1> a, Scratch<1> b) { fuchs_table_thread<L>(tp, i, a, b); }));
+        sp.n = hi; sp.tbl = tp.tbl; sp.kind = kind.data(); sp.n_begin = lo; sp.tbl_row0 = lo + valuation; sp.kind_stride = batch;
+        sp.per_inst = 1; sp.no_rr = 1;
+        SIM_DISPATCH(L_, for (int64_t i = 0; i < batch; i++) (fuchs_shared_thread<L, false, false, true>)(sp, i, S0, S1, A0, A1, A2, G0, G1));
+    }
+    return canaries_ok();
 }
 
 int cbsim_fuchs_intop_batch(int L_, int order, int degree, int valuation, int64_t n, int64_t batch,
