@@ -112,7 +112,7 @@ int cb200_debug_rr_stats(uint64_t* out) {
 size_t cb200_fuchs_workspace_bytes(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
                                    int shared_ode) {
     (void)order;
-    if (valuation >= 0) return carve_bytes(L, FUCHS_NTMP, 2 * batch);
+    if (valuation >= 0) return 256;  // rejected by the solver (CB200_EVALUATION)
     if (!shared_ode) {
         // a table row per instance, built for one range of coefficient rows at a time
         int64_t W = degree - valuation, rt = pi_table_rows(L, W, n + 1 + valuation, batch);

@@ -48,11 +48,6 @@ template <int L> struct Sizes {
     if (idx >= (COUNT)) return;
 
 template <int L>
-__global__ void __launch_bounds__(Cfg<L>::TPB, 1) fuchs_kernel(FuchsParams p) {
-    CB_KERNEL_PROLOGUE(p.batch)
-    fuchs_thread<L>(p, idx, S0, S1);
-}
-template <int L>
 __global__ void __launch_bounds__(Cfg<L>::TPB, 1) frobenius1_kernel(FrobParams p) {
     CB_KERNEL_PROLOGUE(p.batch)
     frobenius1_thread<L>(p, idx, S0, S1);
@@ -296,7 +291,6 @@ int launch(void (*kern)(P), const P& p, int64_t count, cudaStream_t st, int tpb 
 
 // per-precision launch table, filled by kern_L*.cu
 struct LaunchTable {
-    int (*fuchs)(const FuchsParams&, cudaStream_t);
     int (*frobenius1)(const FrobParams&, cudaStream_t);
     int (*horner)(const HornerParams&, cudaStream_t);
     int (*ew)(const EwParams&, cudaStream_t);
@@ -313,7 +307,6 @@ struct LaunchTable {
 
 #define CB_DEFINE_LAUNCH_TABLE(LL)                                                                         \
     namespace cb {                                                                                         \
-    static int fuchs_##LL(const FuchsParams& p, cudaStream_t s) { return launch<LL>(fuchs_kernel<LL>, p, p.batch, s); }   \
     static int frob_##LL(const FrobParams& p, cudaStream_t s) { return launch<LL>(frobenius1_kernel<LL>, p, p.batch, s); } \
     static int horner_##LL(const HornerParams& p, cudaStream_t s) { return launch<LL>(horner_kernel<LL>, p, p.npts, s); } \
     static int ew_##LL(const EwParams& p, cudaStream_t s) { return launch<LL>(ew_kernel<LL>, p, p.n, s); }                \
@@ -363,7 +356,7 @@ struct LaunchTable {
     static int eval_##LL(const EvalParams& p, cudaStream_t s) { return launch<LL>(evaluate_kernel<LL>, p, p.npts, s); } \
     static int trans_##LL(const TransParams& p, cudaStream_t s) { return launch<LL>(trans_kernel<LL>, p, p.n, s); } \
     static int apply_##LL(const ApplyParams& p, cudaStream_t s) { return launch<LL>(apply_kernel<LL>, p, p.batch, s); } \
-    extern const LaunchTable launch_table_L##LL = {fuchs_##LL, frob_##LL, horner_##LL, ew_##LL, ftab_##LL, fsh_##LL, fint_##LL, \
+    extern const LaunchTable launch_table_L##LL = {frob_##LL, horner_##LL, ew_##LL, ftab_##LL, fsh_##LL, fint_##LL, \
                                                    frobg_##LL, solop_##LL, indp_##LL, eval_##LL, trans_##LL, apply_##LL}; \
     }
 

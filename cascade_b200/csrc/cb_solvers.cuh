@@ -1,7 +1,7 @@
 // cb_solvers.cuh -- per-thread bodies of the batched solvers: complex ball ops on top of
 // cb_arith.cuh and the restated Cascade loops, one CUDA thread per ODE instance.
 //
-//   fuchs_thread       <- acb_ode_solve_fuchs            reference src/fuchs_solver.c:96-145
+//   fuchs_table_thread + fuchs_shared_thread  <- acb_ode_solve_fuchs   reference src/fuchs_solver.c:96-145
 //   frobenius1_thread  <- _acb_ode_solve_frobenius       reference src/frobenius_solver.c:72-121
 //                         indicial_polynomial_evaluate   reference src/frobenius_solver.c:41-70
 //   horner_thread      <- acb_poly_evaluate (Horner) and the first `order` Taylor coefficients
@@ -236,56 +236,7 @@ CB_HD void acb_mark_tz(const CRef& z) {
 
 CB_HD int64_t clampi(int64_t x, int64_t lo, int64_t hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
-// ================================================================ Fuchs
-struct FuchsParams {
-    int order, degree, valuation;
-    int64_t n;      // highest coefficient index written (res has n+1 entries)
-    int64_t batch;  // instances
-    CArr ode;       // (order+1)(degree+1) entries, S = 2*batch or 2 (shared)
-    CArr res;       // n+1 entries, S = 2*batch
-    CArr tmp;       // FUCHS_NTMP entries, S = 2*batch
-};
-constexpr int FUCHS_NTMP = 5;
-
-template <int L, class SCR>
-CB_HD void fuchs_thread(const FuchsParams& p, int64_t inst, SCR S0, SCR S1) {
-    const size_t slot = 2 * (size_t)inst;
-    const size_t oslot = (p.ode.S == 2) ? 0 : slot;
-    const int v = p.valuation, D1 = p.degree + 1;
-    CRef acc = at<L>(p.tmp, 0, slot), prod = at<L>(p.tmp, 1, slot), t1 = at<L>(p.tmp, 2, slot),
-         t2 = at<L>(p.tmp, 3, slot), inv = at<L>(p.tmp, 4, slot);
-#pragma unroll 1
-    for (int64_t bmax = -v; bmax <= p.n; bmax++) {
-        acb_zero<L>(acc);
-        int64_t e = bmax + v;
-        int64_t bmin = clampi(e - p.degree, 0, bmax);
-        CRef cur = at<L>(p.ode, 0 * D1 + (e - bmin), oslot);
-        int64_t b = bmin;
-#pragma unroll 1
-        do {
-            acb_mul<L>(prod, at<L>(p.res, b, slot), cur, S0, S1);
-            acb_addsub<L>(acc, acc, prod, true, S0, S1);
-            acb_zero<L>(t2);
-            int64_t fac = 1;
-            b++;
-            int64_t imin = clampi(b - e, 0, -v);
-            int64_t imax = clampi(b - bmin, 0, p.order);
-#pragma unroll 1
-            for (int64_t i = imin; i <= imax; i++) {
-                acb_mul_si<L>(t1, at<L>(p.ode, i * D1 + (i + e - b), oslot), fac, S0);
-                acb_addsub<L>(t2, t2, t1, false, S0, S1);
-                fac *= (b - i);
-            }
-            fac = 1;
-            for (int64_t k = 0; k < imin; k++) fac *= (b - imin + 1 + k);
-            acb_mul_si<L>(t2, t2, fac, S0);
-            cur = t2;
-        } while (b != bmax);
-        acb_div<L>(at<L>(p.res, bmax, slot), acc, t2, inv, S0, S1);
-    }
-}
-
-// ================================================================ Fuchs, operator shared by the batch
+// ================================================================ Fuchs (acb_ode_solve_fuchs, reference src/fuchs_solver.c:96-145)
 // When every instance has the same operator, the integer-weighted multipliers
 //   cur(bmax, b) = sum_i P[i][i+e-b] * fac ...   (reference src/fuchs_solver.c:114,121-135)
 // and the divisor are identical for all instances.  fuchs_table_thread computes them ONCE per
@@ -295,7 +246,10 @@ CB_HD void fuchs_thread(const FuchsParams& p, int64_t inst, SCR S0, SCR S1) {
 // part: W complex multiply-subtracts and one multiply (or a division by a real divisor) per
 // coefficient, with the accumulator held in shared-memory columns.
 //
-// Table layout: shared-format array (S = 2), entry (bmax + v) * (W + 2) + slot, W = degree - v:
+// When the operators differ between instances the same two threads run with a table row PER INSTANCE (S = 2 * batch
+// table slots, built for a range of rows at a time): one table thread per (row, instance).
+//
+// Table layout: entry (bmax + v - tbl_row0) * (W + 2) + slot, W = degree - v (S = 2: one table for the batch):
 //   slot k < cnt    multiplier for b = bmin + k          (cnt = bmax - bmin)
 //   slot cnt        the divisor
 //   slot W + 1      its inverse when kind[bmax + v] == 1 (complex divisor), unused for kind 0 (real)
