@@ -80,8 +80,14 @@ def config3():
     ms = timed(lambda: lib.cb200_frobenius1_batch_dev(L, 2, 2, -1, n, batch, p(d_om), p(d_ot), 0, p(d_rm), p(d_rt), 0,
                                                       p(d_res_m), p(d_res_t), p(ws), wsb, None))
     coeffs = batch * n
-    out.append({"config": 3, "what": f"hypgeom Frobenius M=1, 4096 bits, {batch} (a,b,c) triples, {n} terms", "ms": ms,
+    out.append({"config": 3, "what": f"hypgeom Frobenius M=1, rho = 0, 4096 bits, {batch} (a,b,c) triples, {n} terms", "ms": ms,
                 "ball_coeffs_per_s": coeffs / ms * 1e3, "T_limb_MAC_per_s_36L2": coeffs * 36 * L * L / ms * 1e3 / 1e12})
+    # second exponent of the sweep: rho = 1 - c is a dense complex ball per instance
+    d_r2m, d_r2t = rand_dev(1, L, 2 * batch, 31)
+    ms = timed(lambda: lib.cb200_frobenius1_batch_dev(L, 2, 2, -1, n, batch, p(d_om), p(d_ot), 0, p(d_r2m), p(d_r2t), 0,
+                                                      p(d_res_m), p(d_res_t), p(ws), wsb, None))
+    out.append({"config": 3, "what": f"hypgeom Frobenius M=1, dense complex rho per instance (the rho = 1 - c run), 4096 bits, {batch} triples, {n} terms",
+                "ms": ms, "ball_coeffs_per_s": coeffs / ms * 1e3, "T_limb_MAC_per_s_36L2": coeffs * 36 * L * L / ms * 1e3 / 1e12})
     del d_res_m, d_res_t, ws
     torch.cuda.empty_cache()
 
@@ -153,6 +159,31 @@ def config3_log():
     torch.cuda.empty_cache()
 
 
+def config5_extend():
+    # ---- config 5, "acb_ode_solution_extend" leg: a batch of _acb_ode_solution_extend calls (Horner evaluation of a
+    # polynomial in rho and of its derivatives: reference src/acb_ode_solution.c:97-109; polynomial length 20 as in
+    # reference tests/solution_extend.c), 2048 bits, M = 3
+    L, M, cap, fcap = 64, 3, 8, 20
+    batch = max(1024, int(262144 * args.scale))
+    g_m = torch.zeros((M * cap, L, 2 * batch), dtype=torch.int32, device=dev)
+    g_t = torch.zeros((M * cap, 2 * batch, 4), dtype=torch.int32, device=dev)
+    g_t[:, :, 1] = 2
+    f_m, f_t = rand_dev(fcap, L, 2 * batch, 11)
+    r_m, r_t = rand_dev(1, L, 2 * batch, 12)
+    wsb = lib.cb200_solution_op_workspace_bytes(L, M, batch)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    f_keep_m, f_keep_t = f_m.clone(), f_t.clone()
+
+    def run():
+        f_m.copy_(f_keep_m)  # the call consumes its polynomial
+        f_t.copy_(f_keep_t)
+        return lib.cb200_solution_op_dev(0, L, batch, M, M, cap, 3, p(r_m), p(r_t), p(g_m), p(g_t), p(f_m), p(f_t), fcap,
+                                         p(ws), wsb, None)
+    ms = timed(run, reps=1)
+    out.append({"config": "5-extend", "what": f"_acb_ode_solution_extend, M={M}, polynomial of {fcap} terms in rho, {batch} solutions, 2048 bits (includes restoring the consumed polynomial)",
+                "ms": ms, "extends_per_s": batch / ms * 1e3})
+
+
 def config5_eval():
     # ---- config 5, full acb_ode_solution_evaluate (Horner of M = 2 series + acb_log + acb_pow), 1024 bits
     L, cap, M = 32, 256, 2
@@ -176,6 +207,7 @@ if args.only in (0, 3):
     config3_log()
 if args.only in (0, 5):
     config5_eval()
+    config5_extend()
 if args.only in (0, 4):
     config4()
 if args.only in (0, 5):
