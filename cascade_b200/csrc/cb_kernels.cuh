@@ -50,7 +50,7 @@ template <int L> struct Sizes {
 template <int L>
 __global__ void __launch_bounds__(Cfg<L>::TPB, 1) frobenius1_kernel(FrobParams p) {
     CB_KERNEL_PROLOGUE(p.batch)
-    frobenius1_thread<L>(p, idx, S0, S1);
+    frobenius1_thread<L, true>(p, idx, S0, S1);
 }
 template <int L>
 __global__ void __launch_bounds__(Cfg<L>::TPB, 1) frobenius_general_kernel(FrobGenParams p) {
@@ -82,10 +82,14 @@ __global__ void __launch_bounds__(Cfg<L>::TPB, 1) trans_kernel(TransParams p) {
     CB_KERNEL_PROLOGUE(p.n)
     trans_thread<L>(p, idx, S0, S1);
 }
+#ifndef CB_HORNER_SYNC
+#define CB_HORNER_SYNC 1
+#endif
+constexpr bool HORNER_SYNC = CB_HORNER_SYNC != 0;
 template <int L>
 __global__ void __launch_bounds__(Cfg<L>::TPB, 1) horner_kernel(HornerParams p) {
     CB_KERNEL_PROLOGUE(p.npts)
-    horner_thread<L>(p, idx, S0, S1);
+    horner_thread<L, HORNER_SYNC>(p, idx, S0, S1);
 }
 template <int L>
 __global__ void __launch_bounds__(Cfg<L>::TPB, 1) ew_kernel(EwParams p) {

@@ -587,7 +587,7 @@ struct FrobParams {
 constexpr int FROB_NTMP = 7;
 
 // result may be one of (o1, o2): returns which holds f_nu(rho + shift)
-template <int L, class SCR, class PRM>
+template <int L, bool SYNC = false, class SCR, class PRM>
 CB_HD CRef indicial_eval(const PRM& p, size_t oslot, int64_t nu, const CRef& rho, int64_t shift,
                          CRef o1, CRef o2, const CRef& t, const CRef& kb, SCR S0, SCR S1) {
     const int D1 = p.degree + 1;
@@ -597,6 +597,7 @@ CB_HD CRef indicial_eval(const PRM& p, size_t oslot, int64_t nu, const CRef& rho
 #pragma unroll 1
     for (int64_t lam = clampi(p.degree - nu, 0, p.order); lam >= 0; lam--) {
         acb_add_si<L>(t, rho, shift - lam, kb, S0, S1);
+        CB_PHASE_SYNC();
         acb_mul<L>(o2, o1, t, S0, S1);
         CRef sw = o1;
         o1 = o2;
@@ -607,7 +608,9 @@ CB_HD CRef indicial_eval(const PRM& p, size_t oslot, int64_t nu, const CRef& rho
     return o1;
 }
 
-template <int L, class SCR>
+// SYNC: phase barriers before the long calls of the main loop (its trip counts are launch parameters; the
+// right-hand-side branch before the loop is per instance and has none), see phase_sync
+template <int L, bool SYNC = false, class SCR>
 CB_HD void frobenius1_thread(const FrobParams& p, int64_t inst, SCR S0, SCR S1) {
     const size_t slot = 2 * (size_t)inst;
     const size_t oslot = (p.ode.S == 2) ? 0 : slot;
@@ -635,16 +638,19 @@ CB_HD void frobenius1_thread(const FrobParams& p, int64_t inst, SCR S0, SCR S1) 
         if (nu < rl) acb_set<L>(gnew, at<L>(p.rhs, nu, hslot));
         else acb_zero<L>(gnew);
         int64_t i = clampi(nu, 1, p.degree);
-        CRef ind = indicial_eval<L>(p, oslot, i, rho, nu - i, o1, o2, t, kb, S0, S1);
+        CRef ind = indicial_eval<L, SYNC>(p, oslot, i, rho, nu - i, o1, o2, t, kb, S0, S1);
 #pragma unroll 1
         do {
+            CB_PHASE_SYNC();
             acb_mul<L>(prod, ind, at<L>(p.res, nu - i, slot), S0, S1);
+            CB_PHASE_SYNC();
             acb_addsub<L>(gnew, gnew, prod, true, S0, S1);
             i--;
-            ind = indicial_eval<L>(p, oslot, i, rho, nu - i, o1, o2, t, kb, S0, S1);
+            ind = indicial_eval<L, SYNC>(p, oslot, i, rho, nu - i, o1, o2, t, kb, S0, S1);
         } while (i > 0);
         // g_nu = g_new / f_0(rho + nu); `prod` and the unused one of (o1,o2) are free temporaries
         CRef spare = (ind.m == o1.m) ? o2 : o1;
+        CB_PHASE_SYNC();
         acb_div<L>(at<L>(p.res, nu, slot), gnew, ind, spare, S0, S1);
     }
 }
@@ -789,8 +795,9 @@ CB_HD int64_t poly_scalar_mul(const PolyCtx<L, SCR>& pc, const CArr& A, int64_t 
     while (len > 0 && acb_is_exact_zero(at<L>(A, e0 + len - 1, pc.slot))) len--;
     return len;
 }
-// out = p(x) (acb_poly_evaluate -> Horner; out must not be t1)
-template <int L, class SCR>
+// out = p(x) (acb_poly_evaluate -> Horner; out must not be t1).  SYNC: phase barriers in the Horner loop -- only for
+// callers whose polynomial length is the same for every thread of the block (see phase_sync)
+template <int L, bool SYNC = false, class SCR>
 CB_HD void poly_eval(const PolyCtx<L, SCR>& pc, const CRef& out, int64_t e0, int64_t len, const CRef& x) {
     if (len == 0) {
         acb_zero<L>(out);
@@ -803,7 +810,9 @@ CB_HD void poly_eval(const PolyCtx<L, SCR>& pc, const CRef& out, int64_t e0, int
     }
 #pragma unroll 1
     for (int64_t j = len - 2; j >= 0; j--) {
+        CB_PHASE_SYNC();
         acb_mul<L>(pc.t1, out, x, pc.S0, pc.S1);
+        CB_PHASE_SYNC();
         acb_addsub<L>(out, pc.t1, pc.c(e0, j), false, pc.S0, pc.S1);
     }
 }
@@ -1086,7 +1095,9 @@ struct HornerParams {
 };
 constexpr int HORNER_MAXDER = 4;
 
-template <int L, class SCR>
+// SYNC: phase barriers before the long calls (every thread of the block runs the same loop: len and nder are
+// launch parameters), see phase_sync
+template <int L, bool SYNC = false, class SCR>
 CB_HD void horner_thread(const HornerParams& p, int64_t pt, SCR S0, SCR S1) {
     const size_t slot = 2 * (size_t)pt;
     const size_t fslot = (p.f.S == 2) ? 0 : slot;
@@ -1099,7 +1110,9 @@ CB_HD void horner_thread(const HornerParams& p, int64_t pt, SCR S0, SCR S1) {
 #pragma unroll 1
         for (int k = p.nder - 1; k >= 0; k--) {
             CRef o = at<L>(p.out, k, slot);
+            CB_PHASE_SYNC();
             acb_mul<L>(tmp, o, a, S0, S1);
+            CB_PHASE_SYNC();
             if (k > 0)
                 acb_addsub<L>(o, tmp, at<L>(p.out, k - 1, slot), false, S0, S1);
             else

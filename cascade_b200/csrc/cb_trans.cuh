@@ -28,6 +28,7 @@ namespace cb {
 #endif
 
 constexpr int64_t TR_BIG = ((int64_t)1) << 40;
+constexpr bool EVAL_SYNC = true;  // phase barriers in evaluate_thread's Horner loops (uniform trip counts)
 constexpr int TRANS_NTMP = 16;  // complex temporaries of acb_exp (4) + acb_log (10) + evaluate (2)
 
 template <int L>
@@ -266,7 +267,9 @@ CB_HD void evaluate_thread(const EvalParams& p, int64_t pt, SCR S0, SCR S1) {
     PolyCtx<L, SCR> pc{p.gens, 0, S0, S1, T[0], T[1], T[2], T[3], T[4]};
     auto series_eval = [&](const CRef& y, int i) {
         int64_t e0 = (int64_t)i * p.cap;
-        poly_eval<L>(pc, y, e0, pc.norm(e0, p.cap), a);
+        // the series are shared by all points, so every thread runs the same Horner loop: phase barriers -- unless this
+        // point is an exact zero of the series variable (poly_eval then returns the constant term without looping)
+        poly_eval<L, EVAL_SYNC>(pc, y, e0, pc.norm(e0, p.cap), a);
     };
     series_eval(res, 0);
     int64_t binom = 1;
