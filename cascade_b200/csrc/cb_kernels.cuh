@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(IntopCfg<L>::TPB, 1) fuchs_intop_persistent_ke
 // (measured, 98-coefficient runs: 224 threads 21.7 instances/ms/SM, 384 threads 23.4 -- 25.9 with the phase
 // barriers it is built with --, 448 threads -- 128 registers, 532 B of spills -- 21.4: never chosen; persistent
 // launches at the full BASELINE size: 384 threads 317 ms, 352 340 ms, 416 400 ms, 448 382 ms)
-constexpr double THR_BIG = 1.19, THR_HUGE = 0.98;
+constexpr double THR_BIG = 1.19, THR_HUGE = 0.98, THR_PERS64 = 1.23;  // 2048 bits, measured: 5.3-5.45 T against 4.3 T whole-wave
 // 0: TPB, 1: TPB_BIG, 2: TPB_HUGE.  CB200_TPB_CHOICE=0/1/2 in the environment overrides (development)
 template <int L>
 int choose_block_size(int64_t batch, int sms) {
@@ -260,11 +260,16 @@ int launch_persistent(const FuchsSharedParams& p, int sms, cudaStream_t s) {
     return (int)cudaGetLastError();
 }
 
-// persistent launch: worthwhile when the batch is more than one wave of the big blocks and the fractional-wave cost
-// of the 12-warp variant beats the best whole-wave choice.  CB200_PERSISTENT=0/1 in the environment overrides.
+// persistent launch: worthwhile when the batch is more than one wave of its blocks and the fractional-wave cost
+// of the barrier-synchronised variant beats the best whole-wave choice.  CB200_PERSISTENT=0/1 in the environment
+// overrides.  1024 bits: 12 warps (TPB_BIG); 2048 bits: the same 3 warps as the plain kernel, so the gain is the
+// missing last-wave tail plus what the phase barriers give.
+template <int L> struct PersCfg { static constexpr int TPB = 0; static constexpr double THR = 1.0; };
+template <> struct PersCfg<32> { static constexpr int TPB = CfgShared<32>::TPB_BIG; static constexpr double THR = THR_BIG; };
+template <> struct PersCfg<64> { static constexpr int TPB = CfgShared<64>::TPB; static constexpr double THR = THR_PERS64; };
 template <int L>
 bool use_persistent(int64_t batch, int sms) {
-    if (L != 32 || CfgShared<L>::TPB_BIG == CfgShared<L>::TPB) return false;
+    if (PersCfg<L>::TPB == 0) return false;
     const char* e = getenv("CB200_PERSISTENT");
     if (e && e[0] == '0') return false;
     if (e && e[0] == '1') return true;
@@ -274,11 +279,14 @@ bool use_persistent(int64_t batch, int sms) {
         return (double)waves * tpb / thr;
     };
     double best = cost(CfgShared<L>::TPB, 1.0);
-    double big = cost(CfgShared<L>::TPB_BIG, THR_BIG);
-    if (big < best) best = big;
-    int64_t blocks = (batch + CfgShared<L>::TPB_BIG - 1) / CfgShared<L>::TPB_BIG;
-    if (blocks <= sms) return false;
-    double pers = (double)blocks * CfgShared<L>::TPB_BIG / sms / THR_BIG * 1.02;  // 2 % for the ragged last round
+    if (CfgShared<L>::TPB_BIG != CfgShared<L>::TPB) {
+        double big = cost(CfgShared<L>::TPB_BIG, THR_BIG);
+        if (big < best) best = big;
+    }
+    constexpr int PT = PersCfg<L>::TPB > 0 ? PersCfg<L>::TPB : 1;
+    int64_t blocks = (batch + PT - 1) / PT;
+    if (blocks <= sms) return L == 64 && batch >= PT;  // 2048 bits: same block size, the barriers alone give 1.23x
+    double pers = (double)blocks * PT / sms / PersCfg<L>::THR * 1.02;  // 2 % for the ragged last round
     return pers < best;
 }
 
@@ -327,7 +335,7 @@ struct LaunchTable {
             return launch<LL>(fuchs_shared_kernel<LL, CfgShared<LL>::TPB, true>, p, p.batch, s, CfgShared<LL>::TPB, \
                               Sizes<LL>::SMEM_SHARED_PER_THREAD * CfgShared<LL>::TPB);                     \
         if (p.sched && use_persistent<LL>(p.batch, sms)) {                                                 \
-            return launch_persistent<LL, CfgShared<LL>::TPB_BIG>(p, sms, s);                               \
+            return launch_persistent<LL, (PersCfg<LL>::TPB > 0 ? PersCfg<LL>::TPB : CfgShared<LL>::TPB)>(p, sms, s); \
         }                                                                                                  \
         int choice = choose_block_size<LL>(p.batch, sms);                                                  \
         if (choice == 2)                                                                                   \

@@ -98,3 +98,25 @@ def test_coefficient_ranges_match_one_call(monkeypatch, persistent):
         torch.cuda.synchronize()
         outs.append((d_res_m.cpu(), d_res_t.cpu()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("L,batch", [(64, 1000), (32, 1500)])
+def test_persistent_kernel_matches_whole_wave_kernel(monkeypatch, L, batch):
+    """The work-unit (persistent) recurrence kernel and the one-block-per-instance-block kernel leave the same
+    bytes, ragged last block included -- at 2048 bits too, where the persistent form serves batches that are not
+    a whole number of waves (the continuation pipeline's)."""
+    from cascade_b200 import api
+    from cascade_b200.format import random_balls
+
+    rng = np.random.default_rng(0xBE55 + L)
+    drv = api.HostBufferDriver(0)
+    nu = random_balls(rng, 2, L, 0, 0, "zero")
+    a = random_balls(rng, 2, L, 0, 1, "zero")
+    ode0, _ = api.acb_ode_bessel_batch(nu, driver=drv)
+    ode = api.acb_ode_shift_batch(ode0, a, 2, 2, driver=drv)
+    init = random_balls(rng, batch * 4, L, -1, 0, "ulp")
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("CB200_PERSISTENT", flag)
+        outs.append(api.acb_ode_solve_fuchs_batch(ode, init, 2, 2, 150, batch, True, driver=drv))
+    assert outs[0].same_as(outs[1])
