@@ -126,8 +126,13 @@ size_t cb200_fuchs_workspace_bytes(int L, int order, int degree, int valuation, 
            align256((size_t)2 * (2 * L + 3) * gcols_columns(batch) * sizeof(uint32_t)) +
            align256(sizeof(int) * (size_t)(batch / 32 + 2));
 }
-size_t cb200_frobenius_workspace_bytes(int L, int64_t batch) { return carve_bytes(L, FROB_NTMP, 2 * batch); }
-size_t cb200_horner_workspace_bytes(int L, int64_t npts) { return carve_bytes(L, 1, 2 * npts); }
+static size_t hyb_tail_bytes(int L, int64_t count);
+size_t cb200_frobenius_workspace_bytes(int L, int64_t batch) { return carve_bytes(L, FROB_NTMP, 2 * batch) + hyb_tail_bytes(L, batch); }
+// global tails of the hybrid scratch columns (2048 bits and up; cb_kernels.cuh HybCfg)
+static size_t hyb_tail_bytes(int L, int64_t count) {
+    return L >= 64 ? align256((size_t)2 * (size_t)(L - 2) * (size_t)(count > 0 ? count : 0) * sizeof(uint32_t)) : 0;
+}
+size_t cb200_horner_workspace_bytes(int L, int64_t npts) { return carve_bytes(L, 1, 2 * npts) + hyb_tail_bytes(L, npts); }
 size_t cb200_ew_workspace_bytes(int L, int64_t n) { return carve_bytes(L, 2, 2 * n); }
 
 int cb200_fuchs_batch_dev(int L_, int order, int degree, int valuation, int64_t n, int64_t batch,
@@ -335,6 +340,7 @@ int cb200_frobenius1_rhs_batch_dev(int L_, int order, int degree, int valuation,
     p.rhs_len = rhs_len;
     char* w = (char*)workspace;
     p.tmp = carve(w, L_, FROB_NTMP, 2 * batch);
+    p.gcols = (uint32_t*)w;
     g_launches.fetch_add(batch > 0);
     return table_for(L_)->frobenius1(p, (cudaStream_t)stream);
 }
@@ -514,6 +520,7 @@ int cb200_horner_batch_dev(int L_, int64_t len, int64_t npts, int nder, const ui
     p.out = CArr{out_mant, (Meta*)out_meta, (size_t)(2 * npts)};
     char* w = (char*)workspace;
     p.tmp = carve(w, L_, 1, 2 * npts);
+    p.gcols = (uint32_t*)w;
     g_launches.fetch_add(npts > 0);
     return table_for(L_)->horner(p, (cudaStream_t)stream);
 }
@@ -615,6 +622,7 @@ int cb200_continuation_dev(int L_, int order, int degree, int64_t n, int64_t bat
         hp.out = CArr{y_mant, (Meta*)y_meta, (size_t)S};
         char* hwp = (char*)hws;
         hp.tmp = carve(hwp, L_, 1, S);
+        hp.gcols = (uint32_t*)hwp;
         g_launches.fetch_add(batch > 0);
         rc = table_for(L_)->horner(hp, st);
         if (rc) return rc;

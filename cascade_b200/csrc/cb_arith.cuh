@@ -127,6 +127,56 @@ struct Scratch {
 #endif
 };
 
+// A scratch column whose first KS words live in shared memory and whose tail lives in a global-memory column.
+// The paths every operation takes (truncated blocked products, aligned sums of L-limb operands: at most L + 5
+// words) see only the shared part -- they are handed lo(), a plain Scratch --; the rare exact paths (full
+// 2L-limb products when the guard-bit proof fails, long division) spill their upper words to global memory.
+// This is what lets the 2048/4096-bit kernels keep 8 / 6 warps per SM instead of 6 / 3.5.
+template <int STRIDE, int KS>
+struct HybridScratch {
+#if defined(__CUDA_ARCH__)
+    uint32_t a;    // shared-space byte address of word 0
+    uint32_t* g;   // word k >= KS at g[(k - KS) * gs]
+    uint32_t gs;
+    __device__ __forceinline__ uint32_t ld(int k) const {
+        if (k < KS) {
+            uint32_t v;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a + (uint32_t)(k * (STRIDE * 4))));
+            return v;
+        }
+        return g[(size_t)(k - KS) * gs];
+    }
+    __device__ __forceinline__ void st(int k, uint32_t v) const {
+        if (k < KS)
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(a + (uint32_t)(k * (STRIDE * 4))), "r"(v));
+        else
+            g[(size_t)(k - KS) * gs] = v;
+    }
+    __device__ __forceinline__ Scratch<STRIDE> lo() const { return Scratch<STRIDE>{a}; }
+#else
+    uint32_t* p;
+    uint32_t* g;
+    uint32_t gs;
+    uint32_t ld(int k) const { return k < KS ? p[(ptrdiff_t)k * STRIDE] : g[(size_t)(k - KS) * gs]; }
+    void st(int k, uint32_t v) const {
+        if (k < KS) p[(ptrdiff_t)k * STRIDE] = v;
+        else g[(size_t)(k - KS) * gs] = v;
+    }
+    Scratch<STRIDE> lo() const { return Scratch<STRIDE>{p}; }
+#endif
+};
+template <class S> struct ScrLo {
+    using type = S;
+    static CB_HD S get(S s) { return s; }
+};
+template <int ST, int KS> struct ScrLo<HybridScratch<ST, KS>> {
+    using type = Scratch<ST>;
+    static CB_HD Scratch<ST> get(HybridScratch<ST, KS> s) { return s.lo(); }
+};
+// the shared-memory part of a column (the column itself unless it is a HybridScratch)
+template <class S>
+CB_HD typename ScrLo<S>::type lo_view(S s) { return ScrLo<S>::get(s); }
+
 // ---------------------------------------------------------------- magnitudes (radii)
 // value = man * 2^(exp-30), man in [2^29, 2^30) or 0.  Every function mirrors oracle/cbo_arith.c.
 struct Mag {
@@ -1043,7 +1093,13 @@ CB_NOINLINE Meta arb_fdot2_trunc_blocked(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT
 
 // dst = x + (negy ? -y : y)
 template <int L, class SCR>
-CB_NOINLINE Meta arb_addsub(WRef dst, Opd x, Opd y, bool negy, SCR S0, SCR S1) {
+CB_NOINLINE Meta arb_addsub_impl(WRef dst, Opd x, Opd y, bool negy, SCR S0, SCR S1);
+template <int L, class SCR>
+CB_HD Meta arb_addsub(WRef dst, Opd x, Opd y, bool negy, SCR S0, SCR S1) {  // touches words 0..L+1 only
+    return arb_addsub_impl<L>(dst, x, y, negy, lo_view(S0), lo_view(S1));
+}
+template <int L, class SCR>
+CB_NOINLINE Meta arb_addsub_impl(WRef dst, Opd x, Opd y, bool negy, SCR S0, SCR S1) {
     bool nan = is_nan(x.t) || is_nan(y.t);
     bool zx = is_zero_mid(x.t) || nan, zy = is_zero_mid(y.t) || nan;
     bool nx = (x.t.flags & F_SIGN) != 0, ny = ((y.t.flags & F_SIGN) != 0) != negy;
@@ -1109,7 +1165,13 @@ CB_NOINLINE Meta arb_addsub_cols(SCR A, Meta ta, SCR B, Meta tb, bool negb, SCR*
 
 // dst = x * k, k a signed 64-bit integer (acb_mul_fmpz / acb_mul_si with a small integer)
 template <int L, class SCR>
-CB_NOINLINE Meta arb_mul_si(WRef dst, Opd x, int64_t k, SCR S0) {
+CB_NOINLINE Meta arb_mul_si_impl(WRef dst, Opd x, int64_t k, SCR S0);
+template <int L, class SCR>
+CB_HD Meta arb_mul_si(WRef dst, Opd x, int64_t k, SCR S0) {  // touches words 0..L+1 only
+    return arb_mul_si_impl<L>(dst, x, k, lo_view(S0));
+}
+template <int L, class SCR>
+CB_NOINLINE Meta arb_mul_si_impl(WRef dst, Opd x, int64_t k, SCR S0) {
     bool nan = is_nan(x.t);
     uint64_t ka = k < 0 ? (uint64_t)0 - (uint64_t)k : (uint64_t)k;
     uint32_t k0 = (uint32_t)ka, k1 = (uint32_t)(ka >> 32);

@@ -47,10 +47,36 @@ template <int L> struct Sizes {
     const int64_t idx = (int64_t)blockIdx.x * TPB + threadIdx.x;                               \
     if (idx >= (COUNT)) return;
 
+// 2048 / 4096 bits: hybrid columns (L + 5 words in shared memory, the tail of the rare exact paths in global
+// memory), so that the block is bounded by the 255 registers per thread, not by shared memory
+template <int L> struct HybCfg {
+    static constexpr bool ON = L >= 64;
+    static constexpr int KS = L + 5;                  // shared words per column
+    static constexpr int GW = 2 * L + 3 - KS;         // global words per column
+    static constexpr int TPB = L == 64 ? 256 : (L == 128 ? 192 : Cfg<L>::TPB);
+    static constexpr size_t SMEM = (size_t)2 * KS * TPB * sizeof(uint32_t);
+};
+#define CB_KERNEL_PROLOGUE_HYB(COUNT, GCOLS)                                                   \
+    extern __shared__ uint32_t cb_smem[];                                                      \
+    constexpr int TPB = HybCfg<L>::TPB;                                                        \
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cb_smem) + 4u * threadIdx.x;     \
+    const int64_t idx = (int64_t)blockIdx.x * TPB + threadIdx.x;                               \
+    if (idx >= (COUNT)) return;                                                                \
+    HybridScratch<TPB, HybCfg<L>::KS> S0{sbase, (GCOLS) + idx, (uint32_t)(COUNT)};             \
+    HybridScratch<TPB, HybCfg<L>::KS> S1{sbase + 4u * (uint32_t)(HybCfg<L>::KS * TPB),         \
+                                         (GCOLS) + (size_t)HybCfg<L>::GW * (size_t)(COUNT) + idx, (uint32_t)(COUNT)};
+
 template <int L>
 __global__ void __launch_bounds__(Cfg<L>::TPB, 1) frobenius1_kernel(FrobParams p) {
     CB_KERNEL_PROLOGUE(p.batch)
     frobenius1_thread<L, true>(p, idx, S0, S1);
+}
+template <int L>
+__global__ void __launch_bounds__(HybCfg<L>::TPB, 1) frobenius1_hyb_kernel(FrobParams p) {
+    if constexpr (HybCfg<L>::ON) {
+        CB_KERNEL_PROLOGUE_HYB(p.batch, p.gcols)
+        frobenius1_thread<L, true>(p, idx, S0, S1);
+    }
 }
 template <int L>
 __global__ void __launch_bounds__(Cfg<L>::TPB, 1) frobenius_general_kernel(FrobGenParams p) {
@@ -90,6 +116,13 @@ template <int L>
 __global__ void __launch_bounds__(Cfg<L>::TPB, 1) horner_kernel(HornerParams p) {
     CB_KERNEL_PROLOGUE(p.npts)
     horner_thread<L, HORNER_SYNC>(p, idx, S0, S1);
+}
+template <int L>
+__global__ void __launch_bounds__(HybCfg<L>::TPB, 1) horner_hyb_kernel(HornerParams p) {
+    if constexpr (HybCfg<L>::ON) {
+        CB_KERNEL_PROLOGUE_HYB(p.npts, p.gcols)
+        horner_thread<L, HORNER_SYNC>(p, idx, S0, S1);
+    }
 }
 template <int L>
 __global__ void __launch_bounds__(Cfg<L>::TPB, 1) ew_kernel(EwParams p) {
@@ -255,7 +288,11 @@ int launch_persistent(const FuchsSharedParams& p, int sms, cudaStream_t s) {
     int64_t nblocks = (p.batch + PT - 1) / PT;
     e = cudaMemsetAsync(p.sched, 0, sizeof(int) * (size_t)(nblocks + 1), s);
     if (e != cudaSuccess) return (int)e;
-    int grid = (int)(nblocks < sms ? nblocks : sms);
+    int per_sm = 1;  // resident CTAs per SM (2048 bits: two 96-thread CTAs of 81 KB)
+    if (L == 64) per_sm = 2;
+    if (const char* e = getenv("CB200_PERS_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 4) per_sm = v; }  // development
+    int64_t cap = (int64_t)sms * per_sm;
+    int grid = (int)(nblocks < cap ? nblocks : cap);
     fuchs_shared_persistent_kernel<L, PT><<<grid, PT, Sizes<L>::SMEM_SHARED_PER_THREAD * PT, s>>>(p);
     return (int)cudaGetLastError();
 }
@@ -290,6 +327,11 @@ bool use_persistent(int64_t batch, int sms) {
     return pers < best;
 }
 
+inline int sm_count() {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
 template <int L, class P>
 int launch(void (*kern)(P), const P& p, int64_t count, cudaStream_t st, int tpb = Cfg<L>::TPB,
            size_t smem = Sizes<L>::SMEM) {
@@ -300,6 +342,25 @@ int launch(void (*kern)(P), const P& p, int64_t count, cudaStream_t st, int tpb 
     kern<<<grid, tpb, smem, st>>>(p);
     return (int)cudaGetLastError();
 }
+
+// hybrid-column kernel or the all-shared one?  A wave of the hybrid kernel carries more threads but takes
+// WAVE_RATIO times as long (measured, full waves); CB200_HYBRID=0/1 in the environment overrides (development).
+template <int L>
+bool use_hybrid(int64_t count, int sms, double wave_ratio) {
+    if (!HybCfg<L>::ON) return false;
+    const char* e = getenv("CB200_HYBRID");
+    if (e && e[0] == '0') return false;
+    if (e && e[0] == '1') return true;
+    auto waves = [&](int tpb) { return (double)(((count + tpb - 1) / tpb + sms - 1) / sms); };
+    return waves(HybCfg<L>::TPB) * wave_ratio < waves(Cfg<L>::TPB);
+}
+// time of a full wave of the hybrid kernel / time of a full wave of the all-shared kernel
+template <int L> struct HybRatio { static constexpr double HORNER = 1.0, FROB = 1.0; };
+// (B200, whole waves of both: Horner 2048 bits 5.45 -> 6.99 T limb-MAC/s, 4096 bits 4.79 -> 6.45; Frobenius M = 1
+// 2048 bits 2.34 -> 2.50, 4096 bits 2.25 -> 2.10 -- its long divisions run through the global tails --, so the
+// 4096-bit Frobenius kernel goes hybrid only where that saves a whole wave)
+template <> struct HybRatio<64> { static constexpr double HORNER = 1.04, FROB = 1.25; };
+template <> struct HybRatio<128> { static constexpr double HORNER = 1.27, FROB = 1.83; };
 
 // per-precision launch table, filled by kern_L*.cu
 struct LaunchTable {
@@ -319,8 +380,16 @@ struct LaunchTable {
 
 #define CB_DEFINE_LAUNCH_TABLE(LL)                                                                         \
     namespace cb {                                                                                         \
-    static int frob_##LL(const FrobParams& p, cudaStream_t s) { return launch<LL>(frobenius1_kernel<LL>, p, p.batch, s); } \
-    static int horner_##LL(const HornerParams& p, cudaStream_t s) { return launch<LL>(horner_kernel<LL>, p, p.npts, s); } \
+    static int frob_##LL(const FrobParams& p, cudaStream_t s) {                                            \
+        if (use_hybrid<LL>(p.batch, sm_count(), HybRatio<LL>::FROB))                                       \
+            return launch<LL>(frobenius1_hyb_kernel<LL>, p, p.batch, s, HybCfg<LL>::TPB, HybCfg<LL>::SMEM); \
+        return launch<LL>(frobenius1_kernel<LL>, p, p.batch, s);                                           \
+    }                                                                                                      \
+    static int horner_##LL(const HornerParams& p, cudaStream_t s) {                                        \
+        if (use_hybrid<LL>(p.npts, sm_count(), HybRatio<LL>::HORNER))                                      \
+            return launch<LL>(horner_hyb_kernel<LL>, p, p.npts, s, HybCfg<LL>::TPB, HybCfg<LL>::SMEM);     \
+        return launch<LL>(horner_kernel<LL>, p, p.npts, s);                                                \
+    }                                                                                                      \
     static int ew_##LL(const EwParams& p, cudaStream_t s) { return launch<LL>(ew_kernel<LL>, p, p.n, s); }                \
     static int ftab_##LL(const FuchsTableParams& p, cudaStream_t s) {                                      \
         return launch<LL>(fuchs_table_kernel<LL>, p, p.nrows * p.ninst, s);                            \

@@ -109,7 +109,7 @@ CB_HD Meta fdot2_auto(WRef dst, Opd x1, Opd y1, Opd x2, Opd y2, bool neg2, SCR S
         return t;
     } else if constexpr (L == 64 || L == 128) {
         bool ok;
-        Meta t = arb_fdot2_trunc_blocked<L>(dst, x1, y1, x2, y2, neg2, S0, S1, &ok);
+        Meta t = arb_fdot2_trunc_blocked<L>(dst, x1, y1, x2, y2, neg2, lo_view(S0), lo_view(S1), &ok);  // L + 4 words
         CB_COUNT(ok ? 4 : 5);
         if (!ok) t = arb_fdot2<L>(dst, x1, y1, x2, y2, neg2, S0, S1);
         return t;
@@ -583,6 +583,7 @@ struct FrobParams {
     CArr tmp;  // FROB_NTMP entries
     CArr rhs;  // right-hand side series: rhs_len entries, S = 2*batch or 2 (ignored when rhs_len == 0)
     int64_t rhs_len;
+    uint32_t* gcols;  // 2048 bits and up: global tails of the two scratch columns, 2 * (L - 2) * batch words
 };
 constexpr int FROB_NTMP = 7;
 
@@ -1092,6 +1093,7 @@ struct HornerParams {
     CArr pts;       // 1 entry, S = 2*npts, or S = 2: one point for all series (continuation step)
     CArr out;       // nder entries, S = 2*npts
     CArr tmp;       // 1 entry, S = 2*npts
+    uint32_t* gcols;  // 2048 bits and up: global tails of the two scratch columns, 2 * (L - 2) * npts words
 };
 constexpr int HORNER_MAXDER = 4;
 

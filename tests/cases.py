@@ -341,6 +341,26 @@ def case_horner(oracle, drv, L: int, seed: int, length: int = 40, npts: int = 9)
                     f"horner L={L} nder={nder}")
 
 
+def case_horner_cancellation(oracle, drv, L: int, seed: int, length: int = 24, npts: int = 40):
+    """Points with re == im (and nearly so) under series whose coefficients have re == im (and nearly so): the
+    real part of every product o * a cancels completely or down to a few low bits, which defeats the guard-bit
+    proof of the truncated products and sends the step through the exact full-width path (at 2048 bits and up:
+    the part of the scratch columns that lives in global memory)."""
+    rng = np.random.default_rng(seed)
+    f = random_balls(rng, 2 * length, L, -3, 3, "ulp")
+    pts = random_balls(rng, 2 * npts, L, -2, 0, "zero")
+    for b, stride in ((f, 1), (pts, 1)):
+        b.mant[1::2] = b.mant[0::2]
+        b.meta[1::2] = b.meta[0::2]
+        n = b.n_slots // 2
+        for k in range(0, n, 3):  # every third value: im differs from re in one low bit
+            limb = int(rng.integers(0, 3))
+            b.mant[2 * k + 1, limb] ^= np.uint32(1 << int(rng.integers(0, 32)))
+    for nder in (1, 2):
+        assert_same(oracle.horner_batch(f, pts, nder), api.acb_poly_evaluate_batch(f, pts, nder, driver=drv),
+                    f"horner cancellation L={L} nder={nder}")
+
+
 def _frobenius_test_operator(rng, L: int, order: int, degree: int, dyadic: bool = False):
     """reference tests/frobenius.c:24-31: random operator with P[i][j] = 0 for j <= i and
     P[order][order] = P[order-1][order-1] = 1: valuation 0, rho = order - 2 a double indicial root."""

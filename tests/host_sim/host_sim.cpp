@@ -29,6 +29,19 @@ void run(int64_t count, F body) {
     Scratch<1> S0{s0.data()}, S1{s1.data()};
     for (int64_t i = 0; i < count; i++) body(i, S0, S1);
 }
+// the kernels that run on hybrid columns at 2048 bits and up (cb_kernels.cuh HybCfg): the same split here, with
+// exactly sized parts, so the mapping is checked on the CPU (and under AddressSanitizer)
+template <int L, class F>
+void run_hyb(int64_t count, F body) {
+    if constexpr (L >= 64) {
+        constexpr int KS = L + 5, GW = 2 * L + 3 - KS;
+        std::vector<uint32_t> s0(KS), s1(KS), g0(GW), g1(GW);
+        HybridScratch<1, KS> S0{s0.data(), g0.data(), 1u}, S1{s1.data(), g1.data(), 1u};
+        for (int64_t i = 0; i < count; i++) body(i, S0, S1);
+    } else {
+        run<L>(count, body);
+    }
+}
 #define SIM_DISPATCH(L_, CALL)                                \
     switch (L_) {                                             \
         case 4: { constexpr int L = 4; CALL; } break;         \
@@ -153,7 +166,8 @@ int cbsim_frobenius1_batch(int L_, int order, int degree, int valuation, int64_t
     p.res = CArr{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
     Tmp tmp;
     p.tmp = tmp.arr(L_, FROB_NTMP, 2 * batch);
-    SIM_DISPATCH(L_, run<L>(batch, [&](int64_t i, Scratch<1> a, Scratch<1> b) { frobenius1_thread<L>(p, i, a, b); }));
+    p.gcols = nullptr;
+    SIM_DISPATCH(L_, run_hyb<L>(batch, [&](int64_t i, auto a, auto b) { frobenius1_thread<L>(p, i, a, b); }));
     return 0;
 }
 
@@ -262,7 +276,8 @@ int cbsim_horner_batch(int L_, int64_t len, int64_t npts, int nder, const uint32
     p.out = CArr{out_mant, (Meta*)out_meta, (size_t)(2 * npts)};
     Tmp tmp;
     p.tmp = tmp.arr(L_, 1, 2 * npts);
-    SIM_DISPATCH(L_, run<L>(npts, [&](int64_t i, Scratch<1> a, Scratch<1> b) { horner_thread<L>(p, i, a, b); }));
+    p.gcols = nullptr;
+    SIM_DISPATCH(L_, run_hyb<L>(npts, [&](int64_t i, auto a, auto b) { horner_thread<L>(p, i, a, b); }));
     return 0;
 }
 
@@ -321,7 +336,8 @@ int cbsim_continuation(int L_, int order, int degree, int64_t n, int64_t batch, 
         hp.out = CArr{y_mant, (Meta*)y_meta, (size_t)S};
         Tmp tmp;
         hp.tmp = tmp.arr(L_, 1, S);
-        SIM_DISPATCH(L_, run<L>(batch, [&](int64_t i, Scratch<1> a, Scratch<1> b) { horner_thread<L>(hp, i, a, b); }));
+        hp.gcols = nullptr;
+        SIM_DISPATCH(L_, run_hyb<L>(batch, [&](int64_t i, auto a, auto b) { horner_thread<L>(hp, i, a, b); }));
     }
     return 0;
 }

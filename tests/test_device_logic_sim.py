@@ -57,6 +57,11 @@ def test_horner(oracle, sim_driver, L):
     cases.case_horner(oracle, sim_driver, L, seed=13)
 
 
+@pytest.mark.parametrize("L", [32, 64, 128])
+def test_horner_cancellation(oracle, sim_driver, L):
+    cases.case_horner_cancellation(oracle, sim_driver, L, seed=113 + L, length=12 if L == 128 else 24, npts=12)
+
+
 @pytest.mark.parametrize("L", [4, 32])
 def test_continuation(oracle, sim_driver, L):
     cases.case_continuation(oracle, sim_driver, L, seed=3 + L)

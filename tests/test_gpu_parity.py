@@ -54,9 +54,31 @@ def test_frobenius_singleton(oracle, gpu_driver):
     cases.case_frobenius_singleton(oracle, gpu_driver, 32, seed=21)
 
 
-@pytest.mark.parametrize("L", [4, 32, 64])
+@pytest.mark.parametrize("L", [4, 32, 64, 128])
 def test_horner(oracle, gpu_driver, L):
-    cases.case_horner(oracle, gpu_driver, L, seed=13, length=60, npts=333)
+    cases.case_horner(oracle, gpu_driver, L, seed=13, length=60 if L < 128 else 24, npts=333)
+
+
+@pytest.mark.parametrize("L", [32, 64, 128])
+def test_horner_cancellation(oracle, gpu_driver, L):
+    cases.case_horner_cancellation(oracle, gpu_driver, L, seed=113 + L, length=24, npts=300)
+
+
+def test_frobenius_2048(oracle, gpu_driver):
+    cases.case_frobenius(oracle, gpu_driver, 64, seed=19, n=20, batch=300)
+
+
+@pytest.mark.parametrize("hybrid", ["0", "1"])
+@pytest.mark.parametrize("L", [64, 128])
+def test_hybrid_scratch_columns(monkeypatch, oracle, gpu_driver, L, hybrid):
+    """2048 / 4096 bits: the Horner and Frobenius (M = 1) kernels exist with all-shared scratch columns and with
+    hybrid ones (L + 5 words in shared memory, the tail of the exact paths in global memory); the launcher picks by
+    batch size, so both are forced here -- including the cancellation case that needs the full-width path and the
+    long divisions of the Frobenius recurrence."""
+    monkeypatch.setenv("CB200_HYBRID", hybrid)
+    cases.case_horner(oracle, gpu_driver, L, seed=23, length=30, npts=300)
+    cases.case_horner_cancellation(oracle, gpu_driver, L, seed=213 + L, length=20, npts=300)
+    cases.case_frobenius(oracle, gpu_driver, L, seed=29, n=14, batch=300)
 
 
 @pytest.mark.parametrize("L", [32, 64])

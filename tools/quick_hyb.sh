@@ -1,0 +1,9 @@
+#!/bin/bash
+# development aid: all-shared against hybrid scratch columns at whole-wave sizes of both kernels
+for h in 0 1; do
+  echo "CB200_HYBRID=$h"
+  CB200_HYBRID=$h python tools/quick_general.py 128 198912 40 | grep "^frobenius" | tail -n 1
+  CB200_HYBRID=$h python tools/quick_general.py 64 113664 40 | grep "^frobenius" | tail -n 1
+  CB200_HYBRID=$h python tools/quick_horner.py 128 198912 60 | tail -n 1
+  CB200_HYBRID=$h python tools/quick_horner.py 64 113664 120 | tail -n 1
+done
