@@ -25,7 +25,7 @@ def test_fuchs_random_shared(oracle, sim_driver, L):
     cases.case_fuchs_random_shared(oracle, sim_driver, L, seed=31 + L, trials=6)
 
 
-@pytest.mark.parametrize("L", [4, 32])
+@pytest.mark.parametrize("L", [4, 32, 64])
 def test_fuchs_shared_adversarial(oracle, sim_driver, L):
     cases.case_fuchs_shared_adversarial(oracle, sim_driver, L, seed=77 + L, batch=12)
 
