@@ -1224,20 +1224,25 @@ CB_NOINLINE Meta arb_div(DST dst, OpdT<XS> x, OpdT<YS> y, SCR S0, SCR S1) {
         rad = mag_div(num, mag_mul_lower(yl, gap));
     }
     bool zx = is_zero_mid(x.t);
-    // U[0..2L] = x << 32L (U[2L] = 0), D[0..L) = y (made a harmless normalised dummy when nan)
+    // U[0..2L] = x << 32L (U[2L] = 0), D[0..L) = y (made a harmless normalised dummy when nan).
+    // Step j works on the window U[j .. j+L]; the words above it have cancelled to zero and the words below it
+    // are still the zeros of the shift, so U lives in a ring of R = L + 2 words of S0 (U[k] at word k mod R, the
+    // word entering the window cleared as it enters): the division touches words 0..L+1 of S0 only -- with a
+    // HybridScratch that is the shared-memory part.  After step 0 the window is U[0..L] at words 0..L.
+    constexpr int R = L + 2;
+    auto slot = [](int k) { return k >= R ? k - R : k; };  // k < 2R
 #pragma unroll
-    for (int j = 0; j < L; j++) S0.st(j, 0u);
-#pragma unroll
-    for (int j = 0; j < L; j++) S0.st(L + j, (zx || nan) ? 0u : x.r.ld(j));
-    S0.st(2 * L, 0u);
+    for (int j = 0; j < L; j++) S0.st(slot(L + j), (zx || nan) ? 0u : x.r.ld(j));
+    S0.st(slot(2 * L), 0u);
 #pragma unroll
     for (int j = 0; j < L; j++) S1.st(j, nan ? (j == L - 1 ? 0x80000000u : 0u) : y.r.ld(j));
     uint32_t d1 = S1.ld(L - 1), d0 = S1.ld(L - 2);
-    // quotient words q_j are kept in the upper half of S1 (words L..2L)
+    // quotient words q_j are kept in the upper half of S1 (words L..2L): written once, read once
     int hi = -1;
 #pragma unroll 1
     for (int j = L; j >= 0; j--) {
-        uint32_t u2 = S0.ld(j + L), u1 = S0.ld(j + L - 1), u0 = S0.ld(j + L - 2);
+        if (j < L) S0.st(j, 0u);  // U[j] enters the window (j < R: its own word)
+        uint32_t u2 = S0.ld(slot(j + L)), u1 = S0.ld(slot(j + L - 1)), u0 = S0.ld(slot(j + L - 2));
         uint64_t num = ((uint64_t)u2 << 32) | u1;
         uint64_t qh, rh;
         if (u2 >= d1) {
@@ -1251,28 +1256,39 @@ CB_NOINLINE Meta arb_div(DST dst, OpdT<XS> x, OpdT<YS> y, SCR S0, SCR S1) {
             qh--;
             rh += d1;
         }
-        // U[j .. j+L] -= qh * D
+        // U[j .. j+L] -= qh * D   (words j .. R-1 of the ring, then words 0 ..)
         uint32_t qd = (uint32_t)qh, borrow = 0u, mc = 0u;
+        const int n1 = (R - j) < L ? (R - j) : L;  // i < n1: no wrap
 #pragma unroll 8
-        for (int i = 0; i < L; i++) {
+        for (int i = 0; i < n1; i++) {
             uint64_t p = (uint64_t)qd * S1.ld(i) + mc;
             mc = (uint32_t)(p >> 32);
             uint64_t t = (uint64_t)S0.ld(i + j) - (uint32_t)p - borrow;
             S0.st(i + j, (uint32_t)t);
             borrow = (uint32_t)(t >> 32) & 1u;
         }
-        uint64_t t = (uint64_t)S0.ld(j + L) - mc - borrow;
-        S0.st(j + L, (uint32_t)t);
+#pragma unroll 8
+        for (int i = n1; i < L; i++) {
+            uint64_t p = (uint64_t)qd * S1.ld(i) + mc;
+            mc = (uint32_t)(p >> 32);
+            uint64_t t = (uint64_t)S0.ld(i + j - R) - (uint32_t)p - borrow;
+            S0.st(i + j - R, (uint32_t)t);
+            borrow = (uint32_t)(t >> 32) & 1u;
+        }
+        const int top = slot(j + L);
+        uint64_t t = (uint64_t)S0.ld(top) - mc - borrow;
+        S0.st(top, (uint32_t)t);
         if ((uint32_t)(t >> 32) & 1u) {  // one too large: add the divisor back
             qd--;
             uint32_t c = 0u;
 #pragma unroll 8
             for (int i = 0; i < L; i++) {
-                uint64_t s = (uint64_t)S0.ld(i + j) + S1.ld(i) + c;
-                S0.st(i + j, (uint32_t)s);
+                const int k = slot(i + j);
+                uint64_t s = (uint64_t)S0.ld(k) + S1.ld(i) + c;
+                S0.st(k, (uint32_t)s);
                 c = (uint32_t)(s >> 32);
             }
-            S0.st(j + L, S0.ld(j + L) + c);
+            S0.st(top, S0.ld(top) + c);
         }
         S1.st(L + j, qd);
         if (qd != 0u && hi < 0) hi = j;

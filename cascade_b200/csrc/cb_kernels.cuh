@@ -357,10 +357,10 @@ bool use_hybrid(int64_t count, int sms, double wave_ratio) {
 // time of a full wave of the hybrid kernel / time of a full wave of the all-shared kernel
 template <int L> struct HybRatio { static constexpr double HORNER = 1.0, FROB = 1.0; };
 // (B200, whole waves of both: Horner 2048 bits 5.45 -> 6.99 T limb-MAC/s, 4096 bits 4.79 -> 6.45; Frobenius M = 1
-// 2048 bits 2.34 -> 2.50, 4096 bits 2.25 -> 2.10 -- its long divisions run through the global tails --, so the
-// 4096-bit Frobenius kernel goes hybrid only where that saves a whole wave)
-template <> struct HybRatio<64> { static constexpr double HORNER = 1.04, FROB = 1.25; };
-template <> struct HybRatio<128> { static constexpr double HORNER = 1.27, FROB = 1.83; };
+// 2048 bits 2.30 -> 2.66, 4096 bits 2.21 -> 2.80 -- since the long division keeps its window in a ring of L + 2 words;
+// with the window sliding through the global tails the 4096-bit Frobenius kernel lost 7 %)
+template <> struct HybRatio<64> { static constexpr double HORNER = 1.04, FROB = 1.16; };
+template <> struct HybRatio<128> { static constexpr double HORNER = 1.27, FROB = 1.35; };
 
 // per-precision launch table, filled by kern_L*.cu
 struct LaunchTable {
