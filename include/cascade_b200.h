@@ -61,7 +61,14 @@ uint64_t cb200_kernel_launches(void);
  * carry-chain one; with CB200_RR_STATS=1 as well, out[0] / out[1] = those products accepted / rejected so far */
 int cb200_debug_rr_stats(uint64_t *out);
 
-/* ---- workspace sizes (bytes of device memory the _dev entry points need) ---- */
+/* ---- workspace sizes (bytes of device memory the _dev entry points need) ----
+ * Always ask these functions: what a workspace holds is the library's business and changes between builds (temporaries
+ * of the reference's loops, the multiplier table and scheduling words of the recurrence kernel, at 2048 bits and up
+ * the global-memory tails of the hybrid scratch columns of the Horner / Frobenius kernels).  The contents need no
+ * initialisation and carry nothing from one call to the next.
+ * Development switches read from the environment at launch time (no effect on results, only on which kernel form
+ * runs): CB200_PERSISTENT=0/1 (work-unit recurrence kernel), CB200_HYBRID=0/1 (hybrid scratch columns),
+ * CB200_TPB_CHOICE=0/1/2, CB200_RANGE=<coefficients per work unit>. */
 size_t cb200_fuchs_workspace_bytes(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
                                    int shared_ode);
 size_t cb200_frobenius_workspace_bytes(int L, int64_t batch);
