@@ -1237,6 +1237,10 @@ CB_NOINLINE Meta arb_div(DST dst, OpdT<XS> x, OpdT<YS> y, SCR S0, SCR S1) {
 #pragma unroll
     for (int j = 0; j < L; j++) S1.st(j, nan ? (j == L - 1 ? 0x80000000u : 0u) : y.r.ld(j));
     uint32_t d1 = S1.ld(L - 1), d0 = S1.ld(L - 2);
+    // reciprocal of the (normalised) top divisor word, v = floor((2^64 - 1) / d1) - 2^32: ONE 64-bit division per
+    // arb_div; every quotient-digit estimate below is then Moeller-Granlund's 2-by-1 division (two multiplies and
+    // two corrections, exact) instead of a 64-bit division subroutine
+    const uint32_t dinv = (uint32_t)(0xFFFFFFFFFFFFFFFFull / d1 - 0x100000000ull);
     // quotient words q_j are kept in the upper half of S1 (words L..2L): written once, read once
     int hi = -1;
 #pragma unroll 1
@@ -1248,9 +1252,20 @@ CB_NOINLINE Meta arb_div(DST dst, OpdT<XS> x, OpdT<YS> y, SCR S0, SCR S1) {
         if (u2 >= d1) {
             qh = 0xFFFFFFFFull;
             rh = num - qh * d1;
-        } else {
-            qh = num / d1;
-            rh = num - qh * d1;
+        } else {  // u2 < d1: (qh, rh) = divmod(u2:u1, d1)
+            uint64_t q = (uint64_t)dinv * u2 + num;
+            uint32_t q1 = (uint32_t)(q >> 32) + 1u, q0 = (uint32_t)q;
+            uint32_t r = u1 - q1 * d1;
+            if (r > q0) {
+                q1--;
+                r += d1;
+            }
+            if (r >= d1) {
+                q1++;
+                r -= d1;
+            }
+            qh = q1;
+            rh = r;
         }
         while (rh <= 0xFFFFFFFFull && qh * d0 > ((rh << 32) | u0)) {
             qh--;
