@@ -167,10 +167,12 @@ struct HybridScratch {
 };
 template <class S> struct ScrLo {
     using type = S;
+    static constexpr bool HYBRID = false;
     static CB_HD S get(S s) { return s; }
 };
 template <int ST, int KS> struct ScrLo<HybridScratch<ST, KS>> {
     using type = Scratch<ST>;
+    static constexpr bool HYBRID = true;
     static CB_HD Scratch<ST> get(HybridScratch<ST, KS> s) { return s.lo(); }
 };
 // the shared-memory part of a column (the column itself unless it is a HybridScratch)
@@ -1229,8 +1231,11 @@ CB_NOINLINE Meta arb_div(DST dst, OpdT<XS> x, OpdT<YS> y, SCR S0, SCR S1) {
     // are still the zeros of the shift, so U lives in a ring of R = L + 2 words of S0 (U[k] at word k mod R, the
     // word entering the window cleared as it enters): the division touches words 0..L+1 of S0 only -- with a
     // HybridScratch that is the shared-memory part.  After step 0 the window is U[0..L] at words 0..L.
-    constexpr int R = L + 2;
-    auto slot = [](int k) { return k >= R ? k - R : k; };  // k < 2R
+    // On an all-shared column the ring is as long as the numerator (no wrap, one unsplit inner loop: the split
+    // loops cost the 1024-bit logarithmic Frobenius kernel 9 %).
+    constexpr bool RING = ScrLo<SCR>::HYBRID;
+    constexpr int R = RING ? L + 2 : 2 * L + 2;
+    auto slot = [](int k) { return (RING && k >= R) ? k - R : k; };  // k < 2R
 #pragma unroll
     for (int j = 0; j < L; j++) S0.st(slot(L + j), (zx || nan) ? 0u : x.r.ld(j));
     S0.st(slot(2 * L), 0u);
@@ -1273,22 +1278,24 @@ CB_NOINLINE Meta arb_div(DST dst, OpdT<XS> x, OpdT<YS> y, SCR S0, SCR S1) {
         }
         // U[j .. j+L] -= qh * D   (words j .. R-1 of the ring, then words 0 ..)
         uint32_t qd = (uint32_t)qh, borrow = 0u, mc = 0u;
-        const int n1 = (R - j) < L ? (R - j) : L;  // i < n1: no wrap
+        const int n1 = (RING && (R - j) < L) ? (R - j) : L;  // i < n1: no wrap
 #pragma unroll 8
-        for (int i = 0; i < n1; i++) {
+        for (int i = 0; i < (RING ? n1 : L); i++) {
             uint64_t p = (uint64_t)qd * S1.ld(i) + mc;
             mc = (uint32_t)(p >> 32);
             uint64_t t = (uint64_t)S0.ld(i + j) - (uint32_t)p - borrow;
             S0.st(i + j, (uint32_t)t);
             borrow = (uint32_t)(t >> 32) & 1u;
         }
+        if constexpr (RING) {
 #pragma unroll 8
-        for (int i = n1; i < L; i++) {
-            uint64_t p = (uint64_t)qd * S1.ld(i) + mc;
-            mc = (uint32_t)(p >> 32);
-            uint64_t t = (uint64_t)S0.ld(i + j - R) - (uint32_t)p - borrow;
-            S0.st(i + j - R, (uint32_t)t);
-            borrow = (uint32_t)(t >> 32) & 1u;
+            for (int i = n1; i < L; i++) {
+                uint64_t p = (uint64_t)qd * S1.ld(i) + mc;
+                mc = (uint32_t)(p >> 32);
+                uint64_t t = (uint64_t)S0.ld(i + j - R) - (uint32_t)p - borrow;
+                S0.st(i + j - R, (uint32_t)t);
+                borrow = (uint32_t)(t >> 32) & 1u;
+            }
         }
         const int top = slot(j + L);
         uint64_t t = (uint64_t)S0.ld(top) - mc - borrow;
