@@ -26,8 +26,12 @@ SYMBOLS = [
     "cb200_fuchs_workspace_bytes", "cb200_frobenius_workspace_bytes",
     "cb200_horner_workspace_bytes", "cb200_ew_workspace_bytes",
     "cb200_fuchs_batch_dev", "cb200_fuchs_batch_host", "cb200_fuchs_batch_range_dev",
+    "cb200_host_alloc", "cb200_host_free", "cb200_host_cache_release",
     "cb200_fuchs_intop_batch_dev", "cb200_fuchs_intop_batch_host",
     "cb200_continuation_workspace_bytes", "cb200_continuation_dev", "cb200_continuation_host",
+    "cb200_continuation_series_workspace_bytes", "cb200_continuation_series_dev", "cb200_continuation_series_host",
+    "cb200_ode_shift_workspace_bytes", "cb200_ode_shift_dev", "cb200_ode_shift_host",
+    "cb200_taylor_shift_workspace_bytes", "cb200_taylor_shift_dev", "cb200_taylor_shift_host",
     "cb200_frobenius1_batch_dev", "cb200_frobenius1_batch_host",
     "cb200_frobenius1_rhs_batch_dev", "cb200_frobenius1_rhs_batch_host",
     "cb200_horner_batch_dev", "cb200_horner_batch_host",
@@ -66,6 +70,10 @@ def lib() -> C.CDLL:
         getattr(L, name).argtypes = [C.c_int, C.c_int64]
     L.cb200_fuchs_batch_dev.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_vp, _vp, C.c_int, _vp, _vp, _vp, C.c_size_t, _vp]
     L.cb200_fuchs_batch_range_dev.argtypes = [C.c_int] * 4 + [C.c_int64] * 3 + [_vp, _vp, C.c_int, _vp, _vp, _vp, C.c_size_t, _vp]
+    L.cb200_host_alloc.restype = C.c_void_p
+    L.cb200_host_alloc.argtypes = [C.c_size_t]
+    L.cb200_host_free.argtypes = [C.c_void_p]
+    L.cb200_host_cache_release.restype = None
     L.cb200_fuchs_batch_host.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int]
     _i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
     L.cb200_fuchs_intop_batch_dev.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_vp, C.c_int, _vp, _vp, _vp]
@@ -76,6 +84,22 @@ def lib() -> C.CDLL:
                                          _vp, _vp, _vp, _vp, C.c_size_t, _vp]
     L.cb200_continuation_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, _u32p, _i32p,
                                           _u32p, _i32p, _u32p, _i32p, C.c_int]
+    L.cb200_continuation_series_workspace_bytes.restype = C.c_size_t
+    L.cb200_continuation_series_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64]
+    L.cb200_continuation_series_dev.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp,
+                                                _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]
+    L.cb200_continuation_series_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, _u32p, _i32p,
+                                                 _u32p, _i32p, _u32p, _i32p, _u32p, _i32p, C.c_int]
+    L.cb200_ode_shift_workspace_bytes.restype = C.c_size_t
+    L.cb200_ode_shift_workspace_bytes.argtypes = [C.c_int, C.c_int64]
+    L.cb200_ode_shift_dev.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp,
+                                      C.c_size_t, _vp]
+    L.cb200_ode_shift_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, _u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int,
+                                       _u32p, _i32p, C.c_int]
+    L.cb200_taylor_shift_workspace_bytes.restype = C.c_size_t
+    L.cb200_taylor_shift_workspace_bytes.argtypes = [C.c_int, C.c_int64, C.c_int64]
+    L.cb200_taylor_shift_dev.argtypes = [C.c_int, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_size_t, _vp]
+    L.cb200_taylor_shift_host.argtypes = [C.c_int, C.c_int64, C.c_int64, _u32p, _i32p, _u32p, _i32p, C.c_int, C.c_int]
     L.cb200_frobenius1_batch_dev.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_size_t, _vp]
     L.cb200_frobenius1_batch_host.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int]
     L.cb200_frobenius1_rhs_batch_dev.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_int64, C.c_int, _vp, _vp, _vp, C.c_size_t, _vp]

@@ -41,6 +41,17 @@ class HostBufferDriver:
         return _lib.lib().cb200_continuation_host(L, order, degree, n, batch, path_len, ode_m, ode_t, path_m, path_t,
                                                   y_m, y_t, self.device)
 
+    def continuation_series(self, L, order, degree, n, batch, path_len, ode_m, ode_t, path_m, path_t, y_m, y_t, r_m, r_t):
+        return _lib.lib().cb200_continuation_series_host(L, order, degree, n, batch, path_len, ode_m, ode_t, path_m, path_t,
+                                                         y_m, y_t, r_m, r_t, self.device)
+
+    def ode_shift(self, L, order, degree, batch, ode_m, ode_t, shared, a_m, a_t, shared_a, o_m, o_t):
+        return _lib.lib().cb200_ode_shift_host(L, order, degree, batch, ode_m, ode_t, int(shared), a_m, a_t, int(shared_a),
+                                               o_m, o_t, self.device)
+
+    def taylor_shift(self, L, length, batch, f_m, f_t, a_m, a_t, shared_a):
+        return _lib.lib().cb200_taylor_shift_host(L, length, batch, f_m, f_t, a_m, a_t, int(shared_a), self.device)
+
     def frobenius1(self, L, order, degree, valuation, n, batch, ode_m, ode_t, shared, rho_m, rho_t,
                    shared_rho, res_m, res_t, rhs_m=None, rhs_t=None, rhs_len=0, shared_rhs=False):
         vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
@@ -110,6 +121,37 @@ def acb_ode_valuation(ode: Balls, order: int, degree: int, inst: int = 0) -> int
     return val
 
 
+def acb_ode_valuations(ode: Balls, order: int, degree: int) -> np.ndarray:
+    """``acb_ode_valuation`` of every operator of an ``[instances][entries]`` array at once (one vectorised
+    exact-zero scan of the ball records): int64 ``[instances]``."""
+    ne = (order + 1) * (degree + 1)
+    meta = ode.meta.reshape(-1, ne, 2, 4)
+    exact_zero = ((meta[..., 1] & FLAG_ZERO) != 0) & (meta[..., 2] == 0)
+    zero = exact_zero.all(axis=-1).reshape(-1, order + 1, degree + 1)
+    # ord_z p_i = index of the first coefficient that is not an exact zero (degree + 1 for the zero row)
+    nz = ~zero
+    first = np.where(nz.any(axis=-1), nz.argmax(axis=-1), degree + 1)
+    val = (first - np.arange(order + 1)[None, :]).min(axis=-1)
+    return np.minimum(val, degree).astype(np.int64)
+
+
+def batch_valuation(ode: Balls, order: int, degree: int, shared: bool, what: str) -> int:
+    """The ONE valuation a batched launch runs with.  The kernels take a single scalar valuation per launch
+    (include/cascade_b200.h), so operators that differ between instances must all have the same valuation;
+    exact-zero coefficients (``acb_ode_random`` emits them) can make them differ, and such a batch is rejected
+    here instead of being solved with the wrong recurrence window.  Split it by valuation and call per group."""
+    if shared:
+        return acb_ode_valuation(ode, order, degree)
+    vals = acb_ode_valuations(ode, order, degree)
+    if vals.size and (vals != vals[0]).any():
+        uniq = np.unique(vals)
+        raise _lib.CascadeB200Error(
+            f"{what}: the operators of this batch have different valuations {uniq.tolist()} "
+            f"(instance {int(np.argmax(vals != vals[0]))} differs from instance 0); a batched launch runs with one "
+            "valuation -- group the instances by acb_ode_valuations() and solve each group")
+    return int(vals[0]) if vals.size else acb_ode_valuation(ode, order, degree)
+
+
 def _ode_to_device(ode: Balls, order: int, degree: int, batch: int, shared: bool):
     ne = (order + 1) * (degree + 1)
     nb = 1 if shared else batch
@@ -160,7 +202,7 @@ def acb_ode_solve_fuchs_batch(ode: Balls, init: Balls, order: int, degree: int, 
     reference)."""
     drv = driver or default_driver()
     L = ode.L
-    v = acb_ode_valuation(ode, order, degree) if valuation is None else valuation
+    v = batch_valuation(ode, order, degree, shared_ode, "acb_ode_solve_fuchs_batch") if valuation is None else valuation
     if v >= 0:
         _lib.check(_lib.EVALUATION, "acb_ode_solve_fuchs_batch")
     ninit = -v
@@ -191,7 +233,7 @@ def acb_ode_solve_frobenius1_batch(ode: Balls, rho: Balls, order: int, degree: i
     rho - valuation and g_0 = rhs_0 / f_0(rho) as the reference does (:86-96)."""
     drv = driver or default_driver()
     L = ode.L
-    v = acb_ode_valuation(ode, order, degree) if valuation is None else valuation
+    v = batch_valuation(ode, order, degree, shared_ode, "acb_ode_solve_frobenius1_batch") if valuation is None else valuation
     ode_m, ode_t = _ode_to_device(ode, order, degree, batch, shared_ode)
     nr = 1 if shared_rho else batch
     rho_m, rho_t = pack_entries(rho, 1, 2 * nr)
@@ -219,7 +261,7 @@ def acb_ode_solve_frobenius_batch(ode: Balls, rho: Balls, mul: int, alpha: int, 
     if M == 1:
         return acb_ode_solve_frobenius1_batch(ode, rho, order, degree, n, batch, shared_ode, shared_rho, valuation, drv)
     L = ode.L
-    v = acb_ode_valuation(ode, order, degree) if valuation is None else valuation
+    v = batch_valuation(ode, order, degree, shared_ode, "acb_ode_solve_frobenius_batch") if valuation is None else valuation
     ode_m, ode_t = _ode_to_device(ode, order, degree, batch, shared_ode)
     rho_m, rho_t = pack_entries(rho, 1, 2 * (1 if shared_rho else batch))
     ng = M * (n + 1)
@@ -258,7 +300,7 @@ def indicial_polynomial_batch(ode: Balls, order: int, degree: int, nu: int, shif
     ``[batch][order+1]`` coefficients of f_nu(rho + shift) as a polynomial in rho."""
     drv = driver or default_driver()
     L = ode.L
-    v = acb_ode_valuation(ode, order, degree) if valuation is None else valuation
+    v = batch_valuation(ode, order, degree, shared_ode, "indicial_polynomial_batch") if valuation is None else valuation
     ode_m, ode_t = _ode_to_device(ode, order, degree, batch, shared_ode)
     o_m = np.zeros((order + 2, L, 2 * batch), np.uint32)
     o_t = np.zeros((order + 2, 2 * batch, 4), np.int32)
@@ -284,6 +326,38 @@ def analytic_continuation_batch(ode: Balls, path: Balls, y0: Balls, order: int, 
     _lib.check(drv.continuation(L, order, degree, n, batch, plen, ode_m, ode_t, path_m, path_t, y_m, y_t),
                "analytic_continuation_batch")
     return entry_major_to_instance_major(unpack_entries(L, y_m, y_t), batch, order)
+
+
+def analytic_continuation_series_batch(ode: Balls, path: Balls, y0: Balls, order: int, degree: int, n: int, batch: int,
+                                       driver=None):
+    """``analytic_continuation`` keeping everything the reference leaves in ``res`` (src/fuchs_solver.c:159): returns
+    (y ``[batch][order]``, series ``[batch][n+1]``), the series being the complete re-expansion at the last corner
+    (``acb_poly_taylor_shift``, Horner form)."""
+    drv = driver or default_driver()
+    L = ode.L
+    plen = path.n_slots // 2
+    ode_m, ode_t = _ode_to_device(ode, order, degree, batch, True)
+    path_m, path_t = pack_entries(path, plen, 2)
+    y_m, y_t = pack_entries(instance_major_to_entry_major(y0, batch, order), order, 2 * batch)
+    r_m = np.zeros((n + 1, L, 2 * batch), np.uint32)
+    r_t = np.zeros((n + 1, 2 * batch, 4), np.int32)
+    _lib.check(drv.continuation_series(L, order, degree, n, batch, plen, ode_m, ode_t, path_m, path_t, y_m, y_t, r_m, r_t),
+               "analytic_continuation_series_batch")
+    return (entry_major_to_instance_major(unpack_entries(L, y_m, y_t), batch, order),
+            entry_major_to_instance_major(unpack_entries(L, r_m, r_t), batch, n + 1))
+
+
+def acb_poly_taylor_shift_batch(f: Balls, a: Balls, batch: int, driver=None) -> Balls:
+    """``acb_poly_taylor_shift(f, f, a)`` (reference src/fuchs_solver.c:159) for ``batch`` series ``f[batch][len]``;
+    ``a``: ``[batch]`` balls or one shared ball.  Horner form, O(len^2) ball operations per series."""
+    drv = driver or default_driver()
+    L = f.L
+    length = f.n_slots // (2 * batch)
+    shared_a = a.n_slots == 2
+    f_m, f_t = pack_entries(instance_major_to_entry_major(f, batch, length), length, 2 * batch)
+    a_m, a_t = pack_entries(a, 1, 2 if shared_a else 2 * batch)
+    _lib.check(drv.taylor_shift(L, length, batch, f_m, f_t, a_m, a_t, shared_a), "acb_poly_taylor_shift_batch")
+    return entry_major_to_instance_major(unpack_entries(L, f_m, f_t), batch, length)
 
 
 def acb_poly_evaluate_batch(f: Balls, pts: Balls, nder: int = 1, driver=None) -> Balls:
@@ -456,24 +530,15 @@ def acb_ode_hypgeom_batch(a: Balls, b: Balls, c: Balls, driver=None) -> Balls:
 
 def acb_ode_shift_batch(ode: Balls, a: Balls, order: int, degree: int, driver=None) -> Balls:
     """``acb_ode_shift(out, in, a, bits)`` for a batch (reference src/acb_ode.c:124-135): every row
-    p_i(z) becomes p_i(z + a) by the Horner Taylor shift  p[j] += p[j+1] * a."""
+    p_i(z) becomes p_i(z + a) by the Horner Taylor shift  p[j] += p[j+1] * a, one launch for the batch.
+    ``ode``: ``[batch][entries]`` or one operator (then it is moved to each of the ``batch`` points of ``a``)."""
+    drv = driver or default_driver()
     L, batch = ode.L, a.n_slots // 2
     ne = (order + 1) * (degree + 1)
-    out = ode.copy()
-    if degree == 0:
-        return out
-    m = out.mant.reshape(batch, order + 1, degree + 1, 2, L)
-    t = out.meta.reshape(batch, order + 1, degree + 1, 2, 4)
-    # all rows of all instances advance together: one MUL and one ADD launch per (i, j) step
-    rows = (order + 1) * batch
-    arow = Balls(L, np.repeat(a.mant.reshape(batch, 1, 2, L), order + 1, axis=1).reshape(-1, L),
-                 np.repeat(a.meta.reshape(batch, 1, 2, 4), order + 1, axis=1).reshape(-1, 4))
-    n = degree + 1
-    for i in range(n - 2, -1, -1):
-        for j in range(i, n - 1):
-            pj1 = Balls(L, m[:, :, j + 1].reshape(rows * 2, L).copy(), t[:, :, j + 1].reshape(rows * 2, 4).copy())
-            pj = Balls(L, m[:, :, j].reshape(rows * 2, L).copy(), t[:, :, j].reshape(rows * 2, 4).copy())
-            s = ew(OP_ADD, pj, ew(OP_MUL, pj1, arow, driver=driver), driver=driver)
-            m[:, :, j] = s.mant.reshape(batch, order + 1, 2, L)
-            t[:, :, j] = s.meta.reshape(batch, order + 1, 2, 4)
-    return out
+    shared = ode.n_slots == 2 * ne and batch != 1
+    ode_m, ode_t = _ode_to_device(ode, order, degree, batch, shared)
+    a_m, a_t = pack_entries(a, 1, 2 * batch)
+    o_m = np.zeros((ne, L, 2 * batch), np.uint32)
+    o_t = np.zeros((ne, 2 * batch, 4), np.int32)
+    _lib.check(drv.ode_shift(L, order, degree, batch, ode_m, ode_t, shared, a_m, a_t, False, o_m, o_t), "acb_ode_shift_batch")
+    return entry_major_to_instance_major(unpack_entries(L, o_m, o_t), batch, ne)

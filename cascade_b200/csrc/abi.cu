@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 #include "../../include/cascade_b200.h"
@@ -547,30 +548,96 @@ int cb200_ew_dev(int op, int L_, int64_t n, uint32_t* z_mant, cb_meta* z_meta, c
     return table_for(L_)->ew(p, (cudaStream_t)stream);
 }
 
-// ------------------------------------------------------------------ analytic continuation
-size_t cb200_continuation_workspace_bytes(int L, int order, int degree, int64_t n, int64_t batch) {
-    int64_t ne = (int64_t)(order + 1) * (degree + 1);
-    return carve_bytes(L, ne, 2)            /* shifted operator */
-           + carve_bytes(L, 3, 2)           /* step, product and sum temporaries (single balls) */
-           + carve_bytes(L, n + 1, 2 * batch) /* the series of the current step */
-           + cb200_fuchs_workspace_bytes(L, order, degree, -order, n, batch, 1) + cb200_horner_workspace_bytes(L, batch) +
-           cb200_ew_workspace_bytes(L, 1) + 1024;
+// ------------------------------------------------------------------ acb_ode_shift, acb_poly_taylor_shift
+size_t cb200_ode_shift_workspace_bytes(int L, int64_t batch) { return carve_bytes(L, 1, 2 * batch); }
+int cb200_ode_shift_dev(int L_, int order, int degree, int64_t batch, const uint32_t* ode_mant, const cb_meta* ode_meta,
+                        int shared_ode, const uint32_t* a_mant, const cb_meta* a_meta, int shared_a, uint32_t* out_mant,
+                        cb_meta* out_meta, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!supported_L(L_) || order < 0 || degree < 0 || batch < 0) return CB200_EINVAL;
+    if (workspace_bytes < cb200_ode_shift_workspace_bytes(L_, batch)) return CB200_ENOMEM;
+    ShiftParams p;
+    p.order = order;
+    p.degree = degree;
+    p.batch = batch;
+    p.in = CArr{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta), shared_ode ? (size_t)2 : (size_t)(2 * batch)};
+    p.a = CArr{const_cast<uint32_t*>(a_mant), (Meta*)const_cast<cb_meta*>(a_meta), shared_a ? (size_t)2 : (size_t)(2 * batch)};
+    p.out = CArr{out_mant, (Meta*)out_meta, (size_t)(2 * batch)};
+    char* w = (char*)workspace;
+    p.tmp = carve(w, L_, 1, 2 * batch);
+    g_launches.fetch_add(batch > 0);
+    return table_for(L_)->ode_shift(p, (cudaStream_t)stream);
+}
+size_t cb200_taylor_shift_workspace_bytes(int L, int64_t len, int64_t batch) { return carve_bytes(L, len > 0 ? len : 1, 2 * batch); }
+int cb200_taylor_shift_dev(int L_, int64_t len, int64_t batch, uint32_t* f_mant, cb_meta* f_meta, const uint32_t* a_mant,
+                           const cb_meta* a_meta, int shared_a, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!supported_L(L_) || len < 0 || batch < 0) return CB200_EINVAL;
+    if (workspace_bytes < cb200_taylor_shift_workspace_bytes(L_, len, batch)) return CB200_ENOMEM;
+    TShiftParams p;
+    p.len = len;
+    p.batch = batch;
+    p.f = CArr{f_mant, (Meta*)f_meta, (size_t)(2 * batch)};
+    p.a = CArr{const_cast<uint32_t*>(a_mant), (Meta*)const_cast<cb_meta*>(a_meta), shared_a ? (size_t)2 : (size_t)(2 * batch)};
+    char* w = (char*)workspace;
+    p.tmp = carve(w, L_, len > 0 ? len : 1, 2 * batch);
+    g_launches.fetch_add(batch > 0 && len > 1);
+    return table_for(L_)->taylor_shift(p, (cudaStream_t)stream);
 }
 
-int cb200_continuation_dev(int L_, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
-                           const uint32_t* ode_mant, const cb_meta* ode_meta, const uint32_t* path_mant,
-                           const cb_meta* path_meta, const uint8_t* corner_is_zero, uint32_t* y_mant, cb_meta* y_meta,
-                           void* workspace, size_t workspace_bytes, void* stream) {
+// ------------------------------------------------------------------ analytic continuation
+static size_t fuchs_ws_any_valuation(int L, int order, int degree, int64_t n, int64_t batch) {
+    size_t m = 0;
+    for (int v = -order; v <= -1; v++) {
+        size_t b = cb200_fuchs_workspace_bytes(L, order, degree, v, n, batch, 1);
+        if (b > m) m = b;
+    }
+    return m;
+}
+static size_t continuation_ws(int L, int order, int degree, int64_t n, int64_t batch, bool series) {
+    int64_t ne = (int64_t)(order + 1) * (degree + 1);
+    return carve_bytes(L, ne, 2)            /* shifted operator */
+           + carve_bytes(L, 3, 2)           /* step, and two single-ball temporaries */
+           + carve_bytes(L, n + 1, 2 * batch) /* the series of the current step */
+           + align256(fuchs_ws_any_valuation(L, order, degree, n, batch)) + align256(cb200_horner_workspace_bytes(L, batch)) +
+           align256(cb200_ew_workspace_bytes(L, 1)) + (series ? align256(cb200_taylor_shift_workspace_bytes(L, n + 1, batch)) : 0) +
+           1024;
+}
+size_t cb200_continuation_workspace_bytes(int L, int order, int degree, int64_t n, int64_t batch) {
+    return continuation_ws(L, order, degree, n, batch, false);
+}
+size_t cb200_continuation_series_workspace_bytes(int L, int order, int degree, int64_t n, int64_t batch) {
+    return continuation_ws(L, order, degree, n, batch, true);
+}
+
+// acb_ode_valuation (reference src/acb_ode.c:159-181) from the meta records of one operator (S = 2)
+static int valuation_of(const cb_meta* t, int order, int degree) {
+    int val = degree;
+    for (int i = 0; i <= order; i++) {
+        int z = 0;
+        for (; z <= degree; z++) {
+            const cb_meta* c = t + 2 * (i * (degree + 1) + z);
+            bool zero = (c[0].flags & CB_FLAG_ZERO) && c[0].rman == 0 && (c[1].flags & CB_FLAG_ZERO) && c[1].rman == 0;
+            if (!zero) break;
+        }
+        if (z - i < val) val = z - i;
+    }
+    return val;
+}
+
+static int continuation_impl(int L_, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
+                             const uint32_t* ode_mant, const cb_meta* ode_meta, const uint32_t* path_mant,
+                             const cb_meta* path_meta, uint32_t* y_mant, cb_meta* y_meta, uint32_t* full_mant,
+                             cb_meta* full_meta, void* workspace, size_t workspace_bytes, void* stream) {
     if (!supported_L(L_) || order < 1 || order > HORNER_MAXDER || degree < 0 || batch < 0 || n < order || path_len < 1)
         return CB200_EINVAL;
-    if (workspace_bytes < cb200_continuation_workspace_bytes(L_, order, degree, n, batch)) return CB200_ENOMEM;
+    const bool series = full_mant != nullptr;
+    if (workspace_bytes < continuation_ws(L_, order, degree, n, batch, series)) return CB200_ENOMEM;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t ne = (int64_t)(order + 1) * (degree + 1), S = 2 * batch;
     char* w = (char*)workspace;
     CArr sh = carve(w, L_, ne, 2);
-    CArr tb = carve(w, L_, 3, 2);  // [0] step a, [1] product, [2] sum
+    CArr tb = carve(w, L_, 3, 2);  // [0] step a, [1] temporary of the operator shift
     CArr ser = carve(w, L_, n + 1, S);
-    size_t fw = cb200_fuchs_workspace_bytes(L_, order, degree, -order, n, batch, 1);
+    size_t fw = fuchs_ws_any_valuation(L_, order, degree, n, batch);
     void* fws = w;
     w += align256(fw);
     size_t hw = cb200_horner_workspace_bytes(L_, batch);
@@ -578,41 +645,54 @@ int cb200_continuation_dev(int L_, int order, int degree, int64_t n, int64_t bat
     w += align256(hw);
     size_t ew = cb200_ew_workspace_bytes(L_, 1);
     void* ews = w;
+    w += align256(ew);
+    void* tws = w;
+    const size_t tw = series ? cb200_taylor_shift_workspace_bytes(L_, n + 1, batch) : 0;
     auto ball_m = [&](const CArr& a, int64_t e) { return a.m + (size_t)e * L_ * a.S; };
     auto ball_t = [&](const CArr& a, int64_t e) { return (cb_meta*)(a.t + (size_t)e * a.S); };
-    const size_t ball_mb = arr_mant_bytes(L_, 1, 2), ball_tb = arr_meta_bytes(1, 2);
+    std::vector<cb_meta> hmeta((size_t)ne * 2);
     for (int64_t t = 0; t + 1 < path_len; t++) {
-        // acb_ode_shift(ODE_shift, ODE, path + t): copy, then p[j] += p[j+1] * a (Horner Taylor shift)
-        CUDA_RET(cudaMemcpyAsync(sh.m, ode_mant, arr_mant_bytes(L_, ne, 2), cudaMemcpyDeviceToDevice, st));
-        CUDA_RET(cudaMemcpyAsync(sh.t, ode_meta, arr_meta_bytes(ne, 2), cudaMemcpyDeviceToDevice, st));
+        // acb_ode_shift(ODE_shift, ODE, path + t): one launch (an exactly zero corner leaves the operator as it is)
         const uint32_t* am = path_mant + (size_t)t * L_ * 2;
         const cb_meta* at_ = path_meta + (size_t)t * 2;
-        if (degree > 0 && !(corner_is_zero && corner_is_zero[t])) {
-            int D1 = degree + 1;
-            for (int row = 0; row <= order; row++)
-                for (int i = D1 - 2; i >= 0; i--)
-                    for (int j = i; j <= D1 - 2; j++) {
-                        int64_t ej = (int64_t)row * D1 + j;
-                        int rc = cb200_ew_dev(CB200_OP_MUL, L_, 1, ball_m(tb, 1), ball_t(tb, 1), ball_m(sh, ej + 1),
-                                              ball_t(sh, ej + 1), am, at_, nullptr, ews, ew, stream);
-                        if (rc) return rc;
-                        rc = cb200_ew_dev(CB200_OP_ADD, L_, 1, ball_m(tb, 2), ball_t(tb, 2), ball_m(sh, ej), ball_t(sh, ej),
-                                          ball_m(tb, 1), ball_t(tb, 1), nullptr, ews, ew, stream);
-                        if (rc) return rc;
-                        CUDA_RET(cudaMemcpyAsync(ball_m(sh, ej), ball_m(tb, 2), ball_mb, cudaMemcpyDeviceToDevice, st));
-                        CUDA_RET(cudaMemcpyAsync(ball_t(sh, ej), ball_t(tb, 2), ball_tb, cudaMemcpyDeviceToDevice, st));
-                    }
-        }
-        // acb_ode_solve_fuchs(res, ODE_shift, n): res[0..order-1] = y (an ordinary point: valuation = -order)
-        CUDA_RET(cudaMemcpyAsync(ser.m, y_mant, arr_mant_bytes(L_, order, S), cudaMemcpyDeviceToDevice, st));
-        CUDA_RET(cudaMemcpyAsync(ser.t, y_meta, arr_meta_bytes(order, S), cudaMemcpyDeviceToDevice, st));
-        int rc = cb200_fuchs_batch_dev(L_, order, degree, -order, n, batch, sh.m, (cb_meta*)sh.t, 1, ser.m, (cb_meta*)ser.t,
-                                       fws, fw, stream);
+        ShiftParams shp;
+        shp.order = order;
+        shp.degree = degree;
+        shp.batch = 1;
+        shp.in = CArr{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta), (size_t)2};
+        shp.a = CArr{const_cast<uint32_t*>(am), (Meta*)const_cast<cb_meta*>(at_), (size_t)2};
+        shp.out = sh;
+        shp.tmp = CArr{ball_m(tb, 1), (Meta*)ball_t(tb, 1), (size_t)2};
+        g_launches.fetch_add(1);
+        int rc = table_for(L_)->ode_shift(shp, st);
         if (rc) return rc;
-        // a = path[t+1] - path[t]; y[k] = res^(k)(a)/k! for k < order (all that the next step reads)
+        // acb_ode_solve_fuchs starts from the valuation of the SHIFTED operator (src/fuchs_solver.c:105): 288 bytes of
+        // meta records come back to the host, once per corner (the only synchronisation of the pipeline)
+        CUDA_RET(cudaMemcpyAsync(hmeta.data(), sh.t, arr_meta_bytes(ne, 2), cudaMemcpyDeviceToHost, st));
+        CUDA_RET(cudaStreamSynchronize(st));
+        const int v = valuation_of(hmeta.data(), order, degree);
+        if (v >= 0) return CB200_EVALUATION;
+        // res[0 .. -v-1] = y (the reference reads only those of res as initial values)
+        CUDA_RET(cudaMemcpyAsync(ser.m, y_mant, arr_mant_bytes(L_, -v, S), cudaMemcpyDeviceToDevice, st));
+        CUDA_RET(cudaMemcpyAsync(ser.t, y_meta, arr_meta_bytes(-v, S), cudaMemcpyDeviceToDevice, st));
+        rc = cb200_fuchs_batch_dev(L_, order, degree, v, n, batch, sh.m, (cb_meta*)sh.t, 1, ser.m, (cb_meta*)ser.t, fws, fw,
+                                   stream);
+        if (rc) return rc;
+        // a = path[t+1] - path[t]
         rc = cb200_ew_dev(CB200_OP_SUB, L_, 1, ball_m(tb, 0), ball_t(tb, 0), path_mant + (size_t)(t + 1) * L_ * 2,
                           path_meta + (size_t)(t + 1) * 2, am, at_, nullptr, ews, ew, stream);
         if (rc) return rc;
+        if (series && t + 2 == path_len) {
+            // the last corner: the complete acb_poly_taylor_shift, as the reference leaves it in res (:159)
+            rc = cb200_taylor_shift_dev(L_, n + 1, batch, ser.m, (cb_meta*)ser.t, ball_m(tb, 0), ball_t(tb, 0), 1, tws, tw, stream);
+            if (rc) return rc;
+            CUDA_RET(cudaMemcpyAsync(full_mant, ser.m, arr_mant_bytes(L_, n + 1, S), cudaMemcpyDeviceToDevice, st));
+            CUDA_RET(cudaMemcpyAsync(full_meta, ser.t, arr_meta_bytes(n + 1, S), cudaMemcpyDeviceToDevice, st));
+            CUDA_RET(cudaMemcpyAsync(y_mant, ser.m, arr_mant_bytes(L_, order, S), cudaMemcpyDeviceToDevice, st));
+            CUDA_RET(cudaMemcpyAsync(y_meta, ser.t, arr_meta_bytes(order, S), cudaMemcpyDeviceToDevice, st));
+            break;
+        }
+        // y[k] = res^(k)(a)/k! for k < order (all that the next step reads)
         HornerParams hp;
         hp.nder = order;
         hp.len = n + 1;
@@ -630,6 +710,23 @@ int cb200_continuation_dev(int L_, int order, int degree, int64_t n, int64_t bat
     return 0;
 }
 
+int cb200_continuation_dev(int L_, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
+                           const uint32_t* ode_mant, const cb_meta* ode_meta, const uint32_t* path_mant,
+                           const cb_meta* path_meta, const uint8_t* corner_is_zero, uint32_t* y_mant, cb_meta* y_meta,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+    (void)corner_is_zero;  // kept for ABI stability: the shift kernel recognises an exactly zero corner itself
+    return continuation_impl(L_, order, degree, n, batch, path_len, ode_mant, ode_meta, path_mant, path_meta, y_mant, y_meta,
+                             nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+int cb200_continuation_series_dev(int L_, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
+                                  const uint32_t* ode_mant, const cb_meta* ode_meta, const uint32_t* path_mant,
+                                  const cb_meta* path_meta, uint32_t* y_mant, cb_meta* y_meta, uint32_t* res_mant,
+                                  cb_meta* res_meta, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!res_mant || !res_meta || path_len < 2) return CB200_EINVAL;
+    return continuation_impl(L_, order, degree, n, batch, path_len, ode_mant, ode_meta, path_mant, path_meta, y_mant, y_meta,
+                             res_mant, res_meta, workspace, workspace_bytes, stream);
+}
+
 
 // ------------------------------------------------------------------ host-buffer (end-to-end) entry points
 #define CK(x)                                \
@@ -638,30 +735,143 @@ int cb200_continuation_dev(int L_, int order, int degree, int64_t n, int64_t bat
         if (e_ != cudaSuccess) return (int)e_; \
     } while (0)
 
+// ---- pinned host memory for callers without CUDA headers (result buffers of the *_host entry points: copies into
+// page-locked memory run at PCIe speed and overlap the kernels; pageable buffers work too, more slowly)
+void* cb200_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void cb200_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+namespace {
+// Device buffers, streams and events of the host-buffer solver, kept between calls (a lazily created context:
+// allocating and freeing tens of GB per call would cost a few per cent of a BASELINE-size solve).  One per process,
+// guarded by a mutex; cb200_host_cache_release() frees it.
+struct HostCallCache {
+    std::mutex mu;
+    int device = -1;
+    void* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t cap[5] = {0, 0, 0, 0, 0};
+    cudaStream_t comp = nullptr, copy = nullptr;
+    std::vector<cudaEvent_t> ev;
+    cudaError_t reserve(int i, size_t n) {
+        if (cap[i] >= n && buf[i]) return cudaSuccess;
+        if (buf[i]) cudaFree(buf[i]);
+        buf[i] = nullptr;
+        cap[i] = 0;
+        cudaError_t e = cudaMalloc(&buf[i], n ? n : 1);
+        if (e == cudaSuccess) cap[i] = n;
+        return e;
+    }
+    void release() {
+        for (int i = 0; i < 5; i++) {
+            if (buf[i]) cudaFree(buf[i]);
+            buf[i] = nullptr;
+            cap[i] = 0;
+        }
+        for (auto e : ev) cudaEventDestroy(e);
+        ev.clear();
+        if (comp) cudaStreamDestroy(comp);
+        if (copy) cudaStreamDestroy(copy);
+        comp = copy = nullptr;
+        device = -1;
+    }
+};
+HostCallCache g_hcache;
+}  // namespace
+
+void cb200_host_cache_release(void) {
+    std::lock_guard<std::mutex> lk(g_hcache.mu);
+    if (g_hcache.device >= 0) {
+        cudaSetDevice(g_hcache.device);
+        g_hcache.release();
+    }
+}
+
+// acb_ode_solve_fuchs for a batch, host buffers in and out (the call a host program makes; bench.py's `e2e`).
+// Only the operator and the -valuation initial rows of res go up; the solve runs in coefficient RANGES on one stream
+// (the recurrence resumes from the rows already in HBM) and every finished range -- contiguous rows of the
+// [coefficient][limb][slot] layout -- comes down on a second stream, straight into the caller's result arrays, while
+// the next range is being computed.  With page-locked result arrays (cb200_host_alloc, cudaHostAlloc, a pinned torch
+// tensor) the copies run at PCIe speed; pageable arrays are staged by the driver.
 int cb200_fuchs_batch_host(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
                            const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
                            uint32_t* res_mant, cb_meta* res_meta, int device) {
     if (!supported_L(L) || order < 1 || degree < 0 || batch < 0 || n < 0) return CB200_EINVAL;
     if (valuation >= 0) return CB200_EVALUATION;
+    if (!factor_fits(n, order)) return CB200_ERANGE;
     CK(cudaSetDevice(device));
-    int64_t So = shared_ode ? 2 : 2 * batch, S = 2 * batch, ne = (int64_t)(order + 1) * (degree + 1);
-    DevBuf om, ot, rm, rt, ws;
-    size_t wsb = cb200_fuchs_workspace_bytes(L, order, degree, valuation, n, batch, shared_ode);
-    CK(om.alloc(arr_mant_bytes(L, ne, So)));
-    CK(ot.alloc(arr_meta_bytes(ne, So)));
-    CK(rm.alloc(arr_mant_bytes(L, n + 1, S)));
-    CK(rt.alloc(arr_meta_bytes(n + 1, S)));
-    CK(ws.alloc(wsb));
-    CK(cudaMemcpy(om.p, ode_mant, arr_mant_bytes(L, ne, So), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ot.p, ode_meta, arr_meta_bytes(ne, So), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(rm.p, res_mant, arr_mant_bytes(L, n + 1, S), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(rt.p, res_meta, arr_meta_bytes(n + 1, S), cudaMemcpyHostToDevice));
-    int rc = cb200_fuchs_batch_dev(L, order, degree, valuation, n, batch, (uint32_t*)om.p, (cb_meta*)ot.p,
-                                   shared_ode, (uint32_t*)rm.p, (cb_meta*)rt.p, ws.p, wsb, nullptr);
-    if (rc) return rc;
-    CK(cudaMemcpy(res_mant, rm.p, arr_mant_bytes(L, n + 1, S), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(res_meta, rt.p, arr_meta_bytes(n + 1, S), cudaMemcpyDeviceToHost));
-    return (int)cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_hcache.mu);
+    HostCallCache& hc = g_hcache;
+    if (hc.device != device) {
+        if (hc.device >= 0) {
+            cudaSetDevice(hc.device);
+            hc.release();
+            CK(cudaSetDevice(device));
+        }
+        hc.device = device;
+    }
+    if (!hc.comp) CK(cudaStreamCreateWithFlags(&hc.comp, cudaStreamNonBlocking));
+    if (!hc.copy) CK(cudaStreamCreateWithFlags(&hc.copy, cudaStreamNonBlocking));
+    const int64_t So = shared_ode ? 2 : 2 * batch, S = 2 * batch, ne = (int64_t)(order + 1) * (degree + 1);
+    const size_t wsb = cb200_fuchs_workspace_bytes(L, order, degree, valuation, n, batch, shared_ode);
+    CK(hc.reserve(0, arr_mant_bytes(L, ne, So)));
+    CK(hc.reserve(1, arr_meta_bytes(ne, So)));
+    CK(hc.reserve(2, arr_mant_bytes(L, n + 1, S)));
+    CK(hc.reserve(3, arr_meta_bytes(n + 1, S)));
+    CK(hc.reserve(4, wsb));
+    uint32_t* d_om = (uint32_t*)hc.buf[0];
+    cb_meta* d_ot = (cb_meta*)hc.buf[1];
+    uint32_t* d_rm = (uint32_t*)hc.buf[2];
+    cb_meta* d_rt = (cb_meta*)hc.buf[3];
+    const int64_t ninit = (-valuation < n + 1) ? -valuation : n + 1;
+    CK(cudaMemcpyAsync(d_om, ode_mant, arr_mant_bytes(L, ne, So), cudaMemcpyHostToDevice, hc.comp));
+    CK(cudaMemcpyAsync(d_ot, ode_meta, arr_meta_bytes(ne, So), cudaMemcpyHostToDevice, hc.comp));
+    CK(cudaMemcpyAsync(d_rm, res_mant, arr_mant_bytes(L, ninit, S), cudaMemcpyHostToDevice, hc.comp));
+    CK(cudaMemcpyAsync(d_rt, res_meta, arr_meta_bytes(ninit, S), cudaMemcpyHostToDevice, hc.comp));
+    if (n < -valuation) return (int)cudaStreamSynchronize(hc.comp);  // nothing to compute
+    // coefficient ranges: about 1/8 of the rows each, at least 16 rows, at most 512 MB of result rows
+    const size_t row_bytes = (size_t)S * (4 * (size_t)L + 16);
+    int64_t rows = (n + 8) / 8;
+    if (rows < 16) rows = 16;
+    while (rows > 16 && (size_t)rows * row_bytes > ((size_t)512 << 20)) rows = (rows + 1) / 2;
+    if (const char* e = getenv("CB200_HOST_ROWS")) { int v = atoi(e); if (v >= 1) rows = v; }  // development
+    const int64_t nchunks = (n + 1 + rows - 1) / rows;
+    while ((int64_t)hc.ev.size() < nchunks) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        hc.ev.push_back(e);
+    }
+    // every range is enqueued on the compute stream up front (kernel launches only), so that a blocking copy into
+    // pageable memory below never delays the next range
+    for (int64_t c = 0; c < nchunks; c++) {
+        const int64_t lo = c * rows, hi = (lo + rows - 1 < n) ? lo + rows - 1 : n;
+        if (hi >= -valuation) {
+            int rc = cb200_fuchs_batch_range_dev(L, order, degree, valuation, lo, hi, batch, d_om, d_ot, shared_ode, d_rm, d_rt,
+                                                 hc.buf[4], wsb, hc.comp);
+            if (rc) return rc;
+        }
+        CK(cudaEventRecord(hc.ev[c], hc.comp));
+    }
+    for (int64_t c = 0; c < nchunks; c++) {
+        int64_t lo = c * rows;
+        const int64_t hi = (lo + rows - 1 < n) ? lo + rows - 1 : n;
+        if (lo < ninit) lo = ninit;  // the initial rows are the caller's own
+        if (lo > hi) continue;
+        CK(cudaStreamWaitEvent(hc.copy, hc.ev[c], 0));
+        CK(cudaMemcpyAsync(res_mant + (size_t)lo * L * S, d_rm + (size_t)lo * L * S, arr_mant_bytes(L, hi - lo + 1, S),
+                           cudaMemcpyDeviceToHost, hc.copy));
+        CK(cudaMemcpyAsync(res_meta + (size_t)lo * S, d_rt + (size_t)lo * S, arr_meta_bytes(hi - lo + 1, S),
+                           cudaMemcpyDeviceToHost, hc.copy));
+    }
+    CK(cudaStreamSynchronize(hc.comp));
+    return (int)cudaStreamSynchronize(hc.copy);
 }
 
 int cb200_fuchs_intop_batch_host(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
@@ -671,6 +881,16 @@ int cb200_fuchs_intop_batch_host(int L, int order, int degree, int valuation, in
     if (valuation >= 0) return CB200_EVALUATION;
     CK(cudaSetDevice(device));
     int64_t S = 2 * batch, ne = (int64_t)(order + 1) * (degree + 1);
+    {   // the int64 multipliers of the kernel must not wrap: (order+1) * max|coefficient| * (n+1)^order < 2^62
+        uint64_t pmax = 0;
+        for (int64_t i = 0, cnt = ne * (shared_ode ? 1 : batch); i < cnt; i++) {
+            uint64_t a = ode_int[i] < 0 ? (uint64_t)0 - (uint64_t)ode_int[i] : (uint64_t)ode_int[i];
+            if (a > pmax) pmax = a;
+        }
+        long double bound = (long double)pmax * (order + 1);
+        for (int i = 0; i < order; i++) bound *= (long double)(n + 1);
+        if (!(bound < 4.0e18L)) return CB200_ERANGE;
+    }
     size_t ob = sizeof(int64_t) * ne * (shared_ode ? 1 : batch);
     DevBuf om, rm, rt;
     CK(om.alloc(ob));
@@ -965,25 +1185,26 @@ int cb200_ew_host(int op, int L, int64_t n, uint32_t* z_mant, cb_meta* z_meta, c
     return (int)cudaDeviceSynchronize();
 }
 
-int cb200_continuation_host(int L, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
-                            const uint32_t* ode_mant, const cb_meta* ode_meta, const uint32_t* path_mant,
-                            const cb_meta* path_meta, uint32_t* y_mant, cb_meta* y_meta, int device) {
+static int continuation_host_impl(int L, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
+                                  const uint32_t* ode_mant, const cb_meta* ode_meta, const uint32_t* path_mant,
+                                  const cb_meta* path_meta, uint32_t* y_mant, cb_meta* y_meta, uint32_t* res_mant,
+                                  cb_meta* res_meta, int device) {
     if (!supported_L(L) || order < 1 || degree < 0 || batch < 0 || n < order || path_len < 1) return CB200_EINVAL;
     CK(cudaSetDevice(device));
+    const bool series = res_mant != nullptr;
     int64_t ne = (int64_t)(order + 1) * (degree + 1), S = 2 * batch;
-    std::vector<uint8_t> zero(path_len);
-    for (int64_t t = 0; t < path_len; t++) {
-        const cb_meta* m = path_meta + 2 * t;
-        zero[t] = (m[0].flags & CB_FLAG_ZERO) && m[0].rman == 0 && (m[1].flags & CB_FLAG_ZERO) && m[1].rman == 0;
-    }
-    DevBuf om, ot, pm, pt, ym, yt, ws;
-    size_t wsb = cb200_continuation_workspace_bytes(L, order, degree, n, batch);
+    DevBuf om, ot, pm, pt, ym, yt, rm, rt, ws;
+    size_t wsb = continuation_ws(L, order, degree, n, batch, series);
     CK(om.alloc(arr_mant_bytes(L, ne, 2)));
     CK(ot.alloc(arr_meta_bytes(ne, 2)));
     CK(pm.alloc(arr_mant_bytes(L, path_len, 2)));
     CK(pt.alloc(arr_meta_bytes(path_len, 2)));
     CK(ym.alloc(arr_mant_bytes(L, order, S)));
     CK(yt.alloc(arr_meta_bytes(order, S)));
+    if (series) {
+        CK(rm.alloc(arr_mant_bytes(L, n + 1, S)));
+        CK(rt.alloc(arr_meta_bytes(n + 1, S)));
+    }
     CK(ws.alloc(wsb));
     CK(cudaMemcpy(om.p, ode_mant, arr_mant_bytes(L, ne, 2), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ot.p, ode_meta, arr_meta_bytes(ne, 2), cudaMemcpyHostToDevice));
@@ -991,11 +1212,81 @@ int cb200_continuation_host(int L, int order, int degree, int64_t n, int64_t bat
     CK(cudaMemcpy(pt.p, path_meta, arr_meta_bytes(path_len, 2), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ym.p, y_mant, arr_mant_bytes(L, order, S), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(yt.p, y_meta, arr_meta_bytes(order, S), cudaMemcpyHostToDevice));
-    int rc = cb200_continuation_dev(L, order, degree, n, batch, path_len, (uint32_t*)om.p, (cb_meta*)ot.p, (uint32_t*)pm.p,
-                                    (cb_meta*)pt.p, zero.data(), (uint32_t*)ym.p, (cb_meta*)yt.p, ws.p, wsb, nullptr);
+    int rc = continuation_impl(L, order, degree, n, batch, path_len, (uint32_t*)om.p, (cb_meta*)ot.p, (uint32_t*)pm.p,
+                               (cb_meta*)pt.p, (uint32_t*)ym.p, (cb_meta*)yt.p, series ? (uint32_t*)rm.p : nullptr,
+                               series ? (cb_meta*)rt.p : nullptr, ws.p, wsb, nullptr);
     if (rc) return rc;
     CK(cudaMemcpy(y_mant, ym.p, arr_mant_bytes(L, order, S), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(y_meta, yt.p, arr_meta_bytes(order, S), cudaMemcpyDeviceToHost));
+    if (series) {
+        CK(cudaMemcpy(res_mant, rm.p, arr_mant_bytes(L, n + 1, S), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(res_meta, rt.p, arr_meta_bytes(n + 1, S), cudaMemcpyDeviceToHost));
+    }
+    return (int)cudaDeviceSynchronize();
+}
+int cb200_continuation_host(int L, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
+                            const uint32_t* ode_mant, const cb_meta* ode_meta, const uint32_t* path_mant,
+                            const cb_meta* path_meta, uint32_t* y_mant, cb_meta* y_meta, int device) {
+    return continuation_host_impl(L, order, degree, n, batch, path_len, ode_mant, ode_meta, path_mant, path_meta, y_mant,
+                                  y_meta, nullptr, nullptr, device);
+}
+int cb200_continuation_series_host(int L, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
+                                   const uint32_t* ode_mant, const cb_meta* ode_meta, const uint32_t* path_mant,
+                                   const cb_meta* path_meta, uint32_t* y_mant, cb_meta* y_meta, uint32_t* res_mant,
+                                   cb_meta* res_meta, int device) {
+    if (!res_mant || !res_meta || path_len < 2) return CB200_EINVAL;
+    return continuation_host_impl(L, order, degree, n, batch, path_len, ode_mant, ode_meta, path_mant, path_meta, y_mant,
+                                  y_meta, res_mant, res_meta, device);
+}
+
+int cb200_ode_shift_host(int L, int order, int degree, int64_t batch, const uint32_t* ode_mant, const cb_meta* ode_meta,
+                         int shared_ode, const uint32_t* a_mant, const cb_meta* a_meta, int shared_a, uint32_t* out_mant,
+                         cb_meta* out_meta, int device) {
+    if (!supported_L(L) || order < 0 || degree < 0 || batch < 0) return CB200_EINVAL;
+    CK(cudaSetDevice(device));
+    int64_t ne = (int64_t)(order + 1) * (degree + 1), S = 2 * batch, So = shared_ode ? 2 : S, Sa = shared_a ? 2 : S;
+    DevBuf om, ot, am, at_, rm, rt, ws;
+    size_t wsb = cb200_ode_shift_workspace_bytes(L, batch);
+    CK(om.alloc(arr_mant_bytes(L, ne, So)));
+    CK(ot.alloc(arr_meta_bytes(ne, So)));
+    CK(am.alloc(arr_mant_bytes(L, 1, Sa)));
+    CK(at_.alloc(arr_meta_bytes(1, Sa)));
+    CK(rm.alloc(arr_mant_bytes(L, ne, S)));
+    CK(rt.alloc(arr_meta_bytes(ne, S)));
+    CK(ws.alloc(wsb));
+    CK(cudaMemcpy(om.p, ode_mant, arr_mant_bytes(L, ne, So), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ot.p, ode_meta, arr_meta_bytes(ne, So), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(am.p, a_mant, arr_mant_bytes(L, 1, Sa), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(at_.p, a_meta, arr_meta_bytes(1, Sa), cudaMemcpyHostToDevice));
+    int rc = cb200_ode_shift_dev(L, order, degree, batch, (uint32_t*)om.p, (cb_meta*)ot.p, shared_ode, (uint32_t*)am.p,
+                                 (cb_meta*)at_.p, shared_a, (uint32_t*)rm.p, (cb_meta*)rt.p, ws.p, wsb, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(out_mant, rm.p, arr_mant_bytes(L, ne, S), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out_meta, rt.p, arr_meta_bytes(ne, S), cudaMemcpyDeviceToHost));
+    return (int)cudaDeviceSynchronize();
+}
+
+int cb200_taylor_shift_host(int L, int64_t len, int64_t batch, uint32_t* f_mant, cb_meta* f_meta, const uint32_t* a_mant,
+                            const cb_meta* a_meta, int shared_a, int device) {
+    if (!supported_L(L) || len < 0 || batch < 0) return CB200_EINVAL;
+    CK(cudaSetDevice(device));
+    int64_t S = 2 * batch, Sa = shared_a ? 2 : S;
+    DevBuf fm, ft, am, at_, ws;
+    size_t wsb = cb200_taylor_shift_workspace_bytes(L, len, batch);
+    CK(fm.alloc(arr_mant_bytes(L, len, S)));
+    CK(ft.alloc(arr_meta_bytes(len, S)));
+    CK(am.alloc(arr_mant_bytes(L, 1, Sa)));
+    CK(at_.alloc(arr_meta_bytes(1, Sa)));
+    CK(ws.alloc(wsb));
+    CK(cudaMemcpy(fm.p, f_mant, arr_mant_bytes(L, len, S), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ft.p, f_meta, arr_meta_bytes(len, S), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(am.p, a_mant, arr_mant_bytes(L, 1, Sa), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(at_.p, a_meta, arr_meta_bytes(1, Sa), cudaMemcpyHostToDevice));
+    int rc = cb200_taylor_shift_dev(L, len, batch, (uint32_t*)fm.p, (cb_meta*)ft.p, (uint32_t*)am.p, (cb_meta*)at_.p,
+                                    shared_a, ws.p, wsb, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(f_mant, fm.p, arr_mant_bytes(L, len, S), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(f_meta, ft.p, arr_meta_bytes(len, S), cudaMemcpyDeviceToHost));
     return (int)cudaDeviceSynchronize();
 }
 

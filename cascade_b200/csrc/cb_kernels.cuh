@@ -125,6 +125,28 @@ __global__ void __launch_bounds__(HybCfg<L>::TPB, 1) horner_hyb_kernel(HornerPar
     }
 }
 template <int L>
+__global__ void __launch_bounds__(Cfg<L>::TPB, 1) ode_shift_kernel(ShiftParams p) {
+    CB_KERNEL_PROLOGUE(p.batch)
+    ode_shift_thread<L>(p, idx, S0, S1);
+}
+// one CTA per series (blockIdx.x); see TShiftParams
+template <int L>
+__global__ void __launch_bounds__(Cfg<L>::TPB, 1) taylor_shift_kernel(TShiftParams p) {
+    extern __shared__ uint32_t cb_smem[];
+    constexpr int TPB = Cfg<L>::TPB;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cb_smem) + 4u * threadIdx.x;
+    Scratch<TPB> S0{sbase};
+    Scratch<TPB> S1{sbase + 4u * (uint32_t)(Sizes<L>::WORDS * TPB)};
+    const int64_t inst = blockIdx.x;
+    if (acb_is_exact_zero(at<L>(p.a, 0, (p.a.S == 2) ? 0 : 2 * (size_t)inst))) return;  // uniform over the CTA
+    for (int64_t i = p.len - 2; i >= 0; i--) {
+        for (int64_t j = i + threadIdx.x; j <= p.len - 2; j += TPB) taylor_shift_mul<L>(p, inst, j, S0, S1);
+        __syncthreads();
+        for (int64_t j = i + threadIdx.x; j <= p.len - 2; j += TPB) taylor_shift_add<L>(p, inst, j, S0, S1);
+        __syncthreads();
+    }
+}
+template <int L>
 __global__ void __launch_bounds__(Cfg<L>::TPB, 1) ew_kernel(EwParams p) {
     CB_KERNEL_PROLOGUE(p.n)
     ew_thread<L>(p, idx, S0, S1);
@@ -376,6 +398,8 @@ struct LaunchTable {
     int (*evaluate)(const EvalParams&, cudaStream_t);
     int (*trans)(const TransParams&, cudaStream_t);
     int (*apply)(const ApplyParams&, cudaStream_t);
+    int (*ode_shift)(const ShiftParams&, cudaStream_t);
+    int (*taylor_shift)(const TShiftParams&, cudaStream_t);
 };
 
 #define CB_DEFINE_LAUNCH_TABLE(LL)                                                                         \
@@ -437,8 +461,18 @@ struct LaunchTable {
     static int eval_##LL(const EvalParams& p, cudaStream_t s) { return launch<LL>(evaluate_kernel<LL>, p, p.npts, s); } \
     static int trans_##LL(const TransParams& p, cudaStream_t s) { return launch<LL>(trans_kernel<LL>, p, p.n, s); } \
     static int apply_##LL(const ApplyParams& p, cudaStream_t s) { return launch<LL>(apply_kernel<LL>, p, p.batch, s); } \
+    static int oshift_##LL(const ShiftParams& p, cudaStream_t s) { return launch<LL>(ode_shift_kernel<LL>, p, p.batch, s); } \
+    static int tshift_##LL(const TShiftParams& p, cudaStream_t s) {                                        \
+        if (p.batch <= 0 || p.len <= 1) return 0;                                                          \
+        cudaError_t e = cudaFuncSetAttribute(taylor_shift_kernel<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)Sizes<LL>::SMEM);                                        \
+        if (e != cudaSuccess) return (int)e;                                                               \
+        taylor_shift_kernel<LL><<<(unsigned)p.batch, Cfg<LL>::TPB, Sizes<LL>::SMEM, s>>>(p);               \
+        return (int)cudaGetLastError();                                                                    \
+    }                                                                                                      \
     extern const LaunchTable launch_table_L##LL = {frob_##LL, horner_##LL, ew_##LL, ftab_##LL, fsh_##LL, fint_##LL, \
-                                                   frobg_##LL, solop_##LL, indp_##LL, eval_##LL, trans_##LL, apply_##LL}; \
+                                                   frobg_##LL, solop_##LL, indp_##LL, eval_##LL, trans_##LL, apply_##LL, \
+                                                   oshift_##LL, tshift_##LL}; \
     }
 
 extern const LaunchTable launch_table_L4, launch_table_L32, launch_table_L64, launch_table_L128;

@@ -64,8 +64,20 @@ CB_HD void st_meta(Meta* p, const Meta& t) {
     *p = t;
 #endif
 }
-CB_HD Opd re_of(const CRef& x) { return Opd{RRef{x.m, x.stride}, ld_meta(x.t)}; }
-CB_HD Opd im_of(const CRef& x) { return Opd{RRef{x.m + 1, x.stride}, ld_meta(x.t + 1)}; }
+// Balls that may come from the caller: only the three flag bits of include/cb_format.h are taken from memory; bits
+// 8..15 of flags are an INTERNAL trailing-zero hint (F_TZ_SHIFT) that only this library's own tables may carry --
+// a caller-supplied value there must never be trusted (it would switch off the guard-bit proof of the truncated
+// products).
+CB_HD Meta ld_meta_user(const Meta* p) {
+    Meta t = ld_meta(p);
+    t.flags &= (F_SIGN | F_ZERO | F_NAN);
+    return t;
+}
+CB_HD Opd re_of(const CRef& x) { return Opd{RRef{x.m, x.stride}, ld_meta_user(x.t)}; }
+CB_HD Opd im_of(const CRef& x) { return Opd{RRef{x.m + 1, x.stride}, ld_meta_user(x.t + 1)}; }
+// internal table operands (written by fuchs_table_thread / acb_mark_tz): hints kept
+CB_HD Opd re_of_tbl(const CRef& x) { return Opd{RRef{x.m, x.stride}, ld_meta(x.t)}; }
+CB_HD Opd im_of_tbl(const CRef& x) { return Opd{RRef{x.m + 1, x.stride}, ld_meta(x.t + 1)}; }
 // shared-format entries (S = 2): fixed-stride views
 using OpdS = OpdT<RFix<2>>;
 CB_HD OpdS re_of_shared(const CRef& x) { return OpdS{RFix<2>{x.m}, ld_meta(x.t)}; }
@@ -79,8 +91,8 @@ template <class YO> CB_HD YO y_re(const CRef& x);
 template <class YO> CB_HD YO y_im(const CRef& x);
 template <> CB_HD OpdS y_re<OpdS>(const CRef& x) { return re_of_shared(x); }
 template <> CB_HD OpdS y_im<OpdS>(const CRef& x) { return im_of_shared(x); }
-template <> CB_HD Opd y_re<Opd>(const CRef& x) { return re_of(x); }
-template <> CB_HD Opd y_im<Opd>(const CRef& x) { return im_of(x); }
+template <> CB_HD Opd y_re<Opd>(const CRef& x) { return re_of_tbl(x); }
+template <> CB_HD Opd y_im<Opd>(const CRef& x) { return im_of_tbl(x); }
 
 // does this precision use truncated products (with the exact path as per-lane fallback)?
 template <int L>
@@ -503,7 +515,30 @@ CB_HD void fuchs_intop_thread(const FuchsIntParams& p, int64_t inst, SCR S0, SCR
     const int v = p.valuation, D1 = p.degree + 1;
     const int ne = (p.order + 1) * D1;
     int64_t P[INTOP_MAXENT];
-    for (int e = 0; e < ne; e++) P[e] = p.ode[(size_t)e * (p.ostride ? p.ostride : 1) + (p.ostride ? (size_t)inst : 0)];
+    uint64_t pmax = 0;
+    for (int e = 0; e < ne; e++) {
+        P[e] = p.ode[(size_t)e * (p.ostride ? p.ostride : 1) + (p.ostride ? (size_t)inst : 0)];
+        uint64_t a = P[e] < 0 ? (uint64_t)0 - (uint64_t)P[e] : (uint64_t)P[e];
+        pmax = a > pmax ? a : pmax;
+    }
+    // every multiplier formed below is bounded by (order+1) * max|P| * (n+1)^order; if that does not stay below
+    // 2^62 the int64 arithmetic could wrap, so this instance's coefficients are made indeterminate instead of wrong
+    // (the host-buffer entry point rejects such a batch up front with CB200_ERANGE)
+    {
+        double bound = (double)pmax * (double)(p.order + 1);
+        for (int i = 0; i < p.order; i++) bound *= (double)(p.n + 1);
+        if (!(bound < 4.0e18)) {
+            const int64_t b0 = n_from >= 0 ? n_from : -p.valuation, b1 = n_from >= 0 ? n_to : p.n;
+            for (int64_t b = b0; b <= b1; b++) {
+                CRef out = at<L>(p.res, b, slot);
+                store_nan<L>(wre(out));
+                store_nan<L>(wim(out));
+                st_meta(out.t, meta_nan());
+                st_meta(out.t + 1, meta_nan());
+            }
+            return;
+        }
+    }
     SCR accRe = A0, accIm = A1, spare = A2;
     // (n_from, n_to): the coefficient range of a persistent work unit (the recurrence resumes from res)
     const int64_t b_first = n_from >= 0 ? n_from : -v, b_last = n_from >= 0 ? n_to : p.n;
@@ -1082,6 +1117,62 @@ CB_HD void indicial_poly_thread(const IndicialParams& p, int64_t inst, SCR S0, S
                        at<L>(p.wp, 3, slot), at<L>(p.wp, 4, slot)};
     for (int j = 0; j <= p.order + 1; j++) acb_zero<L>(pc.c(0, j));
     indicial_poly<L>(pc, p, (p.ode.S == 2) ? 0 : slot, 0, p.nu, p.shift);
+}
+
+// ================================================================ acb_ode_shift (reference src/acb_ode.c:124-135)
+// out = in with every row p_i(z) replaced by p_i(z + a): copy, then the Horner Taylor shift of each row
+//   for i = D-2 .. 0: for j = i .. D-2: p[j] += p[j+1] * a        (Arb's _acb_poly_taylor_shift_horner: acb_addmul)
+// One thread per operator; an exact-zero a (or degree 0) leaves the copy (oracle: cbo_ode_shift).
+struct ShiftParams {
+    int order, degree;
+    int64_t batch;
+    CArr in;   // (order+1)(degree+1) entries, S = 2*batch or 2 (one operator shifted to `batch` points)
+    CArr a;    // 1 entry, S = 2*batch or 2
+    CArr out;  // S = 2*batch
+    CArr tmp;  // 1 entry, S = 2*batch
+};
+template <int L, class SCR>
+CB_HD void ode_shift_thread(const ShiftParams& p, int64_t inst, SCR S0, SCR S1) {
+    const size_t slot = 2 * (size_t)inst;
+    const size_t islot = (p.in.S == 2) ? 0 : slot, aslot = (p.a.S == 2) ? 0 : slot;
+    const int D1 = p.degree + 1, ne = (p.order + 1) * D1;
+    for (int e = 0; e < ne; e++) acb_set<L>(at<L>(p.out, e, slot), at<L>(p.in, e, islot));
+    CRef a = at<L>(p.a, 0, aslot), t = at<L>(p.tmp, 0, slot);
+    if (p.degree == 0 || acb_is_exact_zero(a)) return;
+#pragma unroll 1
+    for (int row = 0; row <= p.order; row++)
+#pragma unroll 1
+        for (int i = D1 - 2; i >= 0; i--)
+#pragma unroll 1
+            for (int j = i; j <= D1 - 2; j++) {
+                CRef pj = at<L>(p.out, row * D1 + j, slot);
+                acb_mul<L>(t, at<L>(p.out, row * D1 + j + 1, slot), a, S0, S1);
+                acb_addsub<L>(pj, pj, t, false, S0, S1);
+            }
+}
+
+// ================================================================ acb_poly_taylor_shift (reference src/fuchs_solver.c:159)
+// The complete re-expansion f(x + a) of a series, in the Horner form (oracle: cbo_poly_taylor_shift_horner)
+//   for i = len-2 .. 0: for j = i .. len-2: f[j] += f[j+1] * a
+// Inside one sweep i every update reads the value f[j+1] had BEFORE the sweep, so a sweep is two parallel phases
+// over j: tmp[j] = f[j+1] * a, then f[j] += tmp[j].  One CTA per series runs the sweeps with a barrier between the
+// phases; the entries of a phase are dealt out to its threads.
+struct TShiftParams {
+    int64_t len, batch;
+    CArr f;    // len entries, S = 2*batch, in place
+    CArr a;    // 1 entry, S = 2*batch or 2
+    CArr tmp;  // len entries, S = 2*batch
+};
+template <int L, class SCR>
+CB_HD void taylor_shift_mul(const TShiftParams& p, int64_t inst, int64_t j, SCR S0, SCR S1) {
+    const size_t slot = 2 * (size_t)inst;
+    acb_mul<L>(at<L>(p.tmp, j, slot), at<L>(p.f, j + 1, slot), at<L>(p.a, 0, (p.a.S == 2) ? 0 : slot), S0, S1);
+}
+template <int L, class SCR>
+CB_HD void taylor_shift_add(const TShiftParams& p, int64_t inst, int64_t j, SCR S0, SCR S1) {
+    const size_t slot = 2 * (size_t)inst;
+    CRef fj = at<L>(p.f, j, slot);
+    acb_addsub<L>(fj, fj, at<L>(p.tmp, j, slot), false, S0, S1);
 }
 
 // ================================================================ Horner

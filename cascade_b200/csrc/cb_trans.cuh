@@ -29,7 +29,7 @@ namespace cb {
 
 constexpr int64_t TR_BIG = ((int64_t)1) << 40;
 constexpr bool EVAL_SYNC = true;  // phase barriers in evaluate_thread's Horner loops (uniform trip counts)
-constexpr int TRANS_NTMP = 16;  // complex temporaries of acb_exp (4) + acb_log (10) + evaluate (2)
+constexpr int TRANS_NTMP = 16;  // complex temporaries of acb_exp (4) + acb_log (10 + the negated argument) + evaluate (1)
 
 template <int L>
 CB_HD void acb_set_nan(const CRef& z) {
@@ -190,9 +190,34 @@ CB_HD void arb_set_d(const CRef& z, int part, double d) {
     st_meta(z.t + part, Meta{e11 - 1022, (b >> 63) ? F_SIGN : 0u, 0u, 0});
 }
 
-// res = log(a).  T[0..13]: exp's four, then y0, e, t, u, d, v, v2, s, c, one.  res must not alias a.
+// res = log(a) for a ball that does not straddle the branch cut.  T[0..13]: exp's four, then y0, e, t, u, d, v, v2,
+// s, c, one.  res must not alias a.
+template <int L, class SCR>
+CB_HD void acb_log_main(const CRef& res, const CRef& a, const CRef* T, SCR S0, SCR S1);
+// res = log(a).  A ball that straddles the branch cut (re < 0, im a non-exact ball containing 0) holds points with
+// arg near +pi and near -pi; like Arb's acb_log the result is then Re = log|a| (from log(-a): -a lies around the
+// positive real axis) and Im = [0 +- pi] (oracle/cbo_trans.c, cbo_acb_log).  T[14] holds -a.
+constexpr uint32_t PI_MAG_MAN = 843314857u;  // ceil(pi * 2^28): pi <= man * 2^(2-30)
+constexpr int32_t PI_MAG_EXP = 2;
 template <int L, class SCR>
 CB_HD void acb_log(const CRef& res, const CRef& a, const CRef* T, SCR S0, SCR S1) {
+    Meta tr = ld_meta(a.t), ti = ld_meta(a.t + 1);
+    if (!is_nan(tr) && !is_nan(ti) && !is_zero_mid(tr) && (tr.flags & F_SIGN) && !is_exact_zero(ti) &&
+        arb_contains_zero<L>(a.m + 1, a.stride, ti)) {
+        CRef na = T[14];
+        acb_set<L>(na, a);
+        acb_neg_inplace(na);
+        acb_log_main<L>(res, na, T, S0, S1);
+        if (acb_bound_exp(res) != TR_BIG) {
+            store_nan<L>(wim(res));  // zeros
+            st_meta(res.t + 1, Meta{0, F_ZERO, PI_MAG_MAN, PI_MAG_EXP});
+        }
+        return;
+    }
+    acb_log_main<L>(res, a, T, S0, S1);
+}
+template <int L, class SCR>
+CB_HD void acb_log_main(const CRef& res, const CRef& a, const CRef* T, SCR S0, SCR S1) {
     if (acb_bound_exp(a) == TR_BIG || acb_contains_zero<L>(a)) {
         acb_set_nan<L>(res);
         return;

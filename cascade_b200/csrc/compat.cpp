@@ -17,9 +17,18 @@ const slong UNDEFINED_VAL = -0xFFFF;  // reference src/acb_ode.c:3
     fprintf(stderr, "cascade_b200: %s failed (rc = %d); there is no CPU fallback\n", what, rc);
     abort();
 }
+// Any precision 2 <= prec <= 4096 (the reference's own tests run at 30..157 bits, reference tests/fuchs.c:20): the
+// device arithmetic is compiled for 128, 1024, 2048 and 4096 bits, and a call at `prec` bits runs at the smallest of
+// those that is >= prec.  Every result is then a rigorous ball computed with AT LEAST the requested precision -- an
+// enclosure of the same exact quantity, at least as tight as a prec-bit computation -- which is what every property
+// the reference tests (containment, overlap, residual contains zero) needs.  Bit patterns differ from a prec-bit run,
+// as they do between Arb versions.
 int limbs_of(slong prec) {
-    if (prec == 128 || prec == 1024 || prec == 2048 || prec == 4096) return (int)(prec / 32);
-    fprintf(stderr, "cascade_b200: precision %ld is not supported on the device (use 128, 1024, 2048 or 4096)\n", prec);
+    if (prec >= 2 && prec <= 128) return 4;
+    if (prec <= 1024 && prec > 128) return 32;
+    if (prec <= 2048 && prec > 1024) return 64;
+    if (prec <= 4096 && prec > 2048) return 128;
+    fprintf(stderr, "cascade_b200: precision %ld is not supported on the device (2 <= prec <= 4096)\n", prec);
     abort();
 }
 
@@ -362,18 +371,18 @@ slong acb_ode_valuation(acb_ode_t ODE) {
     return val;
 }
 void acb_ode_shift(acb_ode_t out, acb_ode_t in, acb_srcptr a, slong bits) {
+    // reference src/acb_ode.c:124-135: copy, then the Horner Taylor shift of every row -- one launch (ode_shift_kernel)
     acb_ode_set(out, in);
     if (acb_is_zero(a) || in->degree == 0) return;
-    slong n = out->degree + 1;
-    acb_t t;
-    for (slong row = 0; row <= out->order; row++) {
-        acb_ptr p = acb_ode_poly(out, row);
-        for (slong i = n - 2; i >= 0; i--)
-            for (slong j = i; j <= n - 2; j++) {  // p[j] += p[j+1] * a   (Horner Taylor shift)
-                acb_mul(t, p + j + 1, a, bits);
-                acb_add(p + j, p + j, t, bits);
-            }
-    }
+    int L = limbs_of(bits);
+    slong ne = (in->order + 1) * (in->degree + 1);
+    HostArr hi(L, ne, 2), ha(L, 1, 2), ho(L, ne, 2);
+    for (slong e = 0; e < ne; e++) hi.put(e, 0, in->polys + e);
+    ha.put(0, 0, a);
+    int rc = cb200_ode_shift_host(L, (int)in->order, (int)in->degree, 1, hi.m.data(), hi.t.data(), 1, ha.m.data(), ha.t.data(), 1,
+                                  ho.m.data(), ho.t.data(), 0);
+    if (rc) die("acb_ode_shift (cb200_ode_shift_host)", rc);
+    for (slong e = 0; e < ne; e++) ho.get(e, 0, out->polys + e);
     out->valuation = UNDEFINED_VAL;
 }
 
@@ -519,13 +528,16 @@ void analytic_continuation(acb_poly_t res, acb_ode_t ODE, acb_srcptr path, slong
         acb_poly_get_coeff_acb(c, res, k);
         hy.put(k, 0, c);
     }
-    int rc = cb200_continuation_host(L, ord, (int)ODE->degree, deg, 1, len, ho.m.data(), ho.t.data(), hp.m.data(),
-                                     hp.t.data(), hy.m.data(), hy.t.data(), 0);
-    if (rc) die("analytic_continuation (cb200_continuation_host)", rc);
+    // the reference leaves the COMPLETE re-expanded series (deg + 1 coefficients) in res after the last corner
+    // (src/fuchs_solver.c:159): the _series entry point returns it
+    HostArr hr(L, deg + 1, 2);
+    int rc = cb200_continuation_series_host(L, ord, (int)ODE->degree, deg, 1, len, ho.m.data(), ho.t.data(), hp.m.data(),
+                                            hp.t.data(), hy.m.data(), hy.t.data(), hr.m.data(), hr.t.data(), 0);
+    if (rc) die("analytic_continuation (cb200_continuation_series_host)", rc);
     acb_poly_zero(res);
-    acb_poly_fit_length(res, ord);
-    for (int k = 0; k < ord; k++) hy.get(k, 0, res->coeffs + k);
-    res->length = ord;
+    acb_poly_fit_length(res, deg + 1);
+    for (slong k = 0; k <= deg; k++) hr.get(k, 0, res->coeffs + k);
+    res->length = deg + 1;
     poly_normalise(res);
 }
 

@@ -61,7 +61,9 @@ def solve_fuchs_sharded(ode: Balls, init: Balls, order: int, degree: int, n: int
     from . import api
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi = partition(batch, world, rank)
-    v = api.acb_ode_valuation(ode, order, degree)
+    # one valuation for the WHOLE batch (checked over every instance, not just this rank's block), so that all
+    # ranks agree and a mixed batch is rejected everywhere
+    v = api.batch_valuation(ode, order, degree, shared_ode, "solve_fuchs_sharded")
     ne = (order + 1) * (degree + 1)
     my_ode = ode if shared_ode else shard_instances(ode, batch, ne, lo, hi)
     my_init = shard_instances(init, batch, -v, lo, hi)
@@ -83,7 +85,7 @@ def solve_frobenius_sharded(ode: Balls, rho: Balls, mul: int, alpha: int, order:
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi = partition(batch, world, rank)
     ne = (order + 1) * (degree + 1)
-    v = api.acb_ode_valuation(ode, order, degree)
+    v = api.batch_valuation(ode, order, degree, shared_ode, "solve_frobenius_sharded")
     my_ode = ode if shared_ode else shard_instances(ode, batch, ne, lo, hi)
     my_rho = rho if shared_rho else shard_instances(rho, batch, 1, lo, hi)
     local = api.acb_ode_solve_frobenius_batch(my_ode, my_rho, mul, alpha, order, degree, n, hi - lo, shared_ode,

@@ -80,7 +80,11 @@ size_t cb200_ew_workspace_bytes(int L, int64_t n);
  *       S = 2*batch, or S = 2 when shared_ode != 0 (one operator for the whole batch).
  * res : n+1 entries, S = 2*batch.  On entry, entries 0 .. -valuation-1 hold the initial values
  *       (reference doc/source/cascade.rst:14-16); entries -valuation .. n are written.
- * valuation must be the value acb_ode_valuation (reference src/acb_ode.c:159-181) returns. */
+ * valuation must be the value acb_ode_valuation (reference src/acb_ode.c:159-181) returns.
+ * SINGLE-VALUATION CONTRACT: a launch runs with ONE valuation.  With shared_ode == 0 every operator of the batch
+ * must have that same valuation (exact-zero coefficients can make valuations differ between instances: group the
+ * instances by valuation and call once per group; cascade_b200.api.batch_valuation checks and rejects a mixed
+ * batch).  The same holds for the Frobenius and indicial-polynomial entry points below. */
 int cb200_fuchs_batch_dev(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
                           const uint32_t *ode_mant, const cb_meta *ode_meta, int shared_ode,
                           uint32_t *res_mant, cb_meta *res_meta, void *workspace,
@@ -94,15 +98,29 @@ int cb200_fuchs_batch_range_dev(int L, int order, int degree, int valuation, int
                                 const uint32_t *ode_mant, const cb_meta *ode_meta, int shared_ode,
                                 uint32_t *res_mant, cb_meta *res_meta, void *workspace, size_t workspace_bytes,
                                 void *stream);
+/* Host buffers in and out -- the call a host program makes (reference interface: acb_ode_solve_fuchs(res, ODE, deg,
+ * bits), src/cascade.h:13, for a batch).  res: the caller's FULL result arrays; rows 0 .. -valuation-1 are read, rows
+ * -valuation .. n are written.  Only the operator and the initial rows are uploaded; the solve runs in coefficient
+ * ranges and each finished range is copied into res on a second stream while the next range is computed.  Page-locked
+ * result arrays (cb200_host_alloc below, cudaHostAlloc, pinned torch tensors) make those copies run at PCIe speed;
+ * pageable arrays are accepted (the driver stages them).  Device buffers, two streams and the events are kept between
+ * calls; cb200_host_cache_release() frees them. */
 int cb200_fuchs_batch_host(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
                            const uint32_t *ode_mant, const cb_meta *ode_meta, int shared_ode,
                            uint32_t *res_mant, cb_meta *res_meta, int device);
+/* page-locked host memory without CUDA headers (NULL on failure), and the release of the cached device buffers */
+void *cb200_host_alloc(size_t bytes);
+void cb200_host_free(void *p);
+void cb200_host_cache_release(void);
 
 /* ---- acb_ode_solve_fuchs for operators with exact real INTEGER coefficients (acb_ode_legendre,
  * reference src/examples.c:3-11): ode_int[(order+1)*(degree+1)][batch] int64 (entry-major; one column
  * when shared_ode).  Same balls as cb200_fuchs_batch_*, computed with O(L) work per coefficient.
  * Every multiplier the reference forms at src/fuchs_solver.c:121-135 must stay below 2^62 in magnitude:
- * (order+1) * max|coefficient| * (n+1)^order < 2^62 (the caller checks; cascade_b200.api does). */
+ * (order+1) * max|coefficient| * (n+1)^order < 2^62.  The _host entry point scans ode_int and returns CB200_ERANGE
+ * otherwise; the _dev entry point cannot read device memory without synchronising, so there the KERNEL checks each
+ * instance's coefficients and writes indeterminate balls (CB_FLAG_NAN) for an instance that violates the bound --
+ * never a silently wrapped result. */
 int cb200_fuchs_intop_batch_dev(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
                                 const int64_t *ode_int, int shared_ode, uint32_t *res_mant,
                                 cb_meta *res_meta, void *stream);
@@ -244,17 +262,46 @@ int cb200_horner_batch_host(int L, int64_t len, int64_t npts, int nder, const ui
                             const cb_meta *pts_meta, uint32_t *out_mant, cb_meta *out_meta,
                             int device);
 
+/* ---- acb_ode_shift (reference src/acb_ode.c:124-135) for a batch: out = in with every row p_i(z) replaced by
+ * p_i(z + a), by the Horner Taylor shift p[j] += p[j+1]*a, in ONE launch (one thread per operator).
+ * ode : (order+1)(degree+1) entries, S = 2*batch, or S = 2 (shared_ode: one operator moved to `batch` points).
+ * a   : 1 entry, S = 2*batch or 2 (shared_a).  out : S = 2*batch.  An exactly zero a leaves the copy (:128). */
+size_t cb200_ode_shift_workspace_bytes(int L, int64_t batch);
+int cb200_ode_shift_dev(int L, int order, int degree, int64_t batch, const uint32_t *ode_mant, const cb_meta *ode_meta,
+                        int shared_ode, const uint32_t *a_mant, const cb_meta *a_meta, int shared_a, uint32_t *out_mant,
+                        cb_meta *out_meta, void *workspace, size_t workspace_bytes, void *stream);
+int cb200_ode_shift_host(int L, int order, int degree, int64_t batch, const uint32_t *ode_mant, const cb_meta *ode_meta,
+                         int shared_ode, const uint32_t *a_mant, const cb_meta *a_meta, int shared_a, uint32_t *out_mant,
+                         cb_meta *out_meta, int device);
+
+/* ---- acb_poly_taylor_shift (reference src/fuchs_solver.c:159): the COMPLETE re-expansion f(x + a) of `batch` series
+ * of len coefficients, in place, in the Horner form  for i = len-2..0: for j = i..len-2: f[j] += f[j+1]*a
+ * (one CTA per series, each sweep i as two parallel phases; O(len^2) ball operations per series).
+ * f : len entries, S = 2*batch.  a : 1 entry, S = 2*batch or 2 (shared_a). */
+size_t cb200_taylor_shift_workspace_bytes(int L, int64_t len, int64_t batch);
+int cb200_taylor_shift_dev(int L, int64_t len, int64_t batch, uint32_t *f_mant, cb_meta *f_meta, const uint32_t *a_mant,
+                           const cb_meta *a_meta, int shared_a, void *workspace, size_t workspace_bytes, void *stream);
+int cb200_taylor_shift_host(int L, int64_t len, int64_t batch, uint32_t *f_mant, cb_meta *f_meta, const uint32_t *a_mant,
+                            const cb_meta *a_meta, int shared_a, int device);
+
 /* ---- analytic_continuation (reference src/fuchs_solver.c:147-163) for a batch of solutions of ONE
- * operator along ONE path, device resident: per corner acb_ode_shift (src/acb_ode.c:124-135),
+ * operator along ONE path, device resident: per corner acb_ode_shift (src/acb_ode.c:124-135, one launch),
  * acb_ode_solve_fuchs with n terms, and the re-expansion at the next corner.  Only the first `order`
- * Taylor coefficients survive a step (the next solve overwrites the rest), so the re-expansion is
+ * Taylor coefficients survive a step (the next solve overwrites the rest), so between corners the re-expansion is
  * a Horner evaluation with `order` normalised derivatives instead of a full acb_poly_taylor_shift.
  * ode : (order+1)(degree+1) entries, S = 2.  path : path_len entries (corners), S = 2.
  * y   : order entries, S = 2*batch: Taylor coefficients at path[0] in, at path[path_len-1] out.
- * Every corner must be an ordinary point (leading coefficient nonzero there: valuation -order).
- * corner_is_zero (HOST pointer, may be NULL): path_len flags, 1 where a corner is the exact zero ball
- * (acb_ode_shift then skips the shift, src/acb_ode.c:128). 1 <= order <= 4. */
+ * As in the reference (src/fuchs_solver.c:105) every solve runs with the valuation of the operator SHIFTED to that
+ * corner: the meta records of the shifted operator (a few hundred bytes) are read back once per corner -- the stream
+ * is synchronised there, the one exception to "_dev functions do not synchronise".  An ordinary point has valuation
+ * -order; at a corner where the shifted operator has a smaller |valuation| only the first -valuation entries of y
+ * are read (the reference's res[0 .. -v-1]); a corner with valuation >= 0 returns CB200_EVALUATION (undefined in the
+ * reference).  An exactly zero corner leaves the operator unshifted (src/acb_ode.c:128).
+ * corner_is_zero is ignored (kept for ABI stability; may be NULL).  1 <= order <= 4.
+ * The _series variants also return what the reference leaves in `res` after the last corner: res (n+1 entries,
+ * S = 2*batch) = the complete series re-expanded at path[path_len-1] (cb200_taylor_shift); path_len >= 2. */
 size_t cb200_continuation_workspace_bytes(int L, int order, int degree, int64_t n, int64_t batch);
+size_t cb200_continuation_series_workspace_bytes(int L, int order, int degree, int64_t n, int64_t batch);
 int cb200_continuation_dev(int L, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
                            const uint32_t *ode_mant, const cb_meta *ode_meta, const uint32_t *path_mant,
                            const cb_meta *path_meta, const uint8_t *corner_is_zero, uint32_t *y_mant,
@@ -262,6 +309,14 @@ int cb200_continuation_dev(int L, int order, int degree, int64_t n, int64_t batc
 int cb200_continuation_host(int L, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
                             const uint32_t *ode_mant, const cb_meta *ode_meta, const uint32_t *path_mant,
                             const cb_meta *path_meta, uint32_t *y_mant, cb_meta *y_meta, int device);
+int cb200_continuation_series_dev(int L, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
+                                  const uint32_t *ode_mant, const cb_meta *ode_meta, const uint32_t *path_mant,
+                                  const cb_meta *path_meta, uint32_t *y_mant, cb_meta *y_meta, uint32_t *res_mant,
+                                  cb_meta *res_meta, void *workspace, size_t workspace_bytes, void *stream);
+int cb200_continuation_series_host(int L, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
+                                   const uint32_t *ode_mant, const cb_meta *ode_meta, const uint32_t *path_mant,
+                                   const cb_meta *path_meta, uint32_t *y_mant, cb_meta *y_meta, uint32_t *res_mant,
+                                   cb_meta *res_meta, int device);
 
 /* ---- elementwise ball operations over n complex balls (1 entry, S = 2*n each); k: n integers
  * for the *_SI ops (device pointer in _dev, may be NULL otherwise); y ignored for INV/_SI. */

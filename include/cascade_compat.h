@@ -179,9 +179,11 @@ void acb_ode_hypgeom(acb_ode_t ODE, acb_t a, acb_t b, acb_t c, slong bits);
 
 /* ============================== Solvers (reference src/cascade.h:13-26) ======================= */
 void acb_ode_solve_fuchs(acb_poly_t res, acb_ode_t ODE, slong deg, slong bits);
-/* Per path corner: shift, solve, and re-expand at the next corner.  Only the first `order`
- * Taylor coefficients survive into the next step; they are produced by Horner
- * evaluation on the device.  On return res holds those `order` coefficients at the last corner. */
+/* Per path corner: shift, solve (with the valuation of the shifted operator, as src/fuchs_solver.c:105), and
+ * re-expand at the next corner.  Between corners only the first `order` Taylor coefficients survive:
+ * Horner evaluation with derivatives on the device.  After the LAST corner res holds, as in the reference
+ * (src/fuchs_solver.c:159), the complete re-expanded series of deg + 1 coefficients (acb_poly_taylor_shift, Horner
+ * form).  A corner where the shifted operator has valuation >= 0 aborts (undefined in the reference). */
 void analytic_continuation(acb_poly_t res, acb_ode_t ODE, acb_srcptr path, slong len, slong deg, slong bits);
 /* Monodromy around the origin along the 256-gon of half the convergence radius (reference
  * src/fuchs_solver.c:165-206): the `order` unit initial vectors continue together as one device-resident

@@ -141,6 +141,13 @@ int cbo_ode_apply_flat(int L, int order, int degree, const uint32_t *ode_m, cons
                        const uint32_t *res_m, const int32_t *res_t, int64_t len, uint32_t *out_m, int32_t *out_t);
 int cbo_example_flat(int which, int L, uint64_t n, const uint32_t *par_m, const int32_t *par_t,
                      uint32_t *out_m, int32_t *out_t);
+void cbo_poly_taylor_shift_horner(cbo_acb *p, int64_t len, const cbo_acb *a, int L);
+int cbo_taylor_shift_flat(int L, int64_t len, int64_t batch, uint32_t *f_m, int32_t *f_t, const uint32_t *a_m,
+                          const int32_t *a_t, int shared_a);
+int cbo_continuation_series_flat(int L, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
+                                 const uint32_t *ode_m, const int32_t *ode_t, const uint32_t *path_m,
+                                 const int32_t *path_t, uint32_t *y_m, int32_t *y_t, uint32_t *full_m,
+                                 int32_t *full_t);
 int cbo_continuation_flat(int L, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
                           const uint32_t *ode_m, const int32_t *ode_t, const uint32_t *path_m,
                           const int32_t *path_t, uint32_t *y_m, int32_t *y_t);

@@ -50,6 +50,9 @@ def lib(plain: bool = False) -> C.CDLL:
                                       C.c_int64, C.c_int64]
     L.cbo_continuation_flat.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, _u32p, _i32p,
                                         _u32p, _i32p, _u32p, _i32p]
+    L.cbo_continuation_series_flat.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, _u32p, _i32p,
+                                               _u32p, _i32p, _u32p, _i32p, _u32p, _i32p]
+    L.cbo_taylor_shift_flat.argtypes = [C.c_int, C.c_int64, C.c_int64, _u32p, _i32p, _u32p, _i32p, C.c_int]
     L.cbo_example_flat.argtypes = [C.c_int, C.c_int, C.c_uint64, _u32p, _i32p, _u32p, _i32p]
     L.cbo_ode_apply_flat.argtypes = [C.c_int, C.c_int, C.c_int, _u32p, _i32p, _u32p, _i32p, C.c_int64, _u32p, _i32p]
     L.cbo_ew_trans.argtypes = [C.c_int, C.c_int, C.c_int64, _u32p, _i32p, _u32p, _i32p]
@@ -159,6 +162,28 @@ def continuation(order: int, degree: int, n: int, ode: Balls, path: Balls, y0: B
                                           path.mant, path.meta, y.mant, y.meta)
     assert rc == 0
     return y
+
+
+def continuation_series(order: int, degree: int, n: int, ode: Balls, path: Balls, y0: Balls, batch: int,
+                        plain: bool = False):
+    """analytic_continuation keeping what the reference leaves in ``res``: returns (rc, y[batch][order],
+    series[batch][n+1]) -- the complete series re-expanded at the last corner (acb_poly_taylor_shift, Horner form).
+    rc = -2: a corner where the shifted operator has valuation >= 0."""
+    y = y0.copy()
+    full = Balls.zeros(batch * (n + 1) * 2, ode.L)
+    rc = lib(plain).cbo_continuation_series_flat(ode.L, order, degree, n, batch, path.n_slots // 2, ode.mant, ode.meta,
+                                                 path.mant, path.meta, y.mant, y.meta, full.mant, full.meta)
+    return rc, y, full
+
+
+def taylor_shift(f: Balls, a: Balls, batch: int, plain: bool = False) -> Balls:
+    """acb_poly_taylor_shift (Horner form) of ``batch`` series f[batch][len] by a[batch] (or one shared ball)."""
+    out = f.copy()
+    length = f.n_slots // (2 * batch)
+    rc = lib(plain).cbo_taylor_shift_flat(f.L, length, batch, out.mant, out.meta, a.mant, a.meta,
+                                          int(a.n_slots == 2))
+    assert rc == 0
+    return out
 
 
 def frobenius1_rhs_batch(order: int, degree: int, n: int, ode: Balls, rho: Balls, rhs: Balls, batch: int,

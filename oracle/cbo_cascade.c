@@ -422,14 +422,43 @@ int cbo_ode_apply_flat(int L, int order, int degree, const uint32_t *ode_m, cons
     return 0;
 }
 
+/* acb_poly_taylor_shift (reference src/fuchs_solver.c:159) in the form Arb's _acb_poly_taylor_shift_horner has:
+ *   for i = len-2 .. 0: for j = i .. len-2: p[j] += p[j+1] * a     (acb_addmul)
+ * (Arb switches to divide-and-conquer / convolution for long series -- enclosures of the same numbers with other
+ * rounding sequences; which one runs depends on the unpinned Arb version, so the Horner form is the stated one.)
+ * The first nder coefficients are, operation for operation, what cbo_poly_evaluate_horner(nder) produces. */
+void cbo_poly_taylor_shift_horner(cbo_acb *p, int64_t len, const cbo_acb *a, int L) {
+    if (cbo_acb_is_zero(a)) return;
+    for (int64_t i = len - 2; i >= 0; i--)
+        for (int64_t j = i; j <= len - 2; j++) cbo_acb_addmul(p + j, p + j + 1, a, L);
+}
+/* f: [batch][len] in place; a: [batch] or one ball (shared_a) */
+int cbo_taylor_shift_flat(int L, int64_t len, int64_t batch, uint32_t *f_m, int32_t *f_t, const uint32_t *a_m,
+                          const int32_t *a_t, int shared_a) {
+    cbo_acb *p = (cbo_acb *)malloc(sizeof(cbo_acb) * (len > 0 ? len : 1));
+    for (int64_t s = 0; s < batch; s++) {
+        cbo_acb a;
+        load_acb(&a, a_m, a_t, shared_a ? 0 : s, L);
+        for (int64_t k = 0; k < len; k++) load_acb(p + k, f_m, f_t, s * len + k, L);
+        cbo_poly_taylor_shift_horner(p, len, &a, L);
+        for (int64_t k = 0; k < len; k++) store_acb(f_m, f_t, s * len + k, p + k, L);
+    }
+    free(p);
+    return 0;
+}
+
 /* analytic_continuation (reference src/fuchs_solver.c:147-163) for `batch` solutions of one operator
  * along one path.  y: [batch][order] Taylor coefficients at path[0] in, at the last corner out.
- * Per corner: acb_ode_shift, acb_ode_solve_fuchs (n terms), then the first `order` coefficients of
- * the series re-expanded at the next corner, by Horner evaluation with derivatives (SURVEY.md 3.2:
- * the rest of acb_poly_taylor_shift's output is overwritten by the next solve before it is read). */
-int cbo_continuation_flat(int L, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
-                          const uint32_t *ode_m, const int32_t *ode_t, const uint32_t *path_m,
-                          const int32_t *path_t, uint32_t *y_m, int32_t *y_t) {
+ * Per corner: acb_ode_shift, acb_ode_solve_fuchs (n terms; the valuation is that of the SHIFTED operator, as
+ * acb_ode_solve_fuchs computes it at :105 -- so a corner where the operator is singular but of negative valuation
+ * reads only -v initial values), then the first `order` coefficients of the series re-expanded at the next corner,
+ * by Horner evaluation with derivatives (the rest of acb_poly_taylor_shift's output is overwritten by
+ * the next solve before it is read).  full_m/full_t (may be NULL): [batch][n+1], the COMPLETE re-expanded series
+ * the reference leaves in res after the last step (:159).  Returns -2 when a corner has valuation >= 0. */
+int cbo_continuation_series_flat(int L, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
+                                 const uint32_t *ode_m, const int32_t *ode_t, const uint32_t *path_m,
+                                 const int32_t *path_t, uint32_t *y_m, int32_t *y_t, uint32_t *full_m,
+                                 int32_t *full_t) {
     cbo_ode *o = load_ode(L, order, degree, ode_m, ode_t, 0);
     cbo_ode *sh = cbo_ode_new(degree, order);
     cbo_acb *res = (cbo_acb *)malloc(sizeof(cbo_acb) * (n + 1));
@@ -439,19 +468,36 @@ int cbo_continuation_flat(int L, int order, int degree, int64_t n, int64_t batch
         load_acb(&c0, path_m, path_t, t, L);
         load_acb(&c1, path_m, path_t, t + 1, L);
         cbo_ode_shift(sh, o, &c0, L);
+        sh->valuation = CBO_UNDEFINED;
+        if (cbo_ode_valuation(sh) >= 0) {
+            rc = -2;
+            break;
+        }
         cbo_acb_sub(&a, &c1, &c0, L);
+        const int last = (t + 2 == path_len);
         for (int64_t s = 0; s < batch; s++) {
             for (int k = 0; k < order; k++) load_acb(res + k, y_m, y_t, s * order + k, L);
-            sh->valuation = -order; /* ordinary point by contract (as the device path) */
             if (cbo_solve_fuchs(res, sh, n, L) != 0) rc = -1;
-            cbo_poly_evaluate_horner(out, res, n + 1, &a, order, L);
-            for (int k = 0; k < order; k++) store_acb(y_m, y_t, s * order + k, out + k, L);
+            if (last && full_m) {
+                cbo_poly_taylor_shift_horner(res, n + 1, &a, L);
+                for (int64_t k = 0; k <= n; k++) store_acb(full_m, full_t, s * (n + 1) + k, res + k, L);
+                for (int k = 0; k < order; k++) store_acb(y_m, y_t, s * order + k, res + k, L);
+            } else {
+                cbo_poly_evaluate_horner(out, res, n + 1, &a, order, L);
+                for (int k = 0; k < order; k++) store_acb(y_m, y_t, s * order + k, out + k, L);
+            }
         }
     }
     free(res);
     cbo_ode_free(o);
     cbo_ode_free(sh);
     return rc;
+}
+int cbo_continuation_flat(int L, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
+                          const uint32_t *ode_m, const int32_t *ode_t, const uint32_t *path_m,
+                          const int32_t *path_t, uint32_t *y_m, int32_t *y_t) {
+    return cbo_continuation_series_flat(L, order, degree, n, batch, path_len, ode_m, ode_t, path_m, path_t, y_m, y_t,
+                                        NULL, NULL);
 }
 
 /* which: 0 legendre(n), 1 bessel(par[0]) (par[0] is overwritten with nu^2), 2 hypgeom(par[0..2]) */

@@ -163,7 +163,31 @@ static void arb_set_d(cbo_arb *z, double d, int L) { /* exact; subnormals flush 
 }
 
 /* ---- log */
+static void acb_log_main(cbo_acb *res, const cbo_acb *a, int L);
+/* A ball that straddles the branch cut (re < 0, im a non-exact ball containing 0) holds points with arg near +pi
+ * and points with arg near -pi: the principal log is discontinuous on it.  Like Arb's acb_log (acb_arg returns
+ * [-pi, pi] there) the result is Re = log|a| (taken from log(-a): -a lies around the positive real axis, away from
+ * the cut, and |-a| = |a|) and Im = [0 +- pi], pi rounded up to a 30-bit magnitude.  A point ON the cut (im an
+ * exact zero) keeps the principal value +i pi. */
+#define CBO_PI_MAG_MAN 843314857u /* ceil(pi * 2^28): pi <= man * 2^(2-30) */
+#define CBO_PI_MAG_EXP 2
 void cbo_acb_log(cbo_acb *res, const cbo_acb *a, int L) {
+    int im_exact_zero = (a->im.flags & CBO_ZERO) && a->im.rman == 0;
+    if (cbo_acb_is_finite(a) && !(a->re.flags & CBO_ZERO) && (a->re.flags & CBO_SIGN) && !im_exact_zero &&
+        cbo_arb_contains_zero(&a->im)) {
+        cbo_acb na;
+        cbo_acb_neg(&na, a);
+        acb_log_main(res, &na, L);
+        if (cbo_acb_is_finite(res)) {
+            cbo_arb_zero(&res->im);
+            res->im.rman = CBO_PI_MAG_MAN;
+            res->im.rexp = CBO_PI_MAG_EXP;
+        }
+        return;
+    }
+    acb_log_main(res, a, L);
+}
+static void acb_log_main(cbo_acb *res, const cbo_acb *a, int L) {
     if (!cbo_acb_is_finite(a) || cbo_acb_contains_zero(a)) {
         acb_set_nan(res);
         return;

@@ -8,7 +8,7 @@ from fractions import Fraction as F
 
 import numpy as np
 
-from cascade_b200 import api
+from cascade_b200 import _lib, api
 from cascade_b200.format import FLAG_NAN, FLAG_ZERO, Balls, from_complex, random_balls
 
 
@@ -332,6 +332,89 @@ def case_continuation(oracle, drv, L: int, seed: int, steps: int = 5, n: int = 3
     assert_same(yo, ys, f"analytic continuation from the origin L={L}")
 
 
+def case_ode_shift(oracle, drv, L: int, seed: int, batch: int = 5):
+    """acb_ode_shift (reference src/acb_ode.c:124-135) as ONE launch for a batch: per-instance operators, one operator
+    moved to several points, an exactly zero point (the copy), degree-0 rows."""
+    rng = np.random.default_rng(seed)
+    for order, degree in ((2, 2), (3, 4), (1, 0)):
+        ne = (order + 1) * (degree + 1)
+        odes = random_balls(rng, batch * ne * 2, L, -2, 2, "ulp")
+        a = random_balls(rng, batch * 2, L, -1, 1, "ulp")
+        a.mant[2:4] = 0
+        a.meta[2:4] = (0, FLAG_ZERO, 0, 0)  # instance 1 is not moved
+        got = api.acb_ode_shift_batch(odes, a, order, degree, driver=drv)
+        want = Balls.concat([oracle.ode_shift(order, degree, odes[i * ne * 2:(i + 1) * ne * 2], a[2 * i:2 * i + 2])
+                             for i in range(batch)])
+        assert_same(want, got, f"acb_ode_shift L={L} order={order} degree={degree}")
+        one = odes[: ne * 2]
+        got = api.acb_ode_shift_batch(one, a, order, degree, driver=drv)
+        want = Balls.concat([oracle.ode_shift(order, degree, one, a[2 * i:2 * i + 2]) for i in range(batch)])
+        assert_same(want, got, f"acb_ode_shift of one operator to {batch} points L={L}")
+
+
+def case_taylor_shift(oracle, drv, L: int, seed: int, length: int = 30, batch: int = 3):
+    """acb_poly_taylor_shift (reference src/fuchs_solver.c:159), Horner form, one CTA per series; its first
+    coefficients are bit for bit the Horner evaluation with derivatives that the continuation pipeline keeps."""
+    rng = np.random.default_rng(seed)
+    f = random_balls(rng, batch * length * 2, L, -3, 3, "ulp")
+    a = random_balls(rng, batch * 2, L, -2, 0, "ulp")
+    got = api.acb_poly_taylor_shift_batch(f, a, batch, driver=drv)
+    assert_same(oracle.taylor_shift(f, a, batch), got, f"taylor shift L={L}")
+    a1 = a[:2]
+    got1 = api.acb_poly_taylor_shift_batch(f, a1, batch, driver=drv)
+    assert_same(oracle.taylor_shift(f, a1, batch), got1, f"taylor shift by a shared point L={L}")
+    for s in range(batch):
+        h = oracle.horner_batch(f[s * length * 2:(s + 1) * length * 2], a1, 3)
+        assert h.same_as(got1[s * length * 2: s * length * 2 + 6]), "Horner-with-derivatives == head of the Taylor shift"
+    z = Balls.zeros(2, L)
+    assert_same(f, api.acb_poly_taylor_shift_batch(f, z, batch, driver=drv), "taylor shift by zero")
+    assert_same(oracle.taylor_shift(f[:2], a1, 1), api.acb_poly_taylor_shift_batch(f[:2], a1, 1, driver=drv), "length 1")
+
+
+def case_continuation_series(oracle, drv, L: int, seed: int, steps: int = 3, n: int = 24, batch: int = 2):
+    """analytic_continuation returning what the reference leaves in `res` (the complete re-expanded series), and
+    corners where the shifted operator is SINGULAR: valuation > -order (only -v initial values are read, as in
+    reference src/fuchs_solver.c:105-117) and valuation >= 0 (rejected)."""
+    rng = np.random.default_rng(seed)
+    par = random_balls(rng, 6, L, -1, 1, "zero")
+    ode = oracle.example("hypgeom", L, 0, par)
+    th = np.linspace(0.3, 1.4, steps + 1)
+    path = from_complex([(F(float(0.5 + 0.25 * np.cos(t))).limit_denominator(2**20),
+                          F(float(0.3 * np.sin(t))).limit_denominator(2**20)) for t in th], L)
+    y0 = random_balls(rng, batch * 2 * 2, L, -1, 0, "zero")
+    rc, yo, so = oracle.continuation_series(2, 2, n, ode, path, y0, batch)
+    assert rc == 0
+    ys, ss = api.analytic_continuation_series_batch(ode, path, y0, 2, 2, n, batch, driver=drv)
+    assert_same(yo, ys, f"continuation (series variant) y L={L}")
+    assert_same(so, ss, f"continuation: complete re-expanded series L={L}")
+    assert_same(yo, api.analytic_continuation_batch(ode, path, y0, 2, 2, n, batch, driver=drv), "both variants agree on y")
+    # the hypergeometric operator AT its singular point 0 (exact-zero corner: valuation -1), then on to 1/8
+    path0 = from_complex([0, F(1, 8), F(3, 16)], L)
+    rc, yo, so = oracle.continuation_series(2, 2, n, ode, path0, y0, batch)
+    assert rc == 0
+    ys, ss = api.analytic_continuation_series_batch(ode, path0, y0, 2, 2, n, batch, driver=drv)
+    assert_same(yo, ys, f"continuation from a regular singular corner L={L}")
+    assert_same(so, ss, f"continuation from a regular singular corner, series L={L}")
+    assert not (ys.meta[:, 1] & FLAG_NAN).any()
+    # Legendre moved to its singular point 1: (1 - z^2) -> -2z - z^2 exactly, valuation -1 after the shift
+    leg = oracle.example("legendre", L, 3)
+    path1 = from_complex([1, F(7, 8)], L)
+    rc, yo, so = oracle.continuation_series(2, 2, n, leg, path1, y0, batch)
+    assert rc == 0
+    ys, ss = api.analytic_continuation_series_batch(leg, path1, y0, 2, 2, n, batch, driver=drv)
+    assert_same(yo, ys, f"continuation from a corner that is singular after the shift L={L}")
+    assert_same(so, ss, f"... series L={L}")
+    # Bessel at the origin has valuation 0: undefined in the reference, rejected here
+    bes = oracle.example("bessel", L, 0, random_balls(rng, 2, L, 0, 0, "zero"))
+    rc, _, _ = oracle.continuation_series(2, 2, n, bes, path0, y0, batch)
+    assert rc == -2
+    try:
+        api.analytic_continuation_batch(bes, path0, y0, 2, 2, n, batch, driver=drv)
+        raise AssertionError("valuation >= 0 must be rejected")
+    except _lib.CascadeB200Error:
+        pass
+
+
 def case_horner(oracle, drv, L: int, seed: int, length: int = 40, npts: int = 9):
     rng = np.random.default_rng(seed)
     f = random_balls(rng, 2 * length, L, -3, 3, "ulp")
@@ -530,6 +613,14 @@ def trans_inputs(rng, L: int, n: int) -> Balls:
         x.meta[2 * k, 2], x.meta[2 * k, 3] = 1 << 29, x.meta[2 * k, 0] - 20
         x.meta[2 * k + 2, 2], x.meta[2 * k + 2, 3] = 1 << 29, x.meta[2 * k + 2, 0] + 3
         x.meta[2 * k + 3, 2], x.meta[2 * k + 3, 3] = 1 << 29, x.meta[2 * k + 3, 0] + 3
+    if n > k + 4:
+        # a ball straddling the branch cut of log (re < 0, im = small +- larger): Im log = [0 +- pi]; and its neighbour,
+        # re < 0 with an im ball that stays on one side of the cut
+        for e, wide in ((k + 2, 2), (k + 3, -6)):
+            x.meta[2 * e, 1] |= 1            # re negative
+            x.meta[2 * e, 0] = 1
+            x.meta[2 * e + 1, 0] = -40       # |im| ~ 2^-40
+            x.meta[2 * e + 1, 2], x.meta[2 * e + 1, 3] = 1 << 29, -40 + wide
     return x
 
 

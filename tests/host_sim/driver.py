@@ -35,6 +35,10 @@ def lib():
         L.cbsim_fuchs_batch_range.argtypes = [C.c_int] * 4 + [C.c_int64] * 3 + [_u32p, _i32p, C.c_int, _u32p, _i32p]
         L.cbsim_fuchs_intop_batch.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS"), C.c_int, _u32p, _i32p]
         L.cbsim_continuation.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, _u32p, _i32p, _u32p, _i32p, _u32p, _i32p]
+        L.cbsim_continuation_series.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, _u32p, _i32p, _u32p, _i32p,
+                                                _u32p, _i32p, _u32p, _i32p]
+        L.cbsim_ode_shift.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, _u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int, _u32p, _i32p]
+        L.cbsim_taylor_shift.argtypes = [C.c_int, C.c_int64, C.c_int64, _u32p, _i32p, _u32p, _i32p, C.c_int]
         L.cbsim_frobenius1_batch.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int, _vp, _vp, C.c_int64, C.c_int, _u32p, _i32p]
         L.cbsim_horner_batch.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int, _u32p, _i32p, C.c_int, _u32p, _i32p, _u32p, _i32p]
         L.cbsim_ew.argtypes = [C.c_int, C.c_int, C.c_int64, _u32p, _i32p, _u32p, _i32p, _vp, _vp, _vp]
@@ -66,6 +70,16 @@ class SimDriver:
 
     def continuation(self, L, order, degree, n, batch, path_len, ode_m, ode_t, path_m, path_t, y_m, y_t):
         return lib().cbsim_continuation(L, order, degree, n, batch, path_len, ode_m, ode_t, path_m, path_t, y_m, y_t)
+
+    def continuation_series(self, L, order, degree, n, batch, path_len, ode_m, ode_t, path_m, path_t, y_m, y_t, r_m, r_t):
+        return lib().cbsim_continuation_series(L, order, degree, n, batch, path_len, ode_m, ode_t, path_m, path_t, y_m, y_t,
+                                               r_m, r_t)
+
+    def ode_shift(self, L, order, degree, batch, ode_m, ode_t, shared, a_m, a_t, shared_a, o_m, o_t):
+        return lib().cbsim_ode_shift(L, order, degree, batch, ode_m, ode_t, int(shared), a_m, a_t, int(shared_a), o_m, o_t)
+
+    def taylor_shift(self, L, length, batch, f_m, f_t, a_m, a_t, shared_a):
+        return lib().cbsim_taylor_shift(L, length, batch, f_m, f_t, a_m, a_t, int(shared_a))
 
     def frobenius1(self, L, order, degree, valuation, n, batch, ode_m, ode_t, shared, rho_m, rho_t,
                    shared_rho, res_m, res_t, rhs_m=None, rhs_t=None, rhs_len=0, shared_rhs=False):

@@ -296,39 +296,85 @@ int cbsim_ew(int op, int L_, int64_t n, uint32_t* z_mant, cb_meta* z_meta, const
 }
 
 
-int cbsim_continuation(int L_, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
-                       const uint32_t* ode_mant, const cb_meta* ode_meta, const uint32_t* path_mant,
-                       const cb_meta* path_meta, uint32_t* y_mant, cb_meta* y_meta) {
-    // same sequence of operations as cb200_continuation_dev, on host memory
+int cbsim_ode_shift(int L_, int order, int degree, int64_t batch, const uint32_t* ode_mant, const cb_meta* ode_meta,
+                    int shared_ode, const uint32_t* a_mant, const cb_meta* a_meta, int shared_a, uint32_t* out_mant,
+                    cb_meta* out_meta) {
+    ShiftParams p;
+    p.order = order; p.degree = degree; p.batch = batch;
+    p.in = CArr{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta), shared_ode ? (size_t)2 : (size_t)(2 * batch)};
+    p.a = CArr{const_cast<uint32_t*>(a_mant), (Meta*)const_cast<cb_meta*>(a_meta), shared_a ? (size_t)2 : (size_t)(2 * batch)};
+    p.out = CArr{out_mant, (Meta*)out_meta, (size_t)(2 * batch)};
+    Tmp tmp;
+    p.tmp = tmp.arr(L_, 1, 2 * batch);
+    SIM_DISPATCH(L_, run<L>(batch, [&](int64_t i, Scratch<1> a, Scratch<1> b) { ode_shift_thread<L>(p, i, a, b); }));
+    return 0;
+}
+
+// the two phases of every sweep of taylor_shift_kernel, the "threads" of a phase one after another
+int cbsim_taylor_shift(int L_, int64_t len, int64_t batch, uint32_t* f_mant, cb_meta* f_meta, const uint32_t* a_mant,
+                       const cb_meta* a_meta, int shared_a) {
+    TShiftParams p;
+    p.len = len; p.batch = batch;
+    p.f = CArr{f_mant, (Meta*)f_meta, (size_t)(2 * batch)};
+    p.a = CArr{const_cast<uint32_t*>(a_mant), (Meta*)const_cast<cb_meta*>(a_meta), shared_a ? (size_t)2 : (size_t)(2 * batch)};
+    Tmp tmp;
+    p.tmp = tmp.arr(L_, len > 0 ? len : 1, 2 * batch);
+    for (int64_t inst = 0; inst < batch; inst++) {
+        if (acb_is_exact_zero(at<4>(p.a, 0, shared_a ? 0 : 2 * (size_t)inst))) continue;  // meta only: L irrelevant
+        for (int64_t i = len - 2; i >= 0; i--) {
+            SIM_DISPATCH(L_, run<L>(len - 1 - i, [&](int64_t k, Scratch<1> a, Scratch<1> b) { taylor_shift_mul<L>(p, inst, i + k, a, b); }));
+            SIM_DISPATCH(L_, run<L>(len - 1 - i, [&](int64_t k, Scratch<1> a, Scratch<1> b) { taylor_shift_add<L>(p, inst, i + k, a, b); }));
+        }
+    }
+    return 0;
+}
+
+static int sim_valuation_of(const cb_meta* t, int order, int degree) {
+    int val = degree;
+    for (int i = 0; i <= order; i++) {
+        int z = 0;
+        for (; z <= degree; z++) {
+            const cb_meta* c = t + 2 * (i * (degree + 1) + z);
+            bool zero = (c[0].flags & CB_FLAG_ZERO) && c[0].rman == 0 && (c[1].flags & CB_FLAG_ZERO) && c[1].rman == 0;
+            if (!zero) break;
+        }
+        if (z - i < val) val = z - i;
+    }
+    return val;
+}
+
+int cbsim_continuation_series(int L_, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
+                              const uint32_t* ode_mant, const cb_meta* ode_meta, const uint32_t* path_mant,
+                              const cb_meta* path_meta, uint32_t* y_mant, cb_meta* y_meta, uint32_t* full_mant,
+                              cb_meta* full_meta) {
+    // same sequence of operations as continuation_impl (abi.cu), on host memory
     const int64_t ne = (int64_t)(order + 1) * (degree + 1), S = 2 * batch;
     std::vector<uint32_t> shm((size_t)ne * L_ * 2), serm((size_t)(n + 1) * L_ * S), tbm((size_t)3 * L_ * 2);
     std::vector<cb_meta> sht((size_t)ne * 2), sert((size_t)(n + 1) * S), tbt(6);
     auto bm = [&](std::vector<uint32_t>& v, int64_t e) { return v.data() + (size_t)e * L_ * 2; };
     auto bt = [&](std::vector<cb_meta>& v, int64_t e) { return v.data() + (size_t)e * 2; };
     for (int64_t t = 0; t + 1 < path_len; t++) {
-        memcpy(shm.data(), ode_mant, shm.size() * 4);
-        memcpy(sht.data(), ode_meta, sht.size() * sizeof(cb_meta));
         const uint32_t* am = path_mant + (size_t)t * L_ * 2;
         const cb_meta* at_ = path_meta + (size_t)t * 2;
-        bool zero = (at_[0].flags & CB_FLAG_ZERO) && at_[0].rman == 0 && (at_[1].flags & CB_FLAG_ZERO) && at_[1].rman == 0;
-        if (degree > 0 && !zero) {
-            int D1 = degree + 1;
-            for (int row = 0; row <= order; row++)
-                for (int i = D1 - 2; i >= 0; i--)
-                    for (int j = i; j <= D1 - 2; j++) {
-                        int64_t ej = (int64_t)row * D1 + j;
-                        cbsim_ew(CB200_OP_MUL, L_, 1, bm(tbm, 1), bt(tbt, 1), bm(shm, ej + 1), bt(sht, ej + 1), am, at_, nullptr);
-                        cbsim_ew(CB200_OP_ADD, L_, 1, bm(tbm, 2), bt(tbt, 2), bm(shm, ej), bt(sht, ej), bm(tbm, 1), bt(tbt, 1), nullptr);
-                        memcpy(bm(shm, ej), bm(tbm, 2), (size_t)L_ * 2 * 4);
-                        memcpy(bt(sht, ej), bt(tbt, 2), 2 * sizeof(cb_meta));
-                    }
-        }
-        memcpy(serm.data(), y_mant, (size_t)order * L_ * S * 4);
-        memcpy(sert.data(), y_meta, (size_t)order * S * sizeof(cb_meta));
-        int rc = cbsim_fuchs_batch(L_, order, degree, -order, n, batch, shm.data(), sht.data(), 1, serm.data(), sert.data());
+        int rc = cbsim_ode_shift(L_, order, degree, 1, ode_mant, ode_meta, 1, am, at_, 1, shm.data(), sht.data());
+        if (rc) return rc;
+        const int v = sim_valuation_of(sht.data(), order, degree);
+        if (v >= 0) return CB200_EVALUATION;
+        memcpy(serm.data(), y_mant, (size_t)(-v) * L_ * S * 4);
+        memcpy(sert.data(), y_meta, (size_t)(-v) * S * sizeof(cb_meta));
+        rc = cbsim_fuchs_batch(L_, order, degree, v, n, batch, shm.data(), sht.data(), 1, serm.data(), sert.data());
         if (rc) return rc;
         cbsim_ew(CB200_OP_SUB, L_, 1, bm(tbm, 0), bt(tbt, 0), path_mant + (size_t)(t + 1) * L_ * 2, path_meta + (size_t)(t + 1) * 2,
                  am, at_, nullptr);
+        if (full_mant && t + 2 == path_len) {
+            rc = cbsim_taylor_shift(L_, n + 1, batch, serm.data(), sert.data(), bm(tbm, 0), bt(tbt, 0), 1);
+            if (rc) return rc;
+            memcpy(full_mant, serm.data(), serm.size() * 4);
+            memcpy(full_meta, sert.data(), sert.size() * sizeof(cb_meta));
+            memcpy(y_mant, serm.data(), (size_t)order * L_ * S * 4);
+            memcpy(y_meta, sert.data(), (size_t)order * S * sizeof(cb_meta));
+            break;
+        }
         HornerParams hp;
         hp.nder = order; hp.len = n + 1; hp.npts = batch;
         hp.f = CArr{serm.data(), (Meta*)sert.data(), (size_t)S};
@@ -340,6 +386,12 @@ int cbsim_continuation(int L_, int order, int degree, int64_t n, int64_t batch, 
         SIM_DISPATCH(L_, run_hyb<L>(batch, [&](int64_t i, auto a, auto b) { horner_thread<L>(hp, i, a, b); }));
     }
     return 0;
+}
+int cbsim_continuation(int L_, int order, int degree, int64_t n, int64_t batch, int64_t path_len,
+                       const uint32_t* ode_mant, const cb_meta* ode_meta, const uint32_t* path_mant,
+                       const cb_meta* path_meta, uint32_t* y_mant, cb_meta* y_meta) {
+    return cbsim_continuation_series(L_, order, degree, n, batch, path_len, ode_mant, ode_meta, path_mant, path_meta, y_mant,
+                                     y_meta, nullptr, nullptr);
 }
 
 }  // extern "C"

@@ -21,14 +21,37 @@ def declared(header):
 
 
 def test_library_exports_every_declared_symbol():
+    import ctypes
     lib = _lib.lib()
     names = declared("cascade_b200.h")
     assert set(_lib.SYMBOLS) <= set(names)
-    for name in names + [n for n in declared("cascade_compat.h") if not n.endswith("_struct")]:
+    for name in names:
+        assert hasattr(lib, name), f"{name} is declared in include/cascade_b200.h but not exported"
+    assert b"sm_100a" in lib.cb200_version()
+    # the reference's own names live in the SEPARATE compat library (for machines without Arb)
+    compat = ctypes.CDLL(os.path.join(ROOT, "cascade_b200", "libcascade_b200_compat.so"))
+    for name in [n for n in declared("cascade_compat.h") if not n.endswith("_struct") and not n.startswith("cb200_")]:
         if name in ("acb_ode_poly", "acb_ode_coeff", "acb_ode_t", "acb_ode_solution_t"):
             continue  # macros / types
-        assert hasattr(lib, name), f"{name} is declared in include/ but not exported"
-    assert b"sm_100a" in lib.cb200_version()
+        assert hasattr(compat, name), f"{name} is declared in include/cascade_compat.h but not exported"
+
+
+def test_batch_library_exports_only_its_own_prefix_and_links_next_to_arb_names():
+    """libcascade_b200.so must be linkable into a Cascade that is built against the REAL Arb (INTEGRATION.md
+    section 2): it exports cb200_* and nothing else, so a program that defines (or links a library defining)
+    acb_mul, acb_init, acb_poly_* ... -- Arb's names -- does not clash with it."""
+    import subprocess
+    so = os.path.join(ROOT, "cascade_b200", "libcascade_b200.so")
+    out = subprocess.run(["nm", "-D", "--defined-only", so], check=True, capture_output=True, text=True).stdout
+    syms = [line.split()[-1] for line in out.splitlines() if line.strip()]
+    assert syms and all(x.startswith("cb200_") for x in syms), [x for x in syms if not x.startswith("cb200_")][:5]
+    src = os.path.join(ROOT, "tests", "c", "link_next_to_arb.c")
+    exe = os.path.join(ROOT, "tests", "c", "link_next_to_arb")
+    subprocess.run(["/usr/bin/gcc", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", exe, src,
+                    "-L", os.path.join(ROOT, "cascade_b200"), "-lcascade_b200",
+                    "-Wl,-rpath," + os.path.join(ROOT, "cascade_b200")], check=True)
+    r = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert "own acb_mul: 42" in r and "cascade_b200" in r
 
 
 def test_no_cpu_fallback():
@@ -61,6 +84,27 @@ def test_valuation_matches_reference_rule():
         api.acb_ode_solve_fuchs_batch(bes, Balls.zeros(0, L), 2, 2, 5, 1, True)
 
 
+def test_mixed_valuations_are_rejected():
+    """A batched launch runs with one valuation: per-instance operators whose valuations differ (exact-zero
+    leading coefficients, as acb_ode_random can produce) must be rejected, not solved with instance 0's window."""
+    L = 32
+    good = api.acb_ode_legendre_batch([3, 4, 5], L)            # valuation -2 each
+    assert api.acb_ode_valuations(good, 2, 2).tolist() == [-2, -2, -2]
+    assert api.batch_valuation(good, 2, 2, False, "t") == -2
+    bad = good.copy()
+    e = 2 * (1 * 9 + 2 * 3 + 0)                                 # instance 1: zero P[2][0] -> (1 - z^2) becomes -z^2: valuation 0
+    bad.mant[e:e + 2] = 0
+    bad.meta[e:e + 2] = 0
+    bad.meta[e:e + 2, 1] = FLAG_ZERO
+    assert api.acb_ode_valuations(bad, 2, 2).tolist() == [-2, 0, -2]
+    for inst in range(3):
+        assert api.acb_ode_valuations(bad, 2, 2)[inst] == api.acb_ode_valuation(bad, 2, 2, inst)
+    with pytest.raises(_lib.CascadeB200Error, match="different valuations"):
+        api.acb_ode_solve_fuchs_batch(bad, Balls.zeros(3 * 2 * 2, L), 2, 2, 5, 3, False)
+    with pytest.raises(_lib.CascadeB200Error, match="different valuations"):
+        api.acb_ode_solve_frobenius1_batch(bad, Balls.zeros(3 * 2, L), 2, 2, 5, 3, False)
+
+
 def test_layout_roundtrip():
     rng = np.random.default_rng(0)
     b = random_balls(rng, 5 * 7 * 2, 4, -3, 3, "ulp")
@@ -91,7 +135,7 @@ def test_radius_and_reduce_program():
     exe = os.path.join(ROOT, "tests", "c", "radius_example")
     subprocess.run(["/usr/bin/gcc", "-O1", "-I", os.path.join(ROOT, "include"), "-o", exe,
                     os.path.join(ROOT, "tests", "c", "radius_example.c"), "-L", os.path.join(ROOT, "cascade_b200"),
-                    "-lcascade_b200", "-lm", "-Wl,-rpath," + os.path.join(ROOT, "cascade_b200")], check=True)
+                    "-lcascade_b200_compat", "-lcascade_b200", "-lm", "-Wl,-rpath," + os.path.join(ROOT, "cascade_b200")], check=True)
     out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
     v = {line.split()[0]: line.split()[1:] for line in out.strip().splitlines()}
     r = float(v["radius"][0])

@@ -67,6 +67,21 @@ def test_continuation(oracle, sim_driver, L):
     cases.case_continuation(oracle, sim_driver, L, seed=3 + L)
 
 
+@pytest.mark.parametrize("L", [4, 32])
+def test_continuation_series_and_singular_corners(oracle, sim_driver, L):
+    cases.case_continuation_series(oracle, sim_driver, L, seed=5 + L)
+
+
+@pytest.mark.parametrize("L", [4, 32, 64])
+def test_ode_shift(oracle, sim_driver, L):
+    cases.case_ode_shift(oracle, sim_driver, L, seed=7 + L, batch=4)
+
+
+@pytest.mark.parametrize("L", [4, 32])
+def test_taylor_shift(oracle, sim_driver, L):
+    cases.case_taylor_shift(oracle, sim_driver, L, seed=9 + L, length=20)
+
+
 @pytest.mark.parametrize("L", [4, 32, 64])
 def test_exponent_overflow(oracle, sim_driver, L):
     cases.case_exponent_overflow(oracle, sim_driver, L)

@@ -1,5 +1,5 @@
 """The reference's own API names (include/cascade_compat.h) on the GPU: the README program and a
-Frobenius / continuation / evaluate program, compiled with gcc and linked to libcascade_b200.so."""
+Frobenius / continuation / evaluate program, compiled with gcc and linked to libcascade_b200_compat.so (the reference's names) + libcascade_b200.so (the C ABI)."""
 import math
 import os
 import subprocess
@@ -14,7 +14,7 @@ def build_and_run(name):
     exe = os.path.join(ROOT, "tests", "c", name)
     subprocess.run(["/usr/bin/gcc", "-O1", "-I", os.path.join(ROOT, "include"), "-o", exe,
                     os.path.join(ROOT, "tests", "c", name + ".c"), "-L", os.path.join(ROOT, "cascade_b200"),
-                    "-lcascade_b200", "-Wl,-rpath," + os.path.join(ROOT, "cascade_b200")], check=True)
+                    "-lcascade_b200_compat", "-lcascade_b200", "-Wl,-rpath," + os.path.join(ROOT, "cascade_b200")], check=True)
     return subprocess.run([exe], check=True, capture_output=True, text=True).stdout
 
 

@@ -86,6 +86,21 @@ def test_continuation(oracle, gpu_driver, L):
     cases.case_continuation(oracle, gpu_driver, L, seed=23 + L, steps=6, n=40, batch=5)
 
 
+@pytest.mark.parametrize("L", [4, 32, 64])
+def test_continuation_series_and_singular_corners(oracle, gpu_driver, L):
+    cases.case_continuation_series(oracle, gpu_driver, L, seed=5 + L, n=24 if L < 64 else 16)
+
+
+@pytest.mark.parametrize("L", [4, 32, 64, 128])
+def test_ode_shift(oracle, gpu_driver, L):
+    cases.case_ode_shift(oracle, gpu_driver, L, seed=7 + L, batch=37)
+
+
+@pytest.mark.parametrize("L", [4, 32, 64, 128])
+def test_taylor_shift(oracle, gpu_driver, L):
+    cases.case_taylor_shift(oracle, gpu_driver, L, seed=9 + L, length=300 if L == 32 else 40, batch=3)
+
+
 @pytest.mark.parametrize("L", [4, 32, 64, 128])
 def test_exponent_overflow(oracle, gpu_driver, L):
     cases.case_exponent_overflow(oracle, gpu_driver, L)

@@ -224,6 +224,40 @@ def test_exp_log_enclose_mpmath(oracle, L):
                 assert to_mp(z.rad(2 * i)) <= mag * mp.mpf(2) ** (-(32 * L - 40)), (name, i)
 
 
+@pytest.mark.parametrize("L", [4, 32])
+def test_log_across_the_branch_cut(oracle, L):
+    """A ball that straddles the negative real axis contains points whose principal logarithms have imaginary parts
+    near +pi AND near -pi; acb_log must enclose both (Arb returns Im in [-pi, pi] there).  Points of the ball on both
+    sides of the cut, on the cut, and at the corners are checked with mpmath."""
+    import mpmath as mp
+    from fractions import Fraction as F
+    mp.mp.prec = 32 * L + 200
+    to_mp = lambda q: mp.mpf(q.numerator) / q.denominator
+    cases_ = [((F(-3, 2), F(1, 2**30)), (-20, -25)),    # im = 2^-30 +- 2^-26: straddles (log wants radius/|a| < 2^-8)
+              ((F(-5, 7), F(-1, 2**50)), (-60, -45)),   # re has a radius too
+              ((F(-1, 2**20), 0), (-200, -100))]        # im midpoint exactly zero, radius 2^-101
+    for (re, im), (rre, rim) in cases_:
+        x = from_complex([(re, im)], L)
+        x.meta[0, 2], x.meta[0, 3] = 1 << 29, rre
+        x.meta[1, 2], x.meta[1, 3] = 1 << 29, rim
+        z = oracle.ew_trans("log", x)
+        assert not (int(z.meta[0, 1]) | int(z.meta[1, 1])) & FLAG_NAN
+        for fr in (-1, F(-1, 3), 0, F(1, 2), 1):
+            for fi in (-1, F(-9, 10), F(1, 10**9), F(9, 10), 1):
+                pr = x.mid(0) + fr * x.rad(0)
+                pi_ = x.mid(1) + fi * x.rad(1)
+                tv = mp.log(mp.mpc(to_mp(pr), to_mp(pi_)))
+                assert abs(to_mp(z.mid(0)) - tv.real) <= to_mp(z.rad(0)), (re, im, fr, fi)
+                assert abs(to_mp(z.mid(1)) - tv.imag) <= to_mp(z.rad(1)), (re, im, fr, fi)
+        # the real part stays sharp: only the argument is lost
+        assert z.rad(0) < F(1, 2**20)
+    # a ball next to the cut that does not cross it keeps a tight argument
+    x = from_complex([(F(-3, 2), F(1, 2**30))], L)
+    x.meta[1, 2], x.meta[1, 3] = 1 << 29, -40
+    z = oracle.ew_trans("log", x)
+    assert z.rad(1) < F(1, 2**8) and z.mid(1) > 3
+
+
 def test_solution_evaluate_encloses_mpmath(oracle):
     """acb_ode_solution_evaluate (reference src/acb_ode_solution.c:24-58; property of reference
     tests/solution_eval.c): a^rho * sum_i w_i gens[i](a) log(a)^(M-1-i) with the weights the reference codes,

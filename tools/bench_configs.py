@@ -16,7 +16,9 @@ from cascade_b200.format import instance_major_to_entry_major, pack_entries, ran
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=float, default=1.0)
-ap.add_argument("--only", type=int, default=0, help="run only this config (3, 4 or 5)")
+ap.add_argument("--only", type=int, default=0, help="run only this config (2 = per-instance-operator sweep, 3, 4 or 5)")
+ap.add_argument("--lean", action="store_true", help="only the main kernel of each config (for ncu)")
+ap.add_argument("--terms", type=int, default=0, help="override the number of terms (short runs for ncu)")
 ap.add_argument("--continuation", action="store_true", help="also time the (slow, sequential) continuation leg")
 ap.add_argument("--continuation-batch", type=int, default=2, help="initial vectors continued along the path (2 = one fundamental system)")
 args = ap.parse_args()
@@ -62,7 +64,7 @@ class _Out(list):
 out = _Out()
 def config3():
     # ---- config 3: Frobenius, hypergeometric sweep, 4096 bits, per-instance (a, b, c)
-    L, n = 128, 256
+    L, n = 128, (args.terms or 256)
     batch = max(64, int(16384 * args.scale))
     rng = np.random.default_rng(3)
     small = 64
@@ -95,7 +97,7 @@ def config3():
 
 def config4():
     # ---- config 4: Legendre sweep, per-instance integer operators, real data (integer-operator kernel)
-    L, n = 32, 1000
+    L, n = 32, (args.terms or 1000)
     # the full 2^20 x 1000 sweep is 302 GB of complex results: more than one B200 holds; cap at 2^17 instances per launch
     batch = max(1024, min(2**17, int(2**20 * args.scale)))
     ns = np.arange(batch, dtype=np.int64)
@@ -121,7 +123,7 @@ def config4():
 
 def config5():
     # ---- config 5: Horner at many points, 2048 bits, one 3504-term series
-    L, length = 64, 3504
+    L, length = 64, (args.terms or 3504)
     npts = max(1024, int(10**6 * args.scale))
     f_m, f_t = rand_dev(length, L, 2, 5)
     pts_m, pts_t = rand_dev(1, L, 2 * npts, 6)
@@ -134,6 +136,22 @@ def config5():
     steps = npts * (length - 1)
     out.append({"config": 5, "what": f"Horner evaluation of a {length}-term series at {npts} points, 2048 bits", "ms": ms,
                 "horner_steps_per_s": steps / ms * 1e3, "T_limb_MAC_per_s_4L2": steps * 4 * L * L / ms * 1e3 / 1e12})
+
+def config2_sweep():
+    # ---- configs[1] with an operator per instance (parameter sweep): per-instance table + recurrence
+    L, n = 32, (args.terms or 99)
+    batch = max(1024, int(66304 * args.scale))
+    om, ot = rand_dev(9, L, 2 * batch, 21)
+    rm, rt = rand_dev(n + 1, L, 2 * batch, 22)
+    wsb = lib.cb200_fuchs_workspace_bytes(L, 2, 2, -2, n, batch, 0)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: lib.cb200_fuchs_batch_dev(L, 2, 2, -2, n, batch, p(om), p(ot), 0, p(rm), p(rt), p(ws), wsb, None))
+    coeffs = batch * (n - 1)
+    out.append({"config": "2-sweep", "what": f"configs[1] with an operator per instance, 1024 bits, {batch} instances, {n} terms",
+                "ms": ms, "ball_coeffs_per_s": coeffs / ms * 1e3, "T_limb_MAC_per_s_24L2": coeffs * 24 * L * L / ms * 1e3 / 1e12})
+    del ws
+    torch.cuda.empty_cache()
+
 
 def config3_log():
     # ---- config 3, logarithmic variant: acb_ode_solve_frobenius with M = 2 (polynomial-in-rho recurrence), 1024 bits
@@ -203,10 +221,13 @@ def config5_eval():
                 "ms": ms, "points_per_s": npts / ms * 1e3})
 
 
+if args.only in (0, 2):
+    config2_sweep()
 if args.only in (0, 3):
     config3()
-    config3_log()
-if args.only in (0, 5):
+    if not args.lean:
+        config3_log()
+if args.only in (0, 5) and not args.lean:
     config5_eval()
     config5_extend()
 if args.only in (0, 4):
