@@ -414,8 +414,8 @@ class LegendreSweep(Workload):
     def finish(self):
         if self.world > 1:
             import torch.distributed as dist
-            dist.all_gather_into_tensor(self.g_m, self.d_last_m)
-            dist.all_gather_into_tensor(self.g_t, self.d_last_t)
+            dist.all_gather_into_tensor(self.g_m.view(-1), self.d_last_m.view(-1))
+            dist.all_gather_into_tensor(self.g_t.view(-1), self.d_last_t.view(-1))
 
     def roofline(self, kernel_ms, peaks, imad_peak):
         bytes_out = self.coeffs * 2 * (4 * L + 16)  # complex balls as stored (SURVEY counts the real half only: 144 B)

@@ -16,6 +16,7 @@
 #pragma once
 #include <stdint.h>
 #include <stddef.h>
+#include <type_traits>
 #include "cb_mul.cuh"
 
 #if defined(__CUDACC__)
@@ -565,6 +566,20 @@ CB_HD Meta finish_to(DST dst, const Rounded& rr, bool neg, Mag rad) {
     return t;
 }
 
+// destinations that live in registers (cb_intop.cuh RegDst) take their stores with a STATIC loop index
+template <class T, class = void> struct DstTraits { static constexpr bool REG_DST = false; };
+template <class T> struct DstTraits<T, std::enable_if_t<T::REG_DST>> { static constexpr bool REG_DST = true; };
+template <class DST, int QMIN, int COUNT, int I>
+struct StoreStatic {
+    template <class RX>
+    static CB_HD void run(const DST& dst, int c, int r, RX Rx) {
+        if constexpr (I < COUNT) {
+            dst.template st_static<I>(c, shr_pair(Rx(QMIN + I), Rx(QMIN + I + 1), r));
+            StoreStatic<DST, QMIN, COUNT, I + 1>::run(dst, c, r, Rx);
+        }
+    }
+};
+
 // ---------------------------------------------------------------- in-register fast path
 // The common case of an aligned add: both operands within 31 bits of each other (or one of them
 // zero) and at most about a limb of cancellation.  Everything is statically indexed, so the sum
@@ -676,11 +691,15 @@ CB_HD bool fast_add_round(DST dst, X1 x1, X2 x2, int s1, int s2, bool sub, bool 
         }
     }
     // dst[i - q] = bits [32 i + r, 32 i + r + 32) of R, for the L words with 0 <= i - q < L
+    if constexpr (DstTraits<DST>::REG_DST) {
+        StoreStatic<DST, QMIN, L + 3, 0>::run(dst, q - QMIN, r, Rx);  // register destination: static indices only
+    } else {
 #pragma unroll
-    for (int i = QMIN; i < QMIN + L + 3; i++) {
-        uint32_t v = shr_pair(Rx(i), Rx(i + 1), r);
-        int j = i - q;
-        if ((unsigned)j < (unsigned)L) dst.st(j, v);
+        for (int i = QMIN; i < QMIN + L + 3; i++) {
+            uint32_t v = shr_pair(Rx(i), Rx(i + 1), r);
+            int j = i - q;
+            if ((unsigned)j < (unsigned)L) dst.st(j, v);
+        }
     }
     int64_t e = E - 32 * (int64_t)N - 32 + bl;
     rr->overflow = (e > EXP_LIMIT || e < -EXP_LIMIT);

@@ -234,7 +234,8 @@ __global__ void __launch_bounds__(IntopCfg<L>::TPB, 1) fuchs_intop_kernel(FuchsI
         A2{sbase + 4u * (W0 + 2 * AW) * TPB};
     const int64_t idx = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (idx >= p.batch) return;
-    fuchs_intop_thread<L>(p, idx, S0, A0, A1, A2);
+    if constexpr (L <= 32) fuchs_intop_fast_thread<L>(p, idx, S0, A0, A1, A2);
+    else fuchs_intop_thread<L>(p, idx, S0, A0, A1, A2);
 }
 
 // persistent form of the integer-operator kernel (same work-unit scheme as fuchs_shared_persistent_kernel; the
@@ -269,7 +270,10 @@ __global__ void __launch_bounds__(IntopCfg<L>::TPB, 1) fuchs_intop_persistent_ke
         const int64_t inst = b * TPB + threadIdx.x;
         const int64_t lo = first + r * p.range_len;
         const int64_t hi = lo + p.range_len - 1 < p.n ? lo + p.range_len - 1 : p.n;
-        if (inst < p.batch) fuchs_intop_thread<L>(p, inst, S0, A0, A1, A2, lo, hi);
+        if (inst < p.batch) {
+            if constexpr (L <= 32) fuchs_intop_fast_thread<L>(p, inst, S0, A0, A1, A2, lo, hi);
+            else fuchs_intop_thread<L>(p, inst, S0, A0, A1, A2, lo, hi);
+        }
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) atomicExch(p.sched + 1 + b, (int)(r + 1));

@@ -608,6 +608,10 @@ CB_HD void fuchs_intop_thread(const FuchsIntParams& p, int64_t inst, SCR S0, SCR
     }
 }
 
+}  // namespace cb
+#include "cb_intop.cuh"
+namespace cb {
+
 // ================================================================ Frobenius (M = 1)
 struct FrobParams {
     int order, degree, valuation;

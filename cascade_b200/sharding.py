@@ -108,3 +108,76 @@ def evaluate_sharded(gens: Balls, M: int, rho: Balls, pts: Balls, driver=None, g
     if not gather:
         return local
     return gather_instances(local, npts, 1, group=group)
+
+
+# ---------------------------------------------------------------- device-resident N-GPU path (NCCL over NVLink)
+def gather_device(m_local, t_local, batch: int, group=None):
+    """All-gather of per-rank DEVICE arrays in the device layout -- ``m_local``: int32 ``[entries][L][2*n_local]``,
+    ``t_local``: int32 ``[entries][2*n_local][4]`` -- into ``[entries][L][2*batch]`` / ``[entries][2*batch][4]`` on every
+    rank, without touching the host (uneven shards are padded to the largest and trimmed on the device).  NCCL on the
+    GPU box; any torch.distributed backend that supports all_gather_into_tensor on these tensors works."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    E, L, _ = m_local.shape
+    spans = [partition(batch, world, r) for r in range(world)]
+    nmax = max(hi - lo for lo, hi in spans)
+    pm = torch.zeros((E, L, 2 * nmax), dtype=m_local.dtype, device=m_local.device)
+    pt = torch.zeros((E, 2 * nmax, 4), dtype=t_local.dtype, device=t_local.device)
+    pm[:, :, : m_local.shape[2]] = m_local
+    pt[:, : t_local.shape[1]] = t_local
+    gm = torch.empty((world,) + tuple(pm.shape), dtype=pm.dtype, device=pm.device)
+    gt = torch.empty((world,) + tuple(pt.shape), dtype=pt.dtype, device=pt.device)
+    # flat views: every backend accepts (world * numel) <- (numel)
+    dist.all_gather_into_tensor(gm.view(-1), pm.view(-1), group=group)
+    dist.all_gather_into_tensor(gt.view(-1), pt.view(-1), group=group)
+    m = torch.cat([gm[r, :, :, : 2 * (hi - lo)] for r, (lo, hi) in enumerate(spans)], dim=2)
+    t = torch.cat([gt[r, :, : 2 * (hi - lo)] for r, (lo, hi) in enumerate(spans)], dim=1)
+    return m.contiguous(), t.contiguous()
+
+
+def solve_fuchs_sharded_device(ode: Balls, init: Balls, order: int, degree: int, n: int, batch: int,
+                               shared_ode: bool = True, group=None, device=None, gather_rows=None):
+    """The N-GPU path as it runs on the box: every rank uploads ITS block of the batch, solves it with the
+    device-resident entry point (``cb200_fuchs_batch_dev`` on torch-owned device memory) and the results are
+    all-gathered on the device (NCCL).  ``gather_rows``: None = every coefficient, or a list of coefficient indices
+    (BASELINE configs[3] gathers a reduction: the last coefficient).  Returns device tensors
+    (mant ``[rows][L][2*batch]``, meta ``[rows][2*batch][4]``) in the device layout."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib, api
+    from .format import instance_major_to_entry_major, pack_entries
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    lo, hi = partition(batch, world, rank)
+    nl = hi - lo
+    v = api.batch_valuation(ode, order, degree, shared_ode, "solve_fuchs_sharded_device")
+    if v >= 0:
+        _lib.check(_lib.EVALUATION, "solve_fuchs_sharded_device")
+    ne, L = (order + 1) * (degree + 1), ode.L
+    my_ode = ode if shared_ode else shard_instances(ode, batch, ne, lo, hi)
+    my_init = shard_instances(init, batch, -v, lo, hi)
+    ode_m, ode_t = api._ode_to_device(my_ode, order, degree, nl, shared_ode)
+    init_m, init_t = pack_entries(instance_major_to_entry_major(my_init, nl, -v), -v, 2 * nl)
+    lib = _lib.lib()
+    d = lambda a: torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).to(dev)
+    d_ode_m, d_ode_t = d(ode_m), d(ode_t)
+    res_m = torch.zeros((n + 1, L, 2 * nl), dtype=torch.int32, device=dev)
+    res_t = torch.zeros((n + 1, 2 * nl, 4), dtype=torch.int32, device=dev)
+    res_m[: -v] = d(init_m)
+    res_t[: -v] = d(init_t)
+    wsb = lib.cb200_fuchs_workspace_bytes(L, order, degree, v, n, nl, int(shared_ode))
+    ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    if nl > 0:
+        _lib.check(lib.cb200_fuchs_batch_dev(L, order, degree, v, n, nl, p(d_ode_m), p(d_ode_t), int(shared_ode), p(res_m),
+                                             p(res_t), p(ws), wsb, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                   "solve_fuchs_sharded_device")
+    if gather_rows is not None:
+        idx = torch.tensor(list(gather_rows), device=dev)
+        res_m, res_t = res_m.index_select(0, idx), res_t.index_select(0, idx)
+    return gather_device(res_m, res_t, batch, group=group)

@@ -19,7 +19,7 @@ _lib = None
 
 def build(force: bool = False) -> None:
     deps = [_SRC] + [os.path.join(_HERE, "..", "..", "cascade_b200", "csrc", f)
-                     for f in ("cb_arith.cuh", "cb_solvers.cuh", "cb_mul.cuh", "cb_rr.cuh", "cb_trans.cuh")]
+                     for f in ("cb_arith.cuh", "cb_solvers.cuh", "cb_mul.cuh", "cb_rr.cuh", "cb_trans.cuh", "cb_intop.cuh")]
     if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
         return
     subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-ffp-contract=off",

@@ -142,7 +142,13 @@ int cbsim_fuchs_intop_batch(int L_, int order, int degree, int valuation, int64_
     std::vector<uint32_t> col[4];
     for (int c = 0; c < 4; c++) col[c].assign(sizes[c] + CAN, 0xDEADBEEFu);
     Scratch<1> S0{col[0].data()}, A0{col[1].data()}, A1{col[2].data()}, A2{col[3].data()};
-    SIM_DISPATCH(L_, for (int64_t i = 0; i < batch; i++) fuchs_intop_thread<L>(p, i, S0, A0, A1, A2));
+    // the register fast path with the shared-memory body as per-coefficient fallback (what the kernels run at <= 1024
+    // bits); CBSIM_INTOP_GENERAL=1 runs the general body alone
+    const bool general_only = getenv("CBSIM_INTOP_GENERAL") != nullptr;
+    SIM_DISPATCH(L_, for (int64_t i = 0; i < batch; i++) {
+        if (L <= 32 && !general_only) { if constexpr (L <= 32) fuchs_intop_fast_thread<L>(p, i, S0, A0, A1, A2); }
+        else fuchs_intop_thread<L>(p, i, S0, A0, A1, A2);
+    });
     for (int c = 0; c < 4; c++)
         for (size_t k = sizes[c]; k < sizes[c] + CAN; k++)
             if (col[c][k] != 0xDEADBEEFu) return -1000 - c;

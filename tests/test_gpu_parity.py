@@ -16,9 +16,9 @@ def test_readme_kat(oracle, gpu_driver):
     cases.case_readme_kat(oracle, gpu_driver)
 
 
-@pytest.mark.parametrize("L", [4, 32, 64])
+@pytest.mark.parametrize("L", [4, 32, 64, 128])
 def test_fuchs_random(oracle, gpu_driver, L):
-    cases.case_fuchs_random(oracle, gpu_driver, L, seed=17 + L, trials=5, batch=37)
+    cases.case_fuchs_random(oracle, gpu_driver, L, seed=17 + L, trials=5 if L < 128 else 2, batch=37)
 
 
 @pytest.mark.parametrize("L", [4, 32, 64, 128])
@@ -26,7 +26,7 @@ def test_fuchs_random_shared(oracle, gpu_driver, L):
     cases.case_fuchs_random_shared(oracle, gpu_driver, L, seed=41 + L, trials=6 if L < 128 else 3, batch=45)
 
 
-@pytest.mark.parametrize("L", [4, 32, 64])
+@pytest.mark.parametrize("L", [4, 32, 64, 128])
 def test_fuchs_shared_adversarial(oracle, gpu_driver, L):
     cases.case_fuchs_shared_adversarial(oracle, gpu_driver, L, seed=87 + L, batch=70)
 
@@ -36,9 +36,9 @@ def test_fuchs_integer_operators(oracle, gpu_driver, L):
     cases.case_fuchs_integer_operators(oracle, gpu_driver, L, seed=15 + L)
 
 
-@pytest.mark.parametrize("L", [32, 64])
+@pytest.mark.parametrize("L", [32, 64, 128])
 def test_fuchs_bessel_shared(oracle, gpu_driver, L):
-    cases.case_fuchs_bessel_shared(oracle, gpu_driver, L, seed=5, n=60, batch=300)
+    cases.case_fuchs_bessel_shared(oracle, gpu_driver, L, seed=5, n=60 if L < 128 else 30, batch=300)
 
 
 def test_fuchs_hypgeom(oracle, gpu_driver):
@@ -81,9 +81,9 @@ def test_hybrid_scratch_columns(monkeypatch, oracle, gpu_driver, L, hybrid):
     cases.case_frobenius(oracle, gpu_driver, L, seed=29, n=14, batch=300)
 
 
-@pytest.mark.parametrize("L", [32, 64])
+@pytest.mark.parametrize("L", [32, 64, 128])
 def test_continuation(oracle, gpu_driver, L):
-    cases.case_continuation(oracle, gpu_driver, L, seed=23 + L, steps=6, n=40, batch=5)
+    cases.case_continuation(oracle, gpu_driver, L, seed=23 + L, steps=6 if L < 128 else 3, n=40 if L < 128 else 24, batch=5)
 
 
 @pytest.mark.parametrize("L", [4, 32, 64])
@@ -106,9 +106,9 @@ def test_exponent_overflow(oracle, gpu_driver, L):
     cases.case_exponent_overflow(oracle, gpu_driver, L)
 
 
-@pytest.mark.parametrize("L", [4, 32, 64])
+@pytest.mark.parametrize("L", [4, 32, 64, 128])
 def test_frobenius_general(oracle, gpu_driver, L):
-    cases.case_frobenius_general(oracle, gpu_driver, L, seed=41 + L, trials=4 if L < 64 else 2)
+    cases.case_frobenius_general(oracle, gpu_driver, L, seed=41 + L, trials=4 if L < 64 else (2 if L < 128 else 1))
 
 
 @pytest.mark.parametrize("L", [4, 32, 128])
@@ -116,7 +116,7 @@ def test_frobenius_general_sweep(oracle, gpu_driver, L):
     cases.case_frobenius_general_sweep(oracle, gpu_driver, L, seed=43 + L, n=10 if L < 128 else 5, batch=40)
 
 
-@pytest.mark.parametrize("L", [4, 32, 64])
+@pytest.mark.parametrize("L", [4, 32, 64, 128])
 def test_solution_ops(oracle, gpu_driver, L):
     cases.case_solution_ops(oracle, gpu_driver, L, seed=47 + L, batch=35)
 
@@ -144,12 +144,12 @@ def test_exp_log(oracle, gpu_driver, L):
     cases.case_exp_log(oracle, gpu_driver, L, seed=61 + L, n=40 if L < 128 else 24)
 
 
-@pytest.mark.parametrize("L", [4, 32, 64])
+@pytest.mark.parametrize("L", [4, 32, 64, 128])
 def test_solution_evaluate(oracle, gpu_driver, L):
-    cases.case_solution_evaluate(oracle, gpu_driver, L, seed=67 + L, npts=40, cap=16)
+    cases.case_solution_evaluate(oracle, gpu_driver, L, seed=67 + L, npts=40 if L < 128 else 12, cap=16 if L < 128 else 10)
 
 
-@pytest.mark.parametrize("L", [4, 32, 64])
+@pytest.mark.parametrize("L", [4, 32, 64, 128])
 def test_ode_apply(oracle, gpu_driver, L):
     cases.case_ode_apply(oracle, gpu_driver, L, seed=71 + L, batch=40)
 

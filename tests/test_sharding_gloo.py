@@ -31,6 +31,15 @@ def _worker(rank, world, port, out):
     ode = bessel_shifted(cbo, rng, L)
     init = random_balls(rng, batch * 4, L, -1, 0, "zero")
     full = sharding.solve_fuchs_sharded(ode, init, 2, 2, n, batch, True, driver=SimDriver())
+    # the device-layout gather (what the NCCL path uses on the box), here on CPU tensors over gloo
+    import torch
+    from cascade_b200.format import entry_major_to_instance_major, instance_major_to_entry_major, pack_entries, unpack_entries
+    lo, hi = sharding.partition(batch, world, rank)
+    mine = sharding.shard_instances(full, batch, n + 1, lo, hi)
+    lm, lt = pack_entries(instance_major_to_entry_major(mine, hi - lo, n + 1), n + 1, 2 * (hi - lo))
+    gm, gt = sharding.gather_device(torch.from_numpy(lm.view(np.int32)), torch.from_numpy(lt), batch)
+    regathered = entry_major_to_instance_major(unpack_entries(L, gm.numpy().view(np.uint32), gt.numpy()), batch, n + 1)
+    assert regathered.same_as(full), "device-layout gather differs from the instance-major gather"
     # parameter sweep of the (logarithmic) Frobenius solver and a point sweep of the evaluation
     from cascade_b200.format import Balls
     par = random_balls(rng, batch * 6, L, -1, 1, "zero")
