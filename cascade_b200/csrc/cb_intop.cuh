@@ -10,8 +10,7 @@
 //   acc = round(acc - p)    fast_add_round on register operands (operands within 31 bits, < 1 limb cancelled)
 //   c   = round(acc / d)    quotient digits by Moeller-Granlund 3-by-2 steps in registers; the quotient of two
 //                           normalised operands needs a shift of 0 or 1 bit
-// re and im words of a limb are adjacent in memory (slot = 2 * instance + part), so limbs are loaded and stored as
-// 64-bit pairs.  Radii follow arb_mul_si / arb_addsub / arb_div_u64 step by step; results are BIT-IDENTICAL to
+// Radii follow arb_mul_si / arb_addsub / arb_div_u64 step by step; results are BIT-IDENTICAL to
 // fuchs_intop_thread.  Whatever the fast path does not cover -- indeterminate or zero-midpoint balls with a radius,
 // exponent gaps beyond 31 bits, cancellation of a limb or more, exponent overflow -- makes it return false before
 // anything is stored, and the caller runs that one coefficient through fuchs_intop_thread.
@@ -132,41 +131,108 @@ CB_HD bool reg_sub(uint32_t (&acc)[L], Meta& ta, const uint32_t (&p)[L], const M
     return true;
 }
 
+// what arb_div_u64 derives from the divisor alone: formed once per coefficient and shared by both parts
+struct DivSetup {
+    uint64_t D;      // d << sh, top bit set
+    uint32_t d1;     // its top limb
+    uint32_t recip;  // 2-by-1 reciprocal of d1 (D's low limb zero) or 3-by-2 reciprocal of D
+    Meta yt;         // exponent and sign of the divisor as a ball
+    Mag yl, num_y;   // lower bound of |d| and upper bound of |d| (30-bit magnitudes)
+    bool one_limb;
+};
+CB_HD DivSetup div_setup(uint64_t d, bool dneg) {
+    DivSetup s;
+    const int sh = clz64(d);
+    s.D = d << sh;
+    s.d1 = (uint32_t)(s.D >> 32);
+    s.yt = Meta{64 - sh, dneg ? F_SIGN : 0u, 0u, 0};
+    s.yl = mag_mid_lower(s.yt, s.d1);
+    s.num_y = mag_mid_upper(s.yt, s.d1);
+    s.one_limb = (uint32_t)s.D == 0u;
+    // one-limb divisor (d < 2^32, e.g. the b(b-1) of a Legendre sweep): floor(x * 2^64 / D) = floor(x * 2^32 / d1),
+    // digit for digit the same quotient, by Moeller-Granlund 2-by-1 steps (half the work of a 3-by-2 step)
+    s.recip = s.one_limb ? (uint32_t)(0xFFFFFFFFFFFFFFFFull / s.d1 - 0x100000000ull) : recip_3by2(s.d1, (uint32_t)s.D);
+    return s;
+}
+
 // out = round(x / d), x finite with a nonzero midpoint, d != 0 (arb_div_u64 restated for registers)
 template <int L>
-CB_HD bool reg_div_u64(uint32_t (&out)[L], Meta& to, const uint32_t (&x)[L], const Meta& tx, uint64_t d, bool dneg) {
-    const int sh = clz64(d);
-    const uint64_t D = d << sh;
-    const uint32_t d1 = (uint32_t)(D >> 32);
-    Meta yt{64 - sh, dneg ? F_SIGN : 0u, 0u, 0};
-    const Mag yl = mag_mid_lower(yt, d1);
+CB_HD bool reg_div_u64(uint32_t (&out)[L], Meta& to, const uint32_t (&x)[L], const Meta& tx, const DivSetup& ds) {
     Mag rad = mag_zero();
-    if (tx.rman != 0) rad = mag_div(mag_mul(mag_mid_upper(yt, d1), mag_of(tx)), mag_mul_lower(yl, yl));
-    const uint32_t v = recip_3by2(d1, (uint32_t)D);
-    uint64_t rem = 0;
-    (void)div_3by2(rem, x[L - 1], D, v);
+    if (tx.rman != 0) rad = mag_div(mag_mul(ds.num_y, mag_of(tx)), mag_mul_lower(ds.yl, ds.yl));
     uint32_t q[L + 1];
+    bool rem_nz;
+    if (ds.one_limb) {
+        const uint32_t dinv = ds.recip, d1 = ds.d1;
+        uint32_t r = 0u;
 #pragma unroll
-    for (int j = L; j >= 0; j--) q[j] = div_3by2(rem, (j >= 2) ? x[j - 2] : 0u, D, v);
+        for (int j = L; j >= 0; j--) {
+            const uint32_t u = (j >= 1) ? x[j - 1] : 0u;
+            const uint64_t qq = (uint64_t)dinv * r + (((uint64_t)r << 32) | u);
+            uint32_t q1 = (uint32_t)(qq >> 32) + 1u;
+            const uint32_t q0 = (uint32_t)qq;
+            uint32_t rr2 = u - q1 * d1;
+            if (rr2 > q0) {
+                q1--;
+                rr2 += d1;
+            }
+            if (rr2 >= d1) {
+                q1++;
+                rr2 -= d1;
+            }
+            q[j] = q1;
+            r = rr2;
+        }
+        rem_nz = r != 0u;
+    } else {
+        uint64_t rem = 0;
+        (void)div_3by2(rem, x[L - 1], ds.D, ds.recip);
+#pragma unroll
+        for (int j = L; j >= 0; j--) q[j] = div_3by2(rem, (j >= 2) ? x[j - 2] : 0u, ds.D, ds.recip);
+        rem_nz = rem != 0;
+    }
     // x in [2^(32L-1), 2^(32L)), D in [2^63, 2^64): the quotient has 32L or 32L+1 bits
     const bool one = q[L] != 0u;
-    uint32_t low = (rem != 0) ? 1u : 0u;
+    uint32_t low = rem_nz ? 1u : 0u;
     if (one) low |= q[0] & 1u;
 #pragma unroll
     for (int j = 0; j < L; j++) out[j] = one ? shr_pair(q[j], q[j + 1], 1) : q[j];
-    const int64_t e = (int64_t)tx.exp - yt.exp + (one ? 1 : 0);
+    const int64_t e = (int64_t)tx.exp - ds.yt.exp + (one ? 1 : 0);
     if (e > EXP_LIMIT || e < -EXP_LIMIT) return false;
     Rounded rr;
     rr.exp = (int32_t)e;
     rr.zero = false;
     rr.inexact = low != 0u;
     rr.overflow = false;
-    to = finish<L>(rr, ((tx.flags & F_SIGN) != 0) != dneg, rad);
+    to = finish<L>(rr, ((tx.flags ^ ds.yt.flags) & F_SIGN) != 0, rad);
     return true;
 }
 
-// One coefficient of one instance in registers.  Returns false -- with NOTHING stored -- when a step is outside the
-// fast path; the caller then forms this coefficient with fuchs_intop_thread.
+// multipliers of one coefficient for order = degree = 2 when e - bmin = degree (e >= 2): cur[k], k = 0 .. cnt, with
+//   imin = max(k - 2, 0), imax = min(k, 2), column index i + 2 - k -- all compile-time constants (src/fuchs_solver.c:121-135)
+CB_HD void intop_multipliers_22(int64_t* cur, const int64_t* P, int64_t bmin, int cnt) {
+    const int64_t p02 = P[2], p01 = P[1], p00 = P[0], p12 = P[5], p11 = P[4], p10 = P[3], p22 = P[8], p21 = P[7], p20 = P[6];
+    cur[0] = p02;
+    if (cnt >= 1) {  // k = 1: i in [0, 1], columns 1, 2
+        const int64_t b = bmin + 1;
+        cur[1] = p01 + p12 * b;
+    }
+    if (cnt >= 2) {  // k = 2: i in [0, 2], columns 0, 1, 2
+        const int64_t b = bmin + 2;
+        cur[2] = p00 + p11 * b + p22 * (b * (b - 1));
+    }
+    if (cnt >= 3) {  // k = 3: imin = 1: i in [1, 2], columns 0, 1; common factor b
+        const int64_t b = bmin + 3;
+        cur[3] = (p10 + p21 * (b - 1)) * b;
+    }
+    if (cnt >= 4) {  // k = 4: imin = 2: i = 2, column 0; common factor (b - 1) b
+        const int64_t b = bmin + 4;
+        cur[4] = p20 * ((b - 1) * b);
+    }
+}
+
+// One coefficient of one instance in registers.  Returns false when a step is outside the fast path; the caller then
+// forms this coefficient (both parts) with fuchs_intop_thread.
 constexpr int INTOP_MAXWIN = 12;  // multipliers per coefficient: degree - valuation + 1 <= 12 on the fast path
 template <int L>
 CB_HD bool fuchs_intop_fast_coeff(const FuchsIntParams& p, int64_t inst, const int64_t* P, int64_t bmax) {
@@ -180,44 +246,71 @@ CB_HD bool fuchs_intop_fast_coeff(const FuchsIntParams& p, int64_t inst, const i
     // the multipliers of res[bmin .. bmax-1] and the divisor, exactly as the reference forms temp2 (all integers;
     // reference src/fuchs_solver.c:114,121-135)
     int64_t cur[INTOP_MAXWIN];
-    cur[0] = P[0 * D1 + (e - bmin)];
-    for (int k = 1; k <= cnt; k++) {
-        const int64_t b = bmin + k;
-        int64_t t2 = 0, fac = 1;
-        const int64_t imin = clampi(b - e, 0, -v);
-        const int64_t imax = clampi(b - bmin, 0, p.order);
-        for (int64_t i = imin; i <= imax; i++) {
-            t2 += P[i * D1 + (i + e - b)] * fac;
-            fac *= (b - i);
+    if (p.order == 2 && p.degree == 2 && e >= 2 && cnt <= 4) {
+        // the shipped example operators (reference src/examples.c) in the steady state (e - bmin = degree): every index
+        // below is a compile-time constant, so the nine operator words are loaded up front and the multipliers are a
+        // few integer multiply-adds (same integers as the general loop in the else branch)
+        intop_multipliers_22(cur, P, bmin, cnt);
+    } else {
+        cur[0] = P[0 * D1 + (e - bmin)];
+        for (int k = 1; k <= cnt; k++) {
+            const int64_t b = bmin + k;
+            int64_t t2 = 0, fac = 1;
+            const int64_t imin = clampi(b - e, 0, -v);
+            const int64_t imax = clampi(b - bmin, 0, p.order);
+            for (int64_t i = imin; i <= imax; i++) {
+                t2 += P[i * D1 + (i + e - b)] * fac;
+                fac *= (b - i);
+            }
+            fac = 1;
+            for (int64_t q = 0; q < imin; q++) fac *= (b - imin + 1 + q);
+            cur[k] = t2 * fac;
         }
-        fac = 1;
-        for (int64_t q = 0; q < imin; q++) fac *= (b - imin + 1 + q);
-        cur[k] = t2 * fac;
     }
     const int64_t dv = cur[cnt];
     if (dv == 0) return false;  // division by zero: indeterminate, the general path writes it
-    const uint64_t dmag = dv < 0 ? (uint64_t)0 - (uint64_t)dv : (uint64_t)dv;
-    uint32_t o[2][L];  // only o[part] of the part in flight is live at a time, see the stores below
-    Meta to[2];
-    bool okay = true;
+    uint32_t mask = 0u;         // terms with a nonzero multiplier (x * 0 is an exact zero and acc - 0 leaves acc untouched)
+    for (int k = 0; k < cnt; k++) mask |= (cur[k] != 0) ? (1u << k) : 0u;
+    // the loads of the first term (both meta records and the limbs of its real part) are issued BEFORE the divisor
+    // is prepared (a 64-bit division), so that their latency is covered
+    const int k0 = mask ? (int)(31 - clz32(mask & (0u - mask))) : 0;
+    Meta t0re, t0im;
+    uint32_t x[L];
+    {
+        const size_t b0 = (size_t)(bmin + k0);
+        t0re = ld_meta_user(p.res.t + b0 * S + slot);
+        t0im = ld_meta_user(p.res.t + b0 * S + slot + 1);
+        const uint32_t* q = p.res.m + b0 * L * S + slot;
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+            x[j] = *q;
+            q += S;
+#if defined(__CUDA_ARCH__)
+            asm volatile("" : "+l"(q));
+#endif
+        }
+    }
+    const DivSetup ds = div_setup(dv < 0 ? (uint64_t)0 - (uint64_t)dv : (uint64_t)dv, dv < 0);
+    // a real sweep (Legendre with real initial values): one term whose imaginary part is an exact zero -- the
+    // imaginary part of the coefficient is an exact zero too and goes out with the real part, a 64-bit (re, im) pair
+    // per limb (re and im words of a limb are adjacent: slot = 2 * instance + part)
+    const bool im_zero = (mask & (mask - 1u)) == 0u && is_exact_zero(t0im);
 #pragma unroll 1
-    for (int part = 0; part < 2 && okay; part++) {
+    for (int part = 0; part < (im_zero ? 1 : 2); part++) {
         uint32_t acc[L];
         Meta tacc = meta_zero();
         bool have = false;
+        uint32_t todo = mask;
 #pragma unroll 1
-        for (int k = 0; k < cnt && okay; k++) {
+        while (todo) {
+            const int k = (int)(31 - clz32(todo & (0u - todo)));
+            todo &= todo - 1u;
             const int64_t c = cur[k];
-            if (c == 0) continue;  // x * 0 is an exact zero and acc - 0 leaves acc untouched
             const int64_t b = bmin + k;
-            const Meta tx = ld_meta_user(p.res.t + (size_t)b * S + slot + part);
+            const Meta tx = (k == k0) ? (part ? t0im : t0re) : ld_meta_user(p.res.t + (size_t)b * S + slot + part);
             if (is_exact_zero(tx)) continue;
-            if (is_nan(tx) || is_zero_mid(tx)) {
-                okay = false;
-                break;
-            }
-            uint32_t x[L], pr[L];
-            {
+            if (is_nan(tx) || is_zero_mid(tx)) return false;
+            if (!(k == k0 && part == 0)) {  // the first term of the real part is already in x
                 const uint32_t* q = p.res.m + (size_t)b * L * S + slot + part;
 #pragma unroll
                 for (int j = 0; j < L; j++) {
@@ -228,12 +321,10 @@ CB_HD bool fuchs_intop_fast_coeff(const FuchsIntParams& p, int64_t inst, const i
 #endif
                 }
             }
+            uint32_t pr[L];
             Meta tp;
             const uint64_t ka = c < 0 ? (uint64_t)0 - (uint64_t)c : (uint64_t)c;
-            if (!reg_mul_u64<L>(pr, tp, x, tx, ka, c < 0)) {
-                okay = false;
-                break;
-            }
+            if (!reg_mul_u64<L>(pr, tp, x, tx, ka, c < 0)) return false;
             if (!have) {  // 0 - p = -p exactly
 #pragma unroll
                 for (int j = 0; j < L; j++) acc[j] = pr[j];
@@ -241,37 +332,47 @@ CB_HD bool fuchs_intop_fast_coeff(const FuchsIntParams& p, int64_t inst, const i
                 tacc.flags ^= F_SIGN;
                 have = true;
             } else if (!reg_sub<L>(acc, tacc, pr, tp) || is_zero_mid(tacc)) {
-                okay = false;
-                break;
+                return false;
             }
         }
-        if (!okay) break;
+        // this part of the coefficient: c = acc / divisor.  (A part stored here stays valid if the other part falls
+        // back: the general path recomputes both from earlier coefficients only and writes the same words.)
+        uint32_t o[L];
+        Meta to;
         if (!have) {
 #pragma unroll
-            for (int j = 0; j < L; j++) o[part][j] = 0u;
-            to[part] = meta_zero();
-        } else if (!reg_div_u64<L>(o[part], to[part], acc, tacc, dmag, dv < 0)) {
-            okay = false;
+            for (int j = 0; j < L; j++) o[j] = 0u;
+            to = meta_zero();
+        } else if (!reg_div_u64<L>(o, to, acc, tacc, ds)) {
+            return false;
+        }
+        uint32_t* om = p.res.m + (size_t)bmax * L * S + slot + part;
+        if (im_zero) {
+#pragma unroll
+            for (int j = 0; j < L; j++) {
+#if defined(__CUDA_ARCH__)
+                *reinterpret_cast<uint2*>(om) = make_uint2(o[j], 0u);
+                asm volatile("" : "+l"(om));
+#else
+                om[0] = o[j];
+                om[1] = 0u;
+#endif
+                om += S;
+            }
+            st_meta(p.res.t + (size_t)bmax * S + slot, to);
+            st_meta(p.res.t + (size_t)bmax * S + slot + 1, meta_zero());
+        } else {
+#pragma unroll
+            for (int j = 0; j < L; j++) {
+                *om = o[j];
+                om += S;
+#if defined(__CUDA_ARCH__)
+                asm volatile("" : "+l"(om));
+#endif
+            }
+            st_meta(p.res.t + (size_t)bmax * S + slot + part, to);
         }
     }
-    if (!okay) return false;
-    // re and im words of a limb are adjacent (slot = 2 * instance + part): one 64-bit store per limb
-    uint32_t* om = p.res.m + (size_t)bmax * L * S + slot;
-#pragma unroll
-    for (int j = 0; j < L; j++) {
-#if defined(__CUDA_ARCH__)
-        *reinterpret_cast<uint2*>(om) = make_uint2(o[0][j], o[1][j]);
-        om += S;
-        asm volatile("" : "+l"(om));
-#else
-        om[0] = o[0][j];
-        om[1] = o[1][j];
-        om += S;
-#endif
-    }
-    Meta* ot = p.res.t + (size_t)bmax * S + slot;
-    st_meta(ot, to[0]);
-    st_meta(ot + 1, to[1]);
     return true;
 }
 
