@@ -128,11 +128,18 @@ size_t cb200_fuchs_workspace_bytes(int L, int order, int degree, int valuation, 
            align256(sizeof(int) * (size_t)(batch / 32 + 2));
 }
 static size_t hyb_tail_bytes(int L, int64_t count);
-size_t cb200_frobenius_workspace_bytes(int L, int64_t batch) { return carve_bytes(L, FROB_NTMP, 2 * batch) + hyb_tail_bytes(L, batch); }
-// global tails of the hybrid scratch columns (2048 bits and up; cb_kernels.cuh HybCfg)
-static size_t hyb_tail_bytes(int L, int64_t count) {
-    return L >= 64 ? align256((size_t)2 * (size_t)(L - 2) * (size_t)(count > 0 ? count : 0) * sizeof(uint32_t)) : 0;
+static size_t coop_sched_bytes(int64_t count) { return align256(sizeof(int) * (size_t)((count > 0 ? count : 0) / 64 + 2)); }
+size_t cb200_frobenius_workspace_bytes(int L, int64_t batch) {
+    return carve_bytes(L, FROB_NTMP, 2 * batch) + hyb_tail_bytes(L, batch) + coop_sched_bytes(batch);
 }
+// global tails of the hybrid scratch columns (2048 bits and up; cb_kernels.cuh HybCfg: two columns per instance) --
+// or of the cooperative kernels' columns (CoopCfg: four lanes per instance, the batch padded to whole CTAs)
+static size_t hyb_tail_words(int L, int64_t count) {
+    if (L < 64) return 0;
+    size_t a = (size_t)2 * (size_t)(L - 2) * (size_t)(count > 0 ? count : 0), b = coop_tail_words(L, count);
+    return a > b ? a : b;
+}
+static size_t hyb_tail_bytes(int L, int64_t count) { return align256(hyb_tail_words(L, count) * sizeof(uint32_t)); }
 size_t cb200_horner_workspace_bytes(int L, int64_t npts) { return carve_bytes(L, 1, 2 * npts) + hyb_tail_bytes(L, npts); }
 size_t cb200_ew_workspace_bytes(int L, int64_t n) { return carve_bytes(L, 2, 2 * n); }
 
@@ -342,6 +349,9 @@ int cb200_frobenius1_rhs_batch_dev(int L_, int order, int degree, int valuation,
     char* w = (char*)workspace;
     p.tmp = carve(w, L_, FROB_NTMP, 2 * batch);
     p.gcols = (uint32_t*)w;
+    p.gcols_words = hyb_tail_words(L_, batch);
+    w += hyb_tail_bytes(L_, batch);
+    p.sched = (int*)w;
     g_launches.fetch_add(batch > 0);
     return table_for(L_)->frobenius1(p, (cudaStream_t)stream);
 }
@@ -522,6 +532,7 @@ int cb200_horner_batch_dev(int L_, int64_t len, int64_t npts, int nder, const ui
     char* w = (char*)workspace;
     p.tmp = carve(w, L_, 1, 2 * npts);
     p.gcols = (uint32_t*)w;
+    p.gcols_words = hyb_tail_words(L_, npts);
     g_launches.fetch_add(npts > 0);
     return table_for(L_)->horner(p, (cudaStream_t)stream);
 }
@@ -703,6 +714,7 @@ static int continuation_impl(int L_, int order, int degree, int64_t n, int64_t b
         char* hwp = (char*)hws;
         hp.tmp = carve(hwp, L_, 1, S);
         hp.gcols = (uint32_t*)hwp;
+        hp.gcols_words = hyb_tail_words(L_, batch);
         g_launches.fetch_add(batch > 0);
         rc = table_for(L_)->horner(hp, st);
         if (rc) return rc;

@@ -41,12 +41,29 @@ constexpr uint32_t F_SIGN = 1u, F_ZERO = 2u, F_NAN = 4u;
 // of trailing zero LIMBS of the mantissa (set by the table kernel on the shared multipliers).
 constexpr int F_TZ_SHIFT = 8;
 CB_HD int tz_hint(uint32_t flags) { return (int)((flags >> F_TZ_SHIFT) & 0xFFu); }
-// fill in the hint of an operand that has none: dense operands cost one load, short ones a scan
+// fill in the hint of an operand that has none: dense operands cost one load.  Short ones (integers: up to L - 1
+// zero limbs) are scanned sixteen limbs at a time with independent loads -- one limb after the other every load
+// waited for the one before it, a global-memory round trip per zero limb (the 4096-bit hypergeometric sweep with
+// rho = 0 spent most of its stall time there, profiles/ncu_frobenius1_128_r02_before_summary.txt).
 template <int L, class O>
 CB_HD void tz_scan(O& o) {
     if (tz_hint(o.t.flags) != 0 || (o.t.flags & (F_ZERO | F_NAN))) return;
-    int tz = 0;
-    while (tz < L - 1 && o.r.ld(tz) == 0u) tz++;
+    if (o.r.ld(0) != 0u) return;
+    int tz = L - 1;
+    constexpr int B = L < 16 ? L : 16;
+#pragma unroll 1
+    for (int base = 0; base < L; base += B) {
+        uint32_t w[B];
+#pragma unroll
+        for (int k = 0; k < B; k++) w[k] = (base + k < L) ? o.r.ld(base + k) : 1u;
+        int first = B;
+#pragma unroll
+        for (int k = B - 1; k >= 0; k--) first = w[k] ? k : first;
+        if (first < B) {
+            tz = base + first < L - 1 ? base + first : L - 1;
+            break;
+        }
+    }
     o.t.flags |= (uint32_t)tz << F_TZ_SHIFT;
 }
 constexpr int32_t EXP_LIMIT = 1 << 28;
@@ -1054,31 +1071,41 @@ CB_HD void product_trunc_blocked(SCR Ph, XS x, YS y) {
 // dst = x1*y1 +- x2*y2 above 1024 bits from truncated blocked products;
 // *ok = false when the guard bits cannot prove the result (the caller then runs the exact path).
 // S0, S1: shared columns of at least L + 4 words.
-template <int L, class SCR, class XS = RRef, class YS = RRef, class DST = WRef>
-CB_NOINLINE Meta arb_fdot2_trunc_blocked(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2, OpdT<YS> y2, bool neg2,
-                                         SCR S0, SCR S1, bool* ok) {
+// The work is split into what depends on the operand records only (FdotPrep), the two products (term 1 -> P1, term 2
+// -> P2: independent of each other -- the cooperative kernels of cb_coop.cuh form them on two lanes) and the tail
+// that aligns, adds and rounds them.
+struct FdotPrep {
+    bool nan, z1, z2, n1, n2;
+    int64_t e1, e2;
+    Mag rad;
+    int tz1, tz2;  // trailing zero limbs of the two products (hints; 0 when unknown)
+};
+template <int L, class XS, class YS>
+CB_HD FdotPrep fdot2_prep(const OpdT<XS>& x1, const OpdT<YS>& y1, const OpdT<XS>& x2, const OpdT<YS>& y2, bool neg2) {
+    FdotPrep f;
+    f.nan = is_nan(x1.t) || is_nan(y1.t) || is_nan(x2.t) || is_nan(y2.t);
+    f.z1 = is_zero_mid(x1.t) || is_zero_mid(y1.t) || f.nan;
+    f.z2 = is_zero_mid(x2.t) || is_zero_mid(y2.t) || f.nan;
+    f.rad = mul_rad(mag_zero(), x1.t, top_limb<L>(x1), y1.t, top_limb<L>(y1));
+    f.rad = mul_rad(f.rad, x2.t, top_limb<L>(x2), y2.t, top_limb<L>(y2));
+    f.n1 = ((x1.t.flags ^ y1.t.flags) & F_SIGN) != 0;
+    f.n2 = (((x2.t.flags ^ y2.t.flags) & F_SIGN) != 0) != neg2;
+    f.e1 = (int64_t)x1.t.exp + y1.t.exp;
+    f.e2 = (int64_t)x2.t.exp + y2.t.exp;
+    f.tz1 = tz_hint(x1.t.flags) + tz_hint(y1.t.flags);
+    f.tz2 = tz_hint(x2.t.flags) + tz_hint(y2.t.flags);
+    return f;
+}
+// P1 / P2: the truncated products of term 1 / term 2 (L + 4 words each, untouched for a zero term)
+template <int L, class SCR, class DST>
+CB_NOINLINE Meta fdot2_tb_tail(DST dst, const FdotPrep& f, SCR P1, SCR P2, bool* ok) {
     constexpr int K = L - 4, PW = L + 4;
-    bool nan = is_nan(x1.t) || is_nan(y1.t) || is_nan(x2.t) || is_nan(y2.t);
-    bool z1 = is_zero_mid(x1.t) || is_zero_mid(y1.t) || nan;
-    bool z2 = is_zero_mid(x2.t) || is_zero_mid(y2.t) || nan;
-    Mag rad = mul_rad(mag_zero(), x1.t, top_limb<L>(x1), y1.t, top_limb<L>(y1));
-    rad = mul_rad(rad, x2.t, top_limb<L>(x2), y2.t, top_limb<L>(y2));
-    bool n1 = ((x1.t.flags ^ y1.t.flags) & F_SIGN) != 0;
-    bool n2 = (((x2.t.flags ^ y2.t.flags) & F_SIGN) != 0) != neg2;
-    const int64_t e1 = (int64_t)x1.t.exp + y1.t.exp, e2 = (int64_t)x2.t.exp + y2.t.exp;
-    // term A (zero, else smaller exponent) goes to S0 and may be read with a word offset
-    const bool a_is_1 = z1 ? true : (z2 ? false : (e1 <= e2));
-    const bool zA = a_is_1 ? z1 : z2, zB = a_is_1 ? z2 : z1;
-    const bool nA = a_is_1 ? n1 : n2, nB = a_is_1 ? n2 : n1;
-    const int64_t eA = a_is_1 ? e1 : e2, eB = a_is_1 ? e2 : e1;
-    const XS xA = a_is_1 ? x1.r : x2.r, xB = a_is_1 ? x2.r : x1.r;
-    const YS yA = a_is_1 ? y1.r : y2.r, yB = a_is_1 ? y2.r : y1.r;
-    bool skipA = warp_all(zA), skipB = warp_all(zB);
-#pragma unroll 1
-    for (int term = 0; term < 2; term++) {
-        if (term ? skipB : skipA) continue;
-        product_trunc_blocked<L>(term ? S1 : S0, term ? xB : xA, term ? yB : yA);
-    }
+    // term A (zero, else smaller exponent) may be read with a word offset
+    const bool a_is_1 = f.z1 ? true : (f.z2 ? false : (f.e1 <= f.e2));
+    const bool zA = a_is_1 ? f.z1 : f.z2, zB = a_is_1 ? f.z2 : f.z1;
+    const bool nA = a_is_1 ? f.n1 : f.n2, nB = a_is_1 ? f.n2 : f.n1;
+    const int64_t eA = a_is_1 ? f.e1 : f.e2, eB = a_is_1 ? f.e2 : f.e1;
+    const SCR SA = a_is_1 ? P1 : P2, SB = a_is_1 ? P2 : P1;
     bool done = false, neg = false;
     Rounded rr;
     rr.exp = 0;
@@ -1094,22 +1121,33 @@ CB_NOINLINE Meta arb_fdot2_trunc_blocked(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT
         int m = d > 32 * (2 * L + 8) ? (2 * L + 8) : (int)(d >> 5);
         int sA = (int)(d & 31);
         bool sub = (nA != nB) && !zA;
-        auto wB = [&](int k) -> uint32_t { return zB ? 0u : S1.ld(k - K); };
+        auto wB = [&](int k) -> uint32_t { return zB ? 0u : SB.ld(k - K); };
         auto wA = [&](int k) -> uint32_t {
             int i = k + m - K;
-            return (zA || (unsigned)i >= (unsigned)PW) ? 0u : S0.ld(i);
+            return (zA || (unsigned)i >= (unsigned)PW) ? 0u : SA.ld(i);
         };
-        const int tzA = a_is_1 ? tz_hint(x1.t.flags) + tz_hint(y1.t.flags) : tz_hint(x2.t.flags) + tz_hint(y2.t.flags);
-        const int tzB = a_is_1 ? tz_hint(x2.t.flags) + tz_hint(y2.t.flags) : tz_hint(x1.t.flags) + tz_hint(y1.t.flags);
+        const int tzA = a_is_1 ? f.tz1 : f.tz2, tzB = a_is_1 ? f.tz2 : f.tz1;
         bool trusted = (zA || (tzA >= K && m == 0)) && tzB >= K;
         done = fast_add_round<L, 2 * L, K>(dst, wB, wA, 0, sA, sub, nB, nA, eB, &rr, &neg, trusted);
     }
     *ok = done;
-    if (nan) {
+    if (f.nan) {
         store_nan<L>(dst);
         return meta_nan();
     }
-    return finish_to<L>(dst, rr, neg, rad);
+    return finish_to<L>(dst, rr, neg, f.rad);
+}
+template <int L, class SCR, class XS = RRef, class YS = RRef, class DST = WRef>
+CB_NOINLINE Meta arb_fdot2_trunc_blocked(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT<XS> x2, OpdT<YS> y2, bool neg2,
+                                         SCR S0, SCR S1, bool* ok) {
+    const FdotPrep f = fdot2_prep<L>(x1, y1, x2, y2, neg2);
+    bool skip1 = warp_all(f.z1), skip2 = warp_all(f.z2);
+#pragma unroll 1
+    for (int term = 0; term < 2; term++) {
+        if (term ? skip2 : skip1) continue;
+        product_trunc_blocked<L>(term ? S1 : S0, term ? x2.r : x1.r, term ? y2.r : y1.r);
+    }
+    return fdot2_tb_tail<L>(dst, f, S0, S1, ok);
 }
 
 // dst = x + (negy ? -y : y)
@@ -1142,9 +1180,10 @@ CB_NOINLINE Meta arb_addsub_impl(WRef dst, Opd x, Opd y, bool negy, SCR S0, SCR 
         }
     }
     if (!done) {
-#pragma unroll 8
+        // (32 independent loads in flight per round: these operands come from global memory)
+#pragma unroll 32
         for (int j = 0; j < L; j++) S0.st(j, x.r.ld(j));
-#pragma unroll 8
+#pragma unroll 32
         for (int j = 0; j < L; j++) S1.st(j, y.r.ld(j));
         rr = align_add<L, L>(dst, S0, S1, x.t.exp, y.t.exp, nx, ny, zx, zy, &neg);
     }
@@ -1230,6 +1269,43 @@ CB_NOINLINE Meta arb_mul_si_impl(WRef dst, Opd x, int64_t k, SCR S0) {
     return finish_to<L>(dst, rr, neg, rad);
 }
 
+// One multiply-subtract row of the long division below: u[0 .. B) -= qd * d[0 .. B) with the running multiply carry
+// `mc` and the running borrow, on register blocks (the B products are independent IMAD.WIDE; two short carry chains
+// fold them into the window).  On entry / exit: mc = carry of the products so far, borrow in {0, 1}.
+template <int B>
+CB_HD void div_row_block(uint32_t (&u)[B], const uint32_t (&d)[B], uint32_t qd, uint32_t& mc, uint32_t& borrow) {
+#if defined(__CUDA_ARCH__)
+    uint32_t lo[B], hi[B];
+#pragma unroll
+    for (int k = 0; k < B; k++) {
+        uint64_t p = (uint64_t)qd * d[k];
+        lo[k] = (uint32_t)p;
+        hi[k] = (uint32_t)(p >> 32);
+    }
+    // s[k] = lo[k] + hi[k-1] (hi[-1] = mc), carries chained; the last carry joins hi[B-1] (no overflow: the exact
+    // product qd * d + mc fits B + 1 words)
+    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(lo[0]) : "r"(mc));
+#pragma unroll
+    for (int k = 1; k < B; k++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(lo[k]) : "r"(hi[k - 1]));
+    asm volatile("addc.u32 %0, %1, 0;" : "=r"(mc) : "r"(hi[B - 1]));
+    // u -= s with the incoming borrow
+    uint32_t t;
+    asm volatile("sub.cc.u32 %0, 0, %1;" : "=r"(t) : "r"(borrow));  // CF <- borrow
+#pragma unroll
+    for (int k = 0; k < B; k++) asm volatile("subc.cc.u32 %0, %0, %1;" : "+r"(u[k]) : "r"(lo[k]));
+    asm volatile("subc.u32 %0, 0, 0;" : "=r"(t));
+    borrow = t & 1u;
+#else
+    for (int k = 0; k < B; k++) {
+        uint64_t p = (uint64_t)qd * d[k] + mc;
+        mc = (uint32_t)(p >> 32);
+        uint64_t t = (uint64_t)u[k] - (uint32_t)p - borrow;
+        u[k] = (uint32_t)t;
+        borrow = (uint32_t)(t >> 32) & 1u;
+    }
+#endif
+}
+
 // dst = x / y  (Knuth D on 32-bit limbs; numerator x * 2^(32L) in S0, divisor in S1)
 template <int L, class SCR, class XS = RRef, class YS = RRef, class DST = WRef>
 CB_NOINLINE Meta arb_div(DST dst, OpdT<XS> x, OpdT<YS> y, SCR S0, SCR S1) {
@@ -1295,25 +1371,20 @@ CB_NOINLINE Meta arb_div(DST dst, OpdT<XS> x, OpdT<YS> y, SCR S0, SCR S1) {
             qh--;
             rh += d1;
         }
-        // U[j .. j+L] -= qh * D   (words j .. R-1 of the ring, then words 0 ..)
+        // U[j .. j+L] -= qh * D   (words j .. R-1 of the ring, then words 0 ..), sixteen limbs at a time in registers
         uint32_t qd = (uint32_t)qh, borrow = 0u, mc = 0u;
-        const int n1 = (RING && (R - j) < L) ? (R - j) : L;  // i < n1: no wrap
-#pragma unroll 8
-        for (int i = 0; i < (RING ? n1 : L); i++) {
-            uint64_t p = (uint64_t)qd * S1.ld(i) + mc;
-            mc = (uint32_t)(p >> 32);
-            uint64_t t = (uint64_t)S0.ld(i + j) - (uint32_t)p - borrow;
-            S0.st(i + j, (uint32_t)t);
-            borrow = (uint32_t)(t >> 32) & 1u;
-        }
-        if constexpr (RING) {
-#pragma unroll 8
-            for (int i = n1; i < L; i++) {
-                uint64_t p = (uint64_t)qd * S1.ld(i) + mc;
-                mc = (uint32_t)(p >> 32);
-                uint64_t t = (uint64_t)S0.ld(i + j - R) - (uint32_t)p - borrow;
-                S0.st(i + j - R, (uint32_t)t);
-                borrow = (uint32_t)(t >> 32) & 1u;
+        {
+            constexpr int B = (L % 16 == 0) ? 16 : 4;
+#pragma unroll 1
+            for (int blk = 0; blk < L; blk += B) {
+                uint32_t dd[B], uu[B];
+#pragma unroll
+                for (int k = 0; k < B; k++) dd[k] = S1.ld(blk + k);
+#pragma unroll
+                for (int k = 0; k < B; k++) uu[k] = S0.ld(slot(j + blk + k));
+                div_row_block<B>(uu, dd, qd, mc, borrow);
+#pragma unroll
+                for (int k = 0; k < B; k++) S0.st(slot(j + blk + k), uu[k]);
             }
         }
         const int top = slot(j + L);

@@ -78,6 +78,67 @@ __global__ void __launch_bounds__(HybCfg<L>::TPB, 1) frobenius1_hyb_kernel(FrobP
         frobenius1_thread<L, true>(p, idx, S0, S1);
     }
 }
+// ---- cooperating lanes (cb_coop.cuh): four lanes per instance, one hybrid column per lane, 64 instances per CTA
+template <int L> struct CoopCfg {
+    static constexpr bool ON = L >= 64;
+    static constexpr int TPB = 256, G = TPB / 4;
+    static constexpr int KS = L + 5, GW = 2 * L + 3 - KS;
+    static constexpr size_t SMEM = (size_t)KS * TPB * sizeof(uint32_t);
+    static constexpr int RANGE = 8;  // coefficients per work unit of the Frobenius recurrence
+};
+// Work units = (block of 64 instances, range of RANGE coefficients), handed out by an atomic counter in
+// coefficient-major order; unit (b, r) waits for (b, r - 1) (taken a full round earlier: all CTAs are resident and
+// units are taken in order, so the wait cannot deadlock).  Any batch size fills the SMs without a last-wave tail.
+template <int L>
+__global__ void __launch_bounds__(CoopCfg<L>::TPB, 1) frobenius1_coop_kernel(FrobParams p) {
+    if constexpr (CoopCfg<L>::ON) {
+        extern __shared__ uint32_t cb_smem[];
+        __shared__ int unit_s;
+        constexpr int TPB = CoopCfg<L>::TPB, G = CoopCfg<L>::G;
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cb_smem) + 4u * threadIdx.x;
+        const int64_t nblocks = (p.batch + G - 1) / G;
+        const int64_t nranges = (p.n + CoopCfg<L>::RANGE) / CoopCfg<L>::RANGE;  // coefficients 0 .. n
+        const int64_t total = nblocks * nranges;
+        for (;;) {
+            if (threadIdx.x == 0) {
+                int u = atomicAdd(p.sched, 1);
+                if (u < total) {
+                    int64_t b = u % nblocks, r = u / nblocks;
+                    while (r > 0 && atomicAdd(p.sched + 1 + b, 0) < (int)r) __nanosleep(200);
+                    __threadfence();
+                }
+                unit_s = u;
+            }
+            __syncthreads();
+            const int64_t u = unit_s;
+            if (u >= total) break;
+            const int64_t b = u % nblocks, r = u / nblocks;
+            const int64_t inst = b * G + (threadIdx.x >> 2);
+            const int64_t lo = r * CoopCfg<L>::RANGE;
+            const int64_t hi = lo + CoopCfg<L>::RANGE - 1 < p.n ? lo + CoopCfg<L>::RANGE - 1 : p.n;
+            Quad<TPB, CoopCfg<L>::KS> Q{(int)(threadIdx.x & 3), 0xFu << (threadIdx.x & 28), sbase,
+                                        p.gcols + (size_t)b * TPB + threadIdx.x, (uint32_t)(nblocks * TPB)};
+            if (inst < p.batch) frobenius1_coop_quad<L>(p, inst, Q, lo, hi);
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) atomicExch(p.sched + 1 + b, (int)(r + 1));
+        }
+    }
+}
+// Horner on four lanes per point: one CTA per block of 64 points
+template <int L>
+__global__ void __launch_bounds__(CoopCfg<L>::TPB, 1) horner_coop_kernel(HornerParams p) {
+    if constexpr (CoopCfg<L>::ON) {
+        extern __shared__ uint32_t cb_smem[];
+        constexpr int TPB = CoopCfg<L>::TPB, G = CoopCfg<L>::G;
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cb_smem) + 4u * threadIdx.x;
+        const int64_t pt = (int64_t)blockIdx.x * G + (threadIdx.x >> 2);
+        Quad<TPB, CoopCfg<L>::KS> Q{(int)(threadIdx.x & 3), 0xFu << (threadIdx.x & 28), sbase,
+                                    p.gcols + (size_t)blockIdx.x * TPB + threadIdx.x, (uint32_t)(gridDim.x * TPB)};
+        if (pt < p.npts) horner_coop_quad<L>(p, pt, Q);
+    }
+}
+
 template <int L>
 __global__ void __launch_bounds__(Cfg<L>::TPB, 1) frobenius_general_kernel(FrobGenParams p) {
     CB_KERNEL_PROLOGUE(p.batch)
@@ -388,6 +449,59 @@ template <int L> struct HybRatio { static constexpr double HORNER = 1.0, FROB = 
 template <> struct HybRatio<64> { static constexpr double HORNER = 1.04, FROB = 1.16; };
 template <> struct HybRatio<128> { static constexpr double HORNER = 1.27, FROB = 1.35; };
 
+// ---- cooperative kernels: when, and how they are launched
+// columns (lanes) the cooperative kernels need tails for: the batch padded to whole CTAs, four lanes per instance
+inline size_t coop_tail_words(int L, int64_t count) {
+    if (L < 64) return 0;
+    const int64_t G = 64;
+    return (size_t)(L - 2) * (size_t)(((count > 0 ? count : 0) + G - 1) / G) * 256;
+}
+// CB200_COOP=0/1 in the environment overrides (development).  Default, from measurements on B200 (tools/quick_coop.py,
+// profiles/coop_r02.txt): four lanes per instance win while the batch is at most ONE wave of cooperative CTAs (64
+// instances per SM) -- Horner 2.0-2.9x at 2 .. 4096 points (2048 and 4096 bits), the Frobenius recurrence 1.1-1.4x at
+// 2048 bits -- and lose beyond about two waves (idle lanes in the O(L) phases cost issue slots once the SMs are full);
+// the 4096-bit Frobenius recurrence, whose long divisions dominate, gains nothing and keeps the one-thread kernels.
+template <int L>
+bool coop_wanted(int64_t count, int sms, bool frobenius) {
+    if (!CoopCfg<L>::ON) return false;
+    const char* e = getenv("CB200_COOP");
+    if (e && e[0] == '0') return false;
+    if (e && e[0] == '1') return true;
+    if (frobenius && L >= 128) return false;
+    return count <= (int64_t)sms * CoopCfg<L>::G;
+}
+template <int L>
+bool use_coop_frob(const FrobParams& p) {
+    return CoopCfg<L>::ON && p.rhs_len == 0 && p.sched != nullptr && p.gcols_words >= coop_tail_words(L, p.batch) &&
+           coop_wanted<L>(p.batch, sm_count(), true);
+}
+template <int L>
+int launch_coop_frob(const FrobParams& p, cudaStream_t s) {
+    if (p.batch <= 0) return 0;
+    cudaError_t e = cudaFuncSetAttribute(frobenius1_coop_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CoopCfg<L>::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t nblocks = (p.batch + CoopCfg<L>::G - 1) / CoopCfg<L>::G;
+    e = cudaMemsetAsync(p.sched, 0, sizeof(int) * (size_t)(nblocks + 1), s);
+    if (e != cudaSuccess) return (int)e;
+    const int sms = sm_count();
+    const int grid = (int)(nblocks < sms ? nblocks : sms);
+    frobenius1_coop_kernel<L><<<grid, CoopCfg<L>::TPB, CoopCfg<L>::SMEM, s>>>(p);
+    return (int)cudaGetLastError();
+}
+template <int L>
+bool use_coop_horner(const HornerParams& p) {
+    return CoopCfg<L>::ON && p.gcols_words >= coop_tail_words(L, p.npts) && coop_wanted<L>(p.npts, sm_count(), false);
+}
+template <int L>
+int launch_coop_horner(const HornerParams& p, cudaStream_t s) {
+    if (p.npts <= 0) return 0;
+    cudaError_t e = cudaFuncSetAttribute(horner_coop_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CoopCfg<L>::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    const unsigned grid = (unsigned)((p.npts + CoopCfg<L>::G - 1) / CoopCfg<L>::G);
+    horner_coop_kernel<L><<<grid, CoopCfg<L>::TPB, CoopCfg<L>::SMEM, s>>>(p);
+    return (int)cudaGetLastError();
+}
+
 // per-precision launch table, filled by kern_L*.cu
 struct LaunchTable {
     int (*frobenius1)(const FrobParams&, cudaStream_t);
@@ -409,11 +523,13 @@ struct LaunchTable {
 #define CB_DEFINE_LAUNCH_TABLE(LL)                                                                         \
     namespace cb {                                                                                         \
     static int frob_##LL(const FrobParams& p, cudaStream_t s) {                                            \
+        if (use_coop_frob<LL>(p)) return launch_coop_frob<LL>(p, s);                                       \
         if (use_hybrid<LL>(p.batch, sm_count(), HybRatio<LL>::FROB))                                       \
             return launch<LL>(frobenius1_hyb_kernel<LL>, p, p.batch, s, HybCfg<LL>::TPB, HybCfg<LL>::SMEM); \
         return launch<LL>(frobenius1_kernel<LL>, p, p.batch, s);                                           \
     }                                                                                                      \
     static int horner_##LL(const HornerParams& p, cudaStream_t s) {                                        \
+        if (use_coop_horner<LL>(p)) return launch_coop_horner<LL>(p, s);                                   \
         if (use_hybrid<LL>(p.npts, sm_count(), HybRatio<LL>::HORNER))                                      \
             return launch<LL>(horner_hyb_kernel<LL>, p, p.npts, s, HybCfg<LL>::TPB, HybCfg<LL>::SMEM);     \
         return launch<LL>(horner_kernel<LL>, p, p.npts, s);                                                \

@@ -132,7 +132,7 @@ CB_HD Meta fdot2_auto(WRef dst, Opd x1, Opd y1, Opd x2, Opd y2, bool neg2, SCR S
 
 template <int L>
 CB_HD void acb_set(const CRef& z, const CRef& x) {
-#pragma unroll 8
+#pragma unroll 16
     for (int k = 0; k < L; k++) {
         z.m[k * z.stride] = x.m[k * x.stride];
         z.m[k * z.stride + 1] = x.m[k * x.stride + 1];
@@ -622,7 +622,10 @@ struct FrobParams {
     CArr tmp;  // FROB_NTMP entries
     CArr rhs;  // right-hand side series: rhs_len entries, S = 2*batch or 2 (ignored when rhs_len == 0)
     int64_t rhs_len;
-    uint32_t* gcols;  // 2048 bits and up: global tails of the two scratch columns, 2 * (L - 2) * batch words
+    uint32_t* gcols;  // 2048 bits and up: global tails of the scratch columns (2 per instance; 4 per instance for the
+                      // cooperative kernel, whose lanes own one column each), (L - 2) words per column
+    int* sched;       // cooperative (work-unit) kernel: [0] unit counter, [1 + b] ranges completed for instance block b
+    size_t gcols_words;  // size of gcols in words (the cooperative kernel needs more than the one-thread kernels)
 };
 constexpr int FROB_NTMP = 7;
 
@@ -1188,7 +1191,9 @@ struct HornerParams {
     CArr pts;       // 1 entry, S = 2*npts, or S = 2: one point for all series (continuation step)
     CArr out;       // nder entries, S = 2*npts
     CArr tmp;       // 1 entry, S = 2*npts
-    uint32_t* gcols;  // 2048 bits and up: global tails of the two scratch columns, 2 * (L - 2) * npts words
+    uint32_t* gcols;  // 2048 bits and up: global tails of the scratch columns, (L - 2) words per column: 2 columns per
+                      // point for the one-thread kernels, 4 (one per lane) for the cooperative kernel
+    size_t gcols_words;
 };
 constexpr int HORNER_MAXDER = 4;
 
@@ -1217,6 +1222,10 @@ CB_HD void horner_thread(const HornerParams& p, int64_t pt, SCR S0, SCR S1) {
         }
     }
 }
+
+}  // namespace cb
+#include "cb_coop.cuh"
+namespace cb {
 
 // ================================================================ elementwise (unit-test surface)
 enum { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_DIV = 3, OP_INV = 4, OP_MUL_SI = 16, OP_ADD_SI = 17 };

@@ -19,7 +19,7 @@ _lib = None
 
 def build(force: bool = False) -> None:
     deps = [_SRC] + [os.path.join(_HERE, "..", "..", "cascade_b200", "csrc", f)
-                     for f in ("cb_arith.cuh", "cb_solvers.cuh", "cb_mul.cuh", "cb_rr.cuh", "cb_trans.cuh", "cb_intop.cuh")]
+                     for f in ("cb_arith.cuh", "cb_solvers.cuh", "cb_mul.cuh", "cb_rr.cuh", "cb_trans.cuh", "cb_intop.cuh", "cb_coop.cuh")]
     if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
         return
     subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-ffp-contract=off",
@@ -39,6 +39,8 @@ def lib():
                                                 _u32p, _i32p, _u32p, _i32p]
         L.cbsim_ode_shift.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, _u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int, _u32p, _i32p]
         L.cbsim_taylor_shift.argtypes = [C.c_int, C.c_int64, C.c_int64, _u32p, _i32p, _u32p, _i32p, C.c_int]
+        L.cbsim_frobenius1_coop.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int, _u32p, _i32p]
+        L.cbsim_horner_coop.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int, _u32p, _i32p, C.c_int, _u32p, _i32p, _u32p, _i32p]
         L.cbsim_frobenius1_batch.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int, _vp, _vp, C.c_int64, C.c_int, _u32p, _i32p]
         L.cbsim_horner_batch.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int, _u32p, _i32p, C.c_int, _u32p, _i32p, _u32p, _i32p]
         L.cbsim_ew.argtypes = [C.c_int, C.c_int, C.c_int64, _u32p, _i32p, _u32p, _i32p, _vp, _vp, _vp]
@@ -58,6 +60,11 @@ def lib():
 
 
 class SimDriver:
+    def __init__(self, coop: bool = False):
+        """coop: run the Frobenius (M = 1, homogeneous) and Horner bodies in their four-lanes-per-instance form
+        (cb_coop.cuh) where the device would (2048 bits and up)"""
+        self.coop = coop
+
     def fuchs(self, L, order, degree, valuation, n, batch, ode_m, ode_t, shared, res_m, res_t):
         return lib().cbsim_fuchs_batch(L, order, degree, valuation, n, batch, ode_m, ode_t, int(shared), res_m, res_t)
 
@@ -84,6 +91,9 @@ class SimDriver:
     def frobenius1(self, L, order, degree, valuation, n, batch, ode_m, ode_t, shared, rho_m, rho_t,
                    shared_rho, res_m, res_t, rhs_m=None, rhs_t=None, rhs_len=0, shared_rhs=False):
         vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        if self.coop and L >= 64 and rhs_len == 0:
+            return lib().cbsim_frobenius1_coop(L, order, degree, valuation, n, batch, ode_m, ode_t, int(shared), rho_m, rho_t,
+                                               int(shared_rho), res_m, res_t)
         return lib().cbsim_frobenius1_batch(L, order, degree, valuation, n, batch, ode_m, ode_t, int(shared),
                                             rho_m, rho_t, int(shared_rho), vp(rhs_m), vp(rhs_t), rhs_len,
                                             int(shared_rhs), res_m, res_t)
@@ -111,6 +121,8 @@ class SimDriver:
                                      out_len, deg, solved)
 
     def horner(self, L, length, npts, nder, f_m, f_t, shared_f, p_m, p_t, o_m, o_t):
+        if self.coop and L >= 64:
+            return lib().cbsim_horner_coop(L, length, npts, nder, f_m, f_t, int(shared_f), p_m, p_t, o_m, o_t)
         return lib().cbsim_horner_batch(L, length, npts, nder, f_m, f_t, int(shared_f), p_m, p_t, o_m, o_t)
 
     def ew(self, op, L, n, z_m, z_t, x_m, x_t, y_m, y_t, k):

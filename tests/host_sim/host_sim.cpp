@@ -173,6 +173,8 @@ int cbsim_frobenius1_batch(int L_, int order, int degree, int valuation, int64_t
     Tmp tmp;
     p.tmp = tmp.arr(L_, FROB_NTMP, 2 * batch);
     p.gcols = nullptr;
+    p.sched = nullptr;
+    p.gcols_words = 0;
     SIM_DISPATCH(L_, run_hyb<L>(batch, [&](int64_t i, auto a, auto b) { frobenius1_thread<L>(p, i, a, b); }));
     return 0;
 }
@@ -389,6 +391,7 @@ int cbsim_continuation_series(int L_, int order, int degree, int64_t n, int64_t 
         Tmp tmp;
         hp.tmp = tmp.arr(L_, 1, S);
         hp.gcols = nullptr;
+        hp.gcols_words = 0;
         SIM_DISPATCH(L_, run_hyb<L>(batch, [&](int64_t i, auto a, auto b) { horner_thread<L>(hp, i, a, b); }));
     }
     return 0;
@@ -398,6 +401,90 @@ int cbsim_continuation(int L_, int order, int degree, int64_t n, int64_t batch, 
                        const cb_meta* path_meta, uint32_t* y_mant, cb_meta* y_meta) {
     return cbsim_continuation_series(L_, order, degree, n, batch, path_len, ode_mant, ode_meta, path_mant, path_meta, y_mant,
                                      y_meta, nullptr, nullptr);
+}
+
+// ---- cooperating lanes (cb_coop.cuh): the four lanes of a quad run their phase one after the other (CB_COOP_EACH),
+// each on its own column of exactly the device size (KS shared words + GW global words, followed by canaries)
+extern "C++" {
+template <int L>
+struct SimQuad {
+    static constexpr int KS = L + 5, GW = 2 * L + 3 - KS;
+    static constexpr size_t CAN = 32;
+    std::vector<uint32_t> sh[4], gl[4];
+    Quad<1, KS> Q;
+    SimQuad() {
+        for (int q = 0; q < 4; q++) {
+            sh[q].assign(KS + CAN, 0xDEADBEEFu);
+            gl[q].assign(GW + CAN, 0xDEADBEEFu);
+            Q.p[q] = sh[q].data();
+            Q.g[q] = gl[q].data();
+        }
+    }
+    int check() const {
+        for (int q = 0; q < 4; q++) {
+            for (size_t k = KS; k < KS + CAN; k++) if (sh[q][k] != 0xDEADBEEFu) return -2000 - q;
+            for (size_t k = GW; k < GW + CAN; k++) if (gl[q][k] != 0xDEADBEEFu) return -2100 - q;
+        }
+        return 0;
+    }
+};
+template <int L>
+static int sim_frobenius1_coop(FrobParams& p) {
+    if constexpr (L >= 64) {
+        SimQuad<L> sq;
+        // coefficient ranges as the work units of frobenius1_coop_kernel cut them
+        for (int64_t lo = 0; lo <= p.n; lo += 8)
+            for (int64_t i = 0; i < p.batch; i++) frobenius1_coop_quad<L>(p, i, sq.Q, lo, lo + 7 < p.n ? lo + 7 : p.n);
+        return sq.check();
+    } else {
+        return CB200_EINVAL;
+    }
+}
+template <int L>
+static int sim_horner_coop(HornerParams& p) {
+    if constexpr (L >= 64) {
+        SimQuad<L> sq;
+        for (int64_t i = 0; i < p.npts; i++) horner_coop_quad<L>(p, i, sq.Q);
+        return sq.check();
+    } else {
+        return CB200_EINVAL;
+    }
+}
+}  // extern "C++"
+int cbsim_frobenius1_coop(int L_, int order, int degree, int valuation, int64_t n, int64_t batch, const uint32_t* ode_mant,
+                          const cb_meta* ode_meta, int shared_ode, const uint32_t* rho_mant, const cb_meta* rho_meta,
+                          int shared_rho, uint32_t* res_mant, cb_meta* res_meta) {
+    FrobParams p;
+    p.rhs = CArr{nullptr, nullptr, (size_t)2};
+    p.rhs_len = 0;
+    p.order = order; p.degree = degree; p.valuation = valuation; p.n = n; p.batch = batch;
+    p.ode = CArr{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta), shared_ode ? (size_t)2 : (size_t)(2 * batch)};
+    p.rho = CArr{const_cast<uint32_t*>(rho_mant), (Meta*)const_cast<cb_meta*>(rho_meta), shared_rho ? (size_t)2 : (size_t)(2 * batch)};
+    p.res = CArr{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
+    Tmp tmp;
+    p.tmp = tmp.arr(L_, FROB_NTMP, 2 * batch);
+    p.gcols = nullptr; p.sched = nullptr; p.gcols_words = 0;
+    switch (L_) {
+        case 64: return sim_frobenius1_coop<64>(p);
+        case 128: return sim_frobenius1_coop<128>(p);
+        default: return CB200_EINVAL;
+    }
+}
+int cbsim_horner_coop(int L_, int64_t len, int64_t npts, int nder, const uint32_t* f_mant, const cb_meta* f_meta, int shared_f,
+                      const uint32_t* pts_mant, const cb_meta* pts_meta, uint32_t* out_mant, cb_meta* out_meta) {
+    HornerParams p;
+    p.nder = nder; p.len = len; p.npts = npts;
+    p.f = CArr{const_cast<uint32_t*>(f_mant), (Meta*)const_cast<cb_meta*>(f_meta), shared_f ? (size_t)2 : (size_t)(2 * npts)};
+    p.pts = CArr{const_cast<uint32_t*>(pts_mant), (Meta*)const_cast<cb_meta*>(pts_meta), (size_t)(2 * npts)};
+    p.out = CArr{out_mant, (Meta*)out_meta, (size_t)(2 * npts)};
+    Tmp tmp;
+    p.tmp = tmp.arr(L_, 1, 2 * npts);
+    p.gcols = nullptr; p.gcols_words = 0;
+    switch (L_) {
+        case 64: return sim_horner_coop<64>(p);
+        case 128: return sim_horner_coop<128>(p);
+        default: return CB200_EINVAL;
+    }
 }
 
 }  // extern "C"

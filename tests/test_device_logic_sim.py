@@ -159,3 +159,15 @@ def test_fuchs_coefficient_ranges(oracle, sim_driver):
 @pytest.mark.parametrize("L", [4, 32])
 def test_frobenius_general_edge(oracle, sim_driver, L):
     cases.case_frobenius_general_edge(oracle, sim_driver, L)
+
+
+@pytest.mark.parametrize("L", [64, 128])
+def test_cooperating_lanes(oracle, L):
+    """cb_coop.cuh: four lanes per instance (the products of a complex multiplication on four lanes, real and imaginary
+    parts of everything else on two), simulated lane by lane and phase by phase: Frobenius M = 1 and Horner, including
+    the cancellation case that needs the exact full-width path on one lane's pair of hybrid columns."""
+    from tests.host_sim.driver import SimDriver
+    drv = SimDriver(coop=True)
+    cases.case_frobenius(oracle, drv, L, seed=29, n=12 if L == 64 else 9, batch=5)
+    cases.case_horner(oracle, drv, L, seed=23, length=14, npts=5)
+    cases.case_horner_cancellation(oracle, drv, L, seed=213 + L, length=10, npts=12)

@@ -81,6 +81,20 @@ def test_hybrid_scratch_columns(monkeypatch, oracle, gpu_driver, L, hybrid):
     cases.case_frobenius(oracle, gpu_driver, L, seed=29, n=14, batch=300)
 
 
+@pytest.mark.parametrize("coop", ["0", "1"])
+@pytest.mark.parametrize("L", [64, 128])
+def test_cooperating_lanes(monkeypatch, oracle, gpu_driver, L, coop):
+    """2048 / 4096 bits: the Frobenius (M = 1) and Horner kernels with FOUR lanes per instance (cb_coop.cuh; the
+    launcher picks them for batches below two waves of the one-thread kernels) forced on and off: ragged batches
+    (a last CTA with idle quads, a last warp with idle lanes), several work-unit ranges, the cancellation case that
+    needs the exact full-width path on one lane, and the continuation pipeline on top."""
+    monkeypatch.setenv("CB200_COOP", coop)
+    cases.case_frobenius(oracle, gpu_driver, L, seed=31, n=19 if L == 64 else 12, batch=333)
+    cases.case_horner(oracle, gpu_driver, L, seed=37, length=30, npts=301)
+    cases.case_horner_cancellation(oracle, gpu_driver, L, seed=313 + L, length=20, npts=300)
+    cases.case_continuation(oracle, gpu_driver, L, seed=123 + L, steps=3, n=24, batch=7)
+
+
 @pytest.mark.parametrize("L", [32, 64, 128])
 def test_continuation(oracle, gpu_driver, L):
     cases.case_continuation(oracle, gpu_driver, L, seed=23 + L, steps=6 if L < 128 else 3, n=40 if L < 128 else 24, batch=5)
