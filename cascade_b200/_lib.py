@@ -30,6 +30,8 @@ SYMBOLS = [
     "cb200_fuchs_intop_batch_dev", "cb200_fuchs_intop_batch_host",
     "cb200_continuation_workspace_bytes", "cb200_continuation_dev", "cb200_continuation_host",
     "cb200_continuation_series_workspace_bytes", "cb200_continuation_series_dev", "cb200_continuation_series_host",
+    "cb200_radius_workspace_bytes", "cb200_radius_of_convergence_dev", "cb200_radius_of_convergence_host",
+    "cb200_truncation_workspace_bytes", "cb200_truncation_order_dev", "cb200_truncation_order_host",
     "cb200_ode_shift_workspace_bytes", "cb200_ode_shift_dev", "cb200_ode_shift_host",
     "cb200_taylor_shift_workspace_bytes", "cb200_taylor_shift_dev", "cb200_taylor_shift_host",
     "cb200_frobenius1_batch_dev", "cb200_frobenius1_batch_host",
@@ -90,6 +92,18 @@ def lib() -> C.CDLL:
                                                 _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]
     L.cb200_continuation_series_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, _u32p, _i32p,
                                                  _u32p, _i32p, _u32p, _i32p, _u32p, _i32p, C.c_int]
+    _i64p_ = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+    L.cb200_radius_workspace_bytes.restype = C.c_size_t
+    L.cb200_radius_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int64]
+    L.cb200_radius_of_convergence_dev.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, _vp, _vp, C.c_int, C.c_int64, _vp, _vp, _vp,
+                                                  _vp, C.c_size_t, _vp]
+    L.cb200_radius_of_convergence_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, _u32p, _i32p, C.c_int, C.c_int64, _u32p,
+                                                   _i32p, _i32p, C.c_int]
+    L.cb200_truncation_workspace_bytes.restype = C.c_size_t
+    L.cb200_truncation_workspace_bytes.argtypes = [C.c_int, C.c_int64]
+    L.cb200_truncation_order_dev.argtypes = [C.c_int, C.c_int64, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_size_t, _vp]
+    L.cb200_truncation_order_host.argtypes = [C.c_int, C.c_int64, _u32p, _i32p, _u32p, _i32p, C.c_int64, _u32p, _i32p, _i64p_,
+                                              C.c_int]
     L.cb200_ode_shift_workspace_bytes.restype = C.c_size_t
     L.cb200_ode_shift_workspace_bytes.argtypes = [C.c_int, C.c_int64]
     L.cb200_ode_shift_dev.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp,

@@ -52,6 +52,13 @@ class HostBufferDriver:
     def taylor_shift(self, L, length, batch, f_m, f_t, a_m, a_t, shared_a):
         return _lib.lib().cb200_taylor_shift_host(L, length, batch, f_m, f_t, a_m, a_t, int(shared_a), self.device)
 
+    def radius(self, L, order, degree, batch, ode_m, ode_t, shared, n, o_m, o_t, n_done):
+        return _lib.lib().cb200_radius_of_convergence_host(L, order, degree, batch, ode_m, ode_t, int(shared), n, o_m, o_t,
+                                                           n_done, self.device)
+
+    def truncation(self, L, batch, e_m, e_t, a_m, a_t, bits, n_m, n_t, n_out):
+        return _lib.lib().cb200_truncation_order_host(L, batch, e_m, e_t, a_m, a_t, bits, n_m, n_t, n_out, self.device)
+
     def frobenius1(self, L, order, degree, valuation, n, batch, ode_m, ode_t, shared, rho_m, rho_t,
                    shared_rho, res_m, res_t, rhs_m=None, rhs_t=None, rhs_len=0, shared_rhs=False):
         vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
@@ -358,6 +365,35 @@ def acb_poly_taylor_shift_batch(f: Balls, a: Balls, batch: int, driver=None) -> 
     a_m, a_t = pack_entries(a, 1, 2 if shared_a else 2 * batch)
     _lib.check(drv.taylor_shift(L, length, batch, f_m, f_t, a_m, a_t, shared_a), "acb_poly_taylor_shift_batch")
     return entry_major_to_instance_major(unpack_entries(L, f_m, f_t), batch, length)
+
+
+def radius_of_convergence_batch(ode: Balls, order: int, degree: int, batch: int, n: int = 20, shared_ode: bool = False,
+                                driver=None):
+    """``radius_of_convergence(rad, ODE, n, bits)`` (reference src/fuchs_solver.c:3-54) for a batch of operators, rigorous
+    on the device.  Returns (balls ``[batch]`` -- real, the imaginary parts exact zeros --, ``n_done`` int32 ``[batch]``:
+    Graeffe iterations performed, -1 where the operator has no singularity away from zero: ball indeterminate)."""
+    drv = driver or default_driver()
+    L = ode.L
+    ode_m, ode_t = _ode_to_device(ode, order, degree, batch, shared_ode)
+    o_m = np.zeros((1, L, 2 * batch), np.uint32)
+    o_t = np.zeros((1, 2 * batch, 4), np.int32)
+    nd = np.zeros(batch, np.int32)
+    _lib.check(drv.radius(L, order, degree, batch, ode_m, ode_t, shared_ode, n, o_m, o_t, nd), "radius_of_convergence_batch")
+    return unpack_entries(L, o_m, o_t), nd
+
+
+def truncation_order_batch(eta: Balls, alpha: Balls, bits: int, driver=None):
+    """``truncation_order(eta, alpha, bits)`` (reference src/fuchs_solver.c:56-94) for a batch of pairs: returns
+    (the balls N, the term counts int64 ``[batch]``)."""
+    drv = driver or default_driver()
+    L, batch = eta.L, eta.n_slots // 2
+    e_m, e_t = pack_entries(eta, 1, 2 * batch)
+    a_m, a_t = pack_entries(alpha, 1, 2 * batch)
+    n_m = np.zeros((1, L, 2 * batch), np.uint32)
+    n_t = np.zeros((1, 2 * batch, 4), np.int32)
+    out = np.zeros(batch, np.int64)
+    _lib.check(drv.truncation(L, batch, e_m, e_t, a_m, a_t, bits, n_m, n_t, out), "truncation_order_batch")
+    return unpack_entries(L, n_m, n_t), out
 
 
 def acb_poly_evaluate_batch(f: Balls, pts: Balls, nder: int = 1, driver=None) -> Balls:

@@ -559,6 +559,47 @@ int cb200_ew_dev(int op, int L_, int64_t n, uint32_t* z_mant, cb_meta* z_meta, c
     return table_for(L_)->ew(p, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------ radius_of_convergence, truncation_order
+size_t cb200_radius_workspace_bytes(int L, int degree, int64_t batch) {
+    return carve_bytes(L, 2 * (int64_t)(degree + 1) + RADIUS_NTMP + TRANS_NTMP, 2 * batch);
+}
+int cb200_radius_of_convergence_dev(int L_, int order, int degree, int64_t batch, const uint32_t* ode_mant,
+                                    const cb_meta* ode_meta, int shared_ode, int64_t n, uint32_t* out_mant, cb_meta* out_meta,
+                                    int32_t* n_done, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!supported_L(L_) || order < 0 || degree < 0 || batch < 0 || n < 0 || !n_done) return CB200_EINVAL;
+    if (workspace_bytes < cb200_radius_workspace_bytes(L_, degree, batch)) return CB200_ENOMEM;
+    RadiusParams p;
+    p.order = order;
+    p.degree = degree;
+    p.batch = batch;
+    p.n = n;
+    p.ode = CArr{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta), shared_ode ? (size_t)2 : (size_t)(2 * batch)};
+    p.out = CArr{out_mant, (Meta*)out_meta, (size_t)(2 * batch)};
+    char* w = (char*)workspace;
+    p.wp = carve(w, L_, 2 * (int64_t)(degree + 1) + RADIUS_NTMP + TRANS_NTMP, 2 * batch);
+    p.n_done = n_done;
+    g_launches.fetch_add(batch > 0);
+    return table_for(L_)->radius(p, (cudaStream_t)stream);
+}
+size_t cb200_truncation_workspace_bytes(int L, int64_t batch) { return carve_bytes(L, 8 + TRANS_NTMP, 2 * batch); }
+int cb200_truncation_order_dev(int L_, int64_t batch, const uint32_t* eta_mant, const cb_meta* eta_meta,
+                               const uint32_t* alpha_mant, const cb_meta* alpha_meta, int64_t bits, uint32_t* n_mant,
+                               cb_meta* n_meta, int64_t* n_out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!supported_L(L_) || batch < 0 || bits < 1 || !n_out) return CB200_EINVAL;
+    if (workspace_bytes < cb200_truncation_workspace_bytes(L_, batch)) return CB200_ENOMEM;
+    TruncParams p;
+    p.batch = batch;
+    p.bits = bits;
+    p.eta = CArr{const_cast<uint32_t*>(eta_mant), (Meta*)const_cast<cb_meta*>(eta_meta), (size_t)(2 * batch)};
+    p.alpha = CArr{const_cast<uint32_t*>(alpha_mant), (Meta*)const_cast<cb_meta*>(alpha_meta), (size_t)(2 * batch)};
+    p.nball = CArr{n_mant, (Meta*)n_meta, (size_t)(2 * batch)};
+    char* w = (char*)workspace;
+    p.wp = carve(w, L_, 8 + TRANS_NTMP, 2 * batch);
+    p.n_out = n_out;
+    g_launches.fetch_add(batch > 0);
+    return table_for(L_)->truncation(p, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------ acb_ode_shift, acb_poly_taylor_shift
 size_t cb200_ode_shift_workspace_bytes(int L, int64_t batch) { return carve_bytes(L, 1, 2 * batch); }
 int cb200_ode_shift_dev(int L_, int order, int degree, int64_t batch, const uint32_t* ode_mant, const cb_meta* ode_meta,
@@ -1299,6 +1340,59 @@ int cb200_taylor_shift_host(int L, int64_t len, int64_t batch, uint32_t* f_mant,
     if (rc) return rc;
     CK(cudaMemcpy(f_mant, fm.p, arr_mant_bytes(L, len, S), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(f_meta, ft.p, arr_meta_bytes(len, S), cudaMemcpyDeviceToHost));
+    return (int)cudaDeviceSynchronize();
+}
+
+int cb200_radius_of_convergence_host(int L, int order, int degree, int64_t batch, const uint32_t* ode_mant,
+                                     const cb_meta* ode_meta, int shared_ode, int64_t n, uint32_t* out_mant, cb_meta* out_meta,
+                                     int32_t* n_done, int device) {
+    if (!supported_L(L) || order < 0 || degree < 0 || batch < 0 || n < 0 || !n_done) return CB200_EINVAL;
+    CK(cudaSetDevice(device));
+    int64_t ne = (int64_t)(order + 1) * (degree + 1), S = 2 * batch, So = shared_ode ? 2 : S;
+    DevBuf om, ot, rm, rt, nd, ws;
+    size_t wsb = cb200_radius_workspace_bytes(L, degree, batch);
+    CK(om.alloc(arr_mant_bytes(L, ne, So)));
+    CK(ot.alloc(arr_meta_bytes(ne, So)));
+    CK(rm.alloc(arr_mant_bytes(L, 1, S)));
+    CK(rt.alloc(arr_meta_bytes(1, S)));
+    CK(nd.alloc(sizeof(int32_t) * batch));
+    CK(ws.alloc(wsb));
+    CK(cudaMemcpy(om.p, ode_mant, arr_mant_bytes(L, ne, So), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ot.p, ode_meta, arr_meta_bytes(ne, So), cudaMemcpyHostToDevice));
+    int rc = cb200_radius_of_convergence_dev(L, order, degree, batch, (uint32_t*)om.p, (cb_meta*)ot.p, shared_ode, n,
+                                             (uint32_t*)rm.p, (cb_meta*)rt.p, (int32_t*)nd.p, ws.p, wsb, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(out_mant, rm.p, arr_mant_bytes(L, 1, S), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out_meta, rt.p, arr_meta_bytes(1, S), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(n_done, nd.p, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost));
+    return (int)cudaDeviceSynchronize();
+}
+int cb200_truncation_order_host(int L, int64_t batch, const uint32_t* eta_mant, const cb_meta* eta_meta,
+                                const uint32_t* alpha_mant, const cb_meta* alpha_meta, int64_t bits, uint32_t* n_mant,
+                                cb_meta* n_meta, int64_t* n_out, int device) {
+    if (!supported_L(L) || batch < 0 || bits < 1 || !n_out) return CB200_EINVAL;
+    CK(cudaSetDevice(device));
+    int64_t S = 2 * batch;
+    DevBuf em, et, am, at_, nm, nt, no, ws;
+    size_t wsb = cb200_truncation_workspace_bytes(L, batch);
+    CK(em.alloc(arr_mant_bytes(L, 1, S)));
+    CK(et.alloc(arr_meta_bytes(1, S)));
+    CK(am.alloc(arr_mant_bytes(L, 1, S)));
+    CK(at_.alloc(arr_meta_bytes(1, S)));
+    CK(nm.alloc(arr_mant_bytes(L, 1, S)));
+    CK(nt.alloc(arr_meta_bytes(1, S)));
+    CK(no.alloc(sizeof(int64_t) * batch));
+    CK(ws.alloc(wsb));
+    CK(cudaMemcpy(em.p, eta_mant, arr_mant_bytes(L, 1, S), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(et.p, eta_meta, arr_meta_bytes(1, S), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(am.p, alpha_mant, arr_mant_bytes(L, 1, S), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(at_.p, alpha_meta, arr_meta_bytes(1, S), cudaMemcpyHostToDevice));
+    int rc = cb200_truncation_order_dev(L, batch, (uint32_t*)em.p, (cb_meta*)et.p, (uint32_t*)am.p, (cb_meta*)at_.p, bits,
+                                        (uint32_t*)nm.p, (cb_meta*)nt.p, (int64_t*)no.p, ws.p, wsb, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(n_mant, nm.p, arr_mant_bytes(L, 1, S), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(n_meta, nt.p, arr_meta_bytes(1, S), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(n_out, no.p, sizeof(int64_t) * batch, cudaMemcpyDeviceToHost));
     return (int)cudaDeviceSynchronize();
 }
 

@@ -106,10 +106,10 @@ struct RegDst {
     CB_HD void st(int, uint32_t) const {}
 };
 
-// acc = round(acc - p) on register operands (arb_addsub_cols's fast path); false: not the easy case
+// acc = round(acc -+ p) on register operands (the fast path of arb_addsub / arb_addsub_cols); false: not the easy case
 template <int L>
-CB_HD bool reg_sub(uint32_t (&acc)[L], Meta& ta, const uint32_t (&p)[L], const Meta& tp) {
-    const bool na = (ta.flags & F_SIGN) != 0, nb = (tp.flags & F_SIGN) == 0;  // acc + (-p)
+CB_HD bool reg_addsub(uint32_t (&acc)[L], Meta& ta, const uint32_t (&p)[L], const Meta& tp, bool negp) {
+    const bool na = (ta.flags & F_SIGN) != 0, nb = ((tp.flags & F_SIGN) != 0) != negp;
     const int64_t d = (int64_t)ta.exp - tp.exp;
     if (d > 31 || d < -31) return false;
     const int64_t E = ta.exp > tp.exp ? ta.exp : tp.exp;
@@ -129,6 +129,10 @@ CB_HD bool reg_sub(uint32_t (&acc)[L], Meta& ta, const uint32_t (&p)[L], const M
 #pragma unroll
     for (int j = 0; j < L; j++) acc[j] = res[j];
     return true;
+}
+template <int L>
+CB_HD bool reg_sub(uint32_t (&acc)[L], Meta& ta, const uint32_t (&p)[L], const Meta& tp) {
+    return reg_addsub<L>(acc, ta, p, tp, true);
 }
 
 // what arb_div_u64 derives from the divisor alone: formed once per coefficient and shared by both parts
@@ -399,6 +403,116 @@ CB_HD void fuchs_intop_fast_thread(const FuchsIntParams& p, int64_t inst, SCR S0
 #pragma unroll 1
     for (int64_t bmax = b_first; bmax <= b_last; bmax++)
         if (!fuchs_intop_fast_coeff<L>(p, inst, P, bmax)) fuchs_intop_thread<L>(p, inst, S0, A0, A1, A2, bmax, bmax);
+}
+
+// ================================================================ per-instance multiplier tables in registers
+// fuchs_table_thread (cb_solvers.cuh) forms the multipliers  sum_i P[i][i+e-b] * fac_i  of one table row through
+// acb_mul_si / acb_add on temporaries in global memory (reference src/fuchs_solver.c:121-135): every step waits for
+// the stores of the one before it (ncu: long_scoreboard 7.3 cycles per issue, profiles/
+// ncu_fuchs_table32_pi_r02_before_summary.txt).  The real and the imaginary part of that sum never mix, so here each
+// part of each multiplier is a short chain of register operations -- reg_mul_u64 (ball x integer), reg_addsub -- and
+// goes to the table once, with its trailing-zero hint.  Same operations in the same order: bit-identical.  A step
+// outside the fast path (an indeterminate or zero-midpoint-with-radius operand, an exponent gap beyond 31 bits,
+// cancellation of a limb or more) returns false and the caller recomputes the row with fuchs_table_thread.
+template <int L>
+CB_HD bool fuchs_table_fast_multipliers(const FuchsTableParams& p, int64_t row, size_t oslot, size_t qslot, int64_t base,
+                                        int* cnt_out) {
+    const int v = p.valuation, D1 = p.degree + 1;
+    const int64_t bmax = row - v, e = bmax + v;
+    const int64_t bmin = clampi(e - p.degree, 0, bmax);
+    const int cnt = (int)(bmax - bmin);
+    *cnt_out = cnt;
+    const size_t So = p.ode.S, St = p.tbl.S;
+#pragma unroll 1
+    for (int k = 0; k <= cnt; k++) {
+        const int64_t b = bmin + k;
+        const int64_t imin = k == 0 ? 0 : clampi(b - e, 0, -v), imax = k == 0 ? 0 : clampi(b - bmin, 0, p.order);
+        int64_t fac2 = 1;
+        for (int64_t q = 0; q < imin; q++) fac2 *= (b - imin + 1 + q);
+#pragma unroll 1
+        for (int part = 0; part < 2; part++) {
+            uint32_t acc[L];
+            Meta tacc = meta_zero();
+            bool have = false;
+            int64_t fac = 1;
+#pragma unroll 1
+            for (int64_t i = imin; i <= imax; i++) {
+                const int64_t ent = i * D1 + (k == 0 ? (e - bmin) : (i + e - b));
+                const int64_t f = fac;
+                fac *= (b - i);
+                const Meta tx = ld_meta_user(p.ode.t + (size_t)ent * So + oslot + part);
+                if (is_exact_zero(tx) || f == 0) continue;  // an exact zero term: t2 + 0 leaves t2 untouched
+                if (is_nan(tx) || is_zero_mid(tx)) return false;
+                uint32_t x[L];
+                {
+                    const uint32_t* q = p.ode.m + (size_t)ent * L * So + oslot + part;
+#pragma unroll
+                    for (int j = 0; j < L; j++) {
+                        x[j] = *q;
+                        q += So;
+#if defined(__CUDA_ARCH__)
+                        asm volatile("" : "+l"(q));
+#endif
+                    }
+                }
+                if (k == 0) {  // slot 0 is a plain copy of P[0][e - bmin]
+#pragma unroll
+                    for (int j = 0; j < L; j++) acc[j] = x[j];
+                    tacc = tx;
+                    have = true;
+                    continue;
+                }
+                uint32_t pr[L];
+                Meta tp;
+                const uint64_t ka = f < 0 ? (uint64_t)0 - (uint64_t)f : (uint64_t)f;
+                if (!reg_mul_u64<L>(pr, tp, x, tx, ka, f < 0)) return false;
+                if (!have) {  // 0 + t1 = t1 exactly
+#pragma unroll
+                    for (int j = 0; j < L; j++) acc[j] = pr[j];
+                    tacc = tp;
+                    have = true;
+                } else if (!reg_addsub<L>(acc, tacc, pr, tp, false) || is_zero_mid(tacc)) {
+                    return false;
+                }
+            }
+            if (have && k > 0) {  // t2 *= fac2 (acb_mul_si runs even for a factor 1: the radius bound is |k| rounded up)
+                uint32_t pr[L];
+                Meta tp;
+                if (!reg_mul_u64<L>(pr, tp, acc, tacc, (uint64_t)fac2, false)) return false;
+#pragma unroll
+                for (int j = 0; j < L; j++) acc[j] = pr[j];
+                tacc = tp;
+            }
+            // store this part of slot k with its trailing-zero hint (acb_mark_tz)
+            uint32_t* om = p.tbl.m + (size_t)(base + k) * L * St + qslot + part;
+            if (!have) {
+#pragma unroll
+                for (int j = 0; j < L; j++) {
+                    *om = 0u;
+                    om += St;
+#if defined(__CUDA_ARCH__)
+                    asm volatile("" : "+l"(om));
+#endif
+                }
+                st_meta(p.tbl.t + (size_t)(base + k) * St + qslot + part, meta_zero());
+            } else {
+                int tz = L - 1;
+#pragma unroll
+                for (int j = L - 2; j >= 0; j--) tz = acc[j] ? j : tz;
+#pragma unroll
+                for (int j = 0; j < L; j++) {
+                    *om = acc[j];
+                    om += St;
+#if defined(__CUDA_ARCH__)
+                    asm volatile("" : "+l"(om));
+#endif
+                }
+                tacc.flags = (tacc.flags & 0xFFu) | ((uint32_t)tz << F_TZ_SHIFT);
+                st_meta(p.tbl.t + (size_t)(base + k) * St + qslot + part, tacc);
+            }
+        }
+    }
+    return true;
 }
 
 }  // namespace cb

@@ -169,6 +169,16 @@ __global__ void __launch_bounds__(Cfg<L>::TPB, 1) trans_kernel(TransParams p) {
     CB_KERNEL_PROLOGUE(p.n)
     trans_thread<L>(p, idx, S0, S1);
 }
+template <int L>
+__global__ void __launch_bounds__(Cfg<L>::TPB, 1) radius_kernel(RadiusParams p) {
+    CB_KERNEL_PROLOGUE(p.batch)
+    radius_thread<L>(p, idx, S0, S1);
+}
+template <int L>
+__global__ void __launch_bounds__(Cfg<L>::TPB, 1) truncation_kernel(TruncParams p) {
+    CB_KERNEL_PROLOGUE(p.batch)
+    truncation_thread<L>(p, idx, S0, S1);
+}
 #ifndef CB_HORNER_SYNC
 #define CB_HORNER_SYNC 1
 #endif
@@ -216,7 +226,7 @@ __global__ void __launch_bounds__(Cfg<L>::TPB, 1) ew_kernel(EwParams p) {
 template <int L>
 __global__ void __launch_bounds__(Cfg<L>::TPB, 1) fuchs_table_kernel(FuchsTableParams p) {
     CB_KERNEL_PROLOGUE(p.nrows * p.ninst)
-    fuchs_table_thread<L>(p, idx, S0, S1);
+    fuchs_table_fast_thread<L>(p, idx, S0, S1);
 }
 template <int L, int TPB, bool RR = false, bool SYNC = false, bool PI = false>
 __global__ void __launch_bounds__(TPB, 1) fuchs_shared_kernel(FuchsSharedParams p) {
@@ -518,6 +528,8 @@ struct LaunchTable {
     int (*apply)(const ApplyParams&, cudaStream_t);
     int (*ode_shift)(const ShiftParams&, cudaStream_t);
     int (*taylor_shift)(const TShiftParams&, cudaStream_t);
+    int (*radius)(const RadiusParams&, cudaStream_t);
+    int (*truncation)(const TruncParams&, cudaStream_t);
 };
 
 #define CB_DEFINE_LAUNCH_TABLE(LL)                                                                         \
@@ -581,6 +593,8 @@ struct LaunchTable {
     static int eval_##LL(const EvalParams& p, cudaStream_t s) { return launch<LL>(evaluate_kernel<LL>, p, p.npts, s); } \
     static int trans_##LL(const TransParams& p, cudaStream_t s) { return launch<LL>(trans_kernel<LL>, p, p.n, s); } \
     static int apply_##LL(const ApplyParams& p, cudaStream_t s) { return launch<LL>(apply_kernel<LL>, p, p.batch, s); } \
+    static int radius_##LL(const RadiusParams& p, cudaStream_t s) { return launch<LL>(radius_kernel<LL>, p, p.batch, s); } \
+    static int trunc_##LL(const TruncParams& p, cudaStream_t s) { return launch<LL>(truncation_kernel<LL>, p, p.batch, s); } \
     static int oshift_##LL(const ShiftParams& p, cudaStream_t s) { return launch<LL>(ode_shift_kernel<LL>, p, p.batch, s); } \
     static int tshift_##LL(const TShiftParams& p, cudaStream_t s) {                                        \
         if (p.batch <= 0 || p.len <= 1) return 0;                                                          \
@@ -592,7 +606,7 @@ struct LaunchTable {
     }                                                                                                      \
     extern const LaunchTable launch_table_L##LL = {frob_##LL, horner_##LL, ew_##LL, ftab_##LL, fsh_##LL, fint_##LL, \
                                                    frobg_##LL, solop_##LL, indp_##LL, eval_##LL, trans_##LL, apply_##LL, \
-                                                   oshift_##LL, tshift_##LL}; \
+                                                   oshift_##LL, tshift_##LL, radius_##LL, trunc_##LL}; \
     }
 
 extern const LaunchTable launch_table_L4, launch_table_L32, launch_table_L64, launch_table_L128;

@@ -278,6 +278,27 @@ struct FuchsTableParams {
     int64_t tbl_row0;  // table row stored at entry 0 (0 for the whole-solve table; the range start for a range table)
 };
 
+// what follows the multipliers of a table row: the divisor's kind, the inverse of a complex divisor, the
+// trailing-zero hints of every slot (slots 0 .. cnt hold the multipliers and the divisor)
+template <int L, class SCR>
+CB_HD void fuchs_table_tail(const FuchsTableParams& p, int64_t idx, int64_t row, int64_t inst, int64_t base, size_t qslot,
+                            int cnt, bool hints_done, SCR S0, SCR S1) {
+    const int W = p.degree - p.valuation;
+    CRef scratch = at<L>(p.tmp, 1, 2 * (size_t)idx);
+    CRef t2 = at<L>(p.tbl, base + cnt, qslot);
+    Meta dim = ld_meta(t2.t + 1);
+    int32_t* kind = p.kind + (row - p.tbl_row0) * p.ninst + inst;
+    if (is_exact_zero(dim)) {
+        *kind = 0;
+    } else {
+        *kind = 1;
+        acb_inv<L>(at<L>(p.tbl, base + W + 1, qslot), t2, scratch, S0, S1);
+        acb_mark_tz<L>(at<L>(p.tbl, base + W + 1, qslot));
+    }
+    if (!hints_done)
+        for (int s = 0; s <= cnt; s++) acb_mark_tz<L>(at<L>(p.tbl, base + s, qslot));
+}
+
 // one thread per (table row, instance): idx = (row - row0) * ninst + instance
 template <int L, class SCR>
 CB_HD void fuchs_table_thread(const FuchsTableParams& p, int64_t idx, SCR S0, SCR S1) {
@@ -286,7 +307,7 @@ CB_HD void fuchs_table_thread(const FuchsTableParams& p, int64_t idx, SCR S0, SC
     const size_t oslot = (p.ode.S == 2) ? 0 : 2 * (size_t)inst, qslot = (p.tbl.S == 2) ? 0 : 2 * (size_t)inst;
     const int64_t bmax = row - v;
     const size_t tslot = 2 * (size_t)idx;
-    CRef t1 = at<L>(p.tmp, 0, tslot), scratch = at<L>(p.tmp, 1, tslot);
+    CRef t1 = at<L>(p.tmp, 0, tslot);
     int64_t e = bmax + v;
     int64_t bmin = clampi(e - p.degree, 0, bmax);
     int64_t base = (row - p.tbl_row0) * (W + 2);
@@ -313,16 +334,7 @@ CB_HD void fuchs_table_thread(const FuchsTableParams& p, int64_t idx, SCR S0, SC
         for (int64_t q = 0; q < imin; q++) fac *= (b - imin + 1 + q);
         acb_mul_si<L>(t2, t2, fac, S0);
     } while (b != bmax);
-    Meta dim = ld_meta(t2.t + 1);
-    int32_t* kind = p.kind + (row - p.tbl_row0) * p.ninst + inst;
-    if (is_exact_zero(dim)) {
-        *kind = 0;
-    } else {
-        *kind = 1;
-        acb_inv<L>(at<L>(p.tbl, base + W + 1, qslot), t2, scratch, S0, S1);
-        acb_mark_tz<L>(at<L>(p.tbl, base + W + 1, qslot));
-    }
-    for (int s = 0; s <= k; s++) acb_mark_tz<L>(at<L>(p.tbl, base + s, qslot));
+    fuchs_table_tail<L>(p, idx, row, inst, base, qslot, k, false, S0, S1);
 }
 
 struct FuchsSharedParams {
@@ -611,6 +623,23 @@ CB_HD void fuchs_intop_thread(const FuchsIntParams& p, int64_t inst, SCR S0, SCR
 }  // namespace cb
 #include "cb_intop.cuh"
 namespace cb {
+
+// a table row with the register fast path for its multipliers (<= 1024 bits), the general thread otherwise
+template <int L, class SCR>
+CB_HD void fuchs_table_fast_thread(const FuchsTableParams& p, int64_t idx, SCR S0, SCR S1) {
+    if constexpr (L <= 32) {
+        const int v = p.valuation, W = p.degree - v;
+        const int64_t inst = idx % p.ninst, row = p.row0 + idx / p.ninst;
+        const size_t oslot = (p.ode.S == 2) ? 0 : 2 * (size_t)inst, qslot = (p.tbl.S == 2) ? 0 : 2 * (size_t)inst;
+        const int64_t base = (row - p.tbl_row0) * (W + 2);
+        int cnt = 0;
+        if (fuchs_table_fast_multipliers<L>(p, row, oslot, qslot, base, &cnt)) {
+            fuchs_table_tail<L>(p, idx, row, inst, base, qslot, cnt, true, S0, S1);
+            return;
+        }
+    }
+    fuchs_table_thread<L>(p, idx, S0, S1);
+}
 
 // ================================================================ Frobenius (M = 1)
 struct FrobParams {

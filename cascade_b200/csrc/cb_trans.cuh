@@ -348,6 +348,243 @@ CB_HD void trans_thread(const TransParams& p, int64_t i, SCR S0, SCR S1) {
     else acb_log<L>(z, x, T, S0, S1);
 }
 
+// ---------------------------------------------------------------- radius_of_convergence / truncation_order
+// reference src/fuchs_solver.c:3-94, for a batch, on the device ball type: a RIGOROUS enclosure (every step a ball
+// operation), operation for operation the algorithm stated in oracle/cbo_trans.c (cbo_radius_of_convergence,
+// cbo_truncation_order) -- Graeffe iterations on the reversed leading polynomial with an exact power-of-two rescaling
+// after every step (as many of the n requested as the 32-bit exponent range allows: n_done), the sum form of
+// Fujiwara's root bound, its 2^n_done-th root inverted, and the sharpness (2 m^2 + 1)^(1/2^n_done) - 1 of the bound as
+// the error bar.  One thread per operator.
+constexpr int RADIUS_MAXLEN = 40;
+constexpr int32_t RADIUS_EXP_GUARD = 1 << 24;
+constexpr int RADIUS_NTMP = 14;  // t, tc, w, U, l, v, S, R, X, one, E, inv, kb + 1 spare
+struct RadiusParams {
+    int order, degree;
+    int64_t batch, n;
+    CArr ode;      // S = 2*batch or 2
+    CArr out;      // 1 entry, S = 2*batch
+    CArr wp;       // 2 * (degree + 1) + RADIUS_NTMP + TRANS_NTMP entries, S = 2*batch
+    int32_t* n_done;  // [batch]
+};
+// z.re = the exact ball of a 30-bit upper bound of |x.re|; z.im = 0
+template <int L>
+CB_HD void acb_upper_ball_re(const CRef& z, const CRef& x) {
+    Meta t = ld_meta(x.t);
+    acb_zero<L>(z);
+    if (is_nan(t)) {
+        acb_set_nan<L>(z);
+        return;
+    }
+    Mag u = mag_add(mag_mid_upper(t, x.m[(size_t)(L - 1) * x.stride]), mag_of(t));
+    if (u.man == 0) return;
+    z.m[(size_t)(L - 1) * z.stride] = u.man << 2;
+    st_meta(z.t, Meta{u.exp, 0u, 0u, 0});
+}
+template <int L>
+CB_HD void acb_set_si_exact(const CRef& z, int64_t k) {
+    acb_zero<L>(z);
+    if (k == 0) return;
+    uint64_t ka = k < 0 ? (uint64_t)0 - (uint64_t)k : (uint64_t)k;
+    int sh = clz64(ka);
+    uint64_t kn = ka << sh;
+    z.m[(size_t)(L - 1) * z.stride] = (uint32_t)(kn >> 32);
+    z.m[(size_t)(L - 2) * z.stride] = (uint32_t)kn;
+    st_meta(z.t, Meta{64 - sh, k < 0 ? F_SIGN : 0u, 0u, 0});
+}
+CB_HD bool radius_part_ok(const Meta& t) {
+    if (is_nan(t)) return false;
+    if (!is_zero_mid(t) && (t.exp > RADIUS_EXP_GUARD || t.exp < -RADIUS_EXP_GUARD)) return false;
+    if (t.rman && (t.rexp > RADIUS_EXP_GUARD || t.rexp < -2 * RADIUS_EXP_GUARD)) return false;
+    return true;
+}
+template <int L, class SCR>
+CB_HD void radius_thread(const RadiusParams& p, int64_t inst, SCR S0, SCR S1) {
+    const size_t slot = 2 * (size_t)inst, oslot = (p.ode.S == 2) ? 0 : slot;
+    const int D1 = p.degree + 1;
+    CRef out = at<L>(p.out, 0, slot);
+    int low = -1, top = -1;
+    for (int i = 0; i <= p.degree; i++)
+        if (!acb_is_exact_zero(at<L>(p.ode, p.order * D1 + i, oslot))) {
+            if (low < 0) low = i;
+            top = i;
+        }
+    if (low < 0 || top - low < 1 || top - low + 1 > RADIUS_MAXLEN) {
+        acb_set_nan<L>(out);
+        p.n_done[inst] = -1;
+        return;
+    }
+    const int m = top - low;
+    const int64_t tb = 2 * (int64_t)D1;
+    auto A = [&](int i) { return at<L>(p.wp, i, slot); };
+    auto G = [&](int i) { return at<L>(p.wp, D1 + i, slot); };
+    CRef t = at<L>(p.wp, tb + 0, slot), tc = at<L>(p.wp, tb + 1, slot), w = at<L>(p.wp, tb + 2, slot),
+         U = at<L>(p.wp, tb + 3, slot), l = at<L>(p.wp, tb + 4, slot), v = at<L>(p.wp, tb + 5, slot),
+         S = at<L>(p.wp, tb + 6, slot), R = at<L>(p.wp, tb + 7, slot), X = at<L>(p.wp, tb + 8, slot),
+         one = at<L>(p.wp, tb + 9, slot), E = at<L>(p.wp, tb + 10, slot), inv = at<L>(p.wp, tb + 11, slot),
+         kb = at<L>(p.wp, tb + 12, slot);
+    CRef T[TRANS_NTMP];
+    for (int i = 0; i < TRANS_NTMP; i++) T[i] = at<L>(p.wp, tb + RADIUS_NTMP + i, slot);
+    for (int i = 0; i <= m; i++) acb_set<L>(A(i), at<L>(p.ode, p.order * D1 + (top - i), oslot));
+    int64_t n_done = 0;
+#pragma unroll 1
+    for (int64_t it = 0; it < p.n; it++) {
+        bool ok = true;
+        for (int i = 0; i <= m && ok; i++) ok = radius_part_ok(ld_meta(A(i).t)) && radius_part_ok(ld_meta(A(i).t + 1));
+        if (!ok) break;
+        const int ne = m / 2 + 1, no = (m + 1) / 2;
+        for (int j = 0; j <= m; j++) acb_zero<L>(G(j));
+#pragma unroll 1
+        for (int i = 0; i < ne; i++)
+#pragma unroll 1
+            for (int k = 0; k < ne; k++) {
+                acb_mul<L>(t, A(2 * i), A(2 * k), S0, S1);
+                acb_addsub<L>(G(i + k), G(i + k), t, false, S0, S1);
+            }
+#pragma unroll 1
+        for (int i = 0; i < no; i++)
+#pragma unroll 1
+            for (int k = 0; k < no; k++) {
+                acb_mul<L>(t, A(2 * i + 1), A(2 * k + 1), S0, S1);
+                acb_addsub<L>(G(i + k + 1), G(i + k + 1), t, true, S0, S1);
+            }
+        CRef gm = G(m);
+        if (acb_bound_exp(gm) == TR_BIG || acb_contains_zero<L>(gm)) break;
+        Meta gr = ld_meta(gm.t), gi = ld_meta(gm.t + 1);
+        int64_t e0 = -TR_BIG;
+        if (!is_zero_mid(gr)) e0 = gr.exp;
+        if (!is_zero_mid(gi) && gi.exp > e0) e0 = gi.exp;
+        for (int j = 0; j <= m; j++) {
+            acb_set<L>(A(j), G(j));
+            acb_mul_2exp(A(j), -e0);
+        }
+        n_done++;
+    }
+    p.n_done[inst] = -1;
+    if (acb_bound_exp(A(m)) == TR_BIG || acb_contains_zero<L>(A(m))) {
+        acb_set_nan<L>(out);
+        return;
+    }
+    acb_zero<L>(S);
+#pragma unroll 1
+    for (int k = 1; k <= m; k++) {
+        if (acb_is_exact_zero(A(m - k))) continue;
+        acb_div<L>(t, A(m - k), A(m), inv, S0, S1);
+        if (k == m) acb_mul_2exp(t, -1);
+        acb_set<L>(tc, t);
+        {   // conj(t)
+            Meta ti = ld_meta(tc.t + 1);
+            if (!(ti.flags & (F_ZERO | F_NAN))) {
+                ti.flags ^= F_SIGN;
+                st_meta(tc.t + 1, ti);
+            }
+        }
+        acb_mul<L>(w, t, tc, S0, S1);
+        acb_upper_ball_re<L>(U, w);
+        if (is_zero_mid(ld_meta(U.t)) && !is_nan(ld_meta(U.t))) continue;
+        acb_log<L>(l, U, T, S0, S1);
+        acb_div_si<L>(l, l, 2 * (int64_t)k, S0);
+        acb_exp<L>(v, l, T, S0, S1);
+        acb_addsub<L>(S, S, v, false, S0, S1);
+    }
+    acb_mul_2exp(S, 1);
+    acb_upper_ball_re<L>(U, S);
+    if (acb_bound_exp(U) == TR_BIG || is_zero_mid(ld_meta(U.t))) {
+        acb_set_nan<L>(out);
+        return;
+    }
+    acb_log<L>(l, U, T, S0, S1);
+    acb_mul_2exp(l, -n_done);
+    acb_exp<L>(R, l, T, S0, S1);
+    acb_one<L>(one);
+    acb_div<L>(X, one, R, inv, S0, S1);
+    acb_set_si_exact<L>(w, 2 * (int64_t)m * m + 1);
+    acb_log<L>(l, w, T, S0, S1);
+    acb_mul_2exp(l, -n_done);
+    acb_exp<L>(E, l, T, S0, S1);
+    acb_add_si<L>(E, E, -1, kb, S0, S1);
+    acb_mul<L>(w, X, E, S0, S1);
+    if (acb_bound_exp(X) == TR_BIG || acb_bound_exp(w) == TR_BIG) {
+        acb_set_nan<L>(out);
+        return;
+    }
+    acb_set<L>(out, X);
+    {   // arb_add_error: the radius grows by a 30-bit upper bound of |w.re|; the imaginary part is an exact zero
+        Meta to = ld_meta(out.t), tw = ld_meta(w.t);
+        Mag r = mag_add(mag_of(to), mag_add(mag_mid_upper(tw, w.m[(size_t)(L - 1) * w.stride]), mag_of(tw)));
+        to.rman = r.man;
+        to.rexp = r.man ? r.exp : 0;
+        st_meta(out.t, to);
+        store_nan<L>(wim(out));
+        st_meta(out.t + 1, meta_zero());
+    }
+    p.n_done[inst] = (int32_t)n_done;
+}
+
+struct TruncParams {
+    int64_t batch, bits;
+    CArr eta, alpha;  // 1 entry each, S = 2*batch (real balls: the imaginary parts are ignored as in the reference)
+    CArr nball;       // 1 entry, S = 2*batch: the ball N
+    CArr wp;          // 8 + TRANS_NTMP entries
+    int64_t* n_out;   // [batch]
+};
+template <int L, class SCR>
+CB_HD void truncation_thread(const TruncParams& p, int64_t inst, SCR S0, SCR S1) {
+    const size_t slot = 2 * (size_t)inst;
+    CRef eta = at<L>(p.eta, 0, slot), alpha = at<L>(p.alpha, 0, slot), N = at<L>(p.nball, 0, slot);
+    CRef r = at<L>(p.wp, 0, slot), tmp = at<L>(p.wp, 1, slot), one = at<L>(p.wp, 2, slot), two = at<L>(p.wp, 3, slot),
+         inv = at<L>(p.wp, 4, slot), U = at<L>(p.wp, 5, slot), q = at<L>(p.wp, 6, slot), lg = at<L>(p.wp, 7, slot);
+    CRef T[TRANS_NTMP];
+    for (int i = 0; i < TRANS_NTMP; i++) T[i] = at<L>(p.wp, 8 + i, slot);
+    acb_set_nan<L>(N);
+    if (acb_bound_exp(eta) == TR_BIG || acb_bound_exp(alpha) == TR_BIG) {
+        p.n_out[inst] = 2 * p.bits;
+        return;
+    }
+    acb_addsub<L>(tmp, alpha, eta, true, S0, S1);
+    {
+        Meta t = ld_meta(tmp.t);
+        if ((t.flags & (F_ZERO | F_SIGN)) || arb_contains_zero<L>(tmp.m, tmp.stride, t)) {
+            p.n_out[inst] = 0;
+            return;
+        }
+    }
+    acb_addsub<L>(r, eta, alpha, false, S0, S1);
+    acb_mul_2exp(r, -1);
+    acb_div<L>(q, eta, r, inv, S0, S1);  // r = eta / r
+    acb_one<L>(one);
+    acb_addsub<L>(tmp, one, q, true, S0, S1);
+    acb_log<L>(N, tmp, T, S0, S1);
+    acb_set_si_exact<L>(two, 2);
+    acb_log<L>(tmp, two, T, S0, S1);
+    acb_mul_si<L>(lg, tmp, p.bits, S0);
+    acb_addsub<L>(N, N, lg, true, S0, S1);
+    acb_log<L>(tmp, q, T, S0, S1);
+    acb_div<L>(r, N, tmp, inv, S0, S1);
+    acb_set<L>(N, r);
+    if (acb_bound_exp(N) == TR_BIG) {
+        p.n_out[inst] = 2 * p.bits;
+        return;
+    }
+    acb_upper_ball_re<L>(U, N);
+    Meta tu = ld_meta(U.t), tn = ld_meta(N.t);
+    if (is_zero_mid(tu) || (tn.flags & F_SIGN)) {
+        p.n_out[inst] = 0;
+        return;
+    }
+    if (tu.exp > 62) {
+        p.n_out[inst] = 2 * p.bits;
+        return;
+    }
+    if (tu.exp <= 0) {
+        p.n_out[inst] = 1;
+        return;
+    }
+    uint64_t topw = ((uint64_t)U.m[(size_t)(L - 1) * U.stride] << 32) | U.m[(size_t)(L - 2) * U.stride];
+    uint64_t ip = topw >> (64 - tu.exp);
+    bool frac = (topw << tu.exp) != 0;  // (the upper ball has a 30-bit mantissa: nothing below the top limb)
+    p.n_out[inst] = (int64_t)ip + (frac ? 1 : 0);
+}
+
 // ---------------------------------------------------------------- residual check on the device
 // acb_ode_apply / acb_ode_solves (reference src/acb_ode.c:185-240), the reference's own acceptance test
 // for both solvers, for a batch: out = sum_i p_i * in^(i) truncated to out_len coefficients, and

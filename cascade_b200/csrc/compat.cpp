@@ -690,74 +690,39 @@ void acb_mat_clear(acb_mat_t m) {
     free(m->rows);
 }
 
-// min |root| of the polynomial sum_k c[k] z^k (c[0] != 0, c[n] != 0), Durand-Kerner in complex long double
-static long double min_root_modulus(const long double* cr, const long double* ci, int n) {
-    struct Z { long double r, i; };
-    auto mul = [](Z a, Z b) { return Z{a.r * b.r - a.i * b.i, a.r * b.i + a.i * b.r}; };
-    auto divz = [](Z a, Z b) { long double d = b.r * b.r + b.i * b.i; return Z{(a.r * b.r + a.i * b.i) / d, (a.i * b.r - a.r * b.i) / d}; };
-    std::vector<Z> z(n);
-    long double scale = 0;
-    for (int k = 0; k <= n; k++) scale = fmaxl(scale, hypotl(cr[k], ci[k]));
-    long double R = 1 + scale / hypotl(cr[n], ci[n]);  // Cauchy bound
-    for (int k = 0; k < n; k++) z[k] = Z{0.5L * R * cosl(0.7L + 2.0L * 3.14159265358979323846L * k / n), 0.5L * R * sinl(0.7L + 2.0L * 3.14159265358979323846L * k / n)};
-    for (int it = 0; it < 500; it++) {
-        long double move = 0;
-        for (int k = 0; k < n; k++) {
-            Z p{cr[n], ci[n]};
-            for (int j = n - 1; j >= 0; j--) { p = mul(p, z[k]); p.r += cr[j]; p.i += ci[j]; }
-            Z q{cr[n], ci[n]};
-            for (int j = 0; j < n; j++) if (j != k) q = mul(q, Z{z[k].r - z[j].r, z[k].i - z[j].i});
-            if (q.r == 0 && q.i == 0) { z[k].r += 1e-9L; continue; }
-            Z d = divz(p, q);
-            z[k].r -= d.r;
-            z[k].i -= d.i;
-            move = fmaxl(move, hypotl(d.r, d.i));
-        }
-        if (move < 1e-17L * R) break;
-    }
-    long double m = INFINITY;
-    for (int k = 0; k < n; k++) m = fminl(m, hypotl(z[k].r, z[k].i));
-    return m;
-}
-
 void radius_of_convergence(arb_t rad_of_conv, acb_ode_t ODE, slong n, slong bits) {
-    (void)n;
-    (void)bits;
-    // the leading polynomial without its factor z^i (reference :11-15: a singularity at zero does not count)
-    slong ord = ODE->order, deg = ODE->degree, low = -1;
-    for (slong i = deg; i >= 0; i--)
-        if (!acb_is_zero(acb_ode_coeff(ODE, ord, i))) low = i;
-    slong top = -1;
-    for (slong i = 0; i <= deg; i++)
-        if (!acb_is_zero(acb_ode_coeff(ODE, ord, i))) top = i;
-    if (low < 0 || top - low < 1) {  // no singularities away from zero: indeterminate (reference :17-22)
-        memset(rad_of_conv, 0, sizeof(arb_struct));
-        rad_of_conv->meta.flags = CB_FLAG_NAN;
-        rad_of_conv->meta.rman = CB_MAG_INF_MAN;
-        return;
-    }
-    int m = (int)(top - low);
-    std::vector<long double> cr(m + 1), ci(m + 1);
-    for (int k = 0; k <= m; k++) {
-        cr[k] = acb_get_mid_re_d(acb_ode_coeff(ODE, ord, low + k));
-        ci[k] = acb_get_mid_im_d(acb_ode_coeff(ODE, ord, low + k));
-    }
-    double r = (double)min_root_modulus(cr.data(), ci.data(), m);
-    // a lower estimate with a visible error bar (2^-30 relative), as the reference's enclosure has
-    arb_set_double(rad_of_conv, r * (1.0 - ldexp(1.0, -30)));
-    int e;
-    frexp(r, &e);
-    rad_of_conv->meta.rman = 1u << 29;
-    rad_of_conv->meta.rexp = e - 30 + 1;
+    // reference src/fuchs_solver.c:3-54, rigorous on the device ball type (cb200_radius_of_convergence_host: Graeffe
+    // iterations, Fujiwara's bound in its sum form, the sharpness of the bound as the error bar)
+    int L = limbs_of(bits);
+    slong ne = (ODE->order + 1) * (ODE->degree + 1);
+    HostArr ho(L, ne, 2), hr(L, 1, 2);
+    for (slong e = 0; e < ne; e++) ho.put(e, 0, ODE->polys + e);
+    int32_t n_done = 0;
+    int rc = cb200_radius_of_convergence_host(L, (int)ODE->order, (int)ODE->degree, 1, ho.m.data(), ho.t.data(), 1, n,
+                                              hr.m.data(), hr.t.data(), &n_done, 0);
+    if (rc) die("radius_of_convergence (cb200_radius_of_convergence_host)", rc);
+    acb_t z;
+    hr.get(0, 0, z);
+    *rad_of_conv = z->real;
 }
 
-slong truncation_order(arb_t eta, arb_t alpha, slong bits) {  // reference :56-94
-    if (!arb_is_finite(eta) || !arb_is_finite(alpha)) return 2 * bits;
-    long double e = arb_mid_d(eta), a = arb_mid_d(alpha);
-    if (!(e + arb_rad_d(eta) < a - arb_rad_d(alpha))) return 0;
-    long double r = e / ((e + a) / 2);
-    long double N = (logl(1 - r) - (long double)bits * logl(2.0L)) / logl(r);
-    return (slong)ceill(N);
+slong truncation_order(arb_t eta, arb_t alpha, slong bits) {  // reference :56-94, on the device ball type
+    int L = limbs_of(bits);
+    HostArr he(L, 1, 2), ha(L, 1, 2), hn(L, 1, 2);
+    acb_t e, a;
+    memset(e, 0, sizeof(acb_t));
+    memset(a, 0, sizeof(acb_t));
+    e->real = *eta;
+    e->imag.meta.flags = CB_FLAG_ZERO;
+    a->real = *alpha;
+    a->imag.meta.flags = CB_FLAG_ZERO;
+    he.put(0, 0, e);
+    ha.put(0, 0, a);
+    int64_t n = 0;
+    int rc = cb200_truncation_order_host(L, 1, he.m.data(), he.t.data(), ha.m.data(), ha.t.data(), bits, hn.m.data(),
+                                         hn.t.data(), &n, 0);
+    if (rc) die("truncation_order (cb200_truncation_order_host)", rc);
+    return (slong)n;
 }
 
 void find_monodromy_matrix(acb_mat_t mono, acb_ode_t ODE, slong bits) {

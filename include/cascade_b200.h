@@ -262,6 +262,32 @@ int cb200_horner_batch_host(int L, int64_t len, int64_t npts, int nder, const ui
                             const cb_meta *pts_meta, uint32_t *out_mant, cb_meta *out_meta,
                             int device);
 
+/* ---- radius_of_convergence (reference src/fuchs_solver.c:3-54) for a batch of operators, RIGOROUS on the device
+ * ball type: n Graeffe iterations on the reversed leading polynomial (rescaled by a power of two after every step; as
+ * many of the n requested as the 32-bit exponent range allows -- n_done[i] <= n of them, -1 when the operator has no
+ * singularity away from zero and the ball is indeterminate, :17-22), the sum form of Fujiwara's root bound, its
+ * 2^n_done-th root inverted; the sharpness of the bound gives the error bar, so the ball CONTAINS the distance of the
+ * nearest nonzero root of the leading coefficient.  out : 1 entry, S = 2*batch (imaginary parts exact zeros). */
+size_t cb200_radius_workspace_bytes(int L, int degree, int64_t batch);
+int cb200_radius_of_convergence_dev(int L, int order, int degree, int64_t batch, const uint32_t *ode_mant,
+                                    const cb_meta *ode_meta, int shared_ode, int64_t n, uint32_t *out_mant,
+                                    cb_meta *out_meta, int32_t *n_done, void *workspace, size_t workspace_bytes,
+                                    void *stream);
+int cb200_radius_of_convergence_host(int L, int order, int degree, int64_t batch, const uint32_t *ode_mant,
+                                     const cb_meta *ode_meta, int shared_ode, int64_t n, uint32_t *out_mant,
+                                     cb_meta *out_meta, int32_t *n_done, int device);
+/* ---- truncation_order (reference src/fuchs_solver.c:56-94) for a batch of (eta, alpha) pairs: the ball
+ * N = (log(1 - r) - bits log 2) / log r, r = eta / ((eta + alpha) / 2), and n_out[i] = ceil of its upper end (2*bits for
+ * non-finite input, 0 when eta < alpha cannot be shown -- the reference's early returns).  eta, alpha, n: 1 entry each,
+ * S = 2*batch (real parts used). */
+size_t cb200_truncation_workspace_bytes(int L, int64_t batch);
+int cb200_truncation_order_dev(int L, int64_t batch, const uint32_t *eta_mant, const cb_meta *eta_meta,
+                               const uint32_t *alpha_mant, const cb_meta *alpha_meta, int64_t bits, uint32_t *n_mant,
+                               cb_meta *n_meta, int64_t *n_out, void *workspace, size_t workspace_bytes, void *stream);
+int cb200_truncation_order_host(int L, int64_t batch, const uint32_t *eta_mant, const cb_meta *eta_meta,
+                                const uint32_t *alpha_mant, const cb_meta *alpha_meta, int64_t bits, uint32_t *n_mant,
+                                cb_meta *n_meta, int64_t *n_out, int device);
+
 /* ---- acb_ode_shift (reference src/acb_ode.c:124-135) for a batch: out = in with every row p_i(z) replaced by
  * p_i(z + a), by the Horner Taylor shift p[j] += p[j+1]*a, in ONE launch (one thread per operator).
  * ode : (order+1)(degree+1) entries, S = 2*batch, or S = 2 (shared_ode: one operator moved to `batch` points).

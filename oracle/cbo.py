@@ -53,6 +53,8 @@ def lib(plain: bool = False) -> C.CDLL:
     L.cbo_continuation_series_flat.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, _u32p, _i32p,
                                                _u32p, _i32p, _u32p, _i32p, _u32p, _i32p]
     L.cbo_taylor_shift_flat.argtypes = [C.c_int, C.c_int64, C.c_int64, _u32p, _i32p, _u32p, _i32p, C.c_int]
+    L.cbo_radius_flat.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, _u32p, _i32p, C.c_int64, _u32p, _i32p, _i32p]
+    L.cbo_truncation_flat.argtypes = [C.c_int, C.c_int64, _u32p, _i32p, _u32p, _i32p, C.c_int64, _u32p, _i32p, _i64p]
     L.cbo_example_flat.argtypes = [C.c_int, C.c_int, C.c_uint64, _u32p, _i32p, _u32p, _i32p]
     L.cbo_ode_apply_flat.argtypes = [C.c_int, C.c_int, C.c_int, _u32p, _i32p, _u32p, _i32p, C.c_int64, _u32p, _i32p]
     L.cbo_ew_trans.argtypes = [C.c_int, C.c_int, C.c_int64, _u32p, _i32p, _u32p, _i32p]
@@ -184,6 +186,26 @@ def taylor_shift(f: Balls, a: Balls, batch: int, plain: bool = False) -> Balls:
                                           int(a.n_slots == 2))
     assert rc == 0
     return out
+
+
+def radius_of_convergence(order: int, degree: int, ode: Balls, batch: int, n: int, shared: bool = False, plain: bool = False):
+    """radius_of_convergence (reference src/fuchs_solver.c:3-54) for ``batch`` operators: returns (balls[batch] with a
+    zero imaginary part, n_done int32[batch]; n_done = -1: no singularity away from zero, ball indeterminate)."""
+    out = Balls.zeros(2 * batch, ode.L)
+    nd = np.zeros(batch, np.int32)
+    rc = lib(plain).cbo_radius_flat(ode.L, order, degree, batch, int(shared), ode.mant, ode.meta, n, out.mant, out.meta, nd)
+    assert rc == 0
+    return out, nd
+
+
+def truncation_order(eta: Balls, alpha: Balls, bits: int, plain: bool = False):
+    """truncation_order (reference src/fuchs_solver.c:56-94) for a batch of (eta, alpha): returns (N balls, counts)."""
+    batch = eta.n_slots // 2
+    nb = Balls.zeros(2 * batch, eta.L)
+    out = np.zeros(batch, np.int64)
+    rc = lib(plain).cbo_truncation_flat(eta.L, batch, eta.mant, eta.meta, alpha.mant, alpha.meta, bits, nb.mant, nb.meta, out)
+    assert rc == 0
+    return nb, out
 
 
 def frobenius1_rhs_batch(order: int, degree: int, n: int, ode: Balls, rho: Balls, rhs: Balls, batch: int,

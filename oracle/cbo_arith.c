@@ -770,6 +770,28 @@ void cbo_arb_add_error_2exp(cbo_arb *z, int64_t e) {
     u.exp = e + 1;
     set_rad(z, mg_add(mg_of(z), u));
 }
+/* z = the exact ball of a 30-bit upper bound of |x| (|mid| rounded up to 30 bits, plus the radius) */
+void cbo_arb_upper_ball(cbo_arb *z, const cbo_arb *x, int L) {
+    if (is_nan(x)) {
+        arb_set_nan(z);
+        return;
+    }
+    mg u = mg_add(mg_mid_upper(x, L), mg_of(x));
+    cbo_arb_zero(z);
+    if (u.man == 0) return;
+    z->m.w[L - 1] = u.man << 2;
+    z->exp = u.exp;
+    z->flags = 0;
+}
+/* z.rad += a 30-bit upper bound of |err| (arb_add_error) */
+void cbo_arb_add_error_arb(cbo_arb *z, const cbo_arb *err, int L) {
+    if (is_nan(z)) return;
+    if (is_nan(err)) {
+        arb_set_nan(z);
+        return;
+    }
+    set_rad(z, mg_add(mg_of(z), mg_add(mg_mid_upper(err, L), mg_of(err))));
+}
 /* z *= 2^k, exact */
 void cbo_arb_mul_2exp(cbo_arb *z, int64_t k) {
     if (is_nan(z)) return;

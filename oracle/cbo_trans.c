@@ -311,6 +311,194 @@ int cbo_solution_evaluate_flat(int L, int64_t M, int64_t cap, int64_t npts, cons
     return 0;
 }
 
+/* ---------------------------------------------------------------- radius_of_convergence / truncation_order
+ * reference src/fuchs_solver.c:3-54: Graeffe iterations on the reversed leading polynomial, a root bound, its
+ * 2^n-th root inverted, and the sharpness of the bound as the error bar.  Restated on this ball type with two stated
+ * differences (Arb's versions of the same steps are unpinned anyway): (1) after every Graeffe step the polynomial
+ * is rescaled by a power of two (exact; roots unchanged) and the iteration stops early when an exponent would
+ * leave the 32-bit range of the ball type -- n_done <= n iterations are performed and used in the formulas; (2) the
+ * root bound is the SUM form of Fujiwara's bound, B = 2 sum_k |a_{m-k}/a_m|^(1/k) (the last term halved inside the
+ * root), which satisfies M <= B <= 2 m^2 M for the largest root modulus M, so that the true radius lies in
+ * [X, X (2 m^2 + 1)^(1/2^n_done)] with X = B^(-1/2^n_done).  Every step is a ball operation: the result is a rigorous
+ * enclosure.  Returns n_done, or -1 (out indeterminate) when there is no singularity away from zero (:17-22). */
+void cbo_arb_upper_ball(cbo_arb *z, const cbo_arb *x, int L);
+void cbo_arb_add_error_arb(cbo_arb *z, const cbo_arb *err, int L);
+#define RADIUS_MAXLEN 40
+#define RADIUS_EXP_GUARD (1 << 24)
+static int radius_exps_ok(const cbo_acb *a, int m) {
+    for (int i = 0; i <= m; i++) {
+        const cbo_arb *p[2] = {&a[i].re, &a[i].im};
+        for (int k = 0; k < 2; k++) {
+            if (p[k]->flags & CBO_NAN) return 0;
+            if (!(p[k]->flags & CBO_ZERO) && (p[k]->exp > RADIUS_EXP_GUARD || p[k]->exp < -RADIUS_EXP_GUARD)) return 0;
+            if (p[k]->rman && (p[k]->rexp > RADIUS_EXP_GUARD || p[k]->rexp < -2 * RADIUS_EXP_GUARD)) return 0;
+        }
+    }
+    return 1;
+}
+int cbo_radius_of_convergence(cbo_acb *out, cbo_ode *o, int64_t n, int L) {
+    int low = -1, top = -1;
+    for (int i = 0; i <= o->degree; i++)
+        if (!cbo_acb_is_zero(&o->polys[o->order * (o->degree + 1) + i])) {
+            if (low < 0) low = i;
+            top = i;
+        }
+    if (low < 0 || top - low < 1 || top - low + 1 > RADIUS_MAXLEN) {
+        acb_set_nan(out);
+        return -1;
+    }
+    const int m = top - low;
+    cbo_acb a[RADIUS_MAXLEN], g[RADIUS_MAXLEN], t;
+    for (int i = 0; i <= m; i++) a[i] = o->polys[o->order * (o->degree + 1) + (top - i)];
+    int64_t n_done = 0;
+    for (int64_t it = 0; it < n; it++) {
+        if (!radius_exps_ok(a, m)) break;
+        const int ne = m / 2 + 1, no = (m + 1) / 2;
+        for (int j = 0; j <= m; j++) cbo_acb_zero(&g[j]);
+        for (int i = 0; i < ne; i++)
+            for (int l = 0; l < ne; l++) {
+                cbo_acb_mul(&t, &a[2 * i], &a[2 * l], L);
+                cbo_acb_add(&g[i + l], &g[i + l], &t, L);
+            }
+        for (int i = 0; i < no; i++)
+            for (int l = 0; l < no; l++) {
+                cbo_acb_mul(&t, &a[2 * i + 1], &a[2 * l + 1], L);
+                cbo_acb_sub(&g[i + l + 1], &g[i + l + 1], &t, L);
+            }
+        if (!cbo_acb_is_finite(&g[m]) || cbo_acb_contains_zero(&g[m])) break;
+        int64_t e0 = -BIG;
+        if (!(g[m].re.flags & CBO_ZERO)) e0 = g[m].re.exp;
+        if (!(g[m].im.flags & CBO_ZERO) && g[m].im.exp > e0) e0 = g[m].im.exp;
+        for (int j = 0; j <= m; j++) {
+            a[j] = g[j];
+            acb_mul_2exp(&a[j], -e0);
+        }
+        n_done++;
+    }
+    if (!cbo_acb_is_finite(&a[m]) || cbo_acb_contains_zero(&a[m])) {
+        acb_set_nan(out);
+        return -1;
+    }
+    cbo_acb S, tc, w, U, l, v;
+    cbo_acb_zero(&S);
+    for (int k = 1; k <= m; k++) {
+        if (cbo_acb_is_zero(&a[m - k])) continue;
+        cbo_acb_div(&t, &a[m - k], &a[m], L);
+        if (k == m) acb_mul_2exp(&t, -1);
+        cbo_acb_neg(&tc, &t);
+        tc.re = t.re; /* conj(t): re kept, im negated */
+        cbo_acb_mul(&w, &t, &tc, L);
+        cbo_acb_zero(&U);
+        cbo_arb_upper_ball(&U.re, &w.re, L);
+        if (U.re.flags & CBO_ZERO) continue; /* the coefficient is (numerically) exactly zero */
+        cbo_acb_log(&l, &U, L);
+        acb_div_si(&l, &l, 2 * (int64_t)k, L);
+        cbo_acb_exp(&v, &l, L);
+        cbo_acb_add(&S, &S, &v, L);
+    }
+    acb_mul_2exp(&S, 1);
+    cbo_acb_zero(&U);
+    cbo_arb_upper_ball(&U.re, &S.re, L);
+    if (!cbo_acb_is_finite(&U) || (U.re.flags & CBO_ZERO)) {
+        acb_set_nan(out);
+        return -1;
+    }
+    cbo_acb R, X, one, E;
+    cbo_acb_log(&l, &U, L);
+    acb_mul_2exp(&l, -n_done);
+    cbo_acb_exp(&R, &l, L);
+    cbo_acb_one(&one, L);
+    cbo_acb_div(&X, &one, &R, L);
+    cbo_acb_set_si(&w, 2 * (int64_t)m * m + 1, L);
+    cbo_acb_log(&l, &w, L);
+    acb_mul_2exp(&l, -n_done);
+    cbo_acb_exp(&E, &l, L);
+    cbo_acb_add_si(&E, &E, -1, L);
+    cbo_acb_mul(&w, &X, &E, L);
+    *out = X;
+    cbo_arb_add_error_arb(&out->re, &w.re, L);
+    cbo_arb_zero(&out->im);
+    if (!cbo_acb_is_finite(&X) || !cbo_acb_is_finite(&w)) {
+        acb_set_nan(out);
+        return -1;
+    }
+    return (int)n_done;
+}
+/* truncation_order, reference src/fuchs_solver.c:56-94: N = (log(1 - r) - bits log 2) / log r with r = eta / ((eta +
+ * alpha) / 2), as a real ball; *nball receives it.  Returns ceil of its UPPER end (when the ball does not pin one
+ * integer the reference's arb_get_unique_fmpz gives up; taking the larger count is the safe reading), 2 bits for
+ * non-finite input, 0 when eta < alpha cannot be shown. */
+int64_t cbo_truncation_order(cbo_acb *nball, const cbo_acb *eta, const cbo_acb *alpha, int64_t bits, int L) {
+    cbo_acb r, N, tmp, one, two;
+    acb_set_nan(nball);
+    if (!cbo_acb_is_finite(eta) || !cbo_acb_is_finite(alpha)) return 2 * bits;
+    cbo_acb_sub(&tmp, alpha, eta, L); /* eta < alpha  <=>  alpha - eta is positive */
+    if ((tmp.re.flags & (CBO_ZERO | CBO_SIGN)) || cbo_arb_contains_zero(&tmp.re)) return 0;
+    cbo_acb_add(&r, eta, alpha, L);
+    acb_mul_2exp(&r, -1);
+    cbo_acb_div(&r, eta, &r, L);
+    cbo_acb_one(&one, L);
+    cbo_acb_sub(&tmp, &one, &r, L);
+    cbo_acb_log(&N, &tmp, L);
+    cbo_acb_set_si(&two, 2, L);
+    cbo_acb_log(&tmp, &two, L);
+    cbo_acb_mul_si(&tmp, &tmp, bits, L);
+    cbo_acb_sub(&N, &N, &tmp, L);
+    cbo_acb_log(&tmp, &r, L);
+    cbo_acb_div(&N, &N, &tmp, L);
+    *nball = N;
+    if (!cbo_acb_is_finite(&N)) return 2 * bits;
+    /* ceil of the upper end: the upper ball is exact, its integer part is read from the top limbs */
+    cbo_acb U;
+    cbo_acb_zero(&U);
+    cbo_arb_upper_ball(&U.re, &N.re, L);
+    if (U.re.flags & CBO_ZERO) return 0;
+    if (N.re.flags & CBO_SIGN) return 0; /* a negative count: nothing to add */
+    if (U.re.exp > 62) return 2 * bits;
+    if (U.re.exp <= 0) return 1;
+    uint64_t top = ((uint64_t)U.re.m.w[L - 1] << 32) | U.re.m.w[L - 2];
+    uint64_t ip = top >> (64 - U.re.exp);
+    int frac = (top << U.re.exp) != 0 || U.re.exp > 64;
+    for (int i = 0; i < L - 2 && !frac; i++) frac = U.re.m.w[i] != 0;
+    return (int64_t)ip + (frac ? 1 : 0);
+}
+int cbo_radius_flat(int L, int order, int degree, int64_t batch, int shared, const uint32_t *ode_m, const int32_t *ode_t,
+                    int64_t n, uint32_t *out_m, int32_t *out_t, int32_t *n_done) {
+    int cnt = (order + 1) * (degree + 1);
+    cbo_ode o;
+    o.order = order;
+    o.degree = degree;
+    o.valuation = CBO_UNDEFINED;
+    o.polys = (cbo_acb *)malloc(sizeof(cbo_acb) * cnt);
+    for (int64_t s = 0; s < batch; s++) {
+        for (int k = 0; k < cnt; k++) {
+            int64_t i = (shared ? 0 : s) * cnt + k;
+            cbo_load(&o.polys[k].re, ode_m + (2 * i) * L, ode_t + (2 * i) * 4, L);
+            cbo_load(&o.polys[k].im, ode_m + (2 * i + 1) * L, ode_t + (2 * i + 1) * 4, L);
+        }
+        cbo_acb out;
+        n_done[s] = cbo_radius_of_convergence(&out, &o, n, L);
+        cbo_store(out_m + (2 * s) * L, out_t + (2 * s) * 4, &out.re, L);
+        cbo_store(out_m + (2 * s + 1) * L, out_t + (2 * s + 1) * 4, &out.im, L);
+    }
+    free(o.polys);
+    return 0;
+}
+int cbo_truncation_flat(int L, int64_t batch, const uint32_t *eta_m, const int32_t *eta_t, const uint32_t *al_m,
+                        const int32_t *al_t, int64_t bits, uint32_t *n_m, int32_t *n_t, int64_t *n_out) {
+    for (int64_t s = 0; s < batch; s++) {
+        cbo_acb eta, al, nb;
+        cbo_load(&eta.re, eta_m + (2 * s) * L, eta_t + (2 * s) * 4, L);
+        cbo_load(&eta.im, eta_m + (2 * s + 1) * L, eta_t + (2 * s + 1) * 4, L);
+        cbo_load(&al.re, al_m + (2 * s) * L, al_t + (2 * s) * 4, L);
+        cbo_load(&al.im, al_m + (2 * s + 1) * L, al_t + (2 * s + 1) * 4, L);
+        n_out[s] = cbo_truncation_order(&nb, &eta, &al, bits, L);
+        cbo_store(n_m + (2 * s) * L, n_t + (2 * s) * 4, &nb.re, L);
+        cbo_store(n_m + (2 * s + 1) * L, n_t + (2 * s + 1) * 4, &nb.im, L);
+    }
+    return 0;
+}
+
 /* elementwise transcendental ops for the unit tests: which 0 exp, 1 log */
 int cbo_ew_trans(int which, int L, int64_t n, uint32_t *zm, int32_t *zt, const uint32_t *xm, const int32_t *xt) {
     for (int64_t i = 0; i < n; i++) {

@@ -415,6 +415,82 @@ def case_continuation_series(oracle, drv, L: int, seed: int, steps: int = 3, n: 
         pass
 
 
+def _leading_poly_operator(roots, L: int, order: int = 2, zero_roots: int = 0):
+    """an operator whose leading coefficient is z^zero_roots * prod (z - root) (roots: exact (re, im) Fraction pairs),
+    the other rows small integers; returns (ode, degree)"""
+    from fractions import Fraction as Fr
+    coef = [(Fr(1), Fr(0))]
+    for rr, ri in roots:
+        out = [(Fr(0), Fr(0)) for _ in range(len(coef) + 1)]
+        for i, (a, b) in enumerate(coef):
+            out[i + 1] = (out[i + 1][0] + a, out[i + 1][1] + b)                       # * z
+            out[i] = (out[i][0] - (a * rr - b * ri), out[i][1] - (a * ri + b * rr))   # * (-root)
+        coef = out
+    coef = [(Fr(0), Fr(0))] * zero_roots + coef
+    degree = len(coef) - 1
+    rows = []
+    for i in range(order):
+        rows += [(Fr(i + 1), Fr(0))] + [(Fr(0), Fr(0))] * degree
+    rows += coef
+    return from_complex(rows, L), degree
+
+
+def case_radius_and_truncation(oracle, drv, L: int, seed: int, batch: int = 6):
+    """radius_of_convergence / truncation_order (reference src/fuchs_solver.c:3-94; property of reference tests/radius.c):
+    rigorous on the device -- the balls are the oracle's bit for bit AND contain the true distance of the nearest nonzero
+    root of the leading coefficient (exact rational roots here), also with a singularity at the origin factored out, for
+    several Graeffe counts including one that runs into the exponent guard."""
+    rng = np.random.default_rng(seed)
+    from fractions import Fraction as Fr
+    import math
+    for trial in range(3):
+        nroots = 2 + trial
+        odes, trues = [], []
+        for inst in range(batch):
+            roots = [(Fr(int(rng.integers(-40, 41)), 8), Fr(int(rng.integers(-40, 41)), 8)) for _ in range(nroots)]
+            roots = [r if r != (0, 0) else (Fr(3, 8), Fr(1, 8)) for r in roots]
+            ode, degree = _leading_poly_operator(roots, L, zero_roots=inst % 2)
+            # all instances of a launch share (order, degree): pad with a zero root count of the same parity
+            odes.append((ode, degree, roots))
+        by_deg = {}
+        for ode, degree, roots in odes:
+            by_deg.setdefault(degree, []).append((ode, roots))
+        for degree, lst in by_deg.items():
+            ode = Balls.concat([o for o, _ in lst])
+            nb = len(lst)
+            for n in (6, 20, 40):
+                want, wd = oracle.radius_of_convergence(2, degree, ode, nb, n)
+                got, gd = api.radius_of_convergence_batch(ode, 2, degree, nb, n, driver=drv)
+                assert_same(want, got, f"radius_of_convergence L={L} degree={degree} n={n}")
+                assert (wd == gd).all() and (gd >= 1).all() and (gd <= n).all()
+                for i, (_, roots) in enumerate(lst):
+                    true2 = min(r[0] * r[0] + r[1] * r[1] for r in roots)
+                    lo, hi = got.mid(2 * i) - got.rad(2 * i), got.mid(2 * i) + got.rad(2 * i)
+                    assert lo >= 0 and lo * lo <= true2 <= hi * hi, (L, degree, n, i, float(lo), float(hi), math.sqrt(true2))
+                    assert got.rad(2 * i) <= got.mid(2 * i) * Fr(4 * degree * degree + 2, 2 ** min(int(gd[i]), 30)) + Fr(1, 2 ** 20)
+    # no singularity away from zero: indeterminate, n_done = -1 (reference :17-22)
+    ode, degree = _leading_poly_operator([], L, zero_roots=2)
+    got, gd = api.radius_of_convergence_batch(ode, 2, degree, 1, 10, driver=drv)
+    want, wd = oracle.radius_of_convergence(2, degree, ode, 1, 10)
+    assert_same(want, got, "radius_of_convergence without singularities")
+    assert gd[0] == -1 and wd[0] == -1 and (int(got.meta[0, 1]) & FLAG_NAN)
+    # truncation_order
+    eta = from_complex([Fr(1, 10), Fr(1, 3), Fr(2, 5), Fr(1, 2), Fr(1, 1000), Fr(3, 4)], L)
+    alpha = from_complex([Fr(1, 2), Fr(1, 2), Fr(1, 2), Fr(1, 2), Fr(1, 2), Fr(1, 2)], L)
+    for bits in (64, 32 * L):
+        wn, wc = oracle.truncation_order(eta, alpha, bits)
+        gn, gc = api.truncation_order_batch(eta, alpha, bits, driver=drv)
+        assert_same(wn, gn, f"truncation_order L={L} bits={bits}")
+        assert (wc == gc).all()
+        for i, (e, a) in enumerate(((0.1, 0.5), (1 / 3, 0.5), (0.4, 0.5), (0.5, 0.5), (0.001, 0.5), (0.75, 0.5))):
+            if e >= a:
+                assert gc[i] == 0
+            else:
+                r = e / ((e + a) / 2)
+                exact = (math.log(1 - r) - bits * math.log(2)) / math.log(r)
+                assert abs(gc[i] - math.ceil(exact)) <= 1 and gc[i] >= exact - 1e-9, (i, gc[i], exact)
+
+
 def case_horner(oracle, drv, L: int, seed: int, length: int = 40, npts: int = 9):
     rng = np.random.default_rng(seed)
     f = random_balls(rng, 2 * length, L, -3, 3, "ulp")

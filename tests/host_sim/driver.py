@@ -39,6 +39,9 @@ def lib():
                                                 _u32p, _i32p, _u32p, _i32p]
         L.cbsim_ode_shift.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, _u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int, _u32p, _i32p]
         L.cbsim_taylor_shift.argtypes = [C.c_int, C.c_int64, C.c_int64, _u32p, _i32p, _u32p, _i32p, C.c_int]
+        L.cbsim_radius.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, _u32p, _i32p, C.c_int, C.c_int64, _u32p, _i32p, _i32p]
+        L.cbsim_truncation.argtypes = [C.c_int, C.c_int64, _u32p, _i32p, _u32p, _i32p, C.c_int64, _u32p, _i32p,
+                                       np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")]
         L.cbsim_frobenius1_coop.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int, _u32p, _i32p]
         L.cbsim_horner_coop.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int, _u32p, _i32p, C.c_int, _u32p, _i32p, _u32p, _i32p]
         L.cbsim_frobenius1_batch.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p, C.c_int, _vp, _vp, C.c_int64, C.c_int, _u32p, _i32p]
@@ -77,6 +80,12 @@ class SimDriver:
 
     def continuation(self, L, order, degree, n, batch, path_len, ode_m, ode_t, path_m, path_t, y_m, y_t):
         return lib().cbsim_continuation(L, order, degree, n, batch, path_len, ode_m, ode_t, path_m, path_t, y_m, y_t)
+
+    def radius(self, L, order, degree, batch, ode_m, ode_t, shared, n, o_m, o_t, n_done):
+        return lib().cbsim_radius(L, order, degree, batch, ode_m, ode_t, int(shared), n, o_m, o_t, n_done)
+
+    def truncation(self, L, batch, e_m, e_t, a_m, a_t, bits, n_m, n_t, n_out):
+        return lib().cbsim_truncation(L, batch, e_m, e_t, a_m, a_t, bits, n_m, n_t, n_out)
 
     def continuation_series(self, L, order, degree, n, batch, path_len, ode_m, ode_t, path_m, path_t, y_m, y_t, r_m, r_t):
         return lib().cbsim_continuation_series(L, order, degree, n, batch, path_len, ode_m, ode_t, path_m, path_t, y_m, y_t,

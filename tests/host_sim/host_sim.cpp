@@ -102,7 +102,7 @@ int cbsim_fuchs_batch_range(int L_, int order, int degree, int valuation, int64_
         tp.tbl = tbl.arr(L_, rows * (W + 2), 2);
         tp.tmp = ttmp.arr(L_, 2, 2 * rows);
         tp.kind = kind.data(); tp.row0 = n_begin + valuation; tp.nrows = rows - tp.row0; tp.ninst = 1; tp.tbl_row0 = 0;
-        SIM_DISPATCH(L_, run<L>(tp.nrows, [&](int64_t i, Scratch<1> a, Scratch<1> b) { fuchs_table_thread<L>(tp, i, a, b); }));
+        SIM_DISPATCH(L_, run<L>(tp.nrows, [&](int64_t i, Scratch<1> a, Scratch<1> b) { fuchs_table_fast_thread<L>(tp, i, a, b); }));
         sp.n = n; sp.tbl = tp.tbl; sp.kind = kind.data(); sp.n_begin = n_begin; sp.tbl_row0 = 0; sp.kind_stride = 1; sp.per_inst = 0;
         if (sp.no_rr) {
             SIM_DISPATCH(L_, for (int64_t i = 0; i < batch; i++) (fuchs_shared_thread<L, false>)(sp, i, S0, S1, A0, A1, A2, G0, G1));
@@ -122,7 +122,7 @@ int cbsim_fuchs_batch_range(int L_, int order, int degree, int valuation, int64_
     for (int64_t lo = n_begin; lo <= n; lo += rt) {
         const int64_t hi = lo + rt - 1 < n ? lo + rt - 1 : n;
         tp.row0 = lo + valuation; tp.nrows = hi - lo + 1; tp.tbl_row0 = lo + valuation;
-        SIM_DISPATCH(L_, run<L>(tp.nrows * batch, [&](int64_t i, Scratch<1> a, Scratch<1> b) { fuchs_table_thread<L>(tp, i, a, b); }));
+        SIM_DISPATCH(L_, run<L>(tp.nrows * batch, [&](int64_t i, Scratch<1> a, Scratch<1> b) { fuchs_table_fast_thread<L>(tp, i, a, b); }));
         sp.n = hi; sp.tbl = tp.tbl; sp.kind = kind.data(); sp.n_begin = lo; sp.tbl_row0 = lo + valuation; sp.kind_stride = batch;
         sp.per_inst = 1; sp.no_rr = 1;
         SIM_DISPATCH(L_, for (int64_t i = 0; i < batch; i++) (fuchs_shared_thread<L, false, false, true>)(sp, i, S0, S1, A0, A1, A2, G0, G1));
@@ -485,6 +485,32 @@ int cbsim_horner_coop(int L_, int64_t len, int64_t npts, int nder, const uint32_
         case 128: return sim_horner_coop<128>(p);
         default: return CB200_EINVAL;
     }
+}
+
+int cbsim_radius(int L_, int order, int degree, int64_t batch, const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,
+                 int64_t n, uint32_t* out_mant, cb_meta* out_meta, int32_t* n_done) {
+    RadiusParams p;
+    p.order = order; p.degree = degree; p.batch = batch; p.n = n;
+    p.ode = CArr{const_cast<uint32_t*>(ode_mant), (Meta*)const_cast<cb_meta*>(ode_meta), shared_ode ? (size_t)2 : (size_t)(2 * batch)};
+    p.out = CArr{out_mant, (Meta*)out_meta, (size_t)(2 * batch)};
+    Tmp tmp;
+    p.wp = tmp.arr(L_, 2 * (int64_t)(degree + 1) + RADIUS_NTMP + TRANS_NTMP, 2 * batch);
+    p.n_done = n_done;
+    SIM_DISPATCH(L_, run<L>(batch, [&](int64_t i, Scratch<1> a, Scratch<1> b) { radius_thread<L>(p, i, a, b); }));
+    return 0;
+}
+int cbsim_truncation(int L_, int64_t batch, const uint32_t* eta_mant, const cb_meta* eta_meta, const uint32_t* alpha_mant,
+                     const cb_meta* alpha_meta, int64_t bits, uint32_t* n_mant, cb_meta* n_meta, int64_t* n_out) {
+    TruncParams p;
+    p.batch = batch; p.bits = bits;
+    p.eta = CArr{const_cast<uint32_t*>(eta_mant), (Meta*)const_cast<cb_meta*>(eta_meta), (size_t)(2 * batch)};
+    p.alpha = CArr{const_cast<uint32_t*>(alpha_mant), (Meta*)const_cast<cb_meta*>(alpha_meta), (size_t)(2 * batch)};
+    p.nball = CArr{n_mant, (Meta*)n_meta, (size_t)(2 * batch)};
+    Tmp tmp;
+    p.wp = tmp.arr(L_, 8 + TRANS_NTMP, 2 * batch);
+    p.n_out = n_out;
+    SIM_DISPATCH(L_, run<L>(batch, [&](int64_t i, Scratch<1> a, Scratch<1> b) { truncation_thread<L>(p, i, a, b); }));
+    return 0;
 }
 
 }  // extern "C"

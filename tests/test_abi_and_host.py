@@ -125,20 +125,3 @@ def test_partition_covers_batch():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
-
-
-def test_radius_and_reduce_program():
-    """reference tests/radius.c and tests/reduce.c through the compat names: host-side control-plane scalars, no GPU
-    needed (radius_of_convergence and acb_ode_reduce do no ball arithmetic)."""
-    import math
-    import subprocess
-    exe = os.path.join(ROOT, "tests", "c", "radius_example")
-    subprocess.run(["/usr/bin/gcc", "-O1", "-I", os.path.join(ROOT, "include"), "-o", exe,
-                    os.path.join(ROOT, "tests", "c", "radius_example.c"), "-L", os.path.join(ROOT, "cascade_b200"),
-                    "-lcascade_b200_compat", "-lcascade_b200", "-lm", "-Wl,-rpath," + os.path.join(ROOT, "cascade_b200")], check=True)
-    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
-    v = {line.split()[0]: line.split()[1:] for line in out.strip().splitlines()}
-    r = float(v["radius"][0])
-    assert r <= math.sqrt(2) and math.sqrt(2) - r < 1e-8   # the smallest root modulus is |1 + i|
-    assert v["reduced"] == ["2", "degree", "3", "valuation", "-1"]
-    assert abs(float(v["radius_after_reduce"][0]) - r) < 1e-12

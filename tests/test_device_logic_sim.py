@@ -72,6 +72,11 @@ def test_continuation_series_and_singular_corners(oracle, sim_driver, L):
     cases.case_continuation_series(oracle, sim_driver, L, seed=5 + L)
 
 
+@pytest.mark.parametrize("L", [4, 32])
+def test_radius_and_truncation(oracle, sim_driver, L):
+    cases.case_radius_and_truncation(oracle, sim_driver, L, seed=11 + L, batch=4)
+
+
 @pytest.mark.parametrize("L", [4, 32, 64])
 def test_ode_shift(oracle, sim_driver, L):
     cases.case_ode_shift(oracle, sim_driver, L, seed=7 + L, batch=4)

@@ -14,7 +14,7 @@ def build_and_run(name):
     exe = os.path.join(ROOT, "tests", "c", name)
     subprocess.run(["/usr/bin/gcc", "-O1", "-I", os.path.join(ROOT, "include"), "-o", exe,
                     os.path.join(ROOT, "tests", "c", name + ".c"), "-L", os.path.join(ROOT, "cascade_b200"),
-                    "-lcascade_b200_compat", "-lcascade_b200", "-Wl,-rpath," + os.path.join(ROOT, "cascade_b200")], check=True)
+                    "-lcascade_b200_compat", "-lcascade_b200", "-lm", "-Wl,-rpath," + os.path.join(ROOT, "cascade_b200")], check=True)
     return subprocess.run([exe], check=True, capture_output=True, text=True).stdout
 
 
@@ -98,3 +98,15 @@ def test_reference_fuchs_test_program():
     lines = out.strip().splitlines()
     assert lines[-1] == "failures 0"
     assert sum(1 for line in lines if line.startswith("iter") and line.endswith("solves 1")) >= 6
+
+
+def test_radius_and_reduce_program():
+    """reference tests/radius.c and tests/reduce.c through the compat names.  radius_of_convergence is the rigorous
+    device version (Graeffe iterations + root bound in ball arithmetic): the ball must CONTAIN the smallest root modulus
+    |1 + i| = sqrt(2) of the leading coefficient, from below at its midpoint, with the error bar of 20 iterations."""
+    out = build_and_run("radius_example")
+    v = {line.split()[0]: line.split()[1:] for line in out.strip().splitlines()}
+    r, rad = float(v["radius"][0]), float(v["radius"][1])
+    assert r <= math.sqrt(2) <= r + rad * (1 + 1e-9) and rad < 1e-4
+    assert v["reduced"] == ["2", "degree", "3", "valuation", "-1"]
+    assert abs(float(v["radius_after_reduce"][0]) - r) < 1e-12

@@ -106,6 +106,11 @@ def test_continuation_series_and_singular_corners(oracle, gpu_driver, L):
 
 
 @pytest.mark.parametrize("L", [4, 32, 64, 128])
+def test_radius_and_truncation(oracle, gpu_driver, L):
+    cases.case_radius_and_truncation(oracle, gpu_driver, L, seed=11 + L, batch=6 if L < 128 else 3)
+
+
+@pytest.mark.parametrize("L", [4, 32, 64, 128])
 def test_ode_shift(oracle, gpu_driver, L):
     cases.case_ode_shift(oracle, gpu_driver, L, seed=7 + L, batch=37)
 
