@@ -220,11 +220,16 @@ class FuchsShared(Workload):
         self.ws_bytes = lib.cb200_fuchs_workspace_bytes(L, 2, 2, -2, n, batch, 1)
         self.d_ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
         self.coeffs = batch * (n - 1)
-        self.config = {"workload": "configs[1]: Bessel ODE (complex nu) shifted to an ordinary point, "
-                                   f"{n}-term Fuchs series, 1024 bits, {batch} initial conditions per GPU, shared operator",
-                       "L_limbs": L, "order": ORDER, "degree": DEGREE, "terms": n, "batch_per_gpu": batch, "seed": hex(SEED),
-                       "cache": "outputs (tens of GB per step) and the coefficient window far exceed the 126 MB L2; no flush needed"}
-        self.metric = METRIC
+        self.config = self.describe()
+
+    metric = METRIC
+
+    def describe(self):
+        batch, n = self.args.batch or BATCH, self.args.terms or N_TERMS
+        return {"workload": "configs[1]: Bessel ODE (complex nu) shifted to an ordinary point, "
+                            f"{n}-term Fuchs series, 1024 bits, {batch} initial conditions per GPU, shared operator",
+                "L_limbs": L, "order": ORDER, "degree": DEGREE, "terms": n, "batch_per_gpu": batch, "seed": hex(SEED),
+                "cache": "outputs (tens of GB per step) and the coefficient window far exceed the 126 MB L2; no flush needed"}
 
     def prepare(self):
         self.d_res_m[:2].copy_(self.d_init_m)
@@ -298,11 +303,16 @@ class FrobeniusSweep(Workload):
         self.ws_bytes = lib.cb200_frobenius_workspace_bytes(Lh, batch)
         self.d_ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
         self.coeffs = 2 * batch * n
-        self.config = {"workload": f"configs[2]: Gauss hypergeometric acb_ode_solve_frobenius (M = 1), 4096 bits, {batch} (a,b,c) "
-                                   f"triples per GPU, {n} terms, rho = 0 and rho = 1 - c (one step = both runs)",
-                       "L_limbs": Lh, "order": 2, "degree": 2, "terms": n, "batch_per_gpu": batch, "seed": hex(0x5EED0003),
-                       "cache": "4.4 GB of results and 0.5 GB of per-instance temporaries per run exceed the 126 MB L2; no flush needed"}
-        self.metric = "ball-coeffs/sec, 4096-bit batched acb_ode_solve_frobenius (hypergeometric sweep)"
+        self.config = self.describe()
+
+    metric = "ball-coeffs/sec, 4096-bit batched acb_ode_solve_frobenius (hypergeometric sweep)"
+
+    def describe(self):
+        batch, n = self.args.batch or 16384, self.args.terms or 256
+        return {"workload": f"configs[2]: Gauss hypergeometric acb_ode_solve_frobenius (M = 1), 4096 bits, {batch} (a,b,c) "
+                            f"triples per GPU, {n} terms, rho = 0 and rho = 1 - c (one step = both runs)",
+                "L_limbs": self.Lh, "order": 2, "degree": 2, "terms": n, "batch_per_gpu": batch, "seed": hex(0x5EED0003),
+                "cache": "4.4 GB of results and 0.5 GB of per-instance temporaries per run exceed the 126 MB L2; no flush needed"}
 
     def prepare(self):
         pass
@@ -387,14 +397,22 @@ class LegendreSweep(Workload):
             self.g_m = torch.empty((self.world, L, 2 * self.nmax), dtype=torch.int32, device=dev)
             self.g_t = torch.empty((self.world, 2 * self.nmax, 4), dtype=torch.int32, device=dev)
         self.coeffs = self.mine * (n - 1)
-        self.config = {"workload": f"configs[3]: Legendre sweep n = 0 .. {self.total - 1}, {n} terms, 1024 bits, the whole sweep per step "
-                                   f"in tiles of {self.tile} instances per launch, sharded over the ranks (strong scaling), NCCL "
-                                   "all-gather of the last coefficient of every instance inside the step",
-                       "L_limbs": L, "order": 2, "degree": 2, "terms": n, "instances_total": self.total, "tile": self.tile,
-                       "cache": f"every tile writes {self.tile * (n - 1) * 288 / 1e9:.1f} GB of series: far beyond the 126 MB L2; no flush needed",
-                       "gather": "full series (302 GB at the BASELINE size) stay on the device that computed them; the gathered "
-                                 "reduction is coefficient n of every instance (302 MB at the BASELINE size)"}
-        self.metric = "ball-coeffs/sec, 1024-bit Legendre sweep (integer-operator acb_ode_solve_fuchs)"
+        self.config = self.describe()
+
+    metric = "ball-coeffs/sec, 1024-bit Legendre sweep (integer-operator acb_ode_solve_fuchs)"
+
+    def describe(self):
+        from cascade_b200.sharding import partition
+        total, n = self.args.batch or (1 << 20), self.args.terms or 1000
+        lo, hi = partition(total, self.world, 0)
+        tile = min(self.TILE, max(hi - lo, 1))
+        return {"workload": f"configs[3]: Legendre sweep n = 0 .. {total - 1}, {n} terms, 1024 bits, the whole sweep per step "
+                            f"in tiles of {tile} instances per launch, sharded over the ranks (strong scaling), NCCL "
+                            "all-gather of the last coefficient of every instance inside the step",
+                "L_limbs": L, "order": 2, "degree": 2, "terms": n, "instances_total": total, "tile": tile,
+                "cache": f"every tile writes {tile * (n - 1) * 288 / 1e9:.1f} GB of series: far beyond the 126 MB L2; no flush needed",
+                "gather": "full series (302 GB at the BASELINE size) stay on the device that computed them; the gathered "
+                          "reduction is coefficient n of every instance (302 MB at the BASELINE size)"}
 
     def prepare(self):
         pass
@@ -479,13 +497,18 @@ class HornerPoints(Workload):
         self.ws_bytes = lib.cb200_horner_workspace_bytes(Lh, self.npts)
         self.d_ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
         self.coeffs = self.npts * (self.length - 1)
-        self.config = {"workload": f"configs[4]: Horner evaluation of one {self.length}-term series (truncation_order of the 64-step "
-                                   f"continuation path at 2048 bits) at {self.npts} points per GPU, 2048 bits",
-                       "L_limbs": Lh, "terms": self.length, "points_per_gpu": self.npts, "seed": hex(0x5EED0005),
-                       "cache": "the series (1.9 MB) is meant to stay in L2; the points and accumulators (0.5 GB + temporaries) "
-                                "exceed it; no flush needed",
-                       "continuation_leg": "timed by tools/bench_configs.py --continuation (sequential in the path: not a bench step)"}
-        self.metric = "ball-coeffs/sec, 2048-bit Horner evaluation (series coefficients consumed x points)"
+        self.config = self.describe()
+
+    metric = "ball-coeffs/sec, 2048-bit Horner evaluation (series coefficients consumed x points)"
+
+    def describe(self):
+        npts, length = self.args.batch or 10 ** 6, self.args.terms or 3504
+        return {"workload": f"configs[4]: Horner evaluation of one {length}-term series (truncation_order of the 64-step "
+                            f"continuation path at 2048 bits) at {npts} points per GPU, 2048 bits",
+                "L_limbs": self.Lh, "terms": length, "points_per_gpu": npts, "seed": hex(0x5EED0005),
+                "cache": "the series (1.9 MB) is meant to stay in L2; the points and accumulators (0.5 GB + temporaries) "
+                         "exceed it; no flush needed",
+                "continuation_leg": "timed by tools/bench_configs.py --continuation (sequential in the path: not a bench step)"}
 
     def prepare(self):
         pass
@@ -524,6 +547,15 @@ class HornerPoints(Workload):
 
 
 WORKLOADS = {1: FuchsShared, 2: FrobeniusSweep, 3: LegendreSweep, 4: HornerPoints}
+
+
+def describe(cfg, args, world=1):
+    """The `config` object of a workload without touching a GPU (the reference arm prints the same one)."""
+    class _NoGpu:
+        pass
+    w = WORKLOADS[cfg].__new__(WORKLOADS[cfg])
+    w.args, w.rank, w.world = args, 0, world
+    return w.describe()
 
 
 def traffic_for(cfg, key):
@@ -580,21 +612,19 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        # describe the workload without touching a GPU
         W = WORKLOADS[cfg]
-        vals, sample = [], ""
+        vals, sample, dts = [], "", []
         for _ in range(max(1, args.steps)):
+            t0 = time.perf_counter()
             v, sample = cpu_port(cfg, ncores, 8.0, args)
+            dts.append(time.perf_counter() - t0)
             vals.append(v)
         val = sum(vals) / len(vals)
-        names = {1: METRIC, 2: "ball-coeffs/sec, 4096-bit batched acb_ode_solve_frobenius (hypergeometric sweep)",
-                 3: "ball-coeffs/sec, 1024-bit Legendre sweep (integer-operator acb_ode_solve_fuchs)",
-                 4: "ball-coeffs/sec, 2048-bit Horner evaluation (series coefficients consumed x points)"}
-        line = {"impl": "reference", "metric": names[cfg], "value": val, "unit": UNIT, "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
+        line = {"impl": "reference", "metric": W.metric, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(dts) / len(dts) * 1e3,
                 "higher_is_better": True, "scaling": W.scaling, "vs_baseline": None, "dtype": W.dtype,
-                "data": "synthetic", "config": {"workload": f"configs[{cfg}] (see the GPU arm's line), CPU port on a bounded sample"},
-                "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample},
+                "data": "synthetic", "config": describe(cfg, args, args.gpus),
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample + " per step"},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
         return

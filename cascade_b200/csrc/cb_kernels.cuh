@@ -217,6 +217,118 @@ __global__ void __launch_bounds__(Cfg<L>::TPB, 1) taylor_shift_kernel(TShiftPara
         __syncthreads();
     }
 }
+// ---- Horner with the series staged by TMA: every point of the launch reads the SAME series, one coefficient per
+// step (reference src/acb_ode_solution.c:40: acb_poly_evaluate of one stored series at many points).  Instead of every
+// thread loading that coefficient through L1 / L2 on its critical path, one elected thread streams the series into
+// shared memory in tiles of T coefficients with cp.async.bulk (1-D bulk copies: an entry of the [entry][limb][2]
+// layout is contiguous, 8 L + 32 bytes), double buffered, completion on an mbarrier; the tile for the next T steps
+// is in flight while the current one is consumed.  Same arithmetic as horner_thread: the coefficient is merely read
+// from shared memory.
+template <int L> struct HornerTile {
+    static constexpr int T = L <= 64 ? 16 : 8;
+    static constexpr uint32_t MANT = (uint32_t)T * L * 2 * 4, META = (uint32_t)T * 2 * 16;
+    static constexpr size_t BYTES = (size_t)2 * (MANT + META);
+};
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void tma_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void tma_expect(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
+#endif
+template <int L>
+__global__ void __launch_bounds__(HybCfg<L>::TPB, 1) horner_tma_kernel(HornerParams p) {
+    if constexpr (HybCfg<L>::ON) {
+#if defined(__CUDA_ARCH__)
+        extern __shared__ __align__(128) uint32_t cb_smem_tma[];
+        __shared__ __align__(8) uint64_t mbar[2];
+        constexpr int TPB = HybCfg<L>::TPB, T = HornerTile<L>::T;
+        constexpr bool SYNC = HORNER_SYNC;
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cb_smem_tma) + 4u * threadIdx.x;
+        char* tiles = reinterpret_cast<char*>(cb_smem_tma) + HybCfg<L>::SMEM;
+        auto tile_m = [&](int b) { return reinterpret_cast<uint32_t*>(tiles + (size_t)b * (HornerTile<L>::MANT + HornerTile<L>::META)); };
+        auto tile_t = [&](int b) {
+            return reinterpret_cast<Meta*>(tiles + (size_t)b * (HornerTile<L>::MANT + HornerTile<L>::META) + HornerTile<L>::MANT);
+        };
+        const int64_t idx = (int64_t)blockIdx.x * TPB + threadIdx.x;
+        if (threadIdx.x == 0) {
+            tma_mbar_init(&mbar[0], 1);
+            tma_mbar_init(&mbar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        const int64_t ntiles = (p.len + T - 1) / T;
+        // tile k holds entries j_lo(k) .. j_hi(k), j_hi(k) = len - 1 - k T, walking down the series as Horner does
+        auto issue = [&](int64_t k) {
+            const int64_t j_hi = p.len - 1 - k * T, j_lo = j_hi - T + 1 > 0 ? j_hi - T + 1 : 0;
+            const uint32_t c = (uint32_t)(j_hi - j_lo + 1);
+            const int b = (int)(k & 1);
+            tma_expect(&mbar[b], c * (uint32_t)(L * 2 * 4 + 2 * 16));
+            tma_bulk_g2s(tile_m(b), p.f.m + (size_t)j_lo * L * 2, c * (uint32_t)(L * 2 * 4), &mbar[b]);
+            tma_bulk_g2s(tile_t(b), p.f.t + (size_t)j_lo * 2, c * (uint32_t)(2 * 16), &mbar[b]);
+        };
+        if (threadIdx.x == 0 && ntiles > 0) issue(0);
+        if (idx >= p.npts) return;  // (thread 0 of an existing block is always a live point)
+        HybridScratch<TPB, HybCfg<L>::KS> S0{sbase, p.gcols + idx, (uint32_t)p.npts};
+        HybridScratch<TPB, HybCfg<L>::KS> S1{sbase + 4u * (uint32_t)(HybCfg<L>::KS * TPB),
+                                             p.gcols + (size_t)HybCfg<L>::GW * (size_t)p.npts + idx, (uint32_t)p.npts};
+        const size_t slot = 2 * (size_t)idx;
+        CRef a = at<L>(p.pts, 0, (p.pts.S == 2) ? 0 : slot), tmp = at<L>(p.tmp, 0, slot);
+        for (int k = 0; k < p.nder; k++) acb_zero<L>(at<L>(p.out, k, slot));
+#pragma unroll 1
+        for (int64_t k = 0; k < ntiles; k++) {
+            const int b = (int)(k & 1);
+            const int64_t j_hi = p.len - 1 - k * T, j_lo = j_hi - T + 1 > 0 ? j_hi - T + 1 : 0;
+            // the buffer of tile k + 1 was last read during tile k - 1: every live thread has passed the barrier at the
+            // end of that tile
+            if (threadIdx.x == 0 && k + 1 < ntiles) issue(k + 1);
+            tma_wait(&mbar[b], (uint32_t)((k >> 1) & 1));
+#pragma unroll 1
+            for (int64_t j = j_hi; j >= j_lo; j--) {
+                CRef fj{tile_m(b) + (size_t)(j - j_lo) * L * 2, (size_t)2, tile_t(b) + (size_t)(j - j_lo) * 2};
+                if (j == p.len - 1) {
+                    acb_set<L>(at<L>(p.out, 0, slot), fj);
+                    continue;
+                }
+#pragma unroll 1
+                for (int d = p.nder - 1; d >= 0; d--) {
+                    CRef o = at<L>(p.out, d, slot);
+                    CB_PHASE_SYNC();
+                    acb_mul<L>(tmp, o, a, S0, S1);
+                    CB_PHASE_SYNC();
+                    if (d > 0)
+                        acb_addsub<L>(o, tmp, at<L>(p.out, d - 1, slot), false, S0, S1);
+                    else
+                        acb_addsub<L>(o, tmp, fj, false, S0, S1);
+                }
+            }
+            __syncthreads();
+        }
+#endif
+    }
+}
+
 template <int L>
 __global__ void __launch_bounds__(Cfg<L>::TPB, 1) ew_kernel(EwParams p) {
     CB_KERNEL_PROLOGUE(p.n)
@@ -512,6 +624,18 @@ int launch_coop_horner(const HornerParams& p, cudaStream_t s) {
     return (int)cudaGetLastError();
 }
 
+// the TMA-staged Horner kernel: one series for all points (S = 2), long enough for a few tiles, 16-byte aligned
+// CB200_TMA=0/1 in the environment overrides (development)
+template <int L>
+bool use_horner_tma(const HornerParams& p) {
+    if (!HybCfg<L>::ON) return false;
+    if (p.f.S != 2 || ((uintptr_t)p.f.m & 15) || ((uintptr_t)p.f.t & 15)) return false;
+    const char* e = getenv("CB200_TMA");
+    if (e && e[0] == '0') return false;
+    if (e && e[0] == '1') return true;
+    return p.len >= 4 * HornerTile<L>::T;
+}
+
 // per-precision launch table, filled by kern_L*.cu
 struct LaunchTable {
     int (*frobenius1)(const FrobParams&, cudaStream_t);
@@ -542,8 +666,12 @@ struct LaunchTable {
     }                                                                                                      \
     static int horner_##LL(const HornerParams& p, cudaStream_t s) {                                        \
         if (use_coop_horner<LL>(p)) return launch_coop_horner<LL>(p, s);                                   \
-        if (use_hybrid<LL>(p.npts, sm_count(), HybRatio<LL>::HORNER))                                      \
+        if (use_hybrid<LL>(p.npts, sm_count(), HybRatio<LL>::HORNER)) {                                    \
+            if (use_horner_tma<LL>(p))                                                                     \
+                return launch<LL>(horner_tma_kernel<LL>, p, p.npts, s, HybCfg<LL>::TPB,                     \
+                                  HybCfg<LL>::SMEM + HornerTile<LL>::BYTES);                               \
             return launch<LL>(horner_hyb_kernel<LL>, p, p.npts, s, HybCfg<LL>::TPB, HybCfg<LL>::SMEM);     \
+        }                                                                                                  \
         return launch<LL>(horner_kernel<LL>, p, p.npts, s);                                                \
     }                                                                                                      \
     static int ew_##LL(const EwParams& p, cudaStream_t s) { return launch<LL>(ew_kernel<LL>, p, p.n, s); }                \

@@ -81,6 +81,20 @@ def test_hybrid_scratch_columns(monkeypatch, oracle, gpu_driver, L, hybrid):
     cases.case_frobenius(oracle, gpu_driver, L, seed=29, n=14, batch=300)
 
 
+@pytest.mark.parametrize("tma", ["0", "1"])
+@pytest.mark.parametrize("L", [64, 128])
+def test_horner_series_staged_by_tma(monkeypatch, oracle, gpu_driver, L, tma):
+    """The 2048 / 4096-bit Horner kernel with the series streamed into shared memory by cp.async.bulk (tiles of 16 / 8
+    coefficients, double buffered, mbarrier completion) against the kernel that loads every coefficient itself: series
+    lengths that are and are not a whole number of tiles, one tile, ragged last blocks, several derivatives."""
+    monkeypatch.setenv("CB200_TMA", tma)
+    monkeypatch.setenv("CB200_HYBRID", "1")
+    monkeypatch.setenv("CB200_COOP", "0")
+    for length in (5, 16, 33, 70):
+        cases.case_horner(oracle, gpu_driver, L, seed=41 + length, length=length, npts=300 if length < 70 else 520)
+    cases.case_horner_cancellation(oracle, gpu_driver, L, seed=413 + L, length=20, npts=300)
+
+
 @pytest.mark.parametrize("coop", ["0", "1"])
 @pytest.mark.parametrize("L", [64, 128])
 def test_cooperating_lanes(monkeypatch, oracle, gpu_driver, L, coop):
