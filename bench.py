@@ -249,25 +249,42 @@ class FuchsShared(Workload):
         return imad_roofline(macs, kernel_ms, imad_peak, self.coeffs * 2 * (4 * L + 16), peaks,
                              traffic_for(1, {"batch": self.batch, "terms": self.n}))
 
-    def e2e_setup(self):
-        """Host side of the end-to-end leg: the caller's FULL result arrays, page-locked."""
-        lib, n, S = self.lib, self.n, 2 * self.batch
+    def e2e_host_bytes(self):
+        return (self.n + 1) * 2 * self.batch * (4 * L + 16)
+
+    def e2e_setup(self, tiles=1):
+        """Host side of the end-to-end leg: the caller's FULL result arrays, page-locked.  When the host cannot hold
+        them for every rank of the box (`tiles` > 1, chosen by main from the free memory) the batch goes through the
+        same host call in `tiles` instance tiles whose result arrays are reused -- the same coefficients, the same bytes
+        over PCIe, a caller that consumes one tile before asking for the next."""
+        from cascade_b200.format import pack_entries
+        lib, n = self.lib, self.n
+        self.e2e_tiles = tiles
+        tb = self.batch // tiles
+        S = 2 * tb
         self.h_res_m, pm = pinned_array(lib, (n + 1, L, S), np.uint32)
         self.h_res_t, pt = pinned_array(lib, (n + 1, S, 4), np.int32)
-        self.h_res_m[:2] = self.init_m
-        self.h_res_t[:2] = self.init_t
+        # per-tile initial rows (slots of a tile are contiguous in the [entry][limb][slot] layout of the whole batch)
+        self.h_init = [(np.ascontiguousarray(self.init_m[:, :, 2 * tb * k:2 * tb * (k + 1)]),
+                        np.ascontiguousarray(self.init_t[:, 2 * tb * k:2 * tb * (k + 1)])) for k in range(tiles)]
         # the device-resident leg's buffers are not needed any more: the host call owns its own (cached) ones
         del self.d_res_m, self.d_res_t, self.d_ws
         self.torch.cuda.empty_cache()
-        self.h2d = 2 * L * S * 4 + 2 * S * 16 + self.ode_m.nbytes + self.ode_t.nbytes
-        self.d2h = (n - 1) * S * (L * 4 + 16)
-        return f"cb200_fuchs_batch_host: one call per step, caller-owned full result arrays ({'page-locked' if pm and pt else 'PAGEABLE'}), " \
-               "initial rows and operator uploaded, coefficient ranges copied back on a second stream while the next range is computed"
+        self.h2d = tiles * (self.ode_m.nbytes + self.ode_t.nbytes) + 2 * L * 2 * self.batch * 4 + 2 * 2 * self.batch * 16
+        self.d2h = (n - 1) * 2 * self.batch * (L * 4 + 16)
+        how = f"cb200_fuchs_batch_host: {'one call' if tiles == 1 else str(tiles) + ' calls (instance tiles of ' + str(tb) + ', host arrays reused)'} per step, " \
+              f"caller-owned full result arrays ({'page-locked' if pm and pt else 'PAGEABLE'}), " \
+              "initial rows and operator uploaded, coefficient ranges copied back on a second stream while the next range is computed"
+        return how
 
     def e2e_step(self):
-        rc = self.lib.cb200_fuchs_batch_host(L, ORDER, DEGREE, -2, self.n, self.batch, self.ode_m, self.ode_t, 1,
-                                             self.h_res_m, self.h_res_t.view(np.int32), self.dev.index)
-        assert rc == 0, f"cb200_fuchs_batch_host -> {rc}"
+        tb = self.batch // self.e2e_tiles
+        for k in range(self.e2e_tiles):
+            self.h_res_m[:2] = self.h_init[k][0]
+            self.h_res_t[:2] = self.h_init[k][1]
+            rc = self.lib.cb200_fuchs_batch_host(L, ORDER, DEGREE, -2, self.n, tb, self.ode_m, self.ode_t, 1,
+                                                 self.h_res_m, self.h_res_t.view(np.int32), self.dev.index)
+            assert rc == 0, f"cb200_fuchs_batch_host -> {rc}"
 
     def e2e_check(self):
         from cascade_b200.format import FLAG_NAN
@@ -592,6 +609,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="instances (points) per GPU -- config 3: instances of the whole sweep (default: the BASELINE size)")
     ap.add_argument("--terms", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-tiles", type=int, default=0, help="config 1: force the number of instance tiles of the end-to-end leg (default: 1 if the host memory allows)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
 
@@ -698,8 +716,28 @@ def main():
 
     # ---- end to end: through the host-buffer C-ABI call, host arrays in and out, copies inside the timing
     e2e = None
+    e2e_note = None
     if not args.no_e2e:
-        how = w.e2e_setup()
+        # the caller-owned result arrays of every rank of this box must fit the host's memory (configs[1]: 37.7 GB per
+        # rank); if they do not, the end-to-end leg is skipped rather than measured on something smaller
+        need = getattr(w, "e2e_host_bytes", lambda: 0)() * world
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = None
+        tiles = max(1, args.e2e_tiles)
+        while avail is not None and need / tiles * 1.25 > avail and tiles < 16 and cfg == 1:
+            tiles *= 2
+        short = avail is not None and need / tiles * 1.25 > avail
+        flag = torch.tensor([tiles, 1 if short else 0], device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        tiles = int(flag[0].item())
+        if int(flag[1].item()):
+            e2e_note = f"skipped: {need / 1e9:.0f} GB of host result arrays for {world} rank(s) against {0 if avail is None else avail / 1e9:.0f} GB available"
+    if not args.no_e2e and e2e_note is None:
+        how = w.e2e_setup(tiles) if cfg == 1 else w.e2e_setup()
         w.e2e_step()
         barrier()
         e2e_steps = max(1, min(args.steps, 2))
@@ -743,7 +781,8 @@ def main():
     line = {"metric": w.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": w.scaling,
             "vs_baseline": None, "dtype": w.dtype, "data": "synthetic", "config": w.config,
-            "clocks": summarise_clocks(samples), "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": summarise_clocks(samples), "e2e": e2e if e2e is not None else ({"skipped": e2e_note} if e2e_note else None),
+            "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu}
     emit(line)
     if world > 1:

@@ -295,32 +295,38 @@ int cb200_fuchs_intop_batch_dev(int L_, int order, int degree, int valuation, in
     p.res = CArr{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
     p.range_len = 32;
     p.sched = nullptr;
-    g_launches.fetch_add(batch > 0);
-    // more than one wave of blocks with a ragged last wave: run the persistent form (work units of one instance
-    // block x 32 coefficients, one CTA per SM) on a stream-ordered scheduling buffer
-    {
-        int dev = 0, sms = 148;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int tpb = L_ <= 32 ? 384 : (L_ == 64 ? 192 : 96);  // IntopCfg<L>::TPB
-        int64_t nblocks = (batch + tpb - 1) / tpb, waves = (nblocks + sms - 1) / sms;
-        const char* e = getenv("CB200_PERSISTENT");
-        bool want = nblocks > sms && (double)(waves * sms - nblocks) > 0.04 * (double)nblocks;
-        if (e && e[0] == '0') want = false;
-        if (e && e[0] == '1') want = true;
-        if (want) {
-            int* sched = nullptr;
-            cudaStream_t st = (cudaStream_t)stream;
-            if (cudaMallocAsync((void**)&sched, sizeof(int) * (size_t)(nblocks + 1), st) == cudaSuccess) {
-                CUDA_RET(cudaMemsetAsync(sched, 0, sizeof(int) * (size_t)(nblocks + 1), st));
-                p.sched = sched;
-                int rc = table_for(L_)->fuchs_intop(p, st);
-                cudaFreeAsync(sched, st);
-                return rc;
-            }
-            (void)cudaGetLastError();  // no stream-ordered allocator: fall through to the whole-wave launch
+    if (batch == 0) return 0;
+    g_launches.fetch_add(1);
+    // Stream-ordered scratch: the global product column of the general body (L + 3 words per lane, lanes padded to
+    // whole blocks) and, for the persistent form, the scheduling words.  The persistent form (work units of one
+    // instance block x 32 coefficients, one CTA per SM) runs when the batch is more than one wave of blocks with a
+    // ragged last wave.
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int tpb = intop_tpb(L_);
+    const int64_t nblocks = (batch + tpb - 1) / tpb, waves = (nblocks + sms - 1) / sms;
+    const char* e = getenv("CB200_PERSISTENT");
+    bool want = nblocks > sms && (double)(waves * sms - nblocks) > 0.04 * (double)nblocks;
+    if (e && e[0] == '0') want = false;
+    if (e && e[0] == '1') want = true;
+    const size_t lanes = (size_t)nblocks * tpb;
+    const size_t gbytes = align256((size_t)(L_ + 3) * lanes * sizeof(uint32_t));
+    char* scratch = nullptr;
+    CUDA_RET(cudaMallocAsync((void**)&scratch, gbytes + sizeof(int) * (size_t)(nblocks + 1), st));
+    p.gs0 = (uint32_t*)scratch;
+    p.gs0_stride = lanes;
+    if (want) {
+        p.sched = (int*)(scratch + gbytes);
+        cudaError_t me = cudaMemsetAsync(p.sched, 0, sizeof(int) * (size_t)(nblocks + 1), st);
+        if (me != cudaSuccess) {
+            cudaFreeAsync(scratch, st);
+            return (int)me;
         }
     }
-    return table_for(L_)->fuchs_intop(p, (cudaStream_t)stream);
+    int rc = table_for(L_)->fuchs_intop(p, st);
+    cudaFreeAsync(scratch, st);
+    return rc;
 }
 
 int cb200_frobenius1_rhs_batch_dev(int L_, int order, int degree, int valuation, int64_t n, int64_t batch,

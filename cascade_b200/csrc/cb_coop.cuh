@@ -26,7 +26,10 @@ struct Quad {
     uint32_t a;       // own column: shared-space byte address of word 0
     uint32_t* g;      // own column: global tail
     uint32_t gs;
+    uint32_t a2 = 0;  // own column of a second region (L + 2 words per lane: accumulators of the recurrence kernel)
+    uint32_t* st = nullptr;  // 24 state words of the quad (shared memory, 16-byte aligned)
     __device__ __forceinline__ Col col(int qq) const { return Col{a + 4u * (uint32_t)(qq - q), g + (qq - q), gs}; }
+    __device__ __forceinline__ Scratch<TPB> acol(int qq) const { return Scratch<TPB>{a2 + 4u * (uint32_t)(qq - q)}; }
     __device__ __forceinline__ void sync() const { __syncwarp(qmask); }
 };
 #define CB_COOP_EACH(Q, qv) for (int qv = (Q).q, qv##_go = 1; qv##_go; qv##_go = 0)
@@ -36,7 +39,10 @@ struct Quad {
     using Col = HybridScratch<TPB, KS>;
     uint32_t* p[4];
     uint32_t* g[4];
+    uint32_t* p2[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t* st = nullptr;
     Col col(int qq) const { return Col{p[qq], g[qq], 1u}; }
+    Scratch<TPB> acol(int qq) const { return Scratch<TPB>{p2[qq]}; }
     void sync() const {}
 };
 #define CB_COOP_EACH(Q, qv) for (int qv = 0; qv < 4; qv++)
@@ -267,6 +273,85 @@ CB_HD void horner_coop_quad(const HornerParams& p, int64_t pt, const QD& Q) {
                 coop_addsub<L>(Q, o, tmp, at<L>(p.out, k - 1, slot), false);
             else
                 coop_addsub<L>(Q, o, tmp, at<L>(p.f, j, fslot), false);
+        }
+    }
+}
+
+// acb_ode_solve_fuchs with one operator for the batch (fuchs_shared_thread of cb_solvers.cuh, the recurrence of
+// reference src/fuchs_solver.c:108-139 on the precomputed multiplier table), coefficients b_first .. b_last of one
+// instance on the four lanes of a quad: the analytic continuation of a FEW solutions (reference src/fuchs_solver.c:
+// 147-206: one path, `order` initial vectors) is this loop on one or two instances.  Lanes 0 / 2 own the accumulator
+// and spare columns of the real / imaginary part (acol(0), acol(1) / acol(2), acol(3)); which of the two holds the
+// accumulator after an aligned add depends on the data, so the choice and the meta records travel through the quad's
+// state words.
+template <int L, class QD>
+CB_HD void fuchs_shared_coop_quad(const FuchsSharedParams& p, int64_t inst, const QD& Q, int64_t b_first, int64_t b_last) {
+    const size_t slot = 2 * (size_t)inst;
+    const int v = p.valuation, W = p.degree - v;
+    // state words: [0] re accumulator column (0 or 1), [1] im accumulator column (2 or 3), [4..7] meta re, [8..11] meta im
+    uint32_t* st = Q.st;
+    Meta* stm = reinterpret_cast<Meta*>(st + 4);
+    auto colref = [&](int c) { auto s = Q.acol(c); return RRef{s.generic(), decltype(s)::GSTRIDE}; };
+#pragma unroll 1
+    for (int64_t bmax = b_first; bmax <= b_last; bmax++) {
+        const int64_t e = bmax + v;
+        const int64_t bmin = clampi(e - p.degree, 0, bmax);
+        const int cnt = (int)(bmax - bmin);
+        const int64_t base = (bmax + v - p.tbl_row0) * (W + 2);
+        CB_COOP_EACH(Q, q) {
+            if (q == 0) { st[0] = 0u; st[1] = 2u; stm[0] = meta_zero(); stm[1] = meta_zero(); }
+        }
+        Q.sync();
+#pragma unroll 1
+        for (int k = 0; k < cnt; k++) {
+            CRef x = at<L>(p.res, bmin + k, slot), y = at<L>(p.tbl, base + k, 0);
+            Opd a = re_of(x), b = im_of(x);
+            Opd c = dyn(re_of_shared(y)), d = dyn(im_of_shared(y));
+            const int are = (int)st[0], aim = (int)st[1];   // accumulator columns; the spare ones are their partners
+            const int sre = are ^ 1, sim = aim ^ 1;
+            auto sr = Q.acol(sre);
+            auto si = Q.acol(sim);
+            // (the meta records of the two products go to the state words)
+            FdotJob<L> jr{a, c, b, d, true, WRef{sr.generic(), decltype(sr)::GSTRIDE}, stm + 2};
+            FdotJob<L> ji{a, d, b, c, false, WRef{si.generic(), decltype(si)::GSTRIDE}, stm + 3};
+            coop_fdot2_pair<L>(Q, jr, ji, true);
+            CB_COOP_EACH(Q, q) {
+                if (q & 1) continue;
+                const int part = q >> 1;
+                const int ac = part ? aim : are, sc = part ? sim : sre;
+                Meta pr = stm[2 + part], tacc = stm[part];
+                if (k == 0) {  // 0 - x = -x exactly: adopt the column, flip the sign
+                    if (!is_nan(pr) && !is_zero_mid(pr)) pr.flags ^= F_SIGN;
+                    stm[part] = pr;
+                    st[part] = (uint32_t)sc;
+                } else {
+                    auto A = Q.acol(ac);
+                    auto B = Q.acol(sc);
+                    decltype(A) where = A;
+                    Meta t = arb_addsub_cols<L>(A, tacc, B, pr, true, &where);
+                    stm[part] = t;
+                    st[part] = (where.a_or_p() == B.a_or_p()) ? (uint32_t)sc : (uint32_t)ac;
+                }
+            }
+            Q.sync();
+        }
+        CRef out = at<L>(p.res, bmax, slot);
+        const int are = (int)st[0], aim = (int)st[1];
+        Opd xa{colref(are), stm[0]}, xb{colref(aim), stm[1]};
+        if (p.kind[(bmax + v - p.tbl_row0) * p.kind_stride] == 1) {
+            CRef y = at<L>(p.tbl, base + W + 1, 0);
+            Opd c = dyn(re_of_shared(y)), d = dyn(im_of_shared(y));
+            FdotJob<L> jr{xa, c, xb, d, true, wre(out), out.t}, ji{xa, d, xb, c, false, wim(out), out.t + 1};
+            coop_fdot2_pair<L>(Q, jr, ji, true);
+        } else {
+            CRef y = at<L>(p.tbl, base + cnt, 0);
+            CB_COOP_EACH(Q, q) {
+                if (q & 1) continue;
+                Opd c = re_of(y);
+                if (q == 0) st_meta(out.t, arb_div<L>(wre(out), xa, c, Q.col(0), Q.col(1)));
+                else st_meta(out.t + 1, arb_div<L>(wim(out), xb, c, Q.col(2), Q.col(3)));
+            }
+            Q.sync();
         }
     }
 }

@@ -382,8 +382,8 @@ CB_HD bool fuchs_intop_fast_coeff(const FuchsIntParams& p, int64_t inst, const i
 
 // The recurrence of one instance over coefficients [b_first, b_last]: the fast path per coefficient, the general
 // shared-memory path (fuchs_intop_thread on that single coefficient: it resumes from res) where it does not apply.
-template <int L, class SCR>
-CB_HD void fuchs_intop_fast_thread(const FuchsIntParams& p, int64_t inst, SCR S0, SCR A0, SCR A1, SCR A2,
+template <int L, class S0T, class SCR>
+CB_HD void fuchs_intop_fast_thread(const FuchsIntParams& p, int64_t inst, S0T S0, SCR A0, SCR A1, SCR A2,
                                    int64_t n_from = -1, int64_t n_to = -1) {
     const int ne = (p.order + 1) * (p.degree + 1);
     int64_t P[INTOP_MAXENT];

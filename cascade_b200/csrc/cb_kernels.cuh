@@ -125,6 +125,52 @@ __global__ void __launch_bounds__(CoopCfg<L>::TPB, 1) frobenius1_coop_kernel(Fro
         }
     }
 }
+// the shared-operator Fuchs recurrence on four lanes per instance (few solutions of one operator: analytic
+// continuation, monodromy), work units of G instances x RANGE coefficients as above
+template <int L> struct CoopFuchsCfg {
+    static constexpr int TPB = L <= 64 ? 256 : 128, G = TPB / 4, RANGE = 32, STATE = 24;
+    static constexpr size_t SMEM = (size_t)(CoopCfg<L>::KS + L + 2) * TPB * sizeof(uint32_t) + (size_t)STATE * G * sizeof(uint32_t);
+};
+template <int L>
+__global__ void __launch_bounds__(CoopFuchsCfg<L>::TPB, 1) fuchs_shared_coop_kernel(FuchsSharedParams p) {
+    if constexpr (CoopCfg<L>::ON) {
+        extern __shared__ __align__(16) uint32_t cb_smem_cf[];
+        __shared__ int unit_s;
+        constexpr int TPB = CoopFuchsCfg<L>::TPB, G = CoopFuchsCfg<L>::G, KS = CoopCfg<L>::KS;
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cb_smem_cf);
+        uint32_t* state = cb_smem_cf + (size_t)(KS + L + 2) * TPB;
+        const int64_t nblocks = (p.batch + G - 1) / G;
+        const int64_t first = p.n_begin > -p.valuation ? p.n_begin : -p.valuation;
+        const int64_t nranges = (p.n - first + CoopFuchsCfg<L>::RANGE) / CoopFuchsCfg<L>::RANGE;
+        const int64_t total = nblocks * nranges;
+        for (;;) {
+            if (threadIdx.x == 0) {
+                int u = atomicAdd(p.sched, 1);
+                if (u < total) {
+                    int64_t b = u % nblocks, r = u / nblocks;
+                    while (r > 0 && atomicAdd(p.sched + 1 + b, 0) < (int)r) __nanosleep(200);
+                    __threadfence();
+                }
+                unit_s = u;
+            }
+            __syncthreads();
+            const int64_t u = unit_s;
+            if (u >= total) break;
+            const int64_t b = u % nblocks, r = u / nblocks;
+            const int64_t inst = b * G + (threadIdx.x >> 2);
+            const int64_t lo = first + r * CoopFuchsCfg<L>::RANGE;
+            const int64_t hi = lo + CoopFuchsCfg<L>::RANGE - 1 < p.n ? lo + CoopFuchsCfg<L>::RANGE - 1 : p.n;
+            Quad<TPB, KS> Q{(int)(threadIdx.x & 3), 0xFu << (threadIdx.x & 28), sbase + 4u * threadIdx.x,
+                            p.gcols + (size_t)b * TPB + threadIdx.x, (uint32_t)(nblocks * TPB),
+                            sbase + 4u * (uint32_t)(KS * TPB) + 4u * threadIdx.x,
+                            state + (size_t)CoopFuchsCfg<L>::STATE * (threadIdx.x >> 2)};
+            if (inst < p.batch) fuchs_shared_coop_quad<L>(p, inst, Q, lo, hi);
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) atomicExch(p.sched + 1 + b, (int)(r + 1));
+        }
+    }
+}
 // Horner on four lanes per point: one CTA per block of 64 points
 template <int L>
 __global__ void __launch_bounds__(CoopCfg<L>::TPB, 1) horner_coop_kernel(HornerParams p) {
@@ -405,18 +451,27 @@ __global__ void __launch_bounds__(TPB, 1) fuchs_shared_persistent_kernel(FuchsSh
     }
 }
 
-// integer-operator kernel: 4 columns of ~L+3 words per thread, light on registers
-template <int L> struct IntopCfg { static constexpr int TPB = L <= 32 ? 384 : (L == 64 ? 192 : 96); };
+// integer-operator kernel: three accumulator columns of L + 2 words per thread in shared memory (the general body's
+// product column is in global memory: FuchsIntParams::gs0).  1024 bits: 12 warps at 168 registers -- 16 warps at 128
+// registers (CB_INTOP_TPB32=512) were measured 4 % SLOWER: 420 bytes of spills put the gain back into local-memory waits
+#ifndef CB_INTOP_TPB32
+#define CB_INTOP_TPB32 384
+#endif
+template <int L> struct IntopCfg {
+    static constexpr int TPB = L <= 4 ? 384 : (L <= 32 ? CB_INTOP_TPB32 : (L == 64 ? 192 : 96));
+    static constexpr size_t SMEM = (size_t)3 * (L + 2) * TPB * sizeof(uint32_t);
+};
+inline int intop_tpb(int L) { return L <= 4 ? IntopCfg<4>::TPB : (L <= 32 ? IntopCfg<32>::TPB : (L == 64 ? IntopCfg<64>::TPB : IntopCfg<128>::TPB)); }
 template <int L>
 __global__ void __launch_bounds__(IntopCfg<L>::TPB, 1) fuchs_intop_kernel(FuchsIntParams p) {
     extern __shared__ uint32_t cb_smem[];
     constexpr int TPB = IntopCfg<L>::TPB;
-    constexpr uint32_t W0 = L + 3, AW = L + 2;
+    constexpr uint32_t AW = L + 2;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cb_smem) + 4u * threadIdx.x;
-    Scratch<TPB> S0{sbase}, A0{sbase + 4u * W0 * TPB}, A1{sbase + 4u * (W0 + AW) * TPB},
-        A2{sbase + 4u * (W0 + 2 * AW) * TPB};
+    Scratch<TPB> A0{sbase}, A1{sbase + 4u * AW * TPB}, A2{sbase + 4u * 2 * AW * TPB};
     const int64_t idx = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (idx >= p.batch) return;
+    GScratch S0{p.gs0 + idx, p.gs0_stride};
     if constexpr (L <= 32) fuchs_intop_fast_thread<L>(p, idx, S0, A0, A1, A2);
     else fuchs_intop_thread<L>(p, idx, S0, A0, A1, A2);
 }
@@ -428,10 +483,9 @@ __global__ void __launch_bounds__(IntopCfg<L>::TPB, 1) fuchs_intop_persistent_ke
     extern __shared__ uint32_t cb_smem[];
     __shared__ int unit_s;
     constexpr int TPB = IntopCfg<L>::TPB;
-    constexpr uint32_t W0 = L + 3, AW = L + 2;
+    constexpr uint32_t AW = L + 2;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cb_smem) + 4u * threadIdx.x;
-    Scratch<TPB> S0{sbase}, A0{sbase + 4u * W0 * TPB}, A1{sbase + 4u * (W0 + AW) * TPB},
-        A2{sbase + 4u * (W0 + 2 * AW) * TPB};
+    Scratch<TPB> A0{sbase}, A1{sbase + 4u * AW * TPB}, A2{sbase + 4u * 2 * AW * TPB};
     const int64_t nblocks = (p.batch + TPB - 1) / TPB;
     const int64_t first = -p.valuation;
     const int64_t nranges = (p.n - first + p.range_len) / p.range_len;
@@ -453,6 +507,7 @@ __global__ void __launch_bounds__(IntopCfg<L>::TPB, 1) fuchs_intop_persistent_ke
         const int64_t inst = b * TPB + threadIdx.x;
         const int64_t lo = first + r * p.range_len;
         const int64_t hi = lo + p.range_len - 1 < p.n ? lo + p.range_len - 1 : p.n;
+        GScratch S0{p.gs0 + (size_t)b * TPB + threadIdx.x, p.gs0_stride};
         if (inst < p.batch) {
             if constexpr (L <= 32) fuchs_intop_fast_thread<L>(p, inst, S0, A0, A1, A2, lo, hi);
             else fuchs_intop_thread<L>(p, inst, S0, A0, A1, A2, lo, hi);
@@ -610,6 +665,29 @@ int launch_coop_frob(const FrobParams& p, cudaStream_t s) {
     frobenius1_coop_kernel<L><<<grid, CoopCfg<L>::TPB, CoopCfg<L>::SMEM, s>>>(p);
     return (int)cudaGetLastError();
 }
+// the Fuchs recurrence on four lanes per instance: a shared operator and at most one wave of cooperative CTAs (few
+// solutions continued along a path); measured on B200 (profiles/coop_r02.txt)
+template <int L>
+bool use_coop_fuchs(const FuchsSharedParams& p, int sms) {
+    if (!CoopCfg<L>::ON || p.per_inst || !p.sched) return false;
+    const char* e = getenv("CB200_COOP");
+    if (e && e[0] == '0') return false;
+    if (e && e[0] == '1') return true;
+    return p.batch <= (int64_t)sms * CoopFuchsCfg<L>::G / 4;
+}
+template <int L>
+int launch_coop_fuchs(const FuchsSharedParams& p, int sms, cudaStream_t s) {
+    if (p.batch <= 0) return 0;
+    cudaError_t e = cudaFuncSetAttribute(fuchs_shared_coop_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)CoopFuchsCfg<L>::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t nblocks = (p.batch + CoopFuchsCfg<L>::G - 1) / CoopFuchsCfg<L>::G;
+    e = cudaMemsetAsync(p.sched, 0, sizeof(int) * (size_t)(nblocks + 1), s);
+    if (e != cudaSuccess) return (int)e;
+    const int grid = (int)(nblocks < sms ? nblocks : sms);
+    fuchs_shared_coop_kernel<L><<<grid, CoopFuchsCfg<L>::TPB, CoopFuchsCfg<L>::SMEM, s>>>(p);
+    return (int)cudaGetLastError();
+}
 template <int L>
 bool use_coop_horner(const HornerParams& p) {
     return CoopCfg<L>::ON && p.gcols_words >= coop_tail_words(L, p.npts) && coop_wanted<L>(p.npts, sm_count(), false);
@@ -681,6 +759,7 @@ struct LaunchTable {
     static int fsh_##LL(const FuchsSharedParams& p, cudaStream_t s) {                                      \
         int dev = 0, sms = 148;                                                                            \
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); \
+        if (use_coop_fuchs<LL>(p, sms)) return launch_coop_fuchs<LL>(p, sms, s);                           \
         if (p.per_inst) /* a table row per instance (operators differ between instances) */                \
             return launch<LL>(fuchs_shared_kernel<LL, CfgShared<LL>::TPB, false, false, true>, p, p.batch, s,       \
                               CfgShared<LL>::TPB, Sizes<LL>::SMEM_SHARED_PER_THREAD * CfgShared<LL>::TPB);  \
@@ -701,7 +780,7 @@ struct LaunchTable {
                           Sizes<LL>::SMEM_SHARED_PER_THREAD * CfgShared<LL>::TPB);                         \
     }                                                                                                      \
     static int fint_##LL(const FuchsIntParams& p, cudaStream_t s) {                                        \
-        const size_t smem = (size_t)(LL + 3 + 3 * (LL + 2)) * IntopCfg<LL>::TPB * sizeof(uint32_t);        \
+        const size_t smem = IntopCfg<LL>::SMEM;                                                            \
         if (p.sched) { /* persistent launch: no last-wave tail */                                          \
             int dev = 0, sms = 148;                                                                        \
             if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); \

@@ -517,11 +517,15 @@ struct FuchsIntParams {
     // persistent launch (cb_kernels.cuh): see FuchsSharedParams
     int64_t range_len;
     int* sched;
+    // the product column of the general body lives in GLOBAL memory ([word][lane], L + 3 words per lane): only the
+    // coefficients the register fast path hands back use it, and without it in shared memory a CTA holds 16 warps
+    uint32_t* gs0;
+    size_t gs0_stride;
 };
 constexpr int INTOP_MAXENT = 36;  // (order+1)(degree+1) <= 36
 
-template <int L, class SCR>
-CB_HD void fuchs_intop_thread(const FuchsIntParams& p, int64_t inst, SCR S0, SCR A0, SCR A1, SCR A2,
+template <int L, class S0T, class SCR>
+CB_HD void fuchs_intop_thread(const FuchsIntParams& p, int64_t inst, S0T S0, SCR A0, SCR A1, SCR A2,
                               int64_t n_from = -1, int64_t n_to = -1) {
     const size_t slot = 2 * (size_t)inst;
     const int v = p.valuation, D1 = p.degree + 1;

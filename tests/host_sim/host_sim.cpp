@@ -51,6 +51,8 @@ void run_hyb(int64_t count, F body) {
         default: return CB200_EINVAL;                         \
     }
 }  // namespace
+template <int L>
+static int sim_fuchs_shared_coop(FuchsSharedParams& sp);
 
 extern "C" {
 
@@ -104,6 +106,10 @@ int cbsim_fuchs_batch_range(int L_, int order, int degree, int valuation, int64_
         tp.kind = kind.data(); tp.row0 = n_begin + valuation; tp.nrows = rows - tp.row0; tp.ninst = 1; tp.tbl_row0 = 0;
         SIM_DISPATCH(L_, run<L>(tp.nrows, [&](int64_t i, Scratch<1> a, Scratch<1> b) { fuchs_table_fast_thread<L>(tp, i, a, b); }));
         sp.n = n; sp.tbl = tp.tbl; sp.kind = kind.data(); sp.n_begin = n_begin; sp.tbl_row0 = 0; sp.kind_stride = 1; sp.per_inst = 0;
+        if (getenv("CBSIM_COOP") && L_ >= 64) {
+            int rc = L_ == 64 ? sim_fuchs_shared_coop<64>(sp) : sim_fuchs_shared_coop<128>(sp);
+            return rc ? rc : canaries_ok();
+        }
         if (sp.no_rr) {
             SIM_DISPATCH(L_, for (int64_t i = 0; i < batch; i++) (fuchs_shared_thread<L, false>)(sp, i, S0, S1, A0, A1, A2, G0, G1));
         } else {
@@ -136,12 +142,14 @@ int cbsim_fuchs_intop_batch(int L_, int order, int degree, int valuation, int64_
     FuchsIntParams p;
     p.order = order; p.degree = degree; p.valuation = valuation; p.n = n; p.batch = batch;
     p.ode = ode_int; p.ostride = shared_ode ? 0 : (size_t)batch; p.sched = nullptr; p.range_len = 32;
+    p.gs0 = nullptr; p.gs0_stride = 0;
     p.res = CArr{res_mant, (Meta*)res_meta, (size_t)(2 * batch)};
     const size_t sizes[4] = {(size_t)L_ + 3, (size_t)L_ + 2, (size_t)L_ + 2, (size_t)L_ + 2};
     const size_t CAN = 64;
     std::vector<uint32_t> col[4];
     for (int c = 0; c < 4; c++) col[c].assign(sizes[c] + CAN, 0xDEADBEEFu);
-    Scratch<1> S0{col[0].data()}, A0{col[1].data()}, A1{col[2].data()}, A2{col[3].data()};
+    GScratch S0{col[0].data(), 1};  // the product column of the general body is a global-memory column on the device
+    Scratch<1> A0{col[1].data()}, A1{col[2].data()}, A2{col[3].data()};
     // the register fast path with the shared-memory body as per-coefficient fallback (what the kernels run at <= 1024
     // bits); CBSIM_INTOP_GENERAL=1 runs the general body alone
     const bool general_only = getenv("CBSIM_INTOP_GENERAL") != nullptr;
@@ -428,6 +436,28 @@ struct SimQuad {
         return 0;
     }
 };
+template <int L>
+static int sim_fuchs_shared_coop(FuchsSharedParams& sp) {
+    if constexpr (L >= 64) {
+        SimQuad<L> sq;
+        std::vector<uint32_t> acols[4];
+        std::vector<uint32_t> state(32, 0u);
+        for (int c = 0; c < 4; c++) {
+            acols[c].assign(L + 2 + 32, 0xDEADBEEFu);
+            sq.Q.p2[c] = acols[c].data();
+        }
+        sq.Q.st = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(state.data()) + 15) & ~(uintptr_t)15);
+        const int64_t first = sp.n_begin > -sp.valuation ? sp.n_begin : -sp.valuation;
+        for (int64_t lo = first; lo <= sp.n; lo += 32)
+            for (int64_t i = 0; i < sp.batch; i++) fuchs_shared_coop_quad<L>(sp, i, sq.Q, lo, lo + 31 < sp.n ? lo + 31 : sp.n);
+        for (int c = 0; c < 4; c++)
+            for (size_t k = L + 2; k < (size_t)L + 2 + 32; k++)
+                if (acols[c][k] != 0xDEADBEEFu) return -2200 - c;
+        return sq.check();
+    } else {
+        return CB200_EINVAL;
+    }
+}
 template <int L>
 static int sim_frobenius1_coop(FrobParams& p) {
     if constexpr (L >= 64) {

@@ -167,7 +167,7 @@ def test_frobenius_general_edge(oracle, sim_driver, L):
 
 
 @pytest.mark.parametrize("L", [64, 128])
-def test_cooperating_lanes(oracle, L):
+def test_cooperating_lanes(monkeypatch, oracle, L):
     """cb_coop.cuh: four lanes per instance (the products of a complex multiplication on four lanes, real and imaginary
     parts of everything else on two), simulated lane by lane and phase by phase: Frobenius M = 1 and Horner, including
     the cancellation case that needs the exact full-width path on one lane's pair of hybrid columns."""
@@ -176,3 +176,9 @@ def test_cooperating_lanes(oracle, L):
     cases.case_frobenius(oracle, drv, L, seed=29, n=12 if L == 64 else 9, batch=5)
     cases.case_horner(oracle, drv, L, seed=23, length=14, npts=5)
     cases.case_horner_cancellation(oracle, drv, L, seed=213 + L, length=10, npts=12)
+    # the shared-operator Fuchs recurrence on four lanes per instance (CBSIM_COOP routes the simulation through it)
+    monkeypatch.setenv("CBSIM_COOP", "1")
+    cases.case_fuchs_bessel_shared(oracle, drv, L, seed=5, n=40 if L == 64 else 24, batch=5)
+    cases.case_fuchs_random_shared(oracle, drv, L, seed=41 + L, trials=3, batch=4)
+    cases.case_fuchs_shared_adversarial(oracle, drv, L, seed=87 + L, batch=6)
+    cases.case_continuation(oracle, drv, L, seed=23 + L, steps=3, n=20, batch=2)

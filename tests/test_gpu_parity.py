@@ -107,6 +107,11 @@ def test_cooperating_lanes(monkeypatch, oracle, gpu_driver, L, coop):
     cases.case_horner(oracle, gpu_driver, L, seed=37, length=30, npts=301)
     cases.case_horner_cancellation(oracle, gpu_driver, L, seed=313 + L, length=20, npts=300)
     cases.case_continuation(oracle, gpu_driver, L, seed=123 + L, steps=3, n=24, batch=7)
+    # the shared-operator Fuchs recurrence on four lanes per instance (what a continuation of few solutions runs)
+    cases.case_fuchs_bessel_shared(oracle, gpu_driver, L, seed=5, n=70 if L == 64 else 40, batch=2)
+    cases.case_fuchs_bessel_shared(oracle, gpu_driver, L, seed=6, n=40, batch=131)
+    cases.case_fuchs_random_shared(oracle, gpu_driver, L, seed=141 + L, trials=3, batch=45)
+    cases.case_fuchs_shared_adversarial(oracle, gpu_driver, L, seed=187 + L, batch=70)
 
 
 @pytest.mark.parametrize("L", [32, 64, 128])
