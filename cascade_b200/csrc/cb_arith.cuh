@@ -66,6 +66,18 @@ CB_HD void tz_scan(O& o) {
     }
     o.t.flags |= (uint32_t)tz << F_TZ_SHIFT;
 }
+// the four operands of a fused dot product at once: the first limbs of those without a hint are loaded together (one
+// memory round trip instead of four); only operands whose first limb is zero go on to the scan
+template <int L, class O1, class O2>
+CB_HD void tz_scan4(O1& x1, O2& y1, O1& x2, O2& y2) {
+    auto open = [](uint32_t f) { return tz_hint(f) == 0 && !(f & (F_ZERO | F_NAN)); };
+    const bool ox1 = open(x1.t.flags), oy1 = open(y1.t.flags), ox2 = open(x2.t.flags), oy2 = open(y2.t.flags);
+    const uint32_t a = ox1 ? x1.r.ld(0) : 1u, b = oy1 ? y1.r.ld(0) : 1u, c = ox2 ? x2.r.ld(0) : 1u, d = oy2 ? y2.r.ld(0) : 1u;
+    if (a == 0u) tz_scan<L>(x1);
+    if (b == 0u) tz_scan<L>(y1);
+    if (c == 0u) tz_scan<L>(x2);
+    if (d == 0u) tz_scan<L>(y2);
+}
 constexpr int32_t EXP_LIMIT = 1 << 28;
 
 struct Meta {
@@ -186,11 +198,13 @@ struct HybridScratch {
 template <class S> struct ScrLo {
     using type = S;
     static constexpr bool HYBRID = false;
+    static constexpr int LO_WORDS = 1 << 30;
     static CB_HD S get(S s) { return s; }
 };
 template <int ST, int KS> struct ScrLo<HybridScratch<ST, KS>> {
     using type = Scratch<ST>;
     static constexpr bool HYBRID = true;
+    static constexpr int LO_WORDS = KS;
     static CB_HD Scratch<ST> get(HybridScratch<ST, KS> s) { return s.lo(); }
 };
 // the shared-memory part of a column (the column itself unless it is a HybridScratch)
@@ -344,6 +358,24 @@ struct WRef {
     size_t stride;
     CB_HD void st(int j, uint32_t v) const { m[(size_t)j * stride] = v; }
 };
+
+// put(j, word(j)) for j in [0, N): the words of a block are all LOADED before the first one is stored.  Written as
+// `S.st(j, x.ld(j))` in one loop the store (a volatile shared-memory asm, or a store that may alias the source) pins
+// every load behind the store before it, and each word pays a full global-memory round trip (measured: a third of
+// the stall samples of the 4096-bit Frobenius kernel, profiles/ncu_frobenius1_128_r02_lines.txt).
+template <int N, class GET, class PUT>
+CB_HD void staged_copy(GET word, PUT put) {
+    constexpr int B = N < 32 ? N : 32;
+#pragma unroll 1
+    for (int base = 0; base < N; base += B) {
+        uint32_t w[B];
+#pragma unroll
+        for (int k = 0; k < B; k++) w[k] = (base + k < N) ? word(base + k) : 0u;
+#pragma unroll
+        for (int k = 0; k < B; k++)
+            if (base + k < N) put(base + k, w[k]);
+    }
+}
 
 // Rounded midpoint result description produced by extract()
 struct Rounded {
@@ -1181,10 +1213,8 @@ CB_NOINLINE Meta arb_addsub_impl(WRef dst, Opd x, Opd y, bool negy, SCR S0, SCR 
     }
     if (!done) {
         // (32 independent loads in flight per round: these operands come from global memory)
-#pragma unroll 32
-        for (int j = 0; j < L; j++) S0.st(j, x.r.ld(j));
-#pragma unroll 32
-        for (int j = 0; j < L; j++) S1.st(j, y.r.ld(j));
+        staged_copy<L>([&](int j) { return x.r.ld(j); }, [&](int j, uint32_t v) { S0.st(j, v); });
+        staged_copy<L>([&](int j) { return y.r.ld(j); }, [&](int j, uint32_t v) { S1.st(j, v); });
         rr = align_add<L, L>(dst, S0, S1, x.t.exp, y.t.exp, nx, ny, zx, zy, &neg);
     }
     if (nan) return meta_nan();
@@ -1331,12 +1361,15 @@ CB_NOINLINE Meta arb_div(DST dst, OpdT<XS> x, OpdT<YS> y, SCR S0, SCR S1) {
     constexpr bool RING = ScrLo<SCR>::HYBRID;
     constexpr int R = RING ? L + 2 : 2 * L + 2;
     auto slot = [](int k) { return (RING && k >= R) ? k - R : k; };  // k < 2R
-#pragma unroll
-    for (int j = 0; j < L; j++) S0.st(slot(L + j), (zx || nan) ? 0u : x.r.ld(j));
-    S0.st(slot(2 * L), 0u);
-#pragma unroll
-    for (int j = 0; j < L; j++) S1.st(j, nan ? (j == L - 1 ? 0x80000000u : 0u) : y.r.ld(j));
-    uint32_t d1 = S1.ld(L - 1), d0 = S1.ld(L - 2);
+    // the ring and the divisor sit in the shared-memory part of a hybrid column: addressed there directly (a
+    // HybridScratch access decides between shared and global memory word by word)
+    static_assert(!RING || ScrLo<SCR>::LO_WORDS >= R, "the ring must fit the shared part of a hybrid column");
+    const auto U = lo_view(S0), D = lo_view(S1);
+    staged_copy<L>([&](int j) { return (zx || nan) ? 0u : x.r.ld(j); }, [&](int j, uint32_t v) { U.st(slot(L + j), v); });
+    U.st(slot(2 * L), 0u);
+    staged_copy<L>([&](int j) { return nan ? (j == L - 1 ? 0x80000000u : 0u) : y.r.ld(j); },
+                   [&](int j, uint32_t v) { D.st(j, v); });
+    uint32_t d1 = D.ld(L - 1), d0 = D.ld(L - 2);
     // reciprocal of the (normalised) top divisor word, v = floor((2^64 - 1) / d1) - 2^32: ONE 64-bit division per
     // arb_div; every quotient-digit estimate below is then Moeller-Granlund's 2-by-1 division (two multiplies and
     // two corrections, exact) instead of a 64-bit division subroutine
@@ -1345,8 +1378,8 @@ CB_NOINLINE Meta arb_div(DST dst, OpdT<XS> x, OpdT<YS> y, SCR S0, SCR S1) {
     int hi = -1;
 #pragma unroll 1
     for (int j = L; j >= 0; j--) {
-        if (j < L) S0.st(j, 0u);  // U[j] enters the window (j < R: its own word)
-        uint32_t u2 = S0.ld(slot(j + L)), u1 = S0.ld(slot(j + L - 1)), u0 = S0.ld(slot(j + L - 2));
+        if (j < L) U.st(j, 0u);  // U[j] enters the window (j < R: its own word)
+        uint32_t u2 = U.ld(slot(j + L)), u1 = U.ld(slot(j + L - 1)), u0 = U.ld(slot(j + L - 2));
         uint64_t num = ((uint64_t)u2 << 32) | u1;
         uint64_t qh, rh;
         if (u2 >= d1) {
@@ -1379,28 +1412,43 @@ CB_NOINLINE Meta arb_div(DST dst, OpdT<XS> x, OpdT<YS> y, SCR S0, SCR S1) {
             for (int blk = 0; blk < L; blk += B) {
                 uint32_t dd[B], uu[B];
 #pragma unroll
-                for (int k = 0; k < B; k++) dd[k] = S1.ld(blk + k);
+                for (int k = 0; k < B; k++) dd[k] = D.ld(blk + k);
+                // a block that does not straddle the end of the ring is one run of words (the wrap is then paid once
+                // per block, not once per word)
+                const int base = j + blk;
+                const bool flat = !RING || base + B <= R || base >= R;
+                const int o = (RING && base >= R) ? base - R : base;
+                if (flat) {
 #pragma unroll
-                for (int k = 0; k < B; k++) uu[k] = S0.ld(slot(j + blk + k));
+                    for (int k = 0; k < B; k++) uu[k] = U.ld(o + k);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < B; k++) uu[k] = U.ld(slot(base + k));
+                }
                 div_row_block<B>(uu, dd, qd, mc, borrow);
+                if (flat) {
 #pragma unroll
-                for (int k = 0; k < B; k++) S0.st(slot(j + blk + k), uu[k]);
+                    for (int k = 0; k < B; k++) U.st(o + k, uu[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < B; k++) U.st(slot(base + k), uu[k]);
+                }
             }
         }
         const int top = slot(j + L);
-        uint64_t t = (uint64_t)S0.ld(top) - mc - borrow;
-        S0.st(top, (uint32_t)t);
+        uint64_t t = (uint64_t)U.ld(top) - mc - borrow;
+        U.st(top, (uint32_t)t);
         if ((uint32_t)(t >> 32) & 1u) {  // one too large: add the divisor back
             qd--;
             uint32_t c = 0u;
 #pragma unroll 8
             for (int i = 0; i < L; i++) {
                 const int k = slot(i + j);
-                uint64_t s = (uint64_t)S0.ld(k) + S1.ld(i) + c;
-                S0.st(k, (uint32_t)s);
+                uint64_t s = (uint64_t)U.ld(k) + D.ld(i) + c;
+                U.st(k, (uint32_t)s);
                 c = (uint32_t)(s >> 32);
             }
-            S0.st(top, S0.ld(top) + c);
+            U.st(top, U.ld(top) + c);
         }
         S1.st(L + j, qd);
         if (qd != 0u && hi < 0) hi = j;
@@ -1408,7 +1456,7 @@ CB_NOINLINE Meta arb_div(DST dst, OpdT<XS> x, OpdT<YS> y, SCR S0, SCR S1) {
     // remainder in U[0..L)
     uint32_t rem = 0u;
 #pragma unroll 8
-    for (int i = 0; i < L; i++) rem |= S0.ld(i);
+    for (int i = 0; i < L; i++) rem |= U.ld(i);
     // Q = S1[L .. 2L] (L+1 words), presented to extract() as a column starting at word L
     struct View {
         SCR s;

@@ -17,44 +17,50 @@
 
 namespace cb {
 
+// The four ROLES of an instance (role q forms product q and owns column q; roles 0 and 2 are the real / imaginary
+// workers) are played by four lanes (one role each) or by two lanes (lane 0: roles 0 and 1 -- both products and
+// everything else of the real part --, lane 1: roles 2 and 3).  Two lanes waste no issue slots in the O(L) phases and
+// are the form for batches that fill the SMs; four lanes halve the latency of a product pair once more and are the
+// form for a handful of instances.  CB_COOP_EACH runs the body for every role this lane plays.
 #if defined(__CUDA_ARCH__)
-template <int TPB, int KS>
+template <int STRIDE, int KS>
 struct Quad {
-    using Col = HybridScratch<TPB, KS>;
-    int q;            // this lane's index in its quad
-    unsigned qmask;   // the four lanes of the quad
-    uint32_t a;       // own column: shared-space byte address of word 0
-    uint32_t* g;      // own column: global tail
+    using Col = HybridScratch<STRIDE, KS>;
+    int q0, per;      // first role and number of roles of this lane
+    unsigned qmask;   // the lanes of this instance
+    uint32_t a0;      // column of role 0: shared-space byte address of word 0
+    uint32_t cstep;   // columns between the columns of consecutive roles (1: [word][4 i + role]; G: [word][role][i])
+    uint32_t* g0;     // global tail of the column of role 0 (same column order), gs words between its words
     uint32_t gs;
-    uint32_t a2 = 0;  // own column of a second region (L + 2 words per lane: accumulators of the recurrence kernel)
-    uint32_t* st = nullptr;  // 24 state words of the quad (shared memory, 16-byte aligned)
-    __device__ __forceinline__ Col col(int qq) const { return Col{a + 4u * (uint32_t)(qq - q), g + (qq - q), gs}; }
-    __device__ __forceinline__ Scratch<TPB> acol(int qq) const { return Scratch<TPB>{a2 + 4u * (uint32_t)(qq - q)}; }
+    uint32_t a20 = 0;        // column of role 0 in a second region (L + 2 words: accumulators of the recurrence kernel)
+    uint32_t* st = nullptr;  // 24 state words of the instance (shared memory, 16-byte aligned)
+    __device__ __forceinline__ Col col(int c) const { return Col{a0 + 4u * cstep * (uint32_t)c, g0 + (size_t)cstep * c, gs}; }
+    __device__ __forceinline__ Scratch<STRIDE> acol(int c) const { return Scratch<STRIDE>{a20 + 4u * cstep * (uint32_t)c}; }
     __device__ __forceinline__ void sync() const { __syncwarp(qmask); }
 };
-#define CB_COOP_EACH(Q, qv) for (int qv = (Q).q, qv##_go = 1; qv##_go; qv##_go = 0)
 #else
-template <int TPB, int KS>
+template <int STRIDE, int KS>
 struct Quad {
-    using Col = HybridScratch<TPB, KS>;
+    using Col = HybridScratch<STRIDE, KS>;
+    int q0 = 0, per = 4;  // the simulation plays all four roles, phase by phase
     uint32_t* p[4];
     uint32_t* g[4];
     uint32_t* p2[4] = {nullptr, nullptr, nullptr, nullptr};
     uint32_t* st = nullptr;
     Col col(int qq) const { return Col{p[qq], g[qq], 1u}; }
-    Scratch<TPB> acol(int qq) const { return Scratch<TPB>{p2[qq]}; }
+    Scratch<STRIDE> acol(int qq) const { return Scratch<STRIDE>{p2[qq]}; }
     void sync() const {}
 };
-#define CB_COOP_EACH(Q, qv) for (int qv = 0; qv < 4; qv++)
 #endif
+#define CB_COOP_EACH(Q, qv) for (int qv = (Q).q0; qv < (Q).q0 + (Q).per; qv++)
 
 // ---- copies and constants, limbs dealt out to the four lanes
 template <int L, class QD>
 CB_HD void coop_set(const QD& Q, const CRef& z, const CRef& x) {
     CB_COOP_EACH(Q, q) {
-        const int part = q & 1;
-#pragma unroll 8
-        for (int k = (q >> 1); k < L; k += 2) z.m[k * z.stride + part] = x.m[k * x.stride + part];
+        const int part = q & 1, k0 = q >> 1;
+        staged_copy<L / 2>([&](int j) { return x.m[(size_t)(2 * j + k0) * x.stride + part]; },
+                           [&](int j, uint32_t v) { z.m[(size_t)(2 * j + k0) * z.stride + part] = v; });
         if (q < 2) st_meta(z.t + q, ld_meta(x.t + q));
     }
     Q.sync();
@@ -92,12 +98,24 @@ struct FdotJob {
 };
 template <int L, class QD>
 CB_HD void coop_fdot2_pair(const QD& Q, const FdotJob<L>& j0, const FdotJob<L>& j1, bool have1) {
-    CB_COOP_EACH(Q, q) {  // the products
+    // the products: every lane works through the non-zero ones among its roles in step with the others (a lane playing
+    // two roles whose first product is zero starts on its second at once)
+    unsigned todo = 0u;
+    CB_COOP_EACH(Q, q) {
         const FdotJob<L>& j = (q >> 1) ? j1 : j0;
         if ((q >> 1) && !have1) continue;
+        const uint32_t fl = (q & 1) ? (j.x2.t.flags | j.y2.t.flags) : (j.x1.t.flags | j.y1.t.flags);
+        if (!(fl & (F_ZERO | F_NAN))) todo |= 1u << q;
+    }
+#pragma unroll 1
+    while (todo) {
+        int q = 0;
+        while (!((todo >> q) & 1u)) q++;
+        todo &= todo - 1u;
+        const FdotJob<L>& j = (q >> 1) ? j1 : j0;
         const Opd& xo = (q & 1) ? j.x2 : j.x1;
         const Opd& yo = (q & 1) ? j.y2 : j.y1;
-        if (!((xo.t.flags | yo.t.flags) & (F_ZERO | F_NAN))) product_trunc_blocked<L>(lo_view(Q.col(q)), xo.r, yo.r);
+        product_trunc_blocked<L>(lo_view(Q.col(q)), xo.r, yo.r);
     }
     Q.sync();
     CB_COOP_EACH(Q, q) {  // align, add, round
@@ -107,10 +125,7 @@ CB_HD void coop_fdot2_pair(const QD& Q, const FdotJob<L>& j0, const FdotJob<L>& 
         Opd x1 = j.x1, y1 = j.y1, x2 = j.x2, y2 = j.y2;
         // short (integer-like) operands make exact products, whose guard bits prove nothing: knowing their trailing
         // zero limbs lets the truncated path accept them as exact (as fdot2_auto does)
-        tz_scan<L>(x1);
-        tz_scan<L>(y1);
-        tz_scan<L>(x2);
-        tz_scan<L>(y2);
+        tz_scan4<L>(x1, y1, x2, y2);
         const FdotPrep f = fdot2_prep<L>(x1, y1, x2, y2, j.neg2);
         bool ok;
         Meta t = fdot2_tb_tail<L>(j.dst, f, lo_view(Q.col(q)), lo_view(Q.col(q + 1)), &ok);
@@ -128,20 +143,33 @@ CB_HD void coop_mul(const QD& Q, const CRef& z, const CRef& x, const CRef& y) {
     FdotJob<L> jr{a, c, b, d, true, wre(z), z.t}, ji{a, d, b, c, false, wim(z), z.t + 1};
     coop_fdot2_pair<L>(Q, jr, ji, true);
 }
-// z = x +- y (componentwise; z may alias x or y): real part on lane 0, imaginary part on lane 2
+// part 0 / 1 of a complex ball as an operand / a destination.  The componentwise operations below run ONE call with the
+// operands chosen by the part, so the real and the imaginary workers of a warp stay converged (two calls, one per
+// part, would run one after the other).
+CB_HD Opd part_of(const CRef& x, int part) { return Opd{RRef{x.m + part, x.stride}, ld_meta_user(x.t + part)}; }
+CB_HD WRef wpart(const CRef& z, int part) { return WRef{z.m + part, z.stride}; }
+// z = x +- y (componentwise; z may alias x or y): real part on role 0, imaginary part on role 2
 template <int L, class QD>
 CB_HD void coop_addsub(const QD& Q, const CRef& z, const CRef& x, const CRef& y, bool sub) {
     CB_COOP_EACH(Q, q) {
         if (q & 1) continue;
         const int part = q >> 1;
-        Meta t = part ? arb_addsub<L>(wim(z), im_of(x), im_of(y), sub, Q.col(q), Q.col(q + 1))
-                      : arb_addsub<L>(wre(z), re_of(x), re_of(y), sub, Q.col(q), Q.col(q + 1));
+        Meta t = arb_addsub<L>(wpart(z, part), part_of(x, part), part_of(y, part), sub, Q.col(q), Q.col(q + 1));
         st_meta(z.t + part, t);
     }
     Q.sync();
 }
-// z = x + k (acb_add_si): the real part gets the integer (lane 0), the imaginary part is copied (lane 2)
+// the imaginary part of x into z (role 2)
 template <int L, class QD>
+CB_HD void coop_copy_im(const QD& Q, const CRef& z, const CRef& x) {
+    CB_COOP_EACH(Q, q) {
+        if (q == 2) acb_copy_im<L>(z, x);
+    }
+    Q.sync();
+}
+// z = x + k (acb_add_si): the real part gets the integer (role 0), the imaginary part is copied (role 2) unless the
+// caller has put it there already (COPY_IM = false)
+template <int L, bool COPY_IM = true, class QD>
 CB_HD void coop_add_si(const QD& Q, const CRef& z, const CRef& x, int64_t k, const CRef& kball) {
     CB_COOP_EACH(Q, q) {
         if (q == 0) {
@@ -156,10 +184,8 @@ CB_HD void coop_add_si(const QD& Q, const CRef& z, const CRef& x, int64_t k, con
             Opd ko{RRef{kball.m, kball.stride}, kt};
             Meta tr = arb_addsub<L>(wre(z), re_of(x), ko, false, Q.col(0), Q.col(1));
             st_meta(z.t, tr);
-        } else if (q == 2 && z.m != x.m) {
-#pragma unroll 8
-            for (int j = 0; j < L; j++) z.m[j * z.stride + 1] = x.m[j * x.stride + 1];
-            st_meta(z.t + 1, ld_meta(x.t + 1));
+        } else if (COPY_IM && q == 2 && z.m != x.m) {
+            acb_copy_im<L>(z, x);
         }
     }
     Q.sync();
@@ -172,14 +198,11 @@ CB_HD void coop_inv(const QD& Q, const CRef& z, const CRef& y, const CRef& tmp) 
     coop_fdot2_pair<L>(Q, jt, jt, false);
     CB_COOP_EACH(Q, q) {
         if (q & 1) continue;
+        const int part = q >> 1;
         Opd t{RRef{tmp.m, tmp.stride}, ld_meta(tmp.t)};
-        if (q == 0) {
-            st_meta(z.t, arb_div<L>(wre(z), c, t, Q.col(0), Q.col(1)));
-        } else {
-            Meta ti = arb_div<L>(wim(z), d, t, Q.col(2), Q.col(3));
-            if (!is_nan(ti) && !is_zero_mid(ti)) ti.flags ^= F_SIGN;
-            st_meta(z.t + 1, ti);
-        }
+        Meta r = arb_div<L>(wpart(z, part), part ? d : c, t, Q.col(q), Q.col(q + 1));
+        if (part && !is_nan(r) && !is_zero_mid(r)) r.flags ^= F_SIGN;
+        st_meta(z.t + part, r);
     }
     Q.sync();
 }
@@ -189,9 +212,8 @@ CB_HD void coop_div(const QD& Q, const CRef& z, const CRef& x, const CRef& y, co
     if (is_exact_zero(ld_meta(y.t + 1))) {
         CB_COOP_EACH(Q, q) {
             if (q & 1) continue;
-            Opd c = re_of(y);
-            if (q == 0) st_meta(z.t, arb_div<L>(wre(z), re_of(x), c, Q.col(0), Q.col(1)));
-            else st_meta(z.t + 1, arb_div<L>(wim(z), im_of(x), c, Q.col(2), Q.col(3)));
+            const int part = q >> 1;
+            st_meta(z.t + part, arb_div<L>(wpart(z, part), part_of(x, part), re_of(y), Q.col(q), Q.col(q + 1)));
         }
         Q.sync();
     } else {
@@ -201,7 +223,7 @@ CB_HD void coop_div(const QD& Q, const CRef& z, const CRef& x, const CRef& y, co
 }
 
 // indicial_polynomial_evaluate (reference src/frobenius_solver.c:41-70), as indicial_eval of cb_solvers.cuh
-template <int L, class QD, class PRM>
+template <int L, bool IM_READY = false, class QD, class PRM>
 CB_HD CRef coop_indicial_eval(const QD& Q, const PRM& p, size_t oslot, int64_t nu, const CRef& rho, int64_t shift, CRef o1,
                               CRef o2, const CRef& t, const CRef& kb) {
     const int D1 = p.degree + 1;
@@ -210,7 +232,7 @@ CB_HD CRef coop_indicial_eval(const QD& Q, const PRM& p, size_t oslot, int64_t n
     if (nu > p.degree) return o1;
 #pragma unroll 1
     for (int64_t lam = clampi(p.degree - nu, 0, p.order); lam >= 0; lam--) {
-        coop_add_si<L>(Q, t, rho, shift - lam, kb);
+        coop_add_si<L, !IM_READY>(Q, t, rho, shift - lam, kb);
         coop_mul<L>(Q, o2, o1, t);
         CRef sw = o1;
         o1 = o2;
@@ -236,17 +258,18 @@ CB_HD void frobenius1_coop_quad(const FrobParams& p, int64_t inst, const QD& Q, 
         coop_one<L>(Q, at<L>(p.res, 0, slot));  // g_0 = 1 (src/frobenius_solver.c:84-85)
         nu_from = 1;
     }
+    coop_copy_im<L>(Q, t, rho);  // every f(rho + k) below adds an integer to the same rho
 #pragma unroll 1
     for (int64_t nu = nu_from; nu <= nu_to; nu++) {
         coop_zero<L>(Q, gnew);
         int64_t i = clampi(nu, 1, p.degree);
-        CRef ind = coop_indicial_eval<L>(Q, p, oslot, i, rho, nu - i, o1, o2, t, kb);
+        CRef ind = coop_indicial_eval<L, true>(Q, p, oslot, i, rho, nu - i, o1, o2, t, kb);
 #pragma unroll 1
         do {
             coop_mul<L>(Q, prod, ind, at<L>(p.res, nu - i, slot));
             coop_addsub<L>(Q, gnew, gnew, prod, true);
             i--;
-            ind = coop_indicial_eval<L>(Q, p, oslot, i, rho, nu - i, o1, o2, t, kb);
+            ind = coop_indicial_eval<L, true>(Q, p, oslot, i, rho, nu - i, o1, o2, t, kb);
         } while (i > 0);
         CRef spare = (ind.m == o1.m) ? o2 : o1;
         coop_div<L>(Q, at<L>(p.res, nu, slot), gnew, ind, spare);
@@ -347,9 +370,8 @@ CB_HD void fuchs_shared_coop_quad(const FuchsSharedParams& p, int64_t inst, cons
             CRef y = at<L>(p.tbl, base + cnt, 0);
             CB_COOP_EACH(Q, q) {
                 if (q & 1) continue;
-                Opd c = re_of(y);
-                if (q == 0) st_meta(out.t, arb_div<L>(wre(out), xa, c, Q.col(0), Q.col(1)));
-                else st_meta(out.t + 1, arb_div<L>(wim(out), xb, c, Q.col(2), Q.col(3)));
+                const int part = q >> 1;
+                st_meta(out.t + part, arb_div<L>(wpart(out, part), part ? xb : xa, re_of(y), Q.col(q), Q.col(q + 1)));
             }
             Q.sync();
         }

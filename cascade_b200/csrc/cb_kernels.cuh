@@ -86,16 +86,48 @@ template <int L> struct CoopCfg {
     static constexpr size_t SMEM = (size_t)KS * TPB * sizeof(uint32_t);
     static constexpr int RANGE = 8;  // coefficients per work unit of the Frobenius recurrence
 };
+// two lanes per instance: G instances per CTA, four columns each, laid out [word][role][instance]; G = 8 mod 16 keeps the
+// columns the two lanes of an instance touch at the same time (roles r and r + 2) sixteen banks apart
+template <int L> struct Coop2Cfg {
+    static constexpr int G = L >= 128 ? 104 : 120, TPB = 2 * G, STRIDE = 4 * G;
+    static constexpr int KS = L + 5;
+    static constexpr size_t SMEM = (size_t)KS * STRIDE * sizeof(uint32_t);
+    static_assert(G % 16 == 8, "bank layout");
+};
+// the instance of a thread, and its Quad, for both forms
+template <int L, int LANES>
+struct CoopGeom {
+    static constexpr int G = LANES == 4 ? CoopCfg<L>::G : Coop2Cfg<L>::G;
+    static constexpr int TPB = LANES * G, STRIDE = 4 * G, KS = CoopCfg<L>::KS;
+    static constexpr size_t SMEM = (size_t)KS * STRIDE * sizeof(uint32_t);
+    using Q = Quad<STRIDE, KS>;
+    static __device__ __forceinline__ int local_instance() { return (int)threadIdx.x / LANES; }
+    // sbase: shared-space address of the column region; gcols: global tails; blk, nblocks: this CTA's instance block
+    static __device__ __forceinline__ Q quad(uint32_t sbase, uint32_t* gcols, int64_t blk, int64_t nblocks) {
+        const int i = local_instance(), r = (int)threadIdx.x % LANES;
+        Q q;
+        q.q0 = LANES == 4 ? r : 2 * r;
+        q.per = 4 / LANES;
+        q.qmask = LANES == 4 ? (0xFu << (threadIdx.x & 28)) : (0x3u << (threadIdx.x & 30));
+        const uint32_t col0 = LANES == 4 ? 4u * (uint32_t)i : (uint32_t)i;
+        q.cstep = LANES == 4 ? 1u : (uint32_t)G;
+        q.a0 = sbase + 4u * col0;
+        q.g0 = gcols + (size_t)blk * STRIDE + col0;
+        q.gs = (uint32_t)(nblocks * STRIDE);
+        return q;
+    }
+};
 // Work units = (block of 64 instances, range of RANGE coefficients), handed out by an atomic counter in
 // coefficient-major order; unit (b, r) waits for (b, r - 1) (taken a full round earlier: all CTAs are resident and
 // units are taken in order, so the wait cannot deadlock).  Any batch size fills the SMs without a last-wave tail.
-template <int L>
-__global__ void __launch_bounds__(CoopCfg<L>::TPB, 1) frobenius1_coop_kernel(FrobParams p) {
+template <int L, int LANES>
+__global__ void __launch_bounds__(CoopGeom<L, LANES>::TPB, 1) frobenius1_coop_kernel(FrobParams p) {
     if constexpr (CoopCfg<L>::ON) {
         extern __shared__ uint32_t cb_smem[];
         __shared__ int unit_s;
-        constexpr int TPB = CoopCfg<L>::TPB, G = CoopCfg<L>::G;
-        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cb_smem) + 4u * threadIdx.x;
+        using Geo = CoopGeom<L, LANES>;
+        constexpr int G = Geo::G;
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cb_smem);
         const int64_t nblocks = (p.batch + G - 1) / G;
         const int64_t nranges = (p.n + CoopCfg<L>::RANGE) / CoopCfg<L>::RANGE;  // coefficients 0 .. n
         const int64_t total = nblocks * nranges;
@@ -113,11 +145,10 @@ __global__ void __launch_bounds__(CoopCfg<L>::TPB, 1) frobenius1_coop_kernel(Fro
             const int64_t u = unit_s;
             if (u >= total) break;
             const int64_t b = u % nblocks, r = u / nblocks;
-            const int64_t inst = b * G + (threadIdx.x >> 2);
+            const int64_t inst = b * G + Geo::local_instance();
             const int64_t lo = r * CoopCfg<L>::RANGE;
             const int64_t hi = lo + CoopCfg<L>::RANGE - 1 < p.n ? lo + CoopCfg<L>::RANGE - 1 : p.n;
-            Quad<TPB, CoopCfg<L>::KS> Q{(int)(threadIdx.x & 3), 0xFu << (threadIdx.x & 28), sbase,
-                                        p.gcols + (size_t)b * TPB + threadIdx.x, (uint32_t)(nblocks * TPB)};
+            const typename Geo::Q Q = Geo::quad(sbase, p.gcols, b, nblocks);
             if (inst < p.batch) frobenius1_coop_quad<L>(p, inst, Q, lo, hi);
             __threadfence();
             __syncthreads();
@@ -160,10 +191,16 @@ __global__ void __launch_bounds__(CoopFuchsCfg<L>::TPB, 1) fuchs_shared_coop_ker
             const int64_t inst = b * G + (threadIdx.x >> 2);
             const int64_t lo = first + r * CoopFuchsCfg<L>::RANGE;
             const int64_t hi = lo + CoopFuchsCfg<L>::RANGE - 1 < p.n ? lo + CoopFuchsCfg<L>::RANGE - 1 : p.n;
-            Quad<TPB, KS> Q{(int)(threadIdx.x & 3), 0xFu << (threadIdx.x & 28), sbase + 4u * threadIdx.x,
-                            p.gcols + (size_t)b * TPB + threadIdx.x, (uint32_t)(nblocks * TPB),
-                            sbase + 4u * (uint32_t)(KS * TPB) + 4u * threadIdx.x,
-                            state + (size_t)CoopFuchsCfg<L>::STATE * (threadIdx.x >> 2)};
+            Quad<TPB, KS> Q;
+            Q.q0 = (int)(threadIdx.x & 3);
+            Q.per = 1;
+            Q.qmask = 0xFu << (threadIdx.x & 28);
+            Q.cstep = 1u;
+            Q.a0 = sbase + 4u * (threadIdx.x & ~3u);
+            Q.g0 = p.gcols + (size_t)b * TPB + (threadIdx.x & ~3u);
+            Q.gs = (uint32_t)(nblocks * TPB);
+            Q.a20 = sbase + 4u * (uint32_t)(KS * TPB) + 4u * (threadIdx.x & ~3u);
+            Q.st = state + (size_t)CoopFuchsCfg<L>::STATE * (threadIdx.x >> 2);
             if (inst < p.batch) fuchs_shared_coop_quad<L>(p, inst, Q, lo, hi);
             __threadfence();
             __syncthreads();
@@ -176,11 +213,9 @@ template <int L>
 __global__ void __launch_bounds__(CoopCfg<L>::TPB, 1) horner_coop_kernel(HornerParams p) {
     if constexpr (CoopCfg<L>::ON) {
         extern __shared__ uint32_t cb_smem[];
-        constexpr int TPB = CoopCfg<L>::TPB, G = CoopCfg<L>::G;
-        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cb_smem) + 4u * threadIdx.x;
+        constexpr int G = CoopCfg<L>::G;
         const int64_t pt = (int64_t)blockIdx.x * G + (threadIdx.x >> 2);
-        Quad<TPB, CoopCfg<L>::KS> Q{(int)(threadIdx.x & 3), 0xFu << (threadIdx.x & 28), sbase,
-                                    p.gcols + (size_t)blockIdx.x * TPB + threadIdx.x, (uint32_t)(gridDim.x * TPB)};
+        const typename CoopGeom<L, 4>::Q Q = CoopGeom<L, 4>::quad((uint32_t)__cvta_generic_to_shared(cb_smem), p.gcols, blockIdx.x, gridDim.x);
         if (pt < p.npts) horner_coop_quad<L>(p, pt, Q);
     }
 }
@@ -630,39 +665,51 @@ template <> struct HybRatio<128> { static constexpr double HORNER = 1.27, FROB =
 // columns (lanes) the cooperative kernels need tails for: the batch padded to whole CTAs, four lanes per instance
 inline size_t coop_tail_words(int L, int64_t count) {
     if (L < 64) return 0;
-    const int64_t G = 64;
-    return (size_t)(L - 2) * (size_t)(((count > 0 ? count : 0) + G - 1) / G) * 256;
+    const int64_t c = count > 0 ? count : 0;
+    const int64_t g2 = L >= 128 ? Coop2Cfg<128>::G : Coop2Cfg<64>::G;  // the two-lane form pads to its own CTA size
+    const int64_t cols4 = ((c + 63) / 64) * 256, cols2 = ((c + g2 - 1) / g2) * 4 * g2;
+    return (size_t)(L - 2) * (size_t)(cols4 > cols2 ? cols4 : cols2);
 }
-// CB200_COOP=0/1 in the environment overrides (development).  Default, from measurements on B200 (tools/quick_coop.py,
-// profiles/coop_r02.txt): four lanes per instance win while the batch is at most ONE wave of cooperative CTAs (64
-// instances per SM) -- Horner 2.0-2.9x at 2 .. 4096 points (2048 and 4096 bits), the Frobenius recurrence 1.1-1.4x at
-// 2048 bits -- and lose beyond about two waves (idle lanes in the O(L) phases cost issue slots once the SMs are full);
-// the 4096-bit Frobenius recurrence, whose long divisions dominate, gains nothing and keeps the one-thread kernels.
+// CB200_COOP=0/1 in the environment overrides (development; 2 / 4 force that many lanes for the Frobenius recurrence).
+// Default, from measurements on B200 (tools/quick_coop.py, profiles/coop_r02.txt): four lanes per instance win while
+// the batch is at most ONE wave of cooperative CTAs (64 instances per SM) -- Horner 2.0-2.9x at 2 .. 4096 points (2048
+// and 4096 bits), the Frobenius recurrence 1.8-2.2x at 2048 bits and 1.9-2.5x at 4096 bits -- and lose beyond about two
+// waves (the lanes that only form products idle in the tails and the long divisions).  Beyond one wave the 2048-bit
+// Frobenius recurrence runs on TWO lanes per instance (every lane busy in every phase, twice the warps of the
+// one-thread kernel: 1.46x at 16 384 instances); at 4096 bits two lanes lose to the one-thread kernel (104 instances
+// per SM either way, and the larger code stalls on instruction fetch), which keeps the large batches.
 template <int L>
 bool coop_wanted(int64_t count, int sms, bool frobenius) {
     if (!CoopCfg<L>::ON) return false;
     const char* e = getenv("CB200_COOP");
     if (e && e[0] == '0') return false;
     if (e && e[0] == '1') return true;
-    if (frobenius && L >= 128) return false;
+    (void)frobenius;
     return count <= (int64_t)sms * CoopCfg<L>::G;
 }
+// lanes per instance for the Frobenius recurrence (0: the one-thread kernels)
 template <int L>
-bool use_coop_frob(const FrobParams& p) {
-    return CoopCfg<L>::ON && p.rhs_len == 0 && p.sched != nullptr && p.gcols_words >= coop_tail_words(L, p.batch) &&
-           coop_wanted<L>(p.batch, sm_count(), true);
+int coop_frob_lanes(const FrobParams& p) {
+    if (!CoopCfg<L>::ON || p.rhs_len != 0 || p.sched == nullptr || p.gcols_words < coop_tail_words(L, p.batch)) return 0;
+    const char* e = getenv("CB200_COOP");
+    if (e && e[0] == '2') return 2;
+    if (e && e[0] == '4') return 4;
+    if (e && e[0] == '0') return 0;
+    if (coop_wanted<L>(p.batch, sm_count(), true)) return 4;
+    return L == 64 ? 2 : 0;
 }
-template <int L>
+template <int L, int LANES>
 int launch_coop_frob(const FrobParams& p, cudaStream_t s) {
     if (p.batch <= 0) return 0;
-    cudaError_t e = cudaFuncSetAttribute(frobenius1_coop_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CoopCfg<L>::SMEM);
+    using Geo = CoopGeom<L, LANES>;
+    cudaError_t e = cudaFuncSetAttribute(frobenius1_coop_kernel<L, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo::SMEM);
     if (e != cudaSuccess) return (int)e;
-    const int64_t nblocks = (p.batch + CoopCfg<L>::G - 1) / CoopCfg<L>::G;
+    const int64_t nblocks = (p.batch + Geo::G - 1) / Geo::G;
     e = cudaMemsetAsync(p.sched, 0, sizeof(int) * (size_t)(nblocks + 1), s);
     if (e != cudaSuccess) return (int)e;
     const int sms = sm_count();
     const int grid = (int)(nblocks < sms ? nblocks : sms);
-    frobenius1_coop_kernel<L><<<grid, CoopCfg<L>::TPB, CoopCfg<L>::SMEM, s>>>(p);
+    frobenius1_coop_kernel<L, LANES><<<grid, Geo::TPB, Geo::SMEM, s>>>(p);
     return (int)cudaGetLastError();
 }
 // the Fuchs recurrence on four lanes per instance: a shared operator and at most one wave of cooperative CTAs (few
@@ -737,7 +784,7 @@ struct LaunchTable {
 #define CB_DEFINE_LAUNCH_TABLE(LL)                                                                         \
     namespace cb {                                                                                         \
     static int frob_##LL(const FrobParams& p, cudaStream_t s) {                                            \
-        if (use_coop_frob<LL>(p)) return launch_coop_frob<LL>(p, s);                                       \
+        if (int lanes = coop_frob_lanes<LL>(p)) return lanes == 2 ? launch_coop_frob<LL, 2>(p, s) : launch_coop_frob<LL, 4>(p, s);                                       \
         if (use_hybrid<LL>(p.batch, sm_count(), HybRatio<LL>::FROB))                                       \
             return launch<LL>(frobenius1_hyb_kernel<LL>, p, p.batch, s, HybCfg<LL>::TPB, HybCfg<LL>::SMEM); \
         return launch<LL>(frobenius1_kernel<LL>, p, p.batch, s);                                           \

@@ -109,10 +109,7 @@ CB_HD Meta fdot2_auto(WRef dst, Opd x1, Opd y1, Opd x2, Opd y2, bool neg2, SCR S
         // short (integer-like) operands make exact products, whose guard bits prove nothing:
         // knowing their trailing zero limbs lets the truncated path accept them as exact
         // (at 1024 bits arb_fdot2_trunc finds them itself from the limbs it has in registers)
-        tz_scan<L>(x1);
-        tz_scan<L>(y1);
-        tz_scan<L>(x2);
-        tz_scan<L>(y2);
+        tz_scan4<L>(x1, y1, x2, y2);
     }
     if constexpr (use_trunc<L>()) {
         bool ok;
@@ -132,11 +129,8 @@ CB_HD Meta fdot2_auto(WRef dst, Opd x1, Opd y1, Opd x2, Opd y2, bool neg2, SCR S
 
 template <int L>
 CB_HD void acb_set(const CRef& z, const CRef& x) {
-#pragma unroll 16
-    for (int k = 0; k < L; k++) {
-        z.m[k * z.stride] = x.m[k * x.stride];
-        z.m[k * z.stride + 1] = x.m[k * x.stride + 1];
-    }
+    staged_copy<2 * L>([&](int j) { return x.m[(size_t)(j >> 1) * x.stride + (j & 1)]; },
+                       [&](int j, uint32_t v) { z.m[(size_t)(j >> 1) * z.stride + (j & 1)] = v; });
     st_meta(z.t, ld_meta(x.t));
     st_meta(z.t + 1, ld_meta(x.t + 1));
 }
@@ -182,8 +176,14 @@ CB_HD void acb_mul_si(const CRef& z, const CRef& x, int64_t k, SCR S0) {
     st_meta(z.t, tr);
     st_meta(z.t + 1, ti);
 }
-// z = x + k: real part gets the integer, imaginary part is copied (acb_add_si)
-template <int L, class SCR>
+template <int L>
+CB_HD void acb_copy_im(const CRef& z, const CRef& x) {
+    staged_copy<L>([&](int j) { return x.m[(size_t)j * x.stride + 1]; }, [&](int j, uint32_t v) { z.m[(size_t)j * z.stride + 1] = v; });
+    st_meta(z.t + 1, ld_meta(x.t + 1));
+}
+// z = x + k: real part gets the integer, imaginary part is copied (acb_add_si).  COPY_IM = false: the caller has put
+// the imaginary part of x into z already (a loop adding integers to the same x over and over)
+template <int L, bool COPY_IM = true, class SCR>
 CB_HD void acb_add_si(const CRef& z, const CRef& x, int64_t k, const CRef& kball, SCR S0, SCR S1) {
     // materialise k as an exact ball in kball.re (scratch ball owned by the caller)
     uint64_t ka = k < 0 ? (uint64_t)0 - (uint64_t)k : (uint64_t)k;
@@ -197,11 +197,7 @@ CB_HD void acb_add_si(const CRef& z, const CRef& x, int64_t k, const CRef& kball
     Opd ko{RRef{kball.m, kball.stride}, kt};
     Meta tr = arb_addsub<L>(wre(z), re_of(x), ko, false, S0, S1);
     st_meta(z.t, tr);
-    if (z.m != x.m) {
-#pragma unroll 8
-        for (int j = 0; j < L; j++) z.m[j * z.stride + 1] = x.m[j * x.stride + 1];
-        st_meta(z.t + 1, ld_meta(x.t + 1));
-    }
+    if (COPY_IM && z.m != x.m) acb_copy_im<L>(z, x);
 }
 // z = 1 / y; z must not alias y; uses tmp.re as a real temporary
 template <int L, class SCR>
@@ -662,8 +658,9 @@ struct FrobParams {
 };
 constexpr int FROB_NTMP = 7;
 
-// result may be one of (o1, o2): returns which holds f_nu(rho + shift)
-template <int L, bool SYNC = false, class SCR, class PRM>
+// result may be one of (o1, o2): returns which holds f_nu(rho + shift).  IM_READY: t holds the imaginary part of rho
+// already (acb_copy_im by the caller), so rho + k only writes the real part of t
+template <int L, bool SYNC = false, bool IM_READY = false, class SCR, class PRM>
 CB_HD CRef indicial_eval(const PRM& p, size_t oslot, int64_t nu, const CRef& rho, int64_t shift,
                          CRef o1, CRef o2, const CRef& t, const CRef& kb, SCR S0, SCR S1) {
     const int D1 = p.degree + 1;
@@ -672,7 +669,7 @@ CB_HD CRef indicial_eval(const PRM& p, size_t oslot, int64_t nu, const CRef& rho
     if (nu > p.degree) return o1;
 #pragma unroll 1
     for (int64_t lam = clampi(p.degree - nu, 0, p.order); lam >= 0; lam--) {
-        acb_add_si<L>(t, rho, shift - lam, kb, S0, S1);
+        acb_add_si<L, !IM_READY>(t, rho, shift - lam, kb, S0, S1);
         CB_PHASE_SYNC();
         acb_mul<L>(o2, o1, t, S0, S1);
         CRef sw = o1;
@@ -705,16 +702,19 @@ CB_HD void frobenius1_thread(const FrobParams& p, int64_t inst, SCR S0, SCR S1) 
         CRef radj = at<L>(p.tmp, 6, slot);
         acb_add_si<L>(radj, rho, -(int64_t)p.valuation, kb, S0, S1);
         rho = radj;
-        CRef ind = indicial_eval<L>(p, oslot, 0, rho, 0, o1, o2, t, kb, S0, S1);
+        acb_copy_im<L>(t, rho);
+        CRef ind = indicial_eval<L, false, true>(p, oslot, 0, rho, 0, o1, o2, t, kb, S0, S1);
         CRef spare = (ind.m == o1.m) ? o2 : o1;
         acb_div<L>(at<L>(p.res, 0, slot), at<L>(p.rhs, 0, hslot), ind, spare, S0, S1);
     }
+    // every f(rho + k) below adds an integer to the same rho: its imaginary part goes into t once
+    if (rl == 0) acb_copy_im<L>(t, rho);
 #pragma unroll 1
     for (int64_t nu = 1; nu <= p.n; nu++) {
         if (nu < rl) acb_set<L>(gnew, at<L>(p.rhs, nu, hslot));
         else acb_zero<L>(gnew);
         int64_t i = clampi(nu, 1, p.degree);
-        CRef ind = indicial_eval<L, SYNC>(p, oslot, i, rho, nu - i, o1, o2, t, kb, S0, S1);
+        CRef ind = indicial_eval<L, SYNC, true>(p, oslot, i, rho, nu - i, o1, o2, t, kb, S0, S1);
 #pragma unroll 1
         do {
             CB_PHASE_SYNC();
@@ -722,7 +722,7 @@ CB_HD void frobenius1_thread(const FrobParams& p, int64_t inst, SCR S0, SCR S1) 
             CB_PHASE_SYNC();
             acb_addsub<L>(gnew, gnew, prod, true, S0, S1);
             i--;
-            ind = indicial_eval<L, SYNC>(p, oslot, i, rho, nu - i, o1, o2, t, kb, S0, S1);
+            ind = indicial_eval<L, SYNC, true>(p, oslot, i, rho, nu - i, o1, o2, t, kb, S0, S1);
         } while (i > 0);
         // g_nu = g_new / f_0(rho + nu); `prod` and the unused one of (o1,o2) are free temporaries
         CRef spare = (ind.m == o1.m) ? o2 : o1;

@@ -95,6 +95,17 @@ def test_horner_series_staged_by_tma(monkeypatch, oracle, gpu_driver, L, tma):
     cases.case_horner_cancellation(oracle, gpu_driver, L, seed=413 + L, length=20, npts=300)
 
 
+@pytest.mark.parametrize("L", [64, 128])
+def test_two_lanes_per_instance(monkeypatch, oracle, gpu_driver, L):
+    """The Frobenius (M = 1) recurrence with TWO lanes per instance (each lane plays two of the four roles of
+    cb_coop.cuh; CTAs of 120 / 104 instances with the [word][role][instance] column layout): ragged last CTAs, one
+    instance, several work-unit ranges."""
+    monkeypatch.setenv("CB200_COOP", "2")
+    cases.case_frobenius(oracle, gpu_driver, L, seed=31, n=19 if L == 64 else 12, batch=333)
+    cases.case_frobenius(oracle, gpu_driver, L, seed=32, n=9, batch=1)
+    cases.case_frobenius(oracle, gpu_driver, L, seed=33, n=17, batch=121)
+
+
 @pytest.mark.parametrize("coop", ["0", "1"])
 @pytest.mark.parametrize("L", [64, 128])
 def test_cooperating_lanes(monkeypatch, oracle, gpu_driver, L, coop):

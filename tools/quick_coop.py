@@ -55,7 +55,7 @@ for L in (64, 128):
         wsb = lib.cb200_frobenius_workspace_bytes(L, batch)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         res = []
-        for coop in ("0", "1"):
+        for coop in ("0", "4", "2"):
             os.environ["CB200_COOP"] = coop
             res.append(timed(lambda: lib.cb200_frobenius1_batch_dev(L, 2, 2, -2, n, batch, p(om), p(ot), 0, p(rm), p(rt), 0, p(res_m), p(res_t), p(ws), wsb, None)))
-        print(f"frobenius L={L} n={n} batch={batch}: one-thread {res[0]:.2f} ms, coop {res[1]:.2f} ms", flush=True)
+        print(f"frobenius L={L} n={n} batch={batch}: one-thread {res[0]:.2f} ms, four lanes {res[1]:.2f} ms, two lanes {res[2]:.2f} ms", flush=True)
