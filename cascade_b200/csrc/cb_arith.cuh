@@ -42,7 +42,7 @@ constexpr uint32_t F_SIGN = 1u, F_ZERO = 2u, F_NAN = 4u;
 constexpr int F_TZ_SHIFT = 8;
 CB_HD int tz_hint(uint32_t flags) { return (int)((flags >> F_TZ_SHIFT) & 0xFFu); }
 // fill in the hint of an operand that has none: dense operands cost one load.  Short ones (integers: up to L - 1
-// zero limbs) are scanned sixteen limbs at a time with independent loads -- one limb after the other every load
+// zero limbs) are scanned sixteen (from 2048 bits: sixty-four) limbs at a time with independent loads -- one limb after the other every load
 // waited for the one before it, a global-memory round trip per zero limb (the 4096-bit hypergeometric sweep with
 // rho = 0 spent most of its stall time there, profiles/ncu_frobenius1_128_r02_before_summary.txt).
 template <int L, class O>
@@ -50,7 +50,7 @@ CB_HD void tz_scan(O& o) {
     if (tz_hint(o.t.flags) != 0 || (o.t.flags & (F_ZERO | F_NAN))) return;
     if (o.r.ld(0) != 0u) return;
     int tz = L - 1;
-    constexpr int B = L < 16 ? L : 16;
+    constexpr int B = L < 16 ? L : (L >= 64 ? 64 : 16);  // (4096 bits: an integer-like operand costs two round trips)
 #pragma unroll 1
     for (int base = 0; base < L; base += B) {
         uint32_t w[B];
@@ -351,6 +351,17 @@ template <int L, int STRIDE>
 CB_HD void load_limbs(uint32_t (&a)[L], RFix<STRIDE> x) {
 #pragma unroll
     for (int j = 0; j < L; j++) a[j] = x.ld(j);
+}
+
+// B limbs starting at limb `base` (runtime): pointer walk for a runtime stride, immediates otherwise
+template <int B, class XS>
+CB_HD void load_block(uint32_t (&a)[B], const XS& x, int base) {
+#pragma unroll
+    for (int j = 0; j < B; j++) a[j] = x.ld(base + j);
+}
+template <int B>
+CB_HD void load_block(uint32_t (&a)[B], const RRef& x, int base) {
+    load_limbs<B>(a, RRef{x.m + (size_t)base * x.stride, x.stride});
 }
 
 struct WRef {
@@ -743,11 +754,26 @@ CB_HD bool fast_add_round(DST dst, X1 x1, X2 x2, int s1, int s2, bool sub, bool 
     if constexpr (DstTraits<DST>::REG_DST) {
         StoreStatic<DST, QMIN, L + 3, 0>::run(dst, q - QMIN, r, Rx);  // register destination: static indices only
     } else {
+        if constexpr (std::is_same<DST, WRef>::value) {
+            // runtime stride: walk a pointer (word i goes to limb i - q; the first q - QMIN steps are before limb 0
+            // and store nothing) instead of forming j * stride for every store
+            uint32_t* pw = dst.m - (ptrdiff_t)(q - QMIN) * (ptrdiff_t)dst.stride;
 #pragma unroll
-        for (int i = QMIN; i < QMIN + L + 3; i++) {
-            uint32_t v = shr_pair(Rx(i), Rx(i + 1), r);
-            int j = i - q;
-            if ((unsigned)j < (unsigned)L) dst.st(j, v);
+            for (int i = QMIN; i < QMIN + L + 3; i++) {
+                uint32_t v = shr_pair(Rx(i), Rx(i + 1), r);
+                if ((unsigned)(i - q) < (unsigned)L) *pw = v;
+                pw += dst.stride;
+#if defined(__CUDA_ARCH__)
+                asm volatile("" : "+l"(pw));
+#endif
+            }
+        } else {
+#pragma unroll
+            for (int i = QMIN; i < QMIN + L + 3; i++) {
+                uint32_t v = shr_pair(Rx(i), Rx(i + 1), r);
+                int j = i - q;
+                if ((unsigned)j < (unsigned)L) dst.st(j, v);
+            }
         }
     }
     int64_t e = E - 32 * (int64_t)N - 32 + bl;
@@ -1036,13 +1062,11 @@ CB_HD void product_trunc_blocked(SCR Ph, XS x, YS y) {
 #pragma unroll 1
     for (int bi = 1; bi < NB; bi++) {
         uint32_t a[32];
-#pragma unroll
-        for (int j = 0; j < 32; j++) a[j] = x.ld(32 * bi + j);
+        load_block<32>(a, x, 32 * bi);
 #pragma unroll 1
         for (int bj = NB - bi; bj < NB; bj++) {
             uint32_t b[32], r[64], o[64];
-#pragma unroll
-            for (int j = 0; j < 32; j++) b[j] = y.ld(32 * bj + j);
+            load_block<32>(b, y, 32 * bj);
             mul_full<32>(r, a, b);
             int off = 32 * (bi + bj) - K;
 #pragma unroll
@@ -1058,10 +1082,8 @@ CB_HD void product_trunc_blocked(SCR Ph, XS x, YS y) {
     for (int bi = 0; bi < NB; bi++) {
         int bj = NB - 1 - bi;
         uint32_t a[32], b[32], r[36], o[36];
-#pragma unroll
-        for (int j = 0; j < 32; j++) a[j] = x.ld(32 * bi + j);
-#pragma unroll
-        for (int j = 0; j < 32; j++) b[j] = y.ld(32 * bj + j);
+        load_block<32>(a, x, 32 * bi);
+        load_block<32>(b, y, 32 * bj);
         mul_high<32, 28>(r, a, b);
 #pragma unroll
         for (int k = 0; k < 36; k++) o[k] = Ph.ld(k);

@@ -1,0 +1,23 @@
+#!/bin/bash
+# ncu --set full with CUDA-source correlation after the staged-copy change: Frobenius 4096 bits (one thread per
+# instance, dense-rho run), Horner 2048 bits (hybrid columns), Legendre integer-operator kernel, per-instance table kernel
+set -x
+mkdir -p gpurun_out
+P="python tools/bench_configs.py --lean"
+prof() {  # name, kernel regex, skip, args...
+  local name=$1 rx=$2 skip=$3; shift 3
+  $P "$@" > gpurun_out/${name}_plain.log 2>&1 && \
+  ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c 1 -o /tmp/$name $P "$@" > gpurun_out/${name}_ncu.log 2>&1
+  if [ -f /tmp/$name.ncu-rep ]; then
+    ncu -i /tmp/$name.ncu-rep --page raw --csv > gpurun_out/${name}_raw.csv 2>&1
+    ncu -i /tmp/$name.ncu-rep --page source --csv 2>/dev/null | gzip -9 > gpurun_out/${name}_source.csv.gz
+    ncu -i /tmp/$name.ncu-rep --page source --print-source cuda,sass --csv 2>/dev/null | gzip -9 > gpurun_out/${name}_cuda.csv.gz
+  fi
+}
+export CB200_COOP=0
+prof r02s_frob128 frobenius1 1 --only 3 --terms 12
+unset CB200_COOP
+prof r02s_horner64 horner 0 --only 5 --terms 120
+prof r02s_intop32 fuchs_intop 0 --only 4 --terms 200
+prof r02s_table32 fuchs_table 0 --only 2 --terms 40
+ls -la gpurun_out | tail -14

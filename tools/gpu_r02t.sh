@@ -1,0 +1,11 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r02t_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02t_pytest.log
+tail -5 gpurun_out/r02t_pytest.log
+for cfg in 1 2 3 4; do
+  echo "config$cfg" >> gpurun_out/r02t_bench.log
+  timeout 900 python bench.py --config $cfg --steps 2 --warmup 3 --no-cpu --no-e2e >> gpurun_out/r02t_bench.log 2>&1
+done
+timeout 600 python tools/bench_configs.py --lean --only 2 >> gpurun_out/r02t_pi.log 2>&1
+timeout 900 python tools/quick_coop.py >> gpurun_out/r02t_quick.log 2>&1
