@@ -28,7 +28,8 @@
 #endif
 
 #if defined(CB_COUNT_PATHS) && !defined(__CUDA_ARCH__)
-extern "C" long long cb_path_counts[8];  // host-sim statistics: [0] fdot fast, [1] fdot general, [2] add fast, [3] add general
+extern "C" long long cb_path_counts[8];  // host-sim statistics: [0] fdot fast, [1] fdot general, [2] add fast, [3] add general,
+                                         // [4] blocked fdot accepted, [5] refused, [6] two-row (integer-like operand) products
 #define CB_COUNT(i) (cb_path_counts[i]++)
 #else
 #define CB_COUNT(i) ((void)0)
@@ -77,6 +78,14 @@ CB_HD void tz_scan4(O1& x1, O2& y1, O1& x2, O2& y2) {
     if (b == 0u) tz_scan<L>(y1);
     if (c == 0u) tz_scan<L>(x2);
     if (d == 0u) tz_scan<L>(y2);
+}
+template <int L, class O1, class O2>
+CB_HD void tz_scan2(O1& x, O2& y) {
+    auto open = [](uint32_t f) { return tz_hint(f) == 0 && !(f & (F_ZERO | F_NAN)); };
+    const bool ox = open(x.t.flags), oy = open(y.t.flags);
+    const uint32_t a = ox ? x.r.ld(0) : 1u, b = oy ? y.r.ld(0) : 1u;
+    if (a == 0u) tz_scan<L>(x);
+    if (b == 0u) tz_scan<L>(y);
 }
 constexpr int32_t EXP_LIMIT = 1 << 28;
 
@@ -1122,6 +1131,57 @@ CB_HD void product_trunc_blocked(SCR Ph, XS x, YS y) {
     }
 }
 
+// The same product column for an INTEGER-LIKE y (every limb below L - 2 zero: rho + k with an integer rho, a small
+// rational coefficient, g_0 = 1 ...): two rows instead of L.  All of its limb products lie in columns >= L - 2 > K, so
+// nothing is dropped and the words are those of the exact product -- the same words product_trunc_blocked would give
+// (its dropped columns hold zeros only), at 2 L limb multiplies instead of about L^2 / 2.
+template <int L, class SCR, class XS, class YS>
+CB_HD void product_short_y(SCR Ph, XS x, YS y) {
+    CB_COUNT(6);
+    const uint32_t y0 = y.ld(L - 2), y1 = y.ld(L - 1);
+    Ph.st(0, 0u);
+    Ph.st(1, 0u);
+    // product word (L - 2) + j = Ph[j + 2] = lo(x_j y0) + hi(x_{j-1} y0) + lo(x_{j-1} y1) + hi(x_{j-2} y1) + carry
+    uint32_t carry = 0u, hi0p = 0u, lo1p = 0u, hi1p = 0u, hi1pp = 0u;
+    constexpr int B = 32;
+#pragma unroll 1
+    for (int base = 0; base < L + 2; base += B) {
+        uint32_t xv[B];
+        if (base < L) load_block<B>(xv, x, base);  // (L is a multiple of 32 here)
+#pragma unroll
+        for (int k = 0; k < B; k++) {
+            const int j = base + k;
+            if (j < L + 2) {
+                const uint32_t xj = (base < L) ? xv[k] : 0u;
+                const uint64_t p0 = (uint64_t)xj * y0, p1 = (uint64_t)xj * y1;
+                const uint64_t t = (uint64_t)carry + (uint32_t)p0 + hi0p + lo1p + hi1pp;
+                Ph.st(j + 2, (uint32_t)t);
+                carry = (uint32_t)(t >> 32);
+                hi0p = (uint32_t)(p0 >> 32);
+                hi1pp = hi1p;
+                hi1p = (uint32_t)(p1 >> 32);
+                lo1p = (uint32_t)p1;
+            }
+        }
+    }
+}
+// one truncated product of a fused dot product: the short form when one operand is known (trailing-zero hint) to be
+// integer-like -- for every lane of the warp when UNIFORM (thread-per-instance kernels: a divergent choice would run
+// both forms), for this lane alone otherwise (cooperative kernels, whose lanes diverge anyway).  An operand flagged
+// zero counts as short: its term is masked by the caller.
+template <int L, bool UNIFORM, class SCR, class XS, class YS>
+CB_HD void product_trunc_auto(SCR Ph, const OpdT<XS>& x, const OpdT<YS>& y) {
+    auto is_short = [](uint32_t f) { return tz_hint(f) >= L - 2 || (f & (F_ZERO | F_NAN)) != 0u; };
+    bool sy = is_short(y.t.flags), sx = is_short(x.t.flags);
+    if constexpr (UNIFORM) {
+        sy = warp_all(sy);
+        sx = warp_all(sx);
+    }
+    if (sy) product_short_y<L>(Ph, x.r, y.r);
+    else if (sx) product_short_y<L>(Ph, y.r, x.r);
+    else product_trunc_blocked<L>(Ph, x.r, y.r);
+}
+
 // dst = x1*y1 +- x2*y2 above 1024 bits from truncated blocked products;
 // *ok = false when the guard bits cannot prove the result (the caller then runs the exact path).
 // S0, S1: shared columns of at least L + 4 words.
@@ -1199,7 +1259,7 @@ CB_NOINLINE Meta arb_fdot2_trunc_blocked(DST dst, OpdT<XS> x1, OpdT<YS> y1, OpdT
 #pragma unroll 1
     for (int term = 0; term < 2; term++) {
         if (term ? skip2 : skip1) continue;
-        product_trunc_blocked<L>(term ? S1 : S0, term ? x2.r : x1.r, term ? y2.r : y1.r);
+        product_trunc_auto<L, true>(term ? S1 : S0, term ? x2 : x1, term ? y2 : y1);
     }
     return fdot2_tb_tail<L>(dst, f, S0, S1, ok);
 }

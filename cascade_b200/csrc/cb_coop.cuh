@@ -113,9 +113,9 @@ CB_HD void coop_fdot2_pair(const QD& Q, const FdotJob<L>& j0, const FdotJob<L>& 
         while (!((todo >> q) & 1u)) q++;
         todo &= todo - 1u;
         const FdotJob<L>& j = (q >> 1) ? j1 : j0;
-        const Opd& xo = (q & 1) ? j.x2 : j.x1;
-        const Opd& yo = (q & 1) ? j.y2 : j.y1;
-        product_trunc_blocked<L>(lo_view(Q.col(q)), xo.r, yo.r);
+        Opd xo = (q & 1) ? j.x2 : j.x1, yo = (q & 1) ? j.y2 : j.y1;
+        tz_scan2<L>(xo, yo);  // an integer-like operand takes the two-row product
+        product_trunc_auto<L, false>(lo_view(Q.col(q)), xo, yo);
     }
     Q.sync();
     CB_COOP_EACH(Q, q) {  // align, add, round

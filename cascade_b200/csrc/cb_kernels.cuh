@@ -49,6 +49,9 @@ template <int L> struct Sizes {
 
 // 2048 / 4096 bits: hybrid columns (L + 5 words in shared memory, the tail of the rare exact paths in global
 // memory), so that the block is bounded by the 255 registers per thread, not by shared memory
+#ifndef CB_HYB64_TPB
+#define CB_HYB64_TPB 256
+#endif
 template <int L> struct HybCfg {
     static constexpr bool ON = L >= 64;
     static constexpr int KS = L + 5;                  // shared words per column
@@ -56,9 +59,14 @@ template <int L> struct HybCfg {
     static constexpr int TPB = L == 64 ? 256 : (L == 128 ? 192 : Cfg<L>::TPB);
     static constexpr size_t SMEM = (size_t)2 * KS * TPB * sizeof(uint32_t);
 };
-#define CB_KERNEL_PROLOGUE_HYB(COUNT, GCOLS)                                                   \
+// the Horner kernels on hybrid columns have their own block size (2048 bits: more warps at fewer registers)
+template <int L> struct HornerHyb {
+    static constexpr int TPB = L == 64 ? CB_HYB64_TPB : HybCfg<L>::TPB;
+    static constexpr size_t SMEM = (size_t)2 * HybCfg<L>::KS * TPB * sizeof(uint32_t);
+};
+#define CB_KERNEL_PROLOGUE_HYB(COUNT, GCOLS, TPBV)                                             \
     extern __shared__ uint32_t cb_smem[];                                                      \
-    constexpr int TPB = HybCfg<L>::TPB;                                                        \
+    constexpr int TPB = TPBV;                                                                  \
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cb_smem) + 4u * threadIdx.x;     \
     const int64_t idx = (int64_t)blockIdx.x * TPB + threadIdx.x;                               \
     if (idx >= (COUNT)) return;                                                                \
@@ -74,7 +82,7 @@ __global__ void __launch_bounds__(Cfg<L>::TPB, 1) frobenius1_kernel(FrobParams p
 template <int L>
 __global__ void __launch_bounds__(HybCfg<L>::TPB, 1) frobenius1_hyb_kernel(FrobParams p) {
     if constexpr (HybCfg<L>::ON) {
-        CB_KERNEL_PROLOGUE_HYB(p.batch, p.gcols)
+        CB_KERNEL_PROLOGUE_HYB(p.batch, p.gcols, HybCfg<L>::TPB)
         frobenius1_thread<L, true>(p, idx, S0, S1);
     }
 }
@@ -270,9 +278,9 @@ __global__ void __launch_bounds__(Cfg<L>::TPB, 1) horner_kernel(HornerParams p) 
     horner_thread<L, HORNER_SYNC>(p, idx, S0, S1);
 }
 template <int L>
-__global__ void __launch_bounds__(HybCfg<L>::TPB, 1) horner_hyb_kernel(HornerParams p) {
+__global__ void __launch_bounds__(HornerHyb<L>::TPB, 1) horner_hyb_kernel(HornerParams p) {
     if constexpr (HybCfg<L>::ON) {
-        CB_KERNEL_PROLOGUE_HYB(p.npts, p.gcols)
+        CB_KERNEL_PROLOGUE_HYB(p.npts, p.gcols, HornerHyb<L>::TPB)
         horner_thread<L, HORNER_SYNC>(p, idx, S0, S1);
     }
 }
@@ -306,7 +314,7 @@ __global__ void __launch_bounds__(Cfg<L>::TPB, 1) taylor_shift_kernel(TShiftPara
 // is in flight while the current one is consumed.  Same arithmetic as horner_thread: the coefficient is merely read
 // from shared memory.
 template <int L> struct HornerTile {
-    static constexpr int T = L <= 64 ? 16 : 8;
+    static constexpr int T = (L <= 64 && HornerHyb<L>::TPB <= 256) ? 16 : 8;
     static constexpr uint32_t MANT = (uint32_t)T * L * 2 * 4, META = (uint32_t)T * 2 * 16;
     static constexpr size_t BYTES = (size_t)2 * (MANT + META);
 };
@@ -339,15 +347,15 @@ __device__ __forceinline__ void tma_wait(uint64_t* bar, uint32_t parity) {
 }
 #endif
 template <int L>
-__global__ void __launch_bounds__(HybCfg<L>::TPB, 1) horner_tma_kernel(HornerParams p) {
+__global__ void __launch_bounds__(HornerHyb<L>::TPB, 1) horner_tma_kernel(HornerParams p) {
     if constexpr (HybCfg<L>::ON) {
 #if defined(__CUDA_ARCH__)
         extern __shared__ __align__(128) uint32_t cb_smem_tma[];
         __shared__ __align__(8) uint64_t mbar[2];
-        constexpr int TPB = HybCfg<L>::TPB, T = HornerTile<L>::T;
+        constexpr int TPB = HornerHyb<L>::TPB, T = HornerTile<L>::T;
         constexpr bool SYNC = HORNER_SYNC;
         const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cb_smem_tma) + 4u * threadIdx.x;
-        char* tiles = reinterpret_cast<char*>(cb_smem_tma) + HybCfg<L>::SMEM;
+        char* tiles = reinterpret_cast<char*>(cb_smem_tma) + HornerHyb<L>::SMEM;
         auto tile_m = [&](int b) { return reinterpret_cast<uint32_t*>(tiles + (size_t)b * (HornerTile<L>::MANT + HornerTile<L>::META)); };
         auto tile_t = [&](int b) {
             return reinterpret_cast<Meta*>(tiles + (size_t)b * (HornerTile<L>::MANT + HornerTile<L>::META) + HornerTile<L>::MANT);
@@ -793,9 +801,9 @@ struct LaunchTable {
         if (use_coop_horner<LL>(p)) return launch_coop_horner<LL>(p, s);                                   \
         if (use_hybrid<LL>(p.npts, sm_count(), HybRatio<LL>::HORNER)) {                                    \
             if (use_horner_tma<LL>(p))                                                                     \
-                return launch<LL>(horner_tma_kernel<LL>, p, p.npts, s, HybCfg<LL>::TPB,                     \
-                                  HybCfg<LL>::SMEM + HornerTile<LL>::BYTES);                               \
-            return launch<LL>(horner_hyb_kernel<LL>, p, p.npts, s, HybCfg<LL>::TPB, HybCfg<LL>::SMEM);     \
+                return launch<LL>(horner_tma_kernel<LL>, p, p.npts, s, HornerHyb<LL>::TPB,                  \
+                                  HornerHyb<LL>::SMEM + HornerTile<LL>::BYTES);                            \
+            return launch<LL>(horner_hyb_kernel<LL>, p, p.npts, s, HornerHyb<LL>::TPB, HornerHyb<LL>::SMEM); \
         }                                                                                                  \
         return launch<LL>(horner_kernel<LL>, p, p.npts, s);                                                \
     }                                                                                                      \

@@ -31,6 +31,8 @@ def lib():
     if _lib is None:
         build()
         L = C.CDLL(_SO)
+        L.cbsim_path_count.argtypes = [C.c_int]
+        L.cbsim_path_count.restype = C.c_longlong
         L.cbsim_fuchs_batch.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [_u32p, _i32p, C.c_int, _u32p, _i32p]
         L.cbsim_fuchs_batch_range.argtypes = [C.c_int] * 4 + [C.c_int64] * 3 + [_u32p, _i32p, C.c_int, _u32p, _i32p]
         L.cbsim_fuchs_intop_batch.argtypes = [C.c_int] * 4 + [C.c_int64] * 2 + [np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS"), C.c_int, _u32p, _i32p]
@@ -137,3 +139,8 @@ class SimDriver:
     def ew(self, op, L, n, z_m, z_t, x_m, x_t, y_m, y_t, k):
         vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
         return lib().cbsim_ew(op, L, n, z_m, z_t, x_m, x_t, vp(y_m), vp(y_t), vp(k))
+
+
+def path_count(i: int) -> int:
+    """statistics of the simulated arithmetic (cb_arith.cuh CB_COUNT): e.g. 6 = two-row products of integer-like operands"""
+    return int(lib().cbsim_path_count(i))

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <vector>
 
+#define CB_COUNT_PATHS 1  // path statistics (cbsim_path_count): which arithmetic paths a test went through
 #include "../../include/cascade_b200.h"
 #include "../../cascade_b200/csrc/cb_solvers.cuh"
 
@@ -55,6 +56,9 @@ template <int L>
 static int sim_fuchs_shared_coop(FuchsSharedParams& sp);
 
 extern "C" {
+long long cb_path_counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+long long cbsim_path_count(int i) { return (i >= 0 && i < 8) ? cb_path_counts[i] : -1; }
+
 
 int cbsim_fuchs_batch_range(int L_, int order, int degree, int valuation, int64_t n_begin, int64_t n, int64_t batch,
                             const uint32_t* ode_mant, const cb_meta* ode_meta, int shared_ode,

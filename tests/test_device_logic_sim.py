@@ -48,6 +48,22 @@ def test_frobenius(oracle, sim_driver, L):
     cases.case_frobenius(oracle, sim_driver, L, seed=9, n=12 if L == 128 else 20, batch=2)
 
 
+@pytest.mark.parametrize("L", [64, 128])
+def test_integer_like_operands_take_the_two_row_product(oracle, sim_driver, L):
+    """2048 / 4096 bits: a factor whose limbs below the top two are zero (rho + k with rho = 0, g_0 = 1, an integer
+    exponent) goes through product_short_y; the series must still agree with the oracle bit for bit, also on the
+    cooperating lanes."""
+    from tests.host_sim import driver as simdrv
+    before = simdrv.path_count(6)
+    cases.case_frobenius(oracle, sim_driver, L, seed=19, n=8, batch=2)
+    cases.case_frobenius_singleton(oracle, sim_driver, L, seed=23, trials=1)
+    assert simdrv.path_count(6) > before, "the two-row product was never taken"
+    coop = simdrv.SimDriver(coop=True)
+    mid = simdrv.path_count(6)
+    cases.case_frobenius(oracle, coop, L, seed=29, n=6, batch=2)
+    assert simdrv.path_count(6) > mid
+
+
 def test_frobenius_singleton(oracle, sim_driver):
     cases.case_frobenius_singleton(oracle, sim_driver, 4, seed=21)
 
