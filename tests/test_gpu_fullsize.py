@@ -138,6 +138,47 @@ def _pick(dm, dt, sample, L, entries):
     return entry_major_to_instance_major(unpack_entries(L, m, t), len(sample), entries)
 
 
+def test_frobenius_2048_bits_two_lane_form_chosen_by_the_launcher(oracle):
+    """2048 bits, 12 000 hypergeometric instances (more than one wave of four-lane cooperative CTAs): the launcher
+    picks the TWO-lane cooperative Frobenius kernel (CTAs of 120 instances, ragged last CTA, work units of 8
+    coefficients); sampled instances at CTA / warp edges against the oracle, both exponents."""
+    import torch
+
+    import bench
+    from cascade_b200 import _lib, api
+    from cascade_b200.format import FLAG_NAN, Balls, from_complex, instance_major_to_entry_major, pack_entries
+
+    lib = _lib.lib()
+    L, batch, n = 64, 12000, 20
+    dev = torch.device("cuda:0")
+    drv = api.HostBufferDriver(0)
+    a, b, c = bench.hypgeom_params(batch, L, seed=0x5EED0064)
+    ode = api.acb_ode_hypgeom_batch(a, b, c, driver=drv)
+    rho1 = api.ew(api.OP_SUB, from_complex([1] * batch, L), c, driver=drv)
+    rho0 = Balls.zeros(2 * batch, L)
+    om, ot = pack_entries(instance_major_to_entry_major(ode, batch, 9), 9, 2 * batch)
+    d_om, d_ot = torch.from_numpy(om.view(np.int32)).to(dev), torch.from_numpy(ot).to(dev)
+    d_res_m = torch.empty((n + 1, L, 2 * batch), dtype=torch.int32, device=dev)
+    d_res_t = torch.empty((n + 1, 2 * batch, 4), dtype=torch.int32, device=dev)
+    wsb = lib.cb200_frobenius_workspace_bytes(L, batch)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    sample = _sample(batch, [1, 15, 16, 119, 120, 121, 239, 240, 5999, 6000, 11879, 11880, 11998], 64)
+    sub_ode = Balls.concat([ode[18 * i:18 * i + 18] for i in sample])
+    for name, rho in (("rho = 0", rho0), ("rho = 1 - c", rho1)):
+        rm, rt = pack_entries(rho, 1, 2 * batch)
+        d_rm, d_rt = torch.from_numpy(rm.view(np.int32)).to(dev), torch.from_numpy(rt).to(dev)
+        rc = lib.cb200_frobenius1_batch_dev(L, 2, 2, -1, n, batch, p(d_om), p(d_ot), 0, p(d_rm), p(d_rt), 0, p(d_res_m), p(d_res_t),
+                                            p(ws), wsb, None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert int((d_res_t[:, :, 1] & FLAG_NAN).sum().item()) == 0, name
+        got = _pick(d_res_m, d_res_t, sample, L, n + 1)
+        sub_rho = Balls.concat([rho[2 * i:2 * i + 2] for i in sample])
+        want = oracle.frobenius1_batch(2, 2, n, sub_ode, sub_rho, len(sample), False, nthreads=8)
+        assert got.same_as(want), f"2048-bit Frobenius sweep, {name}: GPU run differs from the oracle on the sampled instances"
+
+
 def test_config2_frobenius_sweep_full_size(oracle):
     """BASELINE configs[2]: Gauss hypergeometric acb_ode_solve_frobenius (M = 1) at 4096 bits, 16 384 (a,b,c) triples,
     256 terms, both exponents (rho = 0 and rho = 1 - c) -- reference src/frobenius_solver.c:72-121."""

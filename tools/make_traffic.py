@@ -1,4 +1,4 @@
-"""profiles/traffic_r02.json from the raw ncu exports of tools/gpu_r02g.sh: DRAM bytes read + written per launch of the
+"""profiles/traffic_r02.json from the raw ncu exports of tools/gpu_r02g.sh / gpu_r02x.sh (argument: the file prefix): DRAM bytes read + written per launch of the
 dominant kernel of every bench.py config, next to the sizes they were captured at (bench.py's roofline.traffic reads it
 and reports null when its own sizes differ)."""
 import csv
@@ -15,9 +15,10 @@ def to_bytes(val, unit):
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[unit]
 
 
+PREFIX = sys.argv[1] if len(sys.argv) > 1 else "r02g"
 out = {}
 for cfg in (1, 2, 3, 4):
-    path = f"gpurun_out/r02g_ncu_cfg{cfg}_raw.csv"
+    path = f"gpurun_out/{PREFIX}_ncu_cfg{cfg}_raw.csv"
     try:
         rows = list(csv.reader(open(path)))
     except OSError:
