@@ -47,7 +47,7 @@ CB_HD int tz_hint(uint32_t flags) { return (int)((flags >> F_TZ_SHIFT) & 0xFFu);
 // waited for the one before it, a global-memory round trip per zero limb (the 4096-bit hypergeometric sweep with
 // rho = 0 spent most of its stall time there, profiles/ncu_frobenius1_128_r02_before_summary.txt).
 template <int L, class O>
-CB_HD void tz_scan(O& o) {
+CB_NOINLINE void tz_scan(O& o) {  // (out of line: it is reached from every fused dot product and rarely runs)
     if (tz_hint(o.t.flags) != 0 || (o.t.flags & (F_ZERO | F_NAN))) return;
     if (o.r.ld(0) != 0u) return;
     int tz = L - 1;

@@ -789,29 +789,32 @@ struct LaunchTable {
     int (*truncation)(const TruncParams&, cudaStream_t);
 };
 
-#define CB_DEFINE_LAUNCH_TABLE(LL)                                                                         \
+// The launch functions of one precision are spread over four translation units (kern_L<LL>.cu: Frobenius M = 1,
+// Horner, elementwise + the table itself; kern_L<LL>f.cu: the Fuchs recurrences; kern_L<LL>t.cu: evaluation, exp / log, radius / truncation; kern_L<LL>x.cu: the
+// rest), so
+// that the build parallelises: each kernel is compiled on its own and the 2048 / 4096-bit units took minutes each.
+#define CB_DECLARE_LAUNCHERS(LL)                                                                           \
+    int ftab_##LL(const FuchsTableParams&, cudaStream_t);                                                  \
+    int fsh_##LL(const FuchsSharedParams&, cudaStream_t);                                                  \
+    int fint_##LL(const FuchsIntParams&, cudaStream_t);                                                    \
+    int frobg_##LL(const FrobGenParams&, cudaStream_t);                                                    \
+    int solop_##LL(const SolOpParams&, cudaStream_t);                                                      \
+    int indp_##LL(const IndicialParams&, cudaStream_t);                                                    \
+    int eval_##LL(const EvalParams&, cudaStream_t);                                                        \
+    int trans_##LL(const TransParams&, cudaStream_t);                                                      \
+    int apply_##LL(const ApplyParams&, cudaStream_t);                                                      \
+    int radius_##LL(const RadiusParams&, cudaStream_t);                                                    \
+    int trunc_##LL(const TruncParams&, cudaStream_t);                                                      \
+    int oshift_##LL(const ShiftParams&, cudaStream_t);                                                     \
+    int tshift_##LL(const TShiftParams&, cudaStream_t);
+
+#define CB_DEFINE_LAUNCH_FUCHS(LL)                                                                         \
     namespace cb {                                                                                         \
-    static int frob_##LL(const FrobParams& p, cudaStream_t s) {                                            \
-        if (int lanes = coop_frob_lanes<LL>(p)) return lanes == 2 ? launch_coop_frob<LL, 2>(p, s) : launch_coop_frob<LL, 4>(p, s);                                       \
-        if (use_hybrid<LL>(p.batch, sm_count(), HybRatio<LL>::FROB))                                       \
-            return launch<LL>(frobenius1_hyb_kernel<LL>, p, p.batch, s, HybCfg<LL>::TPB, HybCfg<LL>::SMEM); \
-        return launch<LL>(frobenius1_kernel<LL>, p, p.batch, s);                                           \
-    }                                                                                                      \
-    static int horner_##LL(const HornerParams& p, cudaStream_t s) {                                        \
-        if (use_coop_horner<LL>(p)) return launch_coop_horner<LL>(p, s);                                   \
-        if (use_hybrid<LL>(p.npts, sm_count(), HybRatio<LL>::HORNER)) {                                    \
-            if (use_horner_tma<LL>(p))                                                                     \
-                return launch<LL>(horner_tma_kernel<LL>, p, p.npts, s, HornerHyb<LL>::TPB,                  \
-                                  HornerHyb<LL>::SMEM + HornerTile<LL>::BYTES);                            \
-            return launch<LL>(horner_hyb_kernel<LL>, p, p.npts, s, HornerHyb<LL>::TPB, HornerHyb<LL>::SMEM); \
-        }                                                                                                  \
-        return launch<LL>(horner_kernel<LL>, p, p.npts, s);                                                \
-    }                                                                                                      \
-    static int ew_##LL(const EwParams& p, cudaStream_t s) { return launch<LL>(ew_kernel<LL>, p, p.n, s); }                \
-    static int ftab_##LL(const FuchsTableParams& p, cudaStream_t s) {                                      \
+    CB_DECLARE_LAUNCHERS(LL)                                                                               \
+    int ftab_##LL(const FuchsTableParams& p, cudaStream_t s) {                                      \
         return launch<LL>(fuchs_table_kernel<LL>, p, p.nrows * p.ninst, s);                            \
     }                                                                                                      \
-    static int fsh_##LL(const FuchsSharedParams& p, cudaStream_t s) {                                      \
+    int fsh_##LL(const FuchsSharedParams& p, cudaStream_t s) {                                      \
         int dev = 0, sms = 148;                                                                            \
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); \
         if (use_coop_fuchs<LL>(p, sms)) return launch_coop_fuchs<LL>(p, sms, s);                           \
@@ -834,7 +837,7 @@ struct LaunchTable {
         return launch<LL>(fuchs_shared_kernel<LL, CfgShared<LL>::TPB>, p, p.batch, s, CfgShared<LL>::TPB,  \
                           Sizes<LL>::SMEM_SHARED_PER_THREAD * CfgShared<LL>::TPB);                         \
     }                                                                                                      \
-    static int fint_##LL(const FuchsIntParams& p, cudaStream_t s) {                                        \
+    int fint_##LL(const FuchsIntParams& p, cudaStream_t s) {                                        \
         const size_t smem = IntopCfg<LL>::SMEM;                                                            \
         if (p.sched) { /* persistent launch: no last-wave tail */                                          \
             int dev = 0, sms = 148;                                                                        \
@@ -849,16 +852,17 @@ struct LaunchTable {
         }                                                                                                  \
         return launch<LL>(fuchs_intop_kernel<LL>, p, p.batch, s, IntopCfg<LL>::TPB, smem);                 \
     }                                                                                                      \
-    static int frobg_##LL(const FrobGenParams& p, cudaStream_t s) { return launch<LL>(frobenius_general_kernel<LL>, p, p.batch, s); } \
-    static int solop_##LL(const SolOpParams& p, cudaStream_t s) { return launch<LL>(solution_op_kernel<LL>, p, p.batch, s); } \
-    static int indp_##LL(const IndicialParams& p, cudaStream_t s) { return launch<LL>(indicial_poly_kernel<LL>, p, p.batch, s); } \
-    static int eval_##LL(const EvalParams& p, cudaStream_t s) { return launch<LL>(evaluate_kernel<LL>, p, p.npts, s); } \
-    static int trans_##LL(const TransParams& p, cudaStream_t s) { return launch<LL>(trans_kernel<LL>, p, p.n, s); } \
-    static int apply_##LL(const ApplyParams& p, cudaStream_t s) { return launch<LL>(apply_kernel<LL>, p, p.batch, s); } \
-    static int radius_##LL(const RadiusParams& p, cudaStream_t s) { return launch<LL>(radius_kernel<LL>, p, p.batch, s); } \
-    static int trunc_##LL(const TruncParams& p, cudaStream_t s) { return launch<LL>(truncation_kernel<LL>, p, p.batch, s); } \
-    static int oshift_##LL(const ShiftParams& p, cudaStream_t s) { return launch<LL>(ode_shift_kernel<LL>, p, p.batch, s); } \
-    static int tshift_##LL(const TShiftParams& p, cudaStream_t s) {                                        \
+    }
+
+#define CB_DEFINE_LAUNCH_OTHER(LL)                                                                         \
+    namespace cb {                                                                                         \
+    CB_DECLARE_LAUNCHERS(LL)                                                                               \
+    int frobg_##LL(const FrobGenParams& p, cudaStream_t s) { return launch<LL>(frobenius_general_kernel<LL>, p, p.batch, s); } \
+    int solop_##LL(const SolOpParams& p, cudaStream_t s) { return launch<LL>(solution_op_kernel<LL>, p, p.batch, s); } \
+    int indp_##LL(const IndicialParams& p, cudaStream_t s) { return launch<LL>(indicial_poly_kernel<LL>, p, p.batch, s); } \
+    int apply_##LL(const ApplyParams& p, cudaStream_t s) { return launch<LL>(apply_kernel<LL>, p, p.batch, s); } \
+    int oshift_##LL(const ShiftParams& p, cudaStream_t s) { return launch<LL>(ode_shift_kernel<LL>, p, p.batch, s); } \
+    int tshift_##LL(const TShiftParams& p, cudaStream_t s) {                                        \
         if (p.batch <= 0 || p.len <= 1) return 0;                                                          \
         cudaError_t e = cudaFuncSetAttribute(taylor_shift_kernel<LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                              (int)Sizes<LL>::SMEM);                                        \
@@ -866,6 +870,37 @@ struct LaunchTable {
         taylor_shift_kernel<LL><<<(unsigned)p.batch, Cfg<LL>::TPB, Sizes<LL>::SMEM, s>>>(p);               \
         return (int)cudaGetLastError();                                                                    \
     }                                                                                                      \
+    }
+
+#define CB_DEFINE_LAUNCH_TRANS(LL)                                                                         \
+    namespace cb {                                                                                         \
+    CB_DECLARE_LAUNCHERS(LL)                                                                               \
+    int eval_##LL(const EvalParams& p, cudaStream_t s) { return launch<LL>(evaluate_kernel<LL>, p, p.npts, s); } \
+    int trans_##LL(const TransParams& p, cudaStream_t s) { return launch<LL>(trans_kernel<LL>, p, p.n, s); } \
+    int radius_##LL(const RadiusParams& p, cudaStream_t s) { return launch<LL>(radius_kernel<LL>, p, p.batch, s); } \
+    int trunc_##LL(const TruncParams& p, cudaStream_t s) { return launch<LL>(truncation_kernel<LL>, p, p.batch, s); } \
+    }
+
+#define CB_DEFINE_LAUNCH_TABLE(LL)                                                                         \
+    namespace cb {                                                                                         \
+    CB_DECLARE_LAUNCHERS(LL)                                                                               \
+    static int frob_##LL(const FrobParams& p, cudaStream_t s) {                                            \
+        if (int lanes = coop_frob_lanes<LL>(p)) return lanes == 2 ? launch_coop_frob<LL, 2>(p, s) : launch_coop_frob<LL, 4>(p, s);                                       \
+        if (use_hybrid<LL>(p.batch, sm_count(), HybRatio<LL>::FROB))                                       \
+            return launch<LL>(frobenius1_hyb_kernel<LL>, p, p.batch, s, HybCfg<LL>::TPB, HybCfg<LL>::SMEM); \
+        return launch<LL>(frobenius1_kernel<LL>, p, p.batch, s);                                           \
+    }                                                                                                      \
+    static int horner_##LL(const HornerParams& p, cudaStream_t s) {                                        \
+        if (use_coop_horner<LL>(p)) return launch_coop_horner<LL>(p, s);                                   \
+        if (use_hybrid<LL>(p.npts, sm_count(), HybRatio<LL>::HORNER)) {                                    \
+            if (use_horner_tma<LL>(p))                                                                     \
+                return launch<LL>(horner_tma_kernel<LL>, p, p.npts, s, HornerHyb<LL>::TPB,                  \
+                                  HornerHyb<LL>::SMEM + HornerTile<LL>::BYTES);                            \
+            return launch<LL>(horner_hyb_kernel<LL>, p, p.npts, s, HornerHyb<LL>::TPB, HornerHyb<LL>::SMEM); \
+        }                                                                                                  \
+        return launch<LL>(horner_kernel<LL>, p, p.npts, s);                                                \
+    }                                                                                                      \
+    static int ew_##LL(const EwParams& p, cudaStream_t s) { return launch<LL>(ew_kernel<LL>, p, p.n, s); }                \
     extern const LaunchTable launch_table_L##LL = {frob_##LL, horner_##LL, ew_##LL, ftab_##LL, fsh_##LL, fint_##LL, \
                                                    frobg_##LL, solop_##LL, indp_##LL, eval_##LL, trans_##LL, apply_##LL, \
                                                    oshift_##LL, tshift_##LL, radius_##LL, trunc_##LL}; \

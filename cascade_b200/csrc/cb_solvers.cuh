@@ -176,6 +176,23 @@ CB_HD void acb_mul_si(const CRef& z, const CRef& x, int64_t k, SCR S0) {
     st_meta(z.t, tr);
     st_meta(z.t + 1, ti);
 }
+// ask the L2 for a ball that will be read a few thousand instructions from now (operands that come around once per
+// coefficient -- the per-instance operator, the earlier coefficients -- have left the L2 by then when the batch's
+// working set exceeds it): one request per limb covers the real and the imaginary word
+template <int L>
+CB_HD void acb_prefetch(const CRef& x) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t* q = x.m;
+#pragma unroll 16
+    for (int j = 0; j < L; j++) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+        q += x.stride;
+    }
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(x.t));
+#else
+    (void)x;
+#endif
+}
 template <int L>
 CB_HD void acb_copy_im(const CRef& z, const CRef& x) {
     staged_copy<L>([&](int j) { return x.m[(size_t)j * x.stride + 1]; }, [&](int j, uint32_t v) { z.m[(size_t)j * z.stride + 1] = v; });
@@ -669,6 +686,7 @@ CB_HD CRef indicial_eval(const PRM& p, size_t oslot, int64_t nu, const CRef& rho
     if (nu > p.degree) return o1;
 #pragma unroll 1
     for (int64_t lam = clampi(p.degree - nu, 0, p.order); lam >= 0; lam--) {
+        if (L >= 64 && lam + nu >= 0) acb_prefetch<L>(at<L>(p.ode, lam * D1 + (lam + nu), oslot));
         acb_add_si<L, !IM_READY>(t, rho, shift - lam, kb, S0, S1);
         CB_PHASE_SYNC();
         acb_mul<L>(o2, o1, t, S0, S1);
@@ -714,6 +732,7 @@ CB_HD void frobenius1_thread(const FrobParams& p, int64_t inst, SCR S0, SCR S1) 
         if (nu < rl) acb_set<L>(gnew, at<L>(p.rhs, nu, hslot));
         else acb_zero<L>(gnew);
         int64_t i = clampi(nu, 1, p.degree);
+        if (L >= 64) acb_prefetch<L>(at<L>(p.res, nu - i, slot));
         CRef ind = indicial_eval<L, SYNC, true>(p, oslot, i, rho, nu - i, o1, o2, t, kb, S0, S1);
 #pragma unroll 1
         do {
@@ -722,6 +741,7 @@ CB_HD void frobenius1_thread(const FrobParams& p, int64_t inst, SCR S0, SCR S1) 
             CB_PHASE_SYNC();
             acb_addsub<L>(gnew, gnew, prod, true, S0, S1);
             i--;
+            if (L >= 64 && i > 0) acb_prefetch<L>(at<L>(p.res, nu - i, slot));
             ind = indicial_eval<L, SYNC, true>(p, oslot, i, rho, nu - i, o1, o2, t, kb, S0, S1);
         } while (i > 0);
         // g_nu = g_new / f_0(rho + nu); `prod` and the unused one of (o1,o2) are free temporaries

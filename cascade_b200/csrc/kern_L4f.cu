@@ -1,0 +1,3 @@
+// kernels for prec = 128 bits: the Fuchs recurrences (table, shared / per-instance operator, integer operator)
+#include "cb_kernels.cuh"
+CB_DEFINE_LAUNCH_FUCHS(4)
