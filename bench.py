@@ -313,11 +313,23 @@ class FrobeniusSweep(Workload):
         self.rho0_t = np.zeros((1, 2 * batch, 4), np.int32)
         self.rho0_t[:, :, 1] = 2
         self.rho1_m, self.rho1_t = pack_entries(one_minus_c, 1, 2 * batch)
+        self.merged = getattr(args, "frob_calls", 1) == 1
+        if self.merged:
+            # ONE call per step: the (operator, exponent) pairs of both runs side by side -- instances 0 .. batch-1 with
+            # rho = 0, batch .. 2 batch-1 with rho = 1 - c (the ABI takes an exponent per instance)
+            self.ode_m = np.ascontiguousarray(np.concatenate([self.ode_m, self.ode_m], axis=2))
+            self.ode_t = np.ascontiguousarray(np.concatenate([self.ode_t, self.ode_t], axis=1))
+            self.rho_m = np.ascontiguousarray(np.concatenate([self.rho0_m, self.rho1_m], axis=2))
+            self.rho_t = np.ascontiguousarray(np.concatenate([self.rho0_t, self.rho1_t], axis=1))
+            self.d_rho = [self.to_dev(self.rho_m, self.rho_t)]
+            self.call_batch = 2 * batch
+        else:
+            self.d_rho = [self.to_dev(self.rho0_m, self.rho0_t), self.to_dev(self.rho1_m, self.rho1_t)]
+            self.call_batch = batch
         self.d_ode = self.to_dev(self.ode_m, self.ode_t)
-        self.d_rho = [self.to_dev(self.rho0_m, self.rho0_t), self.to_dev(self.rho1_m, self.rho1_t)]
-        self.d_res_m = torch.empty((n + 1, Lh, 2 * batch), dtype=torch.int32, device=dev)
-        self.d_res_t = torch.empty((n + 1, 2 * batch, 4), dtype=torch.int32, device=dev)
-        self.ws_bytes = lib.cb200_frobenius_workspace_bytes(Lh, batch)
+        self.d_res_m = torch.empty((n + 1, Lh, 2 * self.call_batch), dtype=torch.int32, device=dev)
+        self.d_res_t = torch.empty((n + 1, 2 * self.call_batch, 4), dtype=torch.int32, device=dev)
+        self.ws_bytes = lib.cb200_frobenius_workspace_bytes(Lh, self.call_batch)
         self.d_ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
         self.coeffs = 2 * batch * n
         self.config = self.describe()
@@ -326,8 +338,10 @@ class FrobeniusSweep(Workload):
 
     def describe(self):
         batch, n = self.args.batch or 16384, self.args.terms or 256
+        calls = getattr(self.args, "frob_calls", 1)
+        how = "one step = both runs, submitted as ONE batch of (operator, exponent) pairs" if calls == 1 else "one step = both runs, one call each"
         return {"workload": f"configs[2]: Gauss hypergeometric acb_ode_solve_frobenius (M = 1), 4096 bits, {batch} (a,b,c) "
-                            f"triples per GPU, {n} terms, rho = 0 and rho = 1 - c (one step = both runs)",
+                            f"triples per GPU, {n} terms, rho = 0 and rho = 1 - c ({how})", "calls_per_step": calls,
                 "L_limbs": self.Lh, "order": 2, "degree": 2, "terms": n, "batch_per_gpu": batch, "seed": hex(0x5EED0003),
                 "cache": "4.4 GB of results and 0.5 GB of per-instance temporaries per run exceed the 126 MB L2; no flush needed"}
 
@@ -337,7 +351,7 @@ class FrobeniusSweep(Workload):
     def kernels(self):
         p = self.p
         for rm, rt in self.d_rho:
-            rc = self.lib.cb200_frobenius1_batch_dev(self.Lh, 2, 2, -1, self.n, self.batch, p(self.d_ode[0]), p(self.d_ode[1]), 0,
+            rc = self.lib.cb200_frobenius1_batch_dev(self.Lh, 2, 2, -1, self.n, self.call_batch, p(self.d_ode[0]), p(self.d_ode[1]), 0,
                                                      p(rm), p(rt), 0, p(self.d_res_m), p(self.d_res_t), p(self.d_ws),
                                                      self.ws_bytes, self.sp)
             assert rc == 0, f"cb200_frobenius1_batch_dev -> {rc}"
@@ -352,19 +366,24 @@ class FrobeniusSweep(Workload):
                              traffic_for(2, {"batch": self.batch, "terms": self.n}))
 
     def e2e_setup(self):
-        Lh, n, S = self.Lh, self.n, 2 * self.batch
+        Lh, n, S = self.Lh, self.n, 2 * self.call_batch
         self.h_res_m, pm = pinned_array(self.lib, (n + 1, Lh, S), np.uint32)
         self.h_res_t, _ = pinned_array(self.lib, (n + 1, S, 4), np.int32)
         del self.d_res_m, self.d_res_t, self.d_ws
         self.torch.cuda.empty_cache()
-        self.h2d = 2 * (self.ode_m.nbytes + self.ode_t.nbytes) + self.rho0_m.nbytes + self.rho0_t.nbytes + self.rho1_m.nbytes + self.rho1_t.nbytes
-        self.d2h = 2 * (n + 1) * S * (Lh * 4 + 16)
-        return "cb200_frobenius1_batch_host twice per step (rho = 0, rho = 1 - c): operators and exponents uploaded, the full " \
-               f"series copied back into caller-owned {'page-locked' if pm else 'pageable'} arrays"
+        calls = 1 if self.merged else 2
+        if self.merged:
+            self.h2d = self.ode_m.nbytes + self.ode_t.nbytes + self.rho_m.nbytes + self.rho_t.nbytes
+        else:
+            self.h2d = 2 * (self.ode_m.nbytes + self.ode_t.nbytes) + self.rho0_m.nbytes + self.rho0_t.nbytes + self.rho1_m.nbytes + self.rho1_t.nbytes
+        self.d2h = calls * (n + 1) * S * (Lh * 4 + 16)
+        return f"cb200_frobenius1_batch_host, {calls} call(s) per step (rho = 0 and rho = 1 - c): operators and exponents uploaded, " \
+               f"the full series copied back into caller-owned {'page-locked' if pm else 'pageable'} arrays"
 
     def e2e_step(self):
-        for rm, rt in ((self.rho0_m, self.rho0_t), (self.rho1_m, self.rho1_t)):
-            rc = self.lib.cb200_frobenius1_batch_host(self.Lh, 2, 2, -1, self.n, self.batch, self.ode_m, self.ode_t, 0, rm, rt, 0,
+        runs = ((self.rho_m, self.rho_t),) if self.merged else ((self.rho0_m, self.rho0_t), (self.rho1_m, self.rho1_t))
+        for rm, rt in runs:
+            rc = self.lib.cb200_frobenius1_batch_host(self.Lh, 2, 2, -1, self.n, self.call_batch, self.ode_m, self.ode_t, 0, rm, rt, 0,
                                                       self.h_res_m, self.h_res_t, self.dev.index)
             assert rc == 0, f"cb200_frobenius1_batch_host -> {rc}"
 
@@ -610,6 +629,7 @@ def main():
     ap.add_argument("--terms", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-tiles", type=int, default=0, help="config 1: force the number of instance tiles of the end-to-end leg (default: 1 if the host memory allows)")
+    ap.add_argument("--frob-calls", type=int, default=1, choices=[1, 2], help="config 2: both exponents as one batch (1) or one call per exponent (2)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
 

@@ -86,6 +86,54 @@ __global__ void __launch_bounds__(HybCfg<L>::TPB, 1) frobenius1_hyb_kernel(FrobP
         frobenius1_thread<L, true>(p, idx, S0, S1);
     }
 }
+// ---- the 4096-bit Frobenius recurrence for batches of more than one wave: persistent CTAs of 208 threads on hybrid
+// columns (6.5 warps per SM against the 3.5 of the all-shared kernel), work units of (208 instances, 8 coefficients)
+// handed out by an atomic counter as in the recurrence kernel -- no wave quantisation, any batch size
+template <int L> struct FrobPersCfg {
+    static constexpr bool ON = L == 128;
+    static constexpr int TPB = 208, KS = HybCfg<L>::KS, RANGE = 8;
+    static constexpr size_t SMEM = (size_t)2 * KS * TPB * sizeof(uint32_t);
+};
+template <int L>
+__global__ void __launch_bounds__(FrobPersCfg<L>::TPB, 1) frobenius1_pers_kernel(FrobParams p) {
+    if constexpr (FrobPersCfg<L>::ON) {
+        extern __shared__ uint32_t cb_smem[];
+        __shared__ int unit_s;
+        constexpr int TPB = FrobPersCfg<L>::TPB, KS = FrobPersCfg<L>::KS;
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(cb_smem) + 4u * threadIdx.x;
+        const int64_t nblocks = (p.batch + TPB - 1) / TPB;
+        const int64_t nranges = (p.n + FrobPersCfg<L>::RANGE) / FrobPersCfg<L>::RANGE;  // coefficients 0 .. n
+        const int64_t total = nblocks * nranges;
+        const uint32_t gs = (uint32_t)(nblocks * TPB);
+        for (;;) {
+            if (threadIdx.x == 0) {
+                int u = atomicAdd(p.sched, 1);
+                if (u < total) {
+                    int64_t b = u % nblocks, r = u / nblocks;
+                    while (r > 0 && atomicAdd(p.sched + 1 + b, 0) < (int)r) __nanosleep(200);
+                    __threadfence();
+                }
+                unit_s = u;
+            }
+            __syncthreads();
+            const int64_t u = unit_s;
+            if (u >= total) break;
+            const int64_t b = u % nblocks, r = u / nblocks;
+            const int64_t inst = b * TPB + threadIdx.x;
+            const int64_t lo = r * FrobPersCfg<L>::RANGE;
+            const int64_t hi = lo + FrobPersCfg<L>::RANGE - 1 < p.n ? lo + FrobPersCfg<L>::RANGE - 1 : p.n;
+            HybridScratch<TPB, KS> S0{sbase, p.gcols + inst, gs};
+            HybridScratch<TPB, KS> S1{sbase + 4u * (uint32_t)(KS * TPB), p.gcols + (size_t)HybCfg<L>::GW * gs + inst, gs};
+            // every thread walks the loops (phase barriers keep the 6.5 warps on the same instruction cache lines:
+            // without them this kernel runs at 0.68 of the speed); threads beyond the batch touch no memory
+            const bool live = inst < p.batch;
+            frobenius1_thread<L, true>(p, live ? inst : 0, S0, S1, lo, hi, live);
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) atomicExch(p.sched + 1 + b, (int)(r + 1));
+        }
+    }
+}
 // ---- cooperating lanes (cb_coop.cuh): four lanes per instance, one hybrid column per lane, 64 instances per CTA
 template <int L> struct CoopCfg {
     static constexpr bool ON = L >= 64;
@@ -706,6 +754,31 @@ int coop_frob_lanes(const FrobParams& p) {
     if (coop_wanted<L>(p.batch, sm_count(), true)) return 4;
     return L == 64 ? 2 : 0;
 }
+// the persistent hybrid kernel: homogeneous solves of more than one wave of the all-shared kernel (CB200_FROBPERS=0/1
+// in the environment overrides)
+template <int L>
+bool use_frob_pers(const FrobParams& p) {
+    if (!FrobPersCfg<L>::ON || p.rhs_len != 0 || p.sched == nullptr) return false;
+    const int64_t padded = (p.batch + FrobPersCfg<L>::TPB - 1) / FrobPersCfg<L>::TPB * FrobPersCfg<L>::TPB;
+    if (p.gcols_words < (size_t)2 * HybCfg<L>::GW * (size_t)padded) return false;
+    const char* e = getenv("CB200_FROBPERS");
+    if (e && e[0] == '0') return false;
+    if (e && e[0] == '1') return true;
+    return p.batch > (int64_t)sm_count() * Cfg<L>::TPB;
+}
+template <int L>
+int launch_frob_pers(const FrobParams& p, cudaStream_t s) {
+    if (p.batch <= 0) return 0;
+    cudaError_t e = cudaFuncSetAttribute(frobenius1_pers_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FrobPersCfg<L>::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t nblocks = (p.batch + FrobPersCfg<L>::TPB - 1) / FrobPersCfg<L>::TPB;
+    e = cudaMemsetAsync(p.sched, 0, sizeof(int) * (size_t)(nblocks + 1), s);
+    if (e != cudaSuccess) return (int)e;
+    const int sms = sm_count();
+    const int grid = (int)(nblocks < sms ? nblocks : sms);
+    frobenius1_pers_kernel<L><<<grid, FrobPersCfg<L>::TPB, FrobPersCfg<L>::SMEM, s>>>(p);
+    return (int)cudaGetLastError();
+}
 template <int L, int LANES>
 int launch_coop_frob(const FrobParams& p, cudaStream_t s) {
     if (p.batch <= 0) return 0;
@@ -886,6 +959,7 @@ struct LaunchTable {
     CB_DECLARE_LAUNCHERS(LL)                                                                               \
     static int frob_##LL(const FrobParams& p, cudaStream_t s) {                                            \
         if (int lanes = coop_frob_lanes<LL>(p)) return lanes == 2 ? launch_coop_frob<LL, 2>(p, s) : launch_coop_frob<LL, 4>(p, s);                                       \
+        if (use_frob_pers<LL>(p)) return launch_frob_pers<LL>(p, s);                                       \
         if (use_hybrid<LL>(p.batch, sm_count(), HybRatio<LL>::FROB))                                       \
             return launch<LL>(frobenius1_hyb_kernel<LL>, p, p.batch, s, HybCfg<LL>::TPB, HybCfg<LL>::SMEM); \
         return launch<LL>(frobenius1_kernel<LL>, p, p.batch, s);                                           \

@@ -676,33 +676,41 @@ struct FrobParams {
 constexpr int FROB_NTMP = 7;
 
 // result may be one of (o1, o2): returns which holds f_nu(rho + shift).  IM_READY: t holds the imaginary part of rho
-// already (acb_copy_im by the caller), so rho + k only writes the real part of t
+// already (acb_copy_im by the caller), so rho + k only writes the real part of t.  active = false: a thread without an
+// instance (ragged last block of the persistent kernel) walks the same loops and meets the same phase barriers but
+// touches no memory.
 template <int L, bool SYNC = false, bool IM_READY = false, class SCR, class PRM>
 CB_HD CRef indicial_eval(const PRM& p, size_t oslot, int64_t nu, const CRef& rho, int64_t shift,
-                         CRef o1, CRef o2, const CRef& t, const CRef& kb, SCR S0, SCR S1) {
+                         CRef o1, CRef o2, const CRef& t, const CRef& kb, SCR S0, SCR S1, bool active = true) {
     const int D1 = p.degree + 1;
     nu += p.valuation;
-    acb_zero<L>(o1);
+    if (active) acb_zero<L>(o1);
     if (nu > p.degree) return o1;
 #pragma unroll 1
     for (int64_t lam = clampi(p.degree - nu, 0, p.order); lam >= 0; lam--) {
-        if (L >= 64 && lam + nu >= 0) acb_prefetch<L>(at<L>(p.ode, lam * D1 + (lam + nu), oslot));
-        acb_add_si<L, !IM_READY>(t, rho, shift - lam, kb, S0, S1);
+        if (active) {
+            if (L >= 64 && lam + nu >= 0) acb_prefetch<L>(at<L>(p.ode, lam * D1 + (lam + nu), oslot));
+            acb_add_si<L, !IM_READY>(t, rho, shift - lam, kb, S0, S1);
+        }
         CB_PHASE_SYNC();
-        acb_mul<L>(o2, o1, t, S0, S1);
+        if (active) acb_mul<L>(o2, o1, t, S0, S1);
         CRef sw = o1;
         o1 = o2;
         o2 = sw;
         if (lam + nu < 0) continue;
-        acb_addsub<L>(o1, o1, at<L>(p.ode, lam * D1 + (lam + nu), oslot), false, S0, S1);
+        if (active) acb_addsub<L>(o1, o1, at<L>(p.ode, lam * D1 + (lam + nu), oslot), false, S0, S1);
     }
     return o1;
 }
 
 // SYNC: phase barriers before the long calls of the main loop (its trip counts are launch parameters; the
 // right-hand-side branch before the loop is per instance and has none), see phase_sync
+// nu_from .. nu_to (nu_to < 0: p.n): the coefficients this call computes -- the recurrence reads the earlier ones back
+// from res, so a homogeneous solve can be cut into ranges (the persistent kernel's work units); nu_from = 0 starts the
+// series (g_0, the right-hand side branch).  active: see indicial_eval (homogeneous solves only).
 template <int L, bool SYNC = false, class SCR>
-CB_HD void frobenius1_thread(const FrobParams& p, int64_t inst, SCR S0, SCR S1) {
+CB_HD void frobenius1_thread(const FrobParams& p, int64_t inst, SCR S0, SCR S1, int64_t nu_from = 0, int64_t nu_to = -1,
+                             bool active = true) {
     const size_t slot = 2 * (size_t)inst;
     const size_t oslot = (p.ode.S == 2) ? 0 : slot;
     const size_t rslot = (p.rho.S == 2) ? 0 : slot;
@@ -713,8 +721,11 @@ CB_HD void frobenius1_thread(const FrobParams& p, int64_t inst, SCR S0, SCR S1) 
     const size_t hslot = (p.rhs_len > 0 && p.rhs.S == 2) ? 0 : slot;
     int64_t rl = p.rhs_len;
     while (rl > 0 && acb_is_exact_zero(at<L>(p.rhs, rl - 1, hslot))) rl--;
-    if (rl == 0) {
-        acb_one<L>(at<L>(p.res, 0, slot));  // homogeneous case: g_0 = 1 (src/frobenius_solver.c:84-85)
+    if (nu_to < 0) nu_to = p.n;
+    if (nu_from > 0) {
+        // a later range of a homogeneous solve: nothing to start
+    } else if (rl == 0) {
+        if (active) acb_one<L>(at<L>(p.res, 0, slot));  // homogeneous case: g_0 = 1 (src/frobenius_solver.c:84-85)
     } else {
         // rho -= v; g_0 = rhs_0 / f_0(rho)   (src/frobenius_solver.c:88-95)
         CRef radj = at<L>(p.tmp, 6, slot);
@@ -726,28 +737,30 @@ CB_HD void frobenius1_thread(const FrobParams& p, int64_t inst, SCR S0, SCR S1) 
         acb_div<L>(at<L>(p.res, 0, slot), at<L>(p.rhs, 0, hslot), ind, spare, S0, S1);
     }
     // every f(rho + k) below adds an integer to the same rho: its imaginary part goes into t once
-    if (rl == 0) acb_copy_im<L>(t, rho);
+    if (rl == 0 && active) acb_copy_im<L>(t, rho);
 #pragma unroll 1
-    for (int64_t nu = 1; nu <= p.n; nu++) {
-        if (nu < rl) acb_set<L>(gnew, at<L>(p.rhs, nu, hslot));
-        else acb_zero<L>(gnew);
+    for (int64_t nu = (nu_from > 1 ? nu_from : 1); nu <= nu_to; nu++) {
+        if (active) {
+            if (nu < rl) acb_set<L>(gnew, at<L>(p.rhs, nu, hslot));
+            else acb_zero<L>(gnew);
+        }
         int64_t i = clampi(nu, 1, p.degree);
-        if (L >= 64) acb_prefetch<L>(at<L>(p.res, nu - i, slot));
-        CRef ind = indicial_eval<L, SYNC, true>(p, oslot, i, rho, nu - i, o1, o2, t, kb, S0, S1);
+        if (L >= 64 && active) acb_prefetch<L>(at<L>(p.res, nu - i, slot));
+        CRef ind = indicial_eval<L, SYNC, true>(p, oslot, i, rho, nu - i, o1, o2, t, kb, S0, S1, active);
 #pragma unroll 1
         do {
             CB_PHASE_SYNC();
-            acb_mul<L>(prod, ind, at<L>(p.res, nu - i, slot), S0, S1);
+            if (active) acb_mul<L>(prod, ind, at<L>(p.res, nu - i, slot), S0, S1);
             CB_PHASE_SYNC();
-            acb_addsub<L>(gnew, gnew, prod, true, S0, S1);
+            if (active) acb_addsub<L>(gnew, gnew, prod, true, S0, S1);
             i--;
-            if (L >= 64 && i > 0) acb_prefetch<L>(at<L>(p.res, nu - i, slot));
-            ind = indicial_eval<L, SYNC, true>(p, oslot, i, rho, nu - i, o1, o2, t, kb, S0, S1);
+            if (L >= 64 && i > 0 && active) acb_prefetch<L>(at<L>(p.res, nu - i, slot));
+            ind = indicial_eval<L, SYNC, true>(p, oslot, i, rho, nu - i, o1, o2, t, kb, S0, S1, active);
         } while (i > 0);
         // g_nu = g_new / f_0(rho + nu); `prod` and the unused one of (o1,o2) are free temporaries
         CRef spare = (ind.m == o1.m) ? o2 : o1;
         CB_PHASE_SYNC();
-        acb_div<L>(at<L>(p.res, nu, slot), gnew, ind, spare, S0, S1);
+        if (active) acb_div<L>(at<L>(p.res, nu, slot), gnew, ind, spare, S0, S1);
     }
 }
 

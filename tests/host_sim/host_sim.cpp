@@ -187,6 +187,16 @@ int cbsim_frobenius1_batch(int L_, int order, int degree, int valuation, int64_t
     p.gcols = nullptr;
     p.sched = nullptr;
     p.gcols_words = 0;
+    // CBSIM_FROB_RANGE=k: a homogeneous solve in ranges of k coefficients, as the persistent kernel's work units run it
+    const char* e = getenv("CBSIM_FROB_RANGE");
+    const int64_t range = (e && rhs_len == 0) ? atoi(e) : 0;
+    if (range > 0) {
+        for (int64_t lo = 0; lo <= n; lo += range) {
+            const int64_t hi = lo + range - 1 < n ? lo + range - 1 : n;
+            SIM_DISPATCH(L_, run_hyb<L>(batch, [&](int64_t i, auto a, auto b) { frobenius1_thread<L>(p, i, a, b, lo, hi); }));
+        }
+        return 0;
+    }
     SIM_DISPATCH(L_, run_hyb<L>(batch, [&](int64_t i, auto a, auto b) { frobenius1_thread<L>(p, i, a, b); }));
     return 0;
 }

@@ -48,6 +48,14 @@ def test_frobenius(oracle, sim_driver, L):
     cases.case_frobenius(oracle, sim_driver, L, seed=9, n=12 if L == 128 else 20, batch=2)
 
 
+@pytest.mark.parametrize("L", [4, 128])
+def test_frobenius_in_coefficient_ranges(monkeypatch, oracle, sim_driver, L):
+    """the persistent 4096-bit Frobenius kernel cuts a homogeneous solve into work units of a few coefficients
+    (frobenius1_thread with nu_from .. nu_to, earlier coefficients read back from the result array)"""
+    monkeypatch.setenv("CBSIM_FROB_RANGE", "3")
+    cases.case_frobenius(oracle, sim_driver, L, seed=39, n=10, batch=2)
+
+
 @pytest.mark.parametrize("L", [64, 128])
 def test_integer_like_operands_take_the_two_row_product(oracle, sim_driver, L):
     """2048 / 4096 bits: a factor whose limbs below the top two are zero (rho + k with rho = 0, g_0 = 1, an integer

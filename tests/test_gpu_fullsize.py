@@ -138,6 +138,48 @@ def _pick(dm, dt, sample, L, entries):
     return entry_major_to_instance_major(unpack_entries(L, m, t), len(sample), entries)
 
 
+def test_config2_both_exponents_in_one_batch_full_size(oracle):
+    """BASELINE configs[2] as `bench.py --config 2` submits it: the 2 x 16 384 (operator, exponent) pairs of both runs in
+    ONE call (rho = 0 for the first half, rho = 1 - c for the second).  More than one wave of the all-shared kernel, so
+    the launcher picks the persistent 208-thread kernel on hybrid columns (work units of 8 coefficients); sampled
+    instances at CTA / warp edges of both halves against the oracle."""
+    import torch
+
+    import bench
+    from cascade_b200 import _lib, api
+    from cascade_b200.format import FLAG_NAN, Balls, from_complex, instance_major_to_entry_major, pack_entries
+
+    lib = _lib.lib()
+    L, half, n = 128, 16384, 256
+    batch = 2 * half
+    dev = torch.device("cuda:0")
+    drv = api.HostBufferDriver(0)
+    a, b, c = bench.hypgeom_params(half, L)
+    ode = api.acb_ode_hypgeom_batch(a, b, c, driver=drv)
+    rho = Balls.concat([Balls.zeros(2 * half, L), api.ew(api.OP_SUB, from_complex([1] * half, L), c, driver=drv)])
+    om, ot = pack_entries(instance_major_to_entry_major(ode, half, 9), 9, 2 * half)
+    d_om = torch.from_numpy(np.concatenate([om, om], axis=2).view(np.int32)).to(dev)
+    d_ot = torch.from_numpy(np.concatenate([ot, ot], axis=1)).to(dev)
+    rm, rt = pack_entries(rho, 1, 2 * batch)
+    d_rm, d_rt = torch.from_numpy(rm.view(np.int32)).to(dev), torch.from_numpy(rt).to(dev)
+    d_res_m = torch.empty((n + 1, L, 2 * batch), dtype=torch.int32, device=dev)
+    d_res_t = torch.empty((n + 1, 2 * batch, 4), dtype=torch.int32, device=dev)
+    wsb = lib.cb200_frobenius_workspace_bytes(L, batch)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    rc = lib.cb200_frobenius1_batch_dev(L, 2, 2, -1, n, batch, p(d_om), p(d_ot), 0, p(d_rm), p(d_rt), 0, p(d_res_m), p(d_res_t),
+                                        p(ws), wsb, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert int((d_res_t[:, :, 1] & FLAG_NAN).sum().item()) == 0
+    sample = _sample(batch, [1, 31, 32, 207, 208, 209, 415, 416, half - 1, half, half + 1, 32655, 32656, batch - 2], 22, extra=4)
+    got = _pick(d_res_m, d_res_t, sample, L, n + 1)
+    sub_ode = Balls.concat([ode[18 * (i % half):18 * (i % half) + 18] for i in sample])
+    sub_rho = Balls.concat([rho[2 * i:2 * i + 2] for i in sample])
+    want = oracle.frobenius1_batch(2, 2, n, sub_ode, sub_rho, len(sample), False, nthreads=8)
+    assert got.same_as(want), "configs[2], both exponents in one batch: full-size GPU run differs from the oracle on the sampled instances"
+
+
 def test_frobenius_2048_bits_two_lane_form_chosen_by_the_launcher(oracle):
     """2048 bits, 12 000 hypergeometric instances (more than one wave of four-lane cooperative CTAs): the launcher
     picks the TWO-lane cooperative Frobenius kernel (CTAs of 120 instances, ragged last CTA, work units of 8
