@@ -363,7 +363,7 @@ class FrobeniusSweep(Workload):
         Lh = self.Lh
         macs = 36 * Lh * Lh * self.coeffs  # 7 complex products + 1 complex division
         return imad_roofline(macs, kernel_ms, imad_peak, self.coeffs * 2 * (4 * Lh + 16), peaks,
-                             traffic_for(2, {"batch": self.batch, "terms": self.n}))
+                             traffic_for(2, {"batch": self.batch, "terms": self.n, "calls": 1 if self.merged else 2}))
 
     def e2e_setup(self):
         Lh, n, S = self.Lh, self.n, 2 * self.call_batch

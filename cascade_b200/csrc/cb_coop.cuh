@@ -34,6 +34,11 @@ struct Quad {
     uint32_t gs;
     uint32_t a20 = 0;        // column of role 0 in a second region (L + 2 words: accumulators of the recurrence kernel)
     uint32_t* st = nullptr;  // 24 state words of the instance (shared memory, 16-byte aligned)
+    bool active = true;      // false: lanes without an instance (ragged last unit): they only meet the phase barriers
+    bool cta_sync = false;   // phase barriers of the whole CTA before the long phases (see phase_sync of cb_solvers.cuh)
+    __device__ __forceinline__ void phase() const {
+        if (cta_sync) __syncthreads();
+    }
     __device__ __forceinline__ Col col(int c) const { return Col{a0 + 4u * cstep * (uint32_t)c, g0 + (size_t)cstep * c, gs}; }
     __device__ __forceinline__ Scratch<STRIDE> acol(int c) const { return Scratch<STRIDE>{a20 + 4u * cstep * (uint32_t)c}; }
     __device__ __forceinline__ void sync() const { __syncwarp(qmask); }
@@ -47,6 +52,8 @@ struct Quad {
     uint32_t* g[4];
     uint32_t* p2[4] = {nullptr, nullptr, nullptr, nullptr};
     uint32_t* st = nullptr;
+    bool active = true, cta_sync = false;
+    void phase() const {}
     Col col(int qq) const { return Col{p[qq], g[qq], 1u}; }
     Scratch<STRIDE> acol(int qq) const { return Scratch<STRIDE>{p2[qq]}; }
     void sync() const {}
@@ -57,6 +64,7 @@ struct Quad {
 // ---- copies and constants, limbs dealt out to the four lanes
 template <int L, class QD>
 CB_HD void coop_set(const QD& Q, const CRef& z, const CRef& x) {
+    if (!Q.active) return;
     CB_COOP_EACH(Q, q) {
         const int part = q & 1, k0 = q >> 1;
         staged_copy<L / 2>([&](int j) { return x.m[(size_t)(2 * j + k0) * x.stride + part]; },
@@ -67,6 +75,7 @@ CB_HD void coop_set(const QD& Q, const CRef& z, const CRef& x) {
 }
 template <int L, class QD>
 CB_HD void coop_zero(const QD& Q, const CRef& z) {
+    if (!Q.active) return;
     CB_COOP_EACH(Q, q) {
         const int part = q & 1;
 #pragma unroll 8
@@ -77,6 +86,7 @@ CB_HD void coop_zero(const QD& Q, const CRef& z) {
 }
 template <int L, class QD>
 CB_HD void coop_one(const QD& Q, const CRef& z) {
+    if (!Q.active) return;
     CB_COOP_EACH(Q, q) {
         const int part = q & 1;
 #pragma unroll 8
@@ -98,6 +108,7 @@ struct FdotJob {
 };
 template <int L, class QD>
 CB_HD void coop_fdot2_pair(const QD& Q, const FdotJob<L>& j0, const FdotJob<L>& j1, bool have1) {  // (inlined: out of line its job records live in local memory, 2048-bit two-lane kernel 16.8 -> 30.7 ms)
+    if (!Q.active) return;
     // the products: every lane works through the non-zero ones among its roles in step with the others (a lane playing
     // two roles whose first product is zero starts on its second at once)
     unsigned todo = 0u;
@@ -139,6 +150,7 @@ CB_HD void coop_fdot2_pair(const QD& Q, const FdotJob<L>& j0, const FdotJob<L>& 
 // z = x * y (acb_mul); z must not alias x or y
 template <int L, class QD>
 CB_HD void coop_mul(const QD& Q, const CRef& z, const CRef& x, const CRef& y) {
+    if (!Q.active) return;
     Opd a = re_of(x), b = im_of(x), c = re_of(y), d = im_of(y);
     FdotJob<L> jr{a, c, b, d, true, wre(z), z.t}, ji{a, d, b, c, false, wim(z), z.t + 1};
     coop_fdot2_pair<L>(Q, jr, ji, true);
@@ -151,6 +163,7 @@ CB_HD WRef wpart(const CRef& z, int part) { return WRef{z.m + part, z.stride}; }
 // z = x +- y (componentwise; z may alias x or y): real part on role 0, imaginary part on role 2
 template <int L, class QD>
 CB_HD void coop_addsub(const QD& Q, const CRef& z, const CRef& x, const CRef& y, bool sub) {
+    if (!Q.active) return;
     CB_COOP_EACH(Q, q) {
         if (q & 1) continue;
         const int part = q >> 1;
@@ -162,6 +175,7 @@ CB_HD void coop_addsub(const QD& Q, const CRef& z, const CRef& x, const CRef& y,
 // the imaginary part of x into z (role 2)
 template <int L, class QD>
 CB_HD void coop_copy_im(const QD& Q, const CRef& z, const CRef& x) {
+    if (!Q.active) return;
     CB_COOP_EACH(Q, q) {
         if (q == 2) acb_copy_im<L>(z, x);
     }
@@ -171,6 +185,7 @@ CB_HD void coop_copy_im(const QD& Q, const CRef& z, const CRef& x) {
 // caller has put it there already (COPY_IM = false)
 template <int L, bool COPY_IM = true, class QD>
 CB_HD void coop_add_si(const QD& Q, const CRef& z, const CRef& x, int64_t k, const CRef& kball) {
+    if (!Q.active) return;
     CB_COOP_EACH(Q, q) {
         if (q == 0) {
             uint64_t ka = k < 0 ? (uint64_t)0 - (uint64_t)k : (uint64_t)k;
@@ -193,6 +208,7 @@ CB_HD void coop_add_si(const QD& Q, const CRef& z, const CRef& x, int64_t k, con
 // z = 1 / y; z must not alias y; uses tmp.re as a real temporary (acb_inv: t = c^2 + d^2 rounded once, then c/t, -d/t)
 template <int L, class QD>
 CB_HD void coop_inv(const QD& Q, const CRef& z, const CRef& y, const CRef& tmp) {
+    if (!Q.active) return;
     Opd c = re_of(y), d = im_of(y);
     FdotJob<L> jt{c, c, d, d, false, wre(tmp), tmp.t};
     coop_fdot2_pair<L>(Q, jt, jt, false);
@@ -209,6 +225,7 @@ CB_HD void coop_inv(const QD& Q, const CRef& z, const CRef& y, const CRef& tmp) 
 // z = x / y; z must not alias x or y; inv: a complex temporary (acb_div: componentwise for a real divisor, else x * inv(y))
 template <int L, class QD>
 CB_HD void coop_div(const QD& Q, const CRef& z, const CRef& x, const CRef& y, const CRef& inv) {
+    if (!Q.active) return;
     if (is_exact_zero(ld_meta(y.t + 1))) {
         CB_COOP_EACH(Q, q) {
             if (q & 1) continue;
@@ -233,6 +250,7 @@ CB_HD CRef coop_indicial_eval(const QD& Q, const PRM& p, size_t oslot, int64_t n
 #pragma unroll 1
     for (int64_t lam = clampi(p.degree - nu, 0, p.order); lam >= 0; lam--) {
         coop_add_si<L, !IM_READY>(Q, t, rho, shift - lam, kb);
+        Q.phase();
         coop_mul<L>(Q, o2, o1, t);
         CRef sw = o1;
         o1 = o2;
@@ -266,12 +284,14 @@ CB_HD void frobenius1_coop_quad(const FrobParams& p, int64_t inst, const QD& Q, 
         CRef ind = coop_indicial_eval<L, true>(Q, p, oslot, i, rho, nu - i, o1, o2, t, kb);
 #pragma unroll 1
         do {
+            Q.phase();
             coop_mul<L>(Q, prod, ind, at<L>(p.res, nu - i, slot));
             coop_addsub<L>(Q, gnew, gnew, prod, true);
             i--;
             ind = coop_indicial_eval<L, true>(Q, p, oslot, i, rho, nu - i, o1, o2, t, kb);
         } while (i > 0);
         CRef spare = (ind.m == o1.m) ? o2 : o1;
+        Q.phase();
         coop_div<L>(Q, at<L>(p.res, nu, slot), gnew, ind, spare);
     }
 }

@@ -204,8 +204,12 @@ __global__ void __launch_bounds__(CoopGeom<L, LANES>::TPB, 1) frobenius1_coop_ke
             const int64_t inst = b * G + Geo::local_instance();
             const int64_t lo = r * CoopCfg<L>::RANGE;
             const int64_t hi = lo + CoopCfg<L>::RANGE - 1 < p.n ? lo + CoopCfg<L>::RANGE - 1 : p.n;
-            const typename Geo::Q Q = Geo::quad(sbase, p.gcols, b, nblocks);
-            if (inst < p.batch) frobenius1_coop_quad<L>(p, inst, Q, lo, hi);
+            typename Geo::Q Q = Geo::quad(sbase, p.gcols, b, nblocks);
+            // every lane walks the loops and meets the CTA-wide phase barriers (instruction cache); lanes without an
+            // instance touch no memory
+            Q.active = inst < p.batch;
+            Q.cta_sync = true;
+            frobenius1_coop_quad<L>(p, Q.active ? inst : 0, Q, lo, hi);
             __threadfence();
             __syncthreads();
             if (threadIdx.x == 0) atomicExch(p.sched + 1 + b, (int)(r + 1));
@@ -728,12 +732,12 @@ inline size_t coop_tail_words(int L, int64_t count) {
 }
 // CB200_COOP=0/1 in the environment overrides (development; 2 / 4 force that many lanes for the Frobenius recurrence).
 // Default, from measurements on B200 (tools/quick_coop.py, profiles/coop_r02.txt): four lanes per instance win while
-// the batch is at most ONE wave of cooperative CTAs (64 instances per SM) -- Horner 2.0-2.9x at 2 .. 4096 points (2048
-// and 4096 bits), the Frobenius recurrence 1.8-2.2x at 2048 bits and 1.9-2.5x at 4096 bits -- and lose beyond about two
-// waves (the lanes that only form products idle in the tails and the long divisions).  Beyond one wave the 2048-bit
-// Frobenius recurrence runs on TWO lanes per instance (every lane busy in every phase, twice the warps of the
-// one-thread kernel: 1.46x at 16 384 instances); at 4096 bits two lanes lose to the one-thread kernel (104 instances
-// per SM either way, and the larger code stalls on instruction fetch), which keeps the large batches.
+// the batch is at most ONE wave of cooperative CTAs (64 instances per SM) -- Horner 2.0-3.4x at 2 .. 4096 points (2048
+// and 4096 bits), the Frobenius recurrence 1.9-2.3x -- and lose beyond about two waves (the lanes that only form
+// products idle in the tails and the long divisions).  Beyond one wave the Frobenius recurrence runs on TWO lanes per
+// instance (every lane busy in every phase, twice the warps of the one-thread kernel; with CTA-wide phase barriers,
+// without which seven warps at different places of the code stall on instruction fetch): 1.5x at 2048 bits, 1.09x at
+// 4096 bits up to one wave of the one-thread kernel; larger 4096-bit batches go to the persistent hybrid kernel.
 template <int L>
 bool coop_wanted(int64_t count, int sms, bool frobenius) {
     if (!CoopCfg<L>::ON) return false;
@@ -752,7 +756,9 @@ int coop_frob_lanes(const FrobParams& p) {
     if (e && e[0] == '4') return 4;
     if (e && e[0] == '0') return 0;
     if (coop_wanted<L>(p.batch, sm_count(), true)) return 4;
-    return L == 64 ? 2 : 0;
+    if (L == 64) return 2;
+    // 4096 bits: two lanes up to one wave of the all-shared kernel (1.09x); beyond that the persistent hybrid kernel
+    return p.batch <= (int64_t)sm_count() * Cfg<L>::TPB ? 2 : 0;
 }
 // the persistent hybrid kernel: homogeneous solves of more than one wave of the all-shared kernel (CB200_FROBPERS=0/1
 // in the environment overrides)

@@ -5,9 +5,9 @@ import csv
 import json
 import sys
 
-CFG = {1: {"batch": 65536, "terms": 2000}, 2: {"batch": 16384, "terms": 256}, 3: {"terms": 1000, "tile": 131072},
+CFG = {1: {"batch": 65536, "terms": 2000}, 2: {"batch": 16384, "terms": 256, "calls": 1}, 3: {"terms": 1000, "tile": 131072},
        4: {"terms": 3504, "points": 1000000}}
-LAUNCHES_PER_STEP = {1: 1, 2: 2, 3: 8, 4: 1}  # launches of that kernel in one bench step (config 3: 8 tiles on one GPU)
+LAUNCHES_PER_STEP = {1: 1, 2: 1, 3: 8, 4: 1}  # launches of that kernel in one bench step (config 3: 8 tiles on one GPU)
 
 
 def to_bytes(val, unit):
