@@ -311,6 +311,7 @@ CB_HD void horner_coop_quad(const HornerParams& p, int64_t pt, const QD& Q) {
 #pragma unroll 1
         for (int k = p.nder - 1; k >= 0; k--) {
             CRef o = at<L>(p.out, k, slot);
+            Q.phase();
             coop_mul<L>(Q, tmp, o, a);
             if (k > 0)
                 coop_addsub<L>(Q, o, tmp, at<L>(p.out, k - 1, slot), false);

@@ -275,8 +275,10 @@ __global__ void __launch_bounds__(CoopCfg<L>::TPB, 1) horner_coop_kernel(HornerP
         extern __shared__ uint32_t cb_smem[];
         constexpr int G = CoopCfg<L>::G;
         const int64_t pt = (int64_t)blockIdx.x * G + (threadIdx.x >> 2);
-        const typename CoopGeom<L, 4>::Q Q = CoopGeom<L, 4>::quad((uint32_t)__cvta_generic_to_shared(cb_smem), p.gcols, blockIdx.x, gridDim.x);
-        if (pt < p.npts) horner_coop_quad<L>(p, pt, Q);
+        typename CoopGeom<L, 4>::Q Q = CoopGeom<L, 4>::quad((uint32_t)__cvta_generic_to_shared(cb_smem), p.gcols, blockIdx.x, gridDim.x);
+        Q.active = pt < p.npts;  // (lanes without a point walk the loops for the phase barriers only)
+        Q.cta_sync = true;
+        horner_coop_quad<L>(p, Q.active ? pt : 0, Q);
     }
 }
 
@@ -733,7 +735,8 @@ inline size_t coop_tail_words(int L, int64_t count) {
 // CB200_COOP=0/1 in the environment overrides (development; 2 / 4 force that many lanes for the Frobenius recurrence).
 // Default, from measurements on B200 (tools/quick_coop.py, profiles/coop_r02.txt): four lanes per instance win while
 // the batch is at most ONE wave of cooperative CTAs (64 instances per SM) -- Horner 2.0-3.4x at 2 .. 4096 points (2048
-// and 4096 bits), the Frobenius recurrence 1.9-2.3x -- and lose beyond about two waves (the lanes that only form
+// and 4096 bits; with the CTA-wide phase barriers it stays ahead up to three waves at 2048 bits and at every size at
+// 4096 bits: 1.5-1.8x), the Frobenius recurrence 1.9-2.3x -- and lose beyond about two waves (the lanes that only form
 // products idle in the tails and the long divisions).  Beyond one wave the Frobenius recurrence runs on TWO lanes per
 // instance (every lane busy in every phase, twice the warps of the one-thread kernel; with CTA-wide phase barriers,
 // without which seven warps at different places of the code stall on instruction fetch): 1.5x at 2048 bits, 1.09x at
@@ -744,7 +747,10 @@ bool coop_wanted(int64_t count, int sms, bool frobenius) {
     const char* e = getenv("CB200_COOP");
     if (e && e[0] == '0') return false;
     if (e && e[0] == '1') return true;
-    (void)frobenius;
+    // Horner at 4096 bits: four lanes at every size (65 536 points: 54 ms against 96 ms on the one-thread hybrid kernel)
+    if (!frobenius && L >= 128) return true;
+    // Horner at 2048 bits: 1.8x at 16 384 points, level at 65 536, behind at 262 144
+    if (!frobenius) return count <= (int64_t)3 * sms * CoopCfg<L>::G;
     return count <= (int64_t)sms * CoopCfg<L>::G;
 }
 // lanes per instance for the Frobenius recurrence (0: the one-thread kernels)

@@ -138,6 +138,28 @@ def _pick(dm, dt, sample, L, entries):
     return entry_major_to_instance_major(unpack_entries(L, m, t), len(sample), entries)
 
 
+@pytest.mark.parametrize("L,npts", [(64, 20000), (128, 40000)])
+def test_horner_cooperative_form_chosen_by_the_launcher_beyond_one_wave(oracle, L, npts):
+    """More points than one wave of cooperative CTAs (9 472): the launcher still picks four lanes per point at 2048 bits
+    up to three waves and at 4096 bits at every size (phase barriers, ragged last CTA); sampled points against the
+    oracle, one and two derivatives."""
+    from cascade_b200 import api
+    from cascade_b200.format import Balls, random_balls
+
+    rng = np.random.default_rng(4100 + L)
+    drv = api.HostBufferDriver(0)
+    length = 14
+    f = random_balls(rng, 2 * length, L, -3, 3, "ulp")
+    pts = random_balls(rng, 2 * npts, L, -2, 0, "zero")
+    sample = _sample(npts, [1, 7, 8, 63, 64, 65, 9471, 9472, 9473, npts - 2], 7)
+    sub = Balls.concat([pts[2 * i:2 * i + 2] for i in sample])
+    for nder in (1, 2):
+        got = api.acb_poly_evaluate_batch(f, pts, nder, driver=drv)
+        want = oracle.horner_batch(f, sub, nder)
+        pick = Balls.concat([got[2 * nder * i:2 * nder * (i + 1)] for i in sample])
+        assert pick.same_as(want), f"Horner L={L} nder={nder}: launcher-chosen cooperative kernel differs from the oracle"
+
+
 def test_config2_both_exponents_in_one_batch_full_size(oracle):
     """BASELINE configs[2] as `bench.py --config 2` submits it: the 2 x 16 384 (operator, exponent) pairs of both runs in
     ONE call (rho = 0 for the first half, rho = 1 - c for the second).  More than one wave of the all-shared kernel, so

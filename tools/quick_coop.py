@@ -33,7 +33,7 @@ def timed(fn):
 
 for L in (64, 128):
     length = 200 if L == 64 else 100
-    for npts in (2, 64, 1024, 4096, 16384):
+    for npts in (2, 64, 1024, 4096, 16384, 65536, 262144):
         f_m, f_t = rand_dev(length, L, 2, 5)
         pts_m, pts_t = rand_dev(1, L, 2 * npts, 6)
         pts_t[:, :, 0] = -2
