@@ -68,7 +68,10 @@ int cb200_debug_rr_stats(uint64_t *out);
  * initialisation and carry nothing from one call to the next.
  * Development switches read from the environment at launch time (no effect on results, only on which kernel form
  * runs): CB200_PERSISTENT=0/1 (work-unit recurrence kernel), CB200_HYBRID=0/1 (hybrid scratch columns),
- * CB200_TPB_CHOICE=0/1/2, CB200_RANGE=<coefficients per work unit>. */
+ * CB200_TPB_CHOICE=0/1/2, CB200_RANGE=<coefficients per work unit>, CB200_COOP=0/1 (cooperating lanes: four per
+ * instance; 2 / 4 force that many lanes for the Frobenius recurrence), CB200_FROBPERS=0/1 (persistent 4096-bit
+ * Frobenius kernel), CB200_TMA=0/1 (Horner series staged by cp.async.bulk), CB200_HOST_ROWS=<rows per copy range of
+ * cb200_fuchs_batch_host>. */
 size_t cb200_fuchs_workspace_bytes(int L, int order, int degree, int valuation, int64_t n, int64_t batch,
                                    int shared_ode);
 size_t cb200_frobenius_workspace_bytes(int L, int64_t batch);
