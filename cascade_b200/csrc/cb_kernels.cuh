@@ -805,15 +805,17 @@ int launch_coop_frob(const FrobParams& p, cudaStream_t s) {
     frobenius1_coop_kernel<L, LANES><<<grid, Geo::TPB, Geo::SMEM, s>>>(p);
     return (int)cudaGetLastError();
 }
-// the Fuchs recurrence on four lanes per instance: a shared operator and at most one wave of cooperative CTAs (few
-// solutions continued along a path); measured on B200 (profiles/coop_r02.txt)
+// the Fuchs recurrence with a shared operator on four lanes per instance: at 2048 / 4096 bits at EVERY batch size.
+// Measured on B200 (profiles/coop_fuchs_r02.txt, 60 coefficients): 2048 bits 2.4x at 256 .. 4 096 instances, 1.9x at
+// 16 384, 1.65x at 262 144 (8.0 T against 4.8 T limb-MAC/s); 4096 bits 3.2-3.7x everywhere (6.9 T against 2.0 T) --
+// the one-thread kernels run 3 warps (2048 bits) or ONE warp (4096 bits) per SM, the cooperative kernel eight / four.
 template <int L>
 bool use_coop_fuchs(const FuchsSharedParams& p, int sms) {
+    (void)sms;
     if (!CoopCfg<L>::ON || p.per_inst || !p.sched) return false;
     const char* e = getenv("CB200_COOP");
     if (e && e[0] == '0') return false;
-    if (e && e[0] == '1') return true;
-    return p.batch <= (int64_t)sms * CoopFuchsCfg<L>::G / 4;
+    return true;
 }
 template <int L>
 int launch_coop_fuchs(const FuchsSharedParams& p, int sms, cudaStream_t s) {
