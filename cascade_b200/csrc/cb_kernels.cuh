@@ -218,8 +218,11 @@ __global__ void __launch_bounds__(CoopGeom<L, LANES>::TPB, 1) frobenius1_coop_ke
 }
 // the shared-operator Fuchs recurrence on four lanes per instance (few solutions of one operator: analytic
 // continuation, monodromy), work units of G instances x RANGE coefficients as above
+#ifndef CB_COOPF128_TPB
+#define CB_COOPF128_TPB 128  // (192 measured: 5.3 T against 6.9 T limb-MAC/s at 65 536 instances)
+#endif
 template <int L> struct CoopFuchsCfg {
-    static constexpr int TPB = L <= 64 ? 256 : 128, G = TPB / 4, RANGE = 32, STATE = 24;
+    static constexpr int TPB = L <= 64 ? 256 : CB_COOPF128_TPB, G = TPB / 4, RANGE = 32, STATE = 24;
     static constexpr size_t SMEM = (size_t)(CoopCfg<L>::KS + L + 2) * TPB * sizeof(uint32_t) + (size_t)STATE * G * sizeof(uint32_t);
 };
 template <int L>
