@@ -342,59 +342,67 @@ CB_HD void fuchs_shared_coop_quad(const FuchsSharedParams& p, int64_t inst, cons
         const int64_t bmin = clampi(e - p.degree, 0, bmax);
         const int cnt = (int)(bmax - bmin);
         const int64_t base = (bmax + v - p.tbl_row0) * (W + 2);
-        CB_COOP_EACH(Q, q) {
-            if (q == 0) { st[0] = 0u; st[1] = 2u; stm[0] = meta_zero(); stm[1] = meta_zero(); }
+        if (Q.active) {
+            CB_COOP_EACH(Q, q) {
+                if (q == 0) { st[0] = 0u; st[1] = 2u; stm[0] = meta_zero(); stm[1] = meta_zero(); }
+            }
+            Q.sync();
         }
-        Q.sync();
 #pragma unroll 1
         for (int k = 0; k < cnt; k++) {
-            CRef x = at<L>(p.res, bmin + k, slot), y = at<L>(p.tbl, base + k, 0);
-            Opd a = re_of(x), b = im_of(x);
-            Opd c = dyn(re_of_shared(y)), d = dyn(im_of_shared(y));
-            const int are = (int)st[0], aim = (int)st[1];   // accumulator columns; the spare ones are their partners
-            const int sre = are ^ 1, sim = aim ^ 1;
-            auto sr = Q.acol(sre);
-            auto si = Q.acol(sim);
-            // (the meta records of the two products go to the state words)
-            FdotJob<L> jr{a, c, b, d, true, WRef{sr.generic(), decltype(sr)::GSTRIDE}, stm + 2};
-            FdotJob<L> ji{a, d, b, c, false, WRef{si.generic(), decltype(si)::GSTRIDE}, stm + 3};
-            coop_fdot2_pair<L>(Q, jr, ji, true);
-            CB_COOP_EACH(Q, q) {
-                if (q & 1) continue;
-                const int part = q >> 1;
-                const int ac = part ? aim : are, sc = part ? sim : sre;
-                Meta pr = stm[2 + part], tacc = stm[part];
-                if (k == 0) {  // 0 - x = -x exactly: adopt the column, flip the sign
-                    if (!is_nan(pr) && !is_zero_mid(pr)) pr.flags ^= F_SIGN;
-                    stm[part] = pr;
-                    st[part] = (uint32_t)sc;
-                } else {
-                    auto A = Q.acol(ac);
-                    auto B = Q.acol(sc);
-                    decltype(A) where = A;
-                    Meta t = arb_addsub_cols<L>(A, tacc, B, pr, true, &where);
-                    stm[part] = t;
-                    st[part] = (where.a_or_p() == B.a_or_p()) ? (uint32_t)sc : (uint32_t)ac;
+            Q.phase();
+            if (Q.active) {
+                CRef x = at<L>(p.res, bmin + k, slot), y = at<L>(p.tbl, base + k, 0);
+                Opd a = re_of(x), b = im_of(x);
+                Opd c = dyn(re_of_shared(y)), d = dyn(im_of_shared(y));
+                const int are = (int)st[0], aim = (int)st[1];   // accumulator columns; the spare ones are their partners
+                const int sre = are ^ 1, sim = aim ^ 1;
+                auto sr = Q.acol(sre);
+                auto si = Q.acol(sim);
+                // (the meta records of the two products go to the state words)
+                FdotJob<L> jr{a, c, b, d, true, WRef{sr.generic(), decltype(sr)::GSTRIDE}, stm + 2};
+                FdotJob<L> ji{a, d, b, c, false, WRef{si.generic(), decltype(si)::GSTRIDE}, stm + 3};
+                coop_fdot2_pair<L>(Q, jr, ji, true);
+                CB_COOP_EACH(Q, q) {
+                    if (q & 1) continue;
+                    const int part = q >> 1;
+                    const int ac = part ? aim : are, sc = part ? sim : sre;
+                    Meta pr = stm[2 + part], tacc = stm[part];
+                    if (k == 0) {  // 0 - x = -x exactly: adopt the column, flip the sign
+                        if (!is_nan(pr) && !is_zero_mid(pr)) pr.flags ^= F_SIGN;
+                        stm[part] = pr;
+                        st[part] = (uint32_t)sc;
+                    } else {
+                        auto A = Q.acol(ac);
+                        auto B = Q.acol(sc);
+                        decltype(A) where = A;
+                        Meta t = arb_addsub_cols<L>(A, tacc, B, pr, true, &where);
+                        stm[part] = t;
+                        st[part] = (where.a_or_p() == B.a_or_p()) ? (uint32_t)sc : (uint32_t)ac;
+                    }
                 }
+                Q.sync();
             }
-            Q.sync();
         }
-        CRef out = at<L>(p.res, bmax, slot);
-        const int are = (int)st[0], aim = (int)st[1];
-        Opd xa{colref(are), stm[0]}, xb{colref(aim), stm[1]};
-        if (p.kind[(bmax + v - p.tbl_row0) * p.kind_stride] == 1) {
-            CRef y = at<L>(p.tbl, base + W + 1, 0);
-            Opd c = dyn(re_of_shared(y)), d = dyn(im_of_shared(y));
-            FdotJob<L> jr{xa, c, xb, d, true, wre(out), out.t}, ji{xa, d, xb, c, false, wim(out), out.t + 1};
-            coop_fdot2_pair<L>(Q, jr, ji, true);
-        } else {
-            CRef y = at<L>(p.tbl, base + cnt, 0);
-            CB_COOP_EACH(Q, q) {
-                if (q & 1) continue;
-                const int part = q >> 1;
-                st_meta(out.t + part, arb_div<L>(wpart(out, part), part ? xb : xa, re_of(y), Q.col(q), Q.col(q + 1)));
+        Q.phase();
+        if (Q.active) {
+            CRef out = at<L>(p.res, bmax, slot);
+            const int are = (int)st[0], aim = (int)st[1];
+            Opd xa{colref(are), stm[0]}, xb{colref(aim), stm[1]};
+            if (p.kind[(bmax + v - p.tbl_row0) * p.kind_stride] == 1) {
+                CRef y = at<L>(p.tbl, base + W + 1, 0);
+                Opd c = dyn(re_of_shared(y)), d = dyn(im_of_shared(y));
+                FdotJob<L> jr{xa, c, xb, d, true, wre(out), out.t}, ji{xa, d, xb, c, false, wim(out), out.t + 1};
+                coop_fdot2_pair<L>(Q, jr, ji, true);
+            } else {
+                CRef y = at<L>(p.tbl, base + cnt, 0);
+                CB_COOP_EACH(Q, q) {
+                    if (q & 1) continue;
+                    const int part = q >> 1;
+                    st_meta(out.t + part, arb_div<L>(wpart(out, part), part ? xb : xa, re_of(y), Q.col(q), Q.col(q + 1)));
+                }
+                Q.sync();
             }
-            Q.sync();
         }
     }
 }

@@ -218,6 +218,9 @@ __global__ void __launch_bounds__(CoopGeom<L, LANES>::TPB, 1) frobenius1_coop_ke
 }
 // the shared-operator Fuchs recurrence on four lanes per instance (few solutions of one operator: analytic
 // continuation, monodromy), work units of G instances x RANGE coefficients as above
+#ifndef CB_COOPF_SYNC
+#define CB_COOPF_SYNC 0  // (phase barriers in the cooperative Fuchs kernel: measured 3-5 % slower, its code is small)
+#endif
 #ifndef CB_COOPF128_TPB
 #define CB_COOPF128_TPB 128  // (192 measured: 5.3 T against 6.9 T limb-MAC/s at 65 536 instances)
 #endif
@@ -264,7 +267,9 @@ __global__ void __launch_bounds__(CoopFuchsCfg<L>::TPB, 1) fuchs_shared_coop_ker
             Q.gs = (uint32_t)(nblocks * TPB);
             Q.a20 = sbase + 4u * (uint32_t)(KS * TPB) + 4u * (threadIdx.x & ~3u);
             Q.st = state + (size_t)CoopFuchsCfg<L>::STATE * (threadIdx.x >> 2);
-            if (inst < p.batch) fuchs_shared_coop_quad<L>(p, inst, Q, lo, hi);
+            Q.active = inst < p.batch;  // (lanes without an instance walk the loops for the phase barriers only)
+            Q.cta_sync = CB_COOPF_SYNC != 0;
+            fuchs_shared_coop_quad<L>(p, Q.active ? inst : 0, Q, lo, hi);
             __threadfence();
             __syncthreads();
             if (threadIdx.x == 0) atomicExch(p.sched + 1 + b, (int)(r + 1));
