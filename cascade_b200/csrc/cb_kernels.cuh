@@ -276,14 +276,14 @@ __global__ void __launch_bounds__(CoopFuchsCfg<L>::TPB, 1) fuchs_shared_coop_ker
         }
     }
 }
-// Horner on four lanes per point: one CTA per block of 64 points
-template <int L>
-__global__ void __launch_bounds__(CoopCfg<L>::TPB, 1) horner_coop_kernel(HornerParams p) {
+// Horner on four (two) lanes per point: one CTA per block of 64 (120 / 104) points
+template <int L, int LANES>
+__global__ void __launch_bounds__(CoopGeom<L, LANES>::TPB, 1) horner_coop_kernel(HornerParams p) {
     if constexpr (CoopCfg<L>::ON) {
         extern __shared__ uint32_t cb_smem[];
-        constexpr int G = CoopCfg<L>::G;
-        const int64_t pt = (int64_t)blockIdx.x * G + (threadIdx.x >> 2);
-        typename CoopGeom<L, 4>::Q Q = CoopGeom<L, 4>::quad((uint32_t)__cvta_generic_to_shared(cb_smem), p.gcols, blockIdx.x, gridDim.x);
+        using Geo = CoopGeom<L, LANES>;
+        const int64_t pt = (int64_t)blockIdx.x * Geo::G + Geo::local_instance();
+        typename Geo::Q Q = Geo::quad((uint32_t)__cvta_generic_to_shared(cb_smem), p.gcols, blockIdx.x, gridDim.x);
         Q.active = pt < p.npts;  // (lanes without a point walk the loops for the phase barriers only)
         Q.cta_sync = true;
         horner_coop_quad<L>(p, Q.active ? pt : 0, Q);
@@ -840,16 +840,27 @@ int launch_coop_fuchs(const FuchsSharedParams& p, int sms, cudaStream_t s) {
 }
 template <int L>
 bool use_coop_horner(const HornerParams& p) {
-    return CoopCfg<L>::ON && p.gcols_words >= coop_tail_words(L, p.npts) && coop_wanted<L>(p.npts, sm_count(), false);
+    if (!CoopCfg<L>::ON || p.gcols_words < coop_tail_words(L, p.npts)) return false;
+    const char* e = getenv("CB200_COOP");
+    if (e && e[0] == '2') return true;
+    return coop_wanted<L>(p.npts, sm_count(), false);
 }
+template <int L, int LANES>
+int launch_coop_horner_lanes(const HornerParams& p, cudaStream_t s) {
+    using Geo = CoopGeom<L, LANES>;
+    cudaError_t e = cudaFuncSetAttribute(horner_coop_kernel<L, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    const unsigned grid = (unsigned)((p.npts + Geo::G - 1) / Geo::G);
+    horner_coop_kernel<L, LANES><<<grid, Geo::TPB, Geo::SMEM, s>>>(p);
+    return (int)cudaGetLastError();
+}
+// CB200_COOP=2 forces two lanes per point (development)
 template <int L>
 int launch_coop_horner(const HornerParams& p, cudaStream_t s) {
     if (p.npts <= 0) return 0;
-    cudaError_t e = cudaFuncSetAttribute(horner_coop_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CoopCfg<L>::SMEM);
-    if (e != cudaSuccess) return (int)e;
-    const unsigned grid = (unsigned)((p.npts + CoopCfg<L>::G - 1) / CoopCfg<L>::G);
-    horner_coop_kernel<L><<<grid, CoopCfg<L>::TPB, CoopCfg<L>::SMEM, s>>>(p);
-    return (int)cudaGetLastError();
+    const char* e = getenv("CB200_COOP");
+    if (e && e[0] == '2') return launch_coop_horner_lanes<L, 2>(p, s);
+    return launch_coop_horner_lanes<L, 4>(p, s);
 }
 
 // the TMA-staged Horner kernel: one series for all points (S = 2), long enough for a few tiles, 16-byte aligned

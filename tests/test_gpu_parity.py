@@ -101,6 +101,8 @@ def test_two_lanes_per_instance(monkeypatch, oracle, gpu_driver, L):
     cb_coop.cuh; CTAs of 120 / 104 instances with the [word][role][instance] column layout): ragged last CTAs, one
     instance, several work-unit ranges."""
     monkeypatch.setenv("CB200_COOP", "2")
+    cases.case_horner(oracle, gpu_driver, L, seed=47, length=25, npts=301)  # (Horner on two lanes per point)
+    cases.case_horner_cancellation(oracle, gpu_driver, L, seed=317 + L, length=20, npts=250)
     cases.case_frobenius(oracle, gpu_driver, L, seed=31, n=19 if L == 64 else 12, batch=333)
     cases.case_frobenius(oracle, gpu_driver, L, seed=32, n=9, batch=1)
     cases.case_frobenius(oracle, gpu_driver, L, seed=33, n=17, batch=121)

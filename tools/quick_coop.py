@@ -42,10 +42,10 @@ for L in (64, 128):
         wsb = lib.cb200_horner_workspace_bytes(L, npts)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         res = []
-        for coop in ("0", "1"):
+        for coop in ("0", "1", "2"):
             os.environ["CB200_COOP"] = coop
             res.append(timed(lambda: lib.cb200_horner_batch_dev(L, length, npts, 1, p(f_m), p(f_t), 1, p(pts_m), p(pts_t), p(o_m), p(o_t), p(ws), wsb, None)))
-        print(f"horner L={L} len={length} npts={npts}: one-thread {res[0]:.2f} ms, coop {res[1]:.2f} ms", flush=True)
+        print(f"horner L={L} len={length} npts={npts}: one-thread {res[0]:.2f} ms, four lanes {res[1]:.2f} ms, two lanes {res[2]:.2f} ms", flush=True)
     n = 24
     for batch in (2, 64, 1024, 4096, 16384):
         om, ot = rand_dev(9, L, 2 * batch, 21)
